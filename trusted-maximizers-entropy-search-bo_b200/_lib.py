@@ -1,0 +1,70 @@
+"""ctypes loader for libtes_b200.so -- the C-ABI shared library (include/tes_b200.h).
+
+There is NO CPU fallback: if the library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libtes_b200.so")
+_lib = None
+
+
+class TesError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile every CUDA source for sm_100a into the in-tree libtes_b200.so (nvcc, no GPU needed)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    if not verbose:
+        cmd.append("-s")
+    subprocess.check_call(cmd)
+    if not os.path.exists(SO_PATH):
+        raise TesError("build finished but %s is missing" % SO_PATH)
+    return SO_PATH
+
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_dbl = ctypes.c_double
+c_ptr = ctypes.c_void_p
+c_u64 = ctypes.c_uint64
+
+# name -> (restype, argtypes); every symbol include/tes_b200.h declares
+SIGNATURES = {
+    "tes_abi_version": (c_int, []),
+    "tes_error_string": (ctypes.c_char_p, [c_int]),
+    "tes_rff_topk_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_int]),
+    "tes_rff_topk_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_dbl, c_int,
+                                 c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "tes_rff_eval_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_dbl, c_ptr,
+                                 c_ptr]),
+    "tes_topk_merge_f64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
+    "tes_fp64_fma_burn": (c_int, [c_int, c_i64, c_ptr, ctypes.POINTER(c_dbl), c_ptr]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise TesError(
+                "libtes_b200.so not found at %s -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % SO_PATH)
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.tes_abi_version() != 1:
+            raise TesError("libtes_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().tes_error_string(int(rc)).decode()
+        raise TesError("%s failed: code %d (%s)" % (what, rc, msg))

@@ -1,0 +1,498 @@
+// rff.cu -- Stage A of the TES hot path on sm_100a: evaluate S random-Fourier-feature posterior
+// function samples on N candidates and keep each sample's top-k (value desc, index asc).
+//
+// Replaces utils_for_continuous.py:172-187 (per-sample F x N cos + tf.math.top_k inside a
+// sequential tf.while_loop) and optfunc.py:389-402.  Arithmetic is the fixed fp64 sequence of
+// include/tes_spec.h, so indices are bit-identical to oracle/tes_oracle.c.
+//
+// Kernel shape (per-sample weights, the reference's semantics -- no GEMM exists here because
+// every function sample owns its W_j, b_j; SURVEY section 7 "Per-sample features"):
+//   * work unit = (candidate chunk, group of `sg` samples); grid = #units, the hardware block
+//     scheduler load-balances them over the 148 SMs;
+//   * each thread keeps C candidates' coordinates in registers; the group's feature records
+//     [w*1/pi (d), b*1/pi, theta] stream through a 3-stage shared-memory ring filled by 1-D bulk
+//     async copies (TMA engine, cp.async.bulk + mbarrier); every thread reads the same record
+//     (shared-memory broadcast), so the loop is bound by the fp64 pipe: d + 13 DFMA-class
+//     instructions per (candidate, sample, feature);
+//   * at the end of a sample the CTA filters its C*256 values against the running k-th best
+//     (one __syncthreads_or); only improving tiles take the slow path (append + warp selection).
+#include "tes_common.cuh"
+
+namespace tes {
+
+constexpr int RFF_THREADS = 256;
+constexpr int RFF_NSTAGE = 3;
+constexpr int RFF_FCH = 128;  // features per pipeline stage
+constexpr int RFF_MAX_K = 16;
+constexpr int RFF_MAX_D_FAST = 10;
+
+__host__ __device__ constexpr int rff_rec(int d) { return (d + 3) & ~1; }  // record doubles, even
+
+// ---- prologue: interleave + prescale into feature records ---------------------------------------
+__global__ void rff_pack_kernel(const double* __restrict__ W, const double* __restrict__ b,
+                                const double* __restrict__ theta, int64_t S, int64_t F, int d, int w_shared,
+                                int rec, double* __restrict__ feat) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S * F) return;
+    int64_t j = t / F, f = t % F;
+    int64_t jw = w_shared ? 0 : j;
+    const double* w = W + (jw * F + f) * d;
+    double* o = feat + t * rec;
+    for (int k = 0; k < d; ++k) o[k] = __dmul_rn(w[k], TES_INV_PI);
+    o[d] = __dmul_rn(b[jw * F + f], TES_INV_PI);
+    o[d + 1] = theta[t];
+    for (int k = d + 2; k < rec; ++k) o[k] = 0.0;
+}
+
+// k rounds of "best entry strictly after the previous winner" over a list in shared memory.
+// Executed by one full warp.  Entries with idx < 0 are invalid.  Duplicated (val, idx) pairs are
+// naturally collapsed.  Results written to (out_val, out_idx)[0..k).
+__device__ __forceinline__ void warp_select_topk(const double* lv, const int64_t* li, int n, int k, double* out_val,
+                                                 int64_t* out_idx, int lane) {
+    double pv = pos_inf();
+    int64_t pi = -1;  // previous winner; (inf, -1) precedes everything
+    for (int r = 0; r < k; ++r) {
+        double bv = neg_inf();
+        int64_t bi = INT64_MAX;
+        for (int e = lane; e < n; e += 32) {
+            double v = lv[e];
+            int64_t i = li[e];
+            if (i >= 0 && better(pv, pi, v, i) && better(v, i, bv, bi)) {
+                bv = v;
+                bi = i;
+            }
+        }
+        warp_argmax(bv, bi);
+        bool found = (bi != INT64_MAX);
+        if (lane == 0) {
+            out_val[r] = found ? bv : neg_inf();
+            out_idx[r] = found ? bi : -1;
+        }
+        if (!found) {
+            for (int q = r + 1; q < k; ++q)
+                if (lane == 0) {
+                    out_val[q] = neg_inf();
+                    out_idx[q] = -1;
+                }
+            break;
+        }
+        pv = bv;
+        pi = bi;
+    }
+}
+
+template <int D, int C>
+__global__ void __launch_bounds__(RFF_THREADS)
+    rff_topk_kernel(const double* __restrict__ cand, int64_t N, const double* __restrict__ feat, int S, int F,
+                    double scale, int k, int sg, int64_t chunk, int64_t idx_offset, double* __restrict__ part_val,
+                    int64_t* __restrict__ part_idx) {
+    constexpr int REC = rff_rec(D);
+    constexpr int TILE = RFF_THREADS * C;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage = reinterpret_cast<double*>(smem_raw);                       // [NSTAGE][FCH*REC]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage + RFF_NSTAGE * RFF_FCH * REC);  // [NSTAGE] (+pad to 8)
+    double* tk_val = reinterpret_cast<double*>(full + 8);                      // [sg*k]
+    int64_t* tk_idx = reinterpret_cast<int64_t*>(tk_val + sg * k);             // [sg*k]
+    double* ap_val = reinterpret_cast<double*>(tk_idx + sg * k);               // [TILE + MAX_K]
+    int64_t* ap_idx = reinterpret_cast<int64_t*>(ap_val + TILE + RFF_MAX_K);   // [TILE + MAX_K]
+    int* ap_count = reinterpret_cast<int*>(ap_idx + TILE + RFF_MAX_K);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int nsg = (S + sg - 1) / sg;
+    const int64_t chunk_id = blockIdx.x / nsg;
+    const int g = blockIdx.x % nsg;
+    const int j0 = g * sg;
+    const int nj = min(sg, S - j0);
+    const int64_t c0 = chunk_id * chunk;
+    const int64_t c1 = min(N, c0 + chunk);
+    const int ntiles = (int)((c1 - c0 + TILE - 1) / TILE);
+    const int nch = (F + RFF_FCH - 1) / RFF_FCH;
+    const int per_tile = nj * nch;
+    const int64_t total = (int64_t)ntiles * per_tile;
+
+    for (int e = tid; e < sg * k; e += RFF_THREADS) {
+        tk_val[e] = neg_inf();
+        tk_idx[e] = -1;
+    }
+    if (tid == 0) {
+        *ap_count = 0;
+        for (int s = 0; s < RFF_NSTAGE; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // producer: thread 0 issues the bulk copy of stream element qq into ring slot qq % NSTAGE
+    auto issue = [&](int64_t qq) {
+        int q = (int)(qq % per_tile);
+        int jj = q / nch, c = q % nch;
+        int fcnt = min(RFF_FCH, F - c * RFF_FCH);
+        uint32_t bytes = (uint32_t)(fcnt * REC * sizeof(double));
+        int slot = (int)(qq % RFF_NSTAGE);
+        const double* src = feat + ((int64_t)(j0 + jj) * F + (int64_t)c * RFF_FCH) * REC;
+        mbar_expect_tx(&full[slot], bytes);
+        bulk_g2s(stage + slot * RFF_FCH * REC, src, bytes, &full[slot]);
+    };
+    if (tid == 0) {
+        for (int64_t p = 0; p < RFF_NSTAGE - 1 && p < total; ++p) issue(p);
+    }
+
+    double x[C][D];
+    double acc[C];
+    int64_t ci[C];
+
+    for (int64_t qq = 0; qq < total; ++qq) {
+        const int q = (int)(qq % per_tile);
+        const int jj = q / nch, c = q % nch;
+        if (q == 0) {  // new candidate tile: load coordinates
+            const int64_t t0 = c0 + (qq / per_tile) * TILE;
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) {
+                ci[cc] = t0 + cc * RFF_THREADS + tid;
+                if (ci[cc] < c1) {
+#pragma unroll
+                    for (int kk = 0; kk < D; ++kk) x[cc][kk] = __ldg(cand + ci[cc] * D + kk);
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < D; ++kk) x[cc][kk] = 0.0;
+                }
+            }
+        }
+        if (c == 0) {
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) acc[cc] = 0.0;
+        }
+        if (tid == 0 && qq + RFF_NSTAGE - 1 < total) issue(qq + RFF_NSTAGE - 1);
+        const int slot = (int)(qq % RFF_NSTAGE);
+        mbar_wait(&full[slot], (uint32_t)((qq / RFF_NSTAGE) & 1));
+
+        const int fcnt = min(RFF_FCH, F - c * RFF_FCH);
+        const double* sp = stage + slot * RFF_FCH * REC;
+#pragma unroll 2
+        for (int f = 0; f < fcnt; ++f) {
+            double w[REC];
+            const double2* rp = reinterpret_cast<const double2*>(sp + f * REC);
+#pragma unroll
+            for (int u = 0; u < REC / 2; ++u) {
+                double2 v = rp[u];
+                w[2 * u] = v.x;
+                w[2 * u + 1] = v.y;
+            }
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) {
+                double h = w[D];
+#pragma unroll
+                for (int kk = 0; kk < D; ++kk) h = fma(w[kk], x[cc][kk], h);
+                acc[cc] = fma(w[D + 1], cospi_spec(h), acc[cc]);
+            }
+        }
+
+        if (c == nch - 1) {  // sample jj finished for this tile
+            const double thr = tk_val[jj * k + k - 1];
+            double v[C];
+            bool qual = false;
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) {
+                v[cc] = (ci[cc] < c1) ? __dmul_rn(scale, acc[cc]) : neg_inf();
+                qual |= (v[cc] > thr);
+            }
+            if (__syncthreads_or(qual)) {
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) {
+                    if (v[cc] > thr) {
+                        int pos = k + atomicAdd(ap_count, 1);
+                        ap_val[pos] = v[cc];
+                        ap_idx[pos] = ci[cc] + idx_offset;
+                    }
+                }
+                if (tid < k) {
+                    ap_val[tid] = tk_val[jj * k + tid];
+                    ap_idx[tid] = tk_idx[jj * k + tid];
+                }
+                __syncthreads();
+                if (tid < 32) {
+                    warp_select_topk(ap_val, ap_idx, k + *ap_count, k, tk_val + jj * k, tk_idx + jj * k, lane);
+                    __syncwarp();
+                    if (tid == 0) *ap_count = 0;
+                }
+                __syncthreads();
+            }
+        } else {
+            __syncthreads();  // ring slot may be refilled after this point
+        }
+    }
+
+    for (int e = tid; e < nj * k; e += RFF_THREADS) {
+        int jj = e / k, r = e % k;
+        int64_t o = (chunk_id * S + j0 + jj) * k + r;
+        part_val[o] = tk_val[e];
+        part_idx[o] = tk_idx[e];
+    }
+}
+
+// generic-d fallback (d > RFF_MAX_D_FAST): one thread per (candidate, sample), records read through L1.
+__global__ void rff_value_kernel_generic(const double* __restrict__ cand, int64_t N, int d,
+                                         const double* __restrict__ feat, int S, int F, int rec, double scale,
+                                         double* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y;
+    if (i >= N) return;
+    const double* x = cand + i * d;
+    const double* fj = feat + (int64_t)j * F * rec;
+    double acc = 0.0;
+    for (int f = 0; f < F; ++f) {
+        const double* r = fj + (int64_t)f * rec;
+        double h = __ldg(r + d);
+        for (int kk = 0; kk < d; ++kk) h = fma(__ldg(r + kk), __ldg(x + kk), h);
+        acc = fma(__ldg(r + d + 1), cospi_spec(h), acc);
+    }
+    out[(int64_t)j * N + i] = __dmul_rn(scale, acc);
+}
+
+// top-k of each row of a dense (S, N) value matrix -> one partial list (generic-d fallback path).
+__global__ void rows_topk_kernel(const double* __restrict__ vals, int64_t N, int k, int64_t idx_offset,
+                                 double* __restrict__ out_val, int64_t* __restrict__ out_idx) {
+    const int j = blockIdx.x;
+    const int lane = threadIdx.x;
+    const double* row = vals + (int64_t)j * N;
+    double pv = pos_inf();
+    int64_t pi = -1;
+    for (int r = 0; r < k; ++r) {
+        double bv = neg_inf();
+        int64_t bi = INT64_MAX;
+        for (int64_t e = lane; e < N; e += 32) {
+            double v = row[e];
+            if (better(pv, pi, v, e) && better(v, e, bv, bi)) {
+                bv = v;
+                bi = e;
+            }
+        }
+        warp_argmax(bv, bi);
+        bool found = (bi != INT64_MAX);
+        if (lane == 0) {
+            out_val[(int64_t)j * k + r] = found ? bv : neg_inf();
+            out_idx[(int64_t)j * k + r] = found ? bi + idx_offset : -1;
+        }
+        if (!found) {
+            for (int q = r + 1; q < k; ++q)
+                if (lane == 0) {
+                    out_val[(int64_t)j * k + q] = neg_inf();
+                    out_idx[(int64_t)j * k + q] = -1;
+                }
+            break;
+        }
+        pv = bv;
+        pi = bi;
+    }
+}
+
+// merge P partial lists per sample: vals/idx (P, S, k) -> (S, k).  One warp per sample.
+__global__ void topk_merge_kernel(const double* __restrict__ vals, const int64_t* __restrict__ idx, int64_t P,
+                                  int64_t S, int k, double* __restrict__ out_val, int64_t* __restrict__ out_idx) {
+    const int64_t j = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int64_t n = P * k;
+    double pv = pos_inf();
+    int64_t pi = -1;
+    for (int r = 0; r < k; ++r) {
+        double bv = neg_inf();
+        int64_t bi = INT64_MAX;
+        for (int64_t e = lane; e < n; e += 32) {
+            int64_t p = e / k, q = e % k;
+            double v = vals[(p * S + j) * k + q];
+            int64_t i = idx[(p * S + j) * k + q];
+            if (i >= 0 && better(pv, pi, v, i) && better(v, i, bv, bi)) {
+                bv = v;
+                bi = i;
+            }
+        }
+        warp_argmax(bv, bi);
+        bool found = (bi != INT64_MAX);
+        if (lane == 0) {
+            out_val[j * k + r] = found ? bv : neg_inf();
+            out_idx[j * k + r] = found ? bi : -1;
+        }
+        if (!found) {
+            for (int q = r + 1; q < k; ++q)
+                if (lane == 0) {
+                    out_val[j * k + q] = neg_inf();
+                    out_idx[j * k + q] = -1;
+                }
+            break;
+        }
+        pv = bv;
+        pi = bi;
+    }
+}
+
+struct RffPlan {
+    int C, tile, sg, rec;
+    int64_t chunk, nchunks, nunits;
+    int64_t feat_bytes, part_val_bytes, part_idx_bytes, dense_bytes;
+    size_t smem;
+};
+
+static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k) {
+    RffPlan p;
+    p.C = 2;
+    p.tile = RFF_THREADS * p.C;
+    p.rec = rff_rec((int)d);
+    int64_t ntiles = (N + p.tile - 1) / p.tile;
+    if (ntiles < 1) ntiles = 1;
+    int64_t tpc = ntiles < 16 ? ntiles : 16;  // tiles per chunk
+    int64_t sg = S < 32 ? S : 32;
+    auto units = [&]() { return ((ntiles + tpc - 1) / tpc) * ((S + sg - 1) / sg); };
+    const int64_t want = 8 * 148;
+    while (units() < want && tpc > 4) tpc = (tpc + 1) / 2;
+    while (units() < want && sg > 1) sg = (sg + 1) / 2;
+    while (units() < want && tpc > 1) tpc = (tpc + 1) / 2;
+    p.sg = (int)sg;
+    p.chunk = tpc * p.tile;
+    p.nchunks = (ntiles + tpc - 1) / tpc;
+    p.nunits = p.nchunks * ((S + sg - 1) / sg);
+    p.feat_bytes = align_up(S * F * p.rec * (int64_t)sizeof(double), 256);
+    p.part_val_bytes = align_up(p.nchunks * S * k * (int64_t)sizeof(double), 256);
+    p.part_idx_bytes = align_up(p.nchunks * S * k * (int64_t)sizeof(int64_t), 256);
+    p.dense_bytes = d > RFF_MAX_D_FAST ? align_up(S * N * (int64_t)sizeof(double), 256) : 0;
+    p.smem = (size_t)RFF_NSTAGE * RFF_FCH * p.rec * sizeof(double) + 8 * sizeof(uint64_t) +
+             (size_t)p.sg * k * 16 + (size_t)(p.tile + RFF_MAX_K) * 16 + 16;
+    return p;
+}
+
+template <int D>
+static int launch_rff_topk(const RffPlan& p, const double* cand, int64_t N, const double* feat, int64_t S, int64_t F,
+                           double scale, int k, int64_t idx_offset, double* part_val, int64_t* part_idx,
+                           cudaStream_t st) {
+    auto kern = rff_topk_kernel<D, 2>;
+    if (p.smem > 48 * 1024)
+        TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    kern<<<(unsigned)p.nunits, RFF_THREADS, p.smem, st>>>(cand, N, feat, (int)S, (int)F, scale, k, p.sg, p.chunk,
+                                                          idx_offset, part_val, part_idx);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace tes
+
+using namespace tes;
+
+extern "C" int64_t tes_rff_topk_workspace_bytes(int64_t N, int64_t d, int64_t S, int64_t F, int k) {
+    if (N < 0 || d < 1 || d > 64 || S < 1 || F < 1 || k < 1 || k > RFF_MAX_K) return -1;
+    RffPlan p = rff_plan(N, d, S, F, k);
+    return p.feat_bytes + p.part_val_bytes + p.part_idx_bytes + p.dense_bytes;
+}
+
+extern "C" int tes_rff_topk_f64(const double* cand, int64_t N, int64_t d, const double* W, const double* b,
+                                const double* theta, int64_t S, int64_t F, int w_shared, double sigma, int k,
+                                int64_t idx_offset, int64_t* out_idx, double* out_val, void* ws, int64_t ws_bytes,
+                                void* stream) {
+    if (N < 0 || (N > 0 && !cand)) return -1;
+    if (d < 1 || d > 64) return -3;
+    if (!W) return -4;
+    if (!b) return -5;
+    if (!theta) return -6;
+    if (S < 1 || S > (1 << 24)) return -7;
+    if (F < 1 || F > (1 << 24)) return -8;
+    if (!(sigma >= 0.0)) return -10;
+    if (k < 1 || k > RFF_MAX_K) return -11;
+    if (!out_idx) return -13;
+    if (!out_val) return -14;
+    RffPlan p = rff_plan(N, d, S, F, k);
+    int64_t need = p.feat_bytes + p.part_val_bytes + p.part_idx_bytes + p.dense_bytes;
+    if (!ws || ws_bytes < need) return -100;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)ws;
+    double* feat = (double*)base;
+    double* part_val = (double*)(base + p.feat_bytes);
+    int64_t* part_idx = (int64_t*)(base + p.feat_bytes + p.part_val_bytes);
+    double* dense = (double*)(base + p.feat_bytes + p.part_val_bytes + p.part_idx_bytes);
+    const double scale = sqrt(2.0 * sigma / (double)F);
+
+    int64_t nsf = S * F;
+    rff_pack_kernel<<<(unsigned)((nsf + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, (int)d, w_shared, p.rec, feat);
+    TES_LAUNCH_OK();
+    int64_t P = p.nchunks;
+    if (N == 0) {
+        P = 0;
+    } else if (d <= RFF_MAX_D_FAST) {
+        int rc = 0;
+        switch (d) {
+#define TES_CASE(DD)                                                                                        \
+    case DD:                                                                                                \
+        rc = launch_rff_topk<DD>(p, cand, N, feat, S, F, scale, k, idx_offset, part_val, part_idx, st);     \
+        break;
+            TES_CASE(1) TES_CASE(2) TES_CASE(3) TES_CASE(4) TES_CASE(5) TES_CASE(6) TES_CASE(7) TES_CASE(8)
+            TES_CASE(9) TES_CASE(10)
+#undef TES_CASE
+        }
+        if (rc) return rc;
+    } else {
+        dim3 grid((unsigned)((N + 127) / 128), (unsigned)S);
+        rff_value_kernel_generic<<<grid, 128, 0, st>>>(cand, N, (int)d, feat, (int)S, (int)F, p.rec, scale, dense);
+        TES_LAUNCH_OK();
+        rows_topk_kernel<<<(unsigned)S, 32, 0, st>>>(dense, N, k, idx_offset, part_val, part_idx);
+        TES_LAUNCH_OK();
+        P = 1;
+    }
+    topk_merge_kernel<<<(unsigned)S, 32, 0, st>>>(part_val, part_idx, P, S, k, out_val, out_idx);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tes_topk_merge_f64(const double* vals, const int64_t* idx, int64_t P, int64_t S, int k,
+                                  double* out_val, int64_t* out_idx, void* stream) {
+    if (!vals) return -1;
+    if (!idx) return -2;
+    if (P < 0) return -3;
+    if (S < 1) return -4;
+    if (k < 1 || k > 64) return -5;
+    if (!out_val) return -6;
+    if (!out_idx) return -7;
+    topk_merge_kernel<<<(unsigned)S, 32, 0, (cudaStream_t)stream>>>(vals, idx, P, S, k, out_val, out_idx);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
+namespace tes {
+// dense values with on-the-fly prescale (no workspace): used by tes_rff_eval_f64
+__global__ void rff_eval_kernel(const double* __restrict__ cand, int64_t N, int d, const double* __restrict__ W,
+                                const double* __restrict__ b, const double* __restrict__ theta, int S, int F,
+                                int w_shared, double scale, double* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y;
+    if (i >= N) return;
+    const double* x = cand + i * d;
+    const int64_t jw = w_shared ? 0 : j;
+    const double* wj = W + jw * F * d;
+    const double* bj = b + jw * F;
+    const double* tj = theta + (int64_t)j * F;
+    double acc = 0.0;
+    for (int f = 0; f < F; ++f) {
+        double h = __dmul_rn(__ldg(bj + f), TES_INV_PI);
+        for (int kk = 0; kk < d; ++kk) h = fma(__dmul_rn(__ldg(wj + (int64_t)f * d + kk), TES_INV_PI), __ldg(x + kk), h);
+        acc = fma(__ldg(tj + f), cospi_spec(h), acc);
+    }
+    out[(int64_t)j * N + i] = __dmul_rn(scale, acc);
+}
+}  // namespace tes
+
+extern "C" int tes_rff_eval_f64(const double* cand, int64_t N, int64_t d, const double* W, const double* b,
+                                const double* theta, int64_t S, int64_t F, int w_shared, double sigma, double* out,
+                                void* stream) {
+    if (N < 0 || (N > 0 && !cand)) return -1;
+    if (d < 1 || d > 64) return -3;
+    if (!W) return -4;
+    if (!b) return -5;
+    if (!theta) return -6;
+    if (S < 1 || S > 65535) return -7;
+    if (F < 1) return -8;
+    if (!(sigma >= 0.0)) return -10;
+    if (!out) return -11;
+    if (N == 0) return 0;
+    const double scale = sqrt(2.0 * sigma / (double)F);
+    dim3 grid((unsigned)((N + 127) / 128), (unsigned)S);
+    rff_eval_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(cand, N, (int)d, W, b, theta, (int)S, (int)F, w_shared,
+                                                            scale, out);
+    TES_LAUNCH_OK();
+    return 0;
+}

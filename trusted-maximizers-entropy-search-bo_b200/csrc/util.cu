@@ -1,0 +1,36 @@
+// util.cu -- ABI version, error strings and the fp64-FMA burn used as the roofline denominator.
+#include "tes_common.cuh"
+
+extern "C" int tes_abi_version(void) { return TES_B200_ABI_VERSION; }
+
+extern "C" const char* tes_error_string(int code) {
+    if (code == 0) return "ok";
+    if (code == -100) return "workspace missing or too small";
+    if (code < 0) return "invalid argument (position = -code)";
+    return cudaGetErrorString((cudaError_t)code);
+}
+
+namespace tes {
+// 8 independent DFMA chains per thread, 256 threads per CTA: enough ILP x TLP to saturate the
+// 64-lane/SM fp64 pipe.  flops = blocks*256*iters*8*2.
+__global__ void __launch_bounds__(256) fp64_fma_burn_kernel(int64_t iters, double* sink) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double m = 0.999999999, c = 1e-9;
+    for (int64_t i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    sink[(int64_t)blockIdx.x * 256 + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+}  // namespace tes
+
+extern "C" int tes_fp64_fma_burn(int blocks, int64_t iters, double* sink, double* flops, void* stream) {
+    if (blocks < 1) return -1;
+    if (iters < 1) return -2;
+    if (!sink) return -3;
+    tes::fp64_fma_burn_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    TES_LAUNCH_OK();
+    if (flops) *flops = (double)blocks * 256.0 * (double)iters * 16.0;
+    return 0;
+}
