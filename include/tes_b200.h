@@ -71,6 +71,91 @@ int tes_rff_eval_f64(const double* cand, int64_t N, int64_t d, const double* W, 
 int tes_topk_merge_f64(const double* vals, const int64_t* idx, int64_t P, int64_t S, int k, double* out_val,
                        int64_t* out_idx, void* stream);
 
+/* ===================================================================================== Stage B
+ * SE-ARD cross kernel k(x_i, xb_c), out (N, m).  Replaces utils.computeKnm (utils.py:703-719),
+ * using the reference's |a|^2 + |b|^2 - 2ab expansion. */
+int tes_se_ard_cross_f64(const double* x, int64_t N, const double* xb, int64_t m, int64_t d, const double* l,
+                         double sigma, double* out, void* stream);
+
+/* Plain fp64 GEMM C[MxN] = A[MxK] * op(B); op(B) = B (ldb = row stride) or B^T when transb != 0
+ * (B stored N x K, ldb = its row stride).  The contraction primitive of stages B/D. */
+int tes_gemm_f64(const double* A, int64_t lda, const double* B, int64_t ldb, int transb, double* C, int64_t ldc,
+                 int64_t M, int64_t N, int64_t K, void* stream);
+
+/* pNK = K([test_xs; X]) + sigma0 * diag(0_T, I_n), (T+n)^2.  Replaces the matrix assembly of
+ * get_pNK_test_obs (criteria/evaluate_mp.py:12-53 and its four copies); invert it with
+ * tes_batched_chol2inv_f64 (the reference uses tf.linalg.inv; the matrix is SPD). */
+int64_t tes_pnk_workspace_bytes(int64_t T, int64_t n, int64_t d);
+int tes_pnk_f64(const double* test_xs, int64_t T, const double* X, int64_t n, int64_t d, const double* l,
+                double sigma, double sigma0, double* out_pNK, void* ws, int64_t ws_bytes, void* stream);
+
+/* Common head of every TES criterion: with k = K(x, [test_xs; X]) (N, T+n),
+ *   out_M (N,T) = k invpNK[:, :T];  out_b (N) = k invpNK[:, T:] Y;  out_Kq (N) = sigma - rowsum((k invpNK) o k)
+ * Replaces evaluate_mp.get_queried_f_stat_given_data_maxidx:76-90 and
+ * evaluate_sample_mp.get_queried_f_stat_given_test_samples:77-124 (tmp_test, query_mean_obs, query_var). */
+int64_t tes_posterior_stats_workspace_bytes(int64_t N, int64_t T, int64_t n, int64_t d);
+int tes_posterior_stats_f64(const double* x, int64_t N, int64_t d, const double* test_xs, int64_t T, const double* X,
+                            int64_t n, const double* Y, const double* l, double sigma, const double* invpNK,
+                            double* out_M, double* out_b, double* out_Kq, void* ws, int64_t ws_bytes, void* stream);
+
+/* GP posterior mean (N) and marginal variance (N, clipped at 1e-100) given NKinv = (K_XX + sigma0 I)^-1.
+ * Replaces utils.compute_mean_var_f with fullcov=False (utils.py:786-815). */
+int64_t tes_gp_mean_var_workspace_bytes(int64_t N, int64_t n);
+int tes_gp_mean_var_f64(const double* x, int64_t N, int64_t d, const double* X, int64_t n, const double* Y,
+                        const double* l, double sigma, const double* NKinv, double* out_mean, double* out_var,
+                        void* ws, int64_t ws_bytes, void* stream);
+
+/* Batched SPD factorisation and inversion (all matrices m x m, contiguous (batch, m, m)).
+ * tes_batched_chol2inv_f64 replaces utils.chol2inv (utils.py:657-674), utils.multichol2inv
+ * (:677-700), utils.precomputeInvKs (:1838-1856), the per-maximizer (n+1)^2 batch of
+ * utils.eval_invKmaxsams (:1859-1883) and the tf.linalg.inv of get_pNK_test_obs
+ * (criteria/evaluate_mp.py:47; that matrix is SPD).  A^-1 = L^-T L^-1, L = chol(A), no jitter.
+ * info[b] = 0, or the 1-based index of the first non-positive pivot (the output then holds NaN).
+ * A is not modified.  `want_inverse` selects the workspace size for chol2inv (1) or potrf (0). */
+int64_t tes_batched_chol_workspace_bytes(int64_t batch, int64_t m, int want_inverse);
+int tes_batched_potrf_f64(const double* A, int64_t batch, int64_t m, double* L, int* info, void* ws,
+                          int64_t ws_bytes, void* stream);
+int tes_batched_chol2inv_f64(const double* A, int64_t batch, int64_t m, double* Ainv, int* info, void* ws,
+                             int64_t ws_bytes, void* stream);
+
+/* ===================================================================================== Stage D
+ * TES_ep acquisition for one hyper-parameter sample (the reference loops over nhyp and averages).
+ * Replaces criteria/evaluate_mp.py:116-295 (mode 0 deterministic, mode 1 stochastic) and
+ * criteria/evaluate_mp_lite.py:116-225 (mode 2); mode 3 only returns the query moments
+ * (get_queried_f_stat_given_data_maxidx, evaluate_mp.py:56-113).
+ *   p (Sp), post_mean (Sp,T), post_cov (Sp,T,T): the maximizers with max_probs > 0 only
+ *   invKobs (n,n): needed by mode 0 (H[y] of the observation-only posterior)
+ *   mode 1 draws: z != NULL -> host-supplied standard normals, layout (niter, nysample, Sp, N);
+ *                 z == NULL -> Philox (include/tes_spec.h) keyed by (seed, iteration) and the
+ *                 logical element (iy*Sp + j)*n_global + (x_offset + x), so results do not depend
+ *                 on how candidates are sharded;
+ *   out_acq (N); out_mean / out_var (N,Sp), optional (NULL to skip): candidate-major moments.
+ * NaN semantics follow the reference (no variance clipping before sqrt). */
+int64_t tes_ep_acq_workspace_bytes(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp);
+int tes_ep_acq_f64(int mode, const double* x, int64_t N, int64_t d, const double* test_xs, int64_t T,
+                   const double* X, int64_t n, const double* Y, const double* l, double sigma, double sigma0,
+                   const double* invpNK, const double* invKobs, const double* p, int64_t Sp,
+                   const double* post_mean, const double* post_cov, int niter, int nysample, const double* z,
+                   uint64_t seed, int64_t n_global, int64_t x_offset, double* out_acq, double* out_mean,
+                   double* out_var, void* ws, int64_t ws_bytes, void* stream);
+
+/* TES_sp acquisition, q = 1 (criteria/evaluate_sample_mp.py:132-336) or batch q <= 8
+ * (criteria/evaluate_batch_sample_mp.py:160-382).  x (nx, q, d); post_samples (Sp,T,K);
+ * post_mask (Sp,K) bytes (1 = valid); z layout (niter, nysample, Sp, nx, K, q) or NULL for Philox
+ * (element ((iy*Sp + j)*n_global + x_offset + x)*K + s)*q + c).  out_acq (nx). */
+int64_t tes_sp_acq_workspace_bytes(int64_t nx, int q, int64_t T, int64_t n, int64_t d, int64_t Sp, int64_t K);
+int tes_sp_acq_f64(const double* x, int64_t nx, int q, int64_t d, const double* test_xs, int64_t T, const double* X,
+                   int64_t n, const double* Y, const double* l, double sigma, double sigma0, const double* invpNK,
+                   const double* p, int64_t Sp, const double* post_samples, const unsigned char* post_mask,
+                   int64_t K, int niter, int nysample, const double* z, uint64_t seed, int64_t n_global,
+                   int64_t x_offset, double* out_acq, void* ws, int64_t ws_bytes, void* stream);
+
+/* Batch TES_ep (criteria/evaluate_batch_mp.py:145-331).  As shipped, the reference scores the
+ * samples under the STANDARD normal and builds the marginal from that same log-prob (:302,
+ * :317-322), so its value is -(sum p) log(sum p) ~ 0 for every input; this entry
+ * point returns exactly that closed form. */
+int tes_batch_ep_acq_f64(const double* p, int64_t Sp, int64_t nx, double* out_acq, void* stream);
+
 /* ============================================================================== measurement aids
  * Sustained fp64 FMA rate of the device, used as the roofline denominator for the fp64-pipe-bound
  * kernels (MEASURED_PEAKS.json carries only HBM and bf16 numbers).  Runs `iters` dependent-chain

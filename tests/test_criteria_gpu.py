@@ -1,0 +1,153 @@
+"""Stage D parity: the TES criteria (CUDA, through the C ABI) vs the numpy oracle on identical
+host-supplied draws.  Bar (north_star): acquisition values within 1e-6 relative in fp64; we add an
+absolute floor of 1e-9 for values near zero and, for the batch TES_ep criterion (which is ~0 by
+construction), an absolute bound of 1e-12.  Selections (arg-max) must be identical."""
+import numpy as np
+import pytest
+
+from oracle import tes_oracle_np as onp
+from tests._problems import BRANIN, HART6, PH, make_problem
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-6, 1e-9
+
+
+def _close(a, b):
+    a = np.asarray(a)
+    np.testing.assert_allclose(a, b, rtol=RTOL, atol=ATOL)
+    assert int(np.argmax(a)) == int(np.argmax(b))
+
+
+def _ep_inputs(pr):
+    p = pr["max_probs"][0]
+    keep = p > 0
+    return p[keep], pr["v0"][0][keep], pr["v1"][0][keep]
+
+
+@pytest.mark.parametrize("hyp,d,n,T,nx", [(BRANIN, 2, 5, 6, 50), (PH, 2, 20, 5, 400), (HART6, 6, 30, 20, 200),
+                                          (BRANIN, 2, 3, 40, 130)])
+def test_tes_ep_deterministic_and_lite_and_moments(hyp, d, n, T, nx):
+    from tes_b200 import ops
+    pr = make_problem(seed=T, d=d, n=n, T=T, nx=nx, hyp=hyp, mode="empirical", nsample=600)
+    p, pm, pc = _ep_inputs(pr)
+    args = (pr["x"], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invpNK"][0],
+            pr["invK"][0], p, pm, pc)
+    acq, mean, var = ops.ep_acq(ops.EP_DETERMINISTIC, *args, want_moments=True)
+    qm, qv = onp.get_queried_f_stat_given_data_maxidx(pr["x"], pr["l"], pr["sigma"], pr["X"], pr["Y"],
+                                                      pr["test_xs"], pr["invpNK"][0], pm, pc)
+    np.testing.assert_allclose(mean.cpu().numpy().T, qm, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(var.cpu().numpy().T, qv, rtol=1e-7, atol=1e-10)
+    ref = onp.evaluate_mp(pr["x"], pr["ls"], pr["sigmas"], pr["sigma0s"], pr["X"], pr["Y"], d, nx, n, 1, 10,
+                          pr["test_xs"], pr["max_probs"], pr["v0"], pr["v1"], pr["invK"], pr["invpNK"],
+                          stochastic=False)
+    _close(acq.cpu().numpy(), ref)
+    lite = ops.ep_acq(ops.EP_LITE, *args)
+    ref_l = onp.evaluate_mp_lite(pr["x"], pr["ls"], pr["sigmas"], pr["sigma0s"], pr["X"], pr["Y"], d, nx, n, 1,
+                                 pr["test_xs"], pr["max_probs"], pr["v0"], pr["v1"], pr["invpNK"])
+    _close(lite.cpu().numpy(), ref_l)
+
+
+@pytest.mark.parametrize("hyp,d,n,T,nx,I,Yn", [(BRANIN, 2, 5, 6, 40, 3, 7), (PH, 2, 20, 5, 100, 5, 10),
+                                               (HART6, 6, 30, 12, 60, 2, 4)])
+def test_tes_ep_stochastic_host_draws(hyp, d, n, T, nx, I, Yn):
+    from tes_b200 import ops
+    pr = make_problem(seed=T + 1, d=d, n=n, T=T, nx=nx, hyp=hyp, mode="empirical", nsample=500)
+    p, pm, pc = _ep_inputs(pr)
+    Sp = p.shape[0]
+    z = pr["rs"].normal(size=(1, I, Yn, Sp, nx))
+    acq = ops.ep_acq(ops.EP_STOCHASTIC, pr["x"], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"],
+                     pr["sigma0"], pr["invpNK"][0], pr["invK"][0], p, pm, pc, niter=I, nysample=Yn, z=z[0])
+    ref = onp.evaluate_mp(pr["x"], pr["ls"], pr["sigmas"], pr["sigma0s"], pr["X"], pr["Y"], d, nx, n, 1, Yn,
+                          pr["test_xs"], pr["max_probs"], pr["v0"], pr["v1"], pr["invK"], pr["invpNK"],
+                          stochastic=True, niteration=I, z=z)
+    _close(acq.cpu().numpy(), ref)
+
+
+def test_tes_ep_stochastic_philox_matches_oracle_generator():
+    """Counter-based draws: the kernel's in-register normals equal the oracle generator's (to libm
+    rounding), so feeding the oracle-generated tensor as host z reproduces the Philox run."""
+    from oracle import c_oracle as co
+    from tes_b200 import ops
+    from tes_b200.spec import STREAM_EP_Y
+    pr = make_problem(seed=3, d=2, n=5, T=6, nx=33, hyp=BRANIN, mode="empirical", nsample=500)
+    p, pm, pc = _ep_inputs(pr)
+    Sp, nx, I, Yn, seed = p.shape[0], 33, 3, 5, 1234567
+    args = (pr["x"], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invpNK"][0],
+            pr["invK"][0], p, pm, pc)
+    a = ops.ep_acq(ops.EP_STOCHASTIC, *args, niter=I, nysample=Yn, seed=seed).cpu().numpy()
+    z = np.stack([co.normals(seed, it, STREAM_EP_Y, 0, Yn * Sp * nx).reshape(Yn, Sp, nx) for it in range(I)])
+    b = ops.ep_acq(ops.EP_STOCHASTIC, *args, niter=I, nysample=Yn, z=z).cpu().numpy()
+    np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
+    # sharding invariance: two shards with x_offset / n_global give the same numbers
+    a1 = ops.ep_acq(ops.EP_STOCHASTIC, pr["x"][:10], *args[1:], niter=I, nysample=Yn, seed=seed, n_global=nx,
+                    x_offset=0).cpu().numpy()
+    a2 = ops.ep_acq(ops.EP_STOCHASTIC, pr["x"][10:], *args[1:], niter=I, nysample=Yn, seed=seed, n_global=nx,
+                    x_offset=10).cpu().numpy()
+    np.testing.assert_array_equal(np.concatenate([a1, a2]), a)
+
+
+@pytest.mark.parametrize("hyp,d,n,T,nx,I,Yn,ns", [(BRANIN, 2, 5, 6, 9, 2, 5, 200), (PH, 2, 12, 5, 6, 3, 4, 120),
+                                                  (HART6, 6, 20, 10, 5, 1, 3, 300)])
+def test_tes_sp_host_draws(hyp, d, n, T, nx, I, Yn, ns):
+    from tes_b200 import ops
+    pr = make_problem(seed=T + 2, d=d, n=n, T=T, nx=nx, hyp=hyp, mode="sample", nsample=ns)
+    p = pr["max_probs"][0]
+    keep = p > 0
+    P, msk = pr["v0"][0][keep], pr["v1"][0][keep]
+    Sp, K = P.shape[0], P.shape[2]
+    z = pr["rs"].normal(size=(1, I, Yn, Sp, nx, K))
+    acq = ops.sp_acq(pr["x"], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"],
+                     pr["invpNK"][0], p[keep], P, msk, niter=I, nysample=Yn, z=z[0])
+    ref = onp.evaluate_sample_mp(pr["x"], pr["ls"], pr["sigmas"], pr["sigma0s"], pr["X"], pr["Y"], d, nx, n, 1, Yn,
+                                 pr["test_xs"], pr["max_probs"], pr["v0"], pr["v1"], pr["invpNK"], niteration=I,
+                                 z=z)
+    _close(acq.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("q", [1, 2, 3, 8])
+def test_tes_sp_batch_host_draws(q):
+    from tes_b200 import ops
+    d, n, T, nx, I, Yn = 2, 5, 6, 5, 2, 3
+    pr = make_problem(seed=40 + q, d=d, n=n, T=T, nx=nx, hyp=BRANIN, mode="sample", nsample=150)
+    p = pr["max_probs"][0]
+    keep = p > 0
+    P, msk = pr["v0"][0][keep], pr["v1"][0][keep]
+    Sp, K = P.shape[0], P.shape[2]
+    xb = pr["rs"].rand(nx, q, d)
+    z = pr["rs"].normal(size=(1, I, Yn, Sp, nx, K, q))
+    acq = ops.sp_acq(xb, pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invpNK"][0],
+                     p[keep], P, msk, niter=I, nysample=Yn, z=z[0])
+    ref = onp.evaluate_batch_sample_mp(xb, pr["ls"], pr["sigmas"], pr["sigma0s"], pr["X"], pr["Y"], d, n, 1, Yn,
+                                       pr["test_xs"], pr["max_probs"], pr["v0"], pr["v1"], pr["invpNK"],
+                                       niteration=I, z=z)
+    _close(acq.cpu().numpy(), ref)
+
+
+def test_batch_tes_ep_is_zero_like_the_reference():
+    from tes_b200 import ops
+    d, n, T, nx, q, I, Yn = 2, 5, 6, 4, 3, 2, 3
+    pr = make_problem(seed=77, d=d, n=n, T=T, nx=nx, hyp=BRANIN, mode="empirical", nsample=300)
+    p, pm, pc = _ep_inputs(pr)
+    xb = pr["rs"].rand(nx, q, d)
+    z = pr["rs"].normal(size=(1, I, Yn, p.shape[0], nx, q))
+    ref = onp.evaluate_batch_mp(xb, pr["ls"], pr["sigmas"], pr["sigma0s"], pr["X"], pr["Y"], d, n, 1, Yn,
+                                pr["test_xs"], pr["max_probs"], pr["v0"], pr["v1"], pr["invK"], pr["invpNK"],
+                                niteration=I, z=z)
+    acq = ops.batch_ep_acq(p, nx).cpu().numpy()
+    assert np.max(np.abs(ref)) < 1e-12 and np.max(np.abs(acq - ref)) < 1e-12  # absolute bound
+
+
+def test_negative_variance_propagates_nan():
+    """no clipping before sqrt(var + sigma0) -- NaN reaches the output (driver retries)."""
+    from tes_b200 import ops
+    pr = make_problem(seed=5, d=2, n=5, T=6, nx=8, hyp=BRANIN, mode="empirical", nsample=300)
+    p, pm, pc = _ep_inputs(pr)
+    pc = pc.copy()
+    pc[0] = -np.eye(pc.shape[1]) * 1e3  # forces var_0 + sigma0 < 0 somewhere
+    acq = ops.ep_acq(ops.EP_DETERMINISTIC, pr["x"], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"],
+                     pr["sigma0"], pr["invpNK"][0], pr["invK"][0], p, pm, pc).cpu().numpy()
+    pv1 = pr["v1"].copy()
+    pv1[0][np.where(pr["max_probs"][0] > 0)[0][0]] = pc[0]
+    ref = onp.evaluate_mp(pr["x"], pr["ls"], pr["sigmas"], pr["sigma0s"], pr["X"], pr["Y"], 2, 8, 5, 1, 10,
+                          pr["test_xs"], pr["max_probs"], pr["v0"], pv1, pr["invK"], pr["invpNK"])
+    assert np.array_equal(np.isnan(acq), np.isnan(ref)) and np.isnan(ref).any()

@@ -42,6 +42,28 @@ SIGNATURES = {
     "tes_rff_eval_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_dbl, c_ptr,
                                  c_ptr]),
     "tes_topk_merge_f64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
+    "tes_se_ard_cross_f64": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_dbl, c_ptr, c_ptr]),
+    "tes_gemm_f64": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr]),
+    "tes_pnk_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
+    "tes_pnk_f64": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr, c_i64, c_ptr]),
+    "tes_posterior_stats_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
+    "tes_posterior_stats_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_dbl,
+                                        c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "tes_gp_mean_var_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "tes_gp_mean_var_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr,
+                                    c_ptr, c_i64, c_ptr]),
+    "tes_batched_chol_workspace_bytes": (c_i64, [c_i64, c_i64, c_int]),
+    "tes_batched_potrf_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "tes_batched_chol2inv_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "tes_ep_acq_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_i64]),
+    "tes_ep_acq_f64": (c_int, [c_int, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_dbl, c_dbl,
+                               c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_int, c_int, c_ptr, c_u64, c_i64, c_i64,
+                               c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "tes_sp_acq_workspace_bytes": (c_i64, [c_i64, c_int, c_i64, c_i64, c_i64, c_i64, c_i64]),
+    "tes_sp_acq_f64": (c_int, [c_ptr, c_i64, c_int, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_dbl, c_dbl,
+                               c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_u64, c_i64, c_i64,
+                               c_ptr, c_ptr, c_i64, c_ptr]),
+    "tes_batch_ep_acq_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "tes_fp64_fma_burn": (c_int, [c_int, c_i64, c_ptr, ctypes.POINTER(c_dbl), c_ptr]),
 }
 

@@ -1,0 +1,757 @@
+// criteria.cu -- Stage D of the TES hot path: the Monte-Carlo entropy criteria.
+//
+//   tes_ep_acq_f64        TES_ep, q=1   criteria/evaluate_mp.py:56-295 (deterministic + stochastic),
+//                                       criteria/evaluate_mp_lite.py:116-225 (closed-form "lite")
+//   tes_sp_acq_f64        TES_sp, q>=1  criteria/evaluate_sample_mp.py:54-336 (q=1) and
+//                                       criteria/evaluate_batch_sample_mp.py:54-382 (batch q)
+//   tes_batch_ep_acq_f64  TES_ep batch  criteria/evaluate_batch_mp.py:145-331
+//
+// One hyper-parameter sample per call (the reference loops `for i in range(nhyp)` and averages).
+// The caller passes only the maximizers with max_probs > 0 (evaluate_mp.py:169-173).
+#include "gemm.cuh"
+#include "gp.cuh"
+
+namespace tes {
+
+constexpr double HALF_LOG_2PI = 0.91893853320467274178;
+
+// ---- TES_ep query moments: var[x][j] = Kq[x] + M[x]^T Sigma_j M[x]  (evaluate_mp.py:103-107) ----
+// Symmetric 16x16 block pairs (ab <= bb): k index = (pair*16 + a_local)*16 + b_local.
+__global__ void blockpair_table_kernel(int nb, int2* table) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int i = 0;
+        for (int a = 0; a < nb; ++a)
+            for (int b = a; b < nb; ++b) table[i++] = make_int2(a, b);
+    }
+}
+
+// Bpack[krow][j] = Sigma_j[a][b] (diagonal block pairs) or Sigma_j[a][b] + Sigma_j[b][a] (ab < bb)
+__global__ void quad_pack_kernel(const double* __restrict__ cov, int64_t Sp, int64_t T, const int2* __restrict__ table,
+                                 int64_t nrows, double* __restrict__ Bpack) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nrows * Sp) return;
+    int64_t krow = e / Sp, j = e % Sp;
+    int2 pr = table[krow >> 8];
+    int64_t a = (int64_t)pr.x * 16 + ((krow >> 4) & 15);
+    int64_t b = (int64_t)pr.y * 16 + (krow & 15);
+    double v = 0.0;
+    if (a < T && b < T) {
+        const double* c = cov + j * T * T;
+        v = c[a * T + b];
+        if (pr.x != pr.y) v += c[b * T + a];
+    }
+    Bpack[e] = v;
+}
+
+struct AQuad {
+    const double* G;  // rows x ldg, the first T columns are M
+    int64_t ldg, M, T;
+    const int2* table;
+    __device__ __forceinline__ void load(int64_t row0, int64_t k0, int t, double regs[8]) const {
+        const int kk = t & 15;
+        const int r = t >> 4;
+        const int64_t kt = k0 >> 4;
+        const int2 pr = __ldg(table + (kt >> 4));
+        const int64_t a = (int64_t)pr.x * 16 + (kt & 15);
+        const int64_t b = (int64_t)pr.y * 16 + kk;
+        const bool ok = a < T && b < T;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            int64_t row = row0 + r + 16 * q;
+            regs[q] = (ok && row < M) ? __dmul_rn(__ldg(G + row * ldg + a), __ldg(G + row * ldg + b)) : 0.0;
+        }
+    }
+    __device__ __forceinline__ void store(double (*as)[GEMM_LDA_S], int t, const double regs[8]) const {
+        const int kk = t & 15;
+        const int r = t >> 4;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) as[kk][r + 16 * q] = regs[q];
+    }
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS)
+    quadform_kernel(const double* __restrict__ G, int64_t ldg, int64_t rows, int64_t T, const int2* __restrict__ table,
+                    int64_t Kdim, const double* __restrict__ Bpack, int64_t Sp, const double* __restrict__ Kq,
+                    double* __restrict__ var) {
+    extern __shared__ __align__(16) unsigned char gemm_smem_raw[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(gemm_smem_raw);
+    const int64_t row0 = (int64_t)blockIdx.x * GEMM_BM;
+    const int64_t col0 = (int64_t)blockIdx.y * GEMM_BN;
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    AQuad ap{G, ldg, rows, T, table};
+    gemm_mainloop(ap, Bpack, Sp, Kdim, Sp, row0, col0, sm, acc);
+    const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int64_t row = row0 + gemm_row_of(ty, i);
+        if (row >= rows) continue;
+        const double kq = Kq[row];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t col = col0 + gemm_col_of(tx, j);
+            if (col < Sp) var[row * Sp + col] = kq + acc[i][j];
+        }
+    }
+}
+
+__global__ void add_col_kernel(double* __restrict__ A, int64_t rows, int64_t cols, const double* __restrict__ v,
+                               int64_t ldv) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * cols) return;
+    A[e] += v[(e / cols) * ldv];
+}
+
+// ---- TES_ep deterministic (evaluate_mp.py:199-219) ----------------------------------------------
+// acq = H[y] - mean_j( p_j * H[y | j] ),  H(s) = 0.5 log(2 pi) + log(s) + 0.5  (utils.py:653)
+__global__ void ep_det_kernel(const double* __restrict__ var, const double* __restrict__ varf,
+                              const double* __restrict__ p, int64_t rows, int64_t Sp, double sigma0,
+                              double* __restrict__ out) {
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    double s = 0.0;
+    for (int64_t j = lane; j < Sp; j += 32) {
+        double sd = sqrt(var[row * Sp + j] + sigma0);  // no clipping: negative -> NaN
+        s += ((HALF_LOG_2PI + log(sd)) + 0.5) * p[j];
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+        double ent = (HALF_LOG_2PI + log(sqrt(varf[row] + sigma0))) + 0.5;
+        out[row] = ent - s / (double)Sp;  // reduce_MEAN over j
+    }
+}
+
+// ---- TES_ep lite (evaluate_mp_lite.py:187-220) ----------------------------------------------------
+// sum_{i,j} p_i p_j [ 0.5 log(v_i/v_j) + 0.5 (v_j + (m_j - m_i)^2)/v_i - 0.5 ],  v = var + sigma0
+__global__ void ep_lite_kernel(const double* __restrict__ mean, const double* __restrict__ var,
+                               const double* __restrict__ p, int64_t rows, int64_t Sp, double sigma0,
+                               double* __restrict__ out) {
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const double* mr = mean + row * Sp;
+    const double* vr = var + row * Sp;
+    double s = 0.0;
+    for (int64_t e = lane; e < Sp * Sp; e += 32) {
+        int64_t i = e / Sp, j = e % Sp;
+        double vi = vr[i] + sigma0, vj = vr[j] + sigma0;
+        double diff = mr[j] - mr[i];
+        double mips = 0.5 * log(vi / vj) + 0.5 * (vj + diff * diff) / vi - 0.5;
+        s += p[i] * p[j] * mips;
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s;
+}
+
+// ---- TES_ep stochastic (evaluate_mp.py:248-295) -----------------------------------------------------
+// per (it, iy, j): y = mu_j + s_j z;  cond term lp_j(y);  marginal LSE_j'( lp_j'(y) + log p_j' ).
+// acq = (1/(I*Y)) sum_{it,iy,j} p_j * ( lp_j(y) - LSE_j' )          (= ent - cond, averaged)
+// One CTA per candidate; z either host-supplied (layout (I, Y, Sp, Nz) with row stride Nz) or
+// Philox (tes_spec.h, stream TES_STREAM_EP_Y, element (iy*Sp + j)*n_global + x_global).
+__global__ void __launch_bounds__(128)
+    ep_stoch_kernel(const double* __restrict__ mean, const double* __restrict__ var, const double* __restrict__ p,
+                    int64_t rows, int Sp, double sigma0, int niter, int ny, const double* __restrict__ z,
+                    int64_t z_n, int64_t z_x0, uint64_t seed, int64_t n_global, int64_t x_global0,
+                    double* __restrict__ out) {
+    extern __shared__ double sh[];
+    double* mu = sh;              // [Sp]
+    double* isd = mu + Sp;        // [Sp] 1/std
+    double* cst = isd + Sp;       // [Sp] -(0.5 log 2pi + log std) + log p
+    double* lgp = cst + Sp;       // [Sp] log p
+    double* sdv = lgp + Sp;       // [Sp] std
+    double* red = sdv + Sp;       // [4]
+    const int64_t row = blockIdx.x;
+    if (row >= rows) return;
+    for (int j = threadIdx.x; j < Sp; j += blockDim.x) {
+        double sd = sqrt(var[row * Sp + j] + sigma0);
+        mu[j] = mean[row * Sp + j];
+        isd[j] = 1.0 / sd;
+        sdv[j] = sd;
+        double lp = log(p[j]);
+        lgp[j] = lp;
+        cst[j] = -(HALF_LOG_2PI + log(sd)) + lp;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    const int64_t items = (int64_t)niter * ny * Sp;
+    for (int64_t it_ = threadIdx.x; it_ < items; it_ += blockDim.x) {
+        const int j = (int)(it_ % Sp);
+        const int iy = (int)((it_ / Sp) % ny);
+        const int it = (int)(it_ / ((int64_t)Sp * ny));
+        double zz;
+        if (z)
+            zz = z[(((int64_t)it * ny + iy) * Sp + j) * z_n + z_x0 + row];
+        else
+            zz = normal_elem(seed, (uint32_t)it, TES_STREAM_EP_Y,
+                             (uint64_t)(((int64_t)iy * Sp + j) * n_global + x_global0 + row));
+        const double y = fma(sdv[j], zz, mu[j]);
+        const double u = (y - mu[j]) * isd[j];
+        const double lpc = -0.5 * u * u + (cst[j] - lgp[j]);
+        // two-pass log-sum-exp over j'
+        double mx = neg_inf();
+        for (int jp = 0; jp < Sp; ++jp) {
+            double w = (y - mu[jp]) * isd[jp];
+            double tt = fma(-0.5 * w, w, cst[jp]);
+            mx = tt > mx ? tt : mx;
+        }
+        const double shift = (mx > neg_inf() && mx < pos_inf()) ? mx : 0.0;  // tf.reduce_logsumexp rule
+        double se = 0.0;
+        for (int jp = 0; jp < Sp; ++jp) {
+            double w = (y - mu[jp]) * isd[jp];
+            double tt = fma(-0.5 * w, w, cst[jp]);
+            se += exp(tt - shift);
+        }
+        const double lse = log(se) + shift;
+        acc += p[j] * (lpc - lse);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) s += red[w];
+        out[row] = s / ((double)niter * (double)ny);
+    }
+}
+
+// ---- TES_sp (evaluate_sample_mp.py:250-336; batch: evaluate_batch_sample_mp.py:294-382) -------------
+// One CTA per query (a query = Q inputs).  Shared memory: mean[j][s][q] for all maximizers j and
+// joint samples s, then per warp a y buffer of K*Q doubles.
+//   lmix[iy,j]     = LSE_{s valid for j}  logN(y_{j,s}; mean[j,s], L)
+//   lmarg[iy,j]    = LSE_{j'} ( log p_j' + LSE_{s valid for SOURCE j} logN(y_{j,s}; mean[j',s], L) )   (Q3)
+//   acq = (1/(I*Y)) sum p_j (lmix - lmarg)
+template <int Q>
+__global__ void __launch_bounds__(256)
+    sp_kernel(const double* __restrict__ Mq,   // (rows*Q, T)   k invpNK[:, :T]
+              const double* __restrict__ bq,   // (rows*Q)      k invpNK[:, T:] Y
+              const double* __restrict__ Linv, // (rows, Q, Q)  inverse of chol(cov_y), lower
+              const double* __restrict__ Lmat, // (rows, Q, Q)  chol(cov_y), lower
+              const double* __restrict__ P,    // (Sp, T, K)
+              const unsigned char* __restrict__ mask,  // (Sp, K)
+              const double* __restrict__ p, int64_t rows, int Sp, int T, int K, int niter, int ny,
+              const double* __restrict__ z, int64_t z_n, int64_t z_x0, uint64_t seed, int64_t n_global,
+              int64_t x_global0, double* __restrict__ mean_g,  // optional global scratch (rows? no: gridDim.x) x Sp*K*Q
+              int mean_in_smem, double* __restrict__ out) {
+    extern __shared__ double sh[];
+    const int nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* red = sh;                       // [8]
+    double* lq = red + 8;                   // [Q*Q] Linv, [Q*Q] L, [Q] b, pad to 2*Q*Q+Q (+1 logdet)
+    double* ybuf = lq + 2 * Q * Q + Q + 1;  // [nwarps][K*Q]
+    double* mean_s = mean_in_smem ? (ybuf + (size_t)nwarps * K * Q) : (mean_g + (size_t)blockIdx.x * Sp * K * Q);
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < Q * Q) {
+            lq[threadIdx.x] = Linv[row * Q * Q + threadIdx.x];
+            lq[Q * Q + threadIdx.x] = Lmat[row * Q * Q + threadIdx.x];
+        }
+        if (threadIdx.x < Q) lq[2 * Q * Q + threadIdx.x] = bq[row * Q + threadIdx.x];
+        if (threadIdx.x == 0) {
+            double ld = 0.0;
+            for (int a = 0; a < Q; ++a) ld += log(Lmat[row * Q * Q + a * Q + a]);
+            lq[2 * Q * Q + Q] = ld;
+        }
+        __syncthreads();
+        // mean[j][s][q] = sum_t M[row*Q+q][t] * P[j][t][s] + b[q]
+        for (int e = threadIdx.x; e < Sp * K; e += blockDim.x) {
+            const int j = e / K, s = e % K;
+            double a[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) a[q] = 0.0;
+            const double* pj = P + ((size_t)j * T) * K + s;
+            for (int t = 0; t < T; ++t) {
+                const double pv = pj[(size_t)t * K];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) a[q] = fma(__ldg(Mq + (row * Q + q) * T + t), pv, a[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) mean_s[((size_t)j * K + s) * Q + q] = a[q] + lq[2 * Q * Q + q];
+        }
+        __syncthreads();
+        const double logdet = lq[2 * Q * Q + Q];
+        const double cnorm = -logdet - 0.5 * Q * 1.8378770664093454836;  // - sum log L_ii - q/2 log(2 pi)
+        double acc = 0.0;
+        double* yb = ybuf + (size_t)warp * K * Q;
+        const int64_t items = (int64_t)niter * ny * Sp;
+        for (int64_t it_ = warp; it_ < items; it_ += nwarps) {
+            const int j = (int)(it_ % Sp);
+            const int iy = (int)((it_ / Sp) % ny);
+            const int it = (int)(it_ / ((int64_t)Sp * ny));
+            const unsigned char* mj = mask + (size_t)j * K;
+            // y_s = mean[j][s] + L z_s for every s (invalid s are never read)
+            __syncwarp();
+            for (int s = lane; s < K; s += 32) {
+                double zz[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    if (z)
+                        zz[q] = z[(((((int64_t)it * ny + iy) * Sp + j) * z_n + z_x0 + row) * K + s) * Q + q];
+                    else
+                        zz[q] = normal_elem(seed, (uint32_t)it, Q == 1 ? TES_STREAM_SP_Y : TES_STREAM_BSP_Y,
+                                            (uint64_t)((((int64_t)iy * Sp + j) * n_global + x_global0 + row) * K + s) * Q + q);
+                }
+#pragma unroll
+                for (int a = 0; a < Q; ++a) {
+                    double v = mean_s[((size_t)j * K + s) * Q + a];
+#pragma unroll
+                    for (int b2 = 0; b2 <= a; ++b2) v = fma(lq[Q * Q + a * Q + b2], zz[b2], v);
+                    yb[s * Q + a] = v;
+                }
+            }
+            __syncwarp();
+            // running log-sum-exp over j' of (log p_j' + LSE_s ...), and the j'==j inner LSE for lmix
+            double lmix = 0.0;
+            double out_mx = neg_inf(), out_se = 0.0;  // online LSE over j' (Sp terms, cheap)
+            bool out_nan = false;
+            for (int jp = 0; jp < Sp; ++jp) {
+                const double* mp_ = mean_s + (size_t)jp * K * Q;
+                // pass 1: min of u^2 over valid s
+                double umin = pos_inf();
+                for (int s = lane; s < K; s += 32) {
+                    if (!mj[s]) continue;
+                    double u2 = 0.0;
+                    double dlt[Q];
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) dlt[q] = yb[s * Q + q] - mp_[s * Q + q];
+#pragma unroll
+                    for (int a = 0; a < Q; ++a) {
+                        double w = 0.0;
+#pragma unroll
+                        for (int b2 = 0; b2 <= a; ++b2) w = fma(lq[a * Q + b2], dlt[b2], w);
+                        u2 = fma(w, w, u2);
+                    }
+                    umin = u2 < umin ? u2 : umin;
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    double o = __shfl_xor_sync(0xffffffffu, umin, off);
+                    umin = o < umin ? o : umin;
+                }
+                // shift = max log-prob if finite else 0 (tf.reduce_logsumexp)
+                const double mxlp = fma(-0.5, umin, cnorm);
+                const double shift = (mxlp > neg_inf() && mxlp < pos_inf()) ? mxlp : 0.0;
+                double se = 0.0;
+                for (int s = lane; s < K; s += 32) {
+                    if (!mj[s]) continue;
+                    double u2 = 0.0;
+                    double dlt[Q];
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) dlt[q] = yb[s * Q + q] - mp_[s * Q + q];
+#pragma unroll
+                    for (int a = 0; a < Q; ++a) {
+                        double w = 0.0;
+#pragma unroll
+                        for (int b2 = 0; b2 <= a; ++b2) w = fma(lq[a * Q + b2], dlt[b2], w);
+                        u2 = fma(w, w, u2);
+                    }
+                    se += exp(fma(-0.5, u2, cnorm) - shift);
+                }
+                se = warp_sum(se);
+                const double lse_s = log(se) + shift;  // (Y, j, j') entry
+                if (jp == j) lmix = lse_s;
+                const double term = lse_s + log(p[jp]);
+                // online LSE over j' with the same non-finite-max rule applied at the end
+                if (term != term) {
+                    out_nan = true;
+                } else if (term > out_mx) {
+                    out_se = out_se * exp(out_mx - term) + 1.0;  // out_mx == -inf: 0 * 0 + 1
+                    out_mx = term;
+                } else if (term > neg_inf()) {
+                    out_se += exp(term - out_mx);
+                }
+            }
+            double lmarg;
+            if (out_nan)
+                lmarg = __longlong_as_double(0x7ff8000000000000LL);
+            else if (out_mx > neg_inf() && out_mx < pos_inf())
+                lmarg = log(out_se) + out_mx;
+            else
+                lmarg = out_mx;  // all -inf (or +inf): propagate
+            acc += p[j] * (lmix - lmarg);
+        }
+        // acc identical across lanes of a warp; reduce over warps
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < nwarps; ++w) s += red[w];
+            out[row] = s / ((double)niter * (double)ny);
+        }
+    }
+}
+
+// cov_y = k_x - k invpNK k^T + sigma0 I (q x q), its Cholesky factor and inverse, per query.
+// Kxx via the reference's expansion (utils.computeKmm, utils.py:740-762).
+template <int Q>
+__global__ void sp_cov_kernel(const double* __restrict__ x, int d, const double* __restrict__ l, double sigma,
+                              double sigma0, const double* __restrict__ G, int64_t ldg, const double* __restrict__ Kc,
+                              int64_t ldk, int64_t m, int64_t rows, double* __restrict__ Lmat,
+                              double* __restrict__ Linv, int* __restrict__ info) {
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    double c[Q][Q];
+    for (int a = 0; a < Q; ++a)
+        for (int b2 = 0; b2 <= a; ++b2) {
+            double qa = 0.0, qb = 0.0, dot = 0.0;
+            for (int k = 0; k < d; ++k) {
+                double sl = sqrt(l[k]);
+                double xa = x[(row * Q + a) * d + k] * sl, xb = x[(row * Q + b2) * d + k] * sl;
+                qa = fma(xa, xa, qa);
+                qb = fma(xb, xb, qb);
+                dot = fma(xa, xb, dot);
+            }
+            double kxx = sigma * exp(-0.5 * ((qa + qb) - 2.0 * dot));
+            double s = 0.0;
+            const double* ga = G + (row * Q + a) * ldg;
+            const double* kb = Kc + (row * Q + b2) * ldk;
+            for (int64_t t = 0; t < m; ++t) s = fma(ga[t], kb[t], s);
+            c[a][b2] = kxx - s + (a == b2 ? sigma0 : 0.0);
+        }
+    // Cholesky (lower), in place
+    bool bad = false;
+    for (int a = 0; a < Q; ++a) {
+        for (int b2 = 0; b2 <= a; ++b2) {
+            double s = c[a][b2];
+            for (int k = 0; k < b2; ++k) s -= c[a][k] * c[b2][k];
+            if (a == b2) {
+                if (!(s > 0.0)) bad = true;
+                c[a][a] = sqrt(s);
+            } else {
+                c[a][b2] = s / c[b2][b2];
+            }
+        }
+    }
+    // inverse of lower-triangular
+    double inv[Q][Q];
+    for (int a = 0; a < Q; ++a)
+        for (int b2 = 0; b2 < Q; ++b2) inv[a][b2] = 0.0;
+    for (int col = 0; col < Q; ++col) {
+        inv[col][col] = 1.0 / c[col][col];
+        for (int a = col + 1; a < Q; ++a) {
+            double s = 0.0;
+            for (int k = col; k < a; ++k) s -= c[a][k] * inv[k][col];
+            inv[a][col] = s / c[a][a];
+        }
+    }
+    for (int a = 0; a < Q; ++a)
+        for (int b2 = 0; b2 < Q; ++b2) {
+            Lmat[row * Q * Q + a * Q + b2] = b2 <= a ? c[a][b2] : 0.0;
+            Linv[row * Q * Q + a * Q + b2] = inv[a][b2];
+        }
+    if (bad && info) atomicAdd(info, 1);
+}
+
+__global__ void const_fill_kernel(double* out, int64_t n, const double* __restrict__ p, int64_t Sp) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double s = 0.0;
+    for (int64_t j = 0; j < Sp; ++j) s += p[j];
+    // evaluate_batch_mp.py:302-327: ent - cond == -(sum p) * log(sum p) for every input
+    out[e] = -s * log(s);
+}
+
+struct EpPlan {
+    int64_t m, nb, nbp, Kdim, nc;
+    int64_t off_xto, off_bext, off_kc, off_gc, off_table, off_bpack, off_mean, off_var, off_kq, off_gobs, off_varf,
+        total;
+};
+
+static EpPlan ep_plan(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp) {
+    EpPlan p;
+    p.m = T + n;
+    p.nb = (T + 15) / 16;
+    p.nbp = p.nb * (p.nb + 1) / 2;
+    p.Kdim = p.nbp * 256;
+    p.nc = N < PS_CHUNK ? (N < 1 ? 1 : N) : PS_CHUNK;
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) {
+        int64_t r = o;
+        o += align_up(bytes, 256);
+        return r;
+    };
+    p.off_xto = take(p.m * d * 8);
+    p.off_bext = take(p.m * (p.m + 1) * 8);
+    p.off_kc = take(p.nc * p.m * 8);
+    p.off_gc = take(p.nc * (p.m + 1) * 8);
+    p.off_table = take((p.nbp + 1) * 8);
+    p.off_bpack = take(p.Kdim * Sp * 8);
+    p.off_mean = take(p.nc * Sp * 8);
+    p.off_var = take(p.nc * Sp * 8);
+    p.off_kq = take(p.nc * 8);
+    p.off_gobs = take(p.nc * (n > 0 ? n : 1) * 8);
+    p.off_varf = take(p.nc * 8);
+    p.total = o;
+    return p;
+}
+
+}  // namespace tes
+
+using namespace tes;
+
+extern "C" int64_t tes_ep_acq_workspace_bytes(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp) {
+    if (N < 0 || T < 1 || n < 0 || d < 1 || Sp < 1) return -1;
+    return ep_plan(N, T, n, d, Sp).total;
+}
+
+extern "C" int tes_ep_acq_f64(int mode, const double* x, int64_t N, int64_t d, const double* test_xs, int64_t T,
+                              const double* X, int64_t n, const double* Y, const double* l, double sigma,
+                              double sigma0, const double* invpNK, const double* invKobs, const double* p,
+                              int64_t Sp, const double* post_mean, const double* post_cov, int niter, int nysample,
+                              const double* z, uint64_t seed, int64_t n_global, int64_t x_offset, double* out_acq,
+                              double* out_mean, double* out_var, void* ws, int64_t ws_bytes, void* stream) {
+    if (mode < 0 || mode > 3) return -1;
+    if (N < 0 || (N > 0 && !x)) return -2;
+    if (d < 1 || d > 64) return -4;
+    if (T < 1 || !test_xs) return -5;
+    if (n < 0 || (n > 0 && (!X || !Y))) return -7;
+    if (!l) return -10;
+    if (!invpNK) return -13;
+    if (mode == 0 && (!invKobs || n < 1)) return -14;
+    if (!p) return -15;
+    if (Sp < 1 || Sp > (1 << 20)) return -16;
+    if (!post_mean) return -17;
+    if (!post_cov) return -18;
+    if (mode == 1 && (niter < 1 || nysample < 1)) return -19;
+    if (mode != 3 && N > 0 && !out_acq) return -25;
+    EpPlan pl = ep_plan(N, T, n, d, Sp);
+    if (!ws || ws_bytes < pl.total) return -100;
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)ws;
+    double* xto = (double*)(base + pl.off_xto);
+    double* Bext = (double*)(base + pl.off_bext);
+    double* Kc = (double*)(base + pl.off_kc);
+    double* Gc = (double*)(base + pl.off_gc);
+    int2* table = (int2*)(base + pl.off_table);
+    double* Bpack = (double*)(base + pl.off_bpack);
+    double* meanc = (double*)(base + pl.off_mean);
+    double* varc = (double*)(base + pl.off_var);
+    double* Kq = (double*)(base + pl.off_kq);
+    double* Gobs = (double*)(base + pl.off_gobs);
+    double* varf = (double*)(base + pl.off_varf);
+    const int64_t m = pl.m;
+    int rc;
+    if ((rc = launch_concat_rows(test_xs, T, X, n, (int)d, xto, st))) return rc;
+    if ((rc = launch_build_bext(invpNK, Y, m, T, Bext, st))) return rc;
+    blockpair_table_kernel<<<1, 32, 0, st>>>((int)pl.nb, table);
+    TES_LAUNCH_OK();
+    {
+        int64_t tot = pl.Kdim * Sp;
+        quad_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(post_cov, Sp, T, table, pl.Kdim, Bpack);
+        TES_LAUNCH_OK();
+    }
+    if (mode == 1) {
+        size_t smem = (size_t)(5 * Sp + 8) * sizeof(double);
+        if (smem > 48 * 1024) {
+            if (smem > 200 * 1024) return -16;
+            TES_CUDA_OK(cudaFuncSetAttribute(ep_stoch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+    }
+    for (int64_t c0 = 0; c0 < N; c0 += PS_CHUNK) {
+        const int64_t nc = (N - c0 < PS_CHUNK) ? (N - c0) : PS_CHUNK;
+        if ((rc = launch_se_ard(x + c0 * d, nc, xto, m, (int)d, l, sigma, -1, 0.0, Kc, m, st))) return rc;
+        if ((rc = launch_gemm(Kc, m, Bext, m + 1, 1, Gc, m + 1, nc, m + 1, m, st))) return rc;
+        if ((rc = launch_rowdot(Gc, m + 1, Kc, m, nc, m, sigma, -INFINITY, Kq, st))) return rc;
+        // mean[x][j] = M mu_j^T + b
+        double* mean_dst = out_mean ? out_mean + c0 * Sp : meanc;
+        double* var_dst = out_var ? out_var + c0 * Sp : varc;
+        if ((rc = launch_gemm(Gc, m + 1, post_mean, 1, T, mean_dst, Sp, nc, Sp, T, st))) return rc;
+        add_col_kernel<<<(unsigned)((nc * Sp + 255) / 256), 256, 0, st>>>(mean_dst, nc, Sp, Gc + m, m + 1);
+        TES_LAUNCH_OK();
+        {
+            dim3 grid((unsigned)((nc + GEMM_BM - 1) / GEMM_BM), (unsigned)((Sp + GEMM_BN - 1) / GEMM_BN));
+            TES_CUDA_OK(cudaFuncSetAttribute(quadform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(GemmSmem)));
+            quadform_kernel<<<grid, GEMM_THREADS, sizeof(GemmSmem), st>>>(Gc, m + 1, nc, T, table, pl.Kdim, Bpack, Sp, Kq, var_dst);
+            TES_LAUNCH_OK();
+        }
+        if (mode == 0) {
+            // H[y] from the observation-only posterior (utils.compute_mean_var_f, clip 1e-100)
+            if ((rc = launch_gemm(Kc + T, m, invKobs, n, 1, Gobs, n, nc, n, n, st))) return rc;
+            if ((rc = launch_rowdot(Gobs, n, Kc + T, m, nc, n, sigma, 1e-100, varf, st))) return rc;
+            ep_det_kernel<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(var_dst, varf, p, nc, Sp, sigma0,
+                                                                            out_acq + c0);
+            TES_LAUNCH_OK();
+        } else if (mode == 2) {
+            ep_lite_kernel<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(mean_dst, var_dst, p, nc, Sp, sigma0,
+                                                                             out_acq + c0);
+            TES_LAUNCH_OK();
+        } else if (mode == 1) {
+            size_t smem = (size_t)(5 * Sp + 8) * sizeof(double);
+            ep_stoch_kernel<<<(unsigned)nc, 128, smem, st>>>(mean_dst, var_dst, p, nc, (int)Sp, sigma0, niter,
+                                                             nysample, z, N, c0, seed, n_global, x_offset + c0,
+                                                             out_acq + c0);
+            TES_LAUNCH_OK();
+        }
+    }
+    return 0;
+}
+
+// ---- TES_sp ------------------------------------------------------------------------------------------
+namespace tes {
+struct SpPlan {
+    int64_t m, nc, rows_c;
+    int64_t off_xto, off_bext, off_kc, off_gc, off_M, off_b, off_L, off_Li, off_meang, total;
+    int nwarps, mean_in_smem;
+    size_t smem;
+    int64_t grid;
+};
+static SpPlan sp_plan(int64_t nx, int q, int64_t T, int64_t n, int64_t d, int64_t Sp, int64_t K) {
+    SpPlan p;
+    p.m = T + n;
+    int64_t rows = nx * q;
+    p.nc = rows < PS_CHUNK ? (rows < 1 ? 1 : rows) : (PS_CHUNK / q) * q;  // whole queries per chunk
+    p.rows_c = p.nc / q;
+    if (p.rows_c < 1) p.rows_c = 1;
+    // shared memory: red[8] + lq + ybuf[nwarps][K*q] (+ mean[Sp*K*q] if it fits)
+    const size_t fixed = (8 + 2 * q * q + q + 1) * sizeof(double);
+    const size_t mean_b = (size_t)Sp * K * q * sizeof(double);
+    const size_t budget = 200 * 1024;
+    p.nwarps = 8;
+    p.mean_in_smem = 1;
+    while (p.nwarps > 1 && fixed + mean_b + (size_t)p.nwarps * K * q * 8 > budget) p.nwarps >>= 1;
+    if (fixed + mean_b + (size_t)p.nwarps * K * q * 8 > budget) {
+        p.mean_in_smem = 0;
+        p.nwarps = 8;
+        while (p.nwarps > 1 && fixed + (size_t)p.nwarps * K * q * 8 > budget) p.nwarps >>= 1;
+    }
+    p.smem = fixed + (p.mean_in_smem ? mean_b : 0) + (size_t)p.nwarps * K * q * 8;
+    p.grid = p.rows_c < 148 * 8 ? p.rows_c : 148 * 8;
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) {
+        int64_t r = o;
+        o += align_up(bytes, 256);
+        return r;
+    };
+    p.off_xto = take(p.m * d * 8);
+    p.off_bext = take(p.m * (p.m + 1) * 8);
+    p.off_kc = take(p.nc * p.m * 8);
+    p.off_gc = take(p.nc * (p.m + 1) * 8);
+    p.off_M = take(p.nc * (T > 0 ? T : 1) * 8);
+    p.off_b = take(p.nc * 8);
+    p.off_L = take(p.rows_c * q * q * 8);
+    p.off_Li = take(p.rows_c * q * q * 8);
+    p.off_meang = take(p.mean_in_smem ? 256 : p.grid * Sp * K * q * 8);
+    p.total = o + 256;  // + info word
+    return p;
+}
+__global__ void extract_mb2_kernel(const double* __restrict__ G, int64_t N, int64_t m, int64_t T,
+                                   double* __restrict__ outM, double* __restrict__ outb) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N * (T + 1)) return;
+    int64_t i = e / (T + 1), c = e % (T + 1);
+    if (c < T)
+        outM[i * T + c] = G[i * (m + 1) + c];
+    else
+        outb[i] = G[i * (m + 1) + m];
+}
+
+template <int Q>
+static int run_sp_chunk(const SpPlan& pl, const double* xq, int64_t rows, int d, const double* l, double sigma,
+                        double sigma0, const double* xto, const double* Bext, double* Kc, double* Gc, double* Mq,
+                        double* bq, double* Lmat, double* Linv, double* meang, int* info, int64_t T, const double* P,
+                        const unsigned char* mask, const double* p, int Sp, int K, int niter, int ny, const double* z,
+                        int64_t z_n, int64_t z_x0, uint64_t seed, int64_t n_global, int64_t x_global0, double* out,
+                        cudaStream_t st) {
+    const int64_t m = pl.m;
+    const int64_t nr = rows * Q;
+    int rc;
+    if ((rc = launch_se_ard(xq, nr, xto, m, d, l, sigma, -1, 0.0, Kc, m, st))) return rc;
+    if ((rc = launch_gemm(Kc, m, Bext, m + 1, 1, Gc, m + 1, nr, m + 1, m, st))) return rc;
+    extract_mb2_kernel<<<(unsigned)((nr * (T + 1) + 255) / 256), 256, 0, st>>>(Gc, nr, m, T, Mq, bq);
+    TES_LAUNCH_OK();
+    sp_cov_kernel<Q><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(xq, d, l, sigma, sigma0, Gc, m + 1, Kc, m, m, rows,
+                                                                     Lmat, Linv, info);
+    TES_LAUNCH_OK();
+    auto kern = sp_kernel<Q>;
+    if (pl.smem > 48 * 1024)
+        TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    int64_t grid = rows < pl.grid ? rows : pl.grid;
+    kern<<<(unsigned)grid, pl.nwarps * 32, pl.smem, st>>>(Mq, bq, Linv, Lmat, P, mask, p, rows, Sp, (int)T, K, niter, ny,
+                                                          z, z_n, z_x0, seed, n_global, x_global0, meang,
+                                                          pl.mean_in_smem, out);
+    TES_LAUNCH_OK();
+    return 0;
+}
+}  // namespace tes
+
+extern "C" int64_t tes_sp_acq_workspace_bytes(int64_t nx, int q, int64_t T, int64_t n, int64_t d, int64_t Sp,
+                                              int64_t K) {
+    if (nx < 0 || q < 1 || q > 8 || T < 1 || n < 0 || d < 1 || Sp < 1 || K < 1) return -1;
+    return sp_plan(nx, q, T, n, d, Sp, K).total;
+}
+
+extern "C" int tes_sp_acq_f64(const double* x, int64_t nx, int q, int64_t d, const double* test_xs, int64_t T,
+                              const double* X, int64_t n, const double* Y, const double* l, double sigma,
+                              double sigma0, const double* invpNK, const double* p, int64_t Sp,
+                              const double* post_samples, const unsigned char* post_mask, int64_t K, int niter,
+                              int nysample, const double* z, uint64_t seed, int64_t n_global, int64_t x_offset,
+                              double* out_acq, void* ws, int64_t ws_bytes, void* stream) {
+    if (nx < 0 || (nx > 0 && !x)) return -1;
+    if (q < 1 || q > 8) return -3;
+    if (d < 1 || d > 64) return -4;
+    if (T < 1 || !test_xs) return -5;
+    if (n < 0 || (n > 0 && (!X || !Y))) return -7;
+    if (!l) return -10;
+    if (!invpNK) return -13;
+    if (!p) return -14;
+    if (Sp < 1) return -15;
+    if (!post_samples) return -16;
+    if (!post_mask) return -17;
+    if (K < 1) return -18;
+    if (niter < 1) return -19;
+    if (nysample < 1) return -20;
+    if (nx > 0 && !out_acq) return -25;
+    SpPlan pl = sp_plan(nx, q, T, n, d, Sp, K);
+    if (!ws || ws_bytes < pl.total) return -100;
+    if (pl.smem > 220 * 1024) return -18;
+    if (nx == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)ws;
+    double* xto = (double*)(base + pl.off_xto);
+    double* Bext = (double*)(base + pl.off_bext);
+    double* Kc = (double*)(base + pl.off_kc);
+    double* Gc = (double*)(base + pl.off_gc);
+    double* Mq = (double*)(base + pl.off_M);
+    double* bq = (double*)(base + pl.off_b);
+    double* Lmat = (double*)(base + pl.off_L);
+    double* Linv = (double*)(base + pl.off_Li);
+    double* meang = (double*)(base + pl.off_meang);
+    int* info = (int*)(base + pl.total - 256);
+    int rc;
+    if ((rc = launch_concat_rows(test_xs, T, X, n, (int)d, xto, st))) return rc;
+    if ((rc = launch_build_bext(invpNK, Y, pl.m, T, Bext, st))) return rc;
+    TES_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int), st));
+    for (int64_t r0 = 0; r0 < nx; r0 += pl.rows_c) {
+        const int64_t rows = (nx - r0 < pl.rows_c) ? (nx - r0) : pl.rows_c;
+        const double* xq = x + r0 * q * d;
+#define TES_SP_CASE(QQ)                                                                                               \
+    case QQ:                                                                                                          \
+        rc = run_sp_chunk<QQ>(pl, xq, rows, (int)d, l, sigma, sigma0, xto, Bext, Kc, Gc, Mq, bq, Lmat, Linv, meang,   \
+                              info, T, post_samples, post_mask, p, (int)Sp, (int)K, niter, nysample, z, nx, r0, seed, \
+                              n_global, x_offset + r0, out_acq + r0, st);                                            \
+        break;
+        switch (q) {
+            TES_SP_CASE(1) TES_SP_CASE(2) TES_SP_CASE(3) TES_SP_CASE(4) TES_SP_CASE(5) TES_SP_CASE(6) TES_SP_CASE(7)
+            TES_SP_CASE(8)
+        }
+#undef TES_SP_CASE
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int tes_batch_ep_acq_f64(const double* p, int64_t Sp, int64_t nx, double* out_acq, void* stream) {
+    if (!p) return -1;
+    if (Sp < 1) return -2;
+    if (nx < 0) return -3;
+    if (nx > 0 && !out_acq) return -4;
+    if (nx == 0) return 0;
+    const_fill_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out_acq, nx, p, Sp);
+    TES_LAUNCH_OK();
+    return 0;
+}

@@ -82,3 +82,220 @@ def fp64_fma_peak(seconds=0.5, device=None):
     it2 = max(iters, int(iters * seconds / max(t, 1e-6)))
     t, fl = run(it2)
     return fl / t * 1e-12
+
+
+# ------------------------------------------------------------------------------------- stage B
+def _l(l, d, device):
+    t = dev(l, device).reshape(-1)
+    if t.numel() != d:
+        raise ValueError("length-scale vector must have %d entries, got %d" % (d, t.numel()))
+    return t
+
+
+def se_ard_cross(x, xb, l, sigma):
+    """utils.computeKnm (utils.py:703-719) -> (N, m)."""
+    x = dev(x)
+    xb = dev(xb, x.device)
+    N, d = x.shape
+    m = xb.shape[0]
+    if xb.shape[1] != d:
+        raise ValueError("x and xb must share the input dimension")
+    l = _l(l, d, x.device)
+    out = torch.empty((N, m), dtype=torch.float64, device=x.device)
+    rc = _lib.lib().tes_se_ard_cross_f64(ptr(x), N, ptr(xb), m, d, ptr(l), float(sigma), ptr(out), stream_ptr())
+    _lib.check(rc, "tes_se_ard_cross_f64")
+    return out
+
+
+def gemm(A, B, transb=False):
+    A = dev(A)
+    B = dev(B, A.device)
+    M, K = A.shape
+    N = B.shape[0] if transb else B.shape[1]
+    if (B.shape[1] if transb else B.shape[0]) != K:
+        raise ValueError("inner dimensions differ")
+    C = torch.empty((M, N), dtype=torch.float64, device=A.device)
+    rc = _lib.lib().tes_gemm_f64(ptr(A), A.stride(0), ptr(B), B.stride(0), int(transb), ptr(C), N, M, N, K,
+                                 stream_ptr())
+    _lib.check(rc, "tes_gemm_f64")
+    return C
+
+
+def pnk(test_xs, X, l, sigma, sigma0):
+    """pNK = K([test;X]) + sigma0 diag(0_T, I_n)  (criteria/evaluate_mp.py:36-46)."""
+    test_xs = dev(test_xs)
+    X = dev(X, test_xs.device)
+    T, d = test_xs.shape
+    n = X.shape[0]
+    l = _l(l, d, X.device)
+    L = _lib.lib()
+    need = L.tes_pnk_workspace_bytes(T, n, d)
+    ws = WORKSPACE.get(need, X.device)
+    out = torch.empty((T + n, T + n), dtype=torch.float64, device=X.device)
+    rc = L.tes_pnk_f64(ptr(test_xs), T, ptr(X), n, d, ptr(l), float(sigma), float(sigma0), ptr(out), ptr(ws),
+                       ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_pnk_f64")
+    return out
+
+
+def batched_chol2inv(A, return_info=False):
+    """utils.chol2inv / multichol2inv (utils.py:657-700) over a (batch, m, m) stack (or one (m, m))."""
+    A = dev(A)
+    single = A.dim() == 2
+    A3 = A.reshape(-1, A.shape[-2], A.shape[-1])
+    batch, m, m2 = A3.shape
+    if m != m2:
+        raise ValueError("matrices must be square")
+    L = _lib.lib()
+    need = L.tes_batched_chol_workspace_bytes(batch, m, 1)
+    ws = WORKSPACE.get(need, A.device)
+    out = torch.empty_like(A3)
+    info = torch.empty((batch,), dtype=torch.int32, device=A.device)
+    rc = L.tes_batched_chol2inv_f64(ptr(A3), batch, m, ptr(out), ptr(info), ptr(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_batched_chol2inv_f64")
+    out = out[0] if single else out.reshape(A.shape)
+    return (out, info) if return_info else out
+
+
+def batched_potrf(A, return_info=False):
+    A = dev(A)
+    single = A.dim() == 2
+    A3 = A.reshape(-1, A.shape[-2], A.shape[-1])
+    batch, m, _ = A3.shape
+    L = _lib.lib()
+    need = L.tes_batched_chol_workspace_bytes(batch, m, 0)
+    ws = WORKSPACE.get(need, A.device)
+    out = torch.empty_like(A3)
+    info = torch.empty((batch,), dtype=torch.int32, device=A.device)
+    rc = L.tes_batched_potrf_f64(ptr(A3), batch, m, ptr(out), ptr(info), ptr(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_batched_potrf_f64")
+    out = out[0] if single else out.reshape(A.shape)
+    return (out, info) if return_info else out
+
+
+def posterior_stats(x, test_xs, X, Y, l, sigma, invpNK):
+    """-> M (N,T), b (N), Kq (N).  evaluate_mp.py:76-90 / evaluate_sample_mp.py:77-124."""
+    x = dev(x)
+    dv = x.device
+    test_xs, X, Y, invpNK = dev(test_xs, dv), dev(X, dv), dev(Y, dv).reshape(-1), dev(invpNK, dv)
+    N, d = x.shape
+    T, n = test_xs.shape[0], X.shape[0]
+    if invpNK.shape != (T + n, T + n):
+        raise ValueError("invpNK must be (T+n, T+n)")
+    l = _l(l, d, dv)
+    L = _lib.lib()
+    need = L.tes_posterior_stats_workspace_bytes(N, T, n, d)
+    ws = WORKSPACE.get(need, dv)
+    M = torch.empty((N, T), dtype=torch.float64, device=dv)
+    b = torch.empty((N,), dtype=torch.float64, device=dv)
+    Kq = torch.empty((N,), dtype=torch.float64, device=dv)
+    rc = L.tes_posterior_stats_f64(ptr(x), N, d, ptr(test_xs), T, ptr(X), n, ptr(Y), ptr(l), float(sigma),
+                                   ptr(invpNK), ptr(M), ptr(b), ptr(Kq), ptr(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_posterior_stats_f64")
+    return M, b, Kq
+
+
+def gp_mean_var(x, X, Y, l, sigma, NKinv):
+    """utils.compute_mean_var_f(fullcov=False) (utils.py:786-815) -> mean (N), var (N)."""
+    x = dev(x)
+    dv = x.device
+    X, Y, NKinv = dev(X, dv), dev(Y, dv).reshape(-1), dev(NKinv, dv)
+    N, d = x.shape
+    n = X.shape[0]
+    l = _l(l, d, dv)
+    L = _lib.lib()
+    ws = WORKSPACE.get(L.tes_gp_mean_var_workspace_bytes(N, n), dv)
+    mean = torch.empty((N,), dtype=torch.float64, device=dv)
+    var = torch.empty((N,), dtype=torch.float64, device=dv)
+    rc = L.tes_gp_mean_var_f64(ptr(x), N, d, ptr(X), n, ptr(Y), ptr(l), float(sigma), ptr(NKinv), ptr(mean),
+                               ptr(var), ptr(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_gp_mean_var_f64")
+    return mean, var
+
+
+# ------------------------------------------------------------------------------------- stage D
+EP_DETERMINISTIC, EP_STOCHASTIC, EP_LITE, EP_MOMENTS = 0, 1, 2, 3
+
+
+def ep_acq(mode, x, test_xs, X, Y, l, sigma, sigma0, invpNK, invKobs, p, post_mean, post_cov, niter=10,
+           nysample=10, z=None, seed=0, n_global=None, x_offset=0, want_moments=False):
+    """TES_ep acquisition for one hyper-parameter sample.  evaluate_mp.py:116-295, evaluate_mp_lite.py."""
+    x = dev(x)
+    dv = x.device
+    test_xs, X, Y, invpNK = dev(test_xs, dv), dev(X, dv), dev(Y, dv).reshape(-1), dev(invpNK, dv)
+    p, post_mean, post_cov = dev(p, dv).reshape(-1), dev(post_mean, dv), dev(post_cov, dv)
+    N, d = x.shape
+    T, n, Sp = test_xs.shape[0], X.shape[0], p.numel()
+    if post_mean.shape != (Sp, T) or post_cov.shape != (Sp, T, T):
+        raise ValueError("post_mean must be (Sp,T) and post_cov (Sp,T,T)")
+    if invpNK.shape != (T + n, T + n):
+        raise ValueError("invpNK must be (T+n, T+n)")
+    invKobs_t = dev(invKobs, dv) if invKobs is not None else None
+    l = _l(l, d, dv)
+    zt = None
+    if z is not None:
+        zt = dev(z, dv)
+        if tuple(zt.shape) != (niter, nysample, Sp, N):
+            raise ValueError("z must be (niter, nysample, Sp, N) = %s, got %s"
+                             % ((niter, nysample, Sp, N), tuple(zt.shape)))
+    L = _lib.lib()
+    ws = WORKSPACE.get(L.tes_ep_acq_workspace_bytes(N, T, n, d, Sp), dv)
+    acq = torch.empty((N,), dtype=torch.float64, device=dv) if mode != EP_MOMENTS else None
+    mom = want_moments or mode == EP_MOMENTS
+    omean = torch.empty((N, Sp), dtype=torch.float64, device=dv) if mom else None
+    ovar = torch.empty((N, Sp), dtype=torch.float64, device=dv) if mom else None
+    rc = L.tes_ep_acq_f64(int(mode), ptr(x), N, d, ptr(test_xs), T, ptr(X), n, ptr(Y), ptr(l), float(sigma),
+                          float(sigma0), ptr(invpNK), ptr(invKobs_t), ptr(p), Sp, ptr(post_mean), ptr(post_cov),
+                          int(niter), int(nysample), ptr(zt), int(seed), int(N if n_global is None else n_global),
+                          int(x_offset), ptr(acq), ptr(omean), ptr(ovar), ptr(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_ep_acq_f64")
+    if mode == EP_MOMENTS:
+        return omean, ovar
+    return (acq, omean, ovar) if want_moments else acq
+
+
+def sp_acq(x, test_xs, X, Y, l, sigma, sigma0, invpNK, p, post_samples, post_mask, niter=10, nysample=10, z=None,
+           seed=0, n_global=None, x_offset=0):
+    """TES_sp acquisition; x (nx,d) or (nx,q,d).  evaluate_sample_mp.py / evaluate_batch_sample_mp.py."""
+    x = dev(x)
+    dv = x.device
+    if x.dim() == 2:
+        x = x.unsqueeze(1)
+    nx, q, d = x.shape
+    test_xs, X, Y, invpNK = dev(test_xs, dv), dev(X, dv), dev(Y, dv).reshape(-1), dev(invpNK, dv)
+    p = dev(p, dv).reshape(-1)
+    P = dev(post_samples, dv)
+    mask = dev(post_mask, dv, dtype=torch.uint8)
+    T, n, Sp = test_xs.shape[0], X.shape[0], p.numel()
+    if P.dim() != 3 or P.shape[0] != Sp or P.shape[1] != T:
+        raise ValueError("post_samples must be (Sp,T,K)")
+    K = P.shape[2]
+    if tuple(mask.shape) != (Sp, K):
+        raise ValueError("post_mask must be (Sp,K)")
+    l = _l(l, d, dv)
+    zt = None
+    if z is not None:
+        zt = dev(z, dv)
+        want = (niter, nysample, Sp, nx, K, q)
+        if zt.numel() != niter * nysample * Sp * nx * K * q:
+            raise ValueError("z must have shape %s" % (want,))
+    L = _lib.lib()
+    need = L.tes_sp_acq_workspace_bytes(nx, q, T, n, d, Sp, K)
+    if need < 0:
+        raise ValueError("invalid sizes for tes_sp_acq_f64")
+    ws = WORKSPACE.get(need, dv)
+    acq = torch.empty((nx,), dtype=torch.float64, device=dv)
+    rc = L.tes_sp_acq_f64(ptr(x), nx, q, d, ptr(test_xs), T, ptr(X), n, ptr(Y), ptr(l), float(sigma), float(sigma0),
+                          ptr(invpNK), ptr(p), Sp, ptr(P), ptr(mask), K, int(niter), int(nysample), ptr(zt),
+                          int(seed), int(nx if n_global is None else n_global), int(x_offset), ptr(acq), ptr(ws),
+                          ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_sp_acq_f64")
+    return acq
+
+
+def batch_ep_acq(p, nx):
+    p = dev(p).reshape(-1)
+    out = torch.empty((nx,), dtype=torch.float64, device=p.device)
+    rc = _lib.lib().tes_batch_ep_acq_f64(ptr(p), p.numel(), nx, ptr(out), stream_ptr())
+    _lib.check(rc, "tes_batch_ep_acq_f64")
+    return out
