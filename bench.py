@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- TES acquisition throughput on B200 (BASELINE.json metric: acq evals/s,
+1 eval = one (candidate, maximizer-sample) pair).
+
+A "step" is ONE full acquisition step (stages A-D of SURVEY.md section 8) over one batch of synthetic
+input.  Default workload = config C3 of BASELINE.json (the largest single-GPU configuration):
+Hartmann-6 hyper-parameters, 10^6 candidates per GPU (rank 0: the 10^6-point mesh; other ranks:
+seeded uniform candidates), S = 1024 RFF function samples with F = 1024 features each, n = 64
+observations, TES_ep (criterion ftl, mode empirical, deterministic) on the <= t_max most frequent
+trusted maximizers.  theta/W/b are host-supplied draws (optfunc.py:303-385), inputs of the step.
+
+  value    evals/s with every input already resident in HBM (device-timed, max over ranks)
+  e2e      the same step through the reference-facing Python API with HOST (pinned) buffers: H2D copies
+           of candidates / observations / RFF weights and the D2H read of the result are inside the
+           timed region
+  roofline the dominant kernel (rff_topk, fp64-pipe bound) against the in-run measured DFMA peak
+  cpu_baseline / --impl reference: the CPU oracle port of the same step on the box's host cores, on a
+           bounded sub-sample of the same workload
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c4s]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HART6 = dict(l=np.array([6.9512, 1.9341, 0.506, 4.2067, 5.0986, 3.5949]), sigma=1.423, sigma0=1e-4)  # functions.py:540-543
+
+
+def hartmann6(x):
+    """functions.negative_rescaled_hartmann6d (functions.py:500-545), restated for the harness."""
+    A = np.array([[10., 3., 17., 3.5, 1.7, 8.], [0.05, 10., 17., 0.1, 8., 14.], [3., 3.5, 1.7, 10., 17., 8.],
+                  [17., 8., 0.05, 10., 0.1, 14.]])
+    alpha = np.array([1., 1.2, 3., 3.2])
+    P = 1e-4 * np.array([[1312., 1696., 5569., 124., 8283., 5886.], [2329., 4135., 8307., 3736., 1004., 9991.],
+                         [2348., 1451., 3522., 2883., 3047., 6650.], [4047., 8828., 8732., 5743., 1091., 381.]])
+    x = x.reshape(-1, 1, 6)
+    return (2.58 + np.sum(alpha * np.exp(-np.sum(A * (x - P) ** 2, axis=2)), axis=1)) / 1.94
+
+
+def meshgrid(xmin, xmax, nx, xdim):
+    """functions.get_meshgrid (functions.py:135-141)."""
+    x1d = np.linspace(xmin, xmax, nx)
+    xds = np.meshgrid(*([x1d] * xdim))
+    return np.concatenate([xd.reshape(-1, 1) for xd in xds], axis=1)
+
+
+WORKLOADS = {
+    # name: (description, d, N per GPU, S, F, n, t_max)
+    "c3": ("C3 Hartmann-6 TES_ep empirical, 1M candidates x 1024 maximizer samples per GPU", 6, 10 ** 6, 1024, 1024, 64, 128),
+    "c3s": ("C3 shapes scaled down (smoke)", 6, 50_000, 128, 256, 32, 32),
+    "c2": ("C2 Brooms-Barn-like 2-D 20x20 grid TES_ep, S=32 (latency case)", 2, 400, 32, 300, 12, 32),
+}
+
+
+def make_workload(name, rank, world):
+    desc, d, N, S, F, n, t_max = WORKLOADS[name]
+    from tes_b200 import optfunc
+    hyp = HART6 if d == 6 else dict(l=np.array([177.9418631280815, 309.4630784148164]), sigma=0.29444226420446995,
+                                    sigma0=0.06476473751595126)
+    rs = np.random.RandomState(1)
+    X = rs.rand(n, d)
+    if d == 6:
+        f = hartmann6(X)
+        Y = (f - f.mean()).reshape(-1, 1)
+    else:
+        Y = rs.randn(n, 1) * 0.5
+    if rank == 0 and d == 6 and N == 10 ** 6:
+        cand = meshgrid(0.0, 1.0, 10, 6)
+    elif d == 2 and N == 400:
+        cand = meshgrid(0.0, 1.0, 20, 2)
+    else:
+        cand = np.random.RandomState(7 + rank).rand(N, d)
+    np.random.seed(11)  # identical draws on every rank
+    theta, W, b = optfunc.draw_random_init_weights_features_np(d, S, F, X, Y, hyp["l"].reshape(1, d), hyp["sigma"],
+                                                              hyp["sigma0"])
+    return dict(name=name, desc=desc, d=d, N=N, S=S, F=F, n=n, t_max=t_max, hyp=hyp, X=X, Y=Y,
+                cand=np.ascontiguousarray(cand), theta=np.ascontiguousarray(theta.reshape(S, F)),
+                W=np.ascontiguousarray(W), b=np.ascontiguousarray(b.reshape(S, F)))
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_step(wl, n_cand, n_samp, seed=0):
+    """The CPU oracle port of one step on a bounded sub-sample: first n_cand candidates x first n_samp
+    function samples of the same workload (stage A: oracle/tes_oracle.c with OpenMP on every host core;
+    stages B-D: numpy oracle with BLAS threads).  Returns (pairs, seconds, info)."""
+    from oracle import pipeline_np
+    cand = wl["cand"][:n_cand]
+    t0 = time.perf_counter()
+    out = pipeline_np.tes_step(cand, wl["X"], wl["Y"], wl["hyp"]["l"], wl["hyp"]["sigma"], wl["hyp"]["sigma0"],
+                               wl["theta"][:n_samp].reshape(n_samp, wl["F"], 1), wl["W"][:n_samp],
+                               wl["b"][:n_samp].reshape(n_samp, wl["F"], 1), criterion="ftl", mode="empirical",
+                               deterministic=True, ntestsample=max(1000, 64 * min(wl["t_max"], n_samp)),
+                               seed=seed, t_max=wl["t_max"])
+    dt = time.perf_counter() - t0
+    return cand.shape[0] * n_samp, dt, out
+
+
+def cpu_sample_sizes(wl):
+    # ~10-30 s of CPU work on a few cores: F*(d+13) fp64 ops per pair at ~1e8 feature-evals/s/core
+    if wl["name"] == "c3":
+        return 16384, 128
+    return min(wl["N"], 4096), min(wl["S"], 64)
+
+
+def run_reference_arm(args, wl, rank):
+    if rank != 0:
+        return
+    nc, ns = cpu_sample_sizes(wl)
+    cores = os.cpu_count()
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_step(wl, nc, ns)
+    times, pairs = [], 0
+    for s in range(args.steps):
+        pairs, dt, info = cpu_step(wl, nc, ns, seed=s)
+        times.append(dt)
+    tmean = float(np.mean(times))
+    val = pairs / tmean
+    sample = "first %d candidates x first %d function samples of %s (F=%d, n=%d), full step A-D" % (
+        nc, ns, wl["name"], wl["F"], wl["n"])
+    line = {
+        "impl": "reference", "metric": "acq evals/s (candidates x maximizer samples)", "value": val, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tmean * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "criterion": "ftl", "mode": "empirical", "deterministic": True,
+                   "N_per_gpu": wl["N"], "S": wl["S"], "F": wl["F"], "n_obs": wl["n"], "d": wl["d"],
+                   "t_max": wl["t_max"]},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        wl = make_workload(args.workload, 0, 1) if rank == 0 else None
+        run_reference_arm(args, wl, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tes_b200 import _lib, acquisition, ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = make_workload(args.workload, rank, world)
+    hyp = wl["hyp"]
+    kw = dict(criterion="ftl", mode="empirical", deterministic=True, ntestsample=max(1000, 64 * wl["t_max"]),
+              t_max=wl["t_max"])
+    shard = acquisition.Shard(wl["N"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident inputs (for `value`) and pinned host inputs (for `e2e`)
+    names = ["cand", "X", "Y", "theta", "W", "b"]
+    host = {k: torch.from_numpy(wl[k]).pin_memory() for k in names}
+    devt = {k: host[k].cuda(non_blocking=True) for k in names}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    h2d_bytes = sum(host[k].numel() * 8 for k in names)
+
+    def step_device(seed, timers=None):
+        return acquisition.tes_step(devt["cand"], devt["X"], devt["Y"], hyp["l"], hyp["sigma"], hyp["sigma0"],
+                                    devt["theta"], devt["W"], devt["b"], seed=seed, shard=shard, timers=timers, **kw)
+
+    def step_e2e(seed):
+        d_ = {k: host[k].cuda(non_blocking=True) for k in names}  # pinned host -> device, every step
+        out = acquisition.tes_step(d_["cand"], d_["X"], d_["Y"], hyp["l"], hyp["sigma"], hyp["sigma0"], d_["theta"],
+                                   d_["W"], d_["b"], seed=seed, shard=shard, **kw)
+        _ = out["argmax_idx"].cpu()  # D2H: the S trusted-maximizer indices (+ query idx/value/point already on host)
+        return out
+
+    # ---- fp64 pipe peak (roofline denominator; not in MEASURED_PEAKS.json)
+    fp64_peak = ops.fp64_fma_peak(1.0)
+
+    for w in range(args.warmup):
+        flush.zero_()
+        out = step_device(w)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    timers = {}
+    launches0 = _lib.lib().tes_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush_ms = 0.0
+    barrier()
+    e0.record()
+    for s in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (its ~0.05 ms is inside the timed region)
+        out = step_device(1000 + s, timers)
+    e1.record()
+    barrier()
+    launches = _lib.lib().tes_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    dev_s = e0.elapsed_time(e1) * 1e-3
+    tt = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_s = float(tt[0])
+    pairs_step = shard.n_global * wl["S"]
+    value = pairs_step * args.steps / dev_s
+
+    # ---- e2e with host buffers
+    step_e2e(0)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for s in range(args.steps):
+        flush.zero_()
+        out2 = step_e2e(2000 + s)
+    e1.record()
+    barrier()
+    e2e_s = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0)
+    tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_s = float(tt[0])
+    e2e_val = pairs_step * args.steps / e2e_s
+    d2h_bytes = wl["S"] * 8 + 8 + 8 + wl["d"] * 8
+
+    # ---- roofline of the dominant kernel (stage A: rff_pack + rff_topk + merge), CUDA events per launch
+    ra = [a.elapsed_time(b_) * 1e-3 for a, b_ in timers.get("rff_topk", [])]
+    rc = [a.elapsed_time(b_) * 1e-3 for a, b_ in timers.get("criterion", [])]
+    t_rff = float(np.mean(ra)) if ra else float("nan")
+    d, F = wl["d"], wl["F"]
+    local_pairs = wl["N"] * wl["S"]
+    instr = local_pairs * F * (d + 13)           # fp64-pipe instructions per launch (tes_spec.h sequence)
+    achieved = 2.0 * instr / t_rff * 1e-12       # FMA-equivalent TFLOP/s, same convention as the DFMA burn
+    algo_excl_cos = local_pairs * F * (2 * d + 3) / t_rff * 1e-12  # SURVEY 8(d) figure, cos not counted
+    roofline = {"bound": "fp64", "kernel": "rff_topk_kernel", "achieved": achieved, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                "peak_source": "measured in this run: tes_fp64_fma_burn (8 DFMA chains/thread, 1 s sustained)",
+                "algorithmic_excl_cos_tflops": algo_excl_cos,
+                "per_unit": "F*(d+13) fp64-pipe instr per (candidate, sample) pair = F*(2d+3) flops + F cos (12 instr)",
+                "launch_ms": t_rff * 1e3, "share_of_step": t_rff * args.steps / dev_s,
+                "criterion_ms": float(np.mean(rc)) * 1e3 if rc else None}
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "acq evals/s (candidates x maximizer samples)", "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "criterion": "ftl", "mode": "empirical", "deterministic": True,
+                       "N_per_gpu": wl["N"], "S": wl["S"], "F": wl["F"], "n_obs": wl["n"], "d": wl["d"],
+                       "t_max": wl["t_max"], "T": out.get("T"), "Sp": out.get("Sp"),
+                       "n_unique_maximizers": out.get("n_unique_maximizers"),
+                       "l2": "flushed between timed iterations (256 MiB memset)",
+                       "sharding": "candidates contiguous per rank; NCCL all-gather of (value,index) partials only"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+        }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        nc, ns = cpu_sample_sizes(wl)
+        pairs, dt, info = cpu_step(wl, nc, ns)
+        line["cpu_baseline"] = {"value": pairs / dt, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": "first %d candidates x first %d function samples, full step A-D, %.1f s"
+                                          % (nc, ns, dt)}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

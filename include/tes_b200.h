@@ -161,6 +161,9 @@ int tes_batch_ep_acq_f64(const double* p, int64_t Sp, int64_t nx, double* out_ac
  * kernels (MEASURED_PEAKS.json carries only HBM and bf16 numbers).  Runs `iters` dependent-chain
  * DFMA rounds on `blocks` CTAs; returns the flop count through *flops; time it with CUDA events on
  * `stream`.  `sink` is a device buffer of at least blocks*256 doubles. */
+/* number of kernels this library has launched in this process so far (monotonic statistic) */
+int64_t tes_launch_count(void);
+
 int tes_fp64_fma_burn(int blocks, int64_t iters, double* sink, double* flops, void* stream);
 
 #ifdef __cplusplus

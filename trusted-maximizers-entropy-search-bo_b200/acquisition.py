@@ -1,0 +1,168 @@
+"""One TES acquisition step, end to end -- the sequence the reference's drivers run per BO iteration
+(bo_discrete.py:504-647 `get_placeholder_values` + :1032-1055; bo_batch.py:550-767 + :994-1061):
+
+  A  evaluate the S RFF posterior function samples on the candidate set, take each sample's arg-max
+     (the trusted maximizers), de-duplicate them                      utils_for_continuous.py:172-187, utils.py:1576
+  B  GP posterior mean/cov at the maximizers, invpNK                   utils.py:786-815, evaluate_mp.py:12-53
+  C  joint samples -> arg-max buckets -> max_probs and per-maximizer sample / empirical / EP statistics
+                                                                      utils.py:1733-1833 (host numpy, as in the reference)
+  D  the TES criterion on every candidate and its arg-max              criteria/*.py, bo_discrete.py:794-807
+
+Candidates may be sharded across ranks (one process per GPU, torch.distributed): each rank holds a
+contiguous slice; only the per-sample (value, index) partials of stage A and one (value, index) pair
+per rank of stage D cross NVLink (NCCL all-gather); results are independent of the number of ranks.
+"""
+import numpy as np
+import torch
+
+from . import ops, utils
+from .device import dev
+
+
+class _Timed:
+    """Records a CUDA-event pair around a region into timers[name] (no-op when timers is None)."""
+
+    def __init__(self, timers, name):
+        self.timers, self.name = timers, name
+
+    def __enter__(self):
+        if self.timers is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.timers is not None:
+            self.e1.record()
+            self.timers.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
+
+class Shard:
+    """Describes this rank's contiguous slice of the global candidate set."""
+
+    def __init__(self, n_local, group=None):
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = group
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        if self.world > 1:
+            counts = torch.zeros(self.world, dtype=torch.int64, device="cuda")
+            counts[self.rank] = n_local
+            self.dist.all_reduce(counts, group=group)
+            c = counts.cpu().numpy()
+            self.offset = int(c[:self.rank].sum())
+            self.n_global = int(c.sum())
+        else:
+            self.offset, self.n_global = 0, int(n_local)
+
+    def all_gather(self, t):
+        if self.world == 1:
+            return t.unsqueeze(0)
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def sum(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, group=self.group)
+        return t
+
+
+def trusted_maximizers(cand, W, b, theta, sigma, shard=None, k=1, timers=None):
+    """Stage A.  Returns (idx (S,k) global indices, val (S,k), pts (S,k,d) coordinates)."""
+    cand = dev(cand)
+    shard = shard or Shard(cand.shape[0])
+    with _Timed(timers, "rff_topk"):
+        idx, val = ops.rff_topk(cand, W, b, theta, sigma, k=k, idx_offset=shard.offset)
+    if shard.world > 1:
+        idx, val = ops.topk_merge(shard.all_gather(val), shard.all_gather(idx))
+    local = idx - shard.offset
+    mine = (local >= 0) & (local < cand.shape[0]) & (idx >= 0)
+    pts = torch.zeros(idx.shape + (cand.shape[1],), dtype=torch.float64, device=cand.device)
+    pts[mine] = cand[local[mine]]
+    pts = shard.sum(pts)  # every winner is owned by exactly one rank
+    return idx, val, pts
+
+
+def select_test_points(max_xs, resolution=1e-3, t_max=None):
+    """De-duplicate the maximizers at `resolution` (bo.py:830-836, bo_discrete.py:553) keeping first
+    occurrences; optionally keep only the `t_max` most frequent ones (ties -> earlier), in original order."""
+    xs = max_xs.cpu().numpy() if torch.is_tensor(max_xs) else np.asarray(max_xs)
+    uniq = utils.remove_duplicates_np(xs, resolution=resolution)
+    if t_max is not None and uniq.shape[0] > t_max:
+        d = np.sqrt(((xs[:, None, :] - uniq[None, :, :]) ** 2).sum(-1))
+        owner = np.argmax(d <= resolution, axis=1)
+        counts = np.bincount(owner, minlength=uniq.shape[0])
+        order = np.lexsort((np.arange(uniq.shape[0]), -counts))[:t_max]
+        uniq = uniq[np.sort(order)]
+    return uniq
+
+
+def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="empirical", deterministic=True,
+             ntestsample=1000, n_min_sample=2, nysample=10, niteration=10, z_joint=None, z=None, seed=0,
+             duplicate_resolution=1e-3, t_max=None, shard=None, return_acq=False, timers=None):
+    """One acquisition step for one hyper-parameter sample.  Returns a dict with the query index /
+    point / value and the intermediate sizes.  `criterion`: 'ftl' (TES_ep) or 'sftl' (TES_sp)."""
+    from .criteria import evaluate_mp, evaluate_sample_mp
+    cand = dev(cand)
+    N, d = cand.shape
+    shard = shard or Shard(N)
+    Xd, Yd = dev(X), dev(Y).reshape(-1, 1)
+    n = Xd.shape[0]
+    ls, sigmas, sigma0s = np.asarray(l, dtype=np.float64).reshape(1, d), np.array([sigma]), np.array([sigma0])
+    # ---- A
+    idx, val, pts = trusted_maximizers(cand, W, b, theta, sigma, shard, k=1, timers=timers)
+    test_xs = select_test_points(pts[:, 0], duplicate_resolution, t_max)
+    out = {"n_unique_maximizers": int(test_xs.shape[0]), "argmax_idx": idx[:, 0], "argmax_val": val[:, 0]}
+    if test_xs.shape[0] == 1:  # bo_discrete.py:557-559: a single maximizer is queried directly
+        out.update(query_x=test_xs[0], query_idx=int(idx[0, 0]), query_val=float("nan"), T=1, Sp=1)
+        return out
+    # ---- B
+    invK = utils.precomputeInvKs(d, 1, ls, sigmas, sigma0s, Xd)
+    mean_t, cov_t = utils.compute_mean_var_f(dev(test_xs), Xd, Yd, ls[0], sigma, sigma0, invK[0], fullcov=True)
+    # ---- C (host, replicated on every rank with identical draws)
+    T0 = test_xs.shape[0]
+    if z_joint is None:
+        z_joint = np.random.RandomState(seed).normal(size=(1, ntestsample, T0, 1))
+    st_mode = "sample" if criterion == "sftl" else mode
+    test_k, max_probs, mean_k, cov_k, v0, v1 = utils.get_testidxs_stats(
+        1, test_xs, mean_t.reshape(1, T0).cpu().numpy(), cov_t.reshape(1, T0, T0).cpu().numpy(), mode=st_mode,
+        nsample=ntestsample, n_min_sample=n_min_sample, z=z_joint)
+    out.update(T=int(test_k.shape[0]), Sp=int((max_probs[0] > 0).sum()))
+    if test_k.shape[0] == 1:
+        out.update(query_x=test_k[0], query_idx=-1, query_val=float("nan"))
+        return out
+    _, invpNK = evaluate_mp.get_pNK_test_obs(ls, sigmas, sigma0s, 1, Xd, dev(test_k))
+    # ---- D
+    tm = _Timed(timers, "criterion")
+    tm.__enter__()
+    if criterion == "ftl":
+        acq = evaluate_mp.mp(cand, ls, sigmas, sigma0s, Xd, Yd, d, N, n, 1, nysample, dev(test_k), dev(max_probs),
+                             dev(v0), dev(v1), invK, invpNK, stochastic=not deterministic, niteration=niteration,
+                             z=z, seed=seed, n_global=shard.n_global, x_offset=shard.offset)
+    elif criterion == "sftl":
+        out["K"] = int(v0.shape[-1])
+        acq = evaluate_sample_mp.mp(cand, ls, sigmas, sigma0s, Xd, Yd, d, N, n, 1, nysample, dev(test_k),
+                                    dev(max_probs), dev(v0), v1, invpNK, niteration=niteration, z=z, seed=seed,
+                                    n_global=shard.n_global, x_offset=shard.offset)
+    else:
+        raise ValueError("criterion must be 'ftl' or 'sftl'")
+    tm.__exit__()
+    # arg-max over all candidates, first maximum wins (bo_discrete.py:806, :1053-1055)
+    lv, li = torch.max(acq, dim=0)
+    pair_v = shard.all_gather(lv.reshape(1))
+    pair_i = shard.all_gather((li + shard.offset).reshape(1))
+    qi, qv = ops.topk_merge(pair_v.reshape(-1, 1, 1), pair_i.reshape(-1, 1, 1))
+    qidx = int(qi[0, 0])
+    loc = qidx - shard.offset
+    qx = torch.zeros(d, dtype=torch.float64, device=cand.device)
+    if 0 <= loc < N:
+        qx = cand[loc].clone()
+    qx = shard.sum(qx)
+    out.update(query_idx=qidx, query_val=float(qv[0, 0]), query_x=qx.cpu().numpy())
+    if return_acq:
+        out["acq"] = acq
+    return out

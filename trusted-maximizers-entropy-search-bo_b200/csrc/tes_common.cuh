@@ -13,10 +13,14 @@
         if (e__ != cudaSuccess) return (int)e__;   \
     } while (0)
 
+// every kernel launch of the library is followed by TES_LAUNCH_OK(): it checks the launch and bumps
+// the process-wide launch counter (a statistic, read by tes_launch_count(); not program state)
+extern "C" void tes_count_launch_(void);
 #define TES_LAUNCH_OK()                                  \
     do {                                                 \
         cudaError_t e__ = cudaGetLastError();            \
         if (e__ != cudaSuccess) return (int)e__;         \
+        tes_count_launch_();                             \
     } while (0)
 
 

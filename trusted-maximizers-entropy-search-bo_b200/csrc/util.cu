@@ -1,6 +1,11 @@
 // util.cu -- ABI version, error strings and the fp64-FMA burn used as the roofline denominator.
 #include "tes_common.cuh"
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+extern "C" void tes_count_launch_(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" int64_t tes_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
 extern "C" int tes_abi_version(void) { return TES_B200_ABI_VERSION; }
 
 extern "C" const char* tes_error_string(int code) {

@@ -1,0 +1,228 @@
+"""Mirror of the reference's utils.py for the TES hot path (same function names and argument
+meaning), backed by the CUDA kernels of libtes_b200.
+
+Device work (SE-ARD kernels, Cholesky inverses, posteriors) goes through the C ABI.  The
+trusted-maximizer bookkeeping of utils.py:1554-1833 is host-side numpy in the reference as well
+(it runs between two sess.run calls); it is restated here with the random draw made injectable.
+Arrays may be numpy or torch; numpy in -> numpy out.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .device import dev
+
+clip_min = 1e-100  # utils.py:11
+
+
+def _ret(t, like):
+    return t.cpu().numpy() if isinstance(like, np.ndarray) else t
+
+
+# ---- kernels / posteriors ------------------------------------------------------------------------
+def computeKnm(X, Xbar, l, sigma, dtype=None):
+    """utils.py:703-719."""
+    return _ret(ops.se_ard_cross(X, Xbar, np.asarray(l).reshape(-1) if not torch.is_tensor(l) else l.reshape(-1),
+                                 float(sigma)), X)
+
+
+computeKnm_np = computeKnm  # utils.py:836-859
+
+
+def computeKmm(X, l, sigma, nd=2, dtype=None):
+    """utils.py:740-762 (nd == 2) -- Gram matrix."""
+    Xt = dev(X)
+    if Xt.dim() != 2:
+        return _ret(torch.stack([ops.se_ard_cross(x, x, l, float(sigma)) for x in Xt.reshape(-1, *Xt.shape[-2:])])
+                    .reshape(*Xt.shape[:-1], Xt.shape[-2]), X)
+    return _ret(ops.se_ard_cross(Xt, Xt, l, float(sigma)), X)
+
+
+computeKmm_np = computeKmm  # utils.py:818-833
+
+
+def computeNKmm(X, l, sigma, sigma0, dtype=None):
+    """utils.py:765-783 (no jitter)."""
+    Xt = dev(X)
+    K = ops.se_ard_cross(Xt, Xt, l, float(sigma))
+    K.diagonal().add_(float(sigma0))
+    return _ret(K, X)
+
+
+def chol2inv(mat, dtype=None):
+    """utils.py:657-674."""
+    return _ret(ops.batched_chol2inv(mat), mat)
+
+
+def multichol2inv(mat, n_mat=None, dtype=None):
+    """utils.py:677-700."""
+    return _ret(ops.batched_chol2inv(mat), mat)
+
+
+def precomputeInvKs(xdim, nhyp, ls, sigmas, sigma0s, Xsamples, dtype=None):
+    """utils.py:1838-1856 -> (nhyp, nobs, nobs)."""
+    ls_, sg, s0 = np.asarray(_np(ls)).reshape(nhyp, xdim), _np(sigmas).reshape(-1), _np(sigma0s).reshape(-1)
+    mats = torch.stack([dev(computeNKmm(dev(Xsamples), ls_[i], sg[i], s0[i])) for i in range(nhyp)])
+    return _ret(ops.batched_chol2inv(mats), Xsamples)
+
+
+def eval_invKmaxsams(xdim, nhyp, nmax, ls, sigmas, sigma0s, Xsamples, maxima, dtype=None):
+    """utils.py:1859-1883: one (n+1)x(n+1) inverse per maximizer, batched on the device."""
+    ls_, sg, s0 = np.asarray(_np(ls)).reshape(nhyp, xdim), _np(sigmas).reshape(-1), _np(sigma0s).reshape(-1)
+    Xs = dev(Xsamples)
+    mx = dev(maxima).reshape(nhyp, nmax, xdim)
+    out = []
+    for i in range(nhyp):
+        stack = torch.stack([dev(computeNKmm(torch.cat([mx[i, j:j + 1], Xs], 0), ls_[i], sg[i], s0[i]))
+                             for j in range(nmax)])
+        out.append(ops.batched_chol2inv(stack))
+    return _ret(torch.stack(out), Xsamples)
+
+
+def compute_mean_var_f(x, Xsamples, Ysamples, l, sigma, sigma0, NKInv=None, fullcov=False, dtype=None):
+    """utils.py:786-815."""
+    xt, Xs = dev(x), dev(Xsamples)
+    if NKInv is None:
+        NKInv = ops.batched_chol2inv(dev(computeNKmm(Xs, l, sigma, sigma0)))
+    NKInv = dev(NKInv)
+    if not fullcov:
+        mean, var = ops.gp_mean_var(xt, Xs, Ysamples, l, float(sigma), NKInv)
+        return _ret(mean, x), _ret(var, x)
+    kstar = ops.se_ard_cross(xt, Xs, l, float(sigma))
+    mean = ops.gemm(kstar, ops.gemm(NKInv, dev(Ysamples).reshape(-1, 1))).reshape(-1)
+    var = ops.se_ard_cross(xt, xt, l, float(sigma)) - ops.gemm(ops.gemm(kstar, NKInv), kstar, transb=True)
+    var.diagonal().clamp_(min=clip_min)
+    return _ret(mean, x), _ret(var, x)
+
+
+def compute_mean_f(x, xdim, n_hyp, Xsamples, Ysamples, ls, sigmas, sigma0s, NKInvs, dtype=None):
+    """utils.py:982-1009."""
+    ls_, sg = np.asarray(_np(ls)).reshape(n_hyp, xdim), _np(sigmas).reshape(-1)
+    acc = 0.0
+    for i in range(n_hyp):
+        mean, _ = ops.gp_mean_var(x, Xsamples, Ysamples, ls_[i], float(sg[i]), dev(NKInvs)[i])
+        acc = acc + mean / n_hyp
+    return _ret(acc, x)
+
+
+def evaluate_norm_entropy(s, dtype=None):
+    """utils.py:653-654."""
+    if torch.is_tensor(s):
+        return 0.5 * np.log(2 * np.pi) + torch.log(s) + 0.5
+    return 0.5 * np.log(2 * np.pi) + np.log(s) + 0.5
+
+
+def _np(a):
+    return a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+
+
+# ---- trusted-maximizer statistics (host side in the reference too) ---------------------------------
+def get_duplicate_mask_np(xs, resolution=1e-5):
+    """utils.py:1554-1573 (first occurrence wins), vectorised row by row."""
+    xs = _np(xs)
+    n = xs.shape[0]
+    mask = np.zeros(n)
+    for i in range(n):
+        if mask[i] == 1.0:
+            continue
+        d = np.sqrt(np.sum((xs[i + 1:] - xs[i]) ** 2, axis=1))
+        mask[i + 1:][d <= resolution] = 1.0
+    return mask
+
+
+def remove_duplicates_np(xs, resolution=1e-5):
+    """utils.py:1576-1581."""
+    xs = _np(xs)
+    return np.delete(xs, np.where(get_duplicate_mask_np(xs, resolution) == 1.0)[0], axis=0)
+
+
+def sample_multivariate_normal_maxidx_np(mean, cov, nsample, n_min_sample=1, get_sample=True,
+                                         remove_correlated_dims=True, z=None):
+    """utils.py:1654-1729.  `z` (nsample, n, 1) replaces the np.random.normal draw of :1674; when
+    omitted the global numpy RNG is used exactly as the reference does."""
+    mean, cov = _np(mean), _np(cov)
+    n = cov.shape[0]
+    mean = mean.reshape(n)
+    e, v = np.linalg.eig(cov)
+    A = v.dot(np.diag(np.sqrt(np.clip(e, 0.0, np.inf))))
+    if z is None:
+        z = np.random.normal(size=(nsample, n, 1))
+    samples = np.mean(mean.reshape(1, n) + np.matmul(A[None], _np(z)), axis=-1)
+    corr_idxs = []
+    if remove_correlated_dims:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            rows, _ = np.where(np.tril(np.corrcoef(samples.T), k=-1) > 1 - 1e-6)
+        corr_idxs = rows
+    masked = samples.copy()
+    masked[:, corr_idxs] = -np.inf
+    maxidxs = np.argmax(masked, axis=1)
+    counts = np.bincount(maxidxs, minlength=n)
+    unique = np.where(counts >= max(n_min_sample, 1))[0]
+    sizes = counts[unique]
+    if not get_sample:
+        return unique, sizes
+    K = int(sizes.max())
+    nmax = len(unique)
+    ret = np.tile(mean.reshape(1, n, 1), (nmax, 1, K))  # padded slots hold the prior mean (:1722)
+    masks = np.zeros([nmax, K], dtype=int)
+    order = np.argsort(maxidxs, kind="stable")
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    for i, mi in enumerate(unique):
+        rows_i = order[starts[mi]:starts[mi + 1]]
+        ret[i, :, :sizes[i]] = samples[rows_i].T
+        masks[i, :sizes[i]] = 1
+    return nmax, unique, K, ret, masks, sizes
+
+
+def get_testidxs_stats(nhyp, test_xs_np, test_means, test_covs, mode="sample", nsample=1000, n_min_sample=2,
+                       z=None):
+    """utils.py:1733-1833.  mode in {'sample','empirical','ep'}; `z` (nhyp, nsample, ntest, 1) optional.
+    mode='ep' runs the EP the reference intends at :1820-1825 (its shipped code raises NameError)."""
+    from . import empirical_approximation, ep
+    test_xs_np, test_means, test_covs = _np(test_xs_np), _np(test_means), _np(test_covs)
+    ntest = test_xs_np.shape[0]
+    alive = np.ones(ntest, dtype=bool)
+    max_probs = np.ones([nhyp, ntest]) / ntest
+    K_all = 0
+    per_hyp = []
+    for i in range(nhyp):
+        nmax, uniq, K, rs, rm, sizes = sample_multivariate_normal_maxidx_np(
+            test_means[i], test_covs[i], nsample, n_min_sample, z=None if z is None else z[i])
+        K_all = max(K_all, K)
+        won = np.zeros(ntest, dtype=bool)
+        won[uniq] = True
+        alive &= won
+        max_probs[i, uniq] = sizes / np.sum(sizes)
+        per_hyp.append((uniq, K, rs, rm))
+    post_samples = np.zeros([nhyp, ntest, ntest, K_all])
+    post_masks = np.zeros([nhyp, ntest, K_all], dtype=bool)
+    for i, (uniq, K, rs, rm) in enumerate(per_hyp):
+        post_samples[i, uniq, :, :K] = rs
+        post_masks[i, uniq, :K] = rm.astype(bool)
+    keep = np.where(alive)[0]
+    if len(keep) != ntest:
+        test_xs_np = test_xs_np[keep]
+        test_means = test_means[:, keep]
+        test_covs = test_covs[:, keep][:, :, keep]
+        max_probs = max_probs[:, keep]
+        post_samples = post_samples[:, keep][:, :, keep]
+        post_masks = post_masks[:, keep]
+    max_probs = max_probs / np.sum(max_probs, axis=1, keepdims=True)
+    ntest = test_xs_np.shape[0]
+    if mode == "sample":
+        return test_xs_np, max_probs, test_means, test_covs, post_samples, post_masks
+    pm = np.zeros([nhyp, ntest, ntest])
+    pc = np.zeros([nhyp, ntest, ntest, ntest])
+    for i in range(nhyp):
+        if mode == "empirical":
+            m, c = empirical_approximation.batched_empirical_stats(post_samples[i], post_masks[i])
+            pm[i], pc[i] = m, c
+        elif mode == "ep":
+            for j in range(ntest):
+                m, c = ep.approximate_EP_np(j, test_means[i].reshape(-1, 1), test_covs[i], resolution=1e-9,
+                                            max_niter=100)
+                pm[i, j] = m.squeeze()
+                pc[i, j] = c
+        else:
+            raise Exception("Unknown mode in get_testidxs_stats!")
+    return test_xs_np, max_probs, test_means, test_covs, pm, pc
