@@ -58,6 +58,7 @@ WORKLOADS = {
     # name: (description, d, N per GPU, S, F, n, t_max)
     "c3": ("C3 Hartmann-6 TES_ep empirical, 1M candidates x 1024 maximizer samples per GPU", 6, 10 ** 6, 1024, 1024, 64, 128),
     "c3s": ("C3 shapes scaled down (smoke)", 6, 50_000, 128, 256, 32, 32),
+    "c3m": ("C3 shapes, mid size (profiling)", 6, 200_000, 256, 1024, 64, 64),
     "c2": ("C2 Brooms-Barn-like 2-D 20x20 grid TES_ep, S=32 (latency case)", 2, 400, 32, 300, 12, 32),
 }
 

@@ -21,7 +21,7 @@ def select_test_points(max_xs, resolution=1e-3, t_max=None):
 
 def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="empirical", deterministic=True,
              ntestsample=1000, n_min_sample=2, nysample=10, niteration=10, z_joint=None, z=None, seed=0,
-             duplicate_resolution=1e-3, t_max=None, return_acq=False):
+             duplicate_resolution=1e-3, t_max=None, return_acq=False, transform=None):
     N, d = cand.shape
     n = X.shape[0]
     Y = Y.reshape(-1, 1)
@@ -40,8 +40,8 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
     st_mode = "sample" if criterion == "sftl" else mode
     test_k, max_probs, mean_k, cov_k, v0, v1 = onp.get_testidxs_stats(
         1, test_xs, mean_t.reshape(1, T0), cov_t.reshape(1, T0, T0), mode=st_mode, nsample=ntestsample,
-        n_min_sample=n_min_sample, z=z_joint)
-    out.update(T=int(test_k.shape[0]), Sp=int((max_probs[0] > 0).sum()))
+        n_min_sample=n_min_sample, z=z_joint, transforms=None if transform is None else [transform])
+    out.update(T=int(test_k.shape[0]), Sp=int((max_probs[0] > 0).sum()), test_cov=cov_t)
     if test_k.shape[0] == 1:
         out.update(query_x=test_k[0], query_idx=-1, query_val=float("nan"))
         return out

@@ -103,7 +103,7 @@ def select_test_points(max_xs, resolution=1e-3, t_max=None):
 
 def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="empirical", deterministic=True,
              ntestsample=1000, n_min_sample=2, nysample=10, niteration=10, z_joint=None, z=None, seed=0,
-             duplicate_resolution=1e-3, t_max=None, shard=None, return_acq=False, timers=None):
+             duplicate_resolution=1e-3, t_max=None, shard=None, return_acq=False, timers=None, transform=None):
     """One acquisition step for one hyper-parameter sample.  Returns a dict with the query index /
     point / value and the intermediate sizes.  `criterion`: 'ftl' (TES_ep) or 'sftl' (TES_sp)."""
     from .criteria import evaluate_mp, evaluate_sample_mp
@@ -130,7 +130,8 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
     st_mode = "sample" if criterion == "sftl" else mode
     test_k, max_probs, mean_k, cov_k, v0, v1 = utils.get_testidxs_stats(
         1, test_xs, mean_t.reshape(1, T0).cpu().numpy(), cov_t.reshape(1, T0, T0).cpu().numpy(), mode=st_mode,
-        nsample=ntestsample, n_min_sample=n_min_sample, z=z_joint)
+        nsample=ntestsample, n_min_sample=n_min_sample, z=z_joint,
+        transforms=None if transform is None else [transform])
     out.update(T=int(test_k.shape[0]), Sp=int((max_probs[0] > 0).sum()))
     if test_k.shape[0] == 1:
         out.update(query_x=test_k[0], query_idx=-1, query_val=float("nan"))

@@ -136,15 +136,23 @@ def remove_duplicates_np(xs, resolution=1e-5):
     return np.delete(xs, np.where(get_duplicate_mask_np(xs, resolution) == 1.0)[0], axis=0)
 
 
+def mvn_transform_matrix(cov):
+    """utils.py:1668-1670: A = V diag(sqrt(clip(e, 0))) from a GENERAL eig of the symmetric cov.  Column
+    order and signs are LAPACK dgeev's and can change under 1e-13 perturbations of cov (near-degenerate
+    eigenvalues), so callers that need identical samples for identical z pass this factor explicitly."""
+    e, v = np.linalg.eig(_np(cov))
+    return v.dot(np.diag(np.sqrt(np.clip(e, 0.0, np.inf))))
+
+
 def sample_multivariate_normal_maxidx_np(mean, cov, nsample, n_min_sample=1, get_sample=True,
-                                         remove_correlated_dims=True, z=None):
+                                         remove_correlated_dims=True, z=None, transform=None):
     """utils.py:1654-1729.  `z` (nsample, n, 1) replaces the np.random.normal draw of :1674; when
-    omitted the global numpy RNG is used exactly as the reference does."""
+    omitted the global numpy RNG is used exactly as the reference does.  `transform` overrides the
+    colouring factor A (default: mvn_transform_matrix(cov), as the reference computes it)."""
     mean, cov = _np(mean), _np(cov)
     n = cov.shape[0]
     mean = mean.reshape(n)
-    e, v = np.linalg.eig(cov)
-    A = v.dot(np.diag(np.sqrt(np.clip(e, 0.0, np.inf))))
+    A = mvn_transform_matrix(cov) if transform is None else _np(transform)
     if z is None:
         z = np.random.normal(size=(nsample, n, 1))
     samples = np.mean(mean.reshape(1, n) + np.matmul(A[None], _np(z)), axis=-1)
@@ -175,7 +183,7 @@ def sample_multivariate_normal_maxidx_np(mean, cov, nsample, n_min_sample=1, get
 
 
 def get_testidxs_stats(nhyp, test_xs_np, test_means, test_covs, mode="sample", nsample=1000, n_min_sample=2,
-                       z=None):
+                       z=None, transforms=None):
     """utils.py:1733-1833.  mode in {'sample','empirical','ep'}; `z` (nhyp, nsample, ntest, 1) optional.
     mode='ep' runs the EP the reference intends at :1820-1825 (its shipped code raises NameError)."""
     from . import empirical_approximation, ep
@@ -187,7 +195,8 @@ def get_testidxs_stats(nhyp, test_xs_np, test_means, test_covs, mode="sample", n
     per_hyp = []
     for i in range(nhyp):
         nmax, uniq, K, rs, rm, sizes = sample_multivariate_normal_maxidx_np(
-            test_means[i], test_covs[i], nsample, n_min_sample, z=None if z is None else z[i])
+            test_means[i], test_covs[i], nsample, n_min_sample, z=None if z is None else z[i],
+            transform=None if transforms is None else transforms[i])
         K_all = max(K_all, K)
         won = np.zeros(ntest, dtype=bool)
         won[uniq] = True
