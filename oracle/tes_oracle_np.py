@@ -288,6 +288,9 @@ def sample_multivariate_normal_maxidx(mean, cov, nsample, n_min_sample=1, z=None
     n = cov.shape[0]
     mean = mean.reshape(n)
     A = mvn_transform_matrix(cov) if transform is None else transform
+    # NOTE (reference quirk Q11): mean.reshape(1,n) broadcasts against the (nsample,n,1) product to
+    # (nsample,n,n) and the mean over the LAST axis then adds average(mean) -- not mean[i] -- to every
+    # coordinate.  Restated literally.
     samples = np.mean(mean.reshape(1, n) + np.matmul(A[None], z), axis=-1)  # (nsample, n)
     corr_idxs = []
     if remove_correlated_dims:

@@ -69,7 +69,7 @@ struct AQuad {
     }
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
     quadform_kernel(const double* __restrict__ G, int64_t ldg, int64_t rows, int64_t T, const int2* __restrict__ table,
                     int64_t Kdim, const double* __restrict__ Bpack, int64_t Sp, const double* __restrict__ Kq,
                     double* __restrict__ var) {
@@ -566,6 +566,7 @@ extern "C" int tes_ep_acq_f64(int mode, const double* x, int64_t N, int64_t d, c
             dim3 grid((unsigned)((nc + GEMM_BM - 1) / GEMM_BM), (unsigned)((Sp + GEMM_BN - 1) / GEMM_BN));
             TES_CUDA_OK(cudaFuncSetAttribute(quadform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(GemmSmem)));
+            TES_CUDA_OK(cudaFuncSetAttribute(quadform_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             quadform_kernel<<<grid, GEMM_THREADS, sizeof(GemmSmem), st>>>(Gc, m + 1, nc, T, table, pl.Kdim, Bpack, Sp, Kq, var_dst);
             TES_LAUNCH_OK();
         }

@@ -129,7 +129,7 @@ __device__ __forceinline__ void gemm_body(const AProv& ap, const double* __restr
 }
 
 template <bool TRANSA>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
     gemm_kernel(GemmArgs g) {
     const int64_t bz = blockIdx.z;
     const double* A = g.A + bz * g.batchA;
@@ -150,10 +150,12 @@ int launch_gemm_ex(const GemmArgs& g, cudaStream_t st) {
     if (g.transa) {
         TES_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(GemmSmem)));
+        TES_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         gemm_kernel<true><<<grid, GEMM_THREADS, sizeof(GemmSmem), st>>>(g);
     } else {
         TES_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(GemmSmem)));
+        TES_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         gemm_kernel<false><<<grid, GEMM_THREADS, sizeof(GemmSmem), st>>>(g);
     }
     TES_LAUNCH_OK();

@@ -3,7 +3,7 @@
 #include "tes_common.cuh"
 
 namespace tes {
-constexpr int64_t PS_CHUNK = 16384;  // candidates per pass: K and G chunks stay L2-resident
+constexpr int64_t PS_CHUNK = 148 * 128;  // candidates per pass: one 128-row GEMM tile per SM; K and G chunks stay L2-resident
 
 int launch_se_ard(const double* x, int64_t N, const double* xb, int64_t m, int d, const double* l, double sigma,
                   int64_t noise_from, double sigma0, double* out, int64_t ldo, cudaStream_t st);

@@ -16,6 +16,9 @@
 //     instructions per (candidate, sample, feature);
 //   * at the end of a sample the CTA filters its C*256 values against the running k-th best
 //     (one __syncthreads_or); only improving tiles take the slow path (append + warp selection).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "tes_common.cuh"
 
 namespace tes {
@@ -81,13 +84,13 @@ __device__ __forceinline__ void warp_select_topk(const double* lv, const int64_t
     }
 }
 
-template <int D, int C>
-__global__ void __launch_bounds__(RFF_THREADS)
+template <int D, int C, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS)
     rff_topk_kernel(const double* __restrict__ cand, int64_t N, const double* __restrict__ feat, int S, int F,
                     double scale, int k, int sg, int64_t chunk, int64_t idx_offset, double* __restrict__ part_val,
                     int64_t* __restrict__ part_idx) {
     constexpr int REC = rff_rec(D);
-    constexpr int TILE = RFF_THREADS * C;
+    constexpr int TILE = THREADS * C;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage = reinterpret_cast<double*>(smem_raw);                       // [NSTAGE][FCH*REC]
     uint64_t* full = reinterpret_cast<uint64_t*>(stage + RFF_NSTAGE * RFF_FCH * REC);  // [NSTAGE] (+pad to 8)
@@ -108,10 +111,9 @@ __global__ void __launch_bounds__(RFF_THREADS)
     const int64_t c1 = min(N, c0 + chunk);
     const int ntiles = (int)((c1 - c0 + TILE - 1) / TILE);
     const int nch = (F + RFF_FCH - 1) / RFF_FCH;
-    const int per_tile = nj * nch;
-    const int64_t total = (int64_t)ntiles * per_tile;
+    const int64_t total = (int64_t)ntiles * nj * nch;
 
-    for (int e = tid; e < sg * k; e += RFF_THREADS) {
+    for (int e = tid; e < sg * k; e += THREADS) {
         tk_val[e] = neg_inf();
         tk_idx[e] = -1;
     }
@@ -122,33 +124,40 @@ __global__ void __launch_bounds__(RFF_THREADS)
     }
     __syncthreads();
 
-    // producer: thread 0 issues the bulk copy of stream element qq into ring slot qq % NSTAGE
-    auto issue = [&](int64_t qq) {
-        int q = (int)(qq % per_tile);
-        int jj = q / nch, c = q % nch;
-        int fcnt = min(RFF_FCH, F - c * RFF_FCH);
-        uint32_t bytes = (uint32_t)(fcnt * REC * sizeof(double));
-        int slot = (int)(qq % RFF_NSTAGE);
-        const double* src = feat + ((int64_t)(j0 + jj) * F + (int64_t)c * RFF_FCH) * REC;
-        mbar_expect_tx(&full[slot], bytes);
-        bulk_g2s(stage + slot * RFF_FCH * REC, src, bytes, &full[slot]);
+    // producer: thread 0 issues the bulk copy of the next stream element into the ring.  The stream
+    // (sample-major, then 128-feature chunk) repeats for every candidate tile; producer and consumer
+    // walk it with incremental counters (no 64-bit div/mod in the loop).
+    int p_jj = 0, p_c = 0, p_slot = 0;
+    int64_t p_left = total;
+    auto issue = [&]() {
+        const int fcnt = min(RFF_FCH, F - p_c * RFF_FCH);
+        const uint32_t bytes = (uint32_t)(fcnt * REC * sizeof(double));
+        const double* src = feat + ((int64_t)(j0 + p_jj) * F + (int64_t)p_c * RFF_FCH) * REC;
+        mbar_expect_tx(&full[p_slot], bytes);
+        bulk_g2s(stage + p_slot * RFF_FCH * REC, src, bytes, &full[p_slot]);
+        if (++p_c == nch) {
+            p_c = 0;
+            if (++p_jj == nj) p_jj = 0;
+        }
+        if (++p_slot == RFF_NSTAGE) p_slot = 0;
+        --p_left;
     };
     if (tid == 0) {
-        for (int64_t p = 0; p < RFF_NSTAGE - 1 && p < total; ++p) issue(p);
+        for (int p = 0; p < RFF_NSTAGE - 1 && p_left > 0; ++p) issue();
     }
 
     double x[C][D];
     double acc[C];
     int64_t ci[C];
+    int slot = 0;
+    uint32_t phase = 0;
 
-    for (int64_t qq = 0; qq < total; ++qq) {
-        const int q = (int)(qq % per_tile);
-        const int jj = q / nch, c = q % nch;
-        if (q == 0) {  // new candidate tile: load coordinates
-            const int64_t t0 = c0 + (qq / per_tile) * TILE;
+    for (int tile = 0; tile < ntiles; ++tile) {
+        {  // new candidate tile: load coordinates
+            const int64_t t0 = c0 + (int64_t)tile * TILE;
 #pragma unroll
             for (int cc = 0; cc < C; ++cc) {
-                ci[cc] = t0 + cc * RFF_THREADS + tid;
+                ci[cc] = t0 + cc * THREADS + tid;
                 if (ci[cc] < c1) {
 #pragma unroll
                     for (int kk = 0; kk < D; ++kk) x[cc][kk] = __ldg(cand + ci[cc] * D + kk);
@@ -158,36 +167,39 @@ __global__ void __launch_bounds__(RFF_THREADS)
                 }
             }
         }
-        if (c == 0) {
+        for (int jj = 0; jj < nj; ++jj) {
 #pragma unroll
             for (int cc = 0; cc < C; ++cc) acc[cc] = 0.0;
-        }
-        if (tid == 0 && qq + RFF_NSTAGE - 1 < total) issue(qq + RFF_NSTAGE - 1);
-        const int slot = (int)(qq % RFF_NSTAGE);
-        mbar_wait(&full[slot], (uint32_t)((qq / RFF_NSTAGE) & 1));
-
-        const int fcnt = min(RFF_FCH, F - c * RFF_FCH);
-        const double* sp = stage + slot * RFF_FCH * REC;
-#pragma unroll 2
-        for (int f = 0; f < fcnt; ++f) {
-            double w[REC];
-            const double2* rp = reinterpret_cast<const double2*>(sp + f * REC);
+            for (int c = 0; c < nch; ++c) {
+                if (tid == 0 && p_left > 0) issue();
+                mbar_wait(&full[slot], phase);
+                const int fcnt = min(RFF_FCH, F - c * RFF_FCH);
+                const double* sp = stage + slot * RFF_FCH * REC;
+#pragma unroll UNROLL
+                for (int f = 0; f < fcnt; ++f) {
+                    double w[REC];
+                    const double2* rp = reinterpret_cast<const double2*>(sp + f * REC);
 #pragma unroll
-            for (int u = 0; u < REC / 2; ++u) {
-                double2 v = rp[u];
-                w[2 * u] = v.x;
-                w[2 * u + 1] = v.y;
+                    for (int u = 0; u < REC / 2; ++u) {
+                        double2 v = rp[u];
+                        w[2 * u] = v.x;
+                        w[2 * u + 1] = v.y;
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < C; ++cc) {
+                        double h = w[D];
+#pragma unroll
+                        for (int kk = 0; kk < D; ++kk) h = fma(w[kk], x[cc][kk], h);
+                        acc[cc] = fma(w[D + 1], cospi_spec(h), acc[cc]);
+                    }
+                }
+                if (++slot == RFF_NSTAGE) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+                if (c != nch - 1) __syncthreads();  // ring slot may be refilled after this point
             }
-#pragma unroll
-            for (int cc = 0; cc < C; ++cc) {
-                double h = w[D];
-#pragma unroll
-                for (int kk = 0; kk < D; ++kk) h = fma(w[kk], x[cc][kk], h);
-                acc[cc] = fma(w[D + 1], cospi_spec(h), acc[cc]);
-            }
-        }
-
-        if (c == nch - 1) {  // sample jj finished for this tile
+            // sample jj finished for this tile
             const double thr = tk_val[jj * k + k - 1];
             double v[C];
             bool qual = false;
@@ -217,12 +229,10 @@ __global__ void __launch_bounds__(RFF_THREADS)
                 }
                 __syncthreads();
             }
-        } else {
-            __syncthreads();  // ring slot may be refilled after this point
         }
     }
 
-    for (int e = tid; e < nj * k; e += RFF_THREADS) {
+    for (int e = tid; e < nj * k; e += THREADS) {
         int jj = e / k, r = e % k;
         int64_t o = (chunk_id * S + j0 + jj) * k + r;
         part_val[o] = tk_val[e];
@@ -326,7 +336,7 @@ __global__ void topk_merge_kernel(const double* __restrict__ vals, const int64_t
 }
 
 struct RffPlan {
-    int C, tile, sg, rec;
+    int C, threads, unroll, tile, sg, rec;
     int64_t chunk, nchunks, nunits;
     int64_t feat_bytes, part_val_bytes, part_idx_bytes, dense_bytes;
     size_t smem;
@@ -334,8 +344,18 @@ struct RffPlan {
 
 static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k) {
     RffPlan p;
-    p.C = 2;
-    p.tile = RFF_THREADS * p.C;
+    p.C = 4;
+    p.threads = 256;
+    p.unroll = 2;
+    if (const char* v = getenv("TES_RFF_VARIANT")) {  // developer knob: "C,threads,unroll"
+        int a = 0, b2 = 0, c2 = 0;
+        if (sscanf(v, "%d,%d,%d", &a, &b2, &c2) == 3) {
+            p.C = a;
+            p.threads = b2;
+            p.unroll = c2;
+        }
+    }
+    p.tile = p.threads * p.C;
     p.rec = rff_rec((int)d);
     int64_t ntiles = (N + p.tile - 1) / p.tile;
     if (ntiles < 1) ntiles = 1;
@@ -359,17 +379,35 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k) {
     return p;
 }
 
+template <int D, int C, int THREADS, int UNROLL>
+static int launch_rff_variant(const RffPlan& p, const double* cand, int64_t N, const double* feat, int64_t S,
+                              int64_t F, double scale, int k, int64_t idx_offset, double* part_val,
+                              int64_t* part_idx, cudaStream_t st) {
+    auto kern = rff_topk_kernel<D, C, THREADS, UNROLL>;
+    if (p.smem > 48 * 1024)
+        TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    kern<<<(unsigned)p.nunits, THREADS, p.smem, st>>>(cand, N, feat, (int)S, (int)F, scale, k, p.sg, p.chunk,
+                                                      idx_offset, part_val, part_idx);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
 template <int D>
 static int launch_rff_topk(const RffPlan& p, const double* cand, int64_t N, const double* feat, int64_t S, int64_t F,
                            double scale, int k, int64_t idx_offset, double* part_val, int64_t* part_idx,
                            cudaStream_t st) {
-    auto kern = rff_topk_kernel<D, 2>;
-    if (p.smem > 48 * 1024)
-        TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    kern<<<(unsigned)p.nunits, RFF_THREADS, p.smem, st>>>(cand, N, feat, (int)S, (int)F, scale, k, p.sg, p.chunk,
-                                                          idx_offset, part_val, part_idx);
-    TES_LAUNCH_OK();
-    return 0;
+#define TES_V(CC, TT, UU)                                                                                   \
+    if (p.C == CC && p.threads == TT && p.unroll == UU)                                                     \
+        return launch_rff_variant<D, CC, TT, UU>(p, cand, N, feat, S, F, scale, k, idx_offset, part_val, part_idx, st);
+    TES_V(4, 256, 2)
+#ifdef TES_RFF_DEV_VARIANTS
+    if constexpr (D == 6 || D == 2 || D == 10) {
+        TES_V(4, 256, 1) TES_V(2, 256, 2) TES_V(2, 512, 2) TES_V(4, 128, 2) TES_V(3, 256, 2) TES_V(2, 256, 4)
+        TES_V(4, 512, 1) TES_V(3, 256, 1) TES_V(2, 256, 1) TES_V(1, 512, 4) TES_V(1, 256, 4) TES_V(2, 128, 2)
+    }
+#endif
+#undef TES_V
+    return -100;
 }
 
 }  // namespace tes

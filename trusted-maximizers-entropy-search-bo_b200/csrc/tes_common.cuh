@@ -26,6 +26,10 @@ extern "C" void tes_count_launch_(void);
 
 namespace tes {
 
+// polynomial of tes_cospi in constant memory: DFMA reads c[bank][off] operands directly
+__constant__ double kCospiC[TES_COSPI_NCOEF] = {TES_COSPI_C0, TES_COSPI_C1, TES_COSPI_C2, TES_COSPI_C3, TES_COSPI_C4,
+                                               TES_COSPI_C5, TES_COSPI_C6, TES_COSPI_C7, TES_COSPI_C8};
+
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 __device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
@@ -40,15 +44,15 @@ __device__ __forceinline__ double cospi_spec(double h) {
     double n = __dsub_rn(t, MAGIC);
     double r = __dsub_rn(h, n);
     double s = __dmul_rn(r, r);
-    double p = TES_COSPI_C8;
-    p = fma(p, s, TES_COSPI_C7);
-    p = fma(p, s, TES_COSPI_C6);
-    p = fma(p, s, TES_COSPI_C5);
-    p = fma(p, s, TES_COSPI_C4);
-    p = fma(p, s, TES_COSPI_C3);
-    p = fma(p, s, TES_COSPI_C2);
-    p = fma(p, s, TES_COSPI_C1);
-    p = fma(p, s, TES_COSPI_C0);
+    double p = kCospiC[8];
+    p = fma(p, s, kCospiC[7]);
+    p = fma(p, s, kCospiC[6]);
+    p = fma(p, s, kCospiC[5]);
+    p = fma(p, s, kCospiC[4]);
+    p = fma(p, s, kCospiC[3]);
+    p = fma(p, s, kCospiC[2]);
+    p = fma(p, s, kCospiC[1]);
+    p = fma(p, s, kCospiC[0]);
     int hi = __double2hiint(p) ^ (lo << 31);
     return __hiloint2double(hi, __double2loint(p));
 }

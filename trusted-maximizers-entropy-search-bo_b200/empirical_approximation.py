@@ -19,7 +19,23 @@ def batched_empirical_stats(post_samples, post_masks):
     -> means (S,T), covs (S,T,T); identical to calling the function above per maximizer."""
     w = post_masks.astype(np.float64)                       # (S,K)
     tw = w.sum(axis=1)                                      # (S,)
-    mean = np.einsum("stk,sk->st", post_samples, w) / tw[:, None]
+    mean = np.matmul(post_samples, w[:, :, None])[:, :, 0] / tw[:, None]
     zs = (post_samples - mean[:, :, None]) * np.sqrt(w)[:, None, :]
-    cov = np.einsum("sak,sbk->sab", zs, zs) / (tw - 1.0)[:, None, None]
+    cov = np.matmul(zs, np.transpose(zs, (0, 2, 1))) / (tw - 1.0)[:, None, None]
+    return mean, cov
+
+
+def bucket_empirical_stats(samples, rows_per_bucket):
+    """Same statistics straight from the bucketed joint samples (no padded tensor): samples (nsample,T),
+    rows_per_bucket = list of row-index arrays, one per kept maximizer."""
+    T = samples.shape[1]
+    S = len(rows_per_bucket)
+    mean = np.empty((S, T))
+    cov = np.empty((S, T, T))
+    for j, rows in enumerate(rows_per_bucket):
+        x = samples[rows]
+        m = x.sum(axis=0) / len(rows)
+        xc = x - m
+        mean[j] = m
+        cov[j] = xc.T.dot(xc) / (len(rows) - 1.0)
     return mean, cov

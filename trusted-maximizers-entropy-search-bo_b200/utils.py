@@ -144,40 +144,54 @@ def mvn_transform_matrix(cov):
     return v.dot(np.diag(np.sqrt(np.clip(e, 0.0, np.inf))))
 
 
-def sample_multivariate_normal_maxidx_np(mean, cov, nsample, n_min_sample=1, get_sample=True,
-                                         remove_correlated_dims=True, z=None, transform=None):
-    """utils.py:1654-1729.  `z` (nsample, n, 1) replaces the np.random.normal draw of :1674; when
-    omitted the global numpy RNG is used exactly as the reference does.  `transform` overrides the
-    colouring factor A (default: mvn_transform_matrix(cov), as the reference computes it)."""
+def _joint_sample_buckets(mean, cov, nsample, n_min_sample, remove_correlated_dims, z, transform):
+    """Core of utils.py:1654-1729: joint samples, correlated-dimension suppression, arg-max bucketing.
+    Returns (samples (nsample,n), unique maximizer ids, sizes, rows per bucket in sample order)."""
     mean, cov = _np(mean), _np(cov)
     n = cov.shape[0]
     mean = mean.reshape(n)
     A = mvn_transform_matrix(cov) if transform is None else _np(transform)
     if z is None:
         z = np.random.normal(size=(nsample, n, 1))
-    samples = np.mean(mean.reshape(1, n) + np.matmul(A[None], _np(z)), axis=-1)
+    # utils.py:1675 broadcasts mean.reshape(1,n) against the (nsample,n,1) product and then averages over the
+    # LAST axis, so what is added to every coordinate is the AVERAGE of the prior means, not mean[i]
+    # (reference quirk Q11, reproduced on purpose).  Evaluated here as ONE GEMM: z A^T + mean(mean).
+    samples = _np(z).reshape(-1, n).dot(A.T) + np.mean(mean)
     corr_idxs = []
     if remove_correlated_dims:
         with np.errstate(invalid="ignore", divide="ignore"):
             rows, _ = np.where(np.tril(np.corrcoef(samples.T), k=-1) > 1 - 1e-6)
         corr_idxs = rows
-    masked = samples.copy()
-    masked[:, corr_idxs] = -np.inf
+    masked = samples
+    if len(corr_idxs):
+        masked = samples.copy()
+        masked[:, corr_idxs] = -np.inf
     maxidxs = np.argmax(masked, axis=1)
     counts = np.bincount(maxidxs, minlength=n)
     unique = np.where(counts >= max(n_min_sample, 1))[0]
     sizes = counts[unique]
+    order = np.argsort(maxidxs, kind="stable")
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    rows_per = [order[starts[mi]:starts[mi + 1]] for mi in unique]
+    return samples, mean, unique, sizes, rows_per
+
+
+def sample_multivariate_normal_maxidx_np(mean, cov, nsample, n_min_sample=1, get_sample=True,
+                                         remove_correlated_dims=True, z=None, transform=None):
+    """utils.py:1654-1729.  `z` (nsample, n, 1) replaces the np.random.normal draw of :1674; when
+    omitted the global numpy RNG is used exactly as the reference does.  `transform` overrides the
+    colouring factor A (default: mvn_transform_matrix(cov), as the reference computes it)."""
+    samples, mean, unique, sizes, rows_per = _joint_sample_buckets(mean, cov, nsample, n_min_sample,
+                                                                   remove_correlated_dims, z, transform)
     if not get_sample:
         return unique, sizes
+    n = mean.shape[0]
     K = int(sizes.max())
     nmax = len(unique)
     ret = np.tile(mean.reshape(1, n, 1), (nmax, 1, K))  # padded slots hold the prior mean (:1722)
     masks = np.zeros([nmax, K], dtype=int)
-    order = np.argsort(maxidxs, kind="stable")
-    starts = np.concatenate([[0], np.cumsum(counts)])
-    for i, mi in enumerate(unique):
-        rows_i = order[starts[mi]:starts[mi + 1]]
-        ret[i, :, :sizes[i]] = samples[rows_i].T
+    for i in range(nmax):
+        ret[i, :, :sizes[i]] = samples[rows_per[i]].T
         masks[i, :sizes[i]] = 1
     return nmax, unique, K, ret, masks, sizes
 
@@ -185,53 +199,59 @@ def sample_multivariate_normal_maxidx_np(mean, cov, nsample, n_min_sample=1, get
 def get_testidxs_stats(nhyp, test_xs_np, test_means, test_covs, mode="sample", nsample=1000, n_min_sample=2,
                        z=None, transforms=None):
     """utils.py:1733-1833.  mode in {'sample','empirical','ep'}; `z` (nhyp, nsample, ntest, 1) optional.
-    mode='ep' runs the EP the reference intends at :1820-1825 (its shipped code raises NameError)."""
+    mode='ep' runs the EP the reference intends at :1820-1825 (its shipped code raises NameError).
+    The padded (nhyp, ntest, ntest, K) sample tensor is only materialised for mode='sample'; the empirical
+    moments are taken straight from the buckets (zero-weight padding contributes nothing)."""
     from . import empirical_approximation, ep
     test_xs_np, test_means, test_covs = _np(test_xs_np), _np(test_means), _np(test_covs)
+    if mode not in ("sample", "empirical", "ep"):
+        raise Exception("Unknown mode in get_testidxs_stats!")
     ntest = test_xs_np.shape[0]
     alive = np.ones(ntest, dtype=bool)
     max_probs = np.ones([nhyp, ntest]) / ntest
-    K_all = 0
     per_hyp = []
     for i in range(nhyp):
-        nmax, uniq, K, rs, rm, sizes = sample_multivariate_normal_maxidx_np(
-            test_means[i], test_covs[i], nsample, n_min_sample, z=None if z is None else z[i],
-            transform=None if transforms is None else transforms[i])
-        K_all = max(K_all, K)
+        samples, mean_i, uniq, sizes, rows_per = _joint_sample_buckets(
+            test_means[i], test_covs[i], nsample, n_min_sample, True, None if z is None else z[i],
+            None if transforms is None else transforms[i])
         won = np.zeros(ntest, dtype=bool)
         won[uniq] = True
         alive &= won
         max_probs[i, uniq] = sizes / np.sum(sizes)
-        per_hyp.append((uniq, K, rs, rm))
-    post_samples = np.zeros([nhyp, ntest, ntest, K_all])
-    post_masks = np.zeros([nhyp, ntest, K_all], dtype=bool)
-    for i, (uniq, K, rs, rm) in enumerate(per_hyp):
-        post_samples[i, uniq, :, :K] = rs
-        post_masks[i, uniq, :K] = rm.astype(bool)
+        per_hyp.append((samples, mean_i, uniq, sizes, rows_per))
     keep = np.where(alive)[0]
+    pos = -np.ones(ntest, dtype=int)
+    pos[keep] = np.arange(len(keep))
     if len(keep) != ntest:
         test_xs_np = test_xs_np[keep]
         test_means = test_means[:, keep]
         test_covs = test_covs[:, keep][:, :, keep]
         max_probs = max_probs[:, keep]
-        post_samples = post_samples[:, keep][:, :, keep]
-        post_masks = post_masks[:, keep]
     max_probs = max_probs / np.sum(max_probs, axis=1, keepdims=True)
-    ntest = test_xs_np.shape[0]
+    nk = len(keep)
     if mode == "sample":
+        K_all = max(int(sz.max()) for (_, _, _, sz, _) in per_hyp)
+        post_samples = np.zeros([nhyp, nk, nk, K_all])
+        post_masks = np.zeros([nhyp, nk, K_all], dtype=bool)
+        for i, (samples, mean_i, uniq, sizes, rows_per) in enumerate(per_hyp):
+            K = int(sizes.max())
+            for u, sz, rows in zip(uniq, sizes, rows_per):
+                if pos[u] < 0:
+                    continue
+                post_samples[i, pos[u], :, :sz] = samples[rows][:, keep].T
+                post_samples[i, pos[u], :, sz:K] = mean_i[keep].reshape(nk, 1)  # prior-mean padding (:1722)
+                post_masks[i, pos[u], :sz] = True
         return test_xs_np, max_probs, test_means, test_covs, post_samples, post_masks
-    pm = np.zeros([nhyp, ntest, ntest])
-    pc = np.zeros([nhyp, ntest, ntest, ntest])
-    for i in range(nhyp):
+    pm = np.zeros([nhyp, nk, nk])
+    pc = np.zeros([nhyp, nk, nk, nk])
+    for i, (samples, mean_i, uniq, sizes, rows_per) in enumerate(per_hyp):
         if mode == "empirical":
-            m, c = empirical_approximation.batched_empirical_stats(post_samples[i], post_masks[i])
-            pm[i], pc[i] = m, c
-        elif mode == "ep":
-            for j in range(ntest):
+            sel = [rows for u, rows in zip(uniq, rows_per) if pos[u] >= 0]
+            pm[i], pc[i] = empirical_approximation.bucket_empirical_stats(samples[:, keep], sel)
+        else:
+            for j in range(nk):
                 m, c = ep.approximate_EP_np(j, test_means[i].reshape(-1, 1), test_covs[i], resolution=1e-9,
                                             max_niter=100)
                 pm[i, j] = m.squeeze()
                 pc[i, j] = c
-        else:
-            raise Exception("Unknown mode in get_testidxs_stats!")
     return test_xs_np, max_probs, test_means, test_covs, pm, pc
