@@ -60,6 +60,16 @@ int tes_rff_topk_f64(const double* cand, int64_t N, int64_t d, const double* W, 
                      int64_t idx_offset, int64_t* out_idx, double* out_val, void* ws, int64_t ws_bytes,
                      void* stream);
 
+/* Same as tes_rff_topk_f64 with an explicit evaluation method (results are bit-identical for every method):
+ *   0 = automatic; 1 = every pair in fp64; 2 = fp32 screen + fp64 refine: all pairs are first scored on the
+ *   packed-fp32 + MUFU pipes with a proven per-sample error bound B_j, every candidate within 2 B_j of the
+ *   running k-th best screen value is re-evaluated with the exact fp64 sequence of tes_spec.h, and a
+ *   (chunk, sample) whose kept set overflows is recomputed in fp64 (needs d <= 10 and k <= 8, else = 1). */
+int tes_rff_topk_method_f64(const double* cand, int64_t N, int64_t d, const double* W, const double* b,
+                            const double* theta, int64_t S, int64_t F, int w_shared, double sigma, int k,
+                            int64_t idx_offset, int64_t* out_idx, double* out_val, void* ws, int64_t ws_bytes,
+                            void* stream, int method);
+
 /* All function-sample values, out (S, N).  Replaces utils_for_continuous.get_function_samples
  * (utils_for_continuous.py:257-296) / optfunc.make_function_sample_np.  Debug / small-N use. */
 int tes_rff_eval_f64(const double* cand, int64_t N, int64_t d, const double* W, const double* b,

@@ -107,3 +107,63 @@ def test_bad_arguments_raise():
         ops.rff_topk(cand, W, b, theta, -1.0, k=1)
     with pytest.raises(ValueError):
         ops.rff_topk(cand, W[:1].repeat(3, 0), b, theta, sigma, k=1)
+
+
+# ---- fp32 screen + fp64 refine: must be BIT-IDENTICAL to the pure fp64 kernel and to the oracle -------------
+@pytest.mark.parametrize("N,d,S,F,k,shared,scale", [
+    (40_000, 6, 24, 200, 1, False, 3.0),
+    (70_001, 6, 16, 257, 3, False, 3.0),     # ragged tile + ragged feature chunk
+    (33_000, 2, 40, 300, 5, False, 30.0),    # Branin/pH-like large inverse length-scales (big arguments)
+    (50_000, 10, 12, 128, 8, False, 1.0),    # max k for the screen
+    (36_000, 3, 9, 100, 2, False, 3.0),      # odd d (padded record)
+    (40_000, 6, 12, 160, 3, True, 3.0),      # shared W
+    (3_000, 6, 7, 64, 3, False, 3.0),        # small N, screen forced
+])
+def test_screened_topk_bit_identical(N, d, S, F, k, shared, scale):
+    import torch
+    from oracle import c_oracle as co
+    from tes_b200 import ops
+    cand, W, b, theta, sigma = _problem(N + d + k, N, d, S, F, shared, scale)
+    i1, v1 = ops.rff_topk(cand, W, b, theta, sigma, k=k, idx_offset=7, method=ops.RFF_FP64)
+    i2, v2 = ops.rff_topk(cand, W, b, theta, sigma, k=k, idx_offset=7, method=ops.RFF_SCREEN)
+    assert torch.equal(i1, i2) and torch.equal(v1, v2)
+    if N * S * F <= 4e9:
+        ridx, rval = co.rff_topk(cand, W, b, theta, sigma, k, idx_offset=7)
+        np.testing.assert_array_equal(i2.cpu().numpy(), ridx)
+        np.testing.assert_array_equal(v2.cpu().numpy(), rval)
+
+
+def test_screened_topk_handles_exact_ties_and_overflow():
+    """(a) duplicated candidates: exact fp64 ties, the lower index must win; (b) a constant function sample
+    (theta = 0) makes EVERY candidate tie, the kept list overflows its 16 slots and the flag-gated fp64
+    fallback must produce the plain fp64 answer (indices 0..k-1)."""
+    import torch
+    from tes_b200 import ops
+    cand, W, b, theta, sigma = _problem(9, 20_000, 6, 6, 96)
+    cand2 = np.concatenate([cand, cand], axis=0)
+    theta = theta.copy()
+    theta[2] = 0.0
+    i1, v1 = ops.rff_topk(cand2, W, b, theta, sigma, k=4, method=ops.RFF_FP64)
+    i2, v2 = ops.rff_topk(cand2, W, b, theta, sigma, k=4, method=ops.RFF_SCREEN)
+    assert torch.equal(i1, i2) and torch.equal(v1, v2)
+    i2 = i2.cpu().numpy()
+    assert list(i2[2]) == [0, 1, 2, 3]
+    for j in (0, 1, 3, 4, 5):
+        assert i2[j, 1] == i2[j, 0] + 20_000 and i2[j, 3] == i2[j, 2] + 20_000
+
+
+def test_screened_topk_near_ties_many_seeds():
+    """Stress: dense candidate clouds around one point make thousands of near-ties within the fp32 bound."""
+    import torch
+    from tes_b200 import ops
+    for seed in range(6):
+        rs = np.random.RandomState(100 + seed)
+        d, S, F, N = 6, 8, 128, 40_000
+        center = rs.rand(1, d)
+        cand = center + rs.randn(N, d) * 10.0 ** (-2 - seed)   # spreads 1e-2 ... 1e-7
+        W = rs.randn(S, F, d) * 2.0
+        b = 2 * np.pi * rs.rand(S, F, 1)
+        theta = rs.randn(S, F, 1)
+        i1, v1 = ops.rff_topk(cand, W, b, theta, 1.3, k=3, method=ops.RFF_FP64)
+        i2, v2 = ops.rff_topk(cand, W, b, theta, 1.3, k=3, method=ops.RFF_SCREEN)
+        assert torch.equal(i1, i2) and torch.equal(v1, v2), seed

@@ -39,6 +39,8 @@ SIGNATURES = {
     "tes_rff_topk_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_int]),
     "tes_rff_topk_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_dbl, c_int,
                                  c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "tes_rff_topk_method_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_dbl, c_int,
+                                        c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_int]),
     "tes_rff_eval_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_dbl, c_ptr,
                                  c_ptr]),
     "tes_topk_merge_f64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),

@@ -88,7 +88,7 @@ template <int D, int C, int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS)
     rff_topk_kernel(const double* __restrict__ cand, int64_t N, const double* __restrict__ feat, int S, int F,
                     double scale, int k, int sg, int64_t chunk, int64_t idx_offset, double* __restrict__ part_val,
-                    int64_t* __restrict__ part_idx) {
+                    int64_t* __restrict__ part_idx, const int* __restrict__ flags, int out_stride, int out_off) {
     constexpr int REC = rff_rec(D);
     constexpr int TILE = THREADS * C;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -112,6 +112,16 @@ __global__ void __launch_bounds__(THREADS)
     const int ntiles = (int)((c1 - c0 + TILE - 1) / TILE);
     const int nch = (F + RFF_FCH - 1) / RFF_FCH;
     const int64_t total = (int64_t)ntiles * nj * nch;
+
+    if (flags != nullptr && flags[chunk_id * S + j0] == 0) {
+        // fallback launch (sg == 1) for a (chunk, sample) whose fp32 screen did not overflow: nothing to do
+        for (int e = tid; e < nj * k; e += THREADS) {
+            int64_t o = (chunk_id * S + j0 + e / k) * out_stride + out_off + e % k;
+            part_val[o] = neg_inf();
+            part_idx[o] = -1;
+        }
+        return;
+    }
 
     for (int e = tid; e < sg * k; e += THREADS) {
         tk_val[e] = neg_inf();
@@ -234,7 +244,7 @@ __global__ void __launch_bounds__(THREADS)
 
     for (int e = tid; e < nj * k; e += THREADS) {
         int jj = e / k, r = e % k;
-        int64_t o = (chunk_id * S + j0 + jj) * k + r;
+        int64_t o = (chunk_id * S + j0 + jj) * out_stride + out_off + r;
         part_val[o] = tk_val[e];
         part_idx[o] = tk_idx[e];
     }
@@ -298,19 +308,20 @@ __global__ void rows_topk_kernel(const double* __restrict__ vals, int64_t N, int
 
 // merge P partial lists per sample: vals/idx (P, S, k) -> (S, k).  One warp per sample.
 __global__ void topk_merge_kernel(const double* __restrict__ vals, const int64_t* __restrict__ idx, int64_t P,
-                                  int64_t S, int k, double* __restrict__ out_val, int64_t* __restrict__ out_idx) {
+                                  int64_t S, int kin, int k, double* __restrict__ out_val,
+                                  int64_t* __restrict__ out_idx) {
     const int64_t j = blockIdx.x;
     const int lane = threadIdx.x;
-    const int64_t n = P * k;
+    const int64_t n = P * kin;
     double pv = pos_inf();
     int64_t pi = -1;
     for (int r = 0; r < k; ++r) {
         double bv = neg_inf();
         int64_t bi = INT64_MAX;
         for (int64_t e = lane; e < n; e += 32) {
-            int64_t p = e / k, q = e % k;
-            double v = vals[(p * S + j) * k + q];
-            int64_t i = idx[(p * S + j) * k + q];
+            int64_t p = e / kin, q = e % kin;
+            double v = vals[(p * S + j) * kin + q];
+            int64_t i = idx[(p * S + j) * kin + q];
             if (i >= 0 && better(pv, pi, v, i) && better(v, i, bv, bi)) {
                 bv = v;
                 bi = i;
@@ -335,15 +346,388 @@ __global__ void topk_merge_kernel(const double* __restrict__ vals, const int64_t
     }
 }
 
+// =====================================================================================================
+// fp32 screen + fp64 refine.  The fp64 pipe (64 lanes/SM) is the bound of rff_topk_kernel; the packed fp32
+// pipe (FFMA2, 2 x 128 lanes/SM) plus the MUFU cos is ~4.7x faster.  The screen evaluates every
+// (candidate, sample) pair in fp32 with a PROVEN error bound B_j per sample and keeps every candidate whose
+// screen value is within 2 B_j of (a lower bound of) the k-th best screen value; only those are re-evaluated
+// with the exact fp64 sequence of tes_spec.h, which alone decides values and indices.  If u_i are screen
+// values with |u_i - v_i| <= B and t is the k-th largest u, every member of the true top-k satisfies
+// u_i >= t - 2B, so the kept set contains the true top-k (ties included) and the result is bit-identical to
+// the pure fp64 kernel.  A (chunk, sample) whose kept set overflows its CAP slots is recomputed by the fp64
+// kernel (flag-gated launch), so correctness never depends on the list capacity.
+//
+// Error bound (u = 2^-24; A_f = |b'_f| + sum_k |w'_fk| max_i |x_ik|):
+//   |h32 - h|      <= (d+4) u A_f           (input rounding of w', b', x and the d FFMA roundings)
+//   |c32 - cos(pi h)| <= pi (d+4) u A_f + 1.3e-6   (exact reduction to [-1,1] half-turns; x = pi32*r: 2.8e-7;
+//                                                    __cosf on [-pi,pi]: 2^-21.19 per the CUDA guide, doubled)
+//   |acc - sum|    <= 34 u sum_f |theta_f|   (theta rounding, products, 32-term fp32 blocks flushed to fp64)
+//   B_j = 1.25 * scale * sum_f |theta_f| (pi (d+4) u A_f + 1.3e-6 + 34 u)
+// =====================================================================================================
+constexpr int SCR_THREADS = 256;
+constexpr int SCR_TILE = SCR_THREADS * 4;  // 4 candidates (2 packed pairs) per thread
+constexpr int SCR_CAP = 16;                // kept candidates per (chunk, sample) before the fp64 fallback
+constexpr int SCR_MAX_K = 8;               // k-th of the 8 warp maxima is the per-tile lower bound
+
+__host__ __device__ constexpr int scr_recp(int d) { return (d + 3) & ~1; }  // 8-byte (v,v) pairs per record
+
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    return ((uint64_t)__float_as_uint(hi) << 32) | (uint64_t)__float_as_uint(lo);
+}
+__device__ __forceinline__ float f2_lo(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float f2_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+__global__ void rff_pack32_kernel(const double* __restrict__ W, const double* __restrict__ b,
+                                  const double* __restrict__ theta, int64_t S, int64_t F, int d, int w_shared,
+                                  int recp, uint64_t* __restrict__ feat32) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S * F) return;
+    int64_t j = t / F, f = t % F;
+    int64_t jw = w_shared ? 0 : j;
+    const double* w = W + (jw * F + f) * d;
+    uint64_t* o = feat32 + t * recp;
+    for (int k = 0; k < d; ++k) {
+        float v = __double2float_rn(__dmul_rn(w[k], TES_INV_PI));
+        o[k] = f2_pack(v, v);
+    }
+    float bv = __double2float_rn(__dmul_rn(b[jw * F + f], TES_INV_PI));
+    o[d] = f2_pack(bv, bv);
+    float tv = __double2float_rn(theta[t]);
+    o[d + 1] = f2_pack(tv, tv);
+    for (int k = d + 2; k < recp; ++k) o[k] = 0ull;
+}
+
+// xmax[k] = max_i |x_ik| (bit pattern of a non-negative double orders like an unsigned integer)
+__global__ void rff_xmax_kernel(const double* __restrict__ cand, int64_t N, int d, unsigned long long* xmax) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; e < N * d; e += stride) {
+        double a = fabs(cand[e]);
+        atomicMax(xmax + (e % d), (unsigned long long)__double_as_longlong(a));
+    }
+}
+
+// one warp per sample: B_j from the fp64 feature records [w'(d), b', theta]
+__global__ void rff_bound_kernel(const double* __restrict__ feat, int rec, int64_t S, int64_t F, int d,
+                                 const unsigned long long* __restrict__ xmax, double scale,
+                                 double* __restrict__ bound) {
+    const int64_t j = blockIdx.x;
+    const int lane = threadIdx.x;
+    const double u = 5.9604644775390625e-08;  // 2^-24
+    double e = 0.0;
+    for (int64_t f = lane; f < F; f += 32) {
+        const double* r = feat + (j * F + f) * rec;
+        double A = fabs(r[d]);
+        for (int k = 0; k < d; ++k) A += fabs(r[k]) * __longlong_as_double((long long)xmax[k]);
+        e += fabs(r[d + 1]) * (3.14159265358979323846 * (d + 4) * u * A + 1.3e-6 + 34.0 * u);
+    }
+    e = warp_sum(e);
+    if (lane == 0) bound[j] = 1.25 * scale * e;
+}
+
+template <int D>
+__global__ void __launch_bounds__(SCR_THREADS)
+    rff_screen_kernel(const double* __restrict__ cand, int64_t N, const uint64_t* __restrict__ feat32, int S, int F,
+                      double scale, int k, int sg, int64_t chunk, int64_t idx_offset,
+                      const double* __restrict__ bound, double* __restrict__ slot_val,
+                      int64_t* __restrict__ slot_idx, int slot_stride, int* __restrict__ flags) {
+    constexpr int RECP = scr_recp(D);
+    constexpr int THREADS = SCR_THREADS;
+    constexpr int TILE = SCR_TILE;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* stage = reinterpret_cast<uint64_t*>(smem_raw);                            // [NSTAGE][FCH*RECP]
+    uint64_t* full = stage + RFF_NSTAGE * RFF_FCH * RECP;                               // [8]
+    double* tk_val = reinterpret_cast<double*>(full + 8);                               // [sg*k] running screen top-k
+    int64_t* tk_idx = reinterpret_cast<int64_t*>(tk_val + sg * k);                      // [sg*k]
+    double* ap_val = reinterpret_cast<double*>(tk_idx + sg * k);                        // [TILE + 16]
+    int64_t* ap_idx = reinterpret_cast<int64_t*>(ap_val + TILE + 16);                   // [TILE + 16]
+    double* wm = reinterpret_cast<double*>(ap_idx + TILE + 16);                         // [8] warp maxima
+    int* slot_cnt = reinterpret_cast<int*>(wm + 8);                                     // [sg]
+    int* ap_count = slot_cnt + sg;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nsg = (S + sg - 1) / sg;
+    const int64_t chunk_id = blockIdx.x / nsg;
+    const int g = blockIdx.x % nsg;
+    const int j0 = g * sg;
+    const int nj = min(sg, S - j0);
+    const int64_t c0 = chunk_id * chunk;
+    const int64_t c1 = min(N, c0 + chunk);
+    const int ntiles = (int)((c1 - c0 + TILE - 1) / TILE);
+    const int nch = (F + RFF_FCH - 1) / RFF_FCH;
+    const int64_t total = (int64_t)ntiles * nj * nch;
+
+    for (int e = tid; e < sg * k; e += THREADS) {
+        tk_val[e] = neg_inf();
+        tk_idx[e] = -1;
+    }
+    for (int e = tid; e < nj * SCR_CAP; e += THREADS) {
+        int64_t o = (chunk_id * S + j0 + e / SCR_CAP) * slot_stride + e % SCR_CAP;
+        slot_idx[o] = -1;
+        slot_val[o] = neg_inf();
+    }
+    for (int e = tid; e < nj; e += THREADS) {
+        slot_cnt[e] = 0;
+        flags[chunk_id * S + j0 + e] = 0;
+    }
+    if (tid == 0) {
+        *ap_count = 0;
+        for (int s = 0; s < RFF_NSTAGE; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    int p_jj = 0, p_c = 0, p_slot = 0;
+    int64_t p_left = total;
+    auto issue = [&]() {
+        const int fcnt = min(RFF_FCH, F - p_c * RFF_FCH);
+        const uint32_t bytes = (uint32_t)(fcnt * RECP * sizeof(uint64_t));
+        const uint64_t* src = feat32 + ((int64_t)(j0 + p_jj) * F + (int64_t)p_c * RFF_FCH) * RECP;
+        mbar_expect_tx(&full[p_slot], bytes);
+        bulk_g2s(stage + p_slot * RFF_FCH * RECP, src, bytes, &full[p_slot]);
+        if (++p_c == nch) {
+            p_c = 0;
+            if (++p_jj == nj) p_jj = 0;
+        }
+        if (++p_slot == RFF_NSTAGE) p_slot = 0;
+        --p_left;
+    };
+    if (tid == 0) {
+        for (int p = 0; p < RFF_NSTAGE - 1 && p_left > 0; ++p) issue();
+    }
+
+    const uint64_t HALF2 = f2_pack(0.5f, 0.5f);
+    const uint64_t MAGIC2 = f2_pack(12582912.0f, 12582912.0f);  // 1.5 * 2^23
+    const uint64_t NMAGIC2 = f2_pack(-12582912.0f, -12582912.0f);
+    const uint64_t NTWO2 = f2_pack(-2.0f, -2.0f);
+    const uint64_t PI2 = f2_pack(3.14159274f, 3.14159274f);
+
+    uint64_t x2[2][D];
+    double dacc[4];
+    int64_t ci[4];
+    int slot = 0;
+    uint32_t phase = 0;
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+        {
+            const int64_t t0 = c0 + (int64_t)tile * TILE;
+            float xf[4][D];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                ci[cc] = t0 + cc * THREADS + tid;
+#pragma unroll
+                for (int kk = 0; kk < D; ++kk)
+                    xf[cc][kk] = (ci[cc] < c1) ? __double2float_rn(__ldg(cand + ci[cc] * D + kk)) : 0.0f;
+            }
+#pragma unroll
+            for (int kk = 0; kk < D; ++kk) {
+                x2[0][kk] = f2_pack(xf[0][kk], xf[1][kk]);
+                x2[1][kk] = f2_pack(xf[2][kk], xf[3][kk]);
+            }
+        }
+        for (int jj = 0; jj < nj; ++jj) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) dacc[cc] = 0.0;
+            for (int c = 0; c < nch; ++c) {
+                if (tid == 0 && p_left > 0) issue();
+                mbar_wait(&full[slot], phase);
+                const int fcnt = min(RFF_FCH, F - c * RFF_FCH);
+                const uint64_t* sp = stage + slot * RFF_FCH * RECP;
+                for (int f0 = 0; f0 < fcnt; f0 += 32) {
+                    const int fe = min(fcnt, f0 + 32);
+                    uint64_t acc2[2] = {0ull, 0ull};
+#pragma unroll 2
+                    for (int f = f0; f < fe; ++f) {
+                        uint64_t w[RECP];
+                        const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(sp + f * RECP);
+#pragma unroll
+                        for (int q = 0; q < RECP / 2; ++q) {
+                            ulonglong2 v = rp[q];
+                            w[2 * q] = v.x;
+                            w[2 * q + 1] = v.y;
+                        }
+#pragma unroll
+                        for (int pp = 0; pp < 2; ++pp) {
+                            uint64_t h = w[D];
+#pragma unroll
+                            for (int kk = 0; kk < D; ++kk) h = ffma2(w[kk], x2[pp][kk], h);
+                            // r = h - 2*rint(h/2) in [-1,1] half-turns (exact), x = pi*r, cos via MUFU
+                            uint64_t t = ffma2(h, HALF2, MAGIC2);
+                            uint64_t n = fadd2(t, NMAGIC2);
+                            uint64_t r = ffma2(n, NTWO2, h);
+                            uint64_t xr = fmul2(r, PI2);
+                            uint64_t cs = f2_pack(__cosf(f2_lo(xr)), __cosf(f2_hi(xr)));
+                            acc2[pp] = ffma2(w[D + 1], cs, acc2[pp]);
+                        }
+                    }
+                    dacc[0] += (double)f2_lo(acc2[0]);
+                    dacc[1] += (double)f2_hi(acc2[0]);
+                    dacc[2] += (double)f2_lo(acc2[1]);
+                    dacc[3] += (double)f2_hi(acc2[1]);
+                }
+                if (++slot == RFF_NSTAGE) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+                __syncthreads();  // ring slot may be refilled after this point
+            }
+            // ---- sample jj finished for this tile: keep everything within 2B of the k-th best screen value
+            double u[4];
+            double tmax = neg_inf();
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                u[cc] = (ci[cc] < c1) ? scale * dacc[cc] : neg_inf();
+                tmax = fmax(tmax, u[cc]);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
+            if (lane == 0) wm[warp] = tmax;
+            __syncthreads();
+            // k-th largest of the 8 warp maxima: a lower bound of the tile's k-th largest value
+            double lk;
+            {
+                double a[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) a[q] = wm[q];
+                lk = neg_inf();
+                double prev = pos_inf();
+                int taken = 0;
+                // selection by repeated max with multiplicity
+                for (int r = 0; r < k; ++r) {
+                    double best = neg_inf();
+                    int cnt = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (a[q] < prev) {
+                            if (a[q] > best) {
+                                best = a[q];
+                                cnt = 1;
+                            } else if (a[q] == best) {
+                                ++cnt;
+                            }
+                        }
+                    }
+                    if (cnt == 0) break;
+                    taken += cnt;
+                    lk = best;
+                    prev = best;
+                    if (taken >= k) break;
+                }
+                if (taken < k) lk = neg_inf();
+            }
+            const double thr = fmax(lk, tk_val[jj * k + k - 1]) - 2.0 * bound[j0 + jj];
+            bool qual = false;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) qual |= (ci[cc] < c1) && (u[cc] >= thr);
+            if (__syncthreads_or(qual)) {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    if ((ci[cc] < c1) && (u[cc] >= thr)) {
+                        int pos = k + atomicAdd(ap_count, 1);
+                        ap_val[pos] = u[cc];
+                        ap_idx[pos] = ci[cc] + idx_offset;
+                    }
+                }
+                if (tid < k) {
+                    ap_val[tid] = tk_val[jj * k + tid];
+                    ap_idx[tid] = tk_idx[jj * k + tid];
+                }
+                __syncthreads();
+                if (tid < 32) {
+                    const int n = *ap_count;
+                    const int cnt = slot_cnt[jj];
+                    const int64_t fo = chunk_id * S + j0 + jj;
+                    if (cnt + n > SCR_CAP) {
+                        if (lane == 0) flags[fo] = 1;  // overflow: the fp64 kernel recomputes this (chunk, sample)
+                    } else {
+                        for (int e = lane; e < n; e += 32) {
+                            slot_val[fo * slot_stride + cnt + e] = ap_val[k + e];
+                            slot_idx[fo * slot_stride + cnt + e] = ap_idx[k + e];
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) slot_cnt[jj] = cnt + n;
+                    warp_select_topk(ap_val, ap_idx, k + n, k, tk_val + jj * k, tk_idx + jj * k, lane);
+                    __syncwarp();
+                    if (tid == 0) *ap_count = 0;
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// exact fp64 re-evaluation (tes_spec.h sequence) of every kept (chunk, sample, slot) candidate
+__global__ void rff_refine_kernel(const double* __restrict__ cand, int d, const double* __restrict__ feat, int rec,
+                                  int64_t S, int64_t F, double scale, int64_t idx_offset, int64_t nslots_total,
+                                  int slot_stride, double* __restrict__ slot_val, int64_t* __restrict__ slot_idx,
+                                  const int* __restrict__ flags) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nslots_total) return;
+    const int64_t cs = t / SCR_CAP;  // chunk*S + j
+    const int c = (int)(t % SCR_CAP);
+    const int64_t o = cs * slot_stride + c;
+    const int64_t gi = slot_idx[o];
+    if (gi < 0) return;
+    if (flags[cs]) {
+        slot_idx[o] = -1;
+        slot_val[o] = neg_inf();
+        return;
+    }
+    const int64_t j = cs % S;
+    const double* x = cand + (gi - idx_offset) * d;
+    const double* fj = feat + j * F * rec;
+    double xr[RFF_MAX_D_FAST];
+    for (int kk = 0; kk < d; ++kk) xr[kk] = __ldg(x + kk);
+    double acc = 0.0;
+    for (int64_t f = 0; f < F; ++f) {
+        const double* r = fj + f * rec;
+        double h = __ldg(r + d);
+        for (int kk = 0; kk < d; ++kk) h = fma(__ldg(r + kk), xr[kk], h);
+        acc = fma(__ldg(r + d + 1), cospi_spec(h), acc);
+    }
+    slot_val[o] = __dmul_rn(scale, acc);
+}
+
 struct RffPlan {
     int C, threads, unroll, tile, sg, rec;
     int64_t chunk, nchunks, nunits;
     int64_t feat_bytes, part_val_bytes, part_idx_bytes, dense_bytes;
     size_t smem;
+    // fp32 screen
+    int screened, recp, slot_stride;
+    int64_t feat32_bytes, aux_bytes, flags_bytes, total_bytes;
+    size_t smem_screen, smem_fallback;
+    int64_t nunits_screen;
+    int sg_screen;
 };
 
-static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k) {
-    RffPlan p;
+constexpr int64_t SCR_MIN_N = 32768;  // below this the screen's fixed costs are not worth it
+
+static size_t rff_smem_fp64(int rec, int sg, int k, int tile) {
+    return (size_t)RFF_NSTAGE * RFF_FCH * rec * sizeof(double) + 8 * sizeof(uint64_t) + (size_t)sg * k * 16 +
+           (size_t)(tile + RFF_MAX_K) * 16 + 16;
+}
+
+// method: 0 = auto, 1 = fp64 only, 2 = fp32 screen + fp64 refine (when the shape allows it)
+static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int method) {
+    RffPlan p{};
     p.C = 4;
     p.threads = 256;
     p.unroll = 2;
@@ -355,8 +739,16 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k) {
             p.unroll = c2;
         }
     }
-    p.tile = p.threads * p.C;
     p.rec = rff_rec((int)d);
+    p.recp = scr_recp((int)d);
+    const bool can_screen = d <= RFF_MAX_D_FAST && k <= SCR_MAX_K && N >= 1;
+    p.screened = can_screen && (method == 2 || (method == 0 && N >= SCR_MIN_N)) ? 1 : 0;
+    if (p.screened) {
+        p.C = 4;
+        p.threads = 256;
+        p.unroll = 2;
+    }
+    p.tile = p.threads * p.C;
     int64_t ntiles = (N + p.tile - 1) / p.tile;
     if (ntiles < 1) ntiles = 1;
     int64_t tpc = ntiles < 16 ? ntiles : 16;  // tiles per chunk
@@ -371,23 +763,40 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k) {
     p.nchunks = (ntiles + tpc - 1) / tpc;
     p.nunits = p.nchunks * ((S + sg - 1) / sg);
     p.feat_bytes = align_up(S * F * p.rec * (int64_t)sizeof(double), 256);
-    p.part_val_bytes = align_up(p.nchunks * S * k * (int64_t)sizeof(double), 256);
-    p.part_idx_bytes = align_up(p.nchunks * S * k * (int64_t)sizeof(int64_t), 256);
     p.dense_bytes = d > RFF_MAX_D_FAST ? align_up(S * N * (int64_t)sizeof(double), 256) : 0;
-    p.smem = (size_t)RFF_NSTAGE * RFF_FCH * p.rec * sizeof(double) + 8 * sizeof(uint64_t) +
-             (size_t)p.sg * k * 16 + (size_t)(p.tile + RFF_MAX_K) * 16 + 16;
+    p.smem = rff_smem_fp64(p.rec, p.sg, k, p.tile);
+    if (p.screened) {
+        p.slot_stride = SCR_CAP + k;
+        p.sg_screen = p.sg;
+        p.nunits_screen = p.nunits;
+        p.part_val_bytes = align_up(p.nchunks * S * p.slot_stride * (int64_t)sizeof(double), 256);
+        p.part_idx_bytes = align_up(p.nchunks * S * p.slot_stride * (int64_t)sizeof(int64_t), 256);
+        p.feat32_bytes = align_up(S * F * p.recp * (int64_t)sizeof(uint64_t), 256);
+        p.aux_bytes = align_up(64 * 8, 256) + align_up(S * 8, 256);  // xmax[64], bound[S]
+        p.flags_bytes = align_up(p.nchunks * S * (int64_t)sizeof(int), 256);
+        p.smem_screen = (size_t)RFF_NSTAGE * RFF_FCH * p.recp * sizeof(uint64_t) + 8 * sizeof(uint64_t) +
+                        (size_t)p.sg * k * 16 + (size_t)(SCR_TILE + 16) * 16 + 8 * sizeof(double) +
+                        (size_t)p.sg * sizeof(int) + 16;
+        p.smem_fallback = rff_smem_fp64(p.rec, 1, k, p.tile);
+    } else {
+        p.slot_stride = k;
+        p.part_val_bytes = align_up(p.nchunks * S * k * (int64_t)sizeof(double), 256);
+        p.part_idx_bytes = align_up(p.nchunks * S * k * (int64_t)sizeof(int64_t), 256);
+    }
+    p.total_bytes = p.feat_bytes + p.part_val_bytes + p.part_idx_bytes + p.dense_bytes + p.feat32_bytes +
+                    p.aux_bytes + p.flags_bytes;
     return p;
 }
 
 template <int D, int C, int THREADS, int UNROLL>
 static int launch_rff_variant(const RffPlan& p, const double* cand, int64_t N, const double* feat, int64_t S,
                               int64_t F, double scale, int k, int64_t idx_offset, double* part_val,
-                              int64_t* part_idx, cudaStream_t st) {
+                              int64_t* part_idx, const int* flags, int out_stride, int out_off, cudaStream_t st) {
     auto kern = rff_topk_kernel<D, C, THREADS, UNROLL>;
     if (p.smem > 48 * 1024)
         TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     kern<<<(unsigned)p.nunits, THREADS, p.smem, st>>>(cand, N, feat, (int)S, (int)F, scale, k, p.sg, p.chunk,
-                                                      idx_offset, part_val, part_idx);
+                                                      idx_offset, part_val, part_idx, flags, out_stride, out_off);
     TES_LAUNCH_OK();
     return 0;
 }
@@ -395,10 +804,11 @@ static int launch_rff_variant(const RffPlan& p, const double* cand, int64_t N, c
 template <int D>
 static int launch_rff_topk(const RffPlan& p, const double* cand, int64_t N, const double* feat, int64_t S, int64_t F,
                            double scale, int k, int64_t idx_offset, double* part_val, int64_t* part_idx,
-                           cudaStream_t st) {
+                           const int* flags, int out_stride, int out_off, cudaStream_t st) {
 #define TES_V(CC, TT, UU)                                                                                   \
     if (p.C == CC && p.threads == TT && p.unroll == UU)                                                     \
-        return launch_rff_variant<D, CC, TT, UU>(p, cand, N, feat, S, F, scale, k, idx_offset, part_val, part_idx, st);
+        return launch_rff_variant<D, CC, TT, UU>(p, cand, N, feat, S, F, scale, k, idx_offset, part_val, part_idx, \
+                                                 flags, out_stride, out_off, st);
     TES_V(4, 256, 2)
 #ifdef TES_RFF_DEV_VARIANTS
     if constexpr (D == 6 || D == 2 || D == 10) {
@@ -410,20 +820,24 @@ static int launch_rff_topk(const RffPlan& p, const double* cand, int64_t N, cons
     return -100;
 }
 
-}  // namespace tes
-
-using namespace tes;
-
-extern "C" int64_t tes_rff_topk_workspace_bytes(int64_t N, int64_t d, int64_t S, int64_t F, int k) {
-    if (N < 0 || d < 1 || d > 64 || S < 1 || F < 1 || k < 1 || k > RFF_MAX_K) return -1;
-    RffPlan p = rff_plan(N, d, S, F, k);
-    return p.feat_bytes + p.part_val_bytes + p.part_idx_bytes + p.dense_bytes;
+template <int D>
+static int launch_rff_screen(const RffPlan& p, const double* cand, int64_t N, const uint64_t* feat32, int64_t S,
+                             int64_t F, double scale, int k, int64_t idx_offset, const double* bound,
+                             double* slot_val, int64_t* slot_idx, int* flags, cudaStream_t st) {
+    auto kern = rff_screen_kernel<D>;
+    if (p.smem_screen > 48 * 1024)
+        TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_screen));
+    kern<<<(unsigned)p.nunits_screen, SCR_THREADS, p.smem_screen, st>>>(cand, N, feat32, (int)S, (int)F, scale, k,
+                                                                        p.sg_screen, p.chunk, idx_offset, bound,
+                                                                        slot_val, slot_idx, p.slot_stride, flags);
+    TES_LAUNCH_OK();
+    return 0;
 }
 
-extern "C" int tes_rff_topk_f64(const double* cand, int64_t N, int64_t d, const double* W, const double* b,
-                                const double* theta, int64_t S, int64_t F, int w_shared, double sigma, int k,
-                                int64_t idx_offset, int64_t* out_idx, double* out_val, void* ws, int64_t ws_bytes,
-                                void* stream) {
+static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* W, const double* b,
+                        const double* theta, int64_t S, int64_t F, int w_shared, double sigma, int k,
+                        int64_t idx_offset, int64_t* out_idx, double* out_val, void* ws, int64_t ws_bytes,
+                        void* stream, int method) {
     if (N < 0 || (N > 0 && !cand)) return -1;
     if (d < 1 || d > 64) return -3;
     if (!W) return -4;
@@ -435,29 +849,84 @@ extern "C" int tes_rff_topk_f64(const double* cand, int64_t N, int64_t d, const 
     if (k < 1 || k > RFF_MAX_K) return -11;
     if (!out_idx) return -13;
     if (!out_val) return -14;
-    RffPlan p = rff_plan(N, d, S, F, k);
-    int64_t need = p.feat_bytes + p.part_val_bytes + p.part_idx_bytes + p.dense_bytes;
-    if (!ws || ws_bytes < need) return -100;
+    if (method < 0 || method > 2) return -18;
+    RffPlan p = rff_plan(N, d, S, F, k, method);
+    if (!ws || ws_bytes < p.total_bytes) return -100;
     cudaStream_t st = (cudaStream_t)stream;
     char* base = (char*)ws;
     double* feat = (double*)base;
-    double* part_val = (double*)(base + p.feat_bytes);
-    int64_t* part_idx = (int64_t*)(base + p.feat_bytes + p.part_val_bytes);
-    double* dense = (double*)(base + p.feat_bytes + p.part_val_bytes + p.part_idx_bytes);
+    base += p.feat_bytes;
+    double* part_val = (double*)base;
+    base += p.part_val_bytes;
+    int64_t* part_idx = (int64_t*)base;
+    base += p.part_idx_bytes;
+    double* dense = (double*)base;
+    base += p.dense_bytes;
+    uint64_t* feat32 = (uint64_t*)base;
+    base += p.feat32_bytes;
+    unsigned long long* xmax = (unsigned long long*)base;
+    double* bound = (double*)(base + align_up(64 * 8, 256));
+    base += p.aux_bytes;
+    int* flags = (int*)base;
     const double scale = sqrt(2.0 * sigma / (double)F);
 
-    int64_t nsf = S * F;
+    const int64_t nsf = S * F;
     rff_pack_kernel<<<(unsigned)((nsf + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, (int)d, w_shared, p.rec, feat);
     TES_LAUNCH_OK();
     int64_t P = p.nchunks;
+    int kin = k;
     if (N == 0) {
         P = 0;
+    } else if (p.screened) {
+        rff_pack32_kernel<<<(unsigned)((nsf + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, (int)d, w_shared, p.recp,
+                                                                          feat32);
+        TES_LAUNCH_OK();
+        TES_CUDA_OK(cudaMemsetAsync(xmax, 0, 64 * 8, st));
+        rff_xmax_kernel<<<148 * 4, 256, 0, st>>>(cand, N, (int)d, xmax);
+        TES_LAUNCH_OK();
+        rff_bound_kernel<<<(unsigned)S, 32, 0, st>>>(feat, p.rec, S, F, (int)d, xmax, scale, bound);
+        TES_LAUNCH_OK();
+        int rc = 0;
+        switch (d) {
+#define TES_CASE(DD)                                                                                            \
+    case DD:                                                                                                    \
+        rc = launch_rff_screen<DD>(p, cand, N, feat32, S, F, scale, k, idx_offset, bound, part_val, part_idx,  \
+                                   flags, st);                                                                  \
+        break;
+            TES_CASE(1) TES_CASE(2) TES_CASE(3) TES_CASE(4) TES_CASE(5) TES_CASE(6) TES_CASE(7) TES_CASE(8)
+            TES_CASE(9) TES_CASE(10)
+#undef TES_CASE
+        }
+        if (rc) return rc;
+        const int64_t nslots = p.nchunks * S * SCR_CAP;
+        rff_refine_kernel<<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>(cand, (int)d, feat, p.rec, S, F, scale,
+                                                                            idx_offset, nslots, p.slot_stride,
+                                                                            part_val, part_idx, flags);
+        TES_LAUNCH_OK();
+        // flag-gated fp64 recomputation of overflowed (chunk, sample) units, one CTA each
+        RffPlan fb = p;
+        fb.sg = 1;
+        fb.nunits = p.nchunks * S;
+        fb.smem = p.smem_fallback;
+        switch (d) {
+#define TES_CASE(DD)                                                                                            \
+    case DD:                                                                                                    \
+        rc = launch_rff_topk<DD>(fb, cand, N, feat, S, F, scale, k, idx_offset, part_val, part_idx, flags,     \
+                                 p.slot_stride, SCR_CAP, st);                                                   \
+        break;
+            TES_CASE(1) TES_CASE(2) TES_CASE(3) TES_CASE(4) TES_CASE(5) TES_CASE(6) TES_CASE(7) TES_CASE(8)
+            TES_CASE(9) TES_CASE(10)
+#undef TES_CASE
+        }
+        if (rc) return rc;
+        kin = p.slot_stride;
     } else if (d <= RFF_MAX_D_FAST) {
         int rc = 0;
         switch (d) {
 #define TES_CASE(DD)                                                                                        \
     case DD:                                                                                                \
-        rc = launch_rff_topk<DD>(p, cand, N, feat, S, F, scale, k, idx_offset, part_val, part_idx, st);     \
+        rc = launch_rff_topk<DD>(p, cand, N, feat, S, F, scale, k, idx_offset, part_val, part_idx, nullptr, \
+                                 k, 0, st);                                                                 \
         break;
             TES_CASE(1) TES_CASE(2) TES_CASE(3) TES_CASE(4) TES_CASE(5) TES_CASE(6) TES_CASE(7) TES_CASE(8)
             TES_CASE(9) TES_CASE(10)
@@ -472,9 +941,36 @@ extern "C" int tes_rff_topk_f64(const double* cand, int64_t N, int64_t d, const 
         TES_LAUNCH_OK();
         P = 1;
     }
-    topk_merge_kernel<<<(unsigned)S, 32, 0, st>>>(part_val, part_idx, P, S, k, out_val, out_idx);
+    topk_merge_kernel<<<(unsigned)S, 32, 0, st>>>(part_val, part_idx, P, S, kin, k, out_val, out_idx);
     TES_LAUNCH_OK();
     return 0;
+}
+
+}  // namespace tes
+
+using namespace tes;
+
+extern "C" int64_t tes_rff_topk_workspace_bytes(int64_t N, int64_t d, int64_t S, int64_t F, int k) {
+    if (N < 0 || d < 1 || d > 64 || S < 1 || F < 1 || k < 1 || k > RFF_MAX_K) return -1;
+    // large enough for every method
+    int64_t a = rff_plan(N, d, S, F, k, 1).total_bytes, c = rff_plan(N, d, S, F, k, 2).total_bytes;
+    return a > c ? a : c;
+}
+
+extern "C" int tes_rff_topk_f64(const double* cand, int64_t N, int64_t d, const double* W, const double* b,
+                                const double* theta, int64_t S, int64_t F, int w_shared, double sigma, int k,
+                                int64_t idx_offset, int64_t* out_idx, double* out_val, void* ws, int64_t ws_bytes,
+                                void* stream) {
+    return rff_topk_run(cand, N, d, W, b, theta, S, F, w_shared, sigma, k, idx_offset, out_idx, out_val, ws,
+                        ws_bytes, stream, 0);
+}
+
+extern "C" int tes_rff_topk_method_f64(const double* cand, int64_t N, int64_t d, const double* W, const double* b,
+                                       const double* theta, int64_t S, int64_t F, int w_shared, double sigma, int k,
+                                       int64_t idx_offset, int64_t* out_idx, double* out_val, void* ws,
+                                       int64_t ws_bytes, void* stream, int method) {
+    return rff_topk_run(cand, N, d, W, b, theta, S, F, w_shared, sigma, k, idx_offset, out_idx, out_val, ws,
+                        ws_bytes, stream, method);
 }
 
 extern "C" int tes_topk_merge_f64(const double* vals, const int64_t* idx, int64_t P, int64_t S, int k,
@@ -486,7 +982,7 @@ extern "C" int tes_topk_merge_f64(const double* vals, const int64_t* idx, int64_
     if (k < 1 || k > 64) return -5;
     if (!out_val) return -6;
     if (!out_idx) return -7;
-    topk_merge_kernel<<<(unsigned)S, 32, 0, (cudaStream_t)stream>>>(vals, idx, P, S, k, out_val, out_idx);
+    topk_merge_kernel<<<(unsigned)S, 32, 0, (cudaStream_t)stream>>>(vals, idx, P, S, k, k, out_val, out_idx);
     TES_LAUNCH_OK();
     return 0;
 }

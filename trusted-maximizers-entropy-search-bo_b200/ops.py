@@ -19,9 +19,12 @@ def _rff_args(cand, W, b, theta):
     return cand, W, b, theta, N, d, S, F, w_shared
 
 
-def rff_topk(cand, W, b, theta, sigma, k=1, idx_offset=0):
+RFF_AUTO, RFF_FP64, RFF_SCREEN = 0, 1, 2
+
+
+def rff_topk(cand, W, b, theta, sigma, k=1, idx_offset=0, method=RFF_AUTO):
     """Top-k candidates of every RFF function sample -> (idx (S,k) int64, val (S,k)) CUDA tensors.
-    utils_for_continuous.py:172-187."""
+    utils_for_continuous.py:172-187.  `method`: RFF_AUTO / RFF_FP64 / RFF_SCREEN (identical results)."""
     cand, W, b, theta, N, d, S, F, ws_ = _rff_args(cand, W, b, theta)
     L = _lib.lib()
     need = L.tes_rff_topk_workspace_bytes(N, d, S, F, k)
@@ -30,8 +33,9 @@ def rff_topk(cand, W, b, theta, sigma, k=1, idx_offset=0):
     ws = WORKSPACE.get(need, cand.device)
     out_idx = torch.empty((S, k), dtype=torch.int64, device=cand.device)
     out_val = torch.empty((S, k), dtype=torch.float64, device=cand.device)
-    rc = L.tes_rff_topk_f64(ptr(cand), N, d, ptr(W), ptr(b), ptr(theta), S, F, ws_, float(sigma), int(k),
-                            int(idx_offset), ptr(out_idx), ptr(out_val), ptr(ws), ws.numel(), stream_ptr())
+    rc = L.tes_rff_topk_method_f64(ptr(cand), N, d, ptr(W), ptr(b), ptr(theta), S, F, ws_, float(sigma), int(k),
+                                   int(idx_offset), ptr(out_idx), ptr(out_val), ptr(ws), ws.numel(), stream_ptr(),
+                                   int(method))
     _lib.check(rc, "tes_rff_topk_f64")
     return out_idx, out_val
 
