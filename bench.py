@@ -246,6 +246,7 @@ def main():
 
     # ---- fp64 pipe peak (roofline denominator; not in MEASURED_PEAKS.json)
     fp64_peak = ops.fp64_fma_peak(1.0)
+    fp32_peak = ops.fp32_fma_peak(1.0)
 
     for w in range(args.warmup):
         flush.zero_()
@@ -297,16 +298,36 @@ def main():
     t_rff = float(np.mean(ra)) if ra else float("nan")
     d, F = wl["d"], wl["F"]
     local_pairs = wl["N"] * wl["S"]
-    instr = local_pairs * F * (d + 13)           # fp64-pipe instructions per launch (tes_spec.h sequence)
-    achieved = 2.0 * instr / t_rff * 1e-12       # FMA-equivalent TFLOP/s, same convention as the DFMA burn
     algo_excl_cos = local_pairs * F * (2 * d + 3) / t_rff * 1e-12  # SURVEY 8(d) figure, cos not counted
-    roofline = {"bound": "fp64", "kernel": "rff_topk_kernel", "achieved": achieved, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
-                "peak_source": "measured in this run: tes_fp64_fma_burn (8 DFMA chains/thread, 1 s sustained)",
-                "algorithmic_excl_cos_tflops": algo_excl_cos,
-                "per_unit": "F*(d+13) fp64-pipe instr per (candidate, sample) pair = F*(2d+3) flops + F cos (12 instr)",
-                "launch_ms": t_rff * 1e3, "share_of_step": t_rff * args.steps / dev_s,
-                "criterion_ms": float(np.mean(rc)) * 1e3 if rc else None}
+    screened = wl["N"] >= 32768 and d <= 10
+    if screened:
+        # stage A = fp32 screen (all pairs, packed FFMA2 + MUFU) + exact fp64 refine of the kept candidates.
+        # fp32-pipe lane operations per (pair, feature): d (dot) + 3 (2*pi reduction) + 1 (theta) packed FMA
+        # lanes + 1 FMUL inside __cosf = d + 5, plus 1 MUFU.COS (XU pipe, reported separately).
+        ops32 = local_pairs * F * (d + 5)
+        achieved = 2.0 * ops32 / t_rff * 1e-12
+        roofline = {"bound": "fp32", "kernel": "rff_screen_kernel (+ pack/xmax/bound/refine/fallback/merge)",
+                    "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                    "traffic": None,
+                    "peak_source": "measured in this run: tes_fp32_fma_burn (packed FFMA2, 8 chains/thread, 1 s)",
+                    "fp64_peak_tflops": fp64_peak,
+                    "algorithmic_excl_cos_tflops": algo_excl_cos,
+                    "algorithmic_vs_fp64_peak": algo_excl_cos / fp64_peak,
+                    "mufu_cos_per_s": local_pairs * F / t_rff,
+                    "per_unit": "F*(d+5) fp32-pipe lane ops + F MUFU.COS per (candidate, sample) pair; "
+                                "algorithmic = F*(2d+3) flops + F cos (SURVEY 8d)",
+                    "launch_ms": t_rff * 1e3, "share_of_step": t_rff * args.steps / dev_s,
+                    "criterion_ms": float(np.mean(rc)) * 1e3 if rc else None}
+    else:
+        instr = local_pairs * F * (d + 13)           # fp64-pipe instructions per launch (tes_spec.h sequence)
+        achieved = 2.0 * instr / t_rff * 1e-12       # FMA-equivalent TFLOP/s, same convention as the DFMA burn
+        roofline = {"bound": "fp64", "kernel": "rff_topk_kernel", "achieved": achieved, "peak": fp64_peak,
+                    "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                    "peak_source": "measured in this run: tes_fp64_fma_burn (8 DFMA chains/thread, 1 s sustained)",
+                    "algorithmic_excl_cos_tflops": algo_excl_cos,
+                    "per_unit": "F*(d+13) fp64-pipe instr per (candidate, sample) pair = F*(2d+3) flops + F cos",
+                    "launch_ms": t_rff * 1e3, "share_of_step": t_rff * args.steps / dev_s,
+                    "criterion_ms": float(np.mean(rc)) * 1e3 if rc else None}
 
     line = None
     if rank == 0:

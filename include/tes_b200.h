@@ -175,6 +175,9 @@ int tes_batch_ep_acq_f64(const double* p, int64_t Sp, int64_t nx, double* out_ac
 int64_t tes_launch_count(void);
 
 int tes_fp64_fma_burn(int blocks, int64_t iters, double* sink, double* flops, void* stream);
+/* Same for the packed fp32 pipe (FFMA2, fma.rn.f32x2): the denominator for the fp32 screen of stage A.
+ * `sink`: at least blocks*256 floats. */
+int tes_fp32_fma_burn(int blocks, int64_t iters, float* sink, double* flops, void* stream);
 
 #ifdef __cplusplus
 }

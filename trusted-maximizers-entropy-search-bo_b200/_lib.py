@@ -67,6 +67,7 @@ SIGNATURES = {
                                c_ptr, c_ptr, c_i64, c_ptr]),
     "tes_batch_ep_acq_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "tes_launch_count": (c_i64, []),
+    "tes_fp32_fma_burn": (c_int, [c_int, c_i64, c_ptr, ctypes.POINTER(c_dbl), c_ptr]),
     "tes_fp64_fma_burn": (c_int, [c_int, c_i64, c_ptr, ctypes.POINTER(c_dbl), c_ptr]),
 }
 

@@ -358,11 +358,12 @@ __global__ void topk_merge_kernel(const double* __restrict__ vals, const int64_t
 // kernel (flag-gated launch), so correctness never depends on the list capacity.
 //
 // Error bound (u = 2^-24; A_f = |b'_f| + sum_k |w'_fk| max_i |x_ik|):
-//   |h32 - h|      <= (d+4) u A_f           (input rounding of w', b', x and the d FFMA roundings)
-//   |c32 - cos(pi h)| <= pi (d+4) u A_f + 1.3e-6   (exact reduction to [-1,1] half-turns; x = pi32*r: 2.8e-7;
-//                                                    __cosf on [-pi,pi]: 2^-21.19 per the CUDA guide, doubled)
-//   |acc - sum|    <= 34 u sum_f |theta_f|   (theta rounding, products, 32-term fp32 blocks flushed to fp64)
-//   B_j = 1.25 * scale * sum_f |theta_f| (pi (d+4) u A_f + 1.3e-6 + 34 u)
+//   the screen works in radians: h = b + w.x, n = rint(h/2pi), r = fma(n, -2pi_f32, h), c = __cosf(r)
+//   |h32 - h|      <= (d+4) u pi A_f        (input rounding of w, b, x and the d FFMA roundings)
+//   |r - (h - 2pi n)| <= 1.75e-7 |n| + 2e-7 (2pi_f32 - 2pi = 1.75e-7; one rounding of |r| <= pi), |n| <= A_f/2 + 1
+//   |__cosf(r) - cos(r)| <= 2^-21.19 on [-pi,pi] per the CUDA guide; 1e-6 used
+//   |acc - sum|    <= 34 u sum_f |theta_f|  (theta rounding, products, 32-term fp32 blocks flushed to fp64)
+//   B_j = 1.25 * scale * sum_f |theta_f| ((d+4) u pi A_f + 1.75e-7 (A_f/2+1) + 1.2e-6 + 34 u)
 // =====================================================================================================
 constexpr int SCR_THREADS = 256;
 constexpr int SCR_TILE = SCR_THREADS * 4;  // 4 candidates (2 packed pairs) per thread
@@ -401,25 +402,36 @@ __global__ void rff_pack32_kernel(const double* __restrict__ W, const double* __
     int64_t jw = w_shared ? 0 : j;
     const double* w = W + (jw * F + f) * d;
     uint64_t* o = feat32 + t * recp;
+    // the fp32 screen works in RADIANS (no 1/pi prescale): the 2*pi reduction folds into one FFMA2
     for (int k = 0; k < d; ++k) {
-        float v = __double2float_rn(__dmul_rn(w[k], TES_INV_PI));
+        float v = __double2float_rn(w[k]);
         o[k] = f2_pack(v, v);
     }
-    float bv = __double2float_rn(__dmul_rn(b[jw * F + f], TES_INV_PI));
+    float bv = __double2float_rn(b[jw * F + f]);
     o[d] = f2_pack(bv, bv);
     float tv = __double2float_rn(theta[t]);
     o[d + 1] = f2_pack(tv, tv);
     for (int k = d + 2; k < recp; ++k) o[k] = 0ull;
 }
 
-// xmax[k] = max_i |x_ik| (bit pattern of a non-negative double orders like an unsigned integer)
+// xmax[k] = max_i |x_ik| (bit pattern of a non-negative double orders like an unsigned integer).
+// Each thread walks whole rows (stride = grid size), keeps d running maxima in registers via shared memory
+// per-dimension atomics, then one global atomic per dimension per block.
 __global__ void rff_xmax_kernel(const double* __restrict__ cand, int64_t N, int d, unsigned long long* xmax) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ unsigned long long sm[64];
+    if (threadIdx.x < 64) sm[threadIdx.x] = 0ull;
+    __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; e < N * d; e += stride) {
-        double a = fabs(cand[e]);
-        atomicMax(xmax + (e % d), (unsigned long long)__double_as_longlong(a));
+    for (int kk = 0; kk < d; ++kk) {
+        double m = 0.0;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
+            m = fmax(m, fabs(cand[i * d + kk]));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+        if ((threadIdx.x & 31) == 0) atomicMax(&sm[kk], (unsigned long long)__double_as_longlong(m));
     }
+    __syncthreads();
+    if (threadIdx.x < d) atomicMax(xmax + threadIdx.x, sm[threadIdx.x]);
 }
 
 // one warp per sample: B_j from the fp64 feature records [w'(d), b', theta]
@@ -432,16 +444,19 @@ __global__ void rff_bound_kernel(const double* __restrict__ feat, int rec, int64
     double e = 0.0;
     for (int64_t f = lane; f < F; f += 32) {
         const double* r = feat + (j * F + f) * rec;
-        double A = fabs(r[d]);
+        double A = fabs(r[d]);  // records hold w/pi, b/pi: A is in half-turns, pi*A in radians
         for (int k = 0; k < d; ++k) A += fabs(r[k]) * __longlong_as_double((long long)xmax[k]);
-        e += fabs(r[d + 1]) * (3.14159265358979323846 * (d + 4) * u * A + 1.3e-6 + 34.0 * u);
+        const double Arad = 3.14159265358979323846 * A;
+        const double nmax = 0.5 * A + 1.0;  // |rint(h / 2pi)| <= A/2 + 1
+        // argument rounding + (2pi_f32 - 2pi) * n + final rounding of r + __cosf error (doubled) + accumulation
+        e += fabs(r[d + 1]) * ((d + 4) * u * Arad + 1.75e-7 * nmax + 2.0e-7 + 1.0e-6 + 34.0 * u);
     }
     e = warp_sum(e);
     if (lane == 0) bound[j] = 1.25 * scale * e;
 }
 
-template <int D>
-__global__ void __launch_bounds__(SCR_THREADS)
+template <int D, int UNROLL, int MINB>
+__global__ void __launch_bounds__(SCR_THREADS, MINB)
     rff_screen_kernel(const double* __restrict__ cand, int64_t N, const uint64_t* __restrict__ feat32, int S, int F,
                       double scale, int k, int sg, int64_t chunk, int64_t idx_offset,
                       const double* __restrict__ bound, double* __restrict__ slot_val,
@@ -512,11 +527,10 @@ __global__ void __launch_bounds__(SCR_THREADS)
         for (int p = 0; p < RFF_NSTAGE - 1 && p_left > 0; ++p) issue();
     }
 
-    const uint64_t HALF2 = f2_pack(0.5f, 0.5f);
+    const uint64_t INV2PI2 = f2_pack(0.15915494f, 0.15915494f);
     const uint64_t MAGIC2 = f2_pack(12582912.0f, 12582912.0f);  // 1.5 * 2^23
     const uint64_t NMAGIC2 = f2_pack(-12582912.0f, -12582912.0f);
-    const uint64_t NTWO2 = f2_pack(-2.0f, -2.0f);
-    const uint64_t PI2 = f2_pack(3.14159274f, 3.14159274f);
+    const uint64_t NTWOPI2 = f2_pack(-6.2831855f, -6.2831855f);
 
     uint64_t x2[2][D];
     double dacc[4];
@@ -552,7 +566,7 @@ __global__ void __launch_bounds__(SCR_THREADS)
                 for (int f0 = 0; f0 < fcnt; f0 += 32) {
                     const int fe = min(fcnt, f0 + 32);
                     uint64_t acc2[2] = {0ull, 0ull};
-#pragma unroll 2
+#pragma unroll UNROLL
                     for (int f = f0; f < fe; ++f) {
                         uint64_t w[RECP];
                         const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(sp + f * RECP);
@@ -567,11 +581,10 @@ __global__ void __launch_bounds__(SCR_THREADS)
                             uint64_t h = w[D];
 #pragma unroll
                             for (int kk = 0; kk < D; ++kk) h = ffma2(w[kk], x2[pp][kk], h);
-                            // r = h - 2*rint(h/2) in [-1,1] half-turns (exact), x = pi*r, cos via MUFU
-                            uint64_t t = ffma2(h, HALF2, MAGIC2);
+                            // r = h - 2pi*rint(h/2pi) in [-pi,pi] (one FFMA2), cos via MUFU
+                            uint64_t t = ffma2(h, INV2PI2, MAGIC2);
                             uint64_t n = fadd2(t, NMAGIC2);
-                            uint64_t r = ffma2(n, NTWO2, h);
-                            uint64_t xr = fmul2(r, PI2);
+                            uint64_t xr = ffma2(n, NTWOPI2, h);
                             uint64_t cs = f2_pack(__cosf(f2_lo(xr)), __cosf(f2_hi(xr)));
                             acc2[pp] = ffma2(w[D + 1], cs, acc2[pp]);
                         }
@@ -824,9 +837,24 @@ template <int D>
 static int launch_rff_screen(const RffPlan& p, const double* cand, int64_t N, const uint64_t* feat32, int64_t S,
                              int64_t F, double scale, int k, int64_t idx_offset, const double* bound,
                              double* slot_val, int64_t* slot_idx, int* flags, cudaStream_t st) {
-    auto kern = rff_screen_kernel<D>;
+    int un = 8, mb = 2;
+    if (const char* v = getenv("TES_SCR_VARIANT")) sscanf(v, "%d,%d", &un, &mb);  // developer knob
+    void (*kern)(const double*, int64_t, const uint64_t*, int, int, double, int, int, int64_t, int64_t, const double*,
+                 double*, int64_t*, int, int*) = rff_screen_kernel<D, 8, 2>;
+#ifdef TES_RFF_DEV_VARIANTS
+    if constexpr (D == 6) {
+        if (un == 4 && mb == 1) kern = rff_screen_kernel<D, 4, 1>;
+        if (un == 2 && mb == 3) kern = rff_screen_kernel<D, 2, 3>;
+        if (un == 4 && mb == 3) kern = rff_screen_kernel<D, 4, 3>;
+        if (un == 4 && mb == 2) kern = rff_screen_kernel<D, 4, 2>;
+        if (un == 2 && mb == 1) kern = rff_screen_kernel<D, 2, 1>;
+        if (un == 1 && mb == 3) kern = rff_screen_kernel<D, 1, 3>;
+        if (un == 8 && mb == 1) kern = rff_screen_kernel<D, 8, 1>;
+    }
+#endif
     if (p.smem_screen > 48 * 1024)
         TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_screen));
+    TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     kern<<<(unsigned)p.nunits_screen, SCR_THREADS, p.smem_screen, st>>>(cand, N, feat32, (int)S, (int)F, scale, k,
                                                                         p.sg_screen, p.chunk, idx_offset, bound,
                                                                         slot_val, slot_idx, p.slot_stride, flags);

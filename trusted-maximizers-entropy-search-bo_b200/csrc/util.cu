@@ -28,7 +28,35 @@ __global__ void __launch_bounds__(256) fp64_fma_burn_kernel(int64_t iters, doubl
     }
     sink[(int64_t)blockIdx.x * 256 + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
+// packed fp32 (FFMA2) burn: 8 independent chains of f32x2 FMAs per thread.  flops = blocks*256*iters*8*2*2.
+__global__ void __launch_bounds__(256) fp32_fma_burn_kernel(int64_t iters, float* sink) {
+    unsigned long long a[8];
+    const float base = 1.0f + threadIdx.x * 1e-6f;
+    for (int q = 0; q < 8; ++q) {
+        float v = base + q * 1e-3f;
+        a[q] = ((unsigned long long)__float_as_uint(v) << 32) | __float_as_uint(v + 1e-4f);
+    }
+    const unsigned long long m = ((unsigned long long)__float_as_uint(0.99999f) << 32) | __float_as_uint(0.99999f);
+    const unsigned long long c = ((unsigned long long)__float_as_uint(1e-5f) << 32) | __float_as_uint(1e-5f);
+    for (int64_t i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[q]) : "l"(m), "l"(c));
+    }
+    float s = 0.f;
+    for (int q = 0; q < 8; ++q) s += __uint_as_float((unsigned)a[q]) + __uint_as_float((unsigned)(a[q] >> 32));
+    sink[(int64_t)blockIdx.x * 256 + threadIdx.x] = s;
+}
 }  // namespace tes
+
+extern "C" int tes_fp32_fma_burn(int blocks, int64_t iters, float* sink, double* flops, void* stream) {
+    if (blocks < 1) return -1;
+    if (iters < 1) return -2;
+    if (!sink) return -3;
+    tes::fp32_fma_burn_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    TES_LAUNCH_OK();
+    if (flops) *flops = (double)blocks * 256.0 * (double)iters * 32.0;
+    return 0;
+}
 
 extern "C" int tes_fp64_fma_burn(int blocks, int64_t iters, double* sink, double* flops, void* stream) {
     if (blocks < 1) return -1;

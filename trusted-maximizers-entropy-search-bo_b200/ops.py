@@ -62,21 +62,22 @@ def topk_merge(vals, idx):
     return out_idx, out_val
 
 
-def fp64_fma_peak(seconds=0.5, device=None):
-    """Sustained DFMA rate (TFLOP/s) of the current device, timed with CUDA events."""
+def fp64_fma_peak(seconds=0.5, device=None, fp32=False):
+    """Sustained DFMA (or, fp32=True, packed-FFMA2) rate in TFLOP/s of the current device, CUDA-event timed."""
     import ctypes
     L = _lib.lib()
     dev_ = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     nsm = torch.cuda.get_device_properties(dev_).multi_processor_count
     blocks = nsm * 8
-    sink = torch.empty(blocks * 256, dtype=torch.float64, device=dev_)
+    sink = torch.empty(blocks * 256, dtype=torch.float32 if fp32 else torch.float64, device=dev_)
     flops = ctypes.c_double(0.0)
     iters = 1 << 16
+    burn = L.tes_fp32_fma_burn if fp32 else L.tes_fp64_fma_burn
 
     def run(it):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(L.tes_fp64_fma_burn(blocks, it, ptr(sink), ctypes.byref(flops), stream_ptr()), "burn")
+        _lib.check(burn(blocks, it, ptr(sink), ctypes.byref(flops), stream_ptr()), "burn")
         e1.record()
         e1.synchronize()
         return e0.elapsed_time(e1) * 1e-3, flops.value
@@ -86,6 +87,10 @@ def fp64_fma_peak(seconds=0.5, device=None):
     it2 = max(iters, int(iters * seconds / max(t, 1e-6)))
     t, fl = run(it2)
     return fl / t * 1e-12
+
+
+def fp32_fma_peak(seconds=0.5, device=None):
+    return fp64_fma_peak(seconds, device, fp32=True)
 
 
 # ------------------------------------------------------------------------------------- stage B
