@@ -42,14 +42,16 @@ class _Timed:
 class Shard:
     """Describes this rank's contiguous slice of the global candidate set."""
 
-    def __init__(self, n_local, group=None):
+    def __init__(self, n_local, group=None, device=None):
         import torch.distributed as dist
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.group = group
         self.world = self.dist.get_world_size(group) if self.dist else 1
         self.rank = self.dist.get_rank(group) if self.dist else 0
         if self.world > 1:
-            counts = torch.zeros(self.world, dtype=torch.int64, device="cuda")
+            if device is None:  # NCCL moves device tensors, gloo (CPU tests of the host logic) host tensors
+                device = "cuda" if self.dist.get_backend(group) == "nccl" else "cpu"
+            counts = torch.zeros(self.world, dtype=torch.int64, device=device)
             counts[self.rank] = n_local
             self.dist.all_reduce(counts, group=group)
             c = counts.cpu().numpy()
@@ -61,14 +63,40 @@ class Shard:
     def all_gather(self, t):
         if self.world == 1:
             return t.unsqueeze(0)
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out
+        flat = t.contiguous().reshape(-1)
+        out = torch.empty(self.world * flat.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, flat, group=self.group)
+        return out.reshape((self.world,) + tuple(t.shape))
 
     def sum(self, t):
         if self.world > 1:
             self.dist.all_reduce(t, group=self.group)
         return t
+
+
+def merge_topk_host(vals, idx, k):
+    """Reference semantics of tes_topk_merge_f64 on host tensors: (P,S,kin) -> (S,k) by (value desc, index asc),
+    entries with idx < 0 ignored, duplicated (value, index) pairs collapsed.  Used by the CPU (gloo) tests of
+    the sharding logic; the product path merges on the device."""
+    P, S, kin = vals.shape
+    ov = torch.full((S, k), float("-inf"), dtype=torch.float64)
+    oi = torch.full((S, k), -1, dtype=torch.int64)
+    for j in range(S):
+        ent = sorted({(-float(vals[p, j, q]), int(idx[p, j, q])) for p in range(P) for q in range(kin)
+                      if int(idx[p, j, q]) >= 0})
+        for r, (nv, i) in enumerate(ent[:k]):
+            ov[j, r], oi[j, r] = -nv, i
+    return oi, ov
+
+
+def gather_and_merge(shard, idx, val):
+    """All-gather the per-rank (S,k) partial lists and merge them (device kernel on CUDA tensors)."""
+    if shard.world == 1:
+        return idx, val
+    gv, gi = shard.all_gather(val), shard.all_gather(idx)
+    if val.is_cuda:
+        return ops.topk_merge(gv, gi)
+    return merge_topk_host(gv, gi, val.shape[1])
 
 
 def trusted_maximizers(cand, W, b, theta, sigma, shard=None, k=1, timers=None):
@@ -77,8 +105,7 @@ def trusted_maximizers(cand, W, b, theta, sigma, shard=None, k=1, timers=None):
     shard = shard or Shard(cand.shape[0])
     with _Timed(timers, "rff_topk"):
         idx, val = ops.rff_topk(cand, W, b, theta, sigma, k=k, idx_offset=shard.offset)
-    if shard.world > 1:
-        idx, val = ops.topk_merge(shard.all_gather(val), shard.all_gather(idx))
+    idx, val = gather_and_merge(shard, idx, val)
     local = idx - shard.offset
     mine = (local >= 0) & (local < cand.shape[0]) & (idx >= 0)
     pts = torch.zeros(idx.shape + (cand.shape[1],), dtype=torch.float64, device=cand.device)
