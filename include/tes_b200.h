@@ -171,10 +171,16 @@ int tes_batch_ep_acq_f64(const double* p, int64_t Sp, int64_t nx, double* out_ac
  * kernels (MEASURED_PEAKS.json carries only HBM and bf16 numbers).  Runs `iters` dependent-chain
  * DFMA rounds on `blocks` CTAs; returns the flop count through *flops; time it with CUDA events on
  * `stream`.  `sink` is a device buffer of at least blocks*256 doubles. */
+/* Test probe for the fp32 screen's error model: max over EVERY float x in [lo, hi] (both signs) of
+ * |__cosf(x) - cos(x)| - e1*|x|, written to *out_max (device double; 0 if never positive). */
+int tes_cosf_error_probe(float lo, float hi, double e1, double* out_max, void* stream);
+
 /* number of kernels this library has launched in this process so far (monotonic statistic) */
 int64_t tes_launch_count(void);
 
 int tes_fp64_fma_burn(int blocks, int64_t iters, double* sink, double* flops, void* stream);
+/* Same for the fp64 tensor-core path (mma.sync m8n8k4 f64): measured to decide whether DMMA is worth using. */
+int tes_fp64_mma_burn(int blocks, int64_t iters, double* sink, double* flops, void* stream);
 /* Same for the packed fp32 pipe (FFMA2, fma.rn.f32x2): the denominator for the fp32 screen of stage A.
  * `sink`: at least blocks*256 floats. */
 int tes_fp32_fma_burn(int blocks, int64_t iters, float* sink, double* flops, void* stream);

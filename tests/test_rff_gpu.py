@@ -167,3 +167,37 @@ def test_screened_topk_near_ties_many_seeds():
         i1, v1 = ops.rff_topk(cand, W, b, theta, 1.3, k=3, method=ops.RFF_FP64)
         i2, v2 = ops.rff_topk(cand, W, b, theta, 1.3, k=3, method=ops.RFF_SCREEN)
         assert torch.equal(i1, i2) and torch.equal(v1, v2), seed
+
+
+def test_cosf_error_model_exhaustive():
+    """The fp32 screen's no-reduction path relies on |__cosf(x) - cos(x)| <= 6.0e-7 + 1.3e-7 |x| for |x| <= 512.
+    Verified here over EVERY float in (0, 512] (both signs) on the device that runs the kernels."""
+    import torch
+    from tes_b200 import _lib
+    from tes_b200.device import ptr, stream_ptr
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    rc = _lib.lib().tes_cosf_error_probe(0.0, 512.0, 1.3e-7, ptr(out), stream_ptr())
+    _lib.check(rc, "tes_cosf_error_probe")
+    worst = float(out.cpu()[0])
+    assert worst < 6.0e-7, worst
+    # and the documented small-argument behaviour, [-pi, pi]: 2^-21.19 (CUDA programming guide) with slack
+    out.zero_()
+    _lib.check(_lib.lib().tes_cosf_error_probe(0.0, 3.1415927, 0.0, ptr(out), stream_ptr()), "probe")
+    assert float(out.cpu()[0]) < 6.0e-7
+
+
+def test_screened_topk_large_arguments_use_reduction_path():
+    """|W x + b| far beyond the verified __cosf domain: the per-sample mode switches to the explicit 2*pi
+    reduction; results stay bit-identical."""
+    import torch
+    from tes_b200 import ops
+    rs = np.random.RandomState(4)
+    N, d, S, F = 40_000, 2, 6, 96
+    cand = rs.rand(N, d) * 10.0
+    W = rs.randn(S, F, d) * 40.0          # |h| up to ~1e3 rad
+    W[:3] *= 0.02                          # first three samples stay in the direct domain
+    b = 2 * np.pi * rs.rand(S, F, 1)
+    theta = rs.randn(S, F, 1)
+    i1, v1 = ops.rff_topk(cand, W, b, theta, 0.9, k=2, method=ops.RFF_FP64)
+    i2, v2 = ops.rff_topk(cand, W, b, theta, 0.9, k=2, method=ops.RFF_SCREEN)
+    assert torch.equal(i1, i2) and torch.equal(v1, v2)

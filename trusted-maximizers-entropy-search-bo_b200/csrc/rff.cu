@@ -18,6 +18,9 @@
 //     (one __syncthreads_or); only improving tiles take the slow path (append + warp selection).
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <type_traits>
 
 #include "tes_common.cuh"
 
@@ -434,33 +437,72 @@ __global__ void rff_xmax_kernel(const double* __restrict__ cand, int64_t N, int 
     if (threadIdx.x < d) atomicMax(xmax + threadIdx.x, sm[threadIdx.x]);
 }
 
-// one warp per sample: B_j from the fp64 feature records [w'(d), b', theta]
+// |__cosf(x) - cos(x)| <= SCR_E0 + SCR_E1 |x| for |x| <= SCR_XMAX: __cosf is FMUL.RZ(x, 1/2pi) (<= 1 ulp = 2^-23
+// relative, i.e. <= 2^-23 |x| radians) followed by MUFU.COS on revolutions (2^-21.19 on [-pi,pi] per the CUDA
+// guide).  The linear model is verified EXHAUSTIVELY over every float in the domain by
+// tes_cosf_error_probe (tests/test_rff_gpu.py); samples whose arguments can exceed SCR_XMAX use the
+// explicit 2*pi reduction instead.
+constexpr double SCR_E0 = 6.0e-7;
+constexpr double SCR_E1 = 1.3e-7;
+constexpr double SCR_XMAX = 512.0;
+
+// one warp per sample: B_j from the fp64 feature records [w'(d), b', theta]; mode[j] = 1 when the explicit
+// range reduction is needed (arguments may leave the verified domain of __cosf)
 __global__ void rff_bound_kernel(const double* __restrict__ feat, int rec, int64_t S, int64_t F, int d,
                                  const unsigned long long* __restrict__ xmax, double scale,
-                                 double* __restrict__ bound) {
+                                 double* __restrict__ bound, int* __restrict__ mode) {
     const int64_t j = blockIdx.x;
     const int lane = threadIdx.x;
     const double u = 5.9604644775390625e-08;  // 2^-24
-    double e = 0.0;
+    double e_red = 0.0, e_dir = 0.0, amax = 0.0;
     for (int64_t f = lane; f < F; f += 32) {
         const double* r = feat + (j * F + f) * rec;
         double A = fabs(r[d]);  // records hold w/pi, b/pi: A is in half-turns, pi*A in radians
         for (int k = 0; k < d; ++k) A += fabs(r[k]) * __longlong_as_double((long long)xmax[k]);
-        const double Arad = 3.14159265358979323846 * A;
+        const double Arad = 3.14159265358979323846 * A * (1.0 + 1e-6);
         const double nmax = 0.5 * A + 1.0;  // |rint(h / 2pi)| <= A/2 + 1
-        // argument rounding + (2pi_f32 - 2pi) * n + final rounding of r + __cosf error (doubled) + accumulation
-        e += fabs(r[d + 1]) * ((d + 4) * u * Arad + 1.75e-7 * nmax + 2.0e-7 + 1.0e-6 + 34.0 * u);
+        const double th = fabs(r[d + 1]);
+        // reduced path: argument rounding + (2pi_f32 - 2pi) n + rounding of r + __cosf on [-pi,pi] + accumulation
+        e_red += th * ((d + 4) * u * Arad + 1.75e-7 * nmax + 2.0e-7 + 1.0e-6 + 34.0 * u);
+        // direct path: argument rounding + verified __cosf model on |x| <= Arad + accumulation
+        e_dir += th * ((d + 4) * u * Arad + SCR_E0 + SCR_E1 * Arad + 34.0 * u);
+        amax = fmax(amax, Arad);
     }
-    e = warp_sum(e);
-    if (lane == 0) bound[j] = 1.25 * scale * e;
+    e_red = warp_sum(e_red);
+    e_dir = warp_sum(e_dir);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+    if (lane == 0) {
+        const int m = (amax <= SCR_XMAX) ? 0 : 1;
+        mode[j] = m;
+        bound[j] = 1.25 * scale * (m ? e_red : e_dir);
+    }
+}
+
+// test probe: max over every float x in [lo, hi] (both signs) of |__cosf(x) - cos(x)| - e1 |x|
+__global__ void cosf_probe_kernel(unsigned lo_bits, unsigned hi_bits, double e1, double* out) {
+    double m = -1.0;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned long long bits = (unsigned long long)lo_bits + blockIdx.x * blockDim.x + threadIdx.x;
+         bits <= hi_bits; bits += stride) {
+        float x = __uint_as_float((unsigned)bits);
+        double ref = cos((double)x);
+        double e = fmax(fabs((double)__cosf(x) - ref), fabs((double)__cosf(-x) - ref)) - e1 * fabs((double)x);
+        m = fmax(m, e);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0 && m > 0.0)
+        atomicMax((unsigned long long*)out, (unsigned long long)__double_as_longlong(m));
 }
 
 template <int D, int UNROLL, int MINB>
 __global__ void __launch_bounds__(SCR_THREADS, MINB)
     rff_screen_kernel(const double* __restrict__ cand, int64_t N, const uint64_t* __restrict__ feat32, int S, int F,
                       double scale, int k, int sg, int64_t chunk, int64_t idx_offset,
-                      const double* __restrict__ bound, double* __restrict__ slot_val,
-                      int64_t* __restrict__ slot_idx, int slot_stride, int* __restrict__ flags) {
+                      const double* __restrict__ bound, const int* __restrict__ mode,
+                      double* __restrict__ slot_val, int64_t* __restrict__ slot_idx, int slot_stride,
+                      int* __restrict__ flags) {
     constexpr int RECP = scr_recp(D);
     constexpr int THREADS = SCR_THREADS;
     constexpr int TILE = SCR_TILE;
@@ -558,42 +600,52 @@ __global__ void __launch_bounds__(SCR_THREADS, MINB)
         for (int jj = 0; jj < nj; ++jj) {
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) dacc[cc] = 0.0;
+            const int red = mode[j0 + jj];
             for (int c = 0; c < nch; ++c) {
                 if (tid == 0 && p_left > 0) issue();
                 mbar_wait(&full[slot], phase);
                 const int fcnt = min(RFF_FCH, F - c * RFF_FCH);
                 const uint64_t* sp = stage + slot * RFF_FCH * RECP;
-                for (int f0 = 0; f0 < fcnt; f0 += 32) {
-                    const int fe = min(fcnt, f0 + 32);
-                    uint64_t acc2[2] = {0ull, 0ull};
+                auto run_chunk = [&](auto reduce_tag) {
+                    constexpr bool REDUCE = decltype(reduce_tag)::value;
+                    for (int f0 = 0; f0 < fcnt; f0 += 32) {
+                        const int fe = min(fcnt, f0 + 32);
+                        uint64_t acc2[2] = {0ull, 0ull};
 #pragma unroll UNROLL
-                    for (int f = f0; f < fe; ++f) {
-                        uint64_t w[RECP];
-                        const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(sp + f * RECP);
+                        for (int f = f0; f < fe; ++f) {
+                            uint64_t w[RECP];
+                            const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(sp + f * RECP);
 #pragma unroll
-                        for (int q = 0; q < RECP / 2; ++q) {
-                            ulonglong2 v = rp[q];
-                            w[2 * q] = v.x;
-                            w[2 * q + 1] = v.y;
+                            for (int q = 0; q < RECP / 2; ++q) {
+                                ulonglong2 v = rp[q];
+                                w[2 * q] = v.x;
+                                w[2 * q + 1] = v.y;
+                            }
+#pragma unroll
+                            for (int pp = 0; pp < 2; ++pp) {
+                                uint64_t h = w[D];
+#pragma unroll
+                                for (int kk = 0; kk < D; ++kk) h = ffma2(w[kk], x2[pp][kk], h);
+                                uint64_t xr = h;
+                                if (REDUCE) {  // r = h - 2pi*rint(h/2pi) in [-pi,pi] (one FFMA2 after the rint)
+                                    uint64_t t = ffma2(h, INV2PI2, MAGIC2);
+                                    uint64_t n = fadd2(t, NMAGIC2);
+                                    xr = ffma2(n, NTWOPI2, h);
+                                }
+                                uint64_t cs = f2_pack(__cosf(f2_lo(xr)), __cosf(f2_hi(xr)));
+                                acc2[pp] = ffma2(w[D + 1], cs, acc2[pp]);
+                            }
                         }
-#pragma unroll
-                        for (int pp = 0; pp < 2; ++pp) {
-                            uint64_t h = w[D];
-#pragma unroll
-                            for (int kk = 0; kk < D; ++kk) h = ffma2(w[kk], x2[pp][kk], h);
-                            // r = h - 2pi*rint(h/2pi) in [-pi,pi] (one FFMA2), cos via MUFU
-                            uint64_t t = ffma2(h, INV2PI2, MAGIC2);
-                            uint64_t n = fadd2(t, NMAGIC2);
-                            uint64_t xr = ffma2(n, NTWOPI2, h);
-                            uint64_t cs = f2_pack(__cosf(f2_lo(xr)), __cosf(f2_hi(xr)));
-                            acc2[pp] = ffma2(w[D + 1], cs, acc2[pp]);
-                        }
+                        dacc[0] += (double)f2_lo(acc2[0]);
+                        dacc[1] += (double)f2_hi(acc2[0]);
+                        dacc[2] += (double)f2_lo(acc2[1]);
+                        dacc[3] += (double)f2_hi(acc2[1]);
                     }
-                    dacc[0] += (double)f2_lo(acc2[0]);
-                    dacc[1] += (double)f2_hi(acc2[0]);
-                    dacc[2] += (double)f2_lo(acc2[1]);
-                    dacc[3] += (double)f2_hi(acc2[1]);
-                }
+                };
+                if (red)
+                    run_chunk(std::true_type{});
+                else
+                    run_chunk(std::false_type{});
                 if (++slot == RFF_NSTAGE) {
                     slot = 0;
                     phase ^= 1u;
@@ -785,7 +837,7 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
         p.part_val_bytes = align_up(p.nchunks * S * p.slot_stride * (int64_t)sizeof(double), 256);
         p.part_idx_bytes = align_up(p.nchunks * S * p.slot_stride * (int64_t)sizeof(int64_t), 256);
         p.feat32_bytes = align_up(S * F * p.recp * (int64_t)sizeof(uint64_t), 256);
-        p.aux_bytes = align_up(64 * 8, 256) + align_up(S * 8, 256);  // xmax[64], bound[S]
+        p.aux_bytes = align_up(64 * 8, 256) + 2 * align_up(S * 8, 256);  // xmax[64], bound[S], mode[S]
         p.flags_bytes = align_up(p.nchunks * S * (int64_t)sizeof(int), 256);
         p.smem_screen = (size_t)RFF_NSTAGE * RFF_FCH * p.recp * sizeof(uint64_t) + 8 * sizeof(uint64_t) +
                         (size_t)p.sg * k * 16 + (size_t)(SCR_TILE + 16) * 16 + 8 * sizeof(double) +
@@ -836,11 +888,11 @@ static int launch_rff_topk(const RffPlan& p, const double* cand, int64_t N, cons
 template <int D>
 static int launch_rff_screen(const RffPlan& p, const double* cand, int64_t N, const uint64_t* feat32, int64_t S,
                              int64_t F, double scale, int k, int64_t idx_offset, const double* bound,
-                             double* slot_val, int64_t* slot_idx, int* flags, cudaStream_t st) {
+                             const int* mode, double* slot_val, int64_t* slot_idx, int* flags, cudaStream_t st) {
     int un = 8, mb = 2;
     if (const char* v = getenv("TES_SCR_VARIANT")) sscanf(v, "%d,%d", &un, &mb);  // developer knob
     void (*kern)(const double*, int64_t, const uint64_t*, int, int, double, int, int, int64_t, int64_t, const double*,
-                 double*, int64_t*, int, int*) = rff_screen_kernel<D, 8, 2>;
+                 const int*, double*, int64_t*, int, int*) = rff_screen_kernel<D, 8, 2>;
 #ifdef TES_RFF_DEV_VARIANTS
     if constexpr (D == 6) {
         if (un == 4 && mb == 1) kern = rff_screen_kernel<D, 4, 1>;
@@ -856,7 +908,7 @@ static int launch_rff_screen(const RffPlan& p, const double* cand, int64_t N, co
         TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_screen));
     TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     kern<<<(unsigned)p.nunits_screen, SCR_THREADS, p.smem_screen, st>>>(cand, N, feat32, (int)S, (int)F, scale, k,
-                                                                        p.sg_screen, p.chunk, idx_offset, bound,
+                                                                        p.sg_screen, p.chunk, idx_offset, bound, mode,
                                                                         slot_val, slot_idx, p.slot_stride, flags);
     TES_LAUNCH_OK();
     return 0;
@@ -894,6 +946,7 @@ static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* 
     base += p.feat32_bytes;
     unsigned long long* xmax = (unsigned long long*)base;
     double* bound = (double*)(base + align_up(64 * 8, 256));
+    int* mode = (int*)(base + align_up(64 * 8, 256) + align_up(S * 8, 256));
     base += p.aux_bytes;
     int* flags = (int*)base;
     const double scale = sqrt(2.0 * sigma / (double)F);
@@ -912,14 +965,14 @@ static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* 
         TES_CUDA_OK(cudaMemsetAsync(xmax, 0, 64 * 8, st));
         rff_xmax_kernel<<<148 * 4, 256, 0, st>>>(cand, N, (int)d, xmax);
         TES_LAUNCH_OK();
-        rff_bound_kernel<<<(unsigned)S, 32, 0, st>>>(feat, p.rec, S, F, (int)d, xmax, scale, bound);
+        rff_bound_kernel<<<(unsigned)S, 32, 0, st>>>(feat, p.rec, S, F, (int)d, xmax, scale, bound, mode);
         TES_LAUNCH_OK();
         int rc = 0;
         switch (d) {
 #define TES_CASE(DD)                                                                                            \
     case DD:                                                                                                    \
-        rc = launch_rff_screen<DD>(p, cand, N, feat32, S, F, scale, k, idx_offset, bound, part_val, part_idx,  \
-                                   flags, st);                                                                  \
+        rc = launch_rff_screen<DD>(p, cand, N, feat32, S, F, scale, k, idx_offset, bound, mode, part_val,      \
+                                   part_idx, flags, st);                                                        \
         break;
             TES_CASE(1) TES_CASE(2) TES_CASE(3) TES_CASE(4) TES_CASE(5) TES_CASE(6) TES_CASE(7) TES_CASE(8)
             TES_CASE(9) TES_CASE(10)
@@ -1055,6 +1108,19 @@ extern "C" int tes_rff_eval_f64(const double* cand, int64_t N, int64_t d, const 
     dim3 grid((unsigned)((N + 127) / 128), (unsigned)S);
     rff_eval_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(cand, N, (int)d, W, b, theta, (int)S, (int)F, w_shared,
                                                             scale, out);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tes_cosf_error_probe(float lo, float hi, double e1, double* out_max, void* stream) {
+    if (!(lo >= 0.0f) || !(hi >= lo)) return -1;
+    if (!out_max) return -4;
+    unsigned lb, hb;
+    memcpy(&lb, &lo, 4);
+    memcpy(&hb, &hi, 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    TES_CUDA_OK(cudaMemsetAsync(out_max, 0, sizeof(double), st));
+    cosf_probe_kernel<<<148 * 8, 256, 0, st>>>(lb, hb, e1, out_max);
     TES_LAUNCH_OK();
     return 0;
 }

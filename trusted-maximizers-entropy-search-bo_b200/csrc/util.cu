@@ -46,7 +46,34 @@ __global__ void __launch_bounds__(256) fp32_fma_burn_kernel(int64_t iters, float
     for (int q = 0; q < 8; ++q) s += __uint_as_float((unsigned)a[q]) + __uint_as_float((unsigned)(a[q] >> 32));
     sink[(int64_t)blockIdx.x * 256 + threadIdx.x] = s;
 }
+// fp64 tensor-core (DMMA m8n8k4) burn: 4 independent accumulator fragments per warp.
+// flops = blocks*8 warps*iters*4*(8*8*4*2).
+__global__ void __launch_bounds__(256) fp64_mma_burn_kernel(int64_t iters, double* sink) {
+    double a = 1.0 + threadIdx.x * 1e-9, b = 0.999999 + threadIdx.x * 1e-10;
+    double c[4][2];
+    for (int q = 0; q < 4; ++q) c[q][0] = c[q][1] = 1e-3 * q;
+    for (int64_t i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[q][0]), "+d"(c[q][1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+    for (int q = 0; q < 4; ++q) s += c[q][0] + c[q][1];
+    sink[(int64_t)blockIdx.x * 256 + threadIdx.x] = s;
+}
 }  // namespace tes
+
+extern "C" int tes_fp64_mma_burn(int blocks, int64_t iters, double* sink, double* flops, void* stream) {
+    if (blocks < 1) return -1;
+    if (iters < 1) return -2;
+    if (!sink) return -3;
+    tes::fp64_mma_burn_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    TES_LAUNCH_OK();
+    if (flops) *flops = (double)blocks * 8.0 * (double)iters * 4.0 * 512.0;
+    return 0;
+}
 
 extern "C" int tes_fp32_fma_burn(int blocks, int64_t iters, float* sink, double* flops, void* stream) {
     if (blocks < 1) return -1;
