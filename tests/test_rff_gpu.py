@@ -170,20 +170,21 @@ def test_screened_topk_near_ties_many_seeds():
 
 
 def test_cosf_error_model_exhaustive():
-    """The fp32 screen's no-reduction path relies on |__cosf(x) - cos(x)| <= 6.0e-7 + 1.3e-7 |x| for |x| <= 512.
-    Verified here over EVERY float in (0, 512] (both signs) on the device that runs the kernels."""
+    """The fp32 screen relies on |__cosf(x) - cos(x)| <= 3.0e-7 + 1.7e-7 |x| for |x| <= 512 (rff.cu SCR_E0/E1).
+    Verified here over EVERY float in (0, 512] (both signs) on the device that runs the kernels; the
+    measured residual on B200 is 1.50e-7, asserted below 2.0e-7 (so E0 keeps a 1.5x margin)."""
     import torch
     from tes_b200 import _lib
     from tes_b200.device import ptr, stream_ptr
     out = torch.zeros(1, dtype=torch.float64, device="cuda")
-    rc = _lib.lib().tes_cosf_error_probe(0.0, 512.0, 1.3e-7, ptr(out), stream_ptr())
+    rc = _lib.lib().tes_cosf_error_probe(0.0, 512.0, 1.7e-7, ptr(out), stream_ptr())
     _lib.check(rc, "tes_cosf_error_probe")
     worst = float(out.cpu()[0])
-    assert worst < 6.0e-7, worst
+    assert worst < 2.0e-7, worst
     # and the documented small-argument behaviour, [-pi, pi]: 2^-21.19 (CUDA programming guide) with slack
     out.zero_()
     _lib.check(_lib.lib().tes_cosf_error_probe(0.0, 3.1415927, 0.0, ptr(out), stream_ptr()), "probe")
-    assert float(out.cpu()[0]) < 6.0e-7
+    assert float(out.cpu()[0]) < 4.5e-7
 
 
 def test_screened_topk_large_arguments_use_reduction_path():

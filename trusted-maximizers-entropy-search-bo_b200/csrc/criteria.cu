@@ -77,24 +77,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
     GemmSmem& sm = *reinterpret_cast<GemmSmem*>(gemm_smem_raw);
     const int64_t row0 = (int64_t)blockIdx.x * GEMM_BM;
     const int64_t col0 = (int64_t)blockIdx.y * GEMM_BN;
-    double acc[8][4];
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     AQuad ap{G, ldg, rows, T, table};
     gemm_mainloop(ap, Bpack, Sp, Kdim, Sp, row0, col0, sm, acc);
-    const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int64_t row = row0 + gemm_row_of(ty, i);
+    for (int i = 0; i < 4; ++i) {
+        int64_t row = row0 + gemm_row_of(warp, lane, i);
         if (row >= rows) continue;
         const double kq = Kq[row];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int64_t col = col0 + gemm_col_of(tx, j);
-            if (col < Sp) var[row * Sp + col] = kq + acc[i][j];
-        }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int64_t col = col0 + gemm_col_of(warp, lane, j, e);
+                if (col < Sp) var[row * Sp + col] = kq + acc[i][j][e];
+            }
     }
 }
 

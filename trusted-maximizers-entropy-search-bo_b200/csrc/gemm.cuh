@@ -1,12 +1,14 @@
 // gemm.cuh -- fp64 tiled GEMM core for the tall-skinny products of stages B and D.
 //
-// B200 has no fp64 path on the tcgen05 tensor cores worth using (fp64 runs on the 64-lane/SM
-// DFMA pipe, 36.3 TFLOP/s measured), so the contraction is a classic register-tiled CUDA-core
-// GEMM: 128x64 CTA tile, 16-deep k-slices, 256 threads each owning an 8x4 accumulator block
-// laid out with the strided-fragment mapping (rows ty*2+{0,1}+32i, cols tx*2+{0,1}+32j) so that
-// every LDS.128 of a warp is conflict-free and A loads broadcast.  Global->shared goes through
-// registers (prefetch of slice t+1 while slice t is multiplied); all loads are bounds-checked with
-// zero fill so any (M, N, K) and leading dimension works.
+// B200's tcgen05 tensor cores have no fp64 path; fp64 contractions run either on the 64-lane/SM DFMA pipe
+// (36.3 TFLOP/s measured) or through the legacy warp-level fp64 MMA (mma.sync m8n8k4, SASS DMMA.8x8x4;
+// 37.2 TFLOP/s measured with tes_fp64_mma_burn).  The peak is the same, but one DMMA retires 256 FMAs for
+// a single issue slot and two 8-byte operand registers per thread, so the GEMM core uses DMMA:
+//   CTA tile 128 x 64, k-slices of 16, 256 threads = 8 warps arranged 4 (rows) x 2 (cols), each warp owning a
+//   32 x 32 block = 4 x 4 DMMA tiles (32 accumulator doubles per thread); per k-step of 4 a warp loads
+//   4 A and 4 B fragments (conflict-free 64-bit LDS thanks to the 132 / 68 strides) and issues 16 DMMAs.
+// Global->shared goes through registers (prefetch of slice t+1 while slice t is multiplied); all loads are
+// bounds-checked with zero fill so any (M, N, K) and leading dimension works.
 //
 // The A operand comes from a provider functor, which lets the TES_ep quadratic forms
 // (evaluate_mp.py:103-107) generate their operand -- products M[x,a]*M[x,b] -- on the fly.
@@ -16,38 +18,43 @@
 namespace tes {
 
 constexpr int GEMM_BM = 128, GEMM_BN = 64, GEMM_BK = 16, GEMM_THREADS = 256;
-constexpr int GEMM_LDA_S = GEMM_BM + 2;  // +2 doubles: k-major stores from the global-load mapping stay <= 2-way conflicted
+// strides = 4 (mod 16) doubles: the 4 k-rows of a fragment land 8 banks apart -> conflict-free 64-bit LDS
+constexpr int GEMM_LDA_S = GEMM_BM + 4;
+constexpr int GEMM_LDB_S = GEMM_BN + 4;
 
 struct GemmSmem {
     double a[2][GEMM_BK][GEMM_LDA_S];
-    double b[2][GEMM_BK][GEMM_BN];
+    double b[2][GEMM_BK][GEMM_LDB_S];
 };
 
-// acc[i][j]: row = row0 + (i/2)*32 + ty*2 + (i&1),  col = col0 + (j/2)*32 + tx*2 + (j&1)
-__device__ __forceinline__ int gemm_row_of(int ty, int i) { return (i >> 1) * 32 + ty * 2 + (i & 1); }
-__device__ __forceinline__ int gemm_col_of(int tx, int j) { return (j >> 1) * 32 + tx * 2 + (j & 1); }
+// accumulator element acc[i][j][e] of a thread: DMMA tile (i, j) of its warp's 32 x 32 block
+__device__ __forceinline__ int gemm_row_of(int warp, int lane, int i) { return (warp >> 1) * 32 + i * 8 + (lane >> 2); }
+__device__ __forceinline__ int gemm_col_of(int warp, int lane, int j, int e) {
+    return (warp & 1) * 32 + j * 8 + (lane & 3) * 2 + e;
+}
 
-__device__ __forceinline__ void gemm_mac_slice(const double (*as)[GEMM_LDA_S], const double (*bs)[GEMM_BN], int ty,
-                                               int tx, double acc[8][4]) {
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void gemm_mac_slice(const double (*as)[GEMM_LDA_S], const double (*bs)[GEMM_LDB_S],
+                                               int warp, int lane, double acc[4][4][2]) {
+    const int rbase = (warp >> 1) * 32 + (lane >> 2);
+    const int cbase = (warp & 1) * 32 + (lane >> 2);
+    const int kq = lane & 3;
 #pragma unroll
-    for (int kk = 0; kk < GEMM_BK; ++kk) {
-        double av[8], bv[4];
+    for (int k0 = 0; k0 < GEMM_BK; k0 += 4) {
+        double av[4], bv[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            double2 v = *reinterpret_cast<const double2*>(&as[kk][i * 32 + ty * 2]);
-            av[2 * i] = v.x;
-            av[2 * i + 1] = v.y;
-        }
+        for (int i = 0; i < 4; ++i) av[i] = as[k0 + kq][rbase + 8 * i];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            double2 v = *reinterpret_cast<const double2*>(&bs[kk][j * 32 + tx * 2]);
-            bv[2 * j] = v.x;
-            bv[2 * j + 1] = v.y;
-        }
+        for (int j = 0; j < 4; ++j) bv[j] = bs[k0 + kq][cbase + 8 * j];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+            for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
     }
 }
 
@@ -112,7 +119,7 @@ __device__ __forceinline__ void gemm_load_b(const double* __restrict__ B, int64_
         regs[q] = (k < K && col < N) ? __ldg(B + k * ldb + col) : 0.0;
     }
 }
-__device__ __forceinline__ void gemm_store_b(double (*bs)[GEMM_BN], int t, const double regs[4]) {
+__device__ __forceinline__ void gemm_store_b(double (*bs)[GEMM_LDB_S], int t, const double regs[4]) {
     const int kk = t >> 4;
     const int c = t & 15;
 #pragma unroll
@@ -123,9 +130,9 @@ __device__ __forceinline__ void gemm_store_b(double (*bs)[GEMM_BN], int t, const
 template <class AProv>
 __device__ __forceinline__ void gemm_mainloop(const AProv& ap, const double* __restrict__ B, int64_t ldb, int64_t K,
                                               int64_t N, int64_t row0, int64_t col0, GemmSmem& sm,
-                                              double acc[8][4]) {
+                                              double acc[4][4][2]) {
     const int t = threadIdx.x;
-    const int ty = t >> 4, tx = t & 15;
+    const int warp = t >> 5, lane = t & 31;
     double ra[8], rb[4];
     const int64_t nk = (K + GEMM_BK - 1) / GEMM_BK;
     ap.load(row0, 0, t, ra);
@@ -139,7 +146,7 @@ __device__ __forceinline__ void gemm_mainloop(const AProv& ap, const double* __r
             ap.load(row0, (kt + 1) * GEMM_BK, t, ra);
             gemm_load_b(B, ldb, K, N, (kt + 1) * GEMM_BK, col0, t, rb);
         }
-        gemm_mac_slice(sm.a[cur], sm.b[cur], ty, tx, acc);
+        gemm_mac_slice(sm.a[cur], sm.b[cur], warp, lane, acc);
         if (kt + 1 < nk) {
             ap.store(sm.a[cur ^ 1], t, ra);
             gemm_store_b(sm.b[cur ^ 1], t, rb);

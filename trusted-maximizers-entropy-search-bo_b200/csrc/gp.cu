@@ -72,12 +72,12 @@ __device__ __forceinline__ void gemm_body(const AProv& ap, const double* __restr
     const int64_t row0 = (int64_t)blockIdx.x * GEMM_BM;
     const int64_t col0 = (int64_t)blockIdx.y * GEMM_BN;
     if (tri && col0 > row0 + GEMM_BM - 1) return;
-    double acc[8][4];
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     if (sbn == 1) {
         gemm_mainloop(ap, B, sbk, K, N, row0, col0, sm, acc);
     } else {
@@ -104,7 +104,7 @@ __device__ __forceinline__ void gemm_body(const AProv& ap, const double* __restr
                 ap.load(row0, (kt + 1) * GEMM_BK, t, ra);
                 loadb((kt + 1) * GEMM_BK);
             }
-            gemm_mac_slice(sm.a[cur], sm.b[cur], ty, tx, acc);
+            gemm_mac_slice(sm.a[cur], sm.b[cur], warp, lane, acc);
             if (kt + 1 < nk) {
                 ap.store(sm.a[cur ^ 1], t, ra);
                 gemm_store_b(sm.b[cur ^ 1], t, rb);
@@ -113,18 +113,20 @@ __device__ __forceinline__ void gemm_body(const AProv& ap, const double* __restr
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int64_t row = row0 + gemm_row_of(ty, i);
+    for (int i = 0; i < 4; ++i) {
+        int64_t row = row0 + gemm_row_of(warp, lane, i);
         if (row >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int64_t col = col0 + gemm_col_of(tx, j);
-            if (col < N) {
-                double v = alpha * acc[i][j];
-                if (beta != 0.0) v = fma(beta, C[row * ldc + col], v);
-                C[row * ldc + col] = v;
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int64_t col = col0 + gemm_col_of(warp, lane, j, e);
+                if (col < N) {
+                    double v = alpha * acc[i][j][e];
+                    if (beta != 0.0) v = fma(beta, C[row * ldc + col], v);
+                    C[row * ldc + col] = v;
+                }
             }
-        }
     }
 }
 

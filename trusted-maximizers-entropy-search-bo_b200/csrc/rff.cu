@@ -360,13 +360,15 @@ __global__ void topk_merge_kernel(const double* __restrict__ vals, const int64_t
 // the pure fp64 kernel.  A (chunk, sample) whose kept set overflows its CAP slots is recomputed by the fp64
 // kernel (flag-gated launch), so correctness never depends on the list capacity.
 //
-// Error bound (u = 2^-24; A_f = |b'_f| + sum_k |w'_fk| max_i |x_ik|):
-//   the screen works in radians: h = b + w.x, n = rint(h/2pi), r = fma(n, -2pi_f32, h), c = __cosf(r)
-//   |h32 - h|      <= (d+4) u pi A_f        (input rounding of w, b, x and the d FFMA roundings)
-//   |r - (h - 2pi n)| <= 1.75e-7 |n| + 2e-7 (2pi_f32 - 2pi = 1.75e-7; one rounding of |r| <= pi), |n| <= A_f/2 + 1
-//   |__cosf(r) - cos(r)| <= 2^-21.19 on [-pi,pi] per the CUDA guide; 1e-6 used
-//   |acc - sum|    <= 34 u sum_f |theta_f|  (theta rounding, products, 32-term fp32 blocks flushed to fp64)
-//   B_j = 1.25 * scale * sum_f |theta_f| ((d+4) u pi A_f + 1.75e-7 (A_f/2+1) + 1.2e-6 + 34 u)
+// Error bound per sample j (u = 2^-24; A_f = |b_f| + sum_k |w_fk| max_i |x_ik| in radians; the screen works in
+// radians, h = b + w.x):
+//   |h32 - h| <= (d+4) u A_f                      input rounding of w, b, x and the d FFMA roundings
+//   direct path (A_f <= 512 for every f): c = __cosf(h32), |c - cos(h32)| <= 3.0e-7 + 1.7e-7 A_f
+//        (exhaustively measured model of FMUL.RZ(x, 1/2pi) + MUFU.COS, see SCR_E0/SCR_E1 below)
+//   reduced path: n = rint(h/2pi), r = fma(n, -2pi_f32, h), c = __cosf(r):
+//        |r - (h - 2pi n)| <= 1.75e-7 |n| + 2e-7,  |n| <= A_f/2pi + 1,  then the model on |r| <= pi
+//   |acc - sum| <= 34 u sum_f |theta_f|           theta rounding, products, 32-term fp32 blocks flushed to fp64
+//   B_j = 1.25 * scale * sum_f |theta_f| * (per-feature bound above)
 // =====================================================================================================
 constexpr int SCR_THREADS = 256;
 constexpr int SCR_TILE = SCR_THREADS * 4;  // 4 candidates (2 packed pairs) per thread
@@ -437,13 +439,14 @@ __global__ void rff_xmax_kernel(const double* __restrict__ cand, int64_t N, int 
     if (threadIdx.x < d) atomicMax(xmax + threadIdx.x, sm[threadIdx.x]);
 }
 
-// |__cosf(x) - cos(x)| <= SCR_E0 + SCR_E1 |x| for |x| <= SCR_XMAX: __cosf is FMUL.RZ(x, 1/2pi) (<= 1 ulp = 2^-23
-// relative, i.e. <= 2^-23 |x| radians) followed by MUFU.COS on revolutions (2^-21.19 on [-pi,pi] per the CUDA
-// guide).  The linear model is verified EXHAUSTIVELY over every float in the domain by
-// tes_cosf_error_probe (tests/test_rff_gpu.py); samples whose arguments can exceed SCR_XMAX use the
-// explicit 2*pi reduction instead.
-constexpr double SCR_E0 = 6.0e-7;
-constexpr double SCR_E1 = 1.3e-7;
+// |__cosf(x) - cos(x)| <= SCR_E0 + SCR_E1 |x| for |x| <= SCR_XMAX: __cosf is FMUL.RZ(x, float(1/2pi)) -- up to
+// 2^-23 relative rounding plus 4e-8 relative error of the constant, i.e. <= 1.6e-7 |x| radians -- followed by
+// MUFU.COS on revolutions.  Measured EXHAUSTIVELY over every float in the domain on B200
+// (tes_cosf_error_probe, tests/test_rff_gpu.py): max(err - 1.7e-7 |x|) = 1.50e-7 up to |x| = 4096, and
+// max err = 4.04e-7 on [-pi, pi] (the CUDA guide's 2^-21.19).  E0 carries a 2x margin on the residual.
+// Samples whose arguments can exceed SCR_XMAX use the explicit 2*pi reduction instead.
+constexpr double SCR_E0 = 3.0e-7;
+constexpr double SCR_E1 = 1.7e-7;
 constexpr double SCR_XMAX = 512.0;
 
 // one warp per sample: B_j from the fp64 feature records [w'(d), b', theta]; mode[j] = 1 when the explicit
@@ -463,7 +466,7 @@ __global__ void rff_bound_kernel(const double* __restrict__ feat, int rec, int64
         const double nmax = 0.5 * A + 1.0;  // |rint(h / 2pi)| <= A/2 + 1
         const double th = fabs(r[d + 1]);
         // reduced path: argument rounding + (2pi_f32 - 2pi) n + rounding of r + __cosf on [-pi,pi] + accumulation
-        e_red += th * ((d + 4) * u * Arad + 1.75e-7 * nmax + 2.0e-7 + 1.0e-6 + 34.0 * u);
+        e_red += th * ((d + 4) * u * Arad + 1.75e-7 * nmax + 2.0e-7 + (SCR_E0 + SCR_E1 * 3.1416) + 34.0 * u);
         // direct path: argument rounding + verified __cosf model on |x| <= Arad + accumulation
         e_dir += th * ((d + 4) * u * Arad + SCR_E0 + SCR_E1 * Arad + 34.0 * u);
         amax = fmax(amax, Arad);
