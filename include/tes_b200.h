@@ -81,6 +81,13 @@ int tes_rff_eval_f64(const double* cand, int64_t N, int64_t d, const double* W, 
 int tes_topk_merge_f64(const double* vals, const int64_t* idx, int64_t P, int64_t S, int k, double* out_val,
                        int64_t* out_idx, void* stream);
 
+/* Arg-max of the acquisition vector, FIRST maximum wins, the first NaN wins over everything (numpy / tf.argmax
+ * semantics).  Replaces bo_discrete.optimize_criterion (bo_discrete.py:794-807) and the chunk merge at
+ * :1053-1055.  out_idx = -1 when N == 0. */
+int64_t tes_argmax_workspace_bytes(int64_t N);
+int tes_argmax_f64(const double* vals, int64_t N, double* out_val, int64_t* out_idx, void* ws, int64_t ws_bytes,
+                   void* stream);
+
 /* ===================================================================================== Stage B
  * SE-ARD cross kernel k(x_i, xb_c), out (N, m).  Replaces utils.computeKnm (utils.py:703-719),
  * using the reference's |a|^2 + |b|^2 - 2ab expansion. */

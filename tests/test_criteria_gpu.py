@@ -151,3 +151,37 @@ def test_negative_variance_propagates_nan():
     ref = onp.evaluate_mp(pr["x"], pr["ls"], pr["sigmas"], pr["sigma0s"], pr["X"], pr["Y"], 2, 8, 5, 1, 10,
                           pr["test_xs"], pr["max_probs"], pr["v0"], pv1, pr["invK"], pr["invpNK"])
     assert np.array_equal(np.isnan(acq), np.isnan(ref)) and np.isnan(ref).any()
+
+
+def test_c4_shapes_batch_tes_sp_philox():
+    """C4 shapes scaled down: d = 10, batch q = 8, T forced small, Philox draws.  The oracle generator
+    (oracle/tes_oracle.c) reproduces the in-kernel normals, so feeding them as host z gives the same numbers;
+    the numpy oracle then checks the value."""
+    from oracle import c_oracle as co
+    from tes_b200 import ops
+    from tes_b200.spec import STREAM_BSP_Y
+    d, n, T, nx, q, I, Yn, seed = 10, 16, 8, 6, 8, 1, 3, 424242
+    hyp = dict(l=np.full(10, 1.0), sigma=2.0, sigma0=1e-3)       # functions.func_gp_prior(10, l=1.0, sigma=2.0)
+    pr = make_problem(seed=4, d=d, n=n, T=T, nx=nx, hyp=hyp, mode="sample", nsample=200)
+    p = pr["max_probs"][0]
+    keep = p > 0
+    P, msk = pr["v0"][0][keep], pr["v1"][0][keep]
+    Sp, K = P.shape[0], P.shape[2]
+    xb = pr["rs"].rand(nx, q, d)
+    a = ops.sp_acq(xb, pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invpNK"][0],
+                   p[keep], P, msk, niter=I, nysample=Yn, seed=seed).cpu().numpy()
+    z = np.stack([co.normals(seed, it, STREAM_BSP_Y, 0, Yn * Sp * nx * K * q).reshape(Yn, Sp, nx, K, q)
+                  for it in range(I)])
+    b = ops.sp_acq(xb, pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invpNK"][0],
+                   p[keep], P, msk, niter=I, nysample=Yn, z=z).cpu().numpy()
+    np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
+    ref = onp.evaluate_batch_sample_mp(xb, pr["ls"], pr["sigmas"], pr["sigma0s"], pr["X"], pr["Y"], d, n, 1, Yn,
+                                       pr["test_xs"], pr["max_probs"], pr["v0"], pr["v1"], pr["invpNK"],
+                                       niteration=I, z=z[None])
+    _close(b, ref)
+    # sharding invariance of the Philox draws (global query index keys the stream)
+    a1 = ops.sp_acq(xb[:2], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invpNK"][0],
+                    p[keep], P, msk, niter=I, nysample=Yn, seed=seed, n_global=nx, x_offset=0).cpu().numpy()
+    a2 = ops.sp_acq(xb[2:], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invpNK"][0],
+                    p[keep], P, msk, niter=I, nysample=Yn, seed=seed, n_global=nx, x_offset=2).cpu().numpy()
+    np.testing.assert_array_equal(np.concatenate([a1, a2]), a)

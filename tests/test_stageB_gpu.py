@@ -104,3 +104,54 @@ def test_gemm(M, N, K, transb):
     C = ops.gemm(A, B, transb=transb).cpu().numpy()
     ref = A @ (B.T if transb else B)
     np.testing.assert_allclose(C, ref, rtol=0, atol=1e-13 * K)
+
+
+def test_argmax_first_maximum_and_nan():
+    from tes_b200 import ops
+    rs = np.random.RandomState(0)
+    v = rs.randn(100_003)
+    v[[777, 50_000, 99_999]] = 9.0
+    i, val = ops.argmax(v)
+    assert int(i) == 777 and float(val) == 9.0 == v[int(np.argmax(v))]
+    v[60_000] = np.nan
+    v[70_000] = np.nan
+    i, val = ops.argmax(v)
+    assert int(i) == int(np.argmax(v)) == 60_000 and np.isnan(float(val))
+    i, val = ops.argmax(np.array([3.0]))
+    assert int(i) == 0
+
+
+def test_discrete_maximizer_sampler(golden):
+    """bo_discrete.py:359-400 on the pH grid: identical arg-max indices for identical z."""
+    from tes_b200 import bo_discrete
+    g = golden("kat_objectives")
+    hyp = g["pH_hyp"]
+    sigma, l, sigma0 = float(hyp[0]), hyp[1:3], float(hyp[3])
+    xs, f = g["pH_xs"], g["pH_f_on_xs"]
+    rs = np.random.RandomState(3)
+    obs = rs.choice(400, 10, replace=False)
+    X, Y = xs[obs], (f[obs] + rs.randn(10) * np.sqrt(sigma0)).reshape(-1, 1)
+    z = rs.randn(7, 400)
+    mx, fs, idx, mean, cov = bo_discrete.sample_maximizers(xs, X, Y, l, sigma, sigma0, z)
+    ridx, rfs = onp.discrete_maximizer_samples(xs, X, Y, l, sigma, sigma0, z)
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_allclose(fs, rfs, rtol=1e-9, atol=1e-10)
+    np.testing.assert_array_equal(mx, xs[ridx])
+
+
+@pytest.mark.parametrize("batch,m", [(3, 512), (2, 1024)])
+def test_batched_chol2inv_large_property(batch, m):
+    """C5 sizes: A A^-1 = I and symmetry (the oracle is too slow to be the checker at the full sweep)."""
+    import torch
+    from tes_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(m)
+    Xp = torch.rand(batch, m, 6, dtype=torch.float64, device="cuda", generator=g)
+    D = ((Xp[:, :, None, :] - Xp[:, None, :, :]) ** 2).sum(-1)
+    A = 1.4 * torch.exp(-0.5 * 3.0 * D) + 1e-2 * torch.eye(m, dtype=torch.float64, device="cuda")
+    inv, info = ops.batched_chol2inv(A, return_info=True)
+    assert int(info.abs().sum()) == 0
+    eye = torch.eye(m, dtype=torch.float64, device="cuda")
+    assert float((A @ inv - eye).abs().max()) < 1e-7
+    assert float((inv - inv.transpose(1, 2)).abs().max()) / float(inv.abs().max()) < 1e-12
+    ref = np.linalg.inv(A[0].cpu().numpy())
+    assert np.abs(inv[0].cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-8

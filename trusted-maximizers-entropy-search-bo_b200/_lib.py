@@ -44,6 +44,8 @@ SIGNATURES = {
     "tes_rff_eval_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_dbl, c_ptr,
                                  c_ptr]),
     "tes_topk_merge_f64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
+    "tes_argmax_workspace_bytes": (c_i64, [c_i64]),
+    "tes_argmax_f64": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "tes_se_ard_cross_f64": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_dbl, c_ptr, c_ptr]),
     "tes_gemm_f64": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr]),
     "tes_pnk_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),

@@ -180,7 +180,7 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
         raise ValueError("criterion must be 'ftl' or 'sftl'")
     tm.__exit__()
     # arg-max over all candidates, first maximum wins (bo_discrete.py:806, :1053-1055)
-    lv, li = torch.max(acq, dim=0)
+    li, lv = ops.argmax(acq)
     pair_v = shard.all_gather(lv.reshape(1))
     pair_i = shard.all_gather((li + shard.offset).reshape(1))
     qi, qv = ops.topk_merge(pair_v.reshape(-1, 1, 1), pair_i.reshape(-1, 1, 1))

@@ -1127,3 +1127,82 @@ extern "C" int tes_cosf_error_probe(float lo, float hi, double e1, double* out_m
     TES_LAUNCH_OK();
     return 0;
 }
+
+// arg-max of a vector, first maximum wins (tf.argmax / np.argmax; bo_discrete.py:806, :1053-1055).
+namespace tes {
+__global__ void argmax_partial_kernel(const double* __restrict__ v, int64_t N, double* __restrict__ pv,
+                                      int64_t* __restrict__ pi) {
+    double bv = neg_inf();
+    int64_t bi = INT64_MAX;
+    bool has_nan = false;
+    int64_t nan_i = INT64_MAX;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (int64_t)gridDim.x * blockDim.x) {
+        double x = v[e];
+        if (x != x) {  // numpy/TF arg-max return the first NaN
+            if (e < nan_i) nan_i = e;
+            has_nan = true;
+        } else if (better(x, e, bv, bi)) {
+            bv = x;
+            bi = e;
+        }
+    }
+    if (has_nan) {
+        bv = pos_inf();
+        bi = nan_i;
+    }
+    warp_argmax(bv, bi);
+    __shared__ double sv[32];
+    __shared__ int64_t si[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        sv[warp] = bv;
+        si[warp] = bi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        bv = lane < (blockDim.x >> 5) ? sv[lane] : neg_inf();
+        bi = lane < (blockDim.x >> 5) ? si[lane] : INT64_MAX;
+        warp_argmax(bv, bi);
+        if (lane == 0) {
+            pv[blockIdx.x] = bv;
+            pi[blockIdx.x] = bi == INT64_MAX ? -1 : bi;
+        }
+    }
+}
+__global__ void argmax_final_kernel(const double* __restrict__ v, const double* __restrict__ pv,
+                                    const int64_t* __restrict__ pi, int nb, double* out_val, int64_t* out_idx) {
+    double bv = neg_inf();
+    int64_t bi = INT64_MAX;
+    for (int e = threadIdx.x; e < nb; e += 32)
+        if (pi[e] >= 0 && better(pv[e], pi[e], bv, bi)) {
+            bv = pv[e];
+            bi = pi[e];
+        }
+    warp_argmax(bv, bi);
+    if (threadIdx.x == 0) {
+        *out_idx = bi == INT64_MAX ? -1 : bi;
+        *out_val = bi == INT64_MAX ? neg_inf() : v[bi];  // a NaN winner reports NaN
+    }
+}
+}  // namespace tes
+
+extern "C" int64_t tes_argmax_workspace_bytes(int64_t N) { return N < 0 ? -1 : 2 * align_up(1024 * 8, 256); }
+
+extern "C" int tes_argmax_f64(const double* vals, int64_t N, double* out_val, int64_t* out_idx, void* ws,
+                              int64_t ws_bytes, void* stream) {
+    if (N < 0 || (N > 0 && !vals)) return -1;
+    if (!out_val) return -3;
+    if (!out_idx) return -4;
+    if (!ws || ws_bytes < tes_argmax_workspace_bytes(N)) return -100;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* pv = (double*)ws;
+    int64_t* pi = (int64_t*)((char*)ws + align_up(1024 * 8, 256));
+    int nb = (int)((N + 1023) / 1024);
+    if (nb > 1024) nb = 1024;
+    if (nb < 1) nb = 1;
+    argmax_partial_kernel<<<nb, 256, 0, st>>>(vals, N, pv, pi);
+    TES_LAUNCH_OK();
+    argmax_final_kernel<<<1, 32, 0, st>>>(vals, pv, pi, nb, out_val, out_idx);
+    TES_LAUNCH_OK();
+    return 0;
+}

@@ -308,3 +308,15 @@ def batch_ep_acq(p, nx):
     rc = _lib.lib().tes_batch_ep_acq_f64(ptr(p), p.numel(), nx, ptr(out), stream_ptr())
     _lib.check(rc, "tes_batch_ep_acq_f64")
     return out
+
+
+def argmax(vals):
+    """First-maximum arg-max of a vector -> (index int, value float tensors on device).  bo_discrete.py:806."""
+    v = dev(vals).reshape(-1)
+    L = _lib.lib()
+    ws = WORKSPACE.get(L.tes_argmax_workspace_bytes(v.numel()), v.device)
+    oi = torch.empty((1,), dtype=torch.int64, device=v.device)
+    ov = torch.empty((1,), dtype=torch.float64, device=v.device)
+    rc = L.tes_argmax_f64(ptr(v), v.numel(), ptr(ov), ptr(oi), ptr(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_argmax_f64")
+    return oi, ov
