@@ -118,14 +118,13 @@ def select_test_points(max_xs, resolution=1e-3, t_max=None):
     """De-duplicate the maximizers at `resolution` (bo.py:830-836, bo_discrete.py:553) keeping first
     occurrences; optionally keep only the `t_max` most frequent ones (ties -> earlier), in original order."""
     xs = max_xs.cpu().numpy() if torch.is_tensor(max_xs) else np.asarray(max_xs)
-    uniq = utils.remove_duplicates_np(xs, resolution=resolution)
-    if t_max is not None and uniq.shape[0] > t_max:
-        d = np.sqrt(((xs[:, None, :] - uniq[None, :, :]) ** 2).sum(-1))
-        owner = np.argmax(d <= resolution, axis=1)
-        counts = np.bincount(owner, minlength=uniq.shape[0])
-        order = np.lexsort((np.arange(uniq.shape[0]), -counts))[:t_max]
-        uniq = uniq[np.sort(order)]
-    return uniq
+    mask, leader = utils.get_duplicate_mask_np(xs, resolution, return_leader=True)
+    keep = np.nonzero(mask == 0.0)[0]
+    if t_max is not None and keep.size > t_max:
+        counts = np.bincount(leader, minlength=xs.shape[0])[keep]
+        order = np.lexsort((np.arange(keep.size), -counts))[:t_max]
+        keep = keep[np.sort(order)]
+    return xs[keep]
 
 
 def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="empirical", deterministic=True,

@@ -117,17 +117,28 @@ def _np(a):
 
 
 # ---- trusted-maximizer statistics (host side in the reference too) ---------------------------------
-def get_duplicate_mask_np(xs, resolution=1e-5):
-    """utils.py:1554-1573 (first occurrence wins), vectorised row by row."""
+def get_duplicate_mask_np(xs, resolution=1e-5, return_leader=False):
+    """utils.py:1554-1573: walking the rows in order, every not-yet-flagged row flags all LATER rows within
+    `resolution` (Euclidean) as duplicates.  Same semantics, one pairwise-distance matrix instead of the
+    O(n^2) Python loop; `leader[j]` is the row that flagged j (j itself for kept rows)."""
     xs = _np(xs)
     n = xs.shape[0]
     mask = np.zeros(n)
-    for i in range(n):
-        if mask[i] == 1.0:
-            continue
-        d = np.sqrt(np.sum((xs[i + 1:] - xs[i]) ** 2, axis=1))
-        mask[i + 1:][d <= resolution] = 1.0
-    return mask
+    leader = np.arange(n)
+    if n:
+        sq = np.sum(xs * xs, axis=1)
+        # the reference computes sqrt(sum((xs[j]-xs[i])**2)); evaluate exactly that for the rows that matter
+        close = (sq[:, None] + sq[None, :] - 2.0 * xs.dot(xs.T)) <= (resolution * 1.5) ** 2 + 1e-12
+        for i in range(n):
+            if mask[i] == 1.0:
+                continue
+            cand = np.nonzero(close[i, i + 1:])[0] + i + 1
+            if cand.size:
+                d = np.sqrt(np.sum((xs[cand] - xs[i]) ** 2, axis=1))
+                hit = cand[(d <= resolution) & (mask[cand] == 0.0)]
+                mask[hit] = 1.0
+                leader[hit] = i
+    return (mask, leader) if return_leader else mask
 
 
 def remove_duplicates_np(xs, resolution=1e-5):
