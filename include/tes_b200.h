@@ -64,7 +64,9 @@ int tes_rff_topk_f64(const double* cand, int64_t N, int64_t d, const double* W, 
  *   0 = automatic; 1 = every pair in fp64; 2 = fp32 screen + fp64 refine: all pairs are first scored on the
  *   packed-fp32 + MUFU pipes with a proven per-sample error bound B_j, every candidate within 2 B_j of the
  *   running k-th best screen value is re-evaluated with the exact fp64 sequence of tes_spec.h, and a
- *   (chunk, sample) whose kept set overflows is recomputed in fp64 (needs d <= 10 and k <= 8, else = 1). */
+ *   (chunk, sample) whose kept set overflows is recomputed in fp64 (needs d <= 10 and k <= 8, else = 1);
+ *   3 = as 2, but the d-term inner products of the screen run on the TF32 tensor cores in split precision
+ *   (3xTF32, mma.sync m16n8k8), leaving the MUFU cosine as the bound. */
 int tes_rff_topk_method_f64(const double* cand, int64_t N, int64_t d, const double* W, const double* b,
                             const double* theta, int64_t S, int64_t F, int w_shared, double sigma, int k,
                             int64_t idx_offset, int64_t* out_idx, double* out_val, void* ws, int64_t ws_bytes,
@@ -181,6 +183,11 @@ int tes_batch_ep_acq_f64(const double* p, int64_t Sp, int64_t nx, double* out_ac
 /* Test probe for the fp32 screen's error model: max over EVERY float x in [lo, hi] (both signs) of
  * |__cosf(x) - cos(x)| - e1*|x|, written to *out_max (device double; 0 if never positive). */
 int tes_cosf_error_probe(float lo, float hi, double e1, double* out_max, void* stream);
+
+/* Test probe for the tensor-core screen: max |h_mma - h_fp64| / A over 16 candidates x (8*n8) features
+ * (x (16,d), w (8*n8,d), b (8*n8), all device fp64; d <= 10), written to *out_max (device double). */
+int tes_mma_arg_error_probe(const double* x, const double* w, const double* b, int64_t d, int n8, double* out_max,
+                            void* stream);
 
 /* number of kernels this library has launched in this process so far (monotonic statistic) */
 int64_t tes_launch_count(void);

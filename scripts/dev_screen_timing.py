@@ -10,7 +10,7 @@ def run(N, d, S, F, k=1):
     b = torch.rand(S, F, dtype=torch.float64, device="cuda", generator=g) * 6.283
     th = torch.randn(S, F, dtype=torch.float64, device="cuda", generator=g)
     res = {}
-    for m in (ops.RFF_FP64, ops.RFF_SCREEN):
+    for m in (ops.RFF_FP64, ops.RFF_SCREEN, ops.RFF_SCREEN_MMA):
         ops.rff_topk(cand, W, b, th, 1.4, k, method=m); torch.cuda.synchronize()
         best = 1e9
         for _ in range(2):
@@ -18,7 +18,7 @@ def run(N, d, S, F, k=1):
             e0.record(); res[m] = ops.rff_topk(cand, W, b, th, 1.4, k, method=m); e1.record(); e1.synchronize()
             best = min(best, e0.elapsed_time(e1) * 1e-3)
         print("N=%d d=%d S=%d F=%d k=%d method=%d: %.4fs  %.3f Gpairs/s" % (N, d, S, F, k, m, best, N * S / best * 1e-9))
-    print("  identical:", torch.equal(res[1][0], res[2][0]) and torch.equal(res[1][1], res[2][1]))
+    print("  identical:", all(torch.equal(res[1][0], res[m][0]) and torch.equal(res[1][1], res[m][1]) for m in (2, 3)))
 run(200_000, 6, 256, 1024)
 run(1_000_000, 6, 1024, 1024)
 run(1_000_000, 6, 1024, 1024, k=3)

@@ -119,13 +119,14 @@ def test_bad_arguments_raise():
     (40_000, 6, 12, 160, 3, True, 3.0),      # shared W
     (3_000, 6, 7, 64, 3, False, 3.0),        # small N, screen forced
 ])
-def test_screened_topk_bit_identical(N, d, S, F, k, shared, scale):
+@pytest.mark.parametrize("method", [2, 3])
+def test_screened_topk_bit_identical(N, d, S, F, k, shared, scale, method):
     import torch
     from oracle import c_oracle as co
     from tes_b200 import ops
     cand, W, b, theta, sigma = _problem(N + d + k, N, d, S, F, shared, scale)
     i1, v1 = ops.rff_topk(cand, W, b, theta, sigma, k=k, idx_offset=7, method=ops.RFF_FP64)
-    i2, v2 = ops.rff_topk(cand, W, b, theta, sigma, k=k, idx_offset=7, method=ops.RFF_SCREEN)
+    i2, v2 = ops.rff_topk(cand, W, b, theta, sigma, k=k, idx_offset=7, method=method)
     assert torch.equal(i1, i2) and torch.equal(v1, v2)
     if N * S * F <= 4e9:
         ridx, rval = co.rff_topk(cand, W, b, theta, sigma, k, idx_offset=7)
@@ -133,7 +134,8 @@ def test_screened_topk_bit_identical(N, d, S, F, k, shared, scale):
         np.testing.assert_array_equal(v2.cpu().numpy(), rval)
 
 
-def test_screened_topk_handles_exact_ties_and_overflow():
+@pytest.mark.parametrize("method", [2, 3])
+def test_screened_topk_handles_exact_ties_and_overflow(method):
     """(a) duplicated candidates: exact fp64 ties, the lower index must win; (b) a constant function sample
     (theta = 0) makes EVERY candidate tie, the kept list overflows its 16 slots and the flag-gated fp64
     fallback must produce the plain fp64 answer (indices 0..k-1)."""
@@ -144,7 +146,7 @@ def test_screened_topk_handles_exact_ties_and_overflow():
     theta = theta.copy()
     theta[2] = 0.0
     i1, v1 = ops.rff_topk(cand2, W, b, theta, sigma, k=4, method=ops.RFF_FP64)
-    i2, v2 = ops.rff_topk(cand2, W, b, theta, sigma, k=4, method=ops.RFF_SCREEN)
+    i2, v2 = ops.rff_topk(cand2, W, b, theta, sigma, k=4, method=method)
     assert torch.equal(i1, i2) and torch.equal(v1, v2)
     i2 = i2.cpu().numpy()
     assert list(i2[2]) == [0, 1, 2, 3]
@@ -152,7 +154,8 @@ def test_screened_topk_handles_exact_ties_and_overflow():
         assert i2[j, 1] == i2[j, 0] + 20_000 and i2[j, 3] == i2[j, 2] + 20_000
 
 
-def test_screened_topk_near_ties_many_seeds():
+@pytest.mark.parametrize("method", [2, 3])
+def test_screened_topk_near_ties_many_seeds(method):
     """Stress: dense candidate clouds around one point make thousands of near-ties within the fp32 bound."""
     import torch
     from tes_b200 import ops
@@ -165,7 +168,7 @@ def test_screened_topk_near_ties_many_seeds():
         b = 2 * np.pi * rs.rand(S, F, 1)
         theta = rs.randn(S, F, 1)
         i1, v1 = ops.rff_topk(cand, W, b, theta, 1.3, k=3, method=ops.RFF_FP64)
-        i2, v2 = ops.rff_topk(cand, W, b, theta, 1.3, k=3, method=ops.RFF_SCREEN)
+        i2, v2 = ops.rff_topk(cand, W, b, theta, 1.3, k=3, method=method)
         assert torch.equal(i1, i2) and torch.equal(v1, v2), seed
 
 
@@ -187,7 +190,8 @@ def test_cosf_error_model_exhaustive():
     assert float(out.cpu()[0]) < 4.5e-7
 
 
-def test_screened_topk_large_arguments_use_reduction_path():
+@pytest.mark.parametrize("method", [2, 3])
+def test_screened_topk_large_arguments_use_reduction_path(method):
     """|W x + b| far beyond the verified __cosf domain: the per-sample mode switches to the explicit 2*pi
     reduction; results stay bit-identical."""
     import torch
@@ -200,5 +204,25 @@ def test_screened_topk_large_arguments_use_reduction_path():
     b = 2 * np.pi * rs.rand(S, F, 1)
     theta = rs.randn(S, F, 1)
     i1, v1 = ops.rff_topk(cand, W, b, theta, 0.9, k=2, method=ops.RFF_FP64)
-    i2, v2 = ops.rff_topk(cand, W, b, theta, 0.9, k=2, method=ops.RFF_SCREEN)
+    i2, v2 = ops.rff_topk(cand, W, b, theta, 0.9, k=2, method=method)
     assert torch.equal(i1, i2) and torch.equal(v1, v2)
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 6, 7, 10])
+def test_mma_split_precision_argument_error(d):
+    """The tensor-core screen's bound assumes |h_mma - h| <= 6e-6 A (rff.cu MMA_HARG).  Measured here on random
+    operands through the same fragment code; asserted below 3e-6 (2x margin)."""
+    import torch
+    from tes_b200 import _lib
+    from tes_b200.device import dev, ptr, stream_ptr
+    worst = 0.0
+    for seed in range(4):
+        rs = np.random.RandomState(seed)
+        n8 = 64
+        x = dev(rs.rand(16, d) * 10 ** rs.uniform(-1, 1))
+        w = dev(rs.randn(8 * n8, d) * 10 ** rs.uniform(-1, 1.5))
+        b = dev(rs.rand(8 * n8) * 6.283)
+        out = torch.zeros(1, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().tes_mma_arg_error_probe(ptr(x), ptr(w), ptr(b), d, n8, ptr(out), stream_ptr()), "probe")
+        worst = max(worst, float(out.cpu()[0]))
+    assert 0.0 < worst < 3.0e-6, worst

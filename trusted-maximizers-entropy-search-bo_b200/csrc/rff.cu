@@ -452,11 +452,12 @@ constexpr double SCR_XMAX = 512.0;
 // one warp per sample: B_j from the fp64 feature records [w'(d), b', theta]; mode[j] = 1 when the explicit
 // range reduction is needed (arguments may leave the verified domain of __cosf)
 __global__ void rff_bound_kernel(const double* __restrict__ feat, int rec, int64_t S, int64_t F, int d,
-                                 const unsigned long long* __restrict__ xmax, double scale,
+                                 const unsigned long long* __restrict__ xmax, double scale, double harg,
                                  double* __restrict__ bound, int* __restrict__ mode) {
     const int64_t j = blockIdx.x;
     const int lane = threadIdx.x;
     const double u = 5.9604644775390625e-08;  // 2^-24
+    // harg: |h_screen - h| <= harg * A_f  ((d+4) u for the FFMA2 screen, MMA_HARG for the 3xTF32 screen)
     double e_red = 0.0, e_dir = 0.0, amax = 0.0;
     for (int64_t f = lane; f < F; f += 32) {
         const double* r = feat + (j * F + f) * rec;
@@ -466,9 +467,9 @@ __global__ void rff_bound_kernel(const double* __restrict__ feat, int rec, int64
         const double nmax = 0.5 * A + 1.0;  // |rint(h / 2pi)| <= A/2 + 1
         const double th = fabs(r[d + 1]);
         // reduced path: argument rounding + (2pi_f32 - 2pi) n + rounding of r + __cosf on [-pi,pi] + accumulation
-        e_red += th * ((d + 4) * u * Arad + 1.75e-7 * nmax + 2.0e-7 + (SCR_E0 + SCR_E1 * 3.1416) + 34.0 * u);
+        e_red += th * (harg * Arad + 1.75e-7 * nmax + 2.0e-7 + (SCR_E0 + SCR_E1 * 3.1416) + 34.0 * u);
         // direct path: argument rounding + verified __cosf model on |x| <= Arad + accumulation
-        e_dir += th * ((d + 4) * u * Arad + SCR_E0 + SCR_E1 * Arad + 34.0 * u);
+        e_dir += th * (harg * Arad + SCR_E0 + SCR_E1 * Arad + 34.0 * u);
         amax = fmax(amax, Arad);
     }
     e_red = warp_sum(e_red);
@@ -497,6 +498,108 @@ __global__ void cosf_probe_kernel(unsigned lo_bits, unsigned hi_bits, double e1,
     for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
     if ((threadIdx.x & 31) == 0 && m > 0.0)
         atomicMax((unsigned long long*)out, (unsigned long long)__double_as_longlong(m));
+}
+
+// shared-memory / global state of the screen's per-sample bookkeeping, common to both screen kernels
+struct ScreenCtx {
+    double* tk_val;
+    int64_t* tk_idx;
+    double* ap_val;
+    int64_t* ap_idx;
+    double* wm;
+    int* slot_cnt;
+    int* ap_count;
+    const double* bound;
+    double* slot_val;
+    int64_t* slot_idx;
+    int* flags;
+    int k, j0, S, slot_stride;
+    int64_t chunk_id, c1, idx_offset;
+};
+
+// A tile's NC-per-thread screen values u (=-inf for invalid candidates) of sample jj: keep every candidate
+// within 2 B_j of max(k-th largest warp maximum of this tile, running k-th best of the chunk).
+template <int NC>
+__device__ __forceinline__ void screen_commit(const ScreenCtx& cx, int jj, const double (&u)[NC],
+                                              const int64_t (&ci)[NC]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = cx.k;
+    double tmax = neg_inf();
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc) tmax = fmax(tmax, u[cc]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
+    if (lane == 0) cx.wm[warp] = tmax;
+    __syncthreads();
+    // k-th largest (with multiplicity) of the 8 warp maxima: a lower bound of the tile's k-th largest value
+    double lk;
+    {
+        double a[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] = cx.wm[q];
+        lk = neg_inf();
+        double prev = pos_inf();
+        int taken = 0;
+        for (int r = 0; r < k; ++r) {
+            double best = neg_inf();
+            int cnt = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (a[q] < prev) {
+                    if (a[q] > best) {
+                        best = a[q];
+                        cnt = 1;
+                    } else if (a[q] == best) {
+                        ++cnt;
+                    }
+                }
+            }
+            if (cnt == 0) break;
+            taken += cnt;
+            lk = best;
+            prev = best;
+            if (taken >= k) break;
+        }
+        if (taken < k) lk = neg_inf();
+    }
+    const double thr = fmax(lk, cx.tk_val[jj * k + k - 1]) - 2.0 * cx.bound[cx.j0 + jj];
+    bool qual = false;
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc) qual |= (ci[cc] < cx.c1) && (u[cc] >= thr);
+    if (__syncthreads_or(qual)) {
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) {
+            if ((ci[cc] < cx.c1) && (u[cc] >= thr)) {
+                int pos = k + atomicAdd(cx.ap_count, 1);
+                cx.ap_val[pos] = u[cc];
+                cx.ap_idx[pos] = ci[cc] + cx.idx_offset;
+            }
+        }
+        if (tid < k) {
+            cx.ap_val[tid] = cx.tk_val[jj * k + tid];
+            cx.ap_idx[tid] = cx.tk_idx[jj * k + tid];
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const int n = *cx.ap_count;
+            const int cnt = cx.slot_cnt[jj];
+            const int64_t fo = cx.chunk_id * cx.S + cx.j0 + jj;
+            if (cnt + n > SCR_CAP) {
+                if (lane == 0) cx.flags[fo] = 1;  // overflow: the fp64 kernel recomputes this (chunk, sample)
+            } else {
+                for (int e = lane; e < n; e += 32) {
+                    cx.slot_val[fo * cx.slot_stride + cnt + e] = cx.ap_val[k + e];
+                    cx.slot_idx[fo * cx.slot_stride + cnt + e] = cx.ap_idx[k + e];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) cx.slot_cnt[jj] = cnt + n;
+            warp_select_topk(cx.ap_val, cx.ap_idx, k + n, k, cx.tk_val + jj * k, cx.tk_idx + jj * k, lane);
+            __syncwarp();
+            if (tid == 0) *cx.ap_count = 0;
+        }
+        __syncthreads();
+    }
 }
 
 template <int D, int UNROLL, int MINB>
@@ -553,6 +656,8 @@ __global__ void __launch_bounds__(SCR_THREADS, MINB)
     }
     __syncthreads();
 
+    const ScreenCtx cx{tk_val, tk_idx, ap_val, ap_idx, wm, slot_cnt, ap_count, bound, slot_val, slot_idx, flags,
+                       k, j0, S, slot_stride, chunk_id, c1, idx_offset};
     int p_jj = 0, p_c = 0, p_slot = 0;
     int64_t p_left = total;
     auto issue = [&]() {
@@ -657,88 +762,358 @@ __global__ void __launch_bounds__(SCR_THREADS, MINB)
             }
             // ---- sample jj finished for this tile: keep everything within 2B of the k-th best screen value
             double u[4];
-            double tmax = neg_inf();
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                u[cc] = (ci[cc] < c1) ? scale * dacc[cc] : neg_inf();
-                tmax = fmax(tmax, u[cc]);
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
-            if (lane == 0) wm[warp] = tmax;
-            __syncthreads();
-            // k-th largest of the 8 warp maxima: a lower bound of the tile's k-th largest value
-            double lk;
-            {
-                double a[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) a[q] = wm[q];
-                lk = neg_inf();
-                double prev = pos_inf();
-                int taken = 0;
-                // selection by repeated max with multiplicity
-                for (int r = 0; r < k; ++r) {
-                    double best = neg_inf();
-                    int cnt = 0;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (a[q] < prev) {
-                            if (a[q] > best) {
-                                best = a[q];
-                                cnt = 1;
-                            } else if (a[q] == best) {
-                                ++cnt;
-                            }
-                        }
-                    }
-                    if (cnt == 0) break;
-                    taken += cnt;
-                    lk = best;
-                    prev = best;
-                    if (taken >= k) break;
-                }
-                if (taken < k) lk = neg_inf();
-            }
-            const double thr = fmax(lk, tk_val[jj * k + k - 1]) - 2.0 * bound[j0 + jj];
-            bool qual = false;
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) qual |= (ci[cc] < c1) && (u[cc] >= thr);
-            if (__syncthreads_or(qual)) {
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    if ((ci[cc] < c1) && (u[cc] >= thr)) {
-                        int pos = k + atomicAdd(ap_count, 1);
-                        ap_val[pos] = u[cc];
-                        ap_idx[pos] = ci[cc] + idx_offset;
-                    }
-                }
-                if (tid < k) {
-                    ap_val[tid] = tk_val[jj * k + tid];
-                    ap_idx[tid] = tk_idx[jj * k + tid];
-                }
-                __syncthreads();
-                if (tid < 32) {
-                    const int n = *ap_count;
-                    const int cnt = slot_cnt[jj];
-                    const int64_t fo = chunk_id * S + j0 + jj;
-                    if (cnt + n > SCR_CAP) {
-                        if (lane == 0) flags[fo] = 1;  // overflow: the fp64 kernel recomputes this (chunk, sample)
-                    } else {
-                        for (int e = lane; e < n; e += 32) {
-                            slot_val[fo * slot_stride + cnt + e] = ap_val[k + e];
-                            slot_idx[fo * slot_stride + cnt + e] = ap_idx[k + e];
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) slot_cnt[jj] = cnt + n;
-                    warp_select_topk(ap_val, ap_idx, k + n, k, tk_val + jj * k, tk_idx + jj * k, lane);
-                    __syncwarp();
-                    if (tid == 0) *ap_count = 0;
-                }
-                __syncthreads();
-            }
+            for (int cc = 0; cc < 4; ++cc) u[cc] = (ci[cc] < c1) ? scale * dacc[cc] : neg_inf();
+            screen_commit<4>(cx, jj, u, ci);
         }
     }
+}
+
+// =====================================================================================================
+// Tensor-core variant of the screen: the d-term inner products h = b + w.x run on the warp-level
+// TF32 tensor-core MMA (mma.sync m16n8k8) in split precision ("3xTF32": x = x_hi + x_lo, w = w_hi + w_lo,
+// h ~ x_hi w_hi + x_hi w_lo + x_lo w_hi, bias as two extra K columns against a constant 1), which removes
+// the dot products from the fp32 pipe; what is left per (candidate, sample, feature) is the MUFU cosine,
+// the FMUL of __cosf and half a packed FFMA2, so the kernel is bound by the MUFU/XU pipe (16 lanes/SM/clk).
+//   * K layout (Kp = 8*KS, KS = ceil((3d+2)/8)): [x_hi | x_hi | x_lo | 1 1] against [w_hi | w_lo | w_hi | b_hi b_lo]
+//   * a warp owns 64 candidates = 4 row tiles of 16; its A fragments (KS*4 registers per row tile) are built
+//     once per candidate tile; B fragments + the two theta values a thread needs arrive pre-arranged in
+//     fragment order from the pack kernel (one 16/32/48-byte record per lane per 8 features), streamed through
+//     the same bulk-copy ring;
+//   * accumulator fragment (c0..c3) = h for rows (g, g+8) x features (2t, 2t+1): cos, packed FFMA2 with
+//     (theta_2t, theta_2t+1) into per-row-tile fp32 accumulators, flushed to fp64 every 16 feature tiles;
+//     at the end of a sample the 4 lanes of a quad are shuffle-reduced.
+// Error model: |h_mma - h| <= 6e-6 A_f (3.5 * 2^-22 from the dropped lo*lo / tf32 residuals / fp32 input
+// rounding, 2^-18 for <= 32 truncating fp32 accumulations), verified by tes_mma_arg_error_probe.
+// =====================================================================================================
+template <int D>
+struct MmaCfg {
+    static constexpr int KS = (3 * D + 2 + 7) / 8;
+    static constexpr int RL = ((2 * KS + 2) + 3) & ~3;  // floats per lane record
+};
+constexpr int MMA_TILE = 512;  // candidates per CTA tile: 8 warps x 4 row tiles x 16 rows
+constexpr double MMA_HARG = 6.0e-6;
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// value of the B operand (feature side) at K index k for one feature: w, b in radians
+template <int D>
+__device__ __forceinline__ float mma_bval(const double* __restrict__ w, double b, int k) {
+    if (k < 2 * D || (k >= 2 * D && k < 3 * D)) {
+        const int kk = k < D ? k : (k < 2 * D ? k - D : k - 2 * D);
+        const float wf = __double2float_rn(w[kk]);
+        const float hi = __uint_as_float(to_tf32(wf));
+        if (k >= D && k < 2 * D) return __uint_as_float(to_tf32(wf - hi));
+        return hi;
+    }
+    if (k == 3 * D || k == 3 * D + 1) {
+        const float bf = __double2float_rn(b);
+        const float hi = __uint_as_float(to_tf32(bf));
+        return k == 3 * D ? hi : __uint_as_float(to_tf32(bf - hi));
+    }
+    return 0.0f;
+}
+
+// fragment-ordered feature records: feat[(j*nt8 + tile)*32 + lane][RL]
+template <int D>
+__global__ void rff_pack_mma_kernel(const double* __restrict__ W, const double* __restrict__ b,
+                                    const double* __restrict__ theta, int64_t S, int64_t F, int w_shared,
+                                    float* __restrict__ featm) {
+    constexpr int KS = MmaCfg<D>::KS, RL = MmaCfg<D>::RL;
+    const int64_t nt8 = (F + 7) / 8;
+    int64_t t_ = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_ >= S * nt8 * 32) return;
+    const int lane = (int)(t_ & 31);
+    const int64_t tile = (t_ >> 5) % nt8, j = (t_ >> 5) / nt8;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t jw = w_shared ? 0 : j;
+    float* o = featm + t_ * RL;
+    const int64_t f = tile * 8 + g;
+    for (int s = 0; s < KS; ++s)
+        for (int e = 0; e < 2; ++e) {
+            float v = 0.0f;
+            if (f < F) v = mma_bval<D>(W + (jw * F + f) * D, b[jw * F + f], 8 * s + 4 * e + t);
+            o[2 * s + e] = v;
+        }
+    const int64_t fa = tile * 8 + 2 * t;
+    o[2 * KS] = fa < F ? __double2float_rn(theta[j * F + fa]) : 0.0f;
+    o[2 * KS + 1] = fa + 1 < F ? __double2float_rn(theta[j * F + fa + 1]) : 0.0f;
+    for (int q = 2 * KS + 2; q < RL; ++q) o[q] = 0.0f;
+}
+
+// A-operand (candidate side) value at compile-time K index k
+template <int D>
+__device__ __forceinline__ float mma_aval(const float (&xh)[D], const float (&xl)[D], int k) {
+    if (k < D) return xh[k];
+    if (k < 2 * D) return xh[k - D];
+    if (k < 3 * D) return xl[k - 2 * D];
+    if (k == 3 * D || k == 3 * D + 1) return 1.0f;
+    return 0.0f;
+}
+
+template <int D>
+__global__ void __launch_bounds__(SCR_THREADS, 2)
+    rff_screen_mma_kernel(const double* __restrict__ cand, int64_t N, const float* __restrict__ featm, int S, int F,
+                          double scale, int k, int sg, int64_t chunk, int64_t idx_offset,
+                          const double* __restrict__ bound, const int* __restrict__ mode,
+                          double* __restrict__ slot_val, int64_t* __restrict__ slot_idx, int slot_stride,
+                          int* __restrict__ flags) {
+    constexpr int KS = MmaCfg<D>::KS, RL = MmaCfg<D>::RL;
+    constexpr int THREADS = SCR_THREADS;
+    constexpr int TILE = MMA_TILE;
+    constexpr int TPS = RFF_FCH / 8;               // feature tiles per pipeline stage
+    constexpr int STAGE_FLOATS = TPS * 32 * RL;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage = reinterpret_cast<float*>(smem_raw);                                  // [NSTAGE][STAGE_FLOATS]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage + RFF_NSTAGE * STAGE_FLOATS);    // [8]
+    double* tk_val = reinterpret_cast<double*>(full + 8);
+    int64_t* tk_idx = reinterpret_cast<int64_t*>(tk_val + sg * k);
+    double* ap_val = reinterpret_cast<double*>(tk_idx + sg * k);                        // [TILE + 16]
+    int64_t* ap_idx = reinterpret_cast<int64_t*>(ap_val + TILE + 16);
+    double* wm = reinterpret_cast<double*>(ap_idx + TILE + 16);
+    int* slot_cnt = reinterpret_cast<int*>(wm + 8);
+    int* ap_count = slot_cnt + sg;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int nsg = (S + sg - 1) / sg;
+    const int64_t chunk_id = blockIdx.x / nsg;
+    const int gq = blockIdx.x % nsg;
+    const int j0 = gq * sg;
+    const int nj = min(sg, S - j0);
+    const int64_t c0 = chunk_id * chunk;
+    const int64_t c1 = min(N, c0 + chunk);
+    const int ntiles = (int)((c1 - c0 + TILE - 1) / TILE);
+    const int nt8 = (F + 7) / 8;                       // feature tiles per sample
+    const int nch = (nt8 + TPS - 1) / TPS;             // pipeline stages per sample
+    const int64_t total = (int64_t)ntiles * nj * nch;
+
+    for (int e = tid; e < sg * k; e += THREADS) {
+        tk_val[e] = neg_inf();
+        tk_idx[e] = -1;
+    }
+    for (int e = tid; e < nj * SCR_CAP; e += THREADS) {
+        int64_t o = (chunk_id * S + j0 + e / SCR_CAP) * slot_stride + e % SCR_CAP;
+        slot_idx[o] = -1;
+        slot_val[o] = neg_inf();
+    }
+    for (int e = tid; e < nj; e += THREADS) {
+        slot_cnt[e] = 0;
+        flags[chunk_id * S + j0 + e] = 0;
+    }
+    if (tid == 0) {
+        *ap_count = 0;
+        for (int s = 0; s < RFF_NSTAGE; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const ScreenCtx cx{tk_val, tk_idx, ap_val, ap_idx, wm, slot_cnt, ap_count, bound, slot_val, slot_idx, flags,
+                       k, j0, S, slot_stride, chunk_id, c1, idx_offset};
+
+    int p_jj = 0, p_c = 0, p_slot = 0;
+    int64_t p_left = total;
+    auto issue = [&]() {
+        const int tcnt = min(TPS, nt8 - p_c * TPS);
+        const uint32_t bytes = (uint32_t)(tcnt * 32 * RL * sizeof(float));
+        const float* src = featm + ((int64_t)(j0 + p_jj) * nt8 + (int64_t)p_c * TPS) * 32 * RL;
+        mbar_expect_tx(&full[p_slot], bytes);
+        bulk_g2s(stage + p_slot * STAGE_FLOATS, src, bytes, &full[p_slot]);
+        if (++p_c == nch) {
+            p_c = 0;
+            if (++p_jj == nj) p_jj = 0;
+        }
+        if (++p_slot == RFF_NSTAGE) p_slot = 0;
+        --p_left;
+    };
+    if (tid == 0) {
+        for (int p = 0; p < RFF_NSTAGE - 1 && p_left > 0; ++p) issue();
+    }
+
+    const uint64_t INV2PI2 = f2_pack(0.15915494f, 0.15915494f);
+    const uint64_t MAGIC2 = f2_pack(12582912.0f, 12582912.0f);
+    const uint64_t NMAGIC2 = f2_pack(-12582912.0f, -12582912.0f);
+    const uint64_t NTWOPI2 = f2_pack(-6.2831855f, -6.2831855f);
+
+    uint32_t afr[4][KS][4];   // A fragments: [row tile][k-step][a0..a3]
+    double dacc[4][2];        // [row tile][row g | row g+8], partial over this lane's feature columns
+    int slot = 0;
+    uint32_t phase = 0;
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int64_t t0 = c0 + (int64_t)tile * TILE + warp * 64;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float xh[2][D], xl[2][D];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int64_t ci_ = t0 + r * 16 + g + 8 * h2;
+#pragma unroll
+                for (int kk = 0; kk < D; ++kk) {
+                    const float xf = (ci_ < c1) ? __double2float_rn(__ldg(cand + ci_ * D + kk)) : 0.0f;
+                    xh[h2][kk] = __uint_as_float(to_tf32(xf));
+                    xl[h2][kk] = __uint_as_float(to_tf32(xf - xh[h2][kk]));
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < KS; ++s)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const float v0 = mma_aval<D>(xh[h2], xl[h2], 8 * s + 4 * e + 0);
+                        const float v1 = mma_aval<D>(xh[h2], xl[h2], 8 * s + 4 * e + 1);
+                        const float v2 = mma_aval<D>(xh[h2], xl[h2], 8 * s + 4 * e + 2);
+                        const float v3 = mma_aval<D>(xh[h2], xl[h2], 8 * s + 4 * e + 3);
+                        const float v = t == 0 ? v0 : (t == 1 ? v1 : (t == 2 ? v2 : v3));
+                        afr[r][s][2 * e + h2] = __float_as_uint(v);  // a0:(g,t) a1:(g+8,t) a2:(g,t+4) a3:(g+8,t+4)
+                    }
+        }
+        for (int jj = 0; jj < nj; ++jj) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dacc[r][0] = dacc[r][1] = 0.0;
+            const int red = mode[j0 + jj];
+            for (int c = 0; c < nch; ++c) {
+                if (tid == 0 && p_left > 0) issue();
+                mbar_wait(&full[slot], phase);
+                const int tcnt = min(TPS, nt8 - c * TPS);
+                const float* sp = stage + slot * STAGE_FLOATS + lane * RL;
+                auto run_stage = [&](auto reduce_tag) {
+                    constexpr bool REDUCE = decltype(reduce_tag)::value;
+                    uint64_t acc2[4][2];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc2[r][0] = acc2[r][1] = 0ull;
+#pragma unroll 2
+                    for (int ft = 0; ft < tcnt; ++ft) {
+                        float rec[RL];
+                        const float4* rp = reinterpret_cast<const float4*>(sp + ft * 32 * RL);
+#pragma unroll
+                        for (int q = 0; q < RL / 4; ++q) {
+                            float4 v = rp[q];
+                            rec[4 * q] = v.x;
+                            rec[4 * q + 1] = v.y;
+                            rec[4 * q + 2] = v.z;
+                            rec[4 * q + 3] = v.w;
+                        }
+                        const uint64_t th2 = f2_pack(rec[2 * KS], rec[2 * KS + 1]);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            float cc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int s = 0; s < KS; ++s)
+                                mma_tf32(cc, afr[r][s], __float_as_uint(rec[2 * s]), __float_as_uint(rec[2 * s + 1]));
+                            uint64_t h01 = f2_pack(cc[0], cc[1]), h23 = f2_pack(cc[2], cc[3]);
+                            if (REDUCE) {
+                                uint64_t ta = ffma2(h01, INV2PI2, MAGIC2), tb = ffma2(h23, INV2PI2, MAGIC2);
+                                h01 = ffma2(fadd2(ta, NMAGIC2), NTWOPI2, h01);
+                                h23 = ffma2(fadd2(tb, NMAGIC2), NTWOPI2, h23);
+                            }
+                            const uint64_t c01 = f2_pack(__cosf(f2_lo(h01)), __cosf(f2_hi(h01)));
+                            const uint64_t c23 = f2_pack(__cosf(f2_lo(h23)), __cosf(f2_hi(h23)));
+                            acc2[r][0] = ffma2(th2, c01, acc2[r][0]);
+                            acc2[r][1] = ffma2(th2, c23, acc2[r][1]);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        dacc[r][0] += (double)f2_lo(acc2[r][0]) + (double)f2_hi(acc2[r][0]);
+                        dacc[r][1] += (double)f2_lo(acc2[r][1]) + (double)f2_hi(acc2[r][1]);
+                    }
+                };
+                if (red)
+                    run_stage(std::true_type{});
+                else
+                    run_stage(std::false_type{});
+                if (++slot == RFF_NSTAGE) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+                __syncthreads();
+            }
+            // quad reduction: the 4 lanes sharing g hold partial sums over disjoint feature columns
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    double v = dacc[r][h2];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    dacc[r][h2] = v;
+                }
+            // lane t of a quad takes row tile t: candidates (t0 + t*16 + g) and (+8)
+            double u[2];
+            int64_t ci[2];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const double v = t == 0 ? dacc[0][h2] : (t == 1 ? dacc[1][h2] : (t == 2 ? dacc[2][h2] : dacc[3][h2]));
+                ci[h2] = t0 + t * 16 + g + 8 * h2;
+                u[h2] = (ci[h2] < c1) ? scale * v : neg_inf();
+            }
+            screen_commit<2>(cx, jj, u, ci);
+        }
+    }
+}
+
+// test probe: max over random (x, w, b) of |h_mma - h_fp64| / A for one K-step configuration D
+template <int D>
+__global__ void mma_arg_probe_kernel(const double* __restrict__ x, const double* __restrict__ w,
+                                     const double* __restrict__ b, int n8, double* out) {
+    // one warp: 16 candidates x (8*n8) features
+    constexpr int KS = MmaCfg<D>::KS;
+    const int lane = threadIdx.x, g = lane >> 2, t = lane & 3;
+    uint32_t afr[KS][4];
+    float xh[2][D], xl[2][D];
+    for (int h2 = 0; h2 < 2; ++h2)
+        for (int kk = 0; kk < D; ++kk) {
+            const float xf = __double2float_rn(x[(g + 8 * h2) * D + kk]);
+            xh[h2][kk] = __uint_as_float(to_tf32(xf));
+            xl[h2][kk] = __uint_as_float(to_tf32(xf - xh[h2][kk]));
+        }
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const float v0 = mma_aval<D>(xh[h2], xl[h2], 8 * s + 4 * e + 0);
+                const float v1 = mma_aval<D>(xh[h2], xl[h2], 8 * s + 4 * e + 1);
+                const float v2 = mma_aval<D>(xh[h2], xl[h2], 8 * s + 4 * e + 2);
+                const float v3 = mma_aval<D>(xh[h2], xl[h2], 8 * s + 4 * e + 3);
+                afr[s][2 * e + h2] = __float_as_uint(t == 0 ? v0 : (t == 1 ? v1 : (t == 2 ? v2 : v3)));
+            }
+    double worst = 0.0;
+    for (int tile = 0; tile < n8; ++tile) {
+        float cc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int64_t f = tile * 8 + g;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const float b0 = mma_bval<D>(w + f * D, b[f], 8 * s + t), b1 = mma_bval<D>(w + f * D, b[f], 8 * s + t + 4);
+            mma_tf32(cc, afr[s], __float_as_uint(b0), __float_as_uint(b1));
+        }
+        for (int q = 0; q < 4; ++q) {
+            const int row = g + 8 * (q >> 1);
+            const int64_t ff = tile * 8 + 2 * t + (q & 1);
+            double h = b[ff], A = fabs(b[ff]);
+            for (int kk = 0; kk < D; ++kk) {
+                h = fma(w[ff * D + kk], x[row * D + kk], h);
+                A += fabs(w[ff * D + kk] * x[row * D + kk]);
+            }
+            worst = fmax(worst, fabs((double)cc[q] - h) / A);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, off));
+    if (lane == 0) *out = worst;
 }
 
 // exact fp64 re-evaluation (tes_spec.h sequence) of every kept (chunk, sample, slot) candidate
@@ -793,7 +1168,8 @@ static size_t rff_smem_fp64(int rec, int sg, int k, int tile) {
            (size_t)(tile + RFF_MAX_K) * 16 + 16;
 }
 
-// method: 0 = auto, 1 = fp64 only, 2 = fp32 screen + fp64 refine (when the shape allows it)
+// method: 0 = auto, 1 = fp64 only, 2 = packed-fp32 screen + fp64 refine, 3 = tensor-core (3xTF32) screen + fp64
+// refine (2/3 only when the shape allows it)
 static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int method) {
     RffPlan p{};
     p.C = 4;
@@ -810,19 +1186,22 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
     p.rec = rff_rec((int)d);
     p.recp = scr_recp((int)d);
     const bool can_screen = d <= RFF_MAX_D_FAST && k <= SCR_MAX_K && N >= 1;
-    p.screened = can_screen && (method == 2 || (method == 0 && N >= SCR_MIN_N)) ? 1 : 0;
+    p.screened = 0;
+    if (can_screen && (method == 2 || method == 3 || (method == 0 && N >= SCR_MIN_N))) p.screened = method == 3 ? 2 : 1;
     if (p.screened) {
         p.C = 4;
         p.threads = 256;
         p.unroll = 2;
     }
     p.tile = p.threads * p.C;
+    if (p.screened == 2) p.tile = MMA_TILE;  // candidate tile of the tensor-core screen (fp64 fallback tiles itself)
     int64_t ntiles = (N + p.tile - 1) / p.tile;
     if (ntiles < 1) ntiles = 1;
     int64_t tpc = ntiles < 16 ? ntiles : 16;  // tiles per chunk
     int64_t sg = S < 32 ? S : 32;
     auto units = [&]() { return ((ntiles + tpc - 1) / tpc) * ((S + sg - 1) / sg); };
     const int64_t want = 8 * 148;
+    if (p.screened == 2) tpc = ntiles < 32 ? ntiles : 32;
     while (units() < want && tpc > 4) tpc = (tpc + 1) / 2;
     while (units() < want && sg > 1) sg = (sg + 1) / 2;
     while (units() < want && tpc > 1) tpc = (tpc + 1) / 2;
@@ -840,12 +1219,20 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
         p.part_val_bytes = align_up(p.nchunks * S * p.slot_stride * (int64_t)sizeof(double), 256);
         p.part_idx_bytes = align_up(p.nchunks * S * p.slot_stride * (int64_t)sizeof(int64_t), 256);
         p.feat32_bytes = align_up(S * F * p.recp * (int64_t)sizeof(uint64_t), 256);
+        if (p.screened == 2) {
+            const int ks = (3 * (int)d + 2 + 7) / 8, rl = ((2 * ks + 2) + 3) & ~3;
+            p.feat32_bytes = align_up(S * ((F + 7) / 8) * 32 * rl * (int64_t)sizeof(float), 256);
+            p.smem_screen = (size_t)RFF_NSTAGE * (RFF_FCH / 8) * 32 * rl * sizeof(float) + 8 * sizeof(uint64_t) +
+                            (size_t)p.sg * k * 16 + (size_t)(MMA_TILE + 16) * 16 + 8 * sizeof(double) +
+                            (size_t)p.sg * sizeof(int) + 16;
+        }
         p.aux_bytes = align_up(64 * 8, 256) + 2 * align_up(S * 8, 256);  // xmax[64], bound[S], mode[S]
         p.flags_bytes = align_up(p.nchunks * S * (int64_t)sizeof(int), 256);
-        p.smem_screen = (size_t)RFF_NSTAGE * RFF_FCH * p.recp * sizeof(uint64_t) + 8 * sizeof(uint64_t) +
-                        (size_t)p.sg * k * 16 + (size_t)(SCR_TILE + 16) * 16 + 8 * sizeof(double) +
-                        (size_t)p.sg * sizeof(int) + 16;
-        p.smem_fallback = rff_smem_fp64(p.rec, 1, k, p.tile);
+        if (p.screened == 1)
+            p.smem_screen = (size_t)RFF_NSTAGE * RFF_FCH * p.recp * sizeof(uint64_t) + 8 * sizeof(uint64_t) +
+                            (size_t)p.sg * k * 16 + (size_t)(SCR_TILE + 16) * 16 + 8 * sizeof(double) +
+                            (size_t)p.sg * sizeof(int) + 16;
+        p.smem_fallback = rff_smem_fp64(p.rec, 1, k, 1024);
     } else {
         p.slot_stride = k;
         p.part_val_bytes = align_up(p.nchunks * S * k * (int64_t)sizeof(double), 256);
@@ -917,6 +1304,21 @@ static int launch_rff_screen(const RffPlan& p, const double* cand, int64_t N, co
     return 0;
 }
 
+template <int D>
+static int launch_rff_screen_mma(const RffPlan& p, const double* cand, int64_t N, const float* featm, int64_t S,
+                                 int64_t F, double scale, int k, int64_t idx_offset, const double* bound,
+                                 const int* mode, double* slot_val, int64_t* slot_idx, int* flags, cudaStream_t st) {
+    auto kern = rff_screen_mma_kernel<D>;
+    if (p.smem_screen > 48 * 1024)
+        TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_screen));
+    TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    kern<<<(unsigned)p.nunits_screen, SCR_THREADS, p.smem_screen, st>>>(cand, N, featm, (int)S, (int)F, scale, k,
+                                                                        p.sg_screen, p.chunk, idx_offset, bound, mode,
+                                                                        slot_val, slot_idx, p.slot_stride, flags);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
 static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* W, const double* b,
                         const double* theta, int64_t S, int64_t F, int w_shared, double sigma, int k,
                         int64_t idx_offset, int64_t* out_idx, double* out_val, void* ws, int64_t ws_bytes,
@@ -932,7 +1334,7 @@ static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* 
     if (k < 1 || k > RFF_MAX_K) return -11;
     if (!out_idx) return -13;
     if (!out_val) return -14;
-    if (method < 0 || method > 2) return -18;
+    if (method < 0 || method > 3) return -18;
     RffPlan p = rff_plan(N, d, S, F, k, method);
     if (!ws || ws_bytes < p.total_bytes) return -100;
     cudaStream_t st = (cudaStream_t)stream;
@@ -962,24 +1364,44 @@ static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* 
     if (N == 0) {
         P = 0;
     } else if (p.screened) {
-        rff_pack32_kernel<<<(unsigned)((nsf + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, (int)d, w_shared, p.recp,
-                                                                          feat32);
-        TES_LAUNCH_OK();
         TES_CUDA_OK(cudaMemsetAsync(xmax, 0, 64 * 8, st));
         rff_xmax_kernel<<<148 * 4, 256, 0, st>>>(cand, N, (int)d, xmax);
         TES_LAUNCH_OK();
-        rff_bound_kernel<<<(unsigned)S, 32, 0, st>>>(feat, p.rec, S, F, (int)d, xmax, scale, bound, mode);
-        TES_LAUNCH_OK();
         int rc = 0;
-        switch (d) {
+        if (p.screened == 2) {
+            const int64_t nrec = S * ((F + 7) / 8) * 32;
+            rff_bound_kernel<<<(unsigned)S, 32, 0, st>>>(feat, p.rec, S, F, (int)d, xmax, scale, MMA_HARG, bound, mode);
+            TES_LAUNCH_OK();
+            switch (d) {
+#define TES_CASE(DD)                                                                                            \
+    case DD:                                                                                                    \
+        rff_pack_mma_kernel<DD><<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, w_shared,    \
+                                                                                (float*)feat32);                \
+        TES_LAUNCH_OK();                                                                                        \
+        rc = launch_rff_screen_mma<DD>(p, cand, N, (const float*)feat32, S, F, scale, k, idx_offset, bound,     \
+                                       mode, part_val, part_idx, flags, st);                                    \
+        break;
+                TES_CASE(1) TES_CASE(2) TES_CASE(3) TES_CASE(4) TES_CASE(5) TES_CASE(6) TES_CASE(7) TES_CASE(8)
+                TES_CASE(9) TES_CASE(10)
+#undef TES_CASE
+            }
+        } else {
+            rff_pack32_kernel<<<(unsigned)((nsf + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, (int)d, w_shared,
+                                                                              p.recp, feat32);
+            TES_LAUNCH_OK();
+            rff_bound_kernel<<<(unsigned)S, 32, 0, st>>>(feat, p.rec, S, F, (int)d, xmax, scale,
+                                                         (d + 4) * 5.9604644775390625e-08, bound, mode);
+            TES_LAUNCH_OK();
+            switch (d) {
 #define TES_CASE(DD)                                                                                            \
     case DD:                                                                                                    \
         rc = launch_rff_screen<DD>(p, cand, N, feat32, S, F, scale, k, idx_offset, bound, mode, part_val,      \
                                    part_idx, flags, st);                                                        \
         break;
-            TES_CASE(1) TES_CASE(2) TES_CASE(3) TES_CASE(4) TES_CASE(5) TES_CASE(6) TES_CASE(7) TES_CASE(8)
-            TES_CASE(9) TES_CASE(10)
+                TES_CASE(1) TES_CASE(2) TES_CASE(3) TES_CASE(4) TES_CASE(5) TES_CASE(6) TES_CASE(7) TES_CASE(8)
+                TES_CASE(9) TES_CASE(10)
 #undef TES_CASE
+            }
         }
         if (rc) return rc;
         const int64_t nslots = p.nchunks * S * SCR_CAP;
@@ -989,6 +1411,10 @@ static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* 
         TES_LAUNCH_OK();
         // flag-gated fp64 recomputation of overflowed (chunk, sample) units, one CTA each
         RffPlan fb = p;
+        fb.C = 4;
+        fb.threads = 256;
+        fb.unroll = 2;
+        fb.tile = 1024;
         fb.sg = 1;
         fb.nunits = p.nchunks * S;
         fb.smem = p.smem_fallback;
@@ -1037,8 +1463,12 @@ using namespace tes;
 extern "C" int64_t tes_rff_topk_workspace_bytes(int64_t N, int64_t d, int64_t S, int64_t F, int k) {
     if (N < 0 || d < 1 || d > 64 || S < 1 || F < 1 || k < 1 || k > RFF_MAX_K) return -1;
     // large enough for every method
-    int64_t a = rff_plan(N, d, S, F, k, 1).total_bytes, c = rff_plan(N, d, S, F, k, 2).total_bytes;
-    return a > c ? a : c;
+    int64_t best = 0;
+    for (int m = 1; m <= 3; ++m) {
+        int64_t v = rff_plan(N, d, S, F, k, m).total_bytes;
+        if (v > best) best = v;
+    }
+    return best;
 }
 
 extern "C" int tes_rff_topk_f64(const double* cand, int64_t N, int64_t d, const double* W, const double* b,
@@ -1203,6 +1633,26 @@ extern "C" int tes_argmax_f64(const double* vals, int64_t N, double* out_val, in
     argmax_partial_kernel<<<nb, 256, 0, st>>>(vals, N, pv, pi);
     TES_LAUNCH_OK();
     argmax_final_kernel<<<1, 32, 0, st>>>(vals, pv, pi, nb, out_val, out_idx);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tes_mma_arg_error_probe(const double* x, const double* w, const double* b, int64_t d, int n8,
+                                       double* out_max, void* stream) {
+    if (!x || !w || !b) return -1;
+    if (d < 1 || d > 10) return -4;
+    if (n8 < 1) return -5;
+    if (!out_max) return -6;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (d) {
+#define TES_CASE(DD)                                                        \
+    case DD:                                                                \
+        mma_arg_probe_kernel<DD><<<1, 32, 0, st>>>(x, w, b, n8, out_max);   \
+        break;
+        TES_CASE(1) TES_CASE(2) TES_CASE(3) TES_CASE(4) TES_CASE(5) TES_CASE(6) TES_CASE(7) TES_CASE(8) TES_CASE(9)
+        TES_CASE(10)
+#undef TES_CASE
+    }
     TES_LAUNCH_OK();
     return 0;
 }
