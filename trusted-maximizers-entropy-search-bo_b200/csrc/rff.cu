@@ -372,7 +372,7 @@ __global__ void topk_merge_kernel(const double* __restrict__ vals, const int64_t
 // =====================================================================================================
 constexpr int SCR_THREADS = 256;
 constexpr int SCR_TILE = SCR_THREADS * 4;  // 4 candidates (2 packed pairs) per thread
-constexpr int SCR_CAP = 16;                // kept candidates per (chunk, sample) before the fp64 fallback
+constexpr int SCR_CAP = 32;                // kept candidates per (chunk, sample) before the fp64 fallback
 constexpr int SCR_MAX_K = 8;               // k-th of the 8 warp maxima is the per-tile lower bound
 
 __host__ __device__ constexpr int scr_recp(int d) { return (d + 3) & ~1; }  // 8-byte (v,v) pairs per record
@@ -582,21 +582,69 @@ __device__ __forceinline__ void screen_commit(const ScreenCtx& cx, int jj, const
         __syncthreads();
         if (tid < 32) {
             const int n = *cx.ap_count;
-            const int cnt = cx.slot_cnt[jj];
+            int cnt = cx.slot_cnt[jj];
             const int64_t fo = cx.chunk_id * cx.S + cx.j0 + jj;
-            if (cnt + n > SCR_CAP) {
-                if (lane == 0) cx.flags[fo] = 1;  // overflow: the fp64 kernel recomputes this (chunk, sample)
-            } else {
-                for (int e = lane; e < n; e += 32) {
-                    cx.slot_val[fo * cx.slot_stride + cnt + e] = cx.ap_val[k + e];
-                    cx.slot_idx[fo * cx.slot_stride + cnt + e] = cx.ap_idx[k + e];
-                }
-            }
-            __syncwarp();
-            if (lane == 0) cx.slot_cnt[jj] = cnt + n;
+            double* sv = cx.slot_val + fo * cx.slot_stride;
+            int64_t* si = cx.slot_idx + fo * cx.slot_stride;
+            // 1. fold the new entries into the running top-k of screen values (ap[0..k) holds the old list)
             warp_select_topk(cx.ap_val, cx.ap_idx, k + n, k, cx.tk_val + jj * k, cx.tk_idx + jj * k, lane);
             __syncwarp();
-            if (tid == 0) *cx.ap_count = 0;
+            // the running k-th best only grows, so anything below (new k-th best - 2B) can never be needed
+            const double thr2 = cx.tk_val[jj * k + k - 1] - 2.0 * cx.bound[cx.j0 + jj];
+            if (cnt > SCR_CAP) {
+                // already flagged: nothing to keep
+            } else if (cnt + n > SCR_CAP) {  // 2. compact the kept list in place before giving up on it
+                int w = 0;
+                for (int base = 0; base < cnt; base += 32) {
+                    const int e = base + lane;
+                    const bool in = e < cnt;
+                    const double v = in ? sv[e] : 0.0;
+                    const int64_t i = in ? si[e] : -1;
+                    const bool keep = in && v >= thr2;
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    __syncwarp();
+                    if (keep) {
+                        const int pos = w + __popc(m & ((1u << lane) - 1u));
+                        sv[pos] = v;
+                        si[pos] = i;
+                    }
+                    w += __popc(m);
+                    __syncwarp();
+                }
+                for (int e = w + lane; e < cnt; e += 32) {
+                    si[e] = -1;
+                    sv[e] = neg_inf();
+                }
+                cnt = w;
+                __syncwarp();
+            }
+            // 3. append the new entries that survive thr2
+            bool overflow = cnt > SCR_CAP;
+            for (int base = 0; base < n && !overflow; base += 32) {
+                const int e = base + lane;
+                const bool keep = e < n && cx.ap_val[k + e] >= thr2;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                const int tot = __popc(m);
+                if (cnt + tot > SCR_CAP) {
+                    overflow = true;
+                    break;
+                }
+                if (keep) {
+                    const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+                    sv[pos] = cx.ap_val[k + e];
+                    si[pos] = cx.ap_idx[k + e];
+                }
+                cnt += tot;
+            }
+            if (overflow) {
+                if (lane == 0) cx.flags[fo] = 1;  // the fp64 kernel recomputes this (chunk, sample)
+                cnt = SCR_CAP + 1;                // stays flagged
+            }
+            __syncwarp();
+            if (lane == 0) {
+                cx.slot_cnt[jj] = cnt;
+                *cx.ap_count = 0;
+            }
         }
         __syncthreads();
     }
@@ -837,18 +885,20 @@ __global__ void rff_pack_mma_kernel(const double* __restrict__ W, const double* 
     const int64_t tile = (t_ >> 5) % nt8, j = (t_ >> 5) / nt8;
     const int g = lane >> 2, t = lane & 3;
     const int64_t jw = w_shared ? 0 : j;
-    float* o = featm + t_ * RL;
+    // record element i of a lane lives at [(tile*RL/4 + i/4)*32 + lane][i%4]: every LDS.128 of a warp is contiguous
+    float* base = featm + (t_ >> 5) * 32 * RL;
+    auto at = [&](int i) -> float& { return base[((i >> 2) * 32 + lane) * 4 + (i & 3)]; };
     const int64_t f = tile * 8 + g;
     for (int s = 0; s < KS; ++s)
         for (int e = 0; e < 2; ++e) {
             float v = 0.0f;
             if (f < F) v = mma_bval<D>(W + (jw * F + f) * D, b[jw * F + f], 8 * s + 4 * e + t);
-            o[2 * s + e] = v;
+            at(2 * s + e) = v;
         }
     const int64_t fa = tile * 8 + 2 * t;
-    o[2 * KS] = fa < F ? __double2float_rn(theta[j * F + fa]) : 0.0f;
-    o[2 * KS + 1] = fa + 1 < F ? __double2float_rn(theta[j * F + fa + 1]) : 0.0f;
-    for (int q = 2 * KS + 2; q < RL; ++q) o[q] = 0.0f;
+    at(2 * KS) = fa < F ? __double2float_rn(theta[j * F + fa]) : 0.0f;
+    at(2 * KS + 1) = fa + 1 < F ? __double2float_rn(theta[j * F + fa + 1]) : 0.0f;
+    for (int q = 2 * KS + 2; q < RL; ++q) at(q) = 0.0f;
 }
 
 // A-operand (candidate side) value at compile-time K index k
@@ -987,7 +1037,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 2)
                 if (tid == 0 && p_left > 0) issue();
                 mbar_wait(&full[slot], phase);
                 const int tcnt = min(TPS, nt8 - c * TPS);
-                const float* sp = stage + slot * STAGE_FLOATS + lane * RL;
+                const float* sp = stage + slot * STAGE_FLOATS + lane * 4;
                 auto run_stage = [&](auto reduce_tag) {
                     constexpr bool REDUCE = decltype(reduce_tag)::value;
                     uint64_t acc2[4][2];
@@ -996,10 +1046,9 @@ __global__ void __launch_bounds__(SCR_THREADS, 2)
 #pragma unroll 2
                     for (int ft = 0; ft < tcnt; ++ft) {
                         float rec[RL];
-                        const float4* rp = reinterpret_cast<const float4*>(sp + ft * 32 * RL);
 #pragma unroll
                         for (int q = 0; q < RL / 4; ++q) {
-                            float4 v = rp[q];
+                            const float4 v = *reinterpret_cast<const float4*>(sp + (ft * (RL / 4) + q) * 128);
                             rec[4 * q] = v.x;
                             rec[4 * q + 1] = v.y;
                             rec[4 * q + 2] = v.z;
