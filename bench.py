@@ -247,6 +247,7 @@ def main():
     # ---- fp64 pipe peak (roofline denominator; not in MEASURED_PEAKS.json)
     fp64_peak = ops.fp64_fma_peak(1.0)
     fp32_peak = ops.fp32_fma_peak(1.0)
+    mufu_peak = ops.mufu_cos_peak(1.0)
 
     for w in range(args.warmup):
         flush.zero_()
@@ -300,7 +301,22 @@ def main():
     local_pairs = wl["N"] * wl["S"]
     algo_excl_cos = local_pairs * F * (2 * d + 3) / t_rff * 1e-12  # SURVEY 8(d) figure, cos not counted
     screened = wl["N"] >= 32768 and d <= 10
-    if screened:
+    if screened and d >= 5:
+        # stage A = tensor-core screen (3xTF32 mma.sync dot products, MUFU cosine) + exact fp64 refine: one
+        # MUFU.COS per (candidate, sample, feature) is the binding resource (XU pipe, 16 lanes/SM/clk)
+        cos_rate = local_pairs * F / t_rff * 1e-12
+        roofline = {"bound": "mufu", "kernel": "rff_screen_mma_kernel (+ pack/xmax/bound/refine/fallback/merge)",
+                    "achieved": cos_rate, "peak": mufu_peak, "unit": "Tcos/s", "frac": cos_rate / mufu_peak,
+                    "traffic": None,
+                    "peak_source": "measured in this run: tes_mufu_cos_burn (__cosf = FMUL.RZ + MUFU.COS, 8 chains/thread)",
+                    "fp64_peak_tflops": fp64_peak, "fp32_peak_tflops": fp32_peak,
+                    "algorithmic_excl_cos_tflops": algo_excl_cos,
+                    "algorithmic_vs_fp64_peak": algo_excl_cos / fp64_peak,
+                    "per_unit": "F MUFU.COS + F*(3d+2) TF32 tensor MACs per (candidate, sample) pair; "
+                                "algorithmic = F*(2d+3) flops + F cos (SURVEY 8d)",
+                    "launch_ms": t_rff * 1e3, "share_of_step": t_rff * args.steps / dev_s,
+                    "criterion_ms": float(np.mean(rc)) * 1e3 if rc else None}
+    elif screened:
         # stage A = fp32 screen (all pairs, packed FFMA2 + MUFU) + exact fp64 refine of the kept candidates.
         # fp32-pipe lane operations per (pair, feature): d (dot) + 3 (2*pi reduction) + 1 (theta) packed FMA
         # lanes + 1 FMUL inside __cosf = d + 5, plus 1 MUFU.COS (XU pipe, reported separately).

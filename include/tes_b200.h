@@ -193,6 +193,9 @@ int tes_mma_arg_error_probe(const double* x, const double* w, const double* b, i
 int64_t tes_launch_count(void);
 
 int tes_fp64_fma_burn(int blocks, int64_t iters, double* sink, double* flops, void* stream);
+/* Same for the special-function unit: __cosf (FMUL.RZ + MUFU.COS) evaluations per second; the denominator for the
+ * tensor-core screen of stage A, which is MUFU-bound.  *ops receives the number of cosines. */
+int tes_mufu_cos_burn(int blocks, int64_t iters, float* sink, double* ops, void* stream);
 /* Same for the fp64 tensor-core path (mma.sync m8n8k4 f64): measured to decide whether DMMA is worth using. */
 int tes_fp64_mma_burn(int blocks, int64_t iters, double* sink, double* flops, void* stream);
 /* Same for the packed fp32 pipe (FFMA2, fma.rn.f32x2): the denominator for the fp32 screen of stage A.

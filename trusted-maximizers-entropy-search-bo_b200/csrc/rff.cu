@@ -1236,7 +1236,8 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
     p.recp = scr_recp((int)d);
     const bool can_screen = d <= RFF_MAX_D_FAST && k <= SCR_MAX_K && N >= 1;
     p.screened = 0;
-    if (can_screen && (method == 2 || method == 3 || (method == 0 && N >= SCR_MIN_N))) p.screened = method == 3 ? 2 : 1;
+    if (can_screen && (method == 2 || method == 3 || (method == 0 && N >= SCR_MIN_N)))
+        p.screened = (method == 3 || (method == 0 && d >= 5)) ? 2 : 1;  // tensor-core screen pays off from d = 5
     if (p.screened) {
         p.C = 4;
         p.threads = 256;

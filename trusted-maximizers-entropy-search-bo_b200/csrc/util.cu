@@ -63,7 +63,29 @@ __global__ void __launch_bounds__(256) fp64_mma_burn_kernel(int64_t iters, doubl
     for (int q = 0; q < 4; ++q) s += c[q][0] + c[q][1];
     sink[(int64_t)blockIdx.x * 256 + threadIdx.x] = s;
 }
+// MUFU.COS burn: 8 independent __cosf chains per thread (FMUL.RZ + MUFU.COS each).  ops = blocks*256*iters*8.
+__global__ void __launch_bounds__(256) mufu_cos_burn_kernel(int64_t iters, float* sink) {
+    float a[8];
+    for (int q = 0; q < 8; ++q) a[q] = 0.1f * (q + 1) + threadIdx.x * 1e-4f;
+    for (int64_t i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] = __cosf(a[q]);
+    }
+    float s = 0.f;
+    for (int q = 0; q < 8; ++q) s += a[q];
+    sink[(int64_t)blockIdx.x * 256 + threadIdx.x] = s;
+}
 }  // namespace tes
+
+extern "C" int tes_mufu_cos_burn(int blocks, int64_t iters, float* sink, double* ops, void* stream) {
+    if (blocks < 1) return -1;
+    if (iters < 1) return -2;
+    if (!sink) return -3;
+    tes::mufu_cos_burn_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    TES_LAUNCH_OK();
+    if (ops) *ops = (double)blocks * 256.0 * (double)iters * 8.0;
+    return 0;
+}
 
 extern "C" int tes_fp64_mma_burn(int blocks, int64_t iters, double* sink, double* flops, void* stream) {
     if (blocks < 1) return -1;

@@ -62,17 +62,18 @@ def topk_merge(vals, idx):
     return out_idx, out_val
 
 
-def fp64_fma_peak(seconds=0.5, device=None, fp32=False):
-    """Sustained DFMA (or, fp32=True, packed-FFMA2) rate in TFLOP/s of the current device, CUDA-event timed."""
+def fp64_fma_peak(seconds=0.5, device=None, fp32=False, mufu=False):
+    """Sustained DFMA (fp32=True: packed-FFMA2) rate in TFLOP/s, or (mufu=True) __cosf evaluations in Tcos/s, of
+    the current device, CUDA-event timed."""
     import ctypes
     L = _lib.lib()
     dev_ = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     nsm = torch.cuda.get_device_properties(dev_).multi_processor_count
     blocks = nsm * 8
-    sink = torch.empty(blocks * 256, dtype=torch.float32 if fp32 else torch.float64, device=dev_)
+    sink = torch.empty(blocks * 256, dtype=torch.float32 if (fp32 or mufu) else torch.float64, device=dev_)
     flops = ctypes.c_double(0.0)
     iters = 1 << 16
-    burn = L.tes_fp32_fma_burn if fp32 else L.tes_fp64_fma_burn
+    burn = L.tes_mufu_cos_burn if mufu else (L.tes_fp32_fma_burn if fp32 else L.tes_fp64_fma_burn)
 
     def run(it):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -91,6 +92,10 @@ def fp64_fma_peak(seconds=0.5, device=None, fp32=False):
 
 def fp32_fma_peak(seconds=0.5, device=None):
     return fp64_fma_peak(seconds, device, fp32=True)
+
+
+def mufu_cos_peak(seconds=0.5, device=None):
+    return fp64_fma_peak(seconds, device, mufu=True)
 
 
 # ------------------------------------------------------------------------------------- stage B
