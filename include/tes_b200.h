@@ -181,8 +181,9 @@ int tes_batch_ep_acq_f64(const double* p, int64_t Sp, int64_t nx, double* out_ac
  * DFMA rounds on `blocks` CTAs; returns the flop count through *flops; time it with CUDA events on
  * `stream`.  `sink` is a device buffer of at least blocks*256 doubles. */
 /* Test probe for the fp32 screen's error model: max over EVERY float x in [lo, hi] (both signs) of
- * |__cosf(x) - cos(x)| - e1*|x|, written to *out_max (device double; 0 if never positive). */
-int tes_cosf_error_probe(float lo, float hi, double e1, double* out_max, void* stream);
+ * |c(x) - cos(x)| - e1*|x|, written to *out_max (device double; 0 if never positive); c = __cosf (which = 0) or
+ * the packed FMA-pipe polynomial cosine of the tensor-core screen (which = 1). */
+int tes_cosf_error_probe(float lo, float hi, double e1, int which, double* out_max, void* stream);
 
 /* Test probe for the tensor-core screen: max |h_mma - h_fp64| / A over 16 candidates x (8*n8) features
  * (x (16,d), w (8*n8,d), b (8*n8), all device fp64; d <= 10), written to *out_max (device double). */

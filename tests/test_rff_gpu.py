@@ -180,13 +180,15 @@ def test_cosf_error_model_exhaustive():
     from tes_b200 import _lib
     from tes_b200.device import ptr, stream_ptr
     out = torch.zeros(1, dtype=torch.float64, device="cuda")
-    rc = _lib.lib().tes_cosf_error_probe(0.0, 512.0, 1.7e-7, ptr(out), stream_ptr())
-    _lib.check(rc, "tes_cosf_error_probe")
-    worst = float(out.cpu()[0])
-    assert worst < 2.0e-7, worst
+    for which in (0, 1):   # 0: __cosf (MUFU), 1: the packed FMA-pipe polynomial of the tensor-core screen
+        out.zero_()
+        rc = _lib.lib().tes_cosf_error_probe(0.0, 512.0, 1.7e-7, which, ptr(out), stream_ptr())
+        _lib.check(rc, "tes_cosf_error_probe")
+        worst = float(out.cpu()[0])
+        assert worst < 2.0e-7, (which, worst)
     # and the documented small-argument behaviour, [-pi, pi]: 2^-21.19 (CUDA programming guide) with slack
     out.zero_()
-    _lib.check(_lib.lib().tes_cosf_error_probe(0.0, 3.1415927, 0.0, ptr(out), stream_ptr()), "probe")
+    _lib.check(_lib.lib().tes_cosf_error_probe(0.0, 3.1415927, 0.0, 0, ptr(out), stream_ptr()), "probe")
     assert float(out.cpu()[0]) < 4.5e-7
 
 

@@ -484,14 +484,21 @@ __global__ void rff_bound_kernel(const double* __restrict__ feat, int rec, int64
 }
 
 // test probe: max over every float x in [lo, hi] (both signs) of |__cosf(x) - cos(x)| - e1 |x|
-__global__ void cosf_probe_kernel(unsigned lo_bits, unsigned hi_bits, double e1, double* out) {
+__device__ __forceinline__ uint64_t cos_poly2(uint64_t h);
+__global__ void cosf_probe_kernel(unsigned lo_bits, unsigned hi_bits, double e1, int which, double* out) {
     double m = -1.0;
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned long long bits = (unsigned long long)lo_bits + blockIdx.x * blockDim.x + threadIdx.x;
          bits <= hi_bits; bits += stride) {
         float x = __uint_as_float((unsigned)bits);
         double ref = cos((double)x);
-        double e = fmax(fabs((double)__cosf(x) - ref), fabs((double)__cosf(-x) - ref)) - e1 * fabs((double)x);
+        float cp = __cosf(x), cm = __cosf(-x);
+        if (which == 1) {
+            const uint64_t pr = cos_poly2(f2_pack(x, -x));
+            cp = f2_lo(pr);
+            cm = f2_hi(pr);
+        }
+        double e = fmax(fabs((double)cp - ref), fabs((double)cm - ref)) - e1 * fabs((double)x);
         m = fmax(m, e);
     }
 #pragma unroll
@@ -519,10 +526,30 @@ struct ScreenCtx {
 
 // A tile's NC-per-thread screen values u (=-inf for invalid candidates) of sample jj: keep every candidate
 // within 2 B_j of max(k-th largest warp maximum of this tile, running k-th best of the chunk).
-template <int NC>
+// barrier policies: the whole CTA (barrier 0), or the 256 epilogue threads of the tcgen05 kernel (named barrier 1)
+struct SyncCta {
+    static __device__ __forceinline__ int tid() { return threadIdx.x; }
+    static __device__ __forceinline__ void sync() { __syncthreads(); }
+    static __device__ __forceinline__ bool sync_or(bool p) { return __syncthreads_or(p); }
+};
+struct SyncEpi {  // threads 64..319
+    static __device__ __forceinline__ int tid() { return threadIdx.x - 64; }
+    static __device__ __forceinline__ void sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+    static __device__ __forceinline__ bool sync_or(bool p) {
+        uint32_t r;
+        asm volatile(
+            "{\n.reg .pred pi, po;\nsetp.ne.u32 pi, %1, 0;\nbar.red.or.pred po, 1, 256, pi;\nselp.u32 %0, 1, 0, po;\n}\n"
+            : "=r"(r)
+            : "r"((uint32_t)p)
+            : "memory");
+        return r != 0;
+    }
+};
+
+template <int NC, class Sync = SyncCta>
 __device__ __forceinline__ void screen_commit(const ScreenCtx& cx, int jj, const double (&u)[NC],
                                               const int64_t (&ci)[NC]) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = Sync::tid(), lane = tid & 31, warp = tid >> 5;
     const int k = cx.k;
     double tmax = neg_inf();
 #pragma unroll
@@ -530,7 +557,7 @@ __device__ __forceinline__ void screen_commit(const ScreenCtx& cx, int jj, const
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
     if (lane == 0) cx.wm[warp] = tmax;
-    __syncthreads();
+    Sync::sync();
     // k-th largest (with multiplicity) of the 8 warp maxima: a lower bound of the tile's k-th largest value
     double lk;
     {
@@ -566,7 +593,7 @@ __device__ __forceinline__ void screen_commit(const ScreenCtx& cx, int jj, const
     bool qual = false;
 #pragma unroll
     for (int cc = 0; cc < NC; ++cc) qual |= (ci[cc] < cx.c1) && (u[cc] >= thr);
-    if (__syncthreads_or(qual)) {
+    if (Sync::sync_or(qual)) {
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc) {
             if ((ci[cc] < cx.c1) && (u[cc] >= thr)) {
@@ -579,7 +606,7 @@ __device__ __forceinline__ void screen_commit(const ScreenCtx& cx, int jj, const
             cx.ap_val[tid] = cx.tk_val[jj * k + tid];
             cx.ap_idx[tid] = cx.tk_idx[jj * k + tid];
         }
-        __syncthreads();
+        Sync::sync();
         if (tid < 32) {
             const int n = *cx.ap_count;
             int cnt = cx.slot_cnt[jj];
@@ -646,7 +673,7 @@ __device__ __forceinline__ void screen_commit(const ScreenCtx& cx, int jj, const
                 *cx.ap_count = 0;
             }
         }
-        __syncthreads();
+        Sync::sync();
     }
 }
 
@@ -834,12 +861,37 @@ __global__ void __launch_bounds__(SCR_THREADS, MINB)
 // Error model: |h_mma - h| <= 6e-6 A_f (3.5 * 2^-22 from the dropped lo*lo / tf32 residuals / fp32 input
 // rounding, 2^-18 for <= 32 truncating fp32 accumulations), verified by tes_mma_arg_error_probe.
 // =====================================================================================================
+// packed fp32 cosine on the FMA pipe: n = rint(h/pi), r = fma(n, -pi_f32, h) in [-pi/2, pi/2] (+ slack), degree-4
+// minimax polynomial in r^2 (approximation error 4.7e-8 on 1.001*pi/2), sign from the parity of n.  It shares
+// the (SCR_E0, SCR_E1) error model of __cosf, verified exhaustively by the same probe (which = 1).
+__device__ __forceinline__ uint64_t cos_poly2(uint64_t h) {
+    const uint64_t INVPI2 = f2_pack(0.31830987f, 0.31830987f);
+    const uint64_t MAGIC2 = f2_pack(12582912.0f, 12582912.0f);
+    const uint64_t NMAGIC2 = f2_pack(-12582912.0f, -12582912.0f);
+    const uint64_t NPI2 = f2_pack(-3.14159274f, -3.14159274f);
+    const uint64_t t = ffma2(h, INVPI2, MAGIC2);
+    const uint64_t n = fadd2(t, NMAGIC2);
+    const uint64_t r = ffma2(n, NPI2, h);
+    const uint64_t s2 = fmul2(r, r);
+    uint64_t p = ffma2(f2_pack(0x1.8467a8p-16f, 0x1.8467a8p-16f), s2, f2_pack(-0x1.6b29b6p-10f, -0x1.6b29b6p-10f));
+    p = ffma2(p, s2, f2_pack(0x1.554ed4p-5f, 0x1.554ed4p-5f));
+    p = ffma2(p, s2, f2_pack(-0x1.ffffcp-2f, -0x1.ffffcp-2f));
+    p = ffma2(p, s2, f2_pack(0x1.fffffep-1f, 0x1.fffffep-1f));
+    const uint32_t lo = (uint32_t)p ^ ((uint32_t)t << 31);
+    const uint32_t hi = (uint32_t)(p >> 32) ^ ((uint32_t)(t >> 32) << 31);
+    return ((uint64_t)hi << 32) | lo;
+}
+
 template <int D>
 struct MmaCfg {
     static constexpr int KS = (3 * D + 2 + 7) / 8;
     static constexpr int RL = ((2 * KS + 2) + 3) & ~3;  // floats per lane record
 };
-constexpr int MMA_TILE = 512;  // candidates per CTA tile: 8 warps x 4 row tiles x 16 rows
+constexpr int MMA_RT = 4;                  // row tiles (of 16 candidates) per warp
+constexpr int MMA_NPOLY = 0;               // accumulator pairs (of 8 per feature tile) whose cosine runs on the FMA pipe:
+                                           // measured slower for every value > 0 here (mma.sync already fills the issue
+                                           // slots); the tcgen05 kernel, whose MMA is off the issue path, uses the mix
+constexpr int MMA_TILE = 8 * MMA_RT * 16;  // candidates per CTA tile
 constexpr double MMA_HARG = 6.0e-6;
 
 __device__ __forceinline__ uint32_t to_tf32(float v) {
@@ -848,7 +900,7 @@ __device__ __forceinline__ uint32_t to_tf32(float v) {
     return r;
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -911,8 +963,8 @@ __device__ __forceinline__ float mma_aval(const float (&xh)[D], const float (&xl
     return 0.0f;
 }
 
-template <int D>
-__global__ void __launch_bounds__(SCR_THREADS, 2)
+template <int D, int RT, int MINB, int NPOLY>
+__global__ void __launch_bounds__(SCR_THREADS, MINB)
     rff_screen_mma_kernel(const double* __restrict__ cand, int64_t N, const float* __restrict__ featm, int S, int F,
                           double scale, int k, int sg, int64_t chunk, int64_t idx_offset,
                           const double* __restrict__ bound, const int* __restrict__ mode,
@@ -920,7 +972,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 2)
                           int* __restrict__ flags) {
     constexpr int KS = MmaCfg<D>::KS, RL = MmaCfg<D>::RL;
     constexpr int THREADS = SCR_THREADS;
-    constexpr int TILE = MMA_TILE;
+    constexpr int TILE = 8 * RT * 16;  // candidates per CTA tile: 8 warps x RT row tiles x 16 rows
     constexpr int TPS = RFF_FCH / 8;               // feature tiles per pipeline stage
     constexpr int STAGE_FLOATS = TPS * 32 * RL;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -995,15 +1047,15 @@ __global__ void __launch_bounds__(SCR_THREADS, 2)
     const uint64_t NMAGIC2 = f2_pack(-12582912.0f, -12582912.0f);
     const uint64_t NTWOPI2 = f2_pack(-6.2831855f, -6.2831855f);
 
-    uint32_t afr[4][KS][4];   // A fragments: [row tile][k-step][a0..a3]
-    double dacc[4][2];        // [row tile][row g | row g+8], partial over this lane's feature columns
+    uint32_t afr[RT][KS][4];   // A fragments: [row tile][k-step][a0..a3]
+    double dacc[RT][2];        // [row tile][row g | row g+8], partial over this lane's feature columns
     int slot = 0;
     uint32_t phase = 0;
 
     for (int tile = 0; tile < ntiles; ++tile) {
-        const int64_t t0 = c0 + (int64_t)tile * TILE + warp * 64;
+        const int64_t t0 = c0 + (int64_t)tile * TILE + warp * (RT * 16);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < RT; ++r) {
             float xh[2][D], xl[2][D];
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
@@ -1031,7 +1083,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 2)
         }
         for (int jj = 0; jj < nj; ++jj) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) dacc[r][0] = dacc[r][1] = 0.0;
+            for (int r = 0; r < RT; ++r) dacc[r][0] = dacc[r][1] = 0.0;
             const int red = mode[j0 + jj];
             for (int c = 0; c < nch; ++c) {
                 if (tid == 0 && p_left > 0) issue();
@@ -1040,9 +1092,9 @@ __global__ void __launch_bounds__(SCR_THREADS, 2)
                 const float* sp = stage + slot * STAGE_FLOATS + lane * 4;
                 auto run_stage = [&](auto reduce_tag) {
                     constexpr bool REDUCE = decltype(reduce_tag)::value;
-                    uint64_t acc2[4][2];
+                    uint64_t acc2[RT][2];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) acc2[r][0] = acc2[r][1] = 0ull;
+                    for (int r = 0; r < RT; ++r) acc2[r][0] = acc2[r][1] = 0ull;
 #pragma unroll 2
                     for (int ft = 0; ft < tcnt; ++ft) {
                         float rec[RL];
@@ -1055,26 +1107,40 @@ __global__ void __launch_bounds__(SCR_THREADS, 2)
                             rec[4 * q + 3] = v.w;
                         }
                         const uint64_t th2 = f2_pack(rec[2 * KS], rec[2 * KS + 1]);
+                        // all RT x KS MMAs first, k-step major: RT independent accumulator chains in flight
+                        float cc[RT][4];
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            float cc[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int r = 0; r < RT; ++r) cc[r][0] = cc[r][1] = cc[r][2] = cc[r][3] = 0.f;
 #pragma unroll
-                            for (int s = 0; s < KS; ++s)
-                                mma_tf32(cc, afr[r][s], __float_as_uint(rec[2 * s]), __float_as_uint(rec[2 * s + 1]));
-                            uint64_t h01 = f2_pack(cc[0], cc[1]), h23 = f2_pack(cc[2], cc[3]);
+                        for (int s = 0; s < KS; ++s)
+#pragma unroll
+                            for (int r = 0; r < RT; ++r)
+                                mma_tf32(cc[r], afr[r][s], __float_as_uint(rec[2 * s]), __float_as_uint(rec[2 * s + 1]));
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) {
+                            uint64_t h01 = f2_pack(cc[r][0], cc[r][1]), h23 = f2_pack(cc[r][2], cc[r][3]);
                             if (REDUCE) {
                                 uint64_t ta = ffma2(h01, INV2PI2, MAGIC2), tb = ffma2(h23, INV2PI2, MAGIC2);
                                 h01 = ffma2(fadd2(ta, NMAGIC2), NTWOPI2, h01);
                                 h23 = ffma2(fadd2(tb, NMAGIC2), NTWOPI2, h23);
                             }
-                            const uint64_t c01 = f2_pack(__cosf(f2_lo(h01)), __cosf(f2_hi(h01)));
-                            const uint64_t c23 = f2_pack(__cosf(f2_lo(h23)), __cosf(f2_hi(h23)));
+                            // the last NPOLY of the 2*RT accumulator pairs of a feature tile take their cosine on the
+                            // FMA pipe (polynomial), the others on the MUFU: both pipes work concurrently
+                            uint64_t c01, c23;
+                            if (2 * r >= 2 * RT - NPOLY)
+                                c01 = cos_poly2(f2_pack(cc[r][0], cc[r][1]));
+                            else
+                                c01 = f2_pack(__cosf(f2_lo(h01)), __cosf(f2_hi(h01)));
+                            if (2 * r + 1 >= 2 * RT - NPOLY)
+                                c23 = cos_poly2(f2_pack(cc[r][2], cc[r][3]));
+                            else
+                                c23 = f2_pack(__cosf(f2_lo(h23)), __cosf(f2_hi(h23)));
                             acc2[r][0] = ffma2(th2, c01, acc2[r][0]);
                             acc2[r][1] = ffma2(th2, c23, acc2[r][1]);
                         }
                     }
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
+                    for (int r = 0; r < RT; ++r) {
                         dacc[r][0] += (double)f2_lo(acc2[r][0]) + (double)f2_hi(acc2[r][0]);
                         dacc[r][1] += (double)f2_lo(acc2[r][1]) + (double)f2_hi(acc2[r][1]);
                     }
@@ -1091,7 +1157,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 2)
             }
             // quad reduction: the 4 lanes sharing g hold partial sums over disjoint feature columns
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < RT; ++r)
 #pragma unroll
                 for (int h2 = 0; h2 < 2; ++h2) {
                     double v = dacc[r][h2];
@@ -1104,8 +1170,11 @@ __global__ void __launch_bounds__(SCR_THREADS, 2)
             int64_t ci[2];
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
-                const double v = t == 0 ? dacc[0][h2] : (t == 1 ? dacc[1][h2] : (t == 2 ? dacc[2][h2] : dacc[3][h2]));
-                ci[h2] = t0 + t * 16 + g + 8 * h2;
+                double v = dacc[0][h2];
+#pragma unroll
+                for (int r = 1; r < RT; ++r) v = (t == r) ? dacc[r][h2] : v;
+                const bool own = t < RT;  // lanes beyond the row-tile count own no candidate
+                ci[h2] = own ? t0 + t * 16 + g + 8 * h2 : c1;
                 u[h2] = (ci[h2] < c1) ? scale * v : neg_inf();
             }
             screen_commit<2>(cx, jj, u, ci);
@@ -1244,7 +1313,11 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
         p.unroll = 2;
     }
     p.tile = p.threads * p.C;
-    if (p.screened == 2) p.tile = MMA_TILE;  // candidate tile of the tensor-core screen (fp64 fallback tiles itself)
+    if (p.screened == 2) {  // candidate tile of the tensor-core screen (the fp64 fallback tiles itself)
+        int rt = MMA_RT, mb = 2;
+        if (const char* v = getenv("TES_MMA_VARIANT")) sscanf(v, "%d,%d", &rt, &mb);
+        p.tile = 8 * rt * 16;
+    }
     int64_t ntiles = (N + p.tile - 1) / p.tile;
     if (ntiles < 1) ntiles = 1;
     int64_t tpc = ntiles < 16 ? ntiles : 16;  // tiles per chunk
@@ -1273,7 +1346,7 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
             const int ks = (3 * (int)d + 2 + 7) / 8, rl = ((2 * ks + 2) + 3) & ~3;
             p.feat32_bytes = align_up(S * ((F + 7) / 8) * 32 * rl * (int64_t)sizeof(float), 256);
             p.smem_screen = (size_t)RFF_NSTAGE * (RFF_FCH / 8) * 32 * rl * sizeof(float) + 8 * sizeof(uint64_t) +
-                            (size_t)p.sg * k * 16 + (size_t)(MMA_TILE + 16) * 16 + 8 * sizeof(double) +
+                            (size_t)p.sg * k * 16 + (size_t)(512 + 16) * 16 + 8 * sizeof(double) +
                             (size_t)p.sg * sizeof(int) + 16;
         }
         p.aux_bytes = align_up(64 * 8, 256) + 2 * align_up(S * 8, 256);  // xmax[64], bound[S], mode[S]
@@ -1358,7 +1431,20 @@ template <int D>
 static int launch_rff_screen_mma(const RffPlan& p, const double* cand, int64_t N, const float* featm, int64_t S,
                                  int64_t F, double scale, int k, int64_t idx_offset, const double* bound,
                                  const int* mode, double* slot_val, int64_t* slot_idx, int* flags, cudaStream_t st) {
-    auto kern = rff_screen_mma_kernel<D>;
+    int rt = MMA_RT, mb = 2;
+    if (const char* v = getenv("TES_MMA_VARIANT")) sscanf(v, "%d,%d", &rt, &mb);  // developer knob
+    void (*kern)(const double*, int64_t, const float*, int, int, double, int, int, int64_t, int64_t, const double*,
+                 const int*, double*, int64_t*, int, int*) = rff_screen_mma_kernel<D, MMA_RT, 2, MMA_NPOLY>;
+#ifdef TES_RFF_DEV_VARIANTS
+    if constexpr (D == 6) {  // developer sweep: second knob = number of polynomial pairs
+        if (rt == 4 && mb == 0) kern = rff_screen_mma_kernel<D, 4, 2, 0>;
+        if (rt == 4 && mb == 1) kern = rff_screen_mma_kernel<D, 4, 2, 1>;
+        if (rt == 4 && mb == 2) kern = rff_screen_mma_kernel<D, 4, 2, 2>;
+        if (rt == 4 && mb == 3) kern = rff_screen_mma_kernel<D, 4, 2, 3>;
+        if (rt == 4 && mb == 4) kern = rff_screen_mma_kernel<D, 4, 2, 4>;
+        if (rt == 4 && mb == 5) kern = rff_screen_mma_kernel<D, 4, 2, 5>;
+    }
+#endif
     if (p.smem_screen > 48 * 1024)
         TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_screen));
     TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -1595,15 +1681,16 @@ extern "C" int tes_rff_eval_f64(const double* cand, int64_t N, int64_t d, const 
     return 0;
 }
 
-extern "C" int tes_cosf_error_probe(float lo, float hi, double e1, double* out_max, void* stream) {
+extern "C" int tes_cosf_error_probe(float lo, float hi, double e1, int which, double* out_max, void* stream) {
     if (!(lo >= 0.0f) || !(hi >= lo)) return -1;
-    if (!out_max) return -4;
+    if (!out_max) return -5;
     unsigned lb, hb;
     memcpy(&lb, &lo, 4);
     memcpy(&hb, &hi, 4);
     cudaStream_t st = (cudaStream_t)stream;
     TES_CUDA_OK(cudaMemsetAsync(out_max, 0, sizeof(double), st));
-    cosf_probe_kernel<<<148 * 8, 256, 0, st>>>(lb, hb, e1, out_max);
+    if (which < 0 || which > 1) return -4;
+    cosf_probe_kernel<<<148 * 8, 256, 0, st>>>(lb, hb, e1, which, out_max);
     TES_LAUNCH_OK();
     return 0;
 }
