@@ -190,6 +190,11 @@ int tes_cosf_error_probe(float lo, float hi, double e1, int which, double* out_m
 int tes_mma_arg_error_probe(const double* x, const double* w, const double* b, int64_t d, int n8, double* out_max,
                             void* stream);
 
+/* Same probe for the tcgen05/TMEM screen (method 4): 128 candidates x (64*nt) features through the kernel's own
+ * operand construction, tcgen05.mma kind::tf32 and tcgen05.ld (x (128,d), w (64*nt,d), b (64*nt)). */
+int tes_tc5_arg_error_probe(const double* x, const double* w, const double* b, int64_t d, int nt, double* out_max,
+                            void* stream);
+
 /* number of kernels this library has launched in this process so far (monotonic statistic) */
 int64_t tes_launch_count(void);
 

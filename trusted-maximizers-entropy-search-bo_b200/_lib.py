@@ -70,6 +70,7 @@ SIGNATURES = {
     "tes_batch_ep_acq_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "tes_cosf_error_probe": (c_int, [ctypes.c_float, ctypes.c_float, c_dbl, c_int, c_ptr, c_ptr]),
     "tes_mma_arg_error_probe": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr]),
+    "tes_tc5_arg_error_probe": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr]),
     "tes_launch_count": (c_i64, []),
     "tes_mufu_cos_burn": (c_int, [c_int, c_i64, c_ptr, ctypes.POINTER(c_dbl), c_ptr]),
     "tes_fp64_mma_burn": (c_int, [c_int, c_i64, c_ptr, ctypes.POINTER(c_dbl), c_ptr]),

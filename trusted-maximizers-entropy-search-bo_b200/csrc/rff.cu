@@ -524,29 +524,86 @@ struct ScreenCtx {
     int64_t chunk_id, c1, idx_offset;
 };
 
+// One full warp folds the n appended entries ap[k .. k+n) (ap[0..k) = the old running list) of sample jj into the
+// running screen top-k and the kept-candidate slots of the (chunk, sample); resets the append counter.
+__device__ __forceinline__ void screen_fold_warp(const ScreenCtx& cx, int jj, int lane) {
+    const int k = cx.k;
+    const int n = *cx.ap_count;
+    int cnt = cx.slot_cnt[jj];
+    const int64_t fo = cx.chunk_id * cx.S + cx.j0 + jj;
+    double* sv = cx.slot_val + fo * cx.slot_stride;
+    int64_t* si = cx.slot_idx + fo * cx.slot_stride;
+    // 1. fold the new entries into the running top-k of screen values (ap[0..k) holds the old list)
+    warp_select_topk(cx.ap_val, cx.ap_idx, k + n, k, cx.tk_val + jj * k, cx.tk_idx + jj * k, lane);
+    __syncwarp();
+    // the running k-th best only grows, so anything below (new k-th best - 2B) can never be needed
+    const double thr2 = cx.tk_val[jj * k + k - 1] - 2.0 * cx.bound[cx.j0 + jj];
+    if (cnt > SCR_CAP) {
+        // already flagged: nothing to keep
+    } else if (cnt + n > SCR_CAP) {  // 2. compact the kept list in place before giving up on it
+        int w = 0;
+        for (int base = 0; base < cnt; base += 32) {
+            const int e = base + lane;
+            const bool in = e < cnt;
+            const double v = in ? sv[e] : 0.0;
+            const int64_t i = in ? si[e] : -1;
+            const bool keep = in && v >= thr2;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();
+            if (keep) {
+                const int pos = w + __popc(m & ((1u << lane) - 1u));
+                sv[pos] = v;
+                si[pos] = i;
+            }
+            w += __popc(m);
+            __syncwarp();
+        }
+        for (int e = w + lane; e < cnt; e += 32) {
+            si[e] = -1;
+            sv[e] = neg_inf();
+        }
+        cnt = w;
+        __syncwarp();
+    }
+    // 3. append the new entries that survive thr2
+    bool overflow = cnt > SCR_CAP;
+    for (int base = 0; base < n && !overflow; base += 32) {
+        const int e = base + lane;
+        const bool keep = e < n && cx.ap_val[k + e] >= thr2;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int tot = __popc(m);
+        if (cnt + tot > SCR_CAP) {
+            overflow = true;
+            break;
+        }
+        if (keep) {
+            const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+            sv[pos] = cx.ap_val[k + e];
+            si[pos] = cx.ap_idx[k + e];
+        }
+        cnt += tot;
+    }
+    if (overflow) {
+        if (lane == 0) cx.flags[fo] = 1;  // the fp64 kernel recomputes this (chunk, sample)
+        cnt = SCR_CAP + 1;                // stays flagged
+    }
+    __syncwarp();
+    if (lane == 0) {
+        cx.slot_cnt[jj] = cnt;
+        *cx.ap_count = 0;
+    }
+}
+
 // A tile's NC-per-thread screen values u (=-inf for invalid candidates) of sample jj: keep every candidate
 // within 2 B_j of max(k-th largest warp maximum of this tile, running k-th best of the chunk).
-// barrier policies: the whole CTA (barrier 0), or the 256 epilogue threads of the tcgen05 kernel (named barrier 1)
+// barrier policy: the whole CTA (barrier 0)
 struct SyncCta {
     static __device__ __forceinline__ int tid() { return threadIdx.x; }
     static __device__ __forceinline__ void sync() { __syncthreads(); }
     static __device__ __forceinline__ bool sync_or(bool p) { return __syncthreads_or(p); }
 };
-struct SyncEpi {  // threads 64..319
-    static __device__ __forceinline__ int tid() { return threadIdx.x - 64; }
-    static __device__ __forceinline__ void sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-    static __device__ __forceinline__ bool sync_or(bool p) {
-        uint32_t r;
-        asm volatile(
-            "{\n.reg .pred pi, po;\nsetp.ne.u32 pi, %1, 0;\nbar.red.or.pred po, 1, 256, pi;\nselp.u32 %0, 1, 0, po;\n}\n"
-            : "=r"(r)
-            : "r"((uint32_t)p)
-            : "memory");
-        return r != 0;
-    }
-};
 
-template <int NC, class Sync = SyncCta>
+template <int NC, class Sync = SyncCta, int NW = 8>
 __device__ __forceinline__ void screen_commit(const ScreenCtx& cx, int jj, const double (&u)[NC],
                                               const int64_t (&ci)[NC]) {
     const int tid = Sync::tid(), lane = tid & 31, warp = tid >> 5;
@@ -558,12 +615,12 @@ __device__ __forceinline__ void screen_commit(const ScreenCtx& cx, int jj, const
     for (int off = 16; off > 0; off >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
     if (lane == 0) cx.wm[warp] = tmax;
     Sync::sync();
-    // k-th largest (with multiplicity) of the 8 warp maxima: a lower bound of the tile's k-th largest value
+    // k-th largest (with multiplicity) of the NW warp maxima: a lower bound of the tile's k-th largest value
     double lk;
     {
-        double a[8];
+        double a[NW];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) a[q] = cx.wm[q];
+        for (int q = 0; q < NW; ++q) a[q] = cx.wm[q];
         lk = neg_inf();
         double prev = pos_inf();
         int taken = 0;
@@ -571,7 +628,7 @@ __device__ __forceinline__ void screen_commit(const ScreenCtx& cx, int jj, const
             double best = neg_inf();
             int cnt = 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < NW; ++q) {
                 if (a[q] < prev) {
                     if (a[q] > best) {
                         best = a[q];
@@ -607,72 +664,7 @@ __device__ __forceinline__ void screen_commit(const ScreenCtx& cx, int jj, const
             cx.ap_idx[tid] = cx.tk_idx[jj * k + tid];
         }
         Sync::sync();
-        if (tid < 32) {
-            const int n = *cx.ap_count;
-            int cnt = cx.slot_cnt[jj];
-            const int64_t fo = cx.chunk_id * cx.S + cx.j0 + jj;
-            double* sv = cx.slot_val + fo * cx.slot_stride;
-            int64_t* si = cx.slot_idx + fo * cx.slot_stride;
-            // 1. fold the new entries into the running top-k of screen values (ap[0..k) holds the old list)
-            warp_select_topk(cx.ap_val, cx.ap_idx, k + n, k, cx.tk_val + jj * k, cx.tk_idx + jj * k, lane);
-            __syncwarp();
-            // the running k-th best only grows, so anything below (new k-th best - 2B) can never be needed
-            const double thr2 = cx.tk_val[jj * k + k - 1] - 2.0 * cx.bound[cx.j0 + jj];
-            if (cnt > SCR_CAP) {
-                // already flagged: nothing to keep
-            } else if (cnt + n > SCR_CAP) {  // 2. compact the kept list in place before giving up on it
-                int w = 0;
-                for (int base = 0; base < cnt; base += 32) {
-                    const int e = base + lane;
-                    const bool in = e < cnt;
-                    const double v = in ? sv[e] : 0.0;
-                    const int64_t i = in ? si[e] : -1;
-                    const bool keep = in && v >= thr2;
-                    const unsigned m = __ballot_sync(0xffffffffu, keep);
-                    __syncwarp();
-                    if (keep) {
-                        const int pos = w + __popc(m & ((1u << lane) - 1u));
-                        sv[pos] = v;
-                        si[pos] = i;
-                    }
-                    w += __popc(m);
-                    __syncwarp();
-                }
-                for (int e = w + lane; e < cnt; e += 32) {
-                    si[e] = -1;
-                    sv[e] = neg_inf();
-                }
-                cnt = w;
-                __syncwarp();
-            }
-            // 3. append the new entries that survive thr2
-            bool overflow = cnt > SCR_CAP;
-            for (int base = 0; base < n && !overflow; base += 32) {
-                const int e = base + lane;
-                const bool keep = e < n && cx.ap_val[k + e] >= thr2;
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                const int tot = __popc(m);
-                if (cnt + tot > SCR_CAP) {
-                    overflow = true;
-                    break;
-                }
-                if (keep) {
-                    const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-                    sv[pos] = cx.ap_val[k + e];
-                    si[pos] = cx.ap_idx[k + e];
-                }
-                cnt += tot;
-            }
-            if (overflow) {
-                if (lane == 0) cx.flags[fo] = 1;  // the fp64 kernel recomputes this (chunk, sample)
-                cnt = SCR_CAP + 1;                // stays flagged
-            }
-            __syncwarp();
-            if (lane == 0) {
-                cx.slot_cnt[jj] = cnt;
-                *cx.ap_count = 0;
-            }
-        }
+        if (tid < 32) screen_fold_warp(cx, jj, lane);
         Sync::sync();
     }
 }
@@ -1266,6 +1258,8 @@ __global__ void rff_refine_kernel(const double* __restrict__ cand, int d, const 
     slot_val[o] = __dmul_rn(scale, acc);
 }
 
+#include "rff_tc5.cuh"
+
 struct RffPlan {
     int C, threads, unroll, tile, sg, rec;
     int64_t chunk, nchunks, nunits;
@@ -1286,8 +1280,8 @@ static size_t rff_smem_fp64(int rec, int sg, int k, int tile) {
            (size_t)(tile + RFF_MAX_K) * 16 + 16;
 }
 
-// method: 0 = auto, 1 = fp64 only, 2 = packed-fp32 screen + fp64 refine, 3 = tensor-core (3xTF32) screen + fp64
-// refine (2/3 only when the shape allows it)
+// method: 0 = auto, 1 = fp64 only, 2 = packed-fp32 screen + fp64 refine, 3 = tensor-core (3xTF32 mma.sync) screen +
+// fp64 refine, 4 = tcgen05/TMEM (3xTF32) screen + fp64 refine (2/3/4 only when the shape allows it)
 static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int method) {
     RffPlan p{};
     p.C = 4;
@@ -1305,8 +1299,8 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
     p.recp = scr_recp((int)d);
     const bool can_screen = d <= RFF_MAX_D_FAST && k <= SCR_MAX_K && N >= 1;
     p.screened = 0;
-    if (can_screen && (method == 2 || method == 3 || (method == 0 && N >= SCR_MIN_N)))
-        p.screened = (method == 3 || (method == 0 && d >= 5)) ? 2 : 1;  // tensor-core screen pays off from d = 5
+    if (can_screen && (method == 2 || method == 3 || method == 4 || (method == 0 && N >= SCR_MIN_N)))
+        p.screened = method == 4 ? 3 : ((method == 3 || (method == 0 && d >= 5)) ? 2 : 1);
     if (p.screened) {
         p.C = 4;
         p.threads = 256;
@@ -1318,13 +1312,14 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
         if (const char* v = getenv("TES_MMA_VARIANT")) sscanf(v, "%d,%d", &rt, &mb);
         p.tile = 8 * rt * 16;
     }
+    if (p.screened == 3) p.tile = TC5_TILE;
     int64_t ntiles = (N + p.tile - 1) / p.tile;
     if (ntiles < 1) ntiles = 1;
     int64_t tpc = ntiles < 16 ? ntiles : 16;  // tiles per chunk
     int64_t sg = S < 32 ? S : 32;
     auto units = [&]() { return ((ntiles + tpc - 1) / tpc) * ((S + sg - 1) / sg); };
     const int64_t want = 8 * 148;
-    if (p.screened == 2) tpc = ntiles < 32 ? ntiles : 32;
+    if (p.screened >= 2) tpc = ntiles < 32 ? ntiles : 32;
     while (units() < want && tpc > 4) tpc = (tpc + 1) / 2;
     while (units() < want && sg > 1) sg = (sg + 1) / 2;
     while (units() < want && tpc > 1) tpc = (tpc + 1) / 2;
@@ -1348,6 +1343,14 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
             p.smem_screen = (size_t)RFF_NSTAGE * (RFF_FCH / 8) * 32 * rl * sizeof(float) + 8 * sizeof(uint64_t) +
                             (size_t)p.sg * k * 16 + (size_t)(512 + 16) * 16 + 8 * sizeof(double) +
                             (size_t)p.sg * sizeof(int) + 16;
+        }
+        if (p.screened == 3) {
+            const int kc = tc5_kc((int)d);
+            const int64_t sf = tc5_stage_floats(kc);
+            p.feat32_bytes = align_up(S * ((F + TC5_NF - 1) / TC5_NF) * sf * (int64_t)sizeof(float), 256);
+            p.smem_screen = (size_t)TC5_MT * kc * 128 * 16 + (size_t)TC5_NSTAGE * sf * sizeof(float) +
+                            (2 * TC5_NSTAGE + 10) * sizeof(uint64_t) + 2 * TC5_TILE * sizeof(double) +
+                            (size_t)p.sg * k * 16 + (size_t)(TC5_TILE + 16) * 16 + (size_t)p.sg * sizeof(int) + 16;
         }
         p.aux_bytes = align_up(64 * 8, 256) + 2 * align_up(S * 8, 256);  // xmax[64], bound[S], mode[S]
         p.flags_bytes = align_up(p.nchunks * S * (int64_t)sizeof(int), 256);
@@ -1455,6 +1458,28 @@ static int launch_rff_screen_mma(const RffPlan& p, const double* cand, int64_t N
     return 0;
 }
 
+static int launch_rff_screen_tc5(const RffPlan& p, const double* cand, int64_t N, int d, const float* featt, int64_t S,
+                                 int64_t F, double scale, int k, int64_t idx_offset, const double* bound,
+                                 const int* mode, double* slot_val, int64_t* slot_idx, int* flags, cudaStream_t st) {
+    int np = TC5_NPOLY;
+    if (const char* v = getenv("TES_TC5_NPOLY")) sscanf(v, "%d", &np);  // developer knob (needs the dev build)
+    void (*kern)(const double*, int64_t, int, const float*, int, int, int, double, int, int, int64_t, int64_t,
+                 const double*, const int*, double*, int64_t*, int, int*) = rff_screen_tc5_kernel<TC5_NPOLY>;
+#ifdef TES_RFF_DEV_VARIANTS
+    if (np == 0) kern = rff_screen_tc5_kernel<0>;
+    if (np == 1) kern = rff_screen_tc5_kernel<1>;
+    if (np == 2) kern = rff_screen_tc5_kernel<2>;
+    if (np == 3) kern = rff_screen_tc5_kernel<3>;
+    if (np == 4) kern = rff_screen_tc5_kernel<4>;
+#endif
+    TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_screen));
+    kern<<<(unsigned)p.nunits_screen, TC5_THREADS, p.smem_screen, st>>>(
+        cand, N, d, featt, tc5_kc(d), (int)S, (int)F, scale, k, p.sg_screen, p.chunk, idx_offset, bound, mode, slot_val,
+        slot_idx, p.slot_stride, flags);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
 static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* W, const double* b,
                         const double* theta, int64_t S, int64_t F, int w_shared, double sigma, int k,
                         int64_t idx_offset, int64_t* out_idx, double* out_val, void* ws, int64_t ws_bytes,
@@ -1470,7 +1495,7 @@ static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* 
     if (k < 1 || k > RFF_MAX_K) return -11;
     if (!out_idx) return -13;
     if (!out_val) return -14;
-    if (method < 0 || method > 3) return -18;
+    if (method < 0 || method > 4) return -18;
     RffPlan p = rff_plan(N, d, S, F, k, method);
     if (!ws || ws_bytes < p.total_bytes) return -100;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1504,7 +1529,16 @@ static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* 
         rff_xmax_kernel<<<148 * 4, 256, 0, st>>>(cand, N, (int)d, xmax);
         TES_LAUNCH_OK();
         int rc = 0;
-        if (p.screened == 2) {
+        if (p.screened == 3) {
+            const int64_t nrow = S * ((F + TC5_NF - 1) / TC5_NF) * TC5_NF;
+            rff_bound_kernel<<<(unsigned)S, 32, 0, st>>>(feat, p.rec, S, F, (int)d, xmax, scale, MMA_HARG, bound, mode);
+            TES_LAUNCH_OK();
+            rff_pack_tc5_kernel<<<(unsigned)((nrow + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, (int)d, w_shared,
+                                                                                 tc5_kc((int)d), (float*)feat32);
+            TES_LAUNCH_OK();
+            rc = launch_rff_screen_tc5(p, cand, N, (int)d, (const float*)feat32, S, F, scale, k, idx_offset, bound, mode,
+                                       part_val, part_idx, flags, st);
+        } else if (p.screened == 2) {
             const int64_t nrec = S * ((F + 7) / 8) * 32;
             rff_bound_kernel<<<(unsigned)S, 32, 0, st>>>(feat, p.rec, S, F, (int)d, xmax, scale, MMA_HARG, bound, mode);
             TES_LAUNCH_OK();
@@ -1600,7 +1634,7 @@ extern "C" int64_t tes_rff_topk_workspace_bytes(int64_t N, int64_t d, int64_t S,
     if (N < 0 || d < 1 || d > 64 || S < 1 || F < 1 || k < 1 || k > RFF_MAX_K) return -1;
     // large enough for every method
     int64_t best = 0;
-    for (int m = 1; m <= 3; ++m) {
+    for (int m = 1; m <= 4; ++m) {
         int64_t v = rff_plan(N, d, S, F, k, m).total_bytes;
         if (v > best) best = v;
     }
@@ -1790,6 +1824,22 @@ extern "C" int tes_mma_arg_error_probe(const double* x, const double* w, const d
         TES_CASE(10)
 #undef TES_CASE
     }
+    TES_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tes_tc5_arg_error_probe(const double* x, const double* w, const double* b, int64_t d, int nt,
+                                       double* out_max, void* stream) {
+    if (!x || !w || !b) return -1;
+    if (d < 1 || d > 10) return -4;
+    if (nt < 1) return -5;
+    if (!out_max) return -6;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kc = tc5_kc((int)d);
+    const size_t smem = (size_t)kc * (128 + TC5_NF) * 16 + 64;
+    TES_CUDA_OK(cudaMemsetAsync(out_max, 0, sizeof(double), st));
+    TES_CUDA_OK(cudaFuncSetAttribute(tc5_arg_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc5_arg_probe_kernel<<<1, 128, smem, st>>>(x, w, b, (int)d, nt, out_max);
     TES_LAUNCH_OK();
     return 0;
 }
