@@ -1226,36 +1226,66 @@ __global__ void mma_arg_probe_kernel(const double* __restrict__ x, const double*
     if (lane == 0) *out = worst;
 }
 
-// exact fp64 re-evaluation (tes_spec.h sequence) of every kept (chunk, sample, slot) candidate
-__global__ void rff_refine_kernel(const double* __restrict__ cand, int d, const double* __restrict__ feat, int rec,
-                                  int64_t S, int64_t F, double scale, int64_t idx_offset, int64_t nslots_total,
-                                  int slot_stride, double* __restrict__ slot_val, int64_t* __restrict__ slot_idx,
-                                  const int* __restrict__ flags) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nslots_total) return;
-    const int64_t cs = t / SCR_CAP;  // chunk*S + j
-    const int c = (int)(t % SCR_CAP);
-    const int64_t o = cs * slot_stride + c;
-    const int64_t gi = slot_idx[o];
-    if (gi < 0) return;
-    if (flags[cs]) {
-        slot_idx[o] = -1;
-        slot_val[o] = neg_inf();
+// exact fp64 re-evaluation (tes_spec.h sequence) of every kept (chunk, sample, slot) candidate: one warp per
+// (chunk, sample); the 32 lanes evaluate cos(pi h_f) of 32 consecutive features in parallel, then every lane replays
+// the SEQUENTIAL accumulation acc = fma(theta_f, c_f, acc), f ascending, from a per-warp shared staging buffer -- the
+// same operation order as the fp64 kernel, hence the same bits.
+constexpr int REFINE_WARPS = 8;
+__global__ void __launch_bounds__(32 * REFINE_WARPS)
+    rff_refine_kernel(const double* __restrict__ cand, int d, const double* __restrict__ feat, int rec, int64_t S,
+                      int64_t F, double scale, int64_t idx_offset, int64_t npairs, int slot_stride,
+                      double* __restrict__ slot_val, int64_t* __restrict__ slot_idx, const int* __restrict__ flags) {
+    __shared__ double2 stage[REFINE_WARPS][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t cs = (int64_t)blockIdx.x * REFINE_WARPS + wib;  // chunk*S + j
+    if (cs >= npairs) return;
+    const int64_t o0 = cs * slot_stride;
+    if (flags[cs]) {  // overflowed: the fp64 kernel recomputes this (chunk, sample)
+        for (int c = lane; c < SCR_CAP; c += 32) {
+            slot_idx[o0 + c] = -1;
+            slot_val[o0 + c] = neg_inf();
+        }
         return;
     }
-    const int64_t j = cs % S;
-    const double* x = cand + (gi - idx_offset) * d;
-    const double* fj = feat + j * F * rec;
-    double xr[RFF_MAX_D_FAST];
-    for (int kk = 0; kk < d; ++kk) xr[kk] = __ldg(x + kk);
-    double acc = 0.0;
-    for (int64_t f = 0; f < F; ++f) {
-        const double* r = fj + f * rec;
-        double h = __ldg(r + d);
-        for (int kk = 0; kk < d; ++kk) h = fma(__ldg(r + kk), xr[kk], h);
-        acc = fma(__ldg(r + d + 1), cospi_spec(h), acc);
+    const double* fj = feat + (cs % S) * F * rec;
+    for (int c = 0; c < SCR_CAP; ++c) {
+        const int64_t gi = slot_idx[o0 + c];
+        if (gi < 0) continue;
+        const double* x = cand + (gi - idx_offset) * d;
+        double xr[RFF_MAX_D_FAST];
+#pragma unroll
+        for (int kk = 0; kk < RFF_MAX_D_FAST; ++kk) xr[kk] = kk < d ? __ldg(x + kk) : 0.0;
+        double acc = 0.0;
+        for (int64_t f0 = 0; f0 < F; f0 += 32) {
+            const int64_t f = f0 + lane;
+            double2 tc = make_double2(0.0, 0.0);
+            if (f < F) {
+                const double* r = fj + f * rec;
+                double h = __ldg(r + d);
+#pragma unroll
+                for (int kk = 0; kk < RFF_MAX_D_FAST; ++kk)
+                    if (kk < d) h = fma(__ldg(r + kk), xr[kk], h);
+                tc = make_double2(__ldg(r + d + 1), cospi_spec(h));
+            }
+            __syncwarp();
+            stage[wib][lane] = tc;
+            __syncwarp();
+            const int nb = (int)(F - f0 < 32 ? F - f0 : 32);
+            if (nb == 32) {
+#pragma unroll
+                for (int l = 0; l < 32; ++l) {
+                    const double2 v = stage[wib][l];
+                    acc = fma(v.x, v.y, acc);
+                }
+            } else {
+                for (int l = 0; l < nb; ++l) {
+                    const double2 v = stage[wib][l];
+                    acc = fma(v.x, v.y, acc);
+                }
+            }
+        }
+        if (lane == 0) slot_val[o0 + c] = __dmul_rn(scale, acc);
     }
-    slot_val[o] = __dmul_rn(scale, acc);
 }
 
 #include "rff_tc5.cuh"
@@ -1300,7 +1330,7 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
     const bool can_screen = d <= RFF_MAX_D_FAST && k <= SCR_MAX_K && N >= 1;
     p.screened = 0;
     if (can_screen && (method == 2 || method == 3 || method == 4 || (method == 0 && N >= SCR_MIN_N)))
-        p.screened = method == 4 ? 3 : ((method == 3 || (method == 0 && d >= 5)) ? 2 : 1);
+        p.screened = (method == 4 || (method == 0 && d >= 5)) ? 3 : (method == 3 ? 2 : 1);
     if (p.screened) {
         p.C = 4;
         p.threads = 256;
@@ -1574,10 +1604,9 @@ static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* 
             }
         }
         if (rc) return rc;
-        const int64_t nslots = p.nchunks * S * SCR_CAP;
-        rff_refine_kernel<<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>(cand, (int)d, feat, p.rec, S, F, scale,
-                                                                            idx_offset, nslots, p.slot_stride,
-                                                                            part_val, part_idx, flags);
+        const int64_t npairs = p.nchunks * S;
+        rff_refine_kernel<<<(unsigned)((npairs + REFINE_WARPS - 1) / REFINE_WARPS), 32 * REFINE_WARPS, 0, st>>>(
+            cand, (int)d, feat, p.rec, S, F, scale, idx_offset, npairs, p.slot_stride, part_val, part_idx, flags);
         TES_LAUNCH_OK();
         // flag-gated fp64 recomputation of overflowed (chunk, sample) units, one CTA each
         RffPlan fb = p;

@@ -29,7 +29,7 @@ constexpr int TC5_TILE = 128 * TC5_MT;      // candidates per CTA tile
 constexpr int TC5_NF = 64;                  // features per MMA tile = TMEM columns per candidate tile
 constexpr int TC5_NSTAGE = 8;               // B ring stages (power of two: cheap ring index)
 constexpr int TC5_MAX_KC = 8;               // K <= 32 (3d + 2 <= 32 <=> d <= 10)
-constexpr int TC5_NPOLY = 2;                // pairs of every 8 whose cosine runs on the FMA pipe
+constexpr int TC5_NPOLY = 1;                // pairs of every 8 whose cosine runs on the FMA pipe
 
 __host__ __device__ constexpr int tc5_kc(int d) { return (((3 * d + 2 + 3) / 4) + 1) & ~1; }  // 16-byte K chunks, even
 __host__ __device__ constexpr int tc5_stage_floats(int kc) { return kc * TC5_NF * 4 + TC5_NF; }
