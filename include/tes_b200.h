@@ -175,6 +175,59 @@ int tes_sp_acq_f64(const double* x, int64_t nx, int q, int64_t d, const double* 
  * point returns exactly that closed form. */
 int tes_batch_ep_acq_f64(const double* p, int64_t Sp, int64_t nx, double* out_acq, void* stream);
 
+/* ===================================================================================== Stage C
+ * Trusted-maximizer statistics on the device.  The reference does all of this in host numpy
+ * (utils.get_testidxs_stats, utils.py:1733-1833); here it stays next to the data so that one
+ * acquisition step has no host round trip of samples or (T,T,T) covariance stacks.
+ */
+
+/* Counter-based N(0,1) draws of include/tes_spec.h (Philox4x32-10 + Box-Muller), elements
+ * first_elem .. first_elem+count-1 of the logical draw tensor (seed, iteration, stream_id).  Replaces the
+ * np.random.normal call of utils.py:1674 when the caller passes a seed instead of the draws themselves. */
+int tes_normal_fill_f64(uint64_t seed, uint32_t iteration, uint32_t stream_id, uint64_t first_elem,
+                        int64_t count, double* out, void* stream);
+
+/* utils.remove_duplicates_np / its mask (utils.py:1554-1581): walking the rows of xs (S, d) in order, every
+ * not-yet-flagged row flags all LATER rows whose Euclidean distance is <= resolution.  The distance is evaluated in
+ * numpy's operation order (pairwise np.sum of the squared differences, then sqrt), so the keep/drop decisions are
+ * bit-identical.  mask (S) int32: 1 = duplicate; leader (S) int64: the row that flagged it (itself if kept).
+ * S <= 49152, d <= 128. */
+int tes_dedup_f64(const double* xs, int64_t S, int64_t d, double resolution, int* mask, int64_t* leader,
+                  void* stream);
+
+/* Batched symmetric eigen-decomposition A_b = V_b diag(e_b) V_b^T (one-sided Jacobi, one CTA per matrix; matrices
+ * up to n = 160 stay in shared memory).  Replaces np.linalg.eig on the symmetric matrices of utils.py:1668
+ * (colouring factor of the joint samples) and optfunc.py:355 (n x n feature Gram of the RFF posterior draw).
+ * A (batch, n, n); evals (batch, n) in the solver's own (deterministic) order; evecs (batch, n, n) row-major with
+ * the eigenvectors as COLUMNS (numpy's convention); sweeps (batch) int32 or NULL. */
+int64_t tes_sym_eig_workspace_bytes(int64_t batch, int64_t n);
+int tes_sym_eig_f64(const double* A, int64_t batch, int64_t n, double* evals, double* evecs, int* sweeps, void* ws,
+                    int64_t ws_bytes, void* stream);
+
+/* out = V diag(sqrt(clip(e, 0, inf)))  (utils.py:1668-1670), (n, n) row-major */
+int tes_color_factor_f64(const double* evals, const double* evecs, int64_t n, double* out, void* stream);
+
+/* Core of utils.sample_multivariate_normal_maxidx_np (utils.py:1675-1705) on joint samples (ns, T) that already
+ * hold z A^T: adds mean(prior_mean) to every entry (reference quirk Q11; skipped when prior_mean is NULL), flags the
+ * correlated dimensions (np.corrcoef > 1 - 1e-6 against an earlier dimension) when remove_correlated != 0, takes
+ * the arg-max of every row over the unflagged dimensions (first maximum wins) and counts the buckets.
+ * masked (T) int32, maxidx (ns) int64, counts (T) int32. */
+int64_t tes_joint_maxidx_workspace_bytes(int64_t ns, int64_t T);
+int tes_joint_maxidx_f64(double* samples, int64_t ns, int64_t T, const double* prior_mean, int remove_correlated,
+                         int* masked, int64_t* maxidx, int* counts, void* ws, int64_t ws_bytes, void* stream);
+
+/* empirical_approximation.get_empirical_stat_from_samples (empirical_approximation.py:86-107) for every bucket at
+ * once: order (ns) = sample rows sorted stably by bucket, starts (nb+1) = bucket boundaries in `order`, cols (nk) =
+ * kept test-point columns.  mean (nb, nk); cov (nb, nk, nk) with the (n_j - 1) denominator. */
+int tes_bucket_moments_f64(const double* samples, int64_t ns, int64_t T, const int64_t* order, const int64_t* starts,
+                           int64_t nb, const int64_t* cols, int64_t nk, double* mean, double* cov, void* stream);
+
+/* Padded per-maximizer sample tensor of mode 'sample' (utils.py:1716-1727): out (nb, nk, K) holds the bucket's
+ * samples in draw order and the PRIOR mean in the padded slots; mask (nb, K) bytes. */
+int tes_bucket_samples_f64(const double* samples, int64_t ns, int64_t T, const int64_t* order, const int64_t* starts,
+                           int64_t nb, const int64_t* cols, int64_t nk, int64_t K, const double* prior_mean,
+                           double* out, uint8_t* mask, void* stream);
+
 /* ============================================================================== measurement aids
  * Sustained fp64 FMA rate of the device, used as the roofline denominator for the fp64-pipe-bound
  * kernels (MEASURED_PEAKS.json carries only HBM and bf16 numbers).  Runs `iters` dependent-chain

@@ -59,5 +59,6 @@
 #define TES_STREAM_SP_Y 2u    /* evaluate_sample_mp.py:268     z[it][iy][j][x][s]         */
 #define TES_STREAM_BSP_Y 3u   /* evaluate_batch_sample_mp.py:315  z[it][iy][j][x][s][q]   */
 #define TES_STREAM_BEP_Y 4u   /* evaluate_batch_mp.py:294      z[it][iy][j][x][q]         */
+#define TES_STREAM_JOINT_Z 5u /* utils.py:1674 joint samples  z[hyp = iteration][sample][t]   */
 
 #endif /* TES_SPEC_H */

@@ -36,7 +36,8 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
     mean_t, cov_t = onp.compute_mean_var_f(test_xs, X, Y, ls[0], sigma, sigma0, invK[0], fullcov=True)
     T0 = test_xs.shape[0]
     if z_joint is None:
-        z_joint = np.random.RandomState(seed).normal(size=(1, ntestsample, T0, 1))
+        # include/tes_spec.h: counter-based draws, stream TES_STREAM_JOINT_Z = 5, iteration = hyper-parameter index
+        z_joint = co.normals(seed, 0, 5, 0, ntestsample * T0).reshape(1, ntestsample, T0, 1)
     st_mode = "sample" if criterion == "sftl" else mode
     test_k, max_probs, mean_k, cov_k, v0, v1 = onp.get_testidxs_stats(
         1, test_xs, mean_t.reshape(1, T0), cov_t.reshape(1, T0, T0), mode=st_mode, nsample=ntestsample,

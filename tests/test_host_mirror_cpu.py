@@ -9,7 +9,7 @@ import pytest
 def test_get_testidxs_stats_matches_reference(golden, tag, mode):
     from tes_b200 import utils
     g = golden("maximizer_stats")
-    out = utils.get_testidxs_stats(1, g[tag + "_test_xs"].copy(), g[tag + "_mean"].copy(), g[tag + "_cov"].copy(),
+    out = utils.get_testidxs_stats_host(1, g[tag + "_test_xs"].copy(), g[tag + "_mean"].copy(), g[tag + "_cov"].copy(),
                                    mode=mode, nsample=int(g[tag + "_nsample"]), n_min_sample=2, z=g[tag + "_z"])
     for i, o in enumerate(out):
         ref = g["%s_%s_out%d" % (tag, mode, i)]
@@ -24,7 +24,7 @@ def test_get_testidxs_stats_uses_global_rng_like_the_reference(golden):
     from tes_b200 import utils
     g = golden("maximizer_stats")
     np.random.seed(42)  # the fixture was generated with np.random.seed(42) before the reference call
-    out = utils.get_testidxs_stats(1, g["t6_test_xs"].copy(), g["t6_mean"].copy(), g["t6_cov"].copy(),
+    out = utils.get_testidxs_stats_host(1, g["t6_test_xs"].copy(), g["t6_mean"].copy(), g["t6_cov"].copy(),
                                    mode="sample", nsample=int(g["t6_nsample"]), n_min_sample=2)
     np.testing.assert_allclose(out[4], g["t6_sample_out4"], rtol=1e-11, atol=1e-12)
 
@@ -39,7 +39,7 @@ def test_ep_mirror(golden, tag):
         np.testing.assert_allclose(m.squeeze(), g[tag + "_ep_mean"][j], rtol=1e-9, atol=1e-11)
         np.testing.assert_allclose(c, g[tag + "_ep_cov"][j], rtol=1e-9, atol=1e-11)
     # mode='ep' end to end (the call utils.py:1820-1825 intends)
-    out = utils.get_testidxs_stats(1, g[tag + "_test_xs"].copy(), g[tag + "_mean"].copy(), g[tag + "_cov"].copy(),
+    out = utils.get_testidxs_stats_host(1, g[tag + "_test_xs"].copy(), g[tag + "_mean"].copy(), g[tag + "_cov"].copy(),
                                    mode="ep", nsample=int(g[tag + "_nsample"]), n_min_sample=2, z=g[tag + "_z"])
     np.testing.assert_allclose(out[4][0], g[tag + "_ep_mean"], rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(out[5][0], g[tag + "_ep_cov"], rtol=1e-9, atol=1e-11)

@@ -79,7 +79,7 @@ def test_c1_branin_tes_sp_subset(golden):
     from oracle import c_oracle as co
     ridx, rval = co.rff_topk(cand, W, b, theta, sigma, 1)
     assert np.array_equal(idx.cpu().numpy(), ridx)
-    test_xs = acquisition.select_test_points(pts[:, 0], 1e-3)
+    test_xs = acquisition.select_test_points(pts[:, 0], 1e-3).cpu().numpy()
     np.testing.assert_array_equal(test_xs, pipeline_np.select_test_points(cand[ridx[:, 0]], 1e-3))
     ls, sg, s0 = l.reshape(1, 2), np.array([sigma]), np.array([sigma0])
     invK = onp.precomputeInvKs(ls, sg, s0, X)

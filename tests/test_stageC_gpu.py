@@ -1,0 +1,169 @@
+"""Stage C on the device (csrc/maxstats.cu) against the numpy oracle and the reference's own outputs
+(tests/golden/maximizer_stats.npz).  Calls go through the C ABI (tes_b200.ops / utils)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle import tes_oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+
+def test_normal_fill_matches_the_c_oracle():
+    from tes_b200 import ops
+    for first, count in [(0, 1001), (7, 4096), (12345, 2)]:
+        got = ops.normal_fill(99, 3, ops.STREAM_JOINT_Z, count, first_elem=first).cpu().numpy()
+        ref = c_oracle.normals(99, 3, 5, first, count)
+        # log/sin/cos come from the platform libm on each side (tes_spec.h): ~1 ulp, not bit-exact
+        np.testing.assert_allclose(got, ref, rtol=0, atol=5e-15)
+    z = ops.normal_fill(1, 0, ops.STREAM_JOINT_Z, 1 << 20).cpu().numpy()
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1.0) < 5e-3
+
+
+@pytest.mark.parametrize("d", [1, 2, 6, 8, 10, 19])
+def test_dedup_is_identical_to_the_reference_walk(d):
+    from tes_b200 import acquisition, ops
+    rs = np.random.RandomState(d)
+    centers = rs.rand(40, d)
+    xs = centers[rs.randint(0, 40, size=700)] + rs.randn(700, d) * 4e-4   # many pairs near the 1e-3 threshold
+    mask, leader = ops.dedup(xs, 1e-3)
+    ref_mask = onp.get_duplicate_mask(xs, 1e-3)
+    np.testing.assert_array_equal(mask.cpu().numpy(), ref_mask.astype(np.int32))
+    np.testing.assert_array_equal(acquisition.select_test_points(xs, 1e-3), onp.remove_duplicates(xs, 1e-3))
+    lead = leader.cpu().numpy()
+    assert np.all(lead[ref_mask == 0] == np.where(ref_mask == 0)[0]) and np.all(lead[ref_mask == 1] < np.where(ref_mask == 1)[0])
+
+
+def test_dedup_golden(golden):
+    from tes_b200 import acquisition
+    g = golden("maximizer_stats")
+    np.testing.assert_array_equal(acquisition.select_test_points(g["dedup_in"].copy(), 1e-3), g["dedup_out"])
+
+
+def test_select_test_points_t_max_matches_oracle_pipeline():
+    from oracle import pipeline_np
+    from tes_b200 import acquisition
+    rs = np.random.RandomState(5)
+    centers = rs.rand(30, 3)
+    xs = centers[rs.randint(0, 30, size=400)]
+    for t_max in (None, 5, 12, 64):
+        np.testing.assert_array_equal(acquisition.select_test_points(xs, 1e-3, t_max),
+                                      pipeline_np.select_test_points(xs, 1e-3, t_max))
+
+
+@pytest.mark.parametrize("n,batch", [(1, 3), (2, 5), (7, 4), (64, 9), (125, 2), (160, 1), (200, 2)])
+def test_sym_eig(n, batch):
+    from tes_b200 import ops
+    rs = np.random.RandomState(n)
+    Z = rs.randn(batch, n, max(n // 2, 1) if n > 100 else 3 * n)   # n > 100: rank-deficient PSD (zero eigenvalues)
+    A = Z @ np.transpose(Z, (0, 2, 1)) + (0.0 if n > 100 else 1e-4) * np.eye(n)
+    e, v, sweeps = ops.sym_eig(A, return_sweeps=True)
+    e, v = e.cpu().numpy(), v.cpu().numpy()
+    assert int(sweeps.max()) < 40
+    scale = np.abs(np.linalg.eigvalsh(A)).max(axis=1)
+    for b in range(batch):
+        np.testing.assert_allclose(np.sort(e[b]), np.linalg.eigvalsh(A[b]), rtol=0, atol=1e-12 * scale[b])
+        rec = (v[b] * e[b]) @ v[b].T
+        np.testing.assert_allclose(rec, A[b], rtol=0, atol=2e-12 * scale[b])
+        keep = np.abs(e[b]) > 1e-9 * scale[b]                          # null-space columns need not be normalised
+        vv = v[b][:, keep]
+        np.testing.assert_allclose(vv.T @ vv, np.eye(keep.sum()), rtol=0, atol=1e-11)
+
+
+def test_color_factor_reproduces_the_covariance():
+    from tes_b200 import ops
+    rs = np.random.RandomState(0)
+    X = rs.rand(40, 3)
+    cov = onp.computeKmm(X, np.array([30.0, 20.0, 10.0]), 1.3) if hasattr(onp, "computeKmm") else None
+    if cov is None:
+        Z = rs.randn(40, 60)
+        cov = Z @ Z.T
+    A = ops.color_factor(cov).cpu().numpy()
+    np.testing.assert_allclose(A @ A.T, cov, rtol=0, atol=1e-12 * np.abs(cov).max())
+
+
+@pytest.mark.parametrize("tag", ["t6", "t12"])
+@pytest.mark.parametrize("mode", ["sample", "empirical", "ep"])
+def test_device_get_testidxs_stats_matches_the_reference_outputs(golden, tag, mode):
+    """Same z and the same colouring factor (np.linalg.eig of the same matrix, as the reference computes it) ->
+    the reference's own outputs."""
+    from tes_b200 import utils
+    g = golden("maximizer_stats")
+    cov = g[tag + "_cov"].copy()
+    A = utils.mvn_transform_matrix(cov[0])
+    out = utils.get_testidxs_stats(1, g[tag + "_test_xs"].copy(), g[tag + "_mean"].copy(), cov, mode=mode,
+                                   nsample=int(g[tag + "_nsample"]), n_min_sample=2, z=g[tag + "_z"], transforms=[A])
+    if mode == "ep":
+        np.testing.assert_allclose(out[4][0], g[tag + "_ep_mean"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(out[5][0], g[tag + "_ep_cov"], rtol=1e-9, atol=1e-11)
+        return
+    for i, o in enumerate(out):
+        ref = g["%s_%s_out%d" % (tag, mode, i)]
+        assert isinstance(o, np.ndarray) and o.shape == ref.shape
+        if ref.dtype == bool:
+            np.testing.assert_array_equal(o, ref)
+        else:
+            np.testing.assert_allclose(o, ref, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("mode", ["sample", "empirical"])
+@pytest.mark.parametrize("T,nsample,nhyp", [(5, 200, 1), (33, 3000, 1), (128, 8192, 1), (9, 500, 3)])
+def test_device_get_testidxs_stats_vs_oracle(mode, T, nsample, nhyp):
+    """Random GP posteriors with near-duplicate test points (exercises the correlated-dimension mask), several
+    hyper-parameter samples (exercises the pruning across them)."""
+    from tes_b200 import utils
+    rs = np.random.RandomState(T)
+    d = 3
+    test_xs = rs.rand(T, d)
+    if T > 6:
+        test_xs[5] = test_xs[2] + 1e-7            # correlation ~ 1: dimension 5 is suppressed
+    X, Y = rs.rand(12, d), rs.randn(12, 1)
+    means, covs, trs = [], [], []
+    for i in range(nhyp):
+        l = np.array([20.0, 9.0, 14.0]) * (1.0 + 0.3 * i)
+        ls, sg, s0 = l.reshape(1, d), np.array([1.1]), np.array([1e-3])
+        invK = onp.precomputeInvKs(ls, sg, s0, X)
+        m, c = onp.compute_mean_var_f(test_xs, X, Y, l, 1.1, 1e-3, invK[0], fullcov=True)
+        means.append(m.reshape(T))
+        covs.append(c)
+        trs.append(utils.mvn_transform_matrix(c))
+    means, covs = np.stack(means), np.stack(covs)
+    z = rs.normal(size=(nhyp, nsample, T, 1))
+    ref = onp.get_testidxs_stats(nhyp, test_xs.copy(), means.copy(), covs.copy(), mode=mode, nsample=nsample,
+                                 n_min_sample=2, z=z, transforms=trs)
+    out = utils.get_testidxs_stats(nhyp, test_xs.copy(), means.copy(), covs.copy(), mode=mode, nsample=nsample,
+                                   n_min_sample=2, z=z, transforms=trs)
+    assert len(ref) == len(out)
+    for o, r in zip(out, ref):
+        r = np.asarray(r)
+        assert o.shape == r.shape
+        if r.dtype == bool:
+            np.testing.assert_array_equal(o, r)
+        else:
+            np.testing.assert_allclose(o, r, rtol=1e-9, atol=1e-11)
+    # CUDA tensors in -> CUDA tensors out, same values
+    out_t = utils.get_testidxs_stats(nhyp, torch.from_numpy(test_xs).cuda(), torch.from_numpy(means).cuda(),
+                                     torch.from_numpy(covs).cuda(), mode=mode, nsample=nsample, n_min_sample=2, z=z,
+                                     transforms=trs)
+    for o, t in zip(out, out_t):
+        assert t.is_cuda
+        np.testing.assert_array_equal(o, t.cpu().numpy())
+
+
+def test_device_joint_samples_with_own_colouring_factor_have_the_right_law():
+    """Without `transforms` the factor comes from the device eigen-solver: same distribution, not the same draws
+    as LAPACK's eig; check the bucket probabilities against the host path statistically."""
+    from tes_b200 import utils
+    rs = np.random.RandomState(1)
+    T, d = 8, 2
+    test_xs, X, Y = rs.rand(T, d), rs.rand(6, d), rs.randn(6, 1)
+    l = np.array([12.0, 7.0])
+    invK = onp.precomputeInvKs(l.reshape(1, d), np.array([1.0]), np.array([1e-3]), X)
+    m, c = onp.compute_mean_var_f(test_xs, X, Y, l, 1.0, 1e-3, invK[0], fullcov=True)
+    a = utils.get_testidxs_stats(1, test_xs, m.reshape(1, T), c[None], mode="empirical", nsample=200000, seed=4)
+    b = utils.get_testidxs_stats_host(1, test_xs, m.reshape(1, T), c[None], mode="empirical", nsample=200000,
+                                      z=rs.normal(size=(1, 200000, T, 1)))
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_allclose(a[1], b[1], atol=6e-3)
+    np.testing.assert_allclose(a[4], b[4], atol=3e-2)

@@ -68,6 +68,16 @@ SIGNATURES = {
                                c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_u64, c_i64, c_i64,
                                c_ptr, c_ptr, c_i64, c_ptr]),
     "tes_batch_ep_acq_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
+    "tes_normal_fill_f64": (c_int, [c_u64, ctypes.c_uint32, ctypes.c_uint32, c_u64, c_i64, c_ptr, c_ptr]),
+    "tes_dedup_f64": (c_int, [c_ptr, c_i64, c_i64, c_dbl, c_ptr, c_ptr, c_ptr]),
+    "tes_sym_eig_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "tes_sym_eig_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "tes_color_factor_f64": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "tes_joint_maxidx_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "tes_joint_maxidx_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "tes_bucket_moments_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    "tes_bucket_samples_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr,
+                                       c_ptr, c_ptr]),
     "tes_cosf_error_probe": (c_int, [ctypes.c_float, ctypes.c_float, c_dbl, c_int, c_ptr, c_ptr]),
     "tes_mma_arg_error_probe": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr]),
     "tes_tc5_arg_error_probe": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr]),

@@ -116,15 +116,18 @@ def trusted_maximizers(cand, W, b, theta, sigma, shard=None, k=1, timers=None):
 
 def select_test_points(max_xs, resolution=1e-3, t_max=None):
     """De-duplicate the maximizers at `resolution` (bo.py:830-836, bo_discrete.py:553) keeping first
-    occurrences; optionally keep only the `t_max` most frequent ones (ties -> earlier), in original order."""
-    xs = max_xs.cpu().numpy() if torch.is_tensor(max_xs) else np.asarray(max_xs)
-    mask, leader = utils.get_duplicate_mask_np(xs, resolution, return_leader=True)
-    keep = np.nonzero(mask == 0.0)[0]
-    if t_max is not None and keep.size > t_max:
-        counts = np.bincount(leader, minlength=xs.shape[0])[keep]
-        order = np.lexsort((np.arange(keep.size), -counts))[:t_max]
-        keep = keep[np.sort(order)]
-    return xs[keep]
+    occurrences; optionally keep only the `t_max` most frequent ones (ties -> earlier), in original order.
+    Runs on the device (tes_dedup_f64: same distance arithmetic as numpy => same decisions); numpy in ->
+    numpy out, CUDA tensor in -> CUDA tensor out."""
+    xs = dev(max_xs)
+    mask, leader = ops.dedup(xs, resolution)
+    keep = torch.nonzero(mask == 0).reshape(-1)
+    if t_max is not None and keep.numel() > t_max:
+        counts = torch.bincount(leader, minlength=xs.shape[0])[keep]
+        order = torch.argsort(-counts, stable=True)[:t_max]      # most frequent first, ties -> earlier row
+        keep = keep[torch.sort(order).values]
+    out = xs[keep]
+    return out if torch.is_tensor(max_xs) else out.cpu().numpy()
 
 
 def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="empirical", deterministic=True,
@@ -141,26 +144,24 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
     ls, sigmas, sigma0s = np.asarray(l, dtype=np.float64).reshape(1, d), np.array([sigma]), np.array([sigma0])
     # ---- A
     idx, val, pts = trusted_maximizers(cand, W, b, theta, sigma, shard, k=1, timers=timers)
-    test_xs = select_test_points(pts[:, 0], duplicate_resolution, t_max)
+    test_xs = select_test_points(pts[:, 0], duplicate_resolution, t_max)   # CUDA tensor
     out = {"n_unique_maximizers": int(test_xs.shape[0]), "argmax_idx": idx[:, 0], "argmax_val": val[:, 0]}
     if test_xs.shape[0] == 1:  # bo_discrete.py:557-559: a single maximizer is queried directly
-        out.update(query_x=test_xs[0], query_idx=int(idx[0, 0]), query_val=float("nan"), T=1, Sp=1)
+        out.update(query_x=test_xs[0].cpu().numpy(), query_idx=int(idx[0, 0]), query_val=float("nan"), T=1, Sp=1)
         return out
     # ---- B
     invK = utils.precomputeInvKs(d, 1, ls, sigmas, sigma0s, Xd)
     mean_t, cov_t = utils.compute_mean_var_f(dev(test_xs), Xd, Yd, ls[0], sigma, sigma0, invK[0], fullcov=True)
-    # ---- C (host, replicated on every rank with identical draws)
+    # ---- C (device, replicated on every rank with identical draws; only the bucket counts visit the host)
     T0 = test_xs.shape[0]
-    if z_joint is None:
-        z_joint = np.random.RandomState(seed).normal(size=(1, ntestsample, T0, 1))
     st_mode = "sample" if criterion == "sftl" else mode
     test_k, max_probs, mean_k, cov_k, v0, v1 = utils.get_testidxs_stats(
-        1, test_xs, mean_t.reshape(1, T0).cpu().numpy(), cov_t.reshape(1, T0, T0).cpu().numpy(), mode=st_mode,
-        nsample=ntestsample, n_min_sample=n_min_sample, z=z_joint,
-        transforms=None if transform is None else [transform])
+        1, test_xs, mean_t.reshape(1, T0), cov_t.reshape(1, T0, T0), mode=st_mode, nsample=ntestsample,
+        n_min_sample=n_min_sample, z=z_joint, transforms=None if transform is None else [transform],
+        seed=None if z_joint is not None else seed)
     out.update(T=int(test_k.shape[0]), Sp=int((max_probs[0] > 0).sum()))
     if test_k.shape[0] == 1:
-        out.update(query_x=test_k[0], query_idx=-1, query_val=float("nan"))
+        out.update(query_x=test_k[0].cpu().numpy(), query_idx=-1, query_val=float("nan"))
         return out
     _, invpNK = evaluate_mp.get_pNK_test_obs(ls, sigmas, sigma0s, 1, Xd, dev(test_k))
     # ---- D

@@ -29,6 +29,9 @@ constexpr int TC5_TILE = 128 * TC5_MT;      // candidates per CTA tile
 constexpr int TC5_NF = 64;                  // features per MMA tile = TMEM columns per candidate tile
 constexpr int TC5_NSTAGE = 8;               // B ring stages (power of two: cheap ring index)
 constexpr int TC5_MAX_KC = 8;               // K <= 32 (3d + 2 <= 32 <=> d <= 10)
+#ifndef TC5_SLEEP_NS
+#define TC5_SLEEP_NS 64
+#endif
 constexpr int TC5_NPOLY = 1;                // pairs of every 8 whose cosine runs on the FMA pipe
 
 __host__ __device__ constexpr int tc5_kc(int d) { return (((3 * d + 2 + 3) / 4) + 1) & ~1; }  // 16-byte K chunks, even
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1)
                     const float* src = featt + (int64_t)(j0 + jj) * nft * stage_floats;
                     for (int ft = 0; ft < nft; ++ft, ++it) {
                         const uint32_t s = it % TC5_NSTAGE, ph = (it / TC5_NSTAGE) & 1u;
-                        mbar_wait(&empty_b[s], ph ^ 1u);
+                        mbar_wait_relaxed(&empty_b[s], ph ^ 1u, TC5_SLEEP_NS);
                         mbar_expect_tx(&full_b[s], stage_bytes);
                         bulk_g2s(sB + s * stage_floats, src + (int64_t)ft * stage_floats, stage_bytes, &full_b[s]);
                     }
@@ -331,14 +334,14 @@ __global__ void __launch_bounds__(TC5_THREADS, 1)
             const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
             uint32_t it = 0;
             for (int tile = 0; tile < ntiles; ++tile) {
-                mbar_wait(a_ready, (uint32_t)tile & 1u);
+                mbar_wait_relaxed(a_ready, (uint32_t)tile & 1u, TC5_SLEEP_NS);
                 tc5_fence_after();
                 for (int jj = 0; jj < nj; ++jj)
                     for (int ft = 0; ft < nft; ++ft, ++it) {
                         const uint32_t s = it % TC5_NSTAGE, ph = (it / TC5_NSTAGE) & 1u;
                         const uint32_t a = it & 1u, pa = (it >> 1) & 1u;
-                        mbar_wait(&full_b[s], ph);
-                        mbar_wait(&tmem_empty[a], pa ^ 1u);
+                        mbar_wait_relaxed(&full_b[s], ph, TC5_SLEEP_NS);
+                        mbar_wait_relaxed(&tmem_empty[a], pa ^ 1u, TC5_SLEEP_NS);
                         tc5_fence_after();
 #pragma unroll
                         for (int mt = 0; mt < TC5_MT; ++mt)
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1)
         for (int tile = 0; tile < ntiles; ++tile)
             for (int jj = 0; jj < nj; ++jj, ++sidx) {
                 const uint32_t ub = sidx & 1u, up = (sidx >> 1) & 1u;
-                mbar_wait(&u_full[ub], up);
+                mbar_wait_relaxed(&u_full[ub], up, TC5_SLEEP_NS);
                 screen_commit_warp(cx, jj, ubuf + ub * TC5_TILE, c0 + (int64_t)tile * TC5_TILE, lane);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&u_empty[ub]);

@@ -108,6 +108,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// same wait for service warps that have slack (producer / MMA issuer / commit): back off with nanosleep instead of
+// spinning so that they do not take issue slots from the compute warps of their scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns) {
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(ns);
+    }
+}
 // global -> shared bulk copy, completion counted in bytes on `bar`.  16-byte aligned, size % 16 == 0.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -325,3 +325,105 @@ def argmax(vals):
     rc = L.tes_argmax_f64(ptr(v), v.numel(), ptr(ov), ptr(oi), ptr(ws), ws.numel(), stream_ptr())
     _lib.check(rc, "tes_argmax_f64")
     return oi, ov
+
+
+# ------------------------------------------------------------------------------------- stage C
+STREAM_JOINT_Z = 5  # include/tes_spec.h TES_STREAM_JOINT_Z
+
+
+def normal_fill(seed, iteration, stream_id, count, first_elem=0, device=None):
+    """Counter-based N(0,1) draws of include/tes_spec.h -> (count,) CUDA tensor."""
+    out = torch.empty((int(count),), dtype=torch.float64,
+                      device=device or torch.device("cuda", torch.cuda.current_device()))
+    rc = _lib.lib().tes_normal_fill_f64(int(seed), int(iteration), int(stream_id), int(first_elem), int(count),
+                                        ptr(out), stream_ptr())
+    _lib.check(rc, "tes_normal_fill_f64")
+    return out
+
+
+def dedup(xs, resolution):
+    """utils.py:1554-1573 -> (mask (S,) int32 with 1 = duplicate, leader (S,) int64)."""
+    xs = dev(xs)
+    S, d = xs.shape
+    mask = torch.empty((S,), dtype=torch.int32, device=xs.device)
+    leader = torch.empty((S,), dtype=torch.int64, device=xs.device)
+    rc = _lib.lib().tes_dedup_f64(ptr(xs), S, d, float(resolution), ptr(mask), ptr(leader), stream_ptr())
+    _lib.check(rc, "tes_dedup_f64")
+    return mask, leader
+
+
+def sym_eig(A, return_sweeps=False):
+    """Batched symmetric eigen-decomposition (one-sided Jacobi): A (batch,n,n) or (n,n) -> evals (..,n),
+    evecs (..,n,n) with eigenvectors as columns."""
+    A = dev(A)
+    single = A.dim() == 2
+    A3 = A.reshape(-1, A.shape[-2], A.shape[-1])
+    batch, n, n2 = A3.shape
+    if n != n2:
+        raise ValueError("matrices must be square")
+    L = _lib.lib()
+    need = L.tes_sym_eig_workspace_bytes(batch, n)
+    if need < 0:
+        raise ValueError("invalid sizes for tes_sym_eig_f64: batch=%d n=%d" % (batch, n))
+    ws = WORKSPACE.get(need, A.device)
+    evals = torch.empty((batch, n), dtype=torch.float64, device=A.device)
+    evecs = torch.empty((batch, n, n), dtype=torch.float64, device=A.device)
+    sweeps = torch.empty((batch,), dtype=torch.int32, device=A.device)
+    rc = L.tes_sym_eig_f64(ptr(A3), batch, n, ptr(evals), ptr(evecs), ptr(sweeps), ptr(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_sym_eig_f64")
+    if single:
+        evals, evecs = evals[0], evecs[0]
+    return (evals, evecs, sweeps) if return_sweeps else (evals, evecs)
+
+
+def color_factor(cov):
+    """utils.py:1668-1670: A = V diag(sqrt(clip(e, 0))) of a symmetric (n,n) covariance, on the device."""
+    cov = dev(cov)
+    n = cov.shape[0]
+    e, v = sym_eig(cov)
+    out = torch.empty((n, n), dtype=torch.float64, device=cov.device)
+    rc = _lib.lib().tes_color_factor_f64(ptr(e), ptr(v), n, ptr(out), stream_ptr())
+    _lib.check(rc, "tes_color_factor_f64")
+    return out
+
+
+def joint_maxidx(samples, prior_mean=None, remove_correlated=True):
+    """utils.py:1675-1705 on samples (ns,T) = z A^T (modified in place: + mean(prior_mean)).
+    -> masked (T,) int32, maxidx (ns,) int64, counts (T,) int32."""
+    ns, T = samples.shape
+    dv = samples.device
+    L = _lib.lib()
+    ws = WORKSPACE.get(L.tes_joint_maxidx_workspace_bytes(ns, T), dv)
+    masked = torch.empty((T,), dtype=torch.int32, device=dv)
+    maxidx = torch.empty((ns,), dtype=torch.int64, device=dv)
+    counts = torch.empty((T,), dtype=torch.int32, device=dv)
+    pm = None if prior_mean is None else dev(prior_mean, dv).reshape(-1)
+    rc = L.tes_joint_maxidx_f64(ptr(samples), ns, T, ptr(pm), int(bool(remove_correlated)), ptr(masked), ptr(maxidx),
+                                ptr(counts), ptr(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_joint_maxidx_f64")
+    return masked, maxidx, counts
+
+
+def bucket_moments(samples, order, starts, cols):
+    """empirical_approximation.py:86-107 for every bucket -> mean (nb,nk), cov (nb,nk,nk)."""
+    ns, T = samples.shape
+    nb, nk = starts.numel() - 1, cols.numel()
+    mean = torch.empty((nb, nk), dtype=torch.float64, device=samples.device)
+    cov = torch.empty((nb, nk, nk), dtype=torch.float64, device=samples.device)
+    rc = _lib.lib().tes_bucket_moments_f64(ptr(samples), ns, T, ptr(order), ptr(starts), nb, ptr(cols), nk, ptr(mean),
+                                           ptr(cov), stream_ptr())
+    _lib.check(rc, "tes_bucket_moments_f64")
+    return mean, cov
+
+
+def bucket_samples(samples, order, starts, cols, K, prior_mean):
+    """utils.py:1716-1727 -> post_samples (nb,nk,K), mask (nb,K) bool."""
+    ns, T = samples.shape
+    nb, nk = starts.numel() - 1, cols.numel()
+    out = torch.empty((nb, nk, K), dtype=torch.float64, device=samples.device)
+    mask = torch.empty((nb, K), dtype=torch.uint8, device=samples.device)
+    rc = _lib.lib().tes_bucket_samples_f64(ptr(samples), ns, T, ptr(order), ptr(starts), nb, ptr(cols), nk, int(K),
+                                           ptr(dev(prior_mean, samples.device).reshape(-1)), ptr(out), ptr(mask),
+                                           stream_ptr())
+    _lib.check(rc, "tes_bucket_samples_f64")
+    return out, mask.bool()

@@ -207,9 +207,12 @@ def sample_multivariate_normal_maxidx_np(mean, cov, nsample, n_min_sample=1, get
     return nmax, unique, K, ret, masks, sizes
 
 
-def get_testidxs_stats(nhyp, test_xs_np, test_means, test_covs, mode="sample", nsample=1000, n_min_sample=2,
-                       z=None, transforms=None):
-    """utils.py:1733-1833.  mode in {'sample','empirical','ep'}; `z` (nhyp, nsample, ntest, 1) optional.
+def get_testidxs_stats_host(nhyp, test_xs_np, test_means, test_covs, mode="sample", nsample=1000, n_min_sample=2,
+                            z=None, transforms=None):
+    """Host-numpy restatement of utils.py:1733-1833 (where the reference runs it).  Kept for mode='ep' (whose
+    EP sweeps are host code here as in the reference) and as the numpy-level mirror; the default entry point
+    `get_testidxs_stats` below runs modes 'sample' and 'empirical' on the device.
+    mode in {'sample','empirical','ep'}; `z` (nhyp, nsample, ntest, 1) optional.
     mode='ep' runs the EP the reference intends at :1820-1825 (its shipped code raises NameError).
     The padded (nhyp, ntest, ntest, K) sample tensor is only materialised for mode='sample'; the empirical
     moments are taken straight from the buckets (zero-weight padding contributes nothing)."""
@@ -266,3 +269,95 @@ def get_testidxs_stats(nhyp, test_xs_np, test_means, test_covs, mode="sample", n
                 pm[i, j] = m.squeeze()
                 pc[i, j] = c
     return test_xs_np, max_probs, test_means, test_covs, pm, pc
+
+
+def _device_buckets(mean, cov, nsample, z, transform, seed, hyp_index):
+    """utils.py:1668-1705 on the device: colouring factor (Jacobi eigen-solver unless `transform` is given),
+    joint samples z A^T + mean(mean) (Q11), correlated-dimension mask, row arg-max, bucket counts."""
+    T = cov.shape[0]
+    A = ops.color_factor(cov) if transform is None else dev(transform, cov.device)
+    if z is not None:
+        zt = dev(z, cov.device).reshape(-1, T)
+    elif seed is not None:
+        zt = ops.normal_fill(seed, hyp_index, ops.STREAM_JOINT_Z, nsample * T, device=cov.device).reshape(nsample, T)
+    else:  # the reference's own draw: global numpy RNG (utils.py:1674)
+        zt = dev(np.random.normal(size=(nsample, T, 1)), cov.device).reshape(nsample, T)
+    samples = ops.gemm(zt, A, transb=True)
+    _, maxidx, counts = ops.joint_maxidx(samples, mean.reshape(-1), True)
+    return samples, maxidx, counts
+
+
+def get_testidxs_stats(nhyp, test_xs_np, test_means, test_covs, mode="sample", nsample=1000, n_min_sample=2,
+                       z=None, transforms=None, seed=None):
+    """utils.py:1733-1833 with the sampling, bucketing and moment estimation on the device.
+    mode in {'sample','empirical','ep'}; `z` (nhyp, nsample, ntest, 1) replaces the np.random.normal draw of
+    utils.py:1674 (or `seed`: counter-based draws of include/tes_spec.h, stream TES_STREAM_JOINT_Z);
+    `transforms[i]` overrides the colouring factor of hyper-parameter sample i.  numpy in -> numpy out, CUDA
+    tensors in -> CUDA tensors out.  Only the T bucket counts cross to the host (they size the outputs)."""
+    if mode not in ("sample", "empirical", "ep"):
+        raise Exception("Unknown mode in get_testidxs_stats!")
+    like = test_means
+    xs_d, means_d, covs_d = dev(test_xs_np), dev(test_means), dev(test_covs)
+    dv = means_d.device
+    ntest = xs_d.shape[0]
+    means_d, covs_d = means_d.reshape(nhyp, ntest), covs_d.reshape(nhyp, ntest, ntest)
+    means_full = means_d
+    alive = np.ones(ntest, dtype=bool)
+    max_probs = np.ones([nhyp, ntest]) / ntest
+    per_hyp = []
+    for i in range(nhyp):
+        samples, maxidx, counts = _device_buckets(means_d[i], covs_d[i], nsample, None if z is None else z[i],
+                                                  None if transforms is None else transforms[i], seed, i)
+        counts_h = counts.cpu().numpy().astype(np.int64)
+        uniq = np.where(counts_h >= max(n_min_sample, 1))[0]
+        sizes = counts_h[uniq]
+        won = np.zeros(ntest, dtype=bool)
+        won[uniq] = True
+        alive &= won
+        max_probs[i, uniq] = sizes / np.sum(sizes)
+        per_hyp.append((samples, maxidx, counts_h, uniq, sizes))
+    keep = np.where(alive)[0]
+    nk = len(keep)
+    keep_d = torch.from_numpy(keep).to(dv)
+    if nk != ntest:
+        xs_d = xs_d[keep_d]
+        means_d = means_d[:, keep_d]
+        covs_d = covs_d[:, keep_d][:, :, keep_d]
+        max_probs = max_probs[:, keep]
+    max_probs = max_probs / np.sum(max_probs, axis=1, keepdims=True)
+    head = (_ret(xs_d, like), _ret(dev(max_probs, dv), like), _ret(means_d, like), _ret(covs_d, like))
+    if mode == "ep":
+        from . import ep
+        m_h, c_h = means_d.cpu().numpy(), covs_d.cpu().numpy()
+        pm = np.zeros([nhyp, nk, nk])
+        pc = np.zeros([nhyp, nk, nk, nk])
+        for i in range(nhyp):
+            for j in range(nk):
+                m, c = ep.approximate_EP_np(j, m_h[i].reshape(-1, 1), c_h[i], resolution=1e-9, max_niter=100)
+                pm[i, j] = m.squeeze()
+                pc[i, j] = c
+        return head + (_ret(dev(pm, dv), like), _ret(dev(pc, dv), like))
+    K_all = max([int(sz.max()) if len(sz) else 1 for (_, _, _, _, sz) in per_hyp])
+    outs0, outs1 = [], []
+    for i, (samples, maxidx, counts_h, uniq, sizes) in enumerate(per_hyp):
+        order = torch.sort(maxidx, stable=True).indices          # sample rows grouped by bucket, draw order inside
+        starts_all = np.concatenate([[0], np.cumsum(counts_h)])
+        kept_b = [u for u in uniq if alive[u]]                    # buckets of the kept test points, ascending
+        pick = np.concatenate([np.arange(starts_all[u], starts_all[u + 1]) for u in kept_b]) if kept_b else \
+            np.zeros(0, dtype=np.int64)
+        order_k = order[torch.from_numpy(pick).to(dv)].contiguous()
+        starts_k = torch.from_numpy(np.concatenate([[0], np.cumsum(counts_h[kept_b])]).astype(np.int64)).to(dv)
+        if mode == "sample":
+            ps, pmask = ops.bucket_samples(samples, order_k, starts_k, keep_d, K_all, means_full[i])
+            # the reference pads every hyper-parameter sample only up to its own K with the prior mean and leaves
+            # zeros beyond (utils.py:1797-1809)
+            Ki = int(sizes.max())
+            if Ki < K_all:
+                ps[:, :, Ki:] = 0.0
+            outs0.append(ps)
+            outs1.append(pmask)
+        else:
+            bm, bc = ops.bucket_moments(samples, order_k, starts_k, keep_d)
+            outs0.append(bm)
+            outs1.append(bc)
+    return head + (_ret(torch.stack(outs0), like), _ret(torch.stack(outs1), like))
