@@ -54,6 +54,10 @@ def meshgrid(xmin, xmax, nx, xdim):
     return np.concatenate([xd.reshape(-1, 1) for xd in xds], axis=1)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE rff_screen_tc5_kernel launch, from the ncu --set full capture
+# summarised in profiles/ (filled per workload once measured; None = not captured)
+TC5_TRAFFIC_BYTES = {"c3": 465.8e6}   # profiles/r01_ncu_rff_screen_tc5.md (algorithmic: 115 MB)
+
 WORKLOADS = {
     # name: (description, d, N per GPU, S, F, n, t_max)
     "c3": ("C3 Hartmann-6 TES_ep empirical, 1M candidates x 1024 maximizer samples per GPU", 6, 10 ** 6, 1024, 1024, 64, 128),
@@ -302,17 +306,18 @@ def main():
     algo_excl_cos = local_pairs * F * (2 * d + 3) / t_rff * 1e-12  # SURVEY 8(d) figure, cos not counted
     screened = wl["N"] >= 32768 and d <= 10
     if screened and d >= 5:
-        # stage A = tensor-core screen (3xTF32 mma.sync dot products, MUFU cosine) + exact fp64 refine: one
-        # MUFU.COS per (candidate, sample, feature) is the binding resource (XU pipe, 16 lanes/SM/clk)
+        # stage A = tcgen05/TMEM screen (3xTF32 dot products on the 5th-gen tensor cores, cosine on the MUFU with 1 of
+        # every 8 pairs on the FMA pipe) + exact fp64 refine: one cosine per (candidate, sample, feature) on the XU
+        # pipe (16 lanes/SM/clk) is the binding resource
         cos_rate = local_pairs * F / t_rff * 1e-12
-        roofline = {"bound": "mufu", "kernel": "rff_screen_mma_kernel (+ pack/xmax/bound/refine/fallback/merge)",
+        roofline = {"bound": "mufu", "kernel": "rff_screen_tc5_kernel (+ pack/xmax/bound/refine/fallback/merge)",
                     "achieved": cos_rate, "peak": mufu_peak, "unit": "Tcos/s", "frac": cos_rate / mufu_peak,
-                    "traffic": None,
+                    "traffic": TC5_TRAFFIC_BYTES.get(wl["name"]),
                     "peak_source": "measured in this run: tes_mufu_cos_burn (__cosf = FMUL.RZ + MUFU.COS, 8 chains/thread)",
                     "fp64_peak_tflops": fp64_peak, "fp32_peak_tflops": fp32_peak,
                     "algorithmic_excl_cos_tflops": algo_excl_cos,
                     "algorithmic_vs_fp64_peak": algo_excl_cos / fp64_peak,
-                    "per_unit": "F MUFU.COS + F*(3d+2) TF32 tensor MACs per (candidate, sample) pair; "
+                    "per_unit": "F cosines (7/8 MUFU.COS, 1/8 FMA-pipe polynomial) + F*(3d+2) TF32 tcgen05 MACs per (candidate, sample) pair; "
                                 "algorithmic = F*(2d+3) flops + F cos (SURVEY 8d)",
                     "launch_ms": t_rff * 1e3, "share_of_step": t_rff * args.steps / dev_s,
                     "criterion_ms": float(np.mean(rc)) * 1e3 if rc else None}

@@ -260,8 +260,11 @@ __global__ void __launch_bounds__(TC5_THREADS, 1)
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int nsg = (S + sg - 1) / sg;
-    const int64_t chunk_id = blockIdx.x / nsg;
-    const int gq = blockIdx.x % nsg;
+    // consecutive CTAs share the sample group and differ in the candidate chunk: the ~150 CTAs in flight then stream
+    // the SAME few feature tiles, which stay L2 hits instead of cycling the whole S x F feature set through DRAM
+    const int nchunks_ = (int)((N + chunk - 1) / chunk);
+    const int64_t chunk_id = blockIdx.x % nchunks_;
+    const int gq = blockIdx.x / nchunks_;
     const int j0 = gq * sg;
     const int nj = min(sg, S - j0);
     const int64_t c0 = chunk_id * chunk;
