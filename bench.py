@@ -67,7 +67,7 @@ WORKLOADS = {
 }
 
 
-def make_workload(name, rank, world):
+def make_workload(name, rank, world, host_only=False):
     desc, d, N, S, F, n, t_max = WORKLOADS[name]
     from tes_b200 import optfunc
     hyp = HART6 if d == 6 else dict(l=np.array([177.9418631280815, 309.4630784148164]), sigma=0.29444226420446995,
@@ -86,8 +86,10 @@ def make_workload(name, rank, world):
     else:
         cand = np.random.RandomState(7 + rank).rand(N, d)
     np.random.seed(11)  # identical draws on every rank
-    theta, W, b = optfunc.draw_random_init_weights_features_np(d, S, F, X, Y, hyp["l"].reshape(1, d), hyp["sigma"],
-                                                              hyp["sigma0"])
+    # the RFF posterior weight draw (optfunc.py:303-385): on the device for the b200 arm, host numpy (where the
+    # reference runs it) for the CPU reference arm; same np.random draws either way
+    draw = optfunc.draw_random_init_weights_features_host if host_only else optfunc.draw_random_init_weights_features_np
+    theta, W, b = draw(d, S, F, X, Y, hyp["l"].reshape(1, d), hyp["sigma"], hyp["sigma0"])
     return dict(name=name, desc=desc, d=d, N=N, S=S, F=F, n=n, t_max=t_max, hyp=hyp, X=X, Y=Y,
                 cand=np.ascontiguousarray(cand), theta=np.ascontiguousarray(theta.reshape(S, F)),
                 W=np.ascontiguousarray(W), b=np.ascontiguousarray(b.reshape(S, F)))
@@ -206,7 +208,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        wl = make_workload(args.workload, 0, 1) if rank == 0 else None
+        wl = make_workload(args.workload, 0, 1, host_only=True) if rank == 0 else None
         run_reference_arm(args, wl, rank)
         return
 

@@ -175,6 +175,19 @@ int tes_sp_acq_f64(const double* x, int64_t nx, int q, int64_t d, const double* 
  * point returns exactly that closed form. */
 int tes_batch_ep_acq_f64(const double* p, int64_t Sp, int64_t nx, double* out_acq, void* stream);
 
+/* ============================================================================ Stage A (draw)
+ * optfunc.draw_random_init_weights_features_np (optfunc.py:303-385): the RFF posterior weight draw for S function
+ * samples at once.  X (n, d) observations, Y (n) centred targets, l (d) inverse squared length-scales; the three
+ * random draws are inputs in the reference's draw order: randn_W (S, F, d) (:329), rand_b (S, F) uniform (:334),
+ * randn_noise (S, F) (:344).  Outputs theta (S, F), W (S, F, d) = randn_W * sqrt(l), b (S, F) = 2 pi rand_b.
+ * n < F: eigen-decomposition route of :348-374 (batched GEMM for Z^T Z + sigma0 I, batched Jacobi eigen-solver);
+ * n >= F: the F x F inverse + Cholesky route of :377-383.  1 <= d <= 64, S <= 65535. */
+int64_t tes_rff_draw_workspace_bytes(int64_t S, int64_t F, int64_t n, int64_t d);
+int tes_rff_draw_f64(const double* X, const double* Y, int64_t n, int64_t d, const double* l, double sigma,
+                     double sigma0, const double* randn_W, const double* rand_b, const double* randn_noise,
+                     int64_t S, int64_t F, double* theta, double* W, double* b, void* ws, int64_t ws_bytes,
+                     void* stream);
+
 /* ===================================================================================== Stage C
  * Trusted-maximizer statistics on the device.  The reference does all of this in host numpy
  * (utils.get_testidxs_stats, utils.py:1733-1833); here it stays next to the data so that one
@@ -186,6 +199,11 @@ int tes_batch_ep_acq_f64(const double* p, int64_t Sp, int64_t nx, double* out_ac
  * np.random.normal call of utils.py:1674 when the caller passes a seed instead of the draws themselves. */
 int tes_normal_fill_f64(uint64_t seed, uint32_t iteration, uint32_t stream_id, uint64_t first_elem,
                         int64_t count, double* out, void* stream);
+
+/* Uniform draws on (0,1) from the same counters: u = (k + 0.5) 2^-53, k = top 53 bits of the Philox words that feed
+ * the Box-Muller pair (element e -> pair e>>1, component e&1). */
+int tes_uniform_fill_f64(uint64_t seed, uint32_t iteration, uint32_t stream_id, uint64_t first_elem,
+                         int64_t count, double* out, void* stream);
 
 /* utils.remove_duplicates_np / its mask (utils.py:1554-1581): walking the rows of xs (S, d) in order, every
  * not-yet-flagged row flags all LATER rows whose Euclidean distance is <= resolution.  The distance is evaluated in

@@ -60,5 +60,8 @@
 #define TES_STREAM_BSP_Y 3u   /* evaluate_batch_sample_mp.py:315  z[it][iy][j][x][s][q]   */
 #define TES_STREAM_BEP_Y 4u   /* evaluate_batch_mp.py:294      z[it][iy][j][x][q]         */
 #define TES_STREAM_JOINT_Z 5u /* utils.py:1674 joint samples  z[hyp = iteration][sample][t]   */
+#define TES_STREAM_RFF_W 6u   /* optfunc.py:329  randn[j][f][k]   (iteration = hyper-parameter index) */
+#define TES_STREAM_RFF_B 7u   /* optfunc.py:334  rand[j][f]  uniform: u = (k + 0.5) 2^-53, k = top 53 bits of the word pair */
+#define TES_STREAM_RFF_E 8u   /* optfunc.py:344  randn[j][f] */
 
 #endif /* TES_SPEC_H */

@@ -60,7 +60,7 @@ def test_rff_weight_draw_mirror(golden, tag, xdim):
     from tes_b200 import optfunc
     g = golden("rff")
     S, F = g[tag + "_theta"].shape[:2]
-    theta, W, b = optfunc.draw_random_init_weights_features_np(
+    theta, W, b = optfunc.draw_random_init_weights_features_host(
         xdim, S, F, g[tag + "_X"], g[tag + "_Y"], g[tag + "_l"], float(g[tag + "_sigma"]), float(g[tag + "_sigma0"]),
         draws=(g[tag + "_randn_W"], g[tag + "_rand_b"], g[tag + "_randn_noise"]))
     np.testing.assert_array_equal(W, g[tag + "_W"])

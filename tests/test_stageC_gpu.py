@@ -167,3 +167,53 @@ def test_device_joint_samples_with_own_colouring_factor_have_the_right_law():
     np.testing.assert_array_equal(a[0], b[0])
     np.testing.assert_allclose(a[1], b[1], atol=6e-3)
     np.testing.assert_allclose(a[4], b[4], atol=3e-2)
+
+
+# ---- RFF posterior weight draw on the device (csrc/rffdraw.cu, optfunc.py:303-385) ------------------------------
+@pytest.mark.parametrize("tag,xdim", [("nltF", 2), ("ngeF", 2), ("d6", 6)])
+def test_device_rff_weight_draw_matches_the_reference_outputs(golden, tag, xdim):
+    from tes_b200 import optfunc
+    g = golden("rff")
+    S, F = g[tag + "_theta"].shape[:2]
+    theta, W, b = optfunc.draw_random_init_weights_features_np(
+        xdim, S, F, g[tag + "_X"], g[tag + "_Y"], g[tag + "_l"], float(g[tag + "_sigma"]), float(g[tag + "_sigma0"]),
+        draws=(g[tag + "_randn_W"], g[tag + "_rand_b"], g[tag + "_randn_noise"]))
+    np.testing.assert_array_equal(W, g[tag + "_W"])        # elementwise products: bit-exact
+    np.testing.assert_array_equal(b, g[tag + "_b"])
+    # theta goes through Sigma^-1 (cond ~ trace/sigma0): 1e-8 relative to the largest weight
+    np.testing.assert_allclose(theta, g[tag + "_theta"], rtol=0, atol=1e-8 * np.abs(g[tag + "_theta"]).max())
+
+
+@pytest.mark.parametrize("S,F,n,d,sigma0", [(16, 256, 64, 6, 1e-4), (5, 300, 5, 2, 1e-4), (3, 512, 200, 4, 1e-2),
+                                            (4, 48, 60, 3, 1e-2), (2, 64, 64, 2, 1e-3)])
+def test_device_rff_weight_draw_vs_oracle(S, F, n, d, sigma0):
+    from tes_b200 import optfunc
+    rs = np.random.RandomState(S * 1000 + n)
+    X, Y = rs.rand(n, d), rs.randn(n, 1)
+    l = 1.0 + 8.0 * rs.rand(d)
+    draws = (rs.randn(S, F, d), rs.rand(S, F, 1), rs.randn(S, F, 1))
+    ref = onp.draw_random_init_weights_features(d, S, F, X, Y, l.reshape(1, d), 1.3, sigma0, *draws)
+    got = optfunc.draw_random_init_weights_features_np(d, S, F, X, Y, l.reshape(1, d), 1.3, sigma0, draws=draws)
+    np.testing.assert_array_equal(got[1], ref[1])
+    np.testing.assert_array_equal(got[2], ref[2])
+    np.testing.assert_allclose(got[0], ref[0], rtol=0, atol=1e-7 * np.abs(ref[0]).max())
+
+
+def test_device_rff_weight_draw_from_seed_is_a_posterior_sample():
+    """Counter-based draws on the device: the function samples must interpolate the observations (posterior with
+    small noise) -- a property test at a size the host path would take seconds for."""
+    from tes_b200 import ops, optfunc
+    rs = np.random.RandomState(0)
+    n, d, S, F = 40, 6, 256, 2048
+    X = rs.rand(n, d)
+    l = np.array([6.9512, 1.9341, 0.506, 4.2067, 5.0986, 3.5949])
+    Y = np.sin(3.0 * X.sum(axis=1, keepdims=True))
+    theta, W, b = optfunc.draw_random_init_weights_features(d, S, F, X, Y, l.reshape(1, d), 1.423, 1e-4, seed=12)
+    assert theta.is_cuda and theta.shape == (S, F, 1)
+    f = ops.rff_eval(X, W, b, theta, 1.423).cpu().numpy()           # (S, n)
+    assert np.abs(f - Y.reshape(1, n)).max() < 0.2                    # sd of the posterior at the data ~ sqrt(sigma0)
+    u = ops.uniform_fill(12, 0, ops.STREAM_RFF_B, 1 << 16).cpu().numpy()
+    assert 0.0 < u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3
+    raw = c_oracle.philox_raw(12, 0, 7, 5)                             # elements 10, 11 of the uniform stream
+    k0 = ((raw[1] << 32) | raw[0]) >> 11
+    assert u[10] == (k0 + 0.5) * 2.0 ** -53

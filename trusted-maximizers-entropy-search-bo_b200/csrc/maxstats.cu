@@ -24,6 +24,22 @@ __global__ void normal_fill_kernel(uint64_t seed, uint32_t iteration, uint32_t s
     if (e1 >= first && e1 < first + (uint64_t)count) out[e1 - first] = z1;
 }
 
+// uniform draws on (0,1) from the same counters: element e -> pair e >> 1, component e & 1, u = (k + 0.5) 2^-53 with
+// k the top 53 bits of (x0 | x1 << 32) resp. (x2 | x3 << 32)  (the u1 / u2 of the Box-Muller pair in tes_spec.h)
+__global__ void uniform_fill_kernel(uint64_t seed, uint32_t iteration, uint32_t stream_id, uint64_t first,
+                                    int64_t count, double* __restrict__ out) {
+    const uint64_t p0 = first >> 1;
+    const uint64_t p1 = (first + (uint64_t)count + 1) >> 1;
+    const uint64_t pair = p0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= p1) return;
+    uint32_t c0 = (uint32_t)pair, c1 = (uint32_t)(pair >> 32), c2 = iteration, c3 = stream_id;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint64_t a = ((uint64_t)c1 << 32) | c0, b = ((uint64_t)c3 << 32) | c2;
+    const uint64_t e0 = 2 * pair, e1 = 2 * pair + 1;
+    if (e0 >= first && e0 < first + (uint64_t)count) out[e0 - first] = ((double)(a >> 11) + 0.5) * 0x1.0p-53;
+    if (e1 >= first && e1 < first + (uint64_t)count) out[e1 - first] = ((double)(b >> 11) + 0.5) * 0x1.0p-53;
+}
+
 // ---- de-duplication (utils.py:1554-1573) ---------------------------------------------------------------------
 // np.sum of a contiguous run of n doubles (numpy's pairwise summation, n <= 128 branch), applied to the squared
 // differences of two rows: identical operation order => identical distance bits => identical keep / drop decisions.
@@ -372,6 +388,18 @@ extern "C" int tes_normal_fill_f64(uint64_t seed, uint32_t iteration, uint32_t s
     const uint64_t npairs = ((first_elem + (uint64_t)count + 1) >> 1) - (first_elem >> 1);
     normal_fill_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, iteration, stream_id,
                                                                                           first_elem, count, out);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tes_uniform_fill_f64(uint64_t seed, uint32_t iteration, uint32_t stream_id, uint64_t first_elem,
+                                    int64_t count, double* out, void* stream) {
+    if (count < 0) return -5;
+    if (count == 0) return 0;
+    if (!out) return -6;
+    const uint64_t npairs = ((first_elem + (uint64_t)count + 1) >> 1) - (first_elem >> 1);
+    uniform_fill_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, iteration, stream_id,
+                                                                                           first_elem, count, out);
     TES_LAUNCH_OK();
     return 0;
 }

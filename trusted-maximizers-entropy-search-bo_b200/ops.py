@@ -427,3 +427,44 @@ def bucket_samples(samples, order, starts, cols, K, prior_mean):
                                            stream_ptr())
     _lib.check(rc, "tes_bucket_samples_f64")
     return out, mask.bool()
+
+
+STREAM_RFF_W, STREAM_RFF_B, STREAM_RFF_E = 6, 7, 8  # include/tes_spec.h
+
+
+def uniform_fill(seed, iteration, stream_id, count, first_elem=0, device=None):
+    """Counter-based uniform draws on (0,1) of include/tes_spec.h -> (count,) CUDA tensor."""
+    out = torch.empty((int(count),), dtype=torch.float64,
+                      device=device or torch.device("cuda", torch.cuda.current_device()))
+    rc = _lib.lib().tes_uniform_fill_f64(int(seed), int(iteration), int(stream_id), int(first_elem), int(count),
+                                         ptr(out), stream_ptr())
+    _lib.check(rc, "tes_uniform_fill_f64")
+    return out
+
+
+def rff_draw(X, Y, l, sigma, sigma0, randn_W, rand_b, randn_noise):
+    """optfunc.py:303-385 on the device -> theta (S,F), W (S,F,d), b (S,F) CUDA tensors."""
+    X = dev(X)
+    dv = X.device
+    n, d = X.shape
+    Y = dev(Y, dv).reshape(-1)
+    randn_W = dev(randn_W, dv)
+    S, F = randn_W.shape[0], randn_W.shape[1]
+    randn_W = randn_W.reshape(S, F, d)
+    rand_b = dev(rand_b, dv).reshape(S, F)
+    randn_noise = dev(randn_noise, dv).reshape(S, F)
+    if Y.numel() != n:
+        raise ValueError("Y must have one entry per observation")
+    l = _l(l, d, dv)
+    L = _lib.lib()
+    need = L.tes_rff_draw_workspace_bytes(S, F, n, d)
+    if need < 0:
+        raise ValueError("invalid sizes for tes_rff_draw_f64: S=%d F=%d n=%d d=%d" % (S, F, n, d))
+    ws = WORKSPACE.get(need, dv)
+    theta = torch.empty((S, F), dtype=torch.float64, device=dv)
+    W = torch.empty((S, F, d), dtype=torch.float64, device=dv)
+    b = torch.empty((S, F), dtype=torch.float64, device=dv)
+    rc = L.tes_rff_draw_f64(ptr(X), ptr(Y), n, d, ptr(l), float(sigma), float(sigma0), ptr(randn_W), ptr(rand_b),
+                            ptr(randn_noise), S, F, ptr(theta), ptr(W), ptr(b), ptr(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_rff_draw_f64")
+    return theta, W, b
