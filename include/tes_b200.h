@@ -246,6 +246,17 @@ int tes_bucket_samples_f64(const double* samples, int64_t ns, int64_t T, const i
                            int64_t nb, const int64_t* cols, int64_t nk, int64_t K, const double* prior_mean,
                            double* out, uint8_t* mask, void* stream);
 
+/* ep.approximate_EP_np (ep.py:73-204) for EVERY maximizer of every hyper-parameter sample in one launch (one CTA per
+ * maximizer, Gauss-Jordan inverse with partial pivoting in shared memory for T <= 160).  mean (nhyp, T), cov
+ * (nhyp, T, T) -> post_mean (nhyp, T, T), post_cov (nhyp, T, T, T); row j = the EP approximation of N(mean, cov)
+ * truncated to {f_j >= f_i for all i}.  niter (nhyp, T) int32 or NULL: the reference's iteration counter at exit.
+ * Same update schedule, skip rule, NaN early-exit and convergence measure as the reference; where the reference's
+ * skip loop would never terminate (every site invalid) the current approximation is returned. */
+int64_t tes_ep_moments_workspace_bytes(int64_t nhyp, int64_t T);
+int tes_ep_moments_f64(const double* mean, const double* cov, int64_t nhyp, int64_t T, double resolution,
+                       int max_niter, double* post_mean, double* post_cov, int* niter, void* ws, int64_t ws_bytes,
+                       void* stream);
+
 /* ============================================================================== measurement aids
  * Sustained fp64 FMA rate of the device, used as the roofline denominator for the fp64-pipe-bound
  * kernels (MEASURED_PEAKS.json carries only HBM and bf16 numbers).  Runs `iters` dependent-chain

@@ -35,7 +35,7 @@ def test_ep_mirror(golden, tag):
     g = golden("maximizer_stats")
     mean_k, cov_k = g[tag + "_sample_out2"], g[tag + "_sample_out3"]
     for j in range(mean_k.shape[1]):
-        m, c = ep.approximate_EP_np(j, mean_k[0].reshape(-1, 1), cov_k[0], 1e-9, 100)
+        m, c = ep.approximate_EP_host(j, mean_k[0].reshape(-1, 1), cov_k[0], 1e-9, 100)
         np.testing.assert_allclose(m.squeeze(), g[tag + "_ep_mean"][j], rtol=1e-9, atol=1e-11)
         np.testing.assert_allclose(c, g[tag + "_ep_cov"][j], rtol=1e-9, atol=1e-11)
     # mode='ep' end to end (the call utils.py:1820-1825 intends)

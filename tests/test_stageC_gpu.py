@@ -217,3 +217,60 @@ def test_device_rff_weight_draw_from_seed_is_a_posterior_sample():
     raw = c_oracle.philox_raw(12, 0, 7, 5)                             # elements 10, 11 of the uniform stream
     k0 = ((raw[1] << 32) | raw[0]) >> 11
     assert u[10] == (k0 + 0.5) * 2.0 ** -53
+
+
+# ---- batched EP on the device (csrc/ep.cu, ep.py:73-204) --------------------------------------------------------
+@pytest.mark.parametrize("tag", ["t6", "t12"])
+def test_device_ep_matches_the_reference_outputs(golden, tag):
+    from tes_b200 import ep
+    g = golden("maximizer_stats")
+    mean_k, cov_k = g[tag + "_sample_out2"], g[tag + "_sample_out3"]
+    pm, pc = ep.approximate_EP_all(mean_k[0], cov_k[0], 1e-9, 100)
+    np.testing.assert_allclose(pm, g[tag + "_ep_mean"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(pc, g[tag + "_ep_cov"], rtol=1e-8, atol=1e-10)
+    m, c = ep.approximate_EP_np(1, mean_k[0].reshape(-1, 1), cov_k[0], 1e-9, 100)     # the reference's signature
+    np.testing.assert_allclose(m.squeeze(), g[tag + "_ep_mean"][1], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(c, g[tag + "_ep_cov"][1], rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize("T,nhyp,max_niter,res", [(2, 1, 100, 1e-9), (3, 2, 100, 1e-9), (9, 1, 1000, 1e-14),
+                                                  (24, 2, 100, 1e-9), (61, 1, 60, 1e-9), (170, 1, 6, 1e-9)])
+def test_device_ep_vs_oracle(T, nhyp, max_niter, res):
+    """Random GP posteriors at well-separated test points (cond(Sigma) moderate so that the two inverses agree to
+    1e-9); T = 170 exercises the global-memory matrix path; same iteration counts as the oracle."""
+    from tes_b200 import ops
+    rs = np.random.RandomState(T)
+    d = 2
+    means, covs = [], []
+    for i in range(nhyp):
+        xs = rs.rand(T, d) * (4.0 if T < 100 else 30.0)
+        X, Y = rs.rand(5, d) * 4.0, rs.randn(5, 1)
+        l = np.array([3.0, 5.0]) * (1 + i)
+        invK = onp.precomputeInvKs(l.reshape(1, d), np.array([1.0]), np.array([1e-2]), X)
+        m, c = onp.compute_mean_var_f(xs, X, Y, l, 1.0, 1e-2, invK[0], fullcov=True)
+        means.append(m.reshape(T))
+        covs.append(c + 1e-6 * np.eye(T))
+    means, covs = np.stack(means), np.stack(covs)
+    pm, pc, nit = ops.ep_moments(means, covs, res, max_niter, return_niter=True)
+    pm, pc = pm.cpu().numpy(), pc.cpu().numpy()
+    for i in range(nhyp):
+        for j in (range(T) if T <= 24 else [0, 1, T // 2, T - 1]):
+            m, c = onp.approximate_EP(j, means[i].reshape(-1, 1), covs[i], res, max_niter)
+            scale = np.abs(covs[i]).max()
+            np.testing.assert_allclose(pm[i, j], m.squeeze(), rtol=0, atol=2e-8 * max(1.0, np.abs(m).max()))
+            np.testing.assert_allclose(pc[i, j], c, rtol=0, atol=2e-8 * scale)
+    assert int(nit.min()) >= 1
+
+
+def test_device_ep_mode_through_get_testidxs_stats_cuda_tensors(golden):
+    from tes_b200 import utils
+    g = golden("maximizer_stats")
+    tag = "t12"
+    cov = g[tag + "_cov"].copy()
+    out = utils.get_testidxs_stats(1, torch.from_numpy(g[tag + "_test_xs"]).cuda(),
+                                   torch.from_numpy(g[tag + "_mean"]).cuda(), torch.from_numpy(cov).cuda(), mode="ep",
+                                   nsample=int(g[tag + "_nsample"]), n_min_sample=2, z=g[tag + "_z"],
+                                   transforms=[utils.mvn_transform_matrix(cov[0])])
+    assert all(o.is_cuda for o in out)
+    np.testing.assert_allclose(out[4][0].cpu().numpy(), g[tag + "_ep_mean"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(out[5][0].cpu().numpy(), g[tag + "_ep_cov"], rtol=1e-8, atol=1e-10)

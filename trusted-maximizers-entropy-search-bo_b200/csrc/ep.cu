@@ -1,0 +1,344 @@
+// ep.cu -- batched expectation propagation for the maximizer-conditioned posteriors on the device.
+//
+// Reference: ep.approximate_EP_np (ep.py:73-204) with its helpers (ep.py:8-70), host numpy/scipy there, called once
+// per trusted maximizer by utils.get_testidxs_stats(mode='ep') (utils.py:1820-1825): EP for N(mu, Sigma) truncated
+// to {f_j >= f_i for all i}, T-1 half-space sites c_i = e_j - e_i, ONE site updated per outer iteration, the Gaussian
+// approximation refreshed by a full T x T inverse after every update, stop at mean-square change <= resolution or
+// max_niter.  Here: one CTA per maximizer (all T of them concurrently), the T x T system matrix lives in shared
+// memory and is inverted in place by Gauss-Jordan elimination with partial pivoting (the same pivoting rule as the
+// LU behind np.linalg.inv); Sigma^-1 is computed once by the same routine and shared through L2.
+#include "tes_common.cuh"
+
+namespace tes {
+
+constexpr int EP_THREADS = 512;
+
+// In-place inverse of the n x n row-major matrix a (shared or global memory), Gauss-Jordan with partial pivoting.
+// piv: n ints of shared scratch; red_v / red_i: one slot per warp.  All threads of the CTA must call.
+__device__ void gj_inverse(double* a, int n, int* piv, double* red_v, int* red_i) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    for (int k = 0; k < n; ++k) {
+        // pivot search in column k, rows k..n-1 (first maximum of |a_ik|, like LAPACK's idamax)
+        double bv = -1.0;
+        int bi = n;
+        for (int i = k + tid; i < n; i += nt) {
+            const double v = fabs(a[(int64_t)i * n + k]);
+            if (v > bv || !(v == v)) {  // a NaN pivot candidate wins: the NaN then propagates like in LAPACK
+                bv = v == v ? v : pos_inf();
+                bi = i;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ov > bv || (ov == bv && oi < bi)) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            red_v[warp] = bv;
+            red_i[warp] = bi;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double v = red_v[0];
+            int i = red_i[0];
+            for (int w = 1; w < nwarps; ++w)
+                if (red_v[w] > v || (red_v[w] == v && red_i[w] < i)) {
+                    v = red_v[w];
+                    i = red_i[w];
+                }
+            piv[k] = i < n ? i : k;
+        }
+        __syncthreads();
+        const int p = piv[k];
+        if (p != k)
+            for (int c = tid; c < n; c += nt) {
+                const double t = a[(int64_t)k * n + c];
+                a[(int64_t)k * n + c] = a[(int64_t)p * n + c];
+                a[(int64_t)p * n + c] = t;
+            }
+        __syncthreads();
+        const double pv = a[(int64_t)k * n + k];
+        __syncthreads();
+        const double ipv = 1.0 / pv;
+        for (int c = tid; c < n; c += nt) a[(int64_t)k * n + c] = (c == k ? 1.0 : a[(int64_t)k * n + c]) * ipv;
+        __syncthreads();
+        // eliminate column k from every other row: thread = (row stripe, column stripe) over the whole matrix
+        for (int e = tid; e < n * n; e += nt) {
+            const int i = e / n, c = e - i * n;
+            if (i == k) continue;
+            const double f = a[(int64_t)i * n + k];
+            if (c == k) continue;  // handled after the barrier (it is the multiplier the other columns still read)
+            a[e] = fma(-f, a[(int64_t)k * n + c], a[e]);
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += nt)
+            if (i != k) a[(int64_t)i * n + k] = -a[(int64_t)i * n + k] * a[(int64_t)k * n + k];
+        __syncthreads();
+    }
+    // undo the row interchanges as column interchanges, in reverse order
+    for (int k = n - 1; k >= 0; --k) {
+        const int p = piv[k];
+        if (p != k)
+            for (int r = tid; r < n; r += nt) {
+                const double t = a[(int64_t)r * n + k];
+                a[(int64_t)r * n + k] = a[(int64_t)r * n + p];
+                a[(int64_t)r * n + p] = t;
+            }
+        __syncthreads();
+    }
+}
+
+// inv_cov = inverse(cov) for each hyper-parameter sample (grid.x = nhyp); h = inv_cov * mean
+__global__ void __launch_bounds__(EP_THREADS) ep_prepare_kernel(const double* __restrict__ cov,
+                                                                const double* __restrict__ mean, int T,
+                                                                double* __restrict__ inv_cov, double* __restrict__ h,
+                                                                double* __restrict__ gscratch, int in_smem) {
+    extern __shared__ double sm[];
+    __shared__ int piv[2048];
+    __shared__ double red_v[32];
+    __shared__ int red_i[32];
+    const int64_t b = blockIdx.x;
+    double* a = in_smem ? sm : gscratch + b * T * T;
+    for (int e = threadIdx.x; e < T * T; e += blockDim.x) a[e] = cov[b * T * T + e];
+    __syncthreads();
+    gj_inverse(a, T, piv, red_v, red_i);
+    for (int e = threadIdx.x; e < T * T; e += blockDim.x) inv_cov[b * T * T + e] = a[e];
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < T; ++k) s = fma(a[(int64_t)i * T + k], mean[b * T + k], s);
+        h[b * T + i] = s;
+    }
+}
+
+__device__ __forceinline__ double norm_pdf(double x) { return exp(-0.5 * x * x) * 0.3989422804014327; }
+__device__ __forceinline__ double norm_cdf(double x) { return 0.5 * erfc(-x * 0.7071067811865476); }
+
+// site column c of maximizer j refers to the test point o(c) = c < j ? c : c + 1
+__device__ __forceinline__ int ep_other(int c, int j) { return c < j ? c : c + 1; }
+
+// M = inv_cov + C diag(1/site_var) C^T, rhs = h + C (site_mean / site_var); then cov = M^-1 (in place), mean = cov rhs
+__device__ void ep_refresh(double* M, int T, int j, const double* __restrict__ inv_cov, const double* __restrict__ h,
+                           const double* site_m, const double* site_v, double* rhs, double* out_mean, int* piv,
+                           double* red_v, int* red_i, double* scal) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < T * T; e += nt) M[e] = inv_cov[e];
+    for (int i = tid; i < T; i += nt) rhs[i] = h[i];
+    __syncthreads();
+    // the reference forms csp = cs / sqrt(site_vars) and csp csp^T: a negative site variance gives NaN (ep.py:17-21)
+    if (tid == 0) {
+        double sw = 0.0, sr = 0.0;
+        for (int c = 0; c < T - 1; ++c) {
+            const double w = 1.0 / sqrt(site_v[c]);
+            sw += w * w;
+            sr += site_m[c] / site_v[c];
+        }
+        scal[0] = sw;
+        scal[1] = sr;
+    }
+    for (int c = tid; c < T - 1; c += nt) {
+        const int o = ep_other(c, j);
+        const double w = 1.0 / sqrt(site_v[c]);
+        const double ww = w * w;
+        M[(int64_t)o * T + o] += ww;
+        M[(int64_t)j * T + o] -= ww;
+        M[(int64_t)o * T + j] -= ww;
+        rhs[o] -= site_m[c] / site_v[c];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        M[(int64_t)j * T + j] += scal[0];
+        rhs[j] += scal[1];
+    }
+    __syncthreads();
+    gj_inverse(M, T, piv, red_v, red_i);
+    for (int i = tid; i < T; i += nt) {
+        double s = 0.0;
+        for (int k = 0; k < T; ++k) s = fma(M[(int64_t)i * T + k], rhs[k], s);
+        out_mean[i] = s;
+    }
+    __syncthreads();
+}
+
+// grid = (T maximizers, nhyp).  Outputs post_mean (nhyp, T, T), post_cov (nhyp, T, T, T), niter (nhyp, T).
+__global__ void __launch_bounds__(EP_THREADS) ep_kernel(const double* __restrict__ mean_all,
+                                                        const double* __restrict__ cov_all,
+                                                        const double* __restrict__ inv_cov_all,
+                                                        const double* __restrict__ h_all, int T, double resolution,
+                                                        int max_niter, double* __restrict__ post_mean,
+                                                        double* __restrict__ post_cov, int* __restrict__ niter,
+                                                        double* __restrict__ gscratch, int in_smem) {
+    extern __shared__ double sm[];
+    __shared__ int piv[2048];
+    __shared__ double red_v[32];
+    __shared__ int red_i[32];
+    __shared__ double scal[4];
+    __shared__ int s_uidx, s_count, s_stop;
+    const int j = blockIdx.x;
+    const int64_t hy = blockIdx.y;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const double* mu = mean_all + hy * T;
+    const double* Sg = cov_all + hy * T * T;
+    const double* inv_cov = inv_cov_all + hy * T * T;
+    const double* h = h_all + hy * T;
+    double* a_cov = post_cov + (hy * T + j) * (int64_t)T * T;   // current approximation (state + output)
+    double* a_mean_out = post_mean + (hy * T + j) * (int64_t)T;
+    // shared layout: [M (T*T) if in_smem] a_mean[T] n_mean[T] rhs[T] site_m[T] site_v[T] new_m[T] new_v[T]
+    double* M = in_smem ? sm : gscratch + (hy * gridDim.x + j) * (int64_t)T * T;
+    double* vec = in_smem ? sm + (int64_t)T * T : sm;
+    double *a_mean = vec, *n_mean = vec + T, *rhs = vec + 2 * T, *site_m = vec + 3 * T, *site_v = vec + 4 * T,
+           *new_m = vec + 5 * T, *new_v = vec + 6 * T;
+
+    // site initialisation (ep.py:107-108): c^T mu and diag(c^T Sigma c)
+    for (int c = tid; c < T - 1; c += nt) {
+        const int o = ep_other(c, j);
+        site_m[c] = mu[j] - mu[o];
+        site_v[c] = (Sg[(int64_t)j * T + j] - Sg[(int64_t)o * T + j]) - (Sg[(int64_t)j * T + o] - Sg[(int64_t)o * T + o]);
+    }
+    __syncthreads();
+    ep_refresh(M, T, j, inv_cov, h, site_m, site_v, rhs, a_mean, piv, red_v, red_i, scal);
+    for (int e = tid; e < T * T; e += nt) a_cov[e] = M[e];
+    if (tid == 0) {
+        s_count = 0;
+        s_stop = 0;
+    }
+    __syncthreads();
+    double diff = 1e10;
+    while (diff > resolution && s_count < max_niter) {
+        __syncthreads();
+        // cavity (ep.py:31-49), truncated-normal moments (:52-60), site update (:63-70), all sites at once
+        for (int c = tid; c < T - 1; c += nt) {
+            const int o = ep_other(c, j);
+            const double ctSc = (a_cov[(int64_t)j * T + j] - a_cov[(int64_t)o * T + j]) -
+                                (a_cov[(int64_t)j * T + o] - a_cov[(int64_t)o * T + o]);
+            const double ctm = a_mean[j] - a_mean[o];
+            const double cav_v = 1.0 / (1.0 / ctSc - 1.0 / site_v[c]);
+            const double cav_m = cav_v * (ctm / ctSc - site_m[c] / site_v[c]);
+            const double sd = sqrt(cav_v);
+            const double beta = cav_m / sd;
+            const double poc = norm_pdf(beta) / norm_cdf(beta);
+            const double cf_m = cav_m + sd * poc;
+            const double cf_v = -cav_m * sd * poc - cf_m * cf_m + 2.0 * cav_m * cf_m - cav_m * cav_m + cav_v;
+            const double nv = 1.0 / (1.0 / cf_v - 1.0 / cav_v);
+            new_v[c] = nv;
+            new_m[c] = nv * (cf_m / cf_v - cav_m / cav_v);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int count = s_count + 1;
+            int uidx = count % (T - 1);
+            const int last = count >= 1 ? count - 1 : T - 2;
+            int guard = 0;
+            auto bad = [&](int u) {
+                const double v = new_v[u];
+                return v <= 0.0 || v != v || isinf(v);
+            };
+            // ep.py:162-172.  The reference's loop has no exit when every site is invalid and count-1 >= T-1; a
+            // device kernel must terminate, so after one full cycle without a valid site the EP stops and returns
+            // the current approximation.
+            while (bad(uidx) && uidx != last) {
+                ++count;
+                uidx = count % (T - 1);
+                if (++guard >= T - 1 && last >= T - 1) {
+                    s_stop = 1;
+                    break;
+                }
+            }
+            s_count = count;
+            s_uidx = uidx;
+            if (!s_stop) {
+                site_m[uidx] = new_m[uidx];
+                site_v[uidx] = new_v[uidx];
+            }
+        }
+        __syncthreads();
+        if (s_stop) break;
+        ep_refresh(M, T, j, inv_cov, h, site_m, site_v, rhs, n_mean, piv, red_v, red_i, scal);
+        // converge_diff = mean over the (T, T) broadcast of dmean_i^2 + dcov_ik^2 (ep.py:190-193); NaN check
+        double part = 0.0;
+        int nan = 0;
+        for (int e = tid; e < T * T; e += nt) {
+            const int i = e / T;
+            const double dm = n_mean[i] - a_mean[i];
+            const double dc = M[e] - a_cov[e];
+            part += dm * dm + dc * dc;
+            nan |= (M[e] != M[e]) || (n_mean[i] != n_mean[i]);
+        }
+        part = warp_sum(part);
+        nan = __any_sync(0xffffffffu, nan);
+        if (lane == 0) {
+            red_v[warp] = part;
+            red_i[warp] = nan;
+        }
+        __syncthreads();
+        double tot = 0.0;
+        int anynan = 0;
+        for (int w = 0; w < nwarps; ++w) {
+            tot += red_v[w];
+            anynan |= red_i[w];
+        }
+        diff = tot / ((double)T * (double)T);
+        __syncthreads();
+        if (anynan) break;  // ep.py:195-199: keep the previous approximation
+        for (int e = tid; e < T * T; e += nt) a_cov[e] = M[e];
+        for (int i = tid; i < T; i += nt) a_mean[i] = n_mean[i];
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int i = tid; i < T; i += nt) a_mean_out[i] = a_mean[i];
+    if (tid == 0 && niter) niter[hy * T + j] = s_count;
+}
+
+}  // namespace tes
+
+using namespace tes;
+
+constexpr int EP_SMEM_MAX_T = 160;
+
+extern "C" int64_t tes_ep_moments_workspace_bytes(int64_t nhyp, int64_t T) {
+    if (nhyp < 1 || T < 2 || T > 2048) return -1;
+    int64_t b = align_up(nhyp * T * T * 8, 256) + align_up(nhyp * T * 8, 256);
+    if (T > EP_SMEM_MAX_T) b += align_up(nhyp * T * T * T * 8, 256);
+    return b;
+}
+
+// Batched EP: mean (nhyp, T), cov (nhyp, T, T) -> post_mean (nhyp, T, T), post_cov (nhyp, T, T, T): row j of the
+// outputs is the EP approximation of N(mean, cov) conditioned on test point j being the maximizer.
+extern "C" int tes_ep_moments_f64(const double* mean, const double* cov, int64_t nhyp, int64_t T, double resolution,
+                                  int max_niter, double* post_mean, double* post_cov, int* niter, void* ws,
+                                  int64_t ws_bytes, void* stream) {
+    if (!mean) return -1;
+    if (!cov) return -2;
+    if (nhyp < 1 || nhyp > 65535) return -3;
+    if (T < 2 || T > 2048) return -4;
+    if (max_niter < 0) return -6;
+    if (!post_mean) return -7;
+    if (!post_cov) return -8;
+    const int64_t need = tes_ep_moments_workspace_bytes(nhyp, T);
+    if (!ws || ws_bytes < need) return -100;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)ws;
+    double* inv_cov = (double*)base;
+    base += align_up(nhyp * T * T * 8, 256);
+    double* h = (double*)base;
+    base += align_up(nhyp * T * 8, 256);
+    double* gscratch = (double*)base;
+    const int in_smem = T <= EP_SMEM_MAX_T;
+    const size_t sm_prep = in_smem ? (size_t)T * T * 8 : 0;
+    const size_t sm_main = (in_smem ? (size_t)T * T * 8 : 0) + (size_t)7 * T * 8;
+    if (sm_prep > 48 * 1024)
+        TES_CUDA_OK(cudaFuncSetAttribute(ep_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_prep));
+    if (sm_main > 48 * 1024)
+        TES_CUDA_OK(cudaFuncSetAttribute(ep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_main));
+    // the prepare step reuses the first nhyp slots of the main kernel's scratch
+    ep_prepare_kernel<<<(unsigned)nhyp, EP_THREADS, sm_prep, st>>>(cov, mean, (int)T, inv_cov, h, gscratch, in_smem);
+    TES_LAUNCH_OK();
+    ep_kernel<<<dim3((unsigned)T, (unsigned)nhyp), EP_THREADS, sm_main, st>>>(mean, cov, inv_cov, h, (int)T, resolution,
+                                                                             max_niter, post_mean, post_cov, niter,
+                                                                             gscratch, in_smem);
+    TES_LAUNCH_OK();
+    return 0;
+}

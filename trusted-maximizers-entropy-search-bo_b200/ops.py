@@ -468,3 +468,26 @@ def rff_draw(X, Y, l, sigma, sigma0, randn_W, rand_b, randn_noise):
                             ptr(randn_noise), S, F, ptr(theta), ptr(W), ptr(b), ptr(ws), ws.numel(), stream_ptr())
     _lib.check(rc, "tes_rff_draw_f64")
     return theta, W, b
+
+
+def ep_moments(mean, cov, resolution=1e-9, max_niter=100, return_niter=False):
+    """ep.approximate_EP_np (ep.py:73-204) for every maximizer at once: mean (nhyp,T), cov (nhyp,T,T) ->
+    post_mean (nhyp,T,T), post_cov (nhyp,T,T,T) CUDA tensors."""
+    cov = dev(cov)
+    dv = cov.device
+    T = cov.shape[-1]
+    cov = cov.reshape(-1, T, T)
+    nhyp = cov.shape[0]
+    mean = dev(mean, dv).reshape(nhyp, T)
+    L = _lib.lib()
+    need = L.tes_ep_moments_workspace_bytes(nhyp, T)
+    if need < 0:
+        raise ValueError("invalid sizes for tes_ep_moments_f64: nhyp=%d T=%d" % (nhyp, T))
+    ws = WORKSPACE.get(need, dv)
+    pm = torch.empty((nhyp, T, T), dtype=torch.float64, device=dv)
+    pc = torch.empty((nhyp, T, T, T), dtype=torch.float64, device=dv)
+    nit = torch.empty((nhyp, T), dtype=torch.int32, device=dv)
+    rc = L.tes_ep_moments_f64(ptr(mean), ptr(cov), nhyp, T, float(resolution), int(max_niter), ptr(pm), ptr(pc),
+                              ptr(nit), ptr(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_ep_moments_f64")
+    return (pm, pc, nit) if return_niter else (pm, pc)

@@ -264,7 +264,7 @@ def get_testidxs_stats_host(nhyp, test_xs_np, test_means, test_covs, mode="sampl
             pm[i], pc[i] = empirical_approximation.bucket_empirical_stats(samples[:, keep], sel)
         else:
             for j in range(nk):
-                m, c = ep.approximate_EP_np(j, test_means[i].reshape(-1, 1), test_covs[i], resolution=1e-9,
+                m, c = ep.approximate_EP_host(j, test_means[i].reshape(-1, 1), test_covs[i], resolution=1e-9,
                                             max_niter=100)
                 pm[i, j] = m.squeeze()
                 pc[i, j] = c
@@ -327,16 +327,10 @@ def get_testidxs_stats(nhyp, test_xs_np, test_means, test_covs, mode="sample", n
     max_probs = max_probs / np.sum(max_probs, axis=1, keepdims=True)
     head = (_ret(xs_d, like), _ret(dev(max_probs, dv), like), _ret(means_d, like), _ret(covs_d, like))
     if mode == "ep":
-        from . import ep
-        m_h, c_h = means_d.cpu().numpy(), covs_d.cpu().numpy()
-        pm = np.zeros([nhyp, nk, nk])
-        pc = np.zeros([nhyp, nk, nk, nk])
-        for i in range(nhyp):
-            for j in range(nk):
-                m, c = ep.approximate_EP_np(j, m_h[i].reshape(-1, 1), c_h[i], resolution=1e-9, max_niter=100)
-                pm[i, j] = m.squeeze()
-                pc[i, j] = c
-        return head + (_ret(dev(pm, dv), like), _ret(dev(pc, dv), like))
+        if nk < 2:  # a single surviving test point has no half-space sites: the prior is the answer
+            return head + (_ret(means_d.reshape(nhyp, nk, nk), like), _ret(covs_d.reshape(nhyp, nk, nk, nk), like))
+        pm, pc = ops.ep_moments(means_d, covs_d, resolution=1e-9, max_niter=100)   # utils.py:1820-1825
+        return head + (_ret(pm, like), _ret(pc, like))
     K_all = max([int(sz.max()) if len(sz) else 1 for (_, _, _, _, sz) in per_hyp])
     outs0, outs1 = [], []
     for i, (samples, maxidx, counts_h, uniq, sizes) in enumerate(per_hyp):
