@@ -5,16 +5,18 @@ import torch
 from tes_b200 import ops
 torch.cuda.set_device(0)
 N, d, S, F, k = [int(a) for a in sys.argv[1:6]]
-npolys = [int(a) for a in sys.argv[6:]] or [2]
+npolys = [a for a in sys.argv[6:]] or ["1"]   # "npoly" or "npoly:pc" (pc = polynomial columns of the specialised variant)
 g = torch.Generator(device="cuda").manual_seed(1)
 cand = torch.rand(N, d, dtype=torch.float64, device="cuda", generator=g)
 W = torch.randn(S, F, d, dtype=torch.float64, device="cuda", generator=g) * 1.5
 b = torch.rand(S, F, dtype=torch.float64, device="cuda", generator=g) * 6.283
 th = torch.randn(S, F, dtype=torch.float64, device="cuda", generator=g)
 ref = ops.rff_topk(cand, W, b, th, 1.4, k, method=3)
-for m, npoly in [(3, None)] + [(4, n) for n in npolys]:
+for m, npoly in [(3, None)] + [((5, n[1:]) if n.startswith('t') else (4, n)) for n in npolys]:
     if npoly is not None:
-        os.environ["TES_TC5_NPOLY"] = str(npoly)
+        np_, _, pc_ = str(npoly).partition(":")
+        os.environ["TES_TC5_NPOLY"] = np_
+        os.environ["TES_TC5_PC"] = pc_ or "0"
     r = ops.rff_topk(cand, W, b, th, 1.4, k, method=m); torch.cuda.synchronize()
     best = 1e9
     for _ in range(3):

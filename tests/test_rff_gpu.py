@@ -119,7 +119,7 @@ def test_bad_arguments_raise():
     (40_000, 6, 12, 160, 3, True, 3.0),      # shared W
     (3_000, 6, 7, 64, 3, False, 3.0),        # small N, screen forced
 ])
-@pytest.mark.parametrize("method", [2, 3])
+@pytest.mark.parametrize("method", [2, 3, 4, 5])
 def test_screened_topk_bit_identical(N, d, S, F, k, shared, scale, method):
     import torch
     from oracle import c_oracle as co
@@ -134,7 +134,7 @@ def test_screened_topk_bit_identical(N, d, S, F, k, shared, scale, method):
         np.testing.assert_array_equal(v2.cpu().numpy(), rval)
 
 
-@pytest.mark.parametrize("method", [2, 3])
+@pytest.mark.parametrize("method", [2, 3, 4, 5])
 def test_screened_topk_handles_exact_ties_and_overflow(method):
     """(a) duplicated candidates: exact fp64 ties, the lower index must win; (b) a constant function sample
     (theta = 0) makes EVERY candidate tie, the kept list overflows its 16 slots and the flag-gated fp64
@@ -154,7 +154,7 @@ def test_screened_topk_handles_exact_ties_and_overflow(method):
         assert i2[j, 1] == i2[j, 0] + 20_000 and i2[j, 3] == i2[j, 2] + 20_000
 
 
-@pytest.mark.parametrize("method", [2, 3])
+@pytest.mark.parametrize("method", [2, 3, 4, 5])
 def test_screened_topk_near_ties_many_seeds(method):
     """Stress: dense candidate clouds around one point make thousands of near-ties within the fp32 bound."""
     import torch
@@ -192,7 +192,7 @@ def test_cosf_error_model_exhaustive():
     assert float(out.cpu()[0]) < 4.5e-7
 
 
-@pytest.mark.parametrize("method", [2, 3])
+@pytest.mark.parametrize("method", [2, 3, 4, 5])
 def test_screened_topk_large_arguments_use_reduction_path(method):
     """|W x + b| far beyond the verified __cosf domain: the per-sample mode switches to the explicit 2*pi
     reduction; results stay bit-identical."""

@@ -1289,6 +1289,7 @@ __global__ void __launch_bounds__(32 * REFINE_WARPS)
 }
 
 #include "rff_tc5.cuh"
+#include "rff_tc5t.cuh"
 
 struct RffPlan {
     int C, threads, unroll, tile, sg, rec;
@@ -1311,7 +1312,8 @@ static size_t rff_smem_fp64(int rec, int sg, int k, int tile) {
 }
 
 // method: 0 = auto, 1 = fp64 only, 2 = packed-fp32 screen + fp64 refine, 3 = tensor-core (3xTF32 mma.sync) screen +
-// fp64 refine, 4 = tcgen05/TMEM (3xTF32) screen + fp64 refine (2/3/4 only when the shape allows it)
+// fp64 refine, 4 = tcgen05/TMEM (3xTF32) screen + fp64 refine, 5 = the same with the transposed (feature-major)
+// accumulator layout (2..5 only when the shape allows it)
 static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int method) {
     RffPlan p{};
     p.C = 4;
@@ -1329,8 +1331,8 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
     p.recp = scr_recp((int)d);
     const bool can_screen = d <= RFF_MAX_D_FAST && k <= SCR_MAX_K && N >= 1;
     p.screened = 0;
-    if (can_screen && (method == 2 || method == 3 || method == 4 || (method == 0 && N >= SCR_MIN_N)))
-        p.screened = (method == 4 || (method == 0 && d >= 5)) ? 3 : (method == 3 ? 2 : 1);
+    if (can_screen && (method >= 2 || (method == 0 && N >= SCR_MIN_N)))
+        p.screened = method == 5 ? 4 : ((method == 4 || (method == 0 && d >= 5)) ? 3 : (method == 3 ? 2 : 1));
     if (p.screened) {
         p.C = 4;
         p.threads = 256;
@@ -1343,13 +1345,23 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
         p.tile = 8 * rt * 16;
     }
     if (p.screened == 3) p.tile = TC5_TILE;
+    if (p.screened == 4) p.tile = T5T_TILE;
     int64_t ntiles = (N + p.tile - 1) / p.tile;
     if (ntiles < 1) ntiles = 1;
     int64_t tpc = ntiles < 16 ? ntiles : 16;  // tiles per chunk
     int64_t sg = S < 32 ? S : 32;
+    if (p.screened >= 3) {
+        // tcgen05 screen: a CTA holds its candidate tile while a sample group streams past; 8-sample groups quarter the
+        // CTA duration (finer wave quantisation: 13.4 -> 53.6 waves at C3, measured -4 %) at the cost of more tile
+        // conversions
+        int sgt = 8;
+        if (const char* v = getenv("TES_TC5_SG")) sscanf(v, "%d", &sgt);  // developer knob
+        if (sgt >= 1 && sgt <= 32 && S > sgt) sg = sgt;
+    }
     auto units = [&]() { return ((ntiles + tpc - 1) / tpc) * ((S + sg - 1) / sg); };
     const int64_t want = 8 * 148;
     if (p.screened >= 2) tpc = ntiles < 32 ? ntiles : 32;
+    if (p.screened == 4) tpc = ntiles < 64 ? ntiles : 64;  // 256-row tiles: same 16 384-candidate chunks
     while (units() < want && tpc > 4) tpc = (tpc + 1) / 2;
     while (units() < want && sg > 1) sg = (sg + 1) / 2;
     while (units() < want && tpc > 1) tpc = (tpc + 1) / 2;
@@ -1379,8 +1391,17 @@ static RffPlan rff_plan(int64_t N, int64_t d, int64_t S, int64_t F, int k, int m
             const int64_t sf = tc5_stage_floats(kc);
             p.feat32_bytes = align_up(S * ((F + TC5_NF - 1) / TC5_NF) * sf * (int64_t)sizeof(float), 256);
             p.smem_screen = (size_t)TC5_MT * kc * 128 * 16 + (size_t)TC5_NSTAGE * sf * sizeof(float) +
-                            (2 * TC5_NSTAGE + 10) * sizeof(uint64_t) + 2 * TC5_TILE * sizeof(double) +
+                            (2 * TC5_NSTAGE + 10) * sizeof(uint64_t) + 4 * TC5_TILE * sizeof(double) +
                             (size_t)p.sg * k * 16 + (size_t)(TC5_TILE + 16) * 16 + (size_t)p.sg * sizeof(int) + 16;
+        }
+        if (p.screened == 4) {
+            const int kc = tc5_kc((int)d);
+            const int64_t sf = t5t_stage_floats(kc);
+            p.feat32_bytes = align_up(S * ((F + T5T_NF - 1) / T5T_NF) * sf * (int64_t)sizeof(float), 256);
+            p.smem_screen = (size_t)kc * T5T_TILE * 16 + (size_t)T5T_NSTAGE * sf * sizeof(float) +
+                            (2 * T5T_NSTAGE + 10) * sizeof(uint64_t) + 8 * T5T_TILE * sizeof(float) +
+                            T5T_TILE * sizeof(double) + (size_t)p.sg * k * 16 + (size_t)(T5T_TILE + 16) * 16 +
+                            (size_t)p.sg * sizeof(int) + 16;
         }
         p.aux_bytes = align_up(64 * 8, 256) + 2 * align_up(S * 8, 256);  // xmax[64], bound[S], mode[S]
         p.flags_bytes = align_up(p.nchunks * S * (int64_t)sizeof(int), 256);
@@ -1491,19 +1512,48 @@ static int launch_rff_screen_mma(const RffPlan& p, const double* cand, int64_t N
 static int launch_rff_screen_tc5(const RffPlan& p, const double* cand, int64_t N, int d, const float* featt, int64_t S,
                                  int64_t F, double scale, int k, int64_t idx_offset, const double* bound,
                                  const int* mode, double* slot_val, int64_t* slot_idx, int* flags, cudaStream_t st) {
-    int np = TC5_NPOLY;
-    if (const char* v = getenv("TES_TC5_NPOLY")) sscanf(v, "%d", &np);  // developer knob (needs the dev build)
+    int np = TC5_NPOLY, pc = TC5_PC;
+    if (const char* v = getenv("TES_TC5_NPOLY")) sscanf(v, "%d", &np);  // developer knobs (need the dev build)
+    if (const char* v = getenv("TES_TC5_PC")) sscanf(v, "%d", &pc);
     void (*kern)(const double*, int64_t, int, const float*, int, int, int, double, int, int, int64_t, int64_t,
-                 const double*, const int*, double*, int64_t*, int, int*) = rff_screen_tc5_kernel<TC5_NPOLY>;
+                 const double*, const int*, double*, int64_t*, int, int*) = rff_screen_tc5_kernel<TC5_NPOLY, TC5_PC>;
+    int threads = TC5_PC > 0 ? TC5_THREADS_SPEC : TC5_THREADS;
 #ifdef TES_RFF_DEV_VARIANTS
-    if (np == 0) kern = rff_screen_tc5_kernel<0>;
-    if (np == 1) kern = rff_screen_tc5_kernel<1>;
-    if (np == 2) kern = rff_screen_tc5_kernel<2>;
-    if (np == 3) kern = rff_screen_tc5_kernel<3>;
-    if (np == 4) kern = rff_screen_tc5_kernel<4>;
+    threads = pc > 0 ? TC5_THREADS_SPEC : TC5_THREADS;
+    if (pc == 0) {
+        if (np == 0) kern = rff_screen_tc5_kernel<0, 0>;
+        if (np == 1) kern = rff_screen_tc5_kernel<1, 0>;
+        if (np == 2) kern = rff_screen_tc5_kernel<2, 0>;
+    }
+    if (pc == 8) kern = rff_screen_tc5_kernel<0, 8>;
+    if (pc == -2) kern = np ? rff_screen_tc5_kernel<1, -2> : rff_screen_tc5_kernel<0, -2>;
+    if (pc == -3) kern = np ? rff_screen_tc5_kernel<1, -3> : rff_screen_tc5_kernel<0, -3>;
+    if (pc == -4) kern = np ? rff_screen_tc5_kernel<1, -4> : rff_screen_tc5_kernel<0, -4>;
+    if (pc == -6) kern = np ? rff_screen_tc5_kernel<1, -6> : rff_screen_tc5_kernel<0, -6>;
+    if (pc == 16) kern = rff_screen_tc5_kernel<0, 16>;
 #endif
     TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_screen));
-    kern<<<(unsigned)p.nunits_screen, TC5_THREADS, p.smem_screen, st>>>(
+    kern<<<(unsigned)p.nunits_screen, threads, p.smem_screen, st>>>(
+        cand, N, d, featt, tc5_kc(d), (int)S, (int)F, scale, k, p.sg_screen, p.chunk, idx_offset, bound, mode, slot_val,
+        slot_idx, p.slot_stride, flags);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
+static int launch_rff_screen_tc5t(const RffPlan& p, const double* cand, int64_t N, int d, const float* featt,
+                                  int64_t S, int64_t F, double scale, int k, int64_t idx_offset, const double* bound,
+                                  const int* mode, double* slot_val, int64_t* slot_idx, int* flags, cudaStream_t st) {
+    int np = 1;
+    if (const char* v = getenv("TES_TC5_NPOLY")) sscanf(v, "%d", &np);  // developer knob (needs the dev build)
+    void (*kern)(const double*, int64_t, int, const float*, int, int, int, double, int, int, int64_t, int64_t,
+                 const double*, const int*, double*, int64_t*, int, int*) = rff_screen_tc5t_kernel<1>;
+#ifdef TES_RFF_DEV_VARIANTS
+    if (np == 0) kern = rff_screen_tc5t_kernel<0>;
+    if (np == 2) kern = rff_screen_tc5t_kernel<2>;
+    if (np == 3) kern = rff_screen_tc5t_kernel<3>;
+#endif
+    TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_screen));
+    kern<<<(unsigned)p.nunits_screen, T5T_THREADS, p.smem_screen, st>>>(
         cand, N, d, featt, tc5_kc(d), (int)S, (int)F, scale, k, p.sg_screen, p.chunk, idx_offset, bound, mode, slot_val,
         slot_idx, p.slot_stride, flags);
     TES_LAUNCH_OK();
@@ -1525,7 +1575,7 @@ static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* 
     if (k < 1 || k > RFF_MAX_K) return -11;
     if (!out_idx) return -13;
     if (!out_val) return -14;
-    if (method < 0 || method > 4) return -18;
+    if (method < 0 || method > 5) return -18;
     RffPlan p = rff_plan(N, d, S, F, k, method);
     if (!ws || ws_bytes < p.total_bytes) return -100;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1559,11 +1609,20 @@ static int rff_topk_run(const double* cand, int64_t N, int64_t d, const double* 
         rff_xmax_kernel<<<148 * 4, 256, 0, st>>>(cand, N, (int)d, xmax);
         TES_LAUNCH_OK();
         int rc = 0;
-        if (p.screened == 3) {
+        if (p.screened == 4) {
+            const int64_t nrow = S * ((F + T5T_NF - 1) / T5T_NF) * T5T_NF;
+            rff_bound_kernel<<<(unsigned)S, 32, 0, st>>>(feat, p.rec, S, F, (int)d, xmax, scale, MMA_HARG, bound, mode);
+            TES_LAUNCH_OK();
+            rff_pack_tc5_kernel<T5T_NF><<<(unsigned)((nrow + 255) / 256), 256, 0, st>>>(
+                W, b, theta, S, F, (int)d, w_shared, tc5_kc((int)d), (float*)feat32);
+            TES_LAUNCH_OK();
+            rc = launch_rff_screen_tc5t(p, cand, N, (int)d, (const float*)feat32, S, F, scale, k, idx_offset, bound,
+                                        mode, part_val, part_idx, flags, st);
+        } else if (p.screened == 3) {
             const int64_t nrow = S * ((F + TC5_NF - 1) / TC5_NF) * TC5_NF;
             rff_bound_kernel<<<(unsigned)S, 32, 0, st>>>(feat, p.rec, S, F, (int)d, xmax, scale, MMA_HARG, bound, mode);
             TES_LAUNCH_OK();
-            rff_pack_tc5_kernel<<<(unsigned)((nrow + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, (int)d, w_shared,
+            rff_pack_tc5_kernel<TC5_NF><<<(unsigned)((nrow + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, (int)d, w_shared,
                                                                                  tc5_kc((int)d), (float*)feat32);
             TES_LAUNCH_OK();
             rc = launch_rff_screen_tc5(p, cand, N, (int)d, (const float*)feat32, S, F, scale, k, idx_offset, bound, mode,
@@ -1663,7 +1722,7 @@ extern "C" int64_t tes_rff_topk_workspace_bytes(int64_t N, int64_t d, int64_t S,
     if (N < 0 || d < 1 || d > 64 || S < 1 || F < 1 || k < 1 || k > RFF_MAX_K) return -1;
     // large enough for every method
     int64_t best = 0;
-    for (int m = 1; m <= 4; ++m) {
+    for (int m = 1; m <= 5; ++m) {
         int64_t v = rff_plan(N, d, S, F, k, m).total_bytes;
         if (v > best) best = v;
     }

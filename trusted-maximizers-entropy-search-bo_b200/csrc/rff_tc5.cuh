@@ -24,6 +24,8 @@
 constexpr int TC5_EPI_WARPS = 16;
 constexpr int TC5_EPI_THREADS = 32 * TC5_EPI_WARPS;
 constexpr int TC5_THREADS = 64 + TC5_EPI_THREADS + 32;
+constexpr int TC5_POLY_WARPS = 4;           // warp-specialised variant: one FMA-pipe cosine warp per TMEM lane quarter
+constexpr int TC5_THREADS_SPEC = TC5_THREADS + 32 * TC5_POLY_WARPS;
 constexpr int TC5_MT = 4;                   // candidate tiles of 128 rows per CTA tile
 constexpr int TC5_TILE = 128 * TC5_MT;      // candidates per CTA tile
 constexpr int TC5_NF = 64;                  // features per MMA tile = TMEM columns per candidate tile
@@ -32,6 +34,7 @@ constexpr int TC5_MAX_KC = 8;               // K <= 32 (3d + 2 <= 32 <=> d <= 10
 #ifndef TC5_SLEEP_NS
 #define TC5_SLEEP_NS 64
 #endif
+constexpr int TC5_PC = 0;                   // default: mixed epilogue (set to 16/24 for the warp-specialised variant)
 constexpr int TC5_NPOLY = 1;                // pairs of every 8 whose cosine runs on the FMA pipe
 
 __host__ __device__ constexpr int tc5_kc(int d) { return (((3 * d + 2 + 3) / 4) + 1) & ~1; }  // 16-byte K chunks, even
@@ -79,6 +82,17 @@ __host__ __device__ constexpr uint32_t tc5_idesc(int m, int n) {
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),     \
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])      \
         : "r"(taddr))
+#define TC5_LD16(v, taddr)                                                                                            \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, "  \
+                 "[%16];"                                                                                             \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),    \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),           \
+                   "=r"(v[15])                                                                                        \
+                 : "r"(taddr))
+#define TC5_LD8(v, taddr)                                                                                             \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                            \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])     \
+                 : "r"(taddr))
 __device__ __forceinline__ void tc5_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- operand values (runtime d) --------------------------------------------------------------------------------
@@ -116,17 +130,18 @@ __device__ __forceinline__ void tc5_store_a_row(float* sA, int rows, int row, co
 }
 
 // feature tiles in operand order: featt[(j * nft + ft) * stage_floats]: [KC chunks][64 rows][4 floats], theta[64]
+template <int NF>
 __global__ void rff_pack_tc5_kernel(const double* __restrict__ W, const double* __restrict__ b,
                                     const double* __restrict__ theta, int64_t S, int64_t F, int d, int w_shared,
                                     int kc, float* __restrict__ featt) {
-    const int64_t nft = (F + TC5_NF - 1) / TC5_NF;
+    const int64_t nft = (F + NF - 1) / NF;
     const int64_t t_ = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t_ >= S * nft * TC5_NF) return;
-    const int row = (int)(t_ % TC5_NF);
-    const int64_t tile = t_ / TC5_NF, ft = tile % nft, j = tile / nft;
+    if (t_ >= S * nft * NF) return;
+    const int row = (int)(t_ % NF);
+    const int64_t tile = t_ / NF, ft = tile % nft, j = tile / nft;
     const int64_t jw = w_shared ? 0 : j;
-    const int64_t f = ft * TC5_NF + row;
-    float* base = featt + tile * tc5_stage_floats(kc);
+    const int64_t f = ft * NF + row;
+    float* base = featt + tile * (kc * NF * 4 + NF);
     for (int c = 0; c < kc; ++c) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (f < F) {
@@ -137,9 +152,9 @@ __global__ void rff_pack_tc5_kernel(const double* __restrict__ W, const double* 
             v.z = tc5_bval(w, bb, d, 4 * c + 2);
             v.w = tc5_bval(w, bb, d, 4 * c + 3);
         }
-        *reinterpret_cast<float4*>(base + (c * TC5_NF + row) * 4) = v;
+        *reinterpret_cast<float4*>(base + (c * NF + row) * 4) = v;
     }
-    base[kc * TC5_NF * 4 + row] = f < F ? __double2float_rn(theta[j * F + f]) : 0.0f;
+    base[kc * NF * 4 + row] = f < F ? __double2float_rn(theta[j * F + f]) : 0.0f;
 }
 
 // 32 accumulator columns of one candidate: cosine (MUFU for most pairs, FMA-pipe polynomial for NPOLY of every 8
@@ -171,6 +186,40 @@ __device__ __forceinline__ void tc5_consume32(const uint32_t (&v)[32], uint32_t 
     }
 }
 
+// NC accumulator columns (NC % 4 == 0) of one candidate, all on the MUFU (POLY = false) or all as the packed FMA-pipe
+// polynomial (POLY = true; it reduces the argument itself), multiply-add with theta into NA packed accumulators
+template <int NC, bool POLY, bool REDUCE, int NA>
+__device__ __forceinline__ void tc5_consume_n(const uint32_t* v, uint32_t th_addr, uint64_t (&acc)[NA]) {
+    const uint64_t INV2PI2 = f2_pack(0.15915494f, 0.15915494f);
+    const uint64_t MAGIC2 = f2_pack(12582912.0f, 12582912.0f);
+    const uint64_t NMAGIC2 = f2_pack(-12582912.0f, -12582912.0f);
+    const uint64_t NTWOPI2 = f2_pack(-6.2831855f, -6.2831855f);
+#pragma unroll
+    for (int q = 0; q < NC / 4; ++q) {
+        uint64_t t01, t23;
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(t01), "=l"(t23) : "r"(th_addr + 16u * q));
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int p = 2 * q + e;
+            uint64_t h2 = ((uint64_t)v[2 * p + 1] << 32) | (uint64_t)v[2 * p];
+            uint64_t c2;
+            if (POLY) {
+                c2 = cos_poly2(h2);
+            } else {
+                if (REDUCE) h2 = ffma2(fadd2(ffma2(h2, INV2PI2, MAGIC2), NMAGIC2), NTWOPI2, h2);
+                c2 = f2_pack(__cosf(f2_lo(h2)), __cosf(f2_hi(h2)));
+            }
+            acc[p % NA] = ffma2(e == 0 ? t01 : t23, c2, acc[p % NA]);
+        }
+    }
+}
+__device__ __forceinline__ double tc5_flush2(uint64_t (&acc)[2]) {
+    const uint64_t s = fadd2(acc[0], acc[1]);
+    const float r = f2_lo(s) + f2_hi(s);
+    acc[0] = acc[1] = 0ull;
+    return (double)r;
+}
+
 __device__ __forceinline__ double tc5_flush(uint64_t (&acc)[4]) {
     // tree sum of the 8 fp32 lanes (3 roundings), one conversion, one DADD per flush
     const uint64_t s01 = fadd2(acc[0], acc[1]), s23 = fadd2(acc[2], acc[3]);
@@ -182,15 +231,17 @@ __device__ __forceinline__ double tc5_flush(uint64_t (&acc)[4]) {
 
 // One warp screens the TC5_TILE values u[] (candidates base .. base + TILE, -inf where invalid) of sample jj: keep every
 // candidate within 2 B_j of max(k-th largest of the 32 lane maxima, running k-th best of the chunk).
+template <int TILE = TC5_TILE>
 __device__ __forceinline__ void screen_commit_warp(const ScreenCtx& cx, int jj, const double* __restrict__ u,
-                                                   int64_t base, int lane) {
-    constexpr int PER = TC5_TILE / 32;
+                                                   const double* __restrict__ u2, int64_t base, int lane) {
+    constexpr int PER = TILE / 32;
     const int k = cx.k;
     double v[PER];
     double lmax = neg_inf();
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
         v[q] = u[q * 32 + lane];
+        if (u2) v[q] += u2[q * 32 + lane];  // part of the sum computed by the FMA-pipe cosine warps
         lmax = fmax(lmax, v[q]);
     }
     // k-th largest (with multiplicity) of the lane maxima: a lower bound of the tile's k-th largest value
@@ -229,8 +280,12 @@ __device__ __forceinline__ void screen_commit_warp(const ScreenCtx& cx, int jj, 
     }
 }
 
-template <int NPOLY>
-__global__ void __launch_bounds__(TC5_THREADS, 1)
+// PC = 0: every epilogue warp mixes MUFU and polynomial cosines (NPOLY of every 8 pairs).  PC > 0 (warp-specialised):
+// the 16 epilogue warps take columns [0, 64 - PC) of their candidate tile on the MUFU only, and 4 extra warps (one per
+// TMEM lane quarter) take columns [64 - PC, 64) of all 4 candidate tiles with the polynomial only.  A warp issues in
+// order: in the mixed scheme a warp stalled on the full MUFU queue cannot reach its FMA-pipe work; dedicated warps can.
+template <int NPOLY, int PC>
+__global__ void __launch_bounds__(PC > 0 ? TC5_THREADS_SPEC : TC5_THREADS, 1)
     rff_screen_tc5_kernel(const double* __restrict__ cand, int64_t N, int d, const float* __restrict__ featt, int kc,
                           int S, int F, double scale, int k, int sg, int64_t chunk, int64_t idx_offset,
                           const double* __restrict__ bound, const int* __restrict__ mode,
@@ -249,7 +304,8 @@ __global__ void __launch_bounds__(TC5_THREADS, 1)
     uint64_t* u_full = a_ready + 1;                                      // [2] epilogue -> commit warp
     uint64_t* u_empty = u_full + 2;                                      // [2] commit warp -> epilogue
     double* ubuf = reinterpret_cast<double*>(bars + 2 * TC5_NSTAGE + 10);  // [2][TILE] screen values of a sample
-    double* tk_val = ubuf + 2 * TC5_TILE;
+    double* ubuf_p = ubuf + 2 * TC5_TILE;                                  // [2][TILE] polynomial-warp part of the sums
+    double* tk_val = ubuf_p + 2 * TC5_TILE;
     int64_t* tk_idx = reinterpret_cast<int64_t*>(tk_val + sg * k);
     double* ap_val = reinterpret_cast<double*>(tk_idx + sg * k);          // [TILE + 16]
     int64_t* ap_idx = reinterpret_cast<int64_t*>(ap_val + TC5_TILE + 16);
@@ -273,33 +329,36 @@ __global__ void __launch_bounds__(TC5_THREADS, 1)
     const int nft = (F + TC5_NF - 1) / TC5_NF;
     const uint32_t stage_bytes = (uint32_t)(stage_floats * sizeof(float));
 
-    for (int e = tid; e < sg * k; e += TC5_THREADS) {
+    constexpr int NTHREADS = PC > 0 ? TC5_THREADS_SPEC : TC5_THREADS;
+    constexpr int NARRIVE = TC5_EPI_WARPS + (PC > 0 ? TC5_POLY_WARPS : 0);   // warps that read an accumulator stage / theta
+    constexpr int CM = TC5_NF - (PC > 0 ? PC : 0);                                       // MUFU columns per candidate tile
+    for (int e = tid; e < sg * k; e += NTHREADS) {
         tk_val[e] = neg_inf();
         tk_idx[e] = -1;
     }
-    for (int e = tid; e < nj * SCR_CAP; e += TC5_THREADS) {
+    for (int e = tid; e < nj * SCR_CAP; e += NTHREADS) {
         int64_t o = (chunk_id * S + j0 + e / SCR_CAP) * slot_stride + e % SCR_CAP;
         slot_idx[o] = -1;
         slot_val[o] = neg_inf();
     }
-    for (int e = tid; e < nj; e += TC5_THREADS) {
+    for (int e = tid; e < nj; e += NTHREADS) {
         slot_cnt[e] = 0;
         flags[chunk_id * S + j0 + e] = 0;
     }
-    for (int e = tid; e < TC5_MT * kc * 128 * 4; e += TC5_THREADS) sA[e] = 0.0f;  // K padding stays zero
+    for (int e = tid; e < TC5_MT * kc * 128 * 4; e += NTHREADS) sA[e] = 0.0f;  // K padding stays zero
     if (tid == 0) {
         *ap_count = 0;
         for (int s = 0; s < TC5_NSTAGE; ++s) {
             mbar_init(&full_b[s], 1);
-            mbar_init(&empty_b[s], TC5_EPI_WARPS);
+            mbar_init(&empty_b[s], NARRIVE);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], TC5_EPI_WARPS);
+            mbar_init(&tmem_empty[a], NARRIVE);
         }
         mbar_init(a_ready, TC5_EPI_WARPS);
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&u_full[a], TC5_EPI_WARPS);
+            mbar_init(&u_full[a], NARRIVE);
             mbar_init(&u_empty[a], 1);
         }
         mbar_fence_init();
@@ -368,10 +427,77 @@ __global__ void __launch_bounds__(TC5_THREADS, 1)
             for (int jj = 0; jj < nj; ++jj, ++sidx) {
                 const uint32_t ub = sidx & 1u, up = (sidx >> 1) & 1u;
                 mbar_wait_relaxed(&u_full[ub], up, TC5_SLEEP_NS);
-                screen_commit_warp(cx, jj, ubuf + ub * TC5_TILE, c0 + (int64_t)tile * TC5_TILE, lane);
+                screen_commit_warp(cx, jj, ubuf + ub * TC5_TILE, PC > 0 ? ubuf_p + ub * TC5_TILE : nullptr,
+                                   c0 + (int64_t)tile * TC5_TILE, lane);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&u_empty[ub]);
             }
+    } else if (PC > 0 && warp > 2 + TC5_EPI_WARPS) {
+        // ---------------- FMA-pipe cosine warps: thread = TMEM lane of its quarter, all 4 candidate tiles -----------
+        constexpr int PCC = PC > 0 ? PC : 16;
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + CM;
+        uint32_t sidx = 0, it = 0;
+        for (int tile = 0; tile < ntiles; ++tile) {
+            for (int jj = 0; jj < nj; ++jj, ++sidx) {
+                double dsum[TC5_MT] = {0.0, 0.0, 0.0, 0.0};
+                uint64_t acc[TC5_MT][2];
+#pragma unroll
+                for (int mt = 0; mt < TC5_MT; ++mt) acc[mt][0] = acc[mt][1] = 0ull;
+                for (int ft = 0; ft < nft; ++ft, ++it) {
+                    const uint32_t s = it % TC5_NSTAGE, ph = (it / TC5_NSTAGE) & 1u;
+                    const uint32_t a = it & 1u, pa = (it >> 1) & 1u;
+                    const uint32_t th = smem_u32(sB + s * stage_floats + kc * TC5_NF * 4) + CM * 4u;
+                    mbar_wait(&full_b[s], ph);
+                    mbar_wait(&tmem_full[a], pa);
+                    tc5_fence_after();
+                    const uint32_t taddr = t_lane + a * (TC5_MT * TC5_NF);
+#pragma unroll
+                    for (int mp = 0; mp < TC5_MT; mp += 2) {
+                        uint32_t va[PCC], vb[PCC];
+                        if (PCC == 8) {
+                            TC5_LD8(va, taddr + mp * TC5_NF);
+                            TC5_LD8(vb, taddr + (mp + 1) * TC5_NF);
+                        } else if (PCC == 16) {
+                            TC5_LD16(va, taddr + mp * TC5_NF);
+                            TC5_LD16(vb, taddr + (mp + 1) * TC5_NF);
+                        } else if (PCC == 24) {
+                            TC5_LD16(va, taddr + mp * TC5_NF);
+                            TC5_LD8((va + 16), taddr + mp * TC5_NF + 16);
+                            TC5_LD16(vb, taddr + (mp + 1) * TC5_NF);
+                            TC5_LD8((vb + 16), taddr + (mp + 1) * TC5_NF + 16);
+                        } else {
+                            TC5_LD32(va, taddr + mp * TC5_NF);
+                            TC5_LD32(vb, taddr + (mp + 1) * TC5_NF);
+                        }
+                        tc5_wait_ld();
+                        tc5_consume_n<PCC, true, false, 2>(va, th, acc[mp]);
+                        tc5_consume_n<PCC, true, false, 2>(vb, th, acc[mp + 1]);
+                    }
+                    tc5_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&tmem_empty[a]);
+                        mbar_arrive(&empty_b[s]);
+                    }
+                    if (ft & 1) {
+#pragma unroll
+                        for (int mt = 0; mt < TC5_MT; ++mt) dsum[mt] += tc5_flush2(acc[mt]);
+                    }
+                }
+                if (nft & 1) {
+#pragma unroll
+                    for (int mt = 0; mt < TC5_MT; ++mt) dsum[mt] += tc5_flush2(acc[mt]);
+                }
+                const uint32_t ub = sidx & 1u, up = (sidx >> 1) & 1u;
+                mbar_wait(&u_empty[ub], up ^ 1u);
+#pragma unroll
+                for (int mt = 0; mt < TC5_MT; ++mt) ubuf_p[ub * TC5_TILE + mt * 128 + row] = scale * dsum[mt];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&u_full[ub]);
+            }
+        }
     } else {
         // ---------------- epilogue: thread = candidate ----------------
         const int ew = warp - 2;
@@ -400,15 +526,59 @@ __global__ void __launch_bounds__(TC5_THREADS, 1)
                     mbar_wait(&tmem_full[a], pa);
                     tc5_fence_after();
                     const uint32_t taddr = t_lane + a * (TC5_MT * TC5_NF);
+                    if (PC < 0) {
+                        // time-alternating roles: this warp evaluates 1 of every -PC feature tiles entirely as the
+                        // FMA-pipe polynomial, staggered by candidate tile so that on every scheduler one warp is on
+                        // the FMA pipe while the others keep the MUFU queue full
+                        const bool poly_stage = ((it + (uint32_t)mt) % (uint32_t)(PC < 0 ? -PC : 1)) == 0u;
 #pragma unroll
-                    for (int cb = 0; cb < 2; ++cb) {
+                        for (int cb = 0; cb < 2; ++cb) {
+                            uint32_t v[32];
+                            TC5_LD32(v, taddr + cb * 32);
+                            tc5_wait_ld();
+                            if (poly_stage)
+                                tc5_consume_n<32, true, false, 4>(v, th + cb * 128u, acc);
+                            else if (red)
+                                tc5_consume32<NPOLY, true>(v, th + cb * 128u, acc);
+                            else
+                                tc5_consume32<NPOLY, false>(v, th + cb * 128u, acc);
+                        }
+                    } else if (PC == 0) {
+#pragma unroll
+                        for (int cb = 0; cb < 2; ++cb) {
+                            uint32_t v[32];
+                            TC5_LD32(v, taddr + cb * 32);
+                            tc5_wait_ld();
+                            if (red)
+                                tc5_consume32<NPOLY, true>(v, th + cb * 128u, acc);
+                            else
+                                tc5_consume32<NPOLY, false>(v, th + cb * 128u, acc);
+                        }
+                    } else {
+                        // columns [0, CM) on the MUFU only: 32 + (CM - 32)
                         uint32_t v[32];
-                        TC5_LD32(v, taddr + cb * 32);
+                        TC5_LD32(v, taddr);
                         tc5_wait_ld();
                         if (red)
-                            tc5_consume32<NPOLY, true>(v, th + cb * 128u, acc);
+                            tc5_consume_n<32, false, true, 4>(v, th, acc);
                         else
-                            tc5_consume32<NPOLY, false>(v, th + cb * 128u, acc);
+                            tc5_consume_n<32, false, false, 4>(v, th, acc);
+                        constexpr int R = CM > 32 ? CM - 32 : 8;
+                        if (CM > 32) {
+                            if (R == 8) {
+                                TC5_LD8(v, taddr + 32);
+                            } else if (R == 16) {
+                                TC5_LD16(v, taddr + 32);
+                            } else {
+                                TC5_LD16(v, taddr + 32);
+                                TC5_LD8((v + 16), taddr + 48);
+                            }
+                            tc5_wait_ld();
+                            if (red)
+                                tc5_consume_n<R, false, true, 4>(v, th + 128u, acc);
+                            else
+                                tc5_consume_n<R, false, false, 4>(v, th + 128u, acc);
+                        }
                     }
                     tc5_fence_before();
                     __syncwarp();

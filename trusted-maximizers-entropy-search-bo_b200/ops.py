@@ -19,7 +19,7 @@ def _rff_args(cand, W, b, theta):
     return cand, W, b, theta, N, d, S, F, w_shared
 
 
-RFF_AUTO, RFF_FP64, RFF_SCREEN, RFF_SCREEN_MMA, RFF_SCREEN_TC5 = 0, 1, 2, 3, 4
+RFF_AUTO, RFF_FP64, RFF_SCREEN, RFF_SCREEN_MMA, RFF_SCREEN_TC5, RFF_SCREEN_TC5T = 0, 1, 2, 3, 4, 5
 
 
 def rff_topk(cand, W, b, theta, sigma, k=1, idx_offset=0, method=RFF_AUTO):
