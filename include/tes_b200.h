@@ -188,6 +188,17 @@ int tes_rff_draw_f64(const double* X, const double* Y, int64_t n, int64_t d, con
                      int64_t S, int64_t F, double* theta, double* W, double* b, void* ws, int64_t ws_bytes,
                      void* stream);
 
+/* Gradient refinement of the trusted maximizers: utils_for_continuous.sample_xmaxs_fmaxs, second half
+ * (utils_for_continuous.py:201-232).  Every (function sample, start point) runs `ntrain` TF-1 Adam steps on
+ * -f_j(x) with the clip-to-[xmin, xmax] variable constraint applied after each step, all inside one launch.
+ *   x0 (S, k, d) start points; W (S or 1, F, d); b (S or 1, F); theta (S, F); xmin, xmax (d) device arrays;
+ *   out_x (S, k, d) refined points; out_f (S, k) the function-sample values there (the caller takes the arg-max over
+ *   k, first maximum, as :222-229 do).  TF-1 defaults: lr 1e-3, beta1 0.9, beta2 0.999, epsilon 1e-8.  d <= 16. */
+int tes_rff_adam_refine_f64(const double* x0, int64_t S, int k, int64_t d, const double* W, const double* b,
+                            const double* theta, int64_t F, int w_shared, double sigma, const double* xmin,
+                            const double* xmax, int ntrain, double lr, double beta1, double beta2, double epsilon,
+                            double* out_x, double* out_f, void* stream);
+
 /* ===================================================================================== Stage C
  * Trusted-maximizer statistics on the device.  The reference does all of this in host numpy
  * (utils.get_testidxs_stats, utils.py:1733-1833); here it stays next to the data so that one

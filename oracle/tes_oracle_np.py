@@ -225,6 +225,39 @@ def rff_fvals(x, theta, W, b, sigma):
     return out
 
 
+def adam_refine_maximizers(x0, theta, W, b, sigma, xmin, xmax, ntrain, lr=1e-3, beta1=0.9, beta2=0.999,
+                           epsilon=1e-8):
+    """utils_for_continuous.py:201-232: TF-1 AdamOptimizer() on -sum_{j,i} f_j(xs[j,i]) for `ntrain` steps with the
+    clip_by_value(xmin, xmax) variable constraint applied after every step.  x0 (S,k,d); theta (S,F,1);
+    W (S,F,d) or (1,F,d); b (S,F,1) or (1,F,1).  Returns (xs (S,k,d), fvals (S,k)).
+    TF-1 Adam (tensorflow/python/training/adam.py): lr_t = lr sqrt(1-beta2^t)/(1-beta1^t);
+    m <- beta1 m + (1-beta1) g; v <- beta2 v + (1-beta2) g^2; var <- var - lr_t m / (sqrt(v) + epsilon).
+    parity unpinned (TF graph code; no reference output available) -- this restatement is the authority."""
+    S, k, d = x0.shape
+    F = theta.shape[1]
+    scale = np.sqrt(2.0 * sigma / F)
+    th = theta.reshape(S, F)
+    xs = x0.copy()
+    m = np.zeros_like(xs)
+    v = np.zeros_like(xs)
+    lo = np.broadcast_to(np.asarray(xmin, dtype=np.float64), (d,))
+    hi = np.broadcast_to(np.asarray(xmax, dtype=np.float64), (d,))
+
+    def args(xs_):
+        Wb = np.broadcast_to(W, (S, F, d))
+        return np.einsum("jfc,jic->jif", Wb, xs_) + np.broadcast_to(b.reshape(-1, 1, F), (S, k, F))
+
+    for t in range(1, ntrain + 1):
+        h = args(xs)                                                        # (S,k,F)
+        g = scale * np.einsum("jif,jfc->jic", th[:, None, :] * np.sin(h), np.broadcast_to(W, (S, F, d)))
+        lr_t = lr * np.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+        m = beta1 * m + (1.0 - beta1) * g
+        v = beta2 * v + (1.0 - beta2) * g * g
+        xs = np.clip(xs - lr_t * m / (np.sqrt(v) + epsilon), lo, hi)
+    fvals = scale * np.sum(th[:, None, :] * np.cos(args(xs)), axis=2)
+    return xs, fvals
+
+
 def top_k_lowest_index(v, k):
     """tf.math.top_k semantics: descending value, ties -> lower index first."""
     order = np.lexsort((np.arange(v.shape[0]), -v))

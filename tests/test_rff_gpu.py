@@ -228,3 +228,46 @@ def test_mma_split_precision_argument_error(d):
         _lib.check(_lib.lib().tes_mma_arg_error_probe(ptr(x), ptr(w), ptr(b), d, n8, ptr(out), stream_ptr()), "probe")
         worst = max(worst, float(out.cpu()[0]))
     assert 0.0 < worst < 3.0e-6, worst
+
+
+# ---- Adam refinement of the trusted maximizers (csrc/rffopt.cu, utils_for_continuous.py:201-232) -----------------
+@pytest.mark.parametrize("S,k,d,F,ntrain,shared", [(5, 3, 2, 300, 50, False), (4, 5, 6, 128, 120, False),
+                                                   (3, 2, 10, 64, 30, True), (2, 1, 1, 32, 10, False)])
+def test_adam_refinement_matches_oracle(S, k, d, F, ntrain, shared):
+    from oracle import tes_oracle_np as onp
+    from tes_b200 import ops
+    rs = np.random.RandomState(S * 100 + d)
+    x0 = rs.rand(S, k, d)
+    x0[0, 0] = 0.999                                   # starts next to the upper bound: exercises the clip constraint
+    W = rs.randn(1 if shared else S, F, d) * 2.0
+    b = rs.rand(1 if shared else S, F, 1) * 2 * np.pi
+    theta = rs.randn(S, F, 1)
+    rx, rf = onp.adam_refine_maximizers(x0, theta, W, b, 1.3, 0.0, 1.0, ntrain)
+    gx, gf = ops.rff_adam_refine(x0, W, b, theta, 1.3, 0.0, 1.0, ntrain)
+    # fp64 both sides, different summation order over the F features: 1e-9 after `ntrain` steps (tolerance of the
+    # refinement: the step size itself is 1e-3)
+    np.testing.assert_allclose(gx.cpu().numpy(), rx, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(gf.cpu().numpy(), rf, rtol=0, atol=1e-9 * max(1.0, np.abs(rf).max()))
+    assert gx.min() >= 0.0 and gx.max() <= 1.0
+    # ascent: the refined values are not below the starting values (Adam with lr 1e-3 on a smooth function)
+    f0 = onp.adam_refine_maximizers(x0, theta, W, b, 1.3, 0.0, 1.0, 0)[1]
+    assert np.all(gf.cpu().numpy() >= f0 - 1e-6)
+
+
+def test_sample_xmaxs_fmaxs_with_refinement_end_to_end():
+    """Top-k over the initialisers + Adam refinement + arg-max over k through the reference-named entry point."""
+    from oracle import tes_oracle_np as onp
+    from tes_b200 import utils_for_continuous as ufc
+    rs = np.random.RandomState(3)
+    d, S, F, k = 2, 6, 100, 3
+    init = rs.rand(500, d)
+    W, b, theta = rs.randn(1, S, F, d) * 3.0, rs.rand(1, S, F, 1) * 6.28, rs.randn(1, S, F, 1)
+    inits, max_xs, max_fs, top_idx, xs = ufc.sample_xmaxs_fmaxs(d, 1, S, F, None, np.array([0.8]), None, theta, W, b, init,
+                                                               k, xmin=0.0, xmax=1.0, get_xs=True, ntrain=80)
+    ridx, _ = onp.rff_topk(init, theta[0], W[0], b[0], 0.8, k)
+    np.testing.assert_array_equal(top_idx[0], ridx)
+    rx, rf = onp.adam_refine_maximizers(init[ridx], theta[0], W[0], b[0], 0.8, 0.0, 1.0, 80)
+    best = np.argmax(rf, axis=1)
+    np.testing.assert_allclose(xs[0], rx, atol=1e-9)
+    np.testing.assert_allclose(max_xs[0], rx[np.arange(S), best], atol=1e-9)
+    np.testing.assert_allclose(max_fs[0], rf[np.arange(S), best], atol=1e-9)

@@ -74,6 +74,8 @@ SIGNATURES = {
     "tes_uniform_fill_f64": (c_int, [c_u64, ctypes.c_uint32, ctypes.c_uint32, c_u64, c_i64, c_ptr, c_ptr]),
     "tes_ep_moments_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "tes_ep_moments_f64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "tes_rff_adam_refine_f64": (c_int, [c_ptr, c_i64, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_dbl, c_ptr,
+                                        c_ptr, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr]),
     "tes_normal_fill_f64": (c_int, [c_u64, ctypes.c_uint32, ctypes.c_uint32, c_u64, c_i64, c_ptr, c_ptr]),
     "tes_dedup_f64": (c_int, [c_ptr, c_i64, c_i64, c_dbl, c_ptr, c_ptr, c_ptr]),
     "tes_sym_eig_workspace_bytes": (c_i64, [c_i64, c_i64]),

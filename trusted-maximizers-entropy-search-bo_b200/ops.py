@@ -1,4 +1,5 @@
 """Thin typed wrappers over the C ABI (include/tes_b200.h) for CUDA torch tensors."""
+import numpy as np
 import torch
 
 from . import _lib
@@ -491,3 +492,27 @@ def ep_moments(mean, cov, resolution=1e-9, max_niter=100, return_niter=False):
                               ptr(nit), ptr(ws), ws.numel(), stream_ptr())
     _lib.check(rc, "tes_ep_moments_f64")
     return (pm, pc, nit) if return_niter else (pm, pc)
+
+
+def rff_adam_refine(x0, W, b, theta, sigma, xmin, xmax, ntrain, lr=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8):
+    """utils_for_continuous.py:201-232: `ntrain` TF-1 Adam steps on every (sample, start point) -> refined points
+    (S,k,d) and their function-sample values (S,k), CUDA tensors."""
+    x0 = dev(x0)
+    S, k, d = x0.shape
+    dv = x0.device
+    theta = dev(theta, dv).reshape(S, -1)
+    F = theta.shape[1]
+    W = dev(W, dv).reshape(-1, F, d)
+    b = dev(b, dv).reshape(-1, F)
+    if W.shape[0] not in (1, S) or b.shape[0] != W.shape[0]:
+        raise ValueError("W must be (S,F,d) or (1,F,d) and b must match")
+    lo = dev(np.broadcast_to(np.asarray(xmin, dtype=np.float64), (d,)).copy(), dv)
+    hi = dev(np.broadcast_to(np.asarray(xmax, dtype=np.float64), (d,)).copy(), dv)
+    out_x = torch.empty_like(x0)
+    out_f = torch.empty((S, k), dtype=torch.float64, device=dv)
+    rc = _lib.lib().tes_rff_adam_refine_f64(ptr(x0), S, k, d, ptr(W), ptr(b), ptr(theta), F,
+                                            int(W.shape[0] == 1 and S > 1), float(sigma), ptr(lo), ptr(hi), int(ntrain),
+                                            float(lr), float(beta1), float(beta2), float(epsilon), ptr(out_x),
+                                            ptr(out_f), stream_ptr())
+    _lib.check(rc, "tes_rff_adam_refine_f64")
+    return out_x, out_f
