@@ -69,7 +69,6 @@ WORKLOADS = {
 
 def make_workload(name, rank, world, host_only=False):
     desc, d, N, S, F, n, t_max = WORKLOADS[name]
-    from tes_b200 import optfunc
     hyp = HART6 if d == 6 else dict(l=np.array([177.9418631280815, 309.4630784148164]), sigma=0.29444226420446995,
                                     sigma0=0.06476473751595126)
     rs = np.random.RandomState(1)
@@ -86,10 +85,17 @@ def make_workload(name, rank, world, host_only=False):
     else:
         cand = np.random.RandomState(7 + rank).rand(N, d)
     np.random.seed(11)  # identical draws on every rank
-    # the RFF posterior weight draw (optfunc.py:303-385): on the device for the b200 arm, host numpy (where the
-    # reference runs it) for the CPU reference arm; same np.random draws either way
-    draw = optfunc.draw_random_init_weights_features_host if host_only else optfunc.draw_random_init_weights_features_np
-    theta, W, b = draw(d, S, F, X, Y, hyp["l"].reshape(1, d), hyp["sigma"], hyp["sigma0"])
+    # the RFF posterior weight draw (optfunc.py:303-385): on the device for the b200 arm; the CPU reference arm runs
+    # the oracle's numpy restatement (where the reference runs it).  Same np.random draws, same order, either way.
+    randn_W, rand_b, noise = np.random.randn(S, F, d), np.random.rand(S, F, 1), np.random.randn(S, F, 1)
+    if host_only:
+        from oracle import tes_oracle_np as onp
+        theta, W, b = onp.draw_random_init_weights_features(d, S, F, X, Y, hyp["l"].reshape(1, d), hyp["sigma"],
+                                                            hyp["sigma0"], randn_W, rand_b, noise)
+    else:
+        from tes_b200 import optfunc
+        theta, W, b = optfunc.draw_random_init_weights_features_np(d, S, F, X, Y, hyp["l"].reshape(1, d), hyp["sigma"],
+                                                                   hyp["sigma0"], draws=(randn_W, rand_b, noise))
     return dict(name=name, desc=desc, d=d, N=N, S=S, F=F, n=n, t_max=t_max, hyp=hyp, X=X, Y=Y,
                 cand=np.ascontiguousarray(cand), theta=np.ascontiguousarray(theta.reshape(S, F)),
                 W=np.ascontiguousarray(W), b=np.ascontiguousarray(b.reshape(S, F)))

@@ -2,7 +2,7 @@
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from tes_b200 import ops, ep
+from tes_b200 import ops
 from oracle import tes_oracle_np as onp
 torch.cuda.set_device(0)
 for T in [int(a) for a in sys.argv[1:]] or [8, 16, 49, 125]:
@@ -17,7 +17,7 @@ for T in [int(a) for a in sys.argv[1:]] or [8, 16, 49, 125]:
     t_dev = time.perf_counter() - t0
     nh = min(T, 4)
     t0 = time.perf_counter()
-    for j in range(nh): ep.approximate_EP_host(j, m.reshape(-1, 1), c, 1e-9, 100)
+    for j in range(nh): onp.approximate_EP(j, m.reshape(-1, 1), c, 1e-9, 100)
     t_host = (time.perf_counter() - t0) / nh * T
     print("T=%d: device (all %d maximizers) %.2f ms, iterations %d..%d; host numpy (extrapolated from %d) %.1f ms -> %.0fx" % (
         T, T, t_dev * 1e3, int(nit.min()), int(nit.max()), nh, t_host * 1e3, t_host / t_dev), flush=True)

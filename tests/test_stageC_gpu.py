@@ -41,6 +41,46 @@ def test_dedup_golden(golden):
     np.testing.assert_array_equal(acquisition.select_test_points(g["dedup_in"].copy(), 1e-3), g["dedup_out"])
 
 
+def test_reference_named_numpy_helpers_run_on_the_device(golden):
+    """remove_duplicates_np / get_duplicate_mask_np (utils.py:1554-1581), get_empirical_stat_from_samples
+    (empirical_approximation.py:86-107) and sample_multivariate_normal_maxidx_np (utils.py:1654-1729) of the package
+    are device-backed; pinned on the reference's own outputs."""
+    from tes_b200 import _lib, utils
+    from tes_b200 import empirical_approximation as ea
+    g = golden("maximizer_stats")
+    n0 = _lib.lib().tes_launch_count()
+    np.testing.assert_array_equal(utils.remove_duplicates_np(g["dedup_in"].copy(), 1e-3), g["dedup_out"])
+    np.testing.assert_array_equal(utils.get_duplicate_mask_np(g["dedup_in"].copy(), 1e-3),
+                                  onp.get_duplicate_mask(g["dedup_in"].copy(), 1e-3))
+    m, c = ea.get_empirical_stat_from_samples(g["emp_samples"], g["emp_weight"])
+    np.testing.assert_allclose(m, g["emp_mean"], rtol=1e-13)
+    np.testing.assert_allclose(c, g["emp_cov"], rtol=1e-12, atol=1e-15)
+    m2, c2 = ea.get_empirical_stat_from_samples(g["emp_samples"])
+    rm, rc = onp.get_empirical_stat_from_samples(g["emp_samples"])
+    np.testing.assert_allclose(m2, rm, rtol=1e-13)
+    np.testing.assert_allclose(c2, rc, rtol=1e-12, atol=1e-15)
+    with pytest.raises(ValueError):
+        ea.get_empirical_stat_from_samples(g["emp_samples"], 0.5 * np.ones(g["emp_samples"].shape[0]))
+    for tag in ("t6", "t12"):
+        mean, cov, z = g[tag + "_mean"][0], g[tag + "_cov"][0], g[tag + "_z"][0]
+        A = onp.mvn_transform_matrix(cov)
+        for rc_ in (True, False):
+            ref = onp.sample_multivariate_normal_maxidx(mean.copy(), cov.copy(), z.shape[0], 2, z=z,
+                                                        remove_correlated_dims=rc_, transform=A)
+            got = utils.sample_multivariate_normal_maxidx_np(mean.copy(), cov.copy(), z.shape[0], 2, z=z,
+                                                             remove_correlated_dims=rc_, transform=A)
+            assert got[0] == ref[0] and got[2] == ref[2]
+            np.testing.assert_array_equal(got[1], ref[1])
+            np.testing.assert_allclose(got[3], ref[3], rtol=1e-12, atol=1e-13)
+            np.testing.assert_array_equal(got[4], ref[4])
+            np.testing.assert_array_equal(got[5], ref[5])
+            u, sz = utils.sample_multivariate_normal_maxidx_np(mean.copy(), cov.copy(), z.shape[0], 2, get_sample=False,
+                                                               z=z, remove_correlated_dims=rc_, transform=A)
+            np.testing.assert_array_equal(u, ref[1])
+            np.testing.assert_array_equal(sz, ref[5])
+    assert _lib.lib().tes_launch_count() > n0
+
+
 def test_select_test_points_t_max_matches_oracle_pipeline():
     from oracle import pipeline_np
     from tes_b200 import acquisition
@@ -91,7 +131,7 @@ def test_device_get_testidxs_stats_matches_the_reference_outputs(golden, tag, mo
     from tes_b200 import utils
     g = golden("maximizer_stats")
     cov = g[tag + "_cov"].copy()
-    A = utils.mvn_transform_matrix(cov[0])
+    A = onp.mvn_transform_matrix(cov[0])
     out = utils.get_testidxs_stats(1, g[tag + "_test_xs"].copy(), g[tag + "_mean"].copy(), cov, mode=mode,
                                    nsample=int(g[tag + "_nsample"]), n_min_sample=2, z=g[tag + "_z"], transforms=[A])
     if mode == "ep":
@@ -127,7 +167,7 @@ def test_device_get_testidxs_stats_vs_oracle(mode, T, nsample, nhyp):
         m, c = onp.compute_mean_var_f(test_xs, X, Y, l, 1.1, 1e-3, invK[0], fullcov=True)
         means.append(m.reshape(T))
         covs.append(c)
-        trs.append(utils.mvn_transform_matrix(c))
+        trs.append(onp.mvn_transform_matrix(c))
     means, covs = np.stack(means), np.stack(covs)
     z = rs.normal(size=(nhyp, nsample, T, 1))
     ref = onp.get_testidxs_stats(nhyp, test_xs.copy(), means.copy(), covs.copy(), mode=mode, nsample=nsample,
@@ -162,8 +202,8 @@ def test_device_joint_samples_with_own_colouring_factor_have_the_right_law():
     invK = onp.precomputeInvKs(l.reshape(1, d), np.array([1.0]), np.array([1e-3]), X)
     m, c = onp.compute_mean_var_f(test_xs, X, Y, l, 1.0, 1e-3, invK[0], fullcov=True)
     a = utils.get_testidxs_stats(1, test_xs, m.reshape(1, T), c[None], mode="empirical", nsample=200000, seed=4)
-    b = utils.get_testidxs_stats_host(1, test_xs, m.reshape(1, T), c[None], mode="empirical", nsample=200000,
-                                      z=rs.normal(size=(1, 200000, T, 1)))
+    b = onp.get_testidxs_stats(1, test_xs, m.reshape(1, T), c[None], mode="empirical", nsample=200000,
+                               z=rs.normal(size=(1, 200000, T, 1)))
     np.testing.assert_array_equal(a[0], b[0])
     np.testing.assert_allclose(a[1], b[1], atol=6e-3)
     np.testing.assert_allclose(a[4], b[4], atol=3e-2)
@@ -270,7 +310,7 @@ def test_device_ep_mode_through_get_testidxs_stats_cuda_tensors(golden):
     out = utils.get_testidxs_stats(1, torch.from_numpy(g[tag + "_test_xs"]).cuda(),
                                    torch.from_numpy(g[tag + "_mean"]).cuda(), torch.from_numpy(cov).cuda(), mode="ep",
                                    nsample=int(g[tag + "_nsample"]), n_min_sample=2, z=g[tag + "_z"],
-                                   transforms=[utils.mvn_transform_matrix(cov[0])])
+                                   transforms=[onp.mvn_transform_matrix(cov[0])])
     assert all(o.is_cuda for o in out)
     np.testing.assert_allclose(out[4][0].cpu().numpy(), g[tag + "_ep_mean"], rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(out[5][0].cpu().numpy(), g[tag + "_ep_cov"], rtol=1e-8, atol=1e-10)

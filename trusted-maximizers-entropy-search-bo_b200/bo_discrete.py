@@ -2,9 +2,11 @@
 on the whole candidate grid, f = sqrtm(Sigma) z^T + mu with utils.sqrtm (SVD, utils.py:49-53), arg-max per
 sample.  O(N^3): only viable for small grids (N ~ 400); the RFF path (stage A) is what scales.
 
-The posterior mean / covariance (utils.compute_mean_var_f, fullcov=True), the colouring GEMM and the arg-max
-run on the device; the N x N SVD square root is taken on the host with numpy, whose U sqrt(S) V^T is the
-reference's definition of sqrtm."""
+Everything runs on the device: the posterior mean / covariance (utils.compute_mean_var_f, fullcov=True), the
+matrix square root (batched Jacobi eigen-solver: for a symmetric matrix V E V^T the SVD factors are U = V sign(E),
+S = |E|, so U sqrt(S) V^T = V sign(E) sqrt|E| V^T), the colouring GEMM and the arg-max.  The rounding-level part of
+the spectrum (|e| ~ 1e-17 |cov|, the null space of the posterior covariance) enters sqrtm at ~3e-9 with LAPACK-
+dependent singular vectors in the reference too; function values agree to ~1e-8, arg-max indices exactly."""
 import numpy as np
 import torch
 
@@ -13,10 +15,11 @@ from .device import dev
 
 
 def sqrtm(mat):
-    """utils.sqrtm (utils.py:49-53): U diag(sqrt(s)) V^T from an SVD."""
-    m = mat.detach().cpu().numpy() if torch.is_tensor(mat) else np.asarray(mat)
-    U, s, Vt = np.linalg.svd(m)
-    return (U * np.sqrt(s)) @ Vt
+    """utils.sqrtm (utils.py:49-53): U diag(sqrt(s)) V^T of an SVD, for the symmetric matrices it is called on."""
+    A = dev(mat)
+    e, v = ops.sym_eig(A)
+    out = ops.gemm(v * (torch.sign(e) * torch.sqrt(e.abs())).reshape(1, -1), v, transb=True)
+    return out if torch.is_tensor(mat) else out.cpu().numpy()
 
 
 def sample_maximizers(xs, X, Y, l, sigma, sigma0, z):
@@ -24,7 +27,7 @@ def sample_maximizers(xs, X, Y, l, sigma, sigma0, z):
     sample_max_fs (nmax,), max_idx (nmax,), mean (nx,), cov (nx,nx))."""
     xs_d = dev(xs)
     mean, cov = utils.compute_mean_var_f(xs_d, dev(X), dev(Y), l, sigma, sigma0, fullcov=True)
-    sq = dev(sqrtm(cov))
+    sq = sqrtm(cov)
     f = ops.gemm(dev(z), sq, transb=True) + mean.reshape(1, -1)     # (nmax, nx) = z sqrt^T + mu
     idx = torch.stack([ops.argmax(f[i])[0][0] for i in range(f.shape[0])])
     fs = f.gather(1, idx.reshape(-1, 1)).reshape(-1)

@@ -1,41 +1,30 @@
-"""Mirror of empirical_approximation.get_empirical_stat_from_samples (empirical_approximation.py:86-107)."""
+"""Mirror of empirical_approximation.get_empirical_stat_from_samples (empirical_approximation.py:86-107),
+computed on the device (tes_bucket_moments_f64)."""
 import numpy as np
+import torch
+
+from . import ops
+from .device import dev
 
 
 def get_empirical_stat_from_samples(samples, weight=None):
-    samples = np.asarray(samples)
-    n = samples.shape[0]
+    """samples (K, T), weight (K,) -> mean (T, 1), cov (T, T) = sum_k w_k (x_k - m)(x_k - m)^T / (sum w - 1).
+    The reference only ever passes the 0/1 validity mask of the padded sample tensor as `weight`
+    (utils.py:1811-1817); other weights are rejected."""
+    like = samples
+    x = dev(samples)
+    K, T = x.shape
     if weight is None:
-        weight = np.ones(n)
-    tw = np.sum(weight)
-    w = np.asarray(weight).reshape(-1, 1)
-    emean = np.sum(samples * w, axis=0, keepdims=True) / tw
-    zs = (samples - emean) * np.sqrt(w)
-    return emean.reshape(-1, 1), zs.T.dot(zs) / (tw - 1.0)
-
-
-def batched_empirical_stats(post_samples, post_masks):
-    """All maximizers of one hyper-parameter sample at once: post_samples (S,T,K), post_masks (S,K)
-    -> means (S,T), covs (S,T,T); identical to calling the function above per maximizer."""
-    w = post_masks.astype(np.float64)                       # (S,K)
-    tw = w.sum(axis=1)                                      # (S,)
-    mean = np.matmul(post_samples, w[:, :, None])[:, :, 0] / tw[:, None]
-    zs = (post_samples - mean[:, :, None]) * np.sqrt(w)[:, None, :]
-    cov = np.matmul(zs, np.transpose(zs, (0, 2, 1))) / (tw - 1.0)[:, None, None]
-    return mean, cov
-
-
-def bucket_empirical_stats(samples, rows_per_bucket):
-    """Same statistics straight from the bucketed joint samples (no padded tensor): samples (nsample,T),
-    rows_per_bucket = list of row-index arrays, one per kept maximizer."""
-    T = samples.shape[1]
-    S = len(rows_per_bucket)
-    mean = np.empty((S, T))
-    cov = np.empty((S, T, T))
-    for j, rows in enumerate(rows_per_bucket):
-        x = samples[rows]
-        m = x.sum(axis=0) / len(rows)
-        xc = x - m
-        mean[j] = m
-        cov[j] = xc.T.dot(xc) / (len(rows) - 1.0)
+        rows = torch.arange(K, dtype=torch.int64, device=x.device)
+    else:
+        w = dev(weight).reshape(-1)
+        if w.numel() != K or bool(((w != 0) & (w != 1)).any()):
+            raise ValueError("weight must be a 0/1 mask of length samples.shape[0]")
+        rows = torch.nonzero(w != 0).reshape(-1).contiguous()
+    starts = torch.tensor([0, rows.numel()], dtype=torch.int64, device=x.device)
+    cols = torch.arange(T, dtype=torch.int64, device=x.device)
+    mean, cov = ops.bucket_moments(x, rows, starts, cols)
+    mean, cov = mean.reshape(T, 1), cov.reshape(T, T)
+    if isinstance(like, np.ndarray):
+        return mean.cpu().numpy(), cov.cpu().numpy()
     return mean, cov

@@ -37,38 +37,6 @@ def draw_random_init_weights_features_np(xdim, n_funcs, n_features, xx, yy, l, s
     return theta.cpu().numpy(), W.cpu().numpy(), b.cpu().numpy()
 
 
-def draw_random_init_weights_features_host(xdim, n_funcs, n_features, xx, yy, l, sigma, sigma0, draws=None):
-    """Host-numpy restatement of optfunc.py:303-385 (where the reference runs it); the CPU-side mirror the
-    non-GPU tests pin against the reference's own outputs."""
-    n = xx.shape[0]
-    l = np.asarray(l, dtype=np.float64).reshape(1, xdim)
-    if draws is None:
-        randn_W = np.random.randn(n_funcs, n_features, xdim)
-        rand_b = np.random.rand(n_funcs, n_features, 1)
-    else:
-        randn_W, rand_b = draws[0], draws[1]
-    W = randn_W * np.sqrt(l).reshape(1, 1, xdim)
-    b = 2.0 * np.pi * rand_b
-    xx_t = np.broadcast_to(xx.reshape(1, n, xdim), (n_funcs, n, xdim))
-    Z = np.sqrt(2.0 * sigma / n_features) * np.cos(np.matmul(W, np.transpose(xx_t, (0, 2, 1))) + b)
-    noise = np.random.randn(n_funcs, n_features, 1) if draws is None else draws[2]
-    yy_t = np.broadcast_to(yy.reshape(1, n, 1), (n_funcs, n, 1))
-    Zt = np.transpose(Z, (0, 2, 1))
-    if n < n_features:
-        Sigma = np.matmul(Zt, Z) + sigma0 * np.eye(n)[None]
-        mu = np.matmul(np.matmul(Z, np.linalg.inv(Sigma)), yy_t)
-        e, v = np.linalg.eig(Sigma)
-        e = e.reshape(n_funcs, n, 1)
-        r = 1.0 / (np.sqrt(e) * (np.sqrt(e) + np.sqrt(sigma0)))
-        theta = noise - np.matmul(Z, np.matmul(v, r * np.matmul(np.transpose(v, (0, 2, 1)),
-                                                               np.matmul(Zt, noise)))) + mu
-    else:
-        Sigma = np.linalg.inv(np.matmul(Z, Zt) / sigma0 + np.eye(n_features)[None])
-        mu = np.matmul(np.matmul(Sigma, Z), yy_t) / sigma0
-        theta = mu + np.matmul(np.linalg.cholesky(Sigma), noise)
-    return theta, W, b
-
-
 def make_function_sample_np(x, n_features, sigma, theta, W, b):
     """optfunc.py:389-402: values of the function sample(s) at x -> (n_funcs, nx) or (nx,)."""
     theta = np.asarray(theta)

@@ -1,9 +1,10 @@
 """Mirror of the reference's utils.py for the TES hot path (same function names and argument
 meaning), backed by the CUDA kernels of libtes_b200.
 
-Device work (SE-ARD kernels, Cholesky inverses, posteriors) goes through the C ABI.  The
-trusted-maximizer bookkeeping of utils.py:1554-1833 is host-side numpy in the reference as well
-(it runs between two sess.run calls); it is restated here with the random draw made injectable.
+All numerical work (SE-ARD kernels, Cholesky inverses, posteriors, and the trusted-maximizer statistics of
+utils.py:1554-1833 that the reference runs as host numpy between two sess.run calls) goes through the C ABI;
+only bucket COUNTS visit the host (they size the outputs).  The random draws are injectable.  There is no host
+implementation in this package (the numpy restatement the tests check against is test infrastructure, outside this package).
 Arrays may be numpy or torch; numpy in -> numpy out.
 """
 import numpy as np
@@ -116,162 +117,57 @@ def _np(a):
     return a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
 
 
-# ---- trusted-maximizer statistics (host side in the reference too) ---------------------------------
+# ---- trusted-maximizer statistics (host numpy in the reference; device kernels here) ----------------
 def get_duplicate_mask_np(xs, resolution=1e-5, return_leader=False):
-    """utils.py:1554-1573: walking the rows in order, every not-yet-flagged row flags all LATER rows within
-    `resolution` (Euclidean) as duplicates.  Same semantics, one pairwise-distance matrix instead of the
-    O(n^2) Python loop; `leader[j]` is the row that flagged j (j itself for kept rows)."""
-    xs = _np(xs)
-    n = xs.shape[0]
-    mask = np.zeros(n)
-    leader = np.arange(n)
-    if n:
-        sq = np.sum(xs * xs, axis=1)
-        # the reference computes sqrt(sum((xs[j]-xs[i])**2)); evaluate exactly that for the rows that matter
-        close = (sq[:, None] + sq[None, :] - 2.0 * xs.dot(xs.T)) <= (resolution * 1.5) ** 2 + 1e-12
-        for i in range(n):
-            if mask[i] == 1.0:
-                continue
-            cand = np.nonzero(close[i, i + 1:])[0] + i + 1
-            if cand.size:
-                d = np.sqrt(np.sum((xs[cand] - xs[i]) ** 2, axis=1))
-                hit = cand[(d <= resolution) & (mask[cand] == 0.0)]
-                mask[hit] = 1.0
-                leader[hit] = i
+    """utils.py:1554-1573 on the device (tes_dedup_f64): walking the rows in order, every not-yet-flagged row
+    flags all LATER rows within `resolution` (Euclidean) as duplicates.  Returns the reference's float mask
+    (1.0 = duplicate); `leader[j]` is the row that flagged j (j itself for kept rows)."""
+    mask, leader = ops.dedup(dev(xs), resolution)
+    mask = mask.to(torch.float64)
+    if not torch.is_tensor(xs):
+        mask, leader = mask.cpu().numpy(), leader.cpu().numpy()
     return (mask, leader) if return_leader else mask
 
 
 def remove_duplicates_np(xs, resolution=1e-5):
-    """utils.py:1576-1581."""
-    xs = _np(xs)
-    return np.delete(xs, np.where(get_duplicate_mask_np(xs, resolution) == 1.0)[0], axis=0)
-
-
-def mvn_transform_matrix(cov):
-    """utils.py:1668-1670: A = V diag(sqrt(clip(e, 0))) from a GENERAL eig of the symmetric cov.  Column
-    order and signs are LAPACK dgeev's and can change under 1e-13 perturbations of cov (near-degenerate
-    eigenvalues), so callers that need identical samples for identical z pass this factor explicitly."""
-    e, v = np.linalg.eig(_np(cov))
-    return v.dot(np.diag(np.sqrt(np.clip(e, 0.0, np.inf))))
-
-
-def _joint_sample_buckets(mean, cov, nsample, n_min_sample, remove_correlated_dims, z, transform):
-    """Core of utils.py:1654-1729: joint samples, correlated-dimension suppression, arg-max bucketing.
-    Returns (samples (nsample,n), unique maximizer ids, sizes, rows per bucket in sample order)."""
-    mean, cov = _np(mean), _np(cov)
-    n = cov.shape[0]
-    mean = mean.reshape(n)
-    A = mvn_transform_matrix(cov) if transform is None else _np(transform)
-    if z is None:
-        z = np.random.normal(size=(nsample, n, 1))
-    # utils.py:1675 broadcasts mean.reshape(1,n) against the (nsample,n,1) product and then averages over the
-    # LAST axis, so what is added to every coordinate is the AVERAGE of the prior means, not mean[i]
-    # (reference quirk Q11, reproduced on purpose).  Evaluated here as ONE GEMM: z A^T + mean(mean).
-    samples = _np(z).reshape(-1, n).dot(A.T) + np.mean(mean)
-    corr_idxs = []
-    if remove_correlated_dims:
-        with np.errstate(invalid="ignore", divide="ignore"):
-            rows, _ = np.where(np.tril(np.corrcoef(samples.T), k=-1) > 1 - 1e-6)
-        corr_idxs = rows
-    masked = samples
-    if len(corr_idxs):
-        masked = samples.copy()
-        masked[:, corr_idxs] = -np.inf
-    maxidxs = np.argmax(masked, axis=1)
-    counts = np.bincount(maxidxs, minlength=n)
-    unique = np.where(counts >= max(n_min_sample, 1))[0]
-    sizes = counts[unique]
-    order = np.argsort(maxidxs, kind="stable")
-    starts = np.concatenate([[0], np.cumsum(counts)])
-    rows_per = [order[starts[mi]:starts[mi + 1]] for mi in unique]
-    return samples, mean, unique, sizes, rows_per
+    """utils.py:1576-1581 on the device: the rows of xs that are not flagged as duplicates, original order."""
+    xs_d = dev(xs)
+    mask, _ = ops.dedup(xs_d, resolution)
+    return _ret(xs_d[mask == 0], xs)
 
 
 def sample_multivariate_normal_maxidx_np(mean, cov, nsample, n_min_sample=1, get_sample=True,
-                                         remove_correlated_dims=True, z=None, transform=None):
-    """utils.py:1654-1729.  `z` (nsample, n, 1) replaces the np.random.normal draw of :1674; when
-    omitted the global numpy RNG is used exactly as the reference does.  `transform` overrides the
-    colouring factor A (default: mvn_transform_matrix(cov), as the reference computes it)."""
-    samples, mean, unique, sizes, rows_per = _joint_sample_buckets(mean, cov, nsample, n_min_sample,
-                                                                   remove_correlated_dims, z, transform)
+                                         remove_correlated_dims=True, z=None, transform=None, seed=None):
+    """utils.py:1654-1729 on the device.  `z` (nsample, n, 1) replaces the np.random.normal draw of :1674
+    (`seed`: counter-based draws; neither: the global numpy RNG exactly as the reference).  `transform`
+    overrides the colouring factor A of :1668-1670 (default: the device eigen-solver's factor -- same law as
+    LAPACK's, different realisation).  Returns (unique, sizes) or
+    (nmax, unique, K, samples (nmax,n,K), masks (nmax,K), sizes) as the reference."""
+    like = mean
+    mean_d, cov_d = dev(mean).reshape(-1), dev(cov)
+    n = cov_d.shape[0]
+    samples, maxidx, counts = _device_buckets(mean_d, cov_d, nsample, z, transform, seed, 0,
+                                              remove_correlated=remove_correlated_dims)
+    counts_h = counts.cpu().numpy().astype(np.int64)
+    unique = np.where(counts_h >= max(n_min_sample, 1))[0]
+    sizes = counts_h[unique]
     if not get_sample:
         return unique, sizes
-    n = mean.shape[0]
     K = int(sizes.max())
-    nmax = len(unique)
-    ret = np.tile(mean.reshape(1, n, 1), (nmax, 1, K))  # padded slots hold the prior mean (:1722)
-    masks = np.zeros([nmax, K], dtype=int)
-    for i in range(nmax):
-        ret[i, :, :sizes[i]] = samples[rows_per[i]].T
-        masks[i, :sizes[i]] = 1
-    return nmax, unique, K, ret, masks, sizes
+    order = torch.sort(maxidx, stable=True).indices
+    starts_all = np.concatenate([[0], np.cumsum(counts_h)])
+    pick = np.concatenate([np.arange(starts_all[u], starts_all[u + 1]) for u in unique])
+    order_k = order[torch.from_numpy(pick).to(cov_d.device)].contiguous()
+    starts_k = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)).to(cov_d.device)
+    cols = torch.arange(n, dtype=torch.int64, device=cov_d.device)
+    ret, masks = ops.bucket_samples(samples, order_k, starts_k, cols, K, mean_d)   # prior-mean padding (:1722)
+    masks = masks.to(torch.int64)
+    if not torch.is_tensor(like):
+        ret, masks = ret.cpu().numpy(), masks.cpu().numpy()
+    return len(unique), unique, K, ret, masks, sizes
 
 
-def get_testidxs_stats_host(nhyp, test_xs_np, test_means, test_covs, mode="sample", nsample=1000, n_min_sample=2,
-                            z=None, transforms=None):
-    """Host-numpy restatement of utils.py:1733-1833 (where the reference runs it).  Kept for mode='ep' (whose
-    EP sweeps are host code here as in the reference) and as the numpy-level mirror; the default entry point
-    `get_testidxs_stats` below runs modes 'sample' and 'empirical' on the device.
-    mode in {'sample','empirical','ep'}; `z` (nhyp, nsample, ntest, 1) optional.
-    mode='ep' runs the EP the reference intends at :1820-1825 (its shipped code raises NameError).
-    The padded (nhyp, ntest, ntest, K) sample tensor is only materialised for mode='sample'; the empirical
-    moments are taken straight from the buckets (zero-weight padding contributes nothing)."""
-    from . import empirical_approximation, ep
-    test_xs_np, test_means, test_covs = _np(test_xs_np), _np(test_means), _np(test_covs)
-    if mode not in ("sample", "empirical", "ep"):
-        raise Exception("Unknown mode in get_testidxs_stats!")
-    ntest = test_xs_np.shape[0]
-    alive = np.ones(ntest, dtype=bool)
-    max_probs = np.ones([nhyp, ntest]) / ntest
-    per_hyp = []
-    for i in range(nhyp):
-        samples, mean_i, uniq, sizes, rows_per = _joint_sample_buckets(
-            test_means[i], test_covs[i], nsample, n_min_sample, True, None if z is None else z[i],
-            None if transforms is None else transforms[i])
-        won = np.zeros(ntest, dtype=bool)
-        won[uniq] = True
-        alive &= won
-        max_probs[i, uniq] = sizes / np.sum(sizes)
-        per_hyp.append((samples, mean_i, uniq, sizes, rows_per))
-    keep = np.where(alive)[0]
-    pos = -np.ones(ntest, dtype=int)
-    pos[keep] = np.arange(len(keep))
-    if len(keep) != ntest:
-        test_xs_np = test_xs_np[keep]
-        test_means = test_means[:, keep]
-        test_covs = test_covs[:, keep][:, :, keep]
-        max_probs = max_probs[:, keep]
-    max_probs = max_probs / np.sum(max_probs, axis=1, keepdims=True)
-    nk = len(keep)
-    if mode == "sample":
-        K_all = max(int(sz.max()) for (_, _, _, sz, _) in per_hyp)
-        post_samples = np.zeros([nhyp, nk, nk, K_all])
-        post_masks = np.zeros([nhyp, nk, K_all], dtype=bool)
-        for i, (samples, mean_i, uniq, sizes, rows_per) in enumerate(per_hyp):
-            K = int(sizes.max())
-            for u, sz, rows in zip(uniq, sizes, rows_per):
-                if pos[u] < 0:
-                    continue
-                post_samples[i, pos[u], :, :sz] = samples[rows][:, keep].T
-                post_samples[i, pos[u], :, sz:K] = mean_i[keep].reshape(nk, 1)  # prior-mean padding (:1722)
-                post_masks[i, pos[u], :sz] = True
-        return test_xs_np, max_probs, test_means, test_covs, post_samples, post_masks
-    pm = np.zeros([nhyp, nk, nk])
-    pc = np.zeros([nhyp, nk, nk, nk])
-    for i, (samples, mean_i, uniq, sizes, rows_per) in enumerate(per_hyp):
-        if mode == "empirical":
-            sel = [rows for u, rows in zip(uniq, rows_per) if pos[u] >= 0]
-            pm[i], pc[i] = empirical_approximation.bucket_empirical_stats(samples[:, keep], sel)
-        else:
-            for j in range(nk):
-                m, c = ep.approximate_EP_host(j, test_means[i].reshape(-1, 1), test_covs[i], resolution=1e-9,
-                                            max_niter=100)
-                pm[i, j] = m.squeeze()
-                pc[i, j] = c
-    return test_xs_np, max_probs, test_means, test_covs, pm, pc
-
-
-def _device_buckets(mean, cov, nsample, z, transform, seed, hyp_index):
+def _device_buckets(mean, cov, nsample, z, transform, seed, hyp_index, remove_correlated=True):
     """utils.py:1668-1705 on the device: colouring factor (Jacobi eigen-solver unless `transform` is given),
     joint samples z A^T + mean(mean) (Q11), correlated-dimension mask, row arg-max, bucket counts."""
     T = cov.shape[0]
@@ -283,7 +179,7 @@ def _device_buckets(mean, cov, nsample, z, transform, seed, hyp_index):
     else:  # the reference's own draw: global numpy RNG (utils.py:1674)
         zt = dev(np.random.normal(size=(nsample, T, 1)), cov.device).reshape(nsample, T)
     samples = ops.gemm(zt, A, transb=True)
-    _, maxidx, counts = ops.joint_maxidx(samples, mean.reshape(-1), True)
+    _, maxidx, counts = ops.joint_maxidx(samples, mean.reshape(-1), remove_correlated)
     return samples, maxidx, counts
 
 
