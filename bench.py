@@ -13,11 +13,11 @@ trusted maximizers.  theta/W/b are host-supplied draws (optfunc.py:303-385), inp
   e2e      the same step through the reference-facing Python API with HOST (pinned) buffers: H2D copies
            of candidates / observations / RFF weights and the D2H read of the result are inside the
            timed region
-  roofline the dominant kernel (rff_topk, fp64-pipe bound) against the in-run measured DFMA peak
+  roofline the dominant kernel (stage A: tcgen05 screen + fp64 refine; MUFU-bound) against the in-run measured peak
   cpu_baseline / --impl reference: the CPU oracle port of the same step on the box's host cores, on a
            bounded sub-sample of the same workload
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c4s]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c3s|c3m|c2|c4|c4m|c4s]
   N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 """
 import argparse
@@ -59,46 +59,97 @@ def meshgrid(xmin, xmax, nx, xdim):
 TC5_TRAFFIC_BYTES = {"c3": 465.8e6}   # profiles/r01_ncu_rff_screen_tc5.md (algorithmic: 115 MB)
 
 WORKLOADS = {
-    # name: (description, d, N per GPU, S, F, n, t_max)
-    "c3": ("C3 Hartmann-6 TES_ep empirical, 1M candidates x 1024 maximizer samples per GPU", 6, 10 ** 6, 1024, 1024, 64, 128),
-    "c3s": ("C3 shapes scaled down (smoke)", 6, 50_000, 128, 256, 32, 32),
-    "c3m": ("C3 shapes, mid size (profiling)", 6, 200_000, 256, 1024, 64, 64),
-    "c2": ("C2 Brooms-Barn-like 2-D 20x20 grid TES_ep, S=32 (latency case)", 2, 400, 32, 300, 12, 32),
+    # d, N per GPU, S function samples, F features, n observations, t_max test points; criterion/mode/q and the
+    # Monte-Carlo sizes of the criterion (I = niteration, Y = nysample)
+    "c3": dict(desc="C3 Hartmann-6 TES_ep empirical, 1M candidates x 1024 maximizer samples per GPU",
+               d=6, N=10 ** 6, S=1024, F=1024, n=64, t_max=128),
+    "c3s": dict(desc="C3 shapes scaled down (smoke)", d=6, N=50_000, S=128, F=256, n=32, t_max=32),
+    "c3m": dict(desc="C3 shapes, mid size (profiling)", d=6, N=200_000, S=256, F=1024, n=64, t_max=64),
+    "c2": dict(desc="C2 Brooms-Barn-like 2-D 20x20 grid TES_ep, S=32 (latency case)", d=2, N=400, S=32, F=300, n=12,
+               t_max=32),
+    # C4: 10-D GP-prior objective, uniform candidates on [0,10]^10, 2^24 candidates over 8 GPUs = 2^21 per
+    # GPU grouped consecutively into batches of q = 8, S = 1024, F = 4096, n = 256, batch TES_sp with T <= 32, I = 1, Y = 8
+    "c4": dict(desc="C4 synthetic 10-D GP objective, batch TES_sp q=8, F=4096, 2^21 candidates x 1024 maximizer samples "
+                    "per GPU (2^24 over 8 GPUs)", d=10, N=2 ** 21, S=1024, F=4096, n=256, t_max=32, criterion="sftl",
+               q=8, niteration=1, nysample=8, ntestsample=1000, xmax=10.0),
+    "c4m": dict(desc="C4 shapes, mid size (profiling)", d=10, N=2 ** 18, S=256, F=1024, n=256, t_max=32, criterion="sftl",
+                q=8, niteration=1, nysample=8, ntestsample=1000, xmax=10.0),
+    "c4s": dict(desc="C4 shapes scaled down (smoke)", d=10, N=2 ** 15, S=64, F=512, n=32, t_max=8, criterion="sftl",
+                q=8, niteration=1, nysample=4, ntestsample=500, xmax=10.0),
 }
+for _w in WORKLOADS.values():
+    _w.setdefault("criterion", "ftl")
+    _w.setdefault("q", 1)
+    _w.setdefault("niteration", 10)
+    _w.setdefault("nysample", 10)
+    _w.setdefault("ntestsample", max(1000, 64 * _w["t_max"]))
+    _w.setdefault("xmax", 1.0)
+
+
+def gp_prior_objective(xdim, l, sigma, seed, n_feats=10000):
+    """functions.func_gp_prior (functions.py:163-177), restated for the harness: one RFF prior sample."""
+    rs = np.random.RandomState(seed)
+    W = rs.randn(n_feats, xdim) * np.sqrt(l)
+    b = 2.0 * np.pi * rs.rand(n_feats, 1)
+    theta = rs.randn(n_feats, 1)
+    return lambda x: (np.sqrt(2.0 * sigma / n_feats) * theta.T.dot(np.cos(W.dot(x.reshape(-1, xdim).T) + b))).reshape(-1)
+
+
+def config_of(wl):
+    c = {"workload": wl["desc"], "criterion": wl["criterion"], "mode": "sample" if wl["criterion"] == "sftl" else "empirical",
+         "deterministic": True, "N_per_gpu": wl["N"], "S": wl["S"], "F": wl["F"], "n_obs": wl["n"], "d": wl["d"],
+         "t_max": wl["t_max"]}
+    if wl["criterion"] == "sftl":
+        c.update(q=wl["q"], niteration=wl["niteration"], nysample=wl["nysample"], ntestsample=wl["ntestsample"])
+    return c
+
+
+def step_kwargs(wl):
+    return dict(criterion=wl["criterion"], mode="empirical", deterministic=True, ntestsample=wl["ntestsample"],
+                t_max=wl["t_max"], q=wl["q"], niteration=wl["niteration"], nysample=wl["nysample"])
 
 
 def make_workload(name, rank, world, host_only=False):
-    desc, d, N, S, F, n, t_max = WORKLOADS[name]
-    hyp = HART6 if d == 6 else dict(l=np.array([177.9418631280815, 309.4630784148164]), sigma=0.29444226420446995,
-                                    sigma0=0.06476473751595126)
+    wl = dict(WORKLOADS[name])
+    d, N, S, F, n = wl["d"], wl["N"], wl["S"], wl["F"], wl["n"]
     rs = np.random.RandomState(1)
-    X = rs.rand(n, d)
+    X = rs.rand(n, d) * wl["xmax"]
     if d == 6:
+        hyp = HART6
         f = hartmann6(X)
         Y = (f - f.mean()).reshape(-1, 1)
+    elif d == 10:
+        hyp = dict(l=np.full(10, 1.0), sigma=2.0, sigma0=1e-3)   # functions.func_gp_prior(10, l=1.0, sigma=2.0, seed=1)
+        Y = gp_prior_objective(10, 1.0, 2.0, 1)(X).reshape(-1, 1)
     else:
+        hyp = dict(l=np.array([177.9418631280815, 309.4630784148164]), sigma=0.29444226420446995,
+                   sigma0=0.06476473751595126)
         Y = rs.randn(n, 1) * 0.5
     if rank == 0 and d == 6 and N == 10 ** 6:
         cand = meshgrid(0.0, 1.0, 10, 6)
     elif d == 2 and N == 400:
         cand = meshgrid(0.0, 1.0, 20, 2)
     else:
-        cand = np.random.RandomState(7 + rank).rand(N, d)
+        cand = np.random.RandomState(7 + rank).rand(N, d) * wl["xmax"]
     np.random.seed(11)  # identical draws on every rank
     # the RFF posterior weight draw (optfunc.py:303-385): on the device for the b200 arm; the CPU reference arm runs
     # the oracle's numpy restatement (where the reference runs it).  Same np.random draws, same order, either way.
-    randn_W, rand_b, noise = np.random.randn(S, F, d), np.random.rand(S, F, 1), np.random.randn(S, F, 1)
+    # The CPU arm only ever uses the first `ns` function samples (cpu_sample_sizes), so it only draws those.
     if host_only:
         from oracle import tes_oracle_np as onp
+        S = min(S, cpu_sample_sizes(wl)[1])
+        randn_W, rand_b, noise = np.random.randn(S, F, d), np.random.rand(S, F, 1), np.random.randn(S, F, 1)
         theta, W, b = onp.draw_random_init_weights_features(d, S, F, X, Y, hyp["l"].reshape(1, d), hyp["sigma"],
                                                             hyp["sigma0"], randn_W, rand_b, noise)
     else:
         from tes_b200 import optfunc
+        randn_W, rand_b, noise = np.random.randn(S, F, d), np.random.rand(S, F, 1), np.random.randn(S, F, 1)
         theta, W, b = optfunc.draw_random_init_weights_features_np(d, S, F, X, Y, hyp["l"].reshape(1, d), hyp["sigma"],
                                                                    hyp["sigma0"], draws=(randn_W, rand_b, noise))
-    return dict(name=name, desc=desc, d=d, N=N, S=S, F=F, n=n, t_max=t_max, hyp=hyp, X=X, Y=Y,
-                cand=np.ascontiguousarray(cand), theta=np.ascontiguousarray(theta.reshape(S, F)),
-                W=np.ascontiguousarray(W), b=np.ascontiguousarray(b.reshape(S, F)))
+    wl.update(name=name, hyp=hyp, X=X, Y=Y, cand=np.ascontiguousarray(cand),
+              theta=np.ascontiguousarray(theta.reshape(-1, F)), W=np.ascontiguousarray(W),
+              b=np.ascontiguousarray(b.reshape(-1, F)))
+    return wl
 
 
 class ClockSampler:
@@ -154,19 +205,21 @@ def cpu_step(wl, n_cand, n_samp, seed=0):
     from oracle import pipeline_np
     cand = wl["cand"][:n_cand]
     t0 = time.perf_counter()
+    kw = step_kwargs(wl)
+    kw["ntestsample"] = min(kw["ntestsample"], max(1000, 64 * min(wl["t_max"], n_samp)))
     out = pipeline_np.tes_step(cand, wl["X"], wl["Y"], wl["hyp"]["l"], wl["hyp"]["sigma"], wl["hyp"]["sigma0"],
                                wl["theta"][:n_samp].reshape(n_samp, wl["F"], 1), wl["W"][:n_samp],
-                               wl["b"][:n_samp].reshape(n_samp, wl["F"], 1), criterion="ftl", mode="empirical",
-                               deterministic=True, ntestsample=max(1000, 64 * min(wl["t_max"], n_samp)),
-                               seed=seed, t_max=wl["t_max"])
+                               wl["b"][:n_samp].reshape(n_samp, wl["F"], 1), seed=seed, **kw)
     dt = time.perf_counter() - t0
     return cand.shape[0] * n_samp, dt, out
 
 
 def cpu_sample_sizes(wl):
     # ~10-30 s of CPU work on a few cores: F*(d+13) fp64 ops per pair at ~1e8 feature-evals/s/core
-    if wl["name"] == "c3":
+    if wl.get("name", "") == "c3" or (wl["d"] == 6 and wl["N"] == 10 ** 6):
         return 16384, 128
+    if wl["q"] > 1:  # the oracle materialises the (Y, S', S', nx, K, q) tensor of evaluate_batch_sample_mp.py:347-365
+        return min(wl["N"], 256), min(wl["S"], 64)
     return min(wl["N"], 4096), min(wl["S"], 64)
 
 
@@ -189,9 +242,7 @@ def run_reference_arm(args, wl, rank):
         "impl": "reference", "metric": "acq evals/s (candidates x maximizer samples)", "value": val, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tmean * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "criterion": "ftl", "mode": "empirical", "deterministic": True,
-                   "N_per_gpu": wl["N"], "S": wl["S"], "F": wl["F"], "n_obs": wl["n"], "d": wl["d"],
-                   "t_max": wl["t_max"]},
+        "config": config_of(wl),
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -229,8 +280,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = make_workload(args.workload, rank, world)
     hyp = wl["hyp"]
-    kw = dict(criterion="ftl", mode="empirical", deterministic=True, ntestsample=max(1000, 64 * wl["t_max"]),
-              t_max=wl["t_max"])
+    kw = step_kwargs(wl)
     shard = acquisition.Shard(wl["N"])
 
     def barrier():
@@ -364,12 +414,10 @@ def main():
             "metric": "acq evals/s (candidates x maximizer samples)", "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "criterion": "ftl", "mode": "empirical", "deterministic": True,
-                       "N_per_gpu": wl["N"], "S": wl["S"], "F": wl["F"], "n_obs": wl["n"], "d": wl["d"],
-                       "t_max": wl["t_max"], "T": out.get("T"), "Sp": out.get("Sp"),
-                       "n_unique_maximizers": out.get("n_unique_maximizers"),
-                       "l2": "flushed between timed iterations (256 MiB memset)",
-                       "sharding": "candidates contiguous per rank; NCCL all-gather of (value,index) partials only"},
+            "config": dict(config_of(wl), T=out.get("T"), Sp=out.get("Sp"), K=out.get("K"),
+                           n_unique_maximizers=out.get("n_unique_maximizers"),
+                           l2="flushed between timed iterations (256 MiB memset)",
+                           sharding="candidates contiguous per rank; NCCL all-gather of (value,index) partials only"),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_s / args.steps * 1e3},

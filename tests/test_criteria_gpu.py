@@ -185,3 +185,64 @@ def test_c4_shapes_batch_tes_sp_philox():
     a2 = ops.sp_acq(xb[2:], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invpNK"][0],
                     p[keep], P, msk, niter=I, nysample=Yn, seed=seed, n_global=nx, x_offset=2).cpu().numpy()
     np.testing.assert_array_equal(np.concatenate([a1, a2]), a)
+
+
+@pytest.mark.parametrize("q,Sp,K,Yn,I", [(1, 2, 5, 1, 1), (1, 30, 37, 7, 2), (2, 3, 70, 5, 1), (3, 9, 20, 4, 2),
+                                         (4, 17, 33, 9, 1), (8, 32, 43, 8, 1), (8, 40, 21, 3, 1), (5, 100, 12, 2, 1),
+                                         (6, 8, 64, 16, 1)])
+@pytest.mark.parametrize("use_seed", [False, True])
+def test_tes_sp_whitened_kernel_matches_direct_kernel(monkeypatch, q, Sp, K, Yn, I, use_seed):
+    """csrc/sp2.cuh (whitened residuals nu_j + z - nu_j', fixed LSE shift, table-driven exp; the default) against the
+    direct kernel (y = mu + L z, triangular solve per log-density, max-shifted LSE, libm exp) on the same inputs:
+    lane-group shapes G = 4...32, several rounds of components, ragged validity masks, ny not a multiple of the
+    register block.  The direct kernel is the one the oracle tests pinned first; both are also checked against the
+    oracle by the tests above (whichever is the default)."""
+    from tes_b200 import ops
+    rs = np.random.RandomState(1000 * q + Sp)
+    d, n, T, nx = 3, 7, Sp, 5
+    l, sigma, sigma0 = np.array([4.0, 2.5, 6.0]), 1.1, 1e-3
+    X, Y, test_xs = rs.rand(n, d), rs.randn(n, 1) * 0.4, rs.rand(T, d)
+    ls, sg, s0 = l.reshape(1, d), np.array([sigma]), np.array([sigma0])
+    _, invpNK = onp.get_pNK_test_obs(ls, sg, s0, 1, X, test_xs)
+    p = rs.rand(Sp) + 0.05
+    p /= p.sum()
+    P = rs.randn(Sp, T, K) * 0.7
+    msk = rs.rand(Sp, K) < 0.7
+    msk[:, 0] = True
+    msk[0, :] = True
+    xb = rs.rand(nx, q, d) if q > 1 else rs.rand(nx, d)
+    kw = dict(niter=I, nysample=Yn)
+    if use_seed:
+        kw.update(seed=99, n_global=nx + 3, x_offset=2)
+    else:
+        kw.update(z=rs.normal(size=(I, Yn, Sp, nx, K) + ((q,) if q > 1 else ())))
+    monkeypatch.setenv("TES_SP_METHOD", "1")
+    a = ops.sp_acq(xb, test_xs, X, Y, l, sigma, sigma0, invpNK[0], p, P, msk, **kw).cpu().numpy()
+    monkeypatch.setenv("TES_SP_METHOD", "2")
+    b = ops.sp_acq(xb, test_xs, X, Y, l, sigma, sigma0, invpNK[0], p, P, msk, **kw).cpu().numpy()
+    assert np.all(np.isfinite(a))
+    np.testing.assert_allclose(b, a, rtol=1e-9, atol=1e-11)
+
+
+def test_tes_sp_whitened_kernel_far_components_and_nan():
+    """Components tens of standard deviations apart underflow in the fixed-shift LSE (-inf) where the max-shifted
+    reference gives ~ -1e3: both contribute exp(.) = 0 to the outer LSE.  A NaN joint sample propagates to NaN."""
+    from tes_b200 import ops
+    pr = make_problem(seed=3, d=2, n=5, T=6, nx=4, hyp=BRANIN, mode="sample", nsample=200)
+    p = pr["max_probs"][0]
+    keep = p > 0
+    P, msk = pr["v0"][0][keep].copy(), pr["v1"][0][keep]
+    Sp, K = P.shape[0], P.shape[2]
+    P[0] += 400.0                    # maximizer 0's joint samples sit ~1e4 sigma away from the others
+    z = pr["rs"].normal(size=(1, 2, 3, Sp, 4, K))
+    v0 = pr["v0"].copy()
+    v0[0][np.where(keep)[0][0]] += 400.0
+    acq = ops.sp_acq(pr["x"], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invpNK"][0],
+                     p[keep], P, msk, niter=2, nysample=3, z=z[0]).cpu().numpy()
+    ref = onp.evaluate_sample_mp(pr["x"], pr["ls"], pr["sigmas"], pr["sigma0s"], pr["X"], pr["Y"], 2, 4, 5, 1, 3,
+                                 pr["test_xs"], pr["max_probs"], v0, pr["v1"], pr["invpNK"], niteration=2, z=z)
+    _close(acq, ref)
+    P[1, 0, 0] = np.nan
+    acq = ops.sp_acq(pr["x"], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invpNK"][0],
+                     p[keep], P, msk, niter=2, nysample=3, z=z[0]).cpu().numpy()
+    assert np.all(np.isnan(acq))

@@ -122,3 +122,23 @@ def test_c2_ph_discrete_step(golden, mode, S):
     ref = pipeline_np.tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, z=z, **kw)
     out = acquisition.tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, z=z, **kw)
     _compare(out, ref)
+
+
+@pytest.mark.parametrize("criterion,det,q", [("ftl", False, 1), ("sftl", True, 1), ("sftl", True, 3), ("sftl", True, 8)])
+def test_step_with_counter_based_draws(criterion, det, q):
+    """Monte-Carlo criteria with the counter-based draws of include/tes_spec.h (no host z): the oracle pipeline
+    regenerates the same normals from (seed, iteration, stream, element), so selections are identical and values
+    agree to 1e-6.  q > 1: batch TES_sp (evaluate_batch_sample_mp.py) on every q consecutive candidates (C4 shape)."""
+    from tes_b200 import acquisition
+    d, n, S, F, N = 3, 6, 12, 64, 48
+    rs = np.random.RandomState(40 + q)
+    l, sigma, sigma0 = np.array([9.0, 5.0, 7.0]), 1.3, 1e-3
+    cand, X = rs.rand(N, d), rs.rand(n, d)
+    Y = rs.randn(n, 1) * 0.4
+    theta, W, b = _draw(rs, S, F, X, Y, l, sigma, sigma0)
+    kw = dict(criterion=criterion, mode="empirical", deterministic=det, ntestsample=300, nysample=3, niteration=2,
+              seed=77, return_acq=True, q=q, t_max=4, transform=_transform(cand, X, Y, l, sigma, sigma0, theta, W, b, 4))
+    ref = pipeline_np.tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, **kw)
+    out = acquisition.tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, **kw)
+    assert ref["T"] >= 2 and out["acq"].shape[0] == N // q
+    _compare(out, ref)

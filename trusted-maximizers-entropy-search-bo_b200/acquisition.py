@@ -132,13 +132,19 @@ def select_test_points(max_xs, resolution=1e-3, t_max=None):
 
 def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="empirical", deterministic=True,
              ntestsample=1000, n_min_sample=2, nysample=10, niteration=10, z_joint=None, z=None, seed=0,
-             duplicate_resolution=1e-3, t_max=None, shard=None, return_acq=False, timers=None, transform=None):
+             duplicate_resolution=1e-3, t_max=None, shard=None, return_acq=False, timers=None, transform=None, q=1):
     """One acquisition step for one hyper-parameter sample.  Returns a dict with the query index /
-    point / value and the intermediate sizes.  `criterion`: 'ftl' (TES_ep) or 'sftl' (TES_sp)."""
-    from .criteria import evaluate_mp, evaluate_sample_mp
+    point / value and the intermediate sizes.  `criterion`: 'ftl' (TES_ep) or 'sftl' (TES_sp).
+    `q` > 1 (criterion 'sftl' only): batch TES_sp (evaluate_batch_sample_mp.py) on the queries formed by every `q`
+    consecutive candidates of this rank's slice (nx = N // q batches; the slice length must be a multiple of q);
+    query_idx is then the global batch index and query_x the (q, d) batch."""
+    from .criteria import evaluate_batch_sample_mp, evaluate_mp, evaluate_sample_mp
     cand = dev(cand)
     N, d = cand.shape
     shard = shard or Shard(N)
+    q = int(q)
+    if q > 1 and (criterion != "sftl" or N % q or shard.offset % q):
+        raise ValueError("q > 1 needs criterion='sftl' and candidate slices that are multiples of q")
     Xd, Yd = dev(X), dev(Y).reshape(-1, 1)
     n = Xd.shape[0]
     ls, sigmas, sigma0s = np.asarray(l, dtype=np.float64).reshape(1, d), np.array([sigma]), np.array([sigma0])
@@ -171,6 +177,11 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
         acq = evaluate_mp.mp(cand, ls, sigmas, sigma0s, Xd, Yd, d, N, n, 1, nysample, dev(test_k), dev(max_probs),
                              dev(v0), dev(v1), invK, invpNK, stochastic=not deterministic, niteration=niteration,
                              z=z, seed=seed, n_global=shard.n_global, x_offset=shard.offset)
+    elif criterion == "sftl" and q > 1:
+        out["K"] = int(v0.shape[-1])
+        acq = evaluate_batch_sample_mp.mp(cand.reshape(N // q, q, d), ls, sigmas, sigma0s, Xd, Yd, d, n, 1, nysample,
+                                          dev(test_k), dev(max_probs), dev(v0), v1, invpNK, niteration=niteration,
+                                          z=z, seed=seed, n_global=shard.n_global // q, x_offset=shard.offset // q)
     elif criterion == "sftl":
         out["K"] = int(v0.shape[-1])
         acq = evaluate_sample_mp.mp(cand, ls, sigmas, sigma0s, Xd, Yd, d, N, n, 1, nysample, dev(test_k),
@@ -182,13 +193,13 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
     # arg-max over all candidates, first maximum wins (bo_discrete.py:806, :1053-1055)
     li, lv = ops.argmax(acq)
     pair_v = shard.all_gather(lv.reshape(1))
-    pair_i = shard.all_gather((li + shard.offset).reshape(1))
+    pair_i = shard.all_gather((li + shard.offset // q).reshape(1))
     qi, qv = ops.topk_merge(pair_v.reshape(-1, 1, 1), pair_i.reshape(-1, 1, 1))
     qidx = int(qi[0, 0])
-    loc = qidx - shard.offset
-    qx = torch.zeros(d, dtype=torch.float64, device=cand.device)
-    if 0 <= loc < N:
-        qx = cand[loc].clone()
+    loc = qidx - shard.offset // q
+    qx = torch.zeros(d if q == 1 else (q, d), dtype=torch.float64, device=cand.device)
+    if 0 <= loc < N // q:
+        qx = cand[loc].clone() if q == 1 else cand[loc * q:(loc + 1) * q].clone()
     qx = shard.sum(qx)
     out.update(query_idx=qidx, query_val=float(qv[0, 0]), query_x=qx.cpu().numpy())
     if return_acq:

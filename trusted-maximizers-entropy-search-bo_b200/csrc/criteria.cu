@@ -8,8 +8,11 @@
 //
 // One hyper-parameter sample per call (the reference loops `for i in range(nhyp)` and averages).
 // The caller passes only the maximizers with max_probs > 0 (evaluate_mp.py:169-173).
+#include <cstdlib>
+
 #include "gemm.cuh"
 #include "gp.cuh"
+#include "sp2.cuh"
 
 namespace tes {
 
@@ -670,6 +673,25 @@ static int run_sp_chunk(const SpPlan& pl, const double* xq, int64_t rows, int d,
     sp_cov_kernel<Q><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(xq, d, l, sigma, sigma0, Gc, m + 1, Kc, m, m, rows,
                                                                      Lmat, Linv, info);
     TES_LAUNCH_OK();
+    // whitened kernel (sp2.cuh) whenever nu fits in shared memory; TES_SP_METHOD=1 forces the direct kernel
+    const char* force = std::getenv("TES_SP_METHOD");
+    int nw2 = 0;
+    if (!(force && force[0] == '1') && K <= 65535) {
+        for (int nw = 16; nw >= 4 && !nw2; nw >>= 1) {
+            Sp2Smem L2 = sp2_layout(Q, Sp, K, nw);
+            if (L2.rounds <= 4 && L2.bytes <= 216 * 1024) nw2 = nw;
+        }
+    }
+    if (nw2) {
+        Sp2Smem L2 = sp2_layout(Q, Sp, K, nw2);
+        auto k2 = sp2_kernel<Q>;
+        TES_CUDA_OK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2.bytes));
+        int64_t grid2 = rows < 148 * 4 ? rows : 148 * 4;
+        k2<<<(unsigned)grid2, nw2 * 32, L2.bytes, st>>>(Mq, bq, Linv, Lmat, P, mask, p, rows, Sp, (int)T, K, niter, ny, z,
+                                                        z_n, z_x0, seed, n_global, x_global0, out);
+        TES_LAUNCH_OK();
+        return 0;
+    }
     auto kern = sp_kernel<Q>;
     if (pl.smem > 48 * 1024)
         TES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
