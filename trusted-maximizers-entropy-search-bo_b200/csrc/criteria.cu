@@ -389,38 +389,61 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// cov_y = k_x - k invpNK k^T + sigma0 I (q x q), its Cholesky factor and inverse, per query.
-// Kxx via the reference's expansion (utils.computeKmm, utils.py:740-762).
+// cov_y = k_x - k invpNK k^T + sigma0 I (q x q), its Cholesky factor and inverse, per query
+// (evaluate_batch_sample_mp.py:152, :251, :306-310).
+// One WARP per query: lanes stride the m = T + n columns (coalesced reads of the q rows of G and of Kc),
+// each lane keeps the q(q+1)/2 partial dot products in registers, butterfly reductions leave the full q x q matrix in
+// every lane, which then runs the (tiny, branch-uniform) Cholesky + triangular inverse redundantly; lane e writes
+// entries e, e+32 of the outputs.  (A thread-per-query version read 2 q m doubles per thread with a row-sized stride:
+// 143 ms at C4; this one is bandwidth-bound on the L2-resident chunk.)
 template <int Q>
-__global__ void sp_cov_kernel(const double* __restrict__ x, int d, const double* __restrict__ l, double sigma,
-                              double sigma0, const double* __restrict__ G, int64_t ldg, const double* __restrict__ Kc,
-                              int64_t ldk, int64_t m, int64_t rows, double* __restrict__ Lmat,
-                              double* __restrict__ Linv, int* __restrict__ info) {
-    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+    sp_cov_warp_kernel(const double* __restrict__ x, int d, const double* __restrict__ l, double sigma, double sigma0,
+                       const double* __restrict__ G, int64_t ldg, const double* __restrict__ Kc, int64_t ldk, int64_t m,
+                       int64_t rows, double* __restrict__ Lmat, double* __restrict__ Linv, int* __restrict__ info) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     double c[Q][Q];
+#pragma unroll
     for (int a = 0; a < Q; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < Q; ++b2) c[a][b2] = 0.0;
+    for (int64_t t = lane; t < m; t += 32) {
+        double ga[Q], kb[Q];
+#pragma unroll
+        for (int a = 0; a < Q; ++a) {
+            ga[a] = G[(row * Q + a) * ldg + t];
+            kb[a] = Kc[(row * Q + a) * ldk + t];
+        }
+#pragma unroll
+        for (int a = 0; a < Q; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 <= a; ++b2) c[a][b2] = fma(ga[a], kb[b2], c[a][b2]);
+    }
+#pragma unroll
+    for (int a = 0; a < Q; ++a)
+#pragma unroll
         for (int b2 = 0; b2 <= a; ++b2) {
-            double qa = 0.0, qb = 0.0, dot = 0.0;
+            const double s = warp_sum(c[a][b2]);
+            double qa = 0.0, qb = 0.0, dot = 0.0;   // Kxx via the reference's expansion (utils.py:740-762)
             for (int k = 0; k < d; ++k) {
-                double sl = sqrt(l[k]);
-                double xa = x[(row * Q + a) * d + k] * sl, xb = x[(row * Q + b2) * d + k] * sl;
+                const double sl = sqrt(l[k]);
+                const double xa = x[(row * Q + a) * d + k] * sl, xb = x[(row * Q + b2) * d + k] * sl;
                 qa = fma(xa, xa, qa);
                 qb = fma(xb, xb, qb);
                 dot = fma(xa, xb, dot);
             }
-            double kxx = sigma * exp(-0.5 * ((qa + qb) - 2.0 * dot));
-            double s = 0.0;
-            const double* ga = G + (row * Q + a) * ldg;
-            const double* kb = Kc + (row * Q + b2) * ldk;
-            for (int64_t t = 0; t < m; ++t) s = fma(ga[t], kb[t], s);
+            const double kxx = sigma * exp(-0.5 * ((qa + qb) - 2.0 * dot));
             c[a][b2] = kxx - s + (a == b2 ? sigma0 : 0.0);
         }
-    // Cholesky (lower), in place
     bool bad = false;
+#pragma unroll
     for (int a = 0; a < Q; ++a) {
+#pragma unroll
         for (int b2 = 0; b2 <= a; ++b2) {
             double s = c[a][b2];
+#pragma unroll
             for (int k = 0; k < b2; ++k) s -= c[a][k] * c[b2][k];
             if (a == b2) {
                 if (!(s > 0.0)) bad = true;
@@ -430,24 +453,33 @@ __global__ void sp_cov_kernel(const double* __restrict__ x, int d, const double*
             }
         }
     }
-    // inverse of lower-triangular
     double inv[Q][Q];
+#pragma unroll
     for (int a = 0; a < Q; ++a)
+#pragma unroll
         for (int b2 = 0; b2 < Q; ++b2) inv[a][b2] = 0.0;
+#pragma unroll
     for (int col = 0; col < Q; ++col) {
         inv[col][col] = 1.0 / c[col][col];
+#pragma unroll
         for (int a = col + 1; a < Q; ++a) {
             double s = 0.0;
+#pragma unroll
             for (int k = col; k < a; ++k) s -= c[a][k] * inv[k][col];
             inv[a][col] = s / c[a][a];
         }
     }
+#pragma unroll
     for (int a = 0; a < Q; ++a)
+#pragma unroll
         for (int b2 = 0; b2 < Q; ++b2) {
-            Lmat[row * Q * Q + a * Q + b2] = b2 <= a ? c[a][b2] : 0.0;
-            Linv[row * Q * Q + a * Q + b2] = inv[a][b2];
+            const int e = a * Q + b2;
+            if ((e & 31) == lane) {
+                Lmat[row * Q * Q + e] = b2 <= a ? c[a][b2] : 0.0;
+                Linv[row * Q * Q + e] = inv[a][b2];
+            }
         }
-    if (bad && info) atomicAdd(info, 1);
+    if (bad && info && lane == 0) atomicAdd(info, 1);
 }
 
 __global__ void const_fill_kernel(double* out, int64_t n, const double* __restrict__ p, int64_t Sp) {
@@ -670,8 +702,8 @@ static int run_sp_chunk(const SpPlan& pl, const double* xq, int64_t rows, int d,
     if ((rc = launch_gemm(Kc, m, Bext, m + 1, 1, Gc, m + 1, nr, m + 1, m, st))) return rc;
     extract_mb2_kernel<<<(unsigned)((nr * (T + 1) + 255) / 256), 256, 0, st>>>(Gc, nr, m, T, Mq, bq);
     TES_LAUNCH_OK();
-    sp_cov_kernel<Q><<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(xq, d, l, sigma, sigma0, Gc, m + 1, Kc, m, m, rows,
-                                                                     Lmat, Linv, info);
+    sp_cov_warp_kernel<Q><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(xq, d, l, sigma, sigma0, Gc, m + 1, Kc, m, m, rows,
+                                                                      Lmat, Linv, info);
     TES_LAUNCH_OK();
     // whitened kernel (sp2.cuh) whenever nu fits in shared memory; TES_SP_METHOD=1 forces the direct kernel
     const char* force = std::getenv("TES_SP_METHOD");

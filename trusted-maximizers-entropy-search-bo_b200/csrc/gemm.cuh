@@ -130,17 +130,19 @@ __device__ __forceinline__ void gemm_store_b(double (*bs)[GEMM_LDB_S], int t, co
 template <class AProv>
 __device__ __forceinline__ void gemm_mainloop(const AProv& ap, const double* __restrict__ B, int64_t ldb, int64_t K,
                                               int64_t N, int64_t row0, int64_t col0, GemmSmem& sm,
-                                              double acc[4][4][2]) {
+                                              double acc[4][4][2], int64_t kbeg = 0) {
     const int t = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
     double ra[8], rb[4];
     const int64_t nk = (K + GEMM_BK - 1) / GEMM_BK;
-    ap.load(row0, 0, t, ra);
-    gemm_load_b(B, ldb, K, N, 0, col0, t, rb);
-    ap.store(sm.a[0], t, ra);
-    gemm_store_b(sm.b[0], t, rb);
+    const int64_t kt0 = kbeg / GEMM_BK;   // slices below kbeg are known to be zero (triangular operands)
+    if (kt0 >= nk) return;
+    ap.load(row0, kt0 * GEMM_BK, t, ra);
+    gemm_load_b(B, ldb, K, N, kt0 * GEMM_BK, col0, t, rb);
+    ap.store(sm.a[kt0 & 1], t, ra);
+    gemm_store_b(sm.b[kt0 & 1], t, rb);
     __syncthreads();
-    for (int64_t kt = 0; kt < nk; ++kt) {
+    for (int64_t kt = kt0; kt < nk; ++kt) {
         const int cur = (int)(kt & 1);
         if (kt + 1 < nk) {
             ap.load(row0, (kt + 1) * GEMM_BK, t, ra);

@@ -66,7 +66,7 @@ int launch_se_ard(const double* x, int64_t N, const double* xb, int64_t m, int d
 template <class AProv>
 __device__ __forceinline__ void gemm_body(const AProv& ap, const double* __restrict__ B, int64_t sbk, int64_t sbn,
                                           double* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                                          double alpha, double beta, int tri) {
+                                          double alpha, double beta, int tri, int kskip = 0) {
     extern __shared__ __align__(16) unsigned char gemm_smem_raw[];
     GemmSmem& sm = *reinterpret_cast<GemmSmem*>(gemm_smem_raw);
     const int64_t row0 = (int64_t)blockIdx.x * GEMM_BM;
@@ -79,7 +79,8 @@ __device__ __forceinline__ void gemm_body(const AProv& ap, const double* __restr
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     if (sbn == 1) {
-        gemm_mainloop(ap, B, sbk, K, N, row0, col0, sm, acc);
+        const int64_t kbeg = kskip == 1 ? (row0 > col0 ? row0 : col0) : (kskip == 2 ? col0 : 0);
+        gemm_mainloop(ap, B, sbk, K, N, row0, col0, sm, acc, kbeg);
     } else {
         double ra[8], rb[4];
         const int64_t nk = (K + GEMM_BK - 1) / GEMM_BK;
@@ -139,10 +140,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
     double* C = g.C + bz * g.batchC;
     if (TRANSA) {
         ATrans ap{A, g.lda, g.M, g.K};
-        gemm_body(ap, B, g.sbk, g.sbn, C, g.ldc, g.M, g.N, g.K, g.alpha, g.beta, g.tri);
+        gemm_body(ap, B, g.sbk, g.sbn, C, g.ldc, g.M, g.N, g.K, g.alpha, g.beta, g.tri, g.kskip);
     } else {
         APlain ap{A, g.lda, g.M, g.K};
-        gemm_body(ap, B, g.sbk, g.sbn, C, g.ldc, g.M, g.N, g.K, g.alpha, g.beta, g.tri);
+        gemm_body(ap, B, g.sbk, g.sbn, C, g.ldc, g.M, g.N, g.K, g.alpha, g.beta, g.tri, g.kskip);
     }
 }
 

@@ -14,6 +14,8 @@ struct GemmArgs {
     int64_t M, N, K;
     double alpha, beta;
     int tri;     // skip CTA tiles strictly above the diagonal
+    int kskip;   // triangular operands (sbn == 1 only): 1 = both op(A)(row,k) and B'(k,col) vanish for k < row resp. k < col
+                 // (X^T X with X lower-triangular): start at k = max(row0, col0); 2 = B'(k,col) = 0 for k < col: start at col0
     int batch;   // grid.z
 };
 int launch_gemm_ex(const GemmArgs& g, cudaStream_t st);

@@ -23,12 +23,20 @@ namespace tes {
 
 constexpr int CH_NB = 64;
 constexpr int CH_LD = CH_NB + 1;
-constexpr size_t CH_SMEM = 2 * CH_NB * CH_LD * sizeof(double) + 16;
+constexpr size_t CH_SMEM = (2 * CH_NB * CH_LD + 5 * CH_NB) * sizeof(double) + 16;
 
-// One CTA per matrix.  Loads the nb x nb diagonal block at (k0,k0) of A (ld = m), factors it in
-// shared memory, writes L (lower, upper zeroed) to Lout at the same position and inv(L) to
-// Dinv[b][blk] (CH_NB x CH_NB, ld CH_NB, zero padded).  If ainv != NULL (m <= 64 path) also writes
-// inv(L)^T inv(L) there.
+// One CTA per matrix.  Loads the nb x nb diagonal block at (k0,k0) of A (ld = m), factors it, writes L (lower,
+// upper zeroed) to Lout at the same position and inv(L) to Dinv[b][blk] (CH_NB x CH_NB, ld CH_NB, zero padded).
+// If ainv != NULL (m <= 64 path) also writes inv(L)^T inv(L) there.
+//
+// Register-tiled right-looking factorisation: the 256 threads form a 16 x 16 grid and thread (ti, tj) owns the 4 x 4
+// cyclic sub-matrix {(ti + 16 a, tj + 16 b)} in registers (the trailing matrix shrinks evenly over the threads).
+// Step k: the owners of column k have published its (unscaled) entries c; with r = rsqrt(c_k) every thread applies
+// a_ij -= (c_i r)(c_j r) to its registers, the column owners keep L_ik = c_i r, and the owners of column k+1 publish
+// their freshly updated entries -- ONE barrier per step, no serial section (the previous version ran sqrt on thread 0
+// between three barriers per step and inverted L with one thread per column: 0.44 ms for 1024 64 x 64 matrices).
+// The triangular inverse X = L^-1 runs the same way: X starts as I, step k publishes row k scaled by 1/L_kk = r_k and
+// every thread applies x_ij -= L_ik x_kj.  Blocks narrower than 64 are padded with the identity.
 __global__ void __launch_bounds__(256)
     potrf_diag_kernel(const double* __restrict__ A, int64_t m, int64_t k0, int nb, double* __restrict__ Lout,
                       double* __restrict__ Dinv, int64_t dinv_batch_stride, int* __restrict__ info,
@@ -36,45 +44,105 @@ __global__ void __launch_bounds__(256)
     extern __shared__ __align__(16) double chsm[];
     double (*a)[CH_LD] = reinterpret_cast<double (*)[CH_LD]>(chsm);
     double (*x)[CH_LD] = a + CH_NB;
-    int& bad = *reinterpret_cast<int*>(x + CH_NB);
+    double* colbuf = reinterpret_cast<double*>(x + CH_NB);   // [2][64]
+    double* rowbuf = colbuf + 2 * CH_NB;                      // [2][64]
+    double* rdiag = rowbuf + 2 * CH_NB;                       // [64]  1 / L_kk
+    int& bad = *reinterpret_cast<int*>(rdiag + CH_NB);
     const int64_t b = blockIdx.x;
     const double* Ab = A + b * m * m;
     const int t = threadIdx.x;
+    const int ti = t >> 4, tj = t & 15;
     if (t == 0) bad = 0;
     for (int e = t; e < CH_NB * CH_NB; e += 256) {
         int i = e / CH_NB, j = e % CH_NB;
-        a[i][j] = (i < nb && j < nb && j <= i) ? Ab[(k0 + i) * m + k0 + j] : 0.0;
-        x[i][j] = 0.0;
+        a[i][j] = (i < nb && j < nb && j <= i) ? Ab[(k0 + i) * m + k0 + j] : ((i == j && i >= nb) ? 1.0 : 0.0);
     }
     __syncthreads();
-    for (int k = 0; k < nb; ++k) {
+    double r[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[p][q] = a[ti + 16 * p][tj + 16 * q];
+    if (tj == 0) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) colbuf[ti + 16 * p] = r[p][0];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < CH_NB; ++k) {
+        const double* cb = colbuf + (k & 1) * CH_NB;
+        const double dkk = cb[k];
+        const double rs = rsqrt(dkk);
         if (t == 0) {
-            double dkk = a[k][k];
-            if (!(dkk > 0.0) && bad == 0) bad = k + 1;
-            a[k][k] = sqrt(dkk);
+            if (!(dkk > 0.0) && bad == 0 && k < nb) bad = k + 1;
+            rdiag[k] = rs;
         }
-        __syncthreads();
-        const double inv = 1.0 / a[k][k];
-        for (int i = k + 1 + t; i < nb; i += 256) a[i][k] *= inv;
-        __syncthreads();
-        // trailing update of the lower triangle: pairs (i, j), k < j <= i < nb
-        const int r = nb - k - 1;
-        for (int e = t; e < r * r; e += 256) {
-            int i = k + 1 + e / r, j = k + 1 + e % r;
-            if (j <= i) a[i][j] = fma(-a[i][k], a[j][k], a[i][j]);
+        double ci[4], cj[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            ci[p] = cb[ti + 16 * p] * rs;
+            cj[p] = cb[tj + 16 * p] * rs;
+        }
+        const int k1 = k + 1;
+        double* nb_ = colbuf + (k1 & 1) * CH_NB;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = tj + 16 * q;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int i = ti + 16 * p;
+                if (j > k && i >= j) r[p][q] = fma(-ci[p], cj[q], r[p][q]);
+                if (j == k) r[p][q] = i > k ? ci[p] : (i == k ? dkk * rs : r[p][q]);  // column k is final: L_ik
+                if (j == k1) nb_[i] = r[p][q];                                         // publish column k+1
+            }
         }
         __syncthreads();
     }
-    // triangular inverse, one thread per column
-    if (t < nb) {
-        const int j = t;
-        x[j][j] = 1.0 / a[j][j];
-        for (int i = j + 1; i < nb; ++i) {
-            double s = 0.0;
-            for (int k = j; k < i; ++k) s = fma(a[i][k], x[k][j], s);
-            x[i][j] = -s / a[i][i];
+    // L (lower) to shared memory; X = I in registers
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = ti + 16 * p, j = tj + 16 * q;
+            a[i][j] = j <= i ? r[p][q] : 0.0;
+            r[p][q] = i == j ? 1.0 : 0.0;
         }
+    if (ti == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rowbuf[tj + 16 * q] = r[0][q] * rdiag[0];
     }
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < CH_NB; ++k) {
+        const double* rb = rowbuf + (k & 1) * CH_NB;
+        double xk[4], lk[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            xk[p] = rb[tj + 16 * p];
+            lk[p] = a[ti + 16 * p][k];
+        }
+        const int k1 = k + 1;
+        double* nr = rowbuf + (k1 & 1) * CH_NB;
+        const double rs1 = rdiag[k1 < CH_NB ? k1 : 0];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int i = ti + 16 * p;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (i > k) r[p][q] = fma(-lk[p], xk[q], r[p][q]);
+                else if (i == k) r[p][q] = xk[q];
+                if (i == k1) nr[tj + 16 * q] = r[p][q] * rs1;   // publish row k+1 scaled by 1 / L_{k+1,k+1}
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = ti + 16 * p, j = tj + 16 * q;
+            x[i][j] = (j <= i && i < nb) ? r[p][q] : 0.0;
+        }
     __syncthreads();
     double* Lb = Lout + b * m * m;
     for (int e = t; e < nb * nb; e += 256) {
@@ -119,6 +187,23 @@ __global__ void copy_diag_inv_kernel(const double* __restrict__ Dinv, int64_t ds
     int i = (int)(r % CH_NB);
     int64_t c = blk * CH_NB + j;
     if (c < m && j <= i) X[b * m * m + r * m + c] = Dinv[b * dstride + blk * CH_NB * CH_NB + i * CH_NB + j];
+}
+
+// A[b][i][j] = A[b][j][i] for j > i (32 x 32 tiles through shared memory: coalesced on both sides)
+__global__ void mirror_lower_kernel(double* __restrict__ A, int64_t m) {
+    __shared__ double tile[32][33];
+    const int64_t bi = blockIdx.y, bj = blockIdx.x;   // destination tile (rows bi, cols bj), strictly-upper elements
+    if (bj < bi) return;
+    double* Ab = A + (int64_t)blockIdx.z * m * m;
+    for (int r = threadIdx.y; r < 32; r += 8) {        // source tile (rows bj, cols bi)
+        const int64_t sr = bj * 32 + r, sc = bi * 32 + threadIdx.x;
+        tile[r][threadIdx.x] = (sr < m && sc < m) ? Ab[sr * m + sc] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int64_t dr = bi * 32 + r, dc = bj * 32 + threadIdx.x;
+        if (dr < m && dc < m && dc > dr) Ab[dr * m + dc] = tile[threadIdx.x][r];
+    }
 }
 
 struct CholPlan {
@@ -210,6 +295,7 @@ static int chol_run(const double* A, int64_t batch, int64_t m, double* L, double
         g.B = X; g.sbk = m; g.sbn = 1; g.batchB = mm;
         g.C = S; g.ldc = m; g.batchC = CH_NB * m;
         g.M = nb; g.N = i0; g.K = i0; g.alpha = 1.0; g.beta = 0.0; g.tri = 0; g.batch = (int)batch;
+        g.kskip = 2;   // X[:i0, :i0] is lower-triangular: rows k < col contribute nothing
         if ((rc = launch_gemm_ex(g, st))) return rc;
         GemmArgs h{};
         h.A = Dinv + ib * CH_NB * CH_NB; h.lda = CH_NB; h.transa = 0; h.batchA = dstride;
@@ -218,13 +304,18 @@ static int chol_run(const double* A, int64_t batch, int64_t m, double* L, double
         h.M = nb; h.N = i0; h.K = nb; h.alpha = -1.0; h.beta = 0.0; h.tri = 0; h.batch = (int)batch;
         if ((rc = launch_gemm_ex(h, st))) return rc;
     }
-    // A^-1 = X^T X
+    // A^-1 = X^T X: lower tiles only, k from max(row0, col0) (X lower-triangular), then mirrored (X^T X is
+    // bit-symmetric: the same products in the same order) -- m^3/3 flops instead of 2 m^3
     GemmArgs f{};
     f.A = X; f.lda = m; f.transa = 1; f.batchA = mm;
     f.B = X; f.sbk = m; f.sbn = 1; f.batchB = mm;
     f.C = Ainv; f.ldc = m; f.batchC = mm;
-    f.M = m; f.N = m; f.K = m; f.alpha = 1.0; f.beta = 0.0; f.tri = 0; f.batch = (int)batch;
-    return launch_gemm_ex(f, st);
+    f.M = m; f.N = m; f.K = m; f.alpha = 1.0; f.beta = 0.0; f.tri = 1; f.kskip = 1; f.batch = (int)batch;
+    if ((rc = launch_gemm_ex(f, st))) return rc;
+    dim3 mg((unsigned)((m + 31) / 32), (unsigned)((m + 31) / 32), (unsigned)batch);
+    mirror_lower_kernel<<<mg, dim3(32, 8), 0, st>>>(Ainv, m);
+    TES_LAUNCH_OK();
+    return 0;
 }
 
 }  // namespace tes
