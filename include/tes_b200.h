@@ -147,7 +147,10 @@ int tes_batched_chol2inv_f64(const double* A, int64_t batch, int64_t m, double* 
  *   mode 1 draws: z != NULL -> host-supplied standard normals, layout (niter, nysample, Sp, N);
  *                 z == NULL -> Philox (include/tes_spec.h) keyed by (seed, iteration) and the
  *                 logical element (iy*Sp + j)*n_global + (x_offset + x), so results do not depend
- *                 on how candidates are sharded;
+ *                 on how candidates are sharded; n_global < 0 -> SHARED draws: every candidate
+ *                 consumes the same normals (element iy*Sp + j), i.e. common random numbers for
+ *                 the finite-difference gradients of the criterion refinement
+ *                 (utils_for_continuous.py:62-87);
  *   out_acq (N); out_mean / out_var (N,Sp), optional (NULL to skip): candidate-major moments.
  * NaN semantics follow the reference (no variance clipping before sqrt). */
 int64_t tes_ep_acq_workspace_bytes(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp);
@@ -161,7 +164,8 @@ int tes_ep_acq_f64(int mode, const double* x, int64_t N, int64_t d, const double
 /* TES_sp acquisition, q = 1 (criteria/evaluate_sample_mp.py:132-336) or batch q <= 8
  * (criteria/evaluate_batch_sample_mp.py:160-382).  x (nx, q, d); post_samples (Sp,T,K);
  * post_mask (Sp,K) bytes (1 = valid); z layout (niter, nysample, Sp, nx, K, q) or NULL for Philox
- * (element ((iy*Sp + j)*n_global + x_offset + x)*K + s)*q + c).  out_acq (nx). */
+ * (element ((iy*Sp + j)*n_global + x_offset + x)*K + s)*q + c; n_global < 0: shared draws, the
+ * query index drops out of the element).  out_acq (nx). */
 int64_t tes_sp_acq_workspace_bytes(int64_t nx, int q, int64_t T, int64_t n, int64_t d, int64_t Sp, int64_t K);
 int tes_sp_acq_f64(const double* x, int64_t nx, int q, int64_t d, const double* test_xs, int64_t T, const double* X,
                    int64_t n, const double* Y, const double* l, double sigma, double sigma0, const double* invpNK,

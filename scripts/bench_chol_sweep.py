@@ -8,7 +8,7 @@ matrix) against the measured fp64 / HBM peaks, and a CPU baseline (the numpy ora
 the same stack, all host cores through BLAS).  The batch is sharded across ranks without any collective
 (torchrun --nproc-per-node N); the reported rate is the whole job's (max time over ranks).
 
-  python scripts/bench_chol_sweep.py [--batch 1024] [--m 64 128 ...] [--reps 3] [--no-cpu]"""
+  python scripts/bench_chol_sweep.py [--batch 1024] [--sizes 64 128 ...] [--reps 3] [--no-cpu]"""
 import argparse
 import json
 import os
@@ -45,7 +45,7 @@ def build_stack(torch, m, batch, first, device):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=1024)
-    ap.add_argument("--m", type=int, nargs="*", default=[64, 128, 256, 512, 1024, 2048])
+    ap.add_argument("--sizes", dest="m", type=int, nargs="*", default=[64, 128, 256, 512, 1024, 2048])
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -62,3 +62,127 @@ def test_discrete_bo_runs_with_the_device_factor_and_rff_sampler(golden, tmp_pat
     assert np.all(d == 0.0)
     bo_discrete.save(out, str(tmp_path), "ftl")
     assert np.array_equal(np.load(str(tmp_path / "ftl_xx.npy")), out["xx"])
+
+
+# ---- bo_batch.py loop (continuous domain, batch queries, Adam refinement of maximisers and criterion) ------------
+class _OracleBackend:
+    """Oracle-backed stand-ins with the signatures the re-hosted bo_batch loop calls, so the SAME control flow can
+    be run on the numpy oracle and its trajectory compared with the device run."""
+
+    def __init__(self):
+        from oracle import c_oracle as co
+        self.co = co
+
+    # utils
+    def precomputeInvKs(self, xdim, nhyp, ls, sigmas, sigma0s, X):
+        return onp.precomputeInvKs(ls, sigmas, sigma0s, X)
+
+    def compute_mean_f(self, x, xdim, n_hyp, X, Y, ls, sigmas, sigma0s, invKs):
+        return onp.compute_mean_var_f(np.asarray(x), X, Y, ls[0], sigmas[0], sigma0s[0], invKs[0])[0].reshape(-1)
+
+    def compute_mean_var_f(self, x, X, Y, l, sigma, sigma0, NKInv=None, fullcov=False):
+        return onp.compute_mean_var_f(x, X, Y, l, sigma, sigma0, NKInv, fullcov=fullcov)
+
+    def get_testidxs_stats(self, nhyp, test_xs, means, covs, mode="sample", nsample=1000, n_min_sample=2,
+                           transforms=None):
+        z = np.random.normal(size=(nsample, test_xs.shape[0], 1))[None]          # utils.py:1674
+        return onp.get_testidxs_stats(nhyp, test_xs, means, covs, mode=mode, nsample=nsample, n_min_sample=n_min_sample,
+                                      z=z, transforms=transforms)
+
+    # optfunc
+    def draw_random_init_weights_features_np(self, xdim, S, F, X, Y, l, sigma, sigma0):
+        rW, rb, rn = np.random.randn(S, F, xdim), np.random.rand(S, F, 1), np.random.randn(S, F, 1)
+        return onp.draw_random_init_weights_features(xdim, S, F, X, Y, l, sigma, sigma0, rW, rb, rn)
+
+    # utils_for_continuous
+    def sample_xmaxs_fmaxs(self, xdim, n_hyp, n_funcs, n_features, ls, sigmas, sigma0s, thetas, Ws, bs, init, k,
+                           xmin=None, xmax=None, ntrain=0):
+        idx, _ = self.co.rff_topk(init, Ws[0], bs[0], thetas[0], float(sigmas[0]), k)
+        x0 = init[idx]
+        xr, fr = onp.adam_refine_maximizers(x0, thetas[0], Ws[0], bs[0], float(sigmas[0]), xmin, xmax, ntrain)
+        best = np.argmax(fr, axis=1)
+        rows = np.arange(fr.shape[0])
+        return x0[None], xr[rows, best][None], fr[rows, best][None], idx[None]
+
+    # criteria.evaluate_batch_sample_mp.mp with SHARED counter-based draws (n_global = -1)
+    def batch_sample_mp(self, x, ls, sigmas, sigma0s, X, Y, xdim, nobs, nhyp, nysample, test_xs, max_probs, v0, v1,
+                        invpNK, niteration=10, seed=0, n_global=None):
+        assert n_global == -1
+        x = np.asarray(x)
+        nx, q, _ = x.shape
+        Sp, K = int((np.asarray(max_probs)[0] > 0).sum()), np.asarray(v0).shape[-1]
+        z = np.stack([self.co.normals(seed, it, 2 if q == 1 else 3, 0, nysample * Sp * K * q)   # tes_spec.h streams
+                     .reshape(nysample, Sp, 1, K, q)
+                      for it in range(niteration)])
+        z = np.broadcast_to(z, (niteration, nysample, Sp, nx, K, q))[None]
+        return _Np(onp.evaluate_batch_sample_mp(x, ls, sigmas, sigma0s, np.asarray(X), np.asarray(Y), xdim, nobs, 1,
+                                                nysample, np.asarray(test_xs), np.asarray(max_probs), np.asarray(v0),
+                                                np.asarray(v1), np.asarray(invpNK), niteration=niteration, z=z))
+
+
+class _Np:  # .cpu().numpy() on a numpy result
+    def __init__(self, a):
+        self.a = a
+
+    def cpu(self):
+        return self
+
+    def numpy(self):
+        return self.a
+
+
+def _branin(golden):
+    g = golden("kat_objectives")
+    xs = g["branin_xs"]
+
+    def f(x):  # functions.negative_Branin (functions.py:548-581), restated
+        x = np.asarray(x).reshape(-1, 2)
+        x1, x2 = 15.0 * x[:, 0] - 5.0, 15.0 * x[:, 1]
+        v = (x2 - 5.1 / (4 * np.pi ** 2) * x1 ** 2 + 5.0 / np.pi * x1 - 6.0) ** 2 + 10.0 * (1 - 1 / (8 * np.pi)) * np.cos(x1) + 10.0
+        return -(v - 54.8104) / 51.9496
+    return f, xs, g["branin_l"], float(g["branin_sigma"]), float(g["branin_sigma0"])
+
+
+def _stable_factor(l, sigma, sigma0):
+    """A colouring factor that is a continuous function of its inputs (symmetric eigen-decomposition, ascending order,
+    sign-normalised vectors): the two runs reach the test points through Adam paths that differ by rounding, and
+    LAPACK's general eig (utils.py:1668) may order / sign its vectors differently for such inputs."""
+    def fn(test_xs, X, Y):
+        invK = onp.precomputeInvKs(np.asarray(l).reshape(1, -1), np.array([sigma]), np.array([sigma0]), X)
+        _, cov = onp.compute_mean_var_f(np.asarray(test_xs), X, Y, l, sigma, sigma0, invK[0], fullcov=True)
+        e, v = np.linalg.eigh(0.5 * (cov + cov.T))
+        v = v * np.sign(v[np.argmax(np.abs(v), axis=0), np.arange(v.shape[1])])
+        return v * np.sqrt(np.clip(e, 0.0, np.inf))
+    return fn
+
+
+@pytest.mark.parametrize("q", [1, 2])
+def test_batch_bo_trajectory_matches_oracle_backend(golden, monkeypatch, q):
+    """C1 (script_batch_branin.sh shapes, scaled: nmax 8, nfeature 64, ntrain 25): the device loop and the same loop
+    on the numpy oracle make the same discrete decisions and follow the same trajectory (Adam paths agree to rounding:
+    1e-5 on the query points)."""
+    from tes_b200 import bo_batch
+    import tes_b200.criteria.evaluate_batch_sample_mp as ebs
+    f, xs, l, sigma, sigma0 = _branin(golden)
+    args = dict(criterion="sftl", mode="sample", nquery=2, nrun=1, ninit=3, nmax=8, nfeature=64, nsto=2, ntrain=25,
+                nysample=4, batchsize=q, ntestsample=300, seed=1,
+                transform_fn=_stable_factor(l, sigma, sigma0))
+    out = bo_batch.run(f, xs, 0.0, 1.0, l, sigma, sigma0, **args)
+    ob = _OracleBackend()
+    for name in ("precomputeInvKs", "compute_mean_f", "compute_mean_var_f", "get_testidxs_stats"):
+        monkeypatch.setattr(bo_batch.utils, name, getattr(ob, name))
+    monkeypatch.setattr(bo_batch.optfunc, "draw_random_init_weights_features_np", ob.draw_random_init_weights_features_np)
+    monkeypatch.setattr(bo_batch.utils_for_continuous, "sample_xmaxs_fmaxs", ob.sample_xmaxs_fmaxs)
+    monkeypatch.setattr(ebs, "mp", ob.batch_sample_mp)
+    monkeypatch.setattr(bo_batch, "dev", lambda a: a)
+    monkeypatch.setattr(bo_batch.evaluate_batch_mp_mod(), "get_pNK_test_obs",
+                        lambda ls, sg, s0, nh, X, tx: onp.get_pNK_test_obs(ls, sg, s0, nh, X, tx))
+    ref = bo_batch.run(f, xs, 0.0, 1.0, l, sigma, sigma0, **args)
+    np.testing.assert_array_equal(out["ntest"], ref["ntest"])
+    assert (ref["ntest"] >= 2).any() and np.isfinite(ref["crit_max"]).any()
+    # Adam on finite-difference gradients amplifies the 1e-13 device/numpy differences of the criterion when the
+    # gradient is small (m / sqrt(v)): the paths agree to ~1e-7, the discrete decisions exactly
+    np.testing.assert_allclose(out["xx"], ref["xx"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(out["guess_xx"], ref["guess_xx"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(out["crit_max"], ref["crit_max"], rtol=1e-5, atol=1e-8)
+    assert out["xx"].shape == (1, 3 + 2 * q, 2)

@@ -162,6 +162,9 @@ __global__ void __launch_bounds__(128)
                     int64_t rows, int Sp, double sigma0, int niter, int ny, const double* __restrict__ z,
                     int64_t z_n, int64_t z_x0, uint64_t seed, int64_t n_global, int64_t x_global0,
                     double* __restrict__ out) {
+    // n_global < 0: SHARED draws -- every candidate consumes the same normals (common random numbers for the
+    // finite-difference gradients of the criterion refinement, utils_for_continuous.py:62-87)
+    const int64_t kg_n = n_global < 0 ? 1 : n_global, kg_x0 = n_global < 0 ? 0 : x_global0, kg_rmul = n_global < 0 ? 0 : 1;
     extern __shared__ double sh[];
     double* mu = sh;              // [Sp]
     double* isd = mu + Sp;        // [Sp] 1/std
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(128)
             zz = z[(((int64_t)it * ny + iy) * Sp + j) * z_n + z_x0 + row];
         else
             zz = normal_elem(seed, (uint32_t)it, TES_STREAM_EP_Y,
-                             (uint64_t)(((int64_t)iy * Sp + j) * n_global + x_global0 + row));
+                             (uint64_t)(((int64_t)iy * Sp + j) * kg_n + kg_x0 + row * kg_rmul));
         const double y = fma(sdv[j], zz, mu[j]);
         const double u = (y - mu[j]) * isd[j];
         const double lpc = -0.5 * u * u + (cst[j] - lgp[j]);
@@ -241,6 +244,7 @@ __global__ void __launch_bounds__(256)
               const double* __restrict__ z, int64_t z_n, int64_t z_x0, uint64_t seed, int64_t n_global,
               int64_t x_global0, double* __restrict__ mean_g,  // optional global scratch (rows? no: gridDim.x) x Sp*K*Q
               int mean_in_smem, double* __restrict__ out) {
+    const int64_t kg_n = n_global < 0 ? 1 : n_global, kg_x0 = n_global < 0 ? 0 : x_global0, kg_rmul = n_global < 0 ? 0 : 1;
     extern __shared__ double sh[];
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(256)
                         zz[q] = z[(((((int64_t)it * ny + iy) * Sp + j) * z_n + z_x0 + row) * K + s) * Q + q];
                     else
                         zz[q] = normal_elem(seed, (uint32_t)it, Q == 1 ? TES_STREAM_SP_Y : TES_STREAM_BSP_Y,
-                                            (uint64_t)((((int64_t)iy * Sp + j) * n_global + x_global0 + row) * K + s) * Q + q);
+                                            (uint64_t)((((int64_t)iy * Sp + j) * kg_n + kg_x0 + row * kg_rmul) * K + s) * Q + q);
                 }
 #pragma unroll
                 for (int a = 0; a < Q; ++a) {

@@ -23,7 +23,7 @@ namespace tes {
 
 constexpr int CH_NB = 64;
 constexpr int CH_LD = CH_NB + 1;
-constexpr size_t CH_SMEM = (2 * CH_NB * CH_LD + 5 * CH_NB) * sizeof(double) + 16;
+constexpr size_t CH_SMEM = (CH_NB * CH_LD + 5 * CH_NB) * sizeof(double) + 16;   // 36 KB: 6 CTAs per SM
 
 // One CTA per matrix.  Loads the nb x nb diagonal block at (k0,k0) of A (ld = m), factors it, writes L (lower,
 // upper zeroed) to Lout at the same position and inv(L) to Dinv[b][blk] (CH_NB x CH_NB, ld CH_NB, zero padded).
@@ -43,8 +43,7 @@ __global__ void __launch_bounds__(256)
                       double* __restrict__ ainv) {
     extern __shared__ __align__(16) double chsm[];
     double (*a)[CH_LD] = reinterpret_cast<double (*)[CH_LD]>(chsm);
-    double (*x)[CH_LD] = a + CH_NB;
-    double* colbuf = reinterpret_cast<double*>(x + CH_NB);   // [2][64]
+    double* colbuf = reinterpret_cast<double*>(a + CH_NB);   // [2][64]
     double* rowbuf = colbuf + 2 * CH_NB;                      // [2][64]
     double* rdiag = rowbuf + 2 * CH_NB;                       // [64]  1 / L_kk
     int& bad = *reinterpret_cast<int*>(rdiag + CH_NB);
@@ -85,15 +84,29 @@ __global__ void __launch_bounds__(256)
         }
         const int k1 = k + 1;
         double* nb_ = colbuf + (k1 & 1) * CH_NB;
+        // only blocks p >= q can hold lower-triangle entries (ti, tj < 16): the other 6 are pruned at compile time
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int j = tj + 16 * q;
+            const bool jgt = j > k;
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const int i = ti + 16 * p;
-                if (j > k && i >= j) r[p][q] = fma(-ci[p], cj[q], r[p][q]);
-                if (j == k) r[p][q] = i > k ? ci[p] : (i == k ? dkk * rs : r[p][q]);  // column k is final: L_ik
-                if (j == k1) nb_[i] = r[p][q];                                         // publish column k+1
+            for (int p = q; p < 4; ++p) {
+                if (p > q) {
+                    if (jgt) r[p][q] = fma(-ci[p], cj[q], r[p][q]);
+                } else {
+                    if (jgt && ti >= tj) r[p][q] = fma(-ci[p], cj[q], r[p][q]);
+                }
+            }
+            if (j == k) {   // column k is final: L_ik = c_i r (i > k), L_kk = d r
+#pragma unroll
+                for (int p = q; p < 4; ++p) {
+                    const int i = ti + 16 * p;
+                    r[p][q] = i > k ? ci[p] : (i == k ? dkk * rs : r[p][q]);
+                }
+            }
+            if (j == k1) {  // publish column k+1 (entries above the diagonal are never read)
+#pragma unroll
+                for (int p = q; p < 4; ++p) nb_[ti + 16 * p] = r[p][q];
             }
         }
         __syncthreads();
@@ -112,6 +125,13 @@ __global__ void __launch_bounds__(256)
         for (int q = 0; q < 4; ++q) rowbuf[tj + 16 * q] = r[0][q] * rdiag[0];
     }
     __syncthreads();
+    {
+        double* Lb = Lout + b * m * m;
+        for (int e = t; e < nb * nb; e += 256) {
+            int i = e / nb, j = e % nb;
+            Lb[(k0 + i) * m + k0 + j] = (j <= i) ? a[i][j] : 0.0;
+        }
+    }
 #pragma unroll 1
     for (int k = 0; k < CH_NB; ++k) {
         const double* rb = rowbuf + (k & 1) * CH_NB;
@@ -124,34 +144,37 @@ __global__ void __launch_bounds__(256)
         const int k1 = k + 1;
         double* nr = rowbuf + (k1 & 1) * CH_NB;
         const double rs1 = rdiag[k1 < CH_NB ? k1 : 0];
+        // X is lower-triangular: blocks p < q stay zero and are pruned at compile time
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             const int i = ti + 16 * p;
+            const bool below = i > k;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (i > k) r[p][q] = fma(-lk[p], xk[q], r[p][q]);
-                else if (i == k) r[p][q] = xk[q];
-                if (i == k1) nr[tj + 16 * q] = r[p][q] * rs1;   // publish row k+1 scaled by 1 / L_{k+1,k+1}
+            for (int q = 0; q <= p; ++q)
+                if (below) r[p][q] = fma(-lk[p], xk[q], r[p][q]);
+            if (i == k) {
+#pragma unroll
+                for (int q = 0; q <= p; ++q) r[p][q] = xk[q];
+            }
+            if (i == k1) {  // publish row k+1 scaled by 1 / L_{k+1,k+1}
+#pragma unroll
+                for (int q = 0; q < 4; ++q) nr[tj + 16 * q] = q <= p ? r[p][q] * rs1 : 0.0;
             }
         }
         __syncthreads();
     }
+    // X overwrites L in shared memory (the last step's barrier has passed: nobody reads L any more)
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int i = ti + 16 * p, j = tj + 16 * q;
-            x[i][j] = (j <= i && i < nb) ? r[p][q] : 0.0;
+            a[i][j] = (j <= i && i < nb) ? r[p][q] : 0.0;
         }
     __syncthreads();
-    double* Lb = Lout + b * m * m;
-    for (int e = t; e < nb * nb; e += 256) {
-        int i = e / nb, j = e % nb;
-        Lb[(k0 + i) * m + k0 + j] = (j <= i) ? a[i][j] : 0.0;
-    }
     if (Dinv) {
         double* Db = Dinv + b * dinv_batch_stride;
-        for (int e = t; e < CH_NB * CH_NB; e += 256) Db[e] = x[e / CH_NB][e % CH_NB];
+        for (int e = t; e < CH_NB * CH_NB; e += 256) Db[e] = a[e / CH_NB][e % CH_NB];
     }
     if (ainv) {
         double* Ib = ainv + b * m * m;
@@ -159,7 +182,7 @@ __global__ void __launch_bounds__(256)
             int i = e / nb, j = e % nb;
             int lo = i > j ? i : j;
             double s = 0.0;
-            for (int k = lo; k < nb; ++k) s = fma(x[k][i], x[k][j], s);
+            for (int k = lo; k < nb; ++k) s = fma(a[k][i], a[k][j], s);
             Ib[i * m + j] = s;
         }
     }

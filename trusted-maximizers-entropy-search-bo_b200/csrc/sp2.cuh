@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(512)
                const double* __restrict__ p, int64_t rows, int Sp, int T, int K, int niter, int ny,
                const double* __restrict__ z, int64_t z_n, int64_t z_x0, uint64_t seed, int64_t n_global,
                int64_t x_global0, double* __restrict__ out) {
+    // n_global < 0: SHARED draws (every query consumes the same normals; common random numbers)
+    const int64_t kg_n = n_global < 0 ? 1 : n_global, kg_x0 = n_global < 0 ? 0 : x_global0, kg_rmul = n_global < 0 ? 0 : 1;
     extern __shared__ __align__(16) double sh[];
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(512)
                         const int s = vl[c0 + c];
                         double z0 = 0.0, z1 = 0.0;
                         if (iy < ny) {
-                            const uint64_t e0 = (uint64_t)((((int64_t)iy * Sp + j) * n_global + x_global0 + row) * K + s) * Q + 2 * qp;
+                            const uint64_t e0 = (uint64_t)((((int64_t)iy * Sp + j) * kg_n + kg_x0 + row * kg_rmul) * K + s) * Q + 2 * qp;
                             normal_pair(seed, (uint32_t)it, TES_STREAM_BSP_Y, e0 >> 1, z0, z1);
                         }
                         double* dst = aw + ((size_t)il * CB + c) * Q + 2 * qp;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(512)
                                 zz = z[(((((int64_t)it * ny + iy) * Sp + j) * z_n + z_x0 + row) * K + s) * Q + q];
                             else
                                 zz = normal_elem(seed, (uint32_t)it, Q == 1 ? TES_STREAM_SP_Y : TES_STREAM_BSP_Y,
-                                                 (uint64_t)((((int64_t)iy * Sp + j) * n_global + x_global0 + row) * K + s) * Q + q);
+                                                 (uint64_t)((((int64_t)iy * Sp + j) * kg_n + kg_x0 + row * kg_rmul) * K + s) * Q + q);
                         }
                         aw[((size_t)il * CB + c) * Q + q] = nu[((size_t)q * K + s) * SpS + j] + zz;
                     }
