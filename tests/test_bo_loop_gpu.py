@@ -120,6 +120,37 @@ class _OracleBackend:
                                                 np.asarray(v1), np.asarray(invpNK), niteration=niteration, z=z))
 
 
+    def _shared_z(self, seed, stream, niteration, shape_tail, nx):
+        """Counter-based draws SHARED by all candidates (n_global = -1): z[it][iy][j][x]... with the x axis broadcast."""
+        n = int(np.prod(shape_tail))
+        return np.stack([self.co.normals(seed, it, stream, 0, n).reshape(shape_tail) for it in range(niteration)])
+
+    # criteria.evaluate_sample_mp.mp (TES_sp, q = 1)
+    def sample_mp(self, x, ls, sigmas, sigma0s, X, Y, xdim, nx, nobs, nhyp, nysample, test_xs, max_probs, v0, v1,
+                  invpNK, niteration=10, seed=0, n_global=None):
+        assert n_global == -1
+        Sp, K = int((np.asarray(max_probs)[0] > 0).sum()), np.asarray(v0).shape[-1]
+        z = self._shared_z(seed, 2, niteration, (nysample, Sp, 1, K), nx)
+        z = np.broadcast_to(z, (niteration, nysample, Sp, nx, K))[None]
+        return _Np(onp.evaluate_sample_mp(np.asarray(x), ls, sigmas, sigma0s, X, Y, xdim, nx, nobs, 1, nysample, test_xs,
+                                          max_probs, v0, v1, invpNK, niteration=niteration, z=z))
+
+    # criteria.evaluate_mp.mp (TES_ep, q = 1)
+    def ep_mp(self, x, ls, sigmas, sigma0s, X, Y, xdim, nx, nobs, nhyp, nysample, test_xs, max_probs, pm, pc, invK,
+              invpNK, stochastic=False, niteration=10, seed=0, n_global=None):
+        assert n_global == -1
+        Sp = int((np.asarray(max_probs)[0] > 0).sum())
+        z = None
+        if stochastic:
+            z = self._shared_z(seed, 1, niteration, (nysample, Sp, 1), nx)
+            z = np.broadcast_to(z, (niteration, nysample, Sp, nx))[None]
+        return _Np(onp.evaluate_mp(np.asarray(x), ls, sigmas, sigma0s, X, Y, xdim, nx, nobs, 1, nysample, test_xs,
+                                   max_probs, pm, pc, invK, invpNK, stochastic=bool(stochastic), niteration=niteration, z=z))
+
+    def remove_duplicates_np(self, xs, resolution=1e-5):
+        return onp.remove_duplicates(np.asarray(xs), resolution)
+
+
 class _Np:  # .cpu().numpy() on a numpy result
     def __init__(self, a):
         self.a = a
@@ -186,3 +217,32 @@ def test_batch_bo_trajectory_matches_oracle_backend(golden, monkeypatch, q):
     np.testing.assert_allclose(out["guess_xx"], ref["guess_xx"], rtol=0, atol=1e-5)
     np.testing.assert_allclose(out["crit_max"], ref["crit_max"], rtol=1e-5, atol=1e-8)
     assert out["xx"].shape == (1, 3 + 2 * q, 2)
+
+
+@pytest.mark.parametrize("criterion,mode,det", [("sftl", "sample", 0), ("ftl", "empirical", 0), ("ftl", "ep", 1)])
+def test_sequential_bo_trajectory_matches_oracle_backend(golden, monkeypatch, criterion, mode, det):
+    """bo.py loop (tes_b200.bo.run): de-duplicated maximisers, evaluate_sample_mp / evaluate_mp as the criterion, all
+    maximisers as start points of its Adam refinement; device run vs the same loop on the numpy oracle."""
+    from tes_b200 import bo, bo_batch
+    import tes_b200.criteria.evaluate_mp as em
+    import tes_b200.criteria.evaluate_sample_mp as es
+    f, xs, l, sigma, sigma0 = _branin(golden)
+    args = dict(criterion=criterion, mode=mode, deterministic=det, nquery=2, nrun=1, ninit=3, nmax=8, nfeature=64, nsto=2,
+                ntrain=20, nysample=4, ntestsample=300, seed=2, transform_fn=_stable_factor(l, sigma, sigma0))
+    out = bo.run(f, xs, 0.0, 1.0, l, sigma, sigma0, **args)
+    ob = _OracleBackend()
+    for name in ("precomputeInvKs", "compute_mean_f", "compute_mean_var_f", "get_testidxs_stats", "remove_duplicates_np"):
+        monkeypatch.setattr(bo_batch.utils, name, getattr(ob, name))
+    monkeypatch.setattr(bo_batch.optfunc, "draw_random_init_weights_features_np", ob.draw_random_init_weights_features_np)
+    monkeypatch.setattr(bo_batch.utils_for_continuous, "sample_xmaxs_fmaxs", ob.sample_xmaxs_fmaxs)
+    monkeypatch.setattr(es, "mp", ob.sample_mp)
+    monkeypatch.setattr(em, "mp", ob.ep_mp)
+    monkeypatch.setattr(bo_batch, "dev", lambda a: a)
+    monkeypatch.setattr(bo_batch.evaluate_batch_mp_mod(), "get_pNK_test_obs",
+                        lambda ls, sg, s0, nh, X, tx: onp.get_pNK_test_obs(ls, sg, s0, nh, X, tx))
+    ref = bo.run(f, xs, 0.0, 1.0, l, sigma, sigma0, **args)
+    np.testing.assert_array_equal(out["ntest"], ref["ntest"])
+    assert (ref["ntest"] >= 2).any() and np.isfinite(ref["crit_max"]).any()
+    np.testing.assert_allclose(out["xx"], ref["xx"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(out["guess_xx"], ref["guess_xx"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(out["crit_max"], ref["crit_max"], rtol=1e-5, atol=1e-8)

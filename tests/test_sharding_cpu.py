@@ -65,3 +65,30 @@ def test_merge_topk_host_semantics():
     idx = torch.tensor([[[5, 9]], [[2, 7]], [[-1, -1]]])
     oi, ov = acquisition.merge_topk_host(vals, idx, 3)
     assert oi.tolist() == [[2, 5, 7]] and ov.tolist() == [[3.0, 3.0, 2.0]]
+
+
+def test_optimize_continuous_function_host_logic():
+    """utils_for_continuous.optimize_continuous_function (:20-87) re-hosted: candidate scoring, top-k start points
+    (value desc, index asc), TF-1 Adam with the clip constraint on central-difference gradients.  The objective here is
+    a plain numpy function (the device criterion is exercised by tests/test_bo_loop_gpu.py)."""
+    import numpy as np
+    from tes_b200 import utils_for_continuous as ufc
+    calls = []
+
+    def f(x, step):
+        calls.append((x.shape[0], step))
+        return -((x - np.array([0.3, 0.8])) ** 2).sum(1)
+    rs = np.random.RandomState(0)
+    cand = rs.rand(12, 2)
+    mx, val, xs, fs = ufc.optimize_continuous_function(2, f, cand, 3, 0.0, 1.0, ntrain=40, rand_candidate_xs=rs.rand(3, 2),
+                                                       debug=True)
+    assert calls[0] == (15, 0) and calls[1] == (3 * 4, 1) and calls[-1] == (3, 41)
+    # Adam moves every coordinate by ~lr per step towards the optimum while the gradient keeps its sign
+    assert mx.shape == (1, 2) and val == fs.max() and np.all(xs >= 0.0) and np.all(xs <= 1.0)
+    assert val > np.sort(f(cand, -1))[-1] - 1e-12
+    # exact TF-1 Adam on a linear objective: g = -1 => x_t = x_0 + sum_t lr_t m_t/(sqrt(v_t)+eps) = x_0 + t*lr (to 1e-8)
+    lin = lambda x, step: x.sum(1)
+    x, fx = ufc.adam_ascent(lin, np.array([[0.1, 0.2]]), -np.inf, np.inf, 10)
+    np.testing.assert_allclose(x, np.array([[0.11, 0.21]]), atol=1e-7)
+    x, fx = ufc.adam_ascent(lin, np.array([[0.995, 0.2]]), 0.0, 1.0, 10)
+    assert x[0, 0] == 1.0 and abs(x[0, 1] - 0.21) < 1e-7

@@ -58,15 +58,22 @@ def crit_start_batches(pool, batchsize, xmin, xmax, n_crit_candidate_xs=5):
 
 def run(f, xs, xmin, xmax, l, sigma, sigma0, criterion="sftl", mode="sample", nquery=3, nrun=1, ninit=2, nmax=30,
         nfeature=300, nsto=10, ntrain=300, nysample=100, batchsize=1, ntestsample=1000, n_min_sample=2, seed=1,
-        top_init_k=3, fd_step=1e-5, transform_fn=None, verbose=False, trace=None):
+        top_init_k=3, fd_step=1e-5, transform_fn=None, verbose=False, trace=None, single=False, deterministic=0,
+        duplicate_resolution=1e-3, max_nan_retry=10):
     """f: objective on (n, xdim) arrays; xs: candidate grid (`f_info['xs']`, bo_batch.py:783) used to start the
     optimisation of the posterior mean and of the function samples; flags as in bo_batch.py (`--criterion --mode
     --numqueries --numruns --ninit --nmax --nfeature --nsto --ntrain --nysample --batchsize`).
     transform_fn(test_xs, X, Y) -> colouring factor for get_testidxs_stats (tests inject LAPACK's; default: device).
+    single=True: the sequential driver bo.py instead (bo.py:1026-1244; see tes_b200/bo.py): batchsize 1, maximisers
+    de-duplicated at `duplicate_resolution` (bo.py:830-836), criteria evaluate_sample_mp.mp ('sftl') / evaluate_mp.mp
+    ('ftl', stochastic = 1 - deterministic), criterion start points = all nmax maximisers (bo.py:1151-1153), lone
+    maximiser queried directly, and the whole query repeated when it comes out NaN (bo.py:1190-1193).
     `trace`: optional list that receives one dict of intermediates per query (maximizers, test points, start batches,
     their criterion values, the refined query).
     Returns the arrays the reference saves (xx, ff, yy, guess_xx, guess_ff) plus per-query diagnostics."""
-    from .criteria import evaluate_batch_sample_mp
+    from .criteria import evaluate_batch_sample_mp, evaluate_mp, evaluate_sample_mp
+    if single and int(batchsize) != 1:
+        raise ValueError("bo.py queries one point at a time")
     if criterion not in ("ftl", "sftl"):
         raise ValueError("only the TES criteria 'ftl' and 'sftl' are on this path")
     xs = np.ascontiguousarray(xs, dtype=np.float64)
@@ -92,56 +99,71 @@ def run(f, xs, xmin, xmax, l, sigma, sigma0, criterion="sftl", mode="sample", nq
         F = np.asarray(f(X), dtype=np.float64).reshape(-1, 1)
         Y = F + np.random.randn(X.shape[0], 1) * np.sqrt(sigma0)
         for nq in range(nquery):
-            invK = utils.precomputeInvKs(xdim, 1, ls, sigmas, sigma0s, X)
-            g = best_guess(X, Y, invK)
-            out["guess_xx"][nr, nq] = g.squeeze()
-            out["guess_ff"][nr, nq] = np.asarray(f(g.reshape(1, xdim))).squeeze()
-            # ---- function samples and their maximisers
-            theta, W, b = optfunc.draw_random_init_weights_features_np(xdim, nmax, nfeature, X, Y, ls, sigma, sigma0)
-            lo = np.broadcast_to(np.asarray(xmin, dtype=np.float64), (xdim,))
-            hi = np.broadcast_to(np.asarray(xmax, dtype=np.float64), (xdim,))
-            cand = np.concatenate([xs, lo + np.random.rand(top_init_k, xdim) * (hi - lo)], axis=0)
-            _, max_xs, _, _ = utils_for_continuous.sample_xmaxs_fmaxs(
-                xdim, 1, nmax, nfeature, ls, sigmas, sigma0s, theta[None], W[None], b[None], cand, top_init_k,
-                xmin=xmin, xmax=xmax, ntrain=ntrain)
-            maximizers = max_xs[0].reshape(-1, xdim)
-            tr_rec = dict(guess=g.copy(), maximizers=maximizers.copy())
-            if trace is not None:
-                trace.append(tr_rec)
-            test_xs, query_x = maximizers, None
-            ntest = test_xs.shape[0]
-            if ntest == 1:
-                query_x = maximizers[:q]
-            else:
-                mean_t, cov_t = utils.compute_mean_var_f(test_xs, X, Y, ls[0], sigma, sigma0, invK[0], fullcov=True)
-                tr = None if transform_fn is None else [transform_fn(test_xs, X, Y)]
-                test_xs, max_probs, _, _, v0, v1 = utils.get_testidxs_stats(
-                    1, test_xs, mean_t.reshape(1, ntest), cov_t.reshape(1, ntest, ntest), mode=st_mode,
-                    nsample=ntestsample, n_min_sample=n_min_sample, transforms=tr)
-                out["ntest"][nr, nq] = test_xs.shape[0]
-                if test_xs.shape[0] == 1:
-                    query_x = maximizers[:q]
-            if query_x is None:
-                _, invpNK = evaluate_batch_mp_mod().get_pNK_test_obs(ls, sigmas, sigma0s, 1, X, test_xs)
-                starts = crit_start_batches(test_xs, q, xmin, xmax)
-                cseed = ((seed + nr) * 100003 + nq) * 100003
-                Xd, Yd, tx, mp_, v0d, inv_d = dev(X), dev(Y), dev(test_xs), dev(max_probs), dev(v0), dev(invpNK)
-                v1b = np.asarray(v1).astype(bool) if criterion == "sftl" else None
+            for _retry in range(max_nan_retry + 1):      # bo.py:1190-1193 / bo_batch.py:1080-1083: repeat on NaN
+                invK = utils.precomputeInvKs(xdim, 1, ls, sigmas, sigma0s, X)
+                g = best_guess(X, Y, invK)
+                out["guess_xx"][nr, nq] = g.squeeze()
+                out["guess_ff"][nr, nq] = np.asarray(f(g.reshape(1, xdim))).squeeze()
+                # ---- function samples and their maximisers
+                theta, W, b = optfunc.draw_random_init_weights_features_np(xdim, nmax, nfeature, X, Y, ls, sigma, sigma0)
+                lo = np.broadcast_to(np.asarray(xmin, dtype=np.float64), (xdim,))
+                hi = np.broadcast_to(np.asarray(xmax, dtype=np.float64), (xdim,))
+                cand = np.concatenate([xs, lo + np.random.rand(top_init_k, xdim) * (hi - lo)], axis=0)
+                _, max_xs, _, _ = utils_for_continuous.sample_xmaxs_fmaxs(
+                    xdim, 1, nmax, nfeature, ls, sigmas, sigma0s, theta[None], W[None], b[None], cand, top_init_k,
+                    xmin=xmin, xmax=xmax, ntrain=ntrain)
+                maximizers = max_xs[0].reshape(-1, xdim)
+                tr_rec = dict(guess=g.copy(), maximizers=maximizers.copy())
+                if trace is not None:
+                    trace.append(tr_rec)
+                test_xs, query_x = maximizers, None
+                if single:
+                    test_xs = utils.remove_duplicates_np(maximizers, resolution=duplicate_resolution).reshape(-1, xdim)
+                lone = (lambda: test_xs) if single else (lambda: maximizers[:q])   # bo.py:843-845 / bo_batch.py:710
+                ntest = test_xs.shape[0]
+                if ntest == 1:
+                    query_x = lone()
+                else:
+                    mean_t, cov_t = utils.compute_mean_var_f(test_xs, X, Y, ls[0], sigma, sigma0, invK[0], fullcov=True)
+                    tr = None if transform_fn is None else [transform_fn(test_xs, X, Y)]
+                    test_xs, max_probs, _, _, v0, v1 = utils.get_testidxs_stats(
+                        1, test_xs, mean_t.reshape(1, ntest), cov_t.reshape(1, ntest, ntest), mode=st_mode,
+                        nsample=ntestsample, n_min_sample=n_min_sample, transforms=tr)
+                    out["ntest"][nr, nq] = test_xs.shape[0]
+                    if test_xs.shape[0] == 1:
+                        query_x = lone()
+                if query_x is None:
+                    _, invpNK = evaluate_batch_mp_mod().get_pNK_test_obs(ls, sigmas, sigma0s, 1, X, test_xs)
+                    starts = maximizers.reshape(-1, 1, xdim) if single else crit_start_batches(test_xs, q, xmin, xmax)
+                    cseed = ((seed + nr) * 100003 + nq) * 100003
+                    Xd, Yd, tx, mp_, v0d, inv_d = dev(X), dev(Y), dev(test_xs), dev(max_probs), dev(v0), dev(invpNK)
+                    v1b = np.asarray(v1).astype(bool) if criterion == "sftl" else None
 
-                def crit(xflat, step):
-                    xb = np.asarray(xflat, dtype=np.float64).reshape(-1, q, xdim)
-                    if criterion == "sftl":
-                        return evaluate_batch_sample_mp.mp(dev(xb), ls, sigmas, sigma0s, Xd, Yd, xdim, X.shape[0], 1,
-                                                           nysample, tx, mp_, v0d, v1b, inv_d, niteration=nsto,
-                                                           seed=cseed + step, n_global=-1).cpu().numpy()
-                    return ops.batch_ep_acq(mp_[0][mp_[0] > 0], xb.shape[0]).cpu().numpy()
-                qx, qv = utils_for_continuous.optimize_continuous_function(
-                    xdim * q, crit, starts.reshape(-1, xdim * q), top_init_k, np.tile(lo, q), np.tile(hi, q),
-                    ntrain=ntrain, fd_step=fd_step)
-                out["crit_max"][nr, nq] = qv
-                query_x = qx.reshape(q, xdim)
-                tr_rec.update(test_xs=np.asarray(test_xs).copy(), max_probs=np.asarray(max_probs).copy(), starts=starts,
-                              start_vals=crit(starts.reshape(-1, xdim * q), 0), qx=qx, qv=qv)
+                    def crit(xflat, step):
+                        xb = np.asarray(xflat, dtype=np.float64).reshape(-1, q, xdim)
+                        if single and criterion == "sftl":
+                            return evaluate_sample_mp.mp(dev(xb[:, 0]), ls, sigmas, sigma0s, Xd, Yd, xdim, xb.shape[0],
+                                                         X.shape[0], 1, nysample, tx, mp_, v0d, v1b, inv_d, niteration=nsto,
+                                                         seed=cseed + step, n_global=-1).cpu().numpy()
+                        if single:
+                            return evaluate_mp.mp(dev(xb[:, 0]), ls, sigmas, sigma0s, Xd, Yd, xdim, xb.shape[0], X.shape[0], 1,
+                                                  nysample, tx, mp_, v0d, dev(v1), dev(invK), inv_d,
+                                                  stochastic=1 - deterministic, niteration=nsto, seed=cseed + step,
+                                                  n_global=-1).cpu().numpy()
+                        if criterion == "sftl":
+                            return evaluate_batch_sample_mp.mp(dev(xb), ls, sigmas, sigma0s, Xd, Yd, xdim, X.shape[0], 1,
+                                                               nysample, tx, mp_, v0d, v1b, inv_d, niteration=nsto,
+                                                               seed=cseed + step, n_global=-1).cpu().numpy()
+                        return ops.batch_ep_acq(mp_[0][mp_[0] > 0], xb.shape[0]).cpu().numpy()
+                    qx, qv = utils_for_continuous.optimize_continuous_function(
+                        xdim * q, crit, starts.reshape(-1, xdim * q), top_init_k, np.tile(lo, q), np.tile(hi, q),
+                        ntrain=ntrain, fd_step=fd_step)
+                    out["crit_max"][nr, nq] = qv
+                    query_x = qx.reshape(q, xdim)
+                    tr_rec.update(test_xs=np.asarray(test_xs).copy(), max_probs=np.asarray(max_probs).copy(), starts=starts,
+                                  start_vals=crit(starts.reshape(-1, xdim * q), 0), qx=qx, qv=qv)
+                if query_x is not None and not np.any(np.isnan(np.asarray(query_x, dtype=np.float64))):
+                    break
             query_x = np.asarray(query_x, dtype=np.float64).reshape(q, xdim)
             query_f = np.asarray(f(query_x), dtype=np.float64).reshape(q, 1)
             query_y = query_f + np.random.randn(q, 1) * np.sqrt(sigma0)

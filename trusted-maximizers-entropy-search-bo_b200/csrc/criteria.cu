@@ -50,7 +50,11 @@ struct AQuad {
     const double* G;  // rows x ldg, the first T columns are M
     int64_t ldg, M, T;
     const int2* table;
-    __device__ __forceinline__ void load(int64_t row0, int64_t k0, int t, double regs[8]) const {
+    // load() only ISSUES the 16 global loads of the next slice (raw M[x,a], M[x,b]); the products are formed in
+    // store(), after the current slice's DMMAs -- a product in load() would stall the warp on the L2 latency before it
+    // can issue its tensor work (ncu: long_scoreboard 3.2 stalls per issue with the product in load()).
+    static constexpr int NREG = 16;
+    __device__ __forceinline__ void load(int64_t row0, int64_t k0, int t, double regs[16]) const {
         const int kk = t & 15;
         const int r = t >> 4;
         const int64_t kt = k0 >> 4;
@@ -61,14 +65,16 @@ struct AQuad {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             int64_t row = row0 + r + 16 * q;
-            regs[q] = (ok && row < M) ? __dmul_rn(__ldg(G + row * ldg + a), __ldg(G + row * ldg + b)) : 0.0;
+            const bool in = ok && row < M;
+            regs[q] = in ? __ldg(G + row * ldg + a) : 0.0;
+            regs[8 + q] = in ? __ldg(G + row * ldg + b) : 0.0;
         }
     }
-    __device__ __forceinline__ void store(double (*as)[GEMM_LDA_S], int t, const double regs[8]) const {
+    __device__ __forceinline__ void store(double (*as)[GEMM_LDA_S], int t, const double regs[16]) const {
         const int kk = t & 15;
         const int r = t >> 4;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) as[kk][r + 16 * q] = regs[q];
+        for (int q = 0; q < 8; ++q) as[kk][r + 16 * q] = __dmul_rn(regs[q], regs[8 + q]);
     }
 };
 

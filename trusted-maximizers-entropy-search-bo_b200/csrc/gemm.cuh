@@ -39,13 +39,15 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                  : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ void gemm_mac_slice(const double (*as)[GEMM_LDA_S], const double (*bs)[GEMM_LDB_S],
+// k-steps [K0, K1) (multiples of 4) of one BK-slice
+template <int K0, int K1>
+__device__ __forceinline__ void gemm_mac_steps(const double (*as)[GEMM_LDA_S], const double (*bs)[GEMM_LDB_S],
                                                int warp, int lane, double acc[4][4][2]) {
     const int rbase = (warp >> 1) * 32 + (lane >> 2);
     const int cbase = (warp & 1) * 32 + (lane >> 2);
     const int kq = lane & 3;
 #pragma unroll
-    for (int k0 = 0; k0 < GEMM_BK; k0 += 4) {
+    for (int k0 = K0; k0 < K1; k0 += 4) {
         double av[4], bv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) av[i] = as[k0 + kq][rbase + 8 * i];
@@ -57,6 +59,10 @@ __device__ __forceinline__ void gemm_mac_slice(const double (*as)[GEMM_LDA_S], c
             for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
     }
 }
+__device__ __forceinline__ void gemm_mac_slice(const double (*as)[GEMM_LDA_S], const double (*bs)[GEMM_LDB_S],
+                                               int warp, int lane, double acc[4][4][2]) {
+    gemm_mac_steps<0, GEMM_BK>(as, bs, warp, lane, acc);
+}
 
 // Plain row-major operand loaders -------------------------------------------------------------
 // A slice: BM x BK, thread t loads 8 elements: row = t/2 ... choose mapping for coalescing along K:
@@ -66,6 +72,7 @@ struct APlain {
     int64_t lda;
     int64_t M, K;
     static constexpr bool kTransposed = false;
+    static constexpr int NREG = 8;
     __device__ __forceinline__ void load(int64_t row0, int64_t k0, int t, double regs[8]) const {
         const int kk = t & 15;
         const int r = t >> 4;
@@ -90,6 +97,7 @@ struct ATrans {
     const double* A;
     int64_t ldt;
     int64_t M, K;
+    static constexpr int NREG = 8;
     __device__ __forceinline__ void load(int64_t row0, int64_t k0, int t, double regs[8]) const {
         const int r = t & 127;
         const int kb = t >> 7;
@@ -133,7 +141,7 @@ __device__ __forceinline__ void gemm_mainloop(const AProv& ap, const double* __r
                                               double acc[4][4][2], int64_t kbeg = 0) {
     const int t = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
-    double ra[8], rb[4];
+    double ra[AProv::NREG], rb[4];
     const int64_t nk = (K + GEMM_BK - 1) / GEMM_BK;
     const int64_t kt0 = kbeg / GEMM_BK;   // slices below kbeg are known to be zero (triangular operands)
     if (kt0 >= nk) return;
@@ -148,11 +156,17 @@ __device__ __forceinline__ void gemm_mainloop(const AProv& ap, const double* __r
             ap.load(row0, (kt + 1) * GEMM_BK, t, ra);
             gemm_load_b(B, ldb, K, N, (kt + 1) * GEMM_BK, col0, t, rb);
         }
-        gemm_mac_slice(sm.a[cur], sm.b[cur], warp, lane, acc);
+        // the next slice's operands go to shared memory in the MIDDLE of this slice's DMMA stream: the other buffer
+        // is free since the last barrier, the loads issued above have had two k-steps to land, and the warp reaches
+        // the barrier straight after its last DMMA, so the fp64 pipe keeps draining queued DMMAs across the barrier
+        // (with the store after the slice, its DMULs queued behind the DMMAs and the pipe idled at every barrier:
+        // ncu showed 17 % of all stall samples on the first DMUL, DMMA pipe 63 % busy)
+        gemm_mac_steps<0, GEMM_BK / 2>(sm.a[cur], sm.b[cur], warp, lane, acc);
         if (kt + 1 < nk) {
             ap.store(sm.a[cur ^ 1], t, ra);
             gemm_store_b(sm.b[cur ^ 1], t, rb);
         }
+        gemm_mac_steps<GEMM_BK / 2, GEMM_BK>(sm.a[cur], sm.b[cur], warp, lane, acc);
         __syncthreads();
     }
 }

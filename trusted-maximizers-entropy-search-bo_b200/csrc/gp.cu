@@ -82,7 +82,7 @@ __device__ __forceinline__ void gemm_body(const AProv& ap, const double* __restr
         const int64_t kbeg = kskip == 1 ? (row0 > col0 ? row0 : col0) : (kskip == 2 ? col0 : 0);
         gemm_mainloop(ap, B, sbk, K, N, row0, col0, sm, acc, kbeg);
     } else {
-        double ra[8], rb[4];
+        double ra[AProv::NREG], rb[4];
         const int64_t nk = (K + GEMM_BK - 1) / GEMM_BK;
         auto loadb = [&](int64_t k0) {
             const int kk = t >> 4, c = t & 15;
@@ -105,11 +105,12 @@ __device__ __forceinline__ void gemm_body(const AProv& ap, const double* __restr
                 ap.load(row0, (kt + 1) * GEMM_BK, t, ra);
                 loadb((kt + 1) * GEMM_BK);
             }
-            gemm_mac_slice(sm.a[cur], sm.b[cur], warp, lane, acc);
+            gemm_mac_steps<0, GEMM_BK / 2>(sm.a[cur], sm.b[cur], warp, lane, acc);
             if (kt + 1 < nk) {
                 ap.store(sm.a[cur ^ 1], t, ra);
                 gemm_store_b(sm.b[cur ^ 1], t, rb);
             }
+            gemm_mac_steps<GEMM_BK / 2, GEMM_BK>(sm.a[cur], sm.b[cur], warp, lane, acc);
             __syncthreads();
         }
     }

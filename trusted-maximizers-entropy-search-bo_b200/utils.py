@@ -168,10 +168,18 @@ def sample_multivariate_normal_maxidx_np(mean, cov, nsample, n_min_sample=1, get
 
 
 def _device_buckets(mean, cov, nsample, z, transform, seed, hyp_index, remove_correlated=True):
-    """utils.py:1668-1705 on the device: colouring factor (Jacobi eigen-solver unless `transform` is given),
+    """utils.py:1668-1705 on the device: colouring factor (`transform`, else Cholesky, else the Jacobi eigen-solver),
     joint samples z A^T + mean(mean) (Q11), correlated-dimension mask, row arg-max, bucket counts."""
     T = cov.shape[0]
-    A = ops.color_factor(cov) if transform is None else dev(transform, cov.device)
+    if transform is not None:
+        A = dev(transform, cov.device)
+    else:
+        # any A with A A^T = cov gives the reference's law.  The Cholesky factor (blocked potrf, ~0.3 ms at T = 128)
+        # is used when cov is numerically positive definite; otherwise the reference's own construction
+        # V sqrt(clip(e, 0)) from the device eigen-solver (12 ms at T = 128), which also covers semi-definite cov.
+        A, info = ops.batched_potrf(cov, return_info=True)
+        if int(info.reshape(-1)[0]) != 0 or not bool(torch.isfinite(A).all()):
+            A = ops.color_factor(cov)
     if z is not None:
         zt = dev(z, cov.device).reshape(-1, T)
     elif seed is not None:
