@@ -65,8 +65,8 @@ WORKLOADS = {
                d=6, N=10 ** 6, S=1024, F=1024, n=64, t_max=128),
     "c3s": dict(desc="C3 shapes scaled down (smoke)", d=6, N=50_000, S=128, F=256, n=32, t_max=32),
     "c3m": dict(desc="C3 shapes, mid size (profiling)", d=6, N=200_000, S=256, F=1024, n=64, t_max=64),
-    "c2": dict(desc="C2 Brooms-Barn-like 2-D 20x20 grid TES_ep, S=32 (latency case)", d=2, N=400, S=32, F=300, n=12,
-               t_max=32),
+    "c2": dict(desc="C2 Brooms-Barn pH hyper-parameters, 2-D 20x20 grid, TES_ep (ftl, ep), S=32 (launch-latency case)", d=2,
+               N=400, S=32, F=300, n=12, t_max=32, mode="ep"),
     # C4: 10-D GP-prior objective, uniform candidates on [0,10]^10, 2^24 candidates over 8 GPUs = 2^21 per
     # GPU grouped consecutively into batches of q = 8, S = 1024, F = 4096, n = 256, batch TES_sp with T <= 32, I = 1, Y = 8
     "c4": dict(desc="C4 synthetic 10-D GP objective, batch TES_sp q=8, F=4096, 2^21 candidates x 1024 maximizer samples "
@@ -79,6 +79,7 @@ WORKLOADS = {
 }
 for _w in WORKLOADS.values():
     _w.setdefault("criterion", "ftl")
+    _w.setdefault("mode", "empirical")
     _w.setdefault("q", 1)
     _w.setdefault("niteration", 10)
     _w.setdefault("nysample", 10)
@@ -96,7 +97,7 @@ def gp_prior_objective(xdim, l, sigma, seed, n_feats=10000):
 
 
 def config_of(wl):
-    c = {"workload": wl["desc"], "criterion": wl["criterion"], "mode": "sample" if wl["criterion"] == "sftl" else "empirical",
+    c = {"workload": wl["desc"], "criterion": wl["criterion"], "mode": "sample" if wl["criterion"] == "sftl" else wl["mode"],
          "deterministic": True, "N_per_gpu": wl["N"], "S": wl["S"], "F": wl["F"], "n_obs": wl["n"], "d": wl["d"],
          "t_max": wl["t_max"]}
     if wl["criterion"] == "sftl":
@@ -105,7 +106,7 @@ def config_of(wl):
 
 
 def step_kwargs(wl):
-    return dict(criterion=wl["criterion"], mode="empirical", deterministic=True, ntestsample=wl["ntestsample"],
+    return dict(criterion=wl["criterion"], mode=wl["mode"], deterministic=True, ntestsample=wl["ntestsample"],
                 t_max=wl["t_max"], q=wl["q"], niteration=wl["niteration"], nysample=wl["nysample"])
 
 
@@ -258,6 +259,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C2 latency case reported beside C3")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -424,6 +426,33 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
+    if rank == 0 and world == 1 and args.workload == "c3" and not args.no_secondary:
+        # BASELINE config 2 (the 400-point pH grid, TES_ep mode ep) in the same run: a launch-latency case, reported
+        # beside the headline so that both single-GPU configurations are on the line
+        w2 = make_workload("c2", 0, 1)
+        d2 = {k: torch.from_numpy(w2[k]).cuda() for k in names}
+        kw2, sh2 = step_kwargs(w2), acquisition.Shard(w2["N"])
+        run2 = lambda sd: acquisition.tes_step(d2["cand"], d2["X"], d2["Y"], w2["hyp"]["l"], w2["hyp"]["sigma"],
+                                               w2["hyp"]["sigma0"], d2["theta"], d2["W"], d2["b"], seed=sd, shard=sh2, **kw2)
+        for w in range(3):
+            o2 = run2(w)
+        torch.cuda.synchronize()
+        n2, l0 = 20, _lib.lib().tes_launch_count()
+        e0.record()
+        for s in range(n2):
+            flush.zero_()
+            o2 = run2(100 + s)
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / n2
+        t0 = time.perf_counter()
+        cpu_step(w2, w2["N"], w2["S"])
+        cpu2 = time.perf_counter() - t0
+        line["secondary"] = {"c2": {"workload": w2["desc"], "ms_per_step": ms2, "value": w2["N"] * w2["S"] / (ms2 * 1e-3),
+                                    "unit": "evals/s", "steps": n2, "T": o2.get("T"),
+                                    "gpu_launches_per_step": (_lib.lib().tes_launch_count() - l0) / n2,
+                                    "cpu_ms_per_step": cpu2 * 1e3, "cpu_cores": os.cpu_count(),
+                                    "note": "whole step incl. EP on the device; host-latency bound (launches + the bucket-count sync)"}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         nc, ns = cpu_sample_sizes(wl)
         pairs, dt, info = cpu_step(wl, nc, ns)
