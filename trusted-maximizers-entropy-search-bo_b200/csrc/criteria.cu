@@ -19,29 +19,65 @@ namespace tes {
 constexpr double HALF_LOG_2PI = 0.91893853320467274178;
 
 // ---- TES_ep query moments: var[x][j] = Kq[x] + M[x]^T Sigma_j M[x]  (evaluate_mp.py:103-107) ----
-// Symmetric 16x16 block pairs (ab <= bb): k index = (pair*16 + a_local)*16 + b_local.
-__global__ void blockpair_table_kernel(int nb, int2* table) {
+// The quadratic form is a GEMM over the index pairs (a <= b) of the symmetric Sigma_j:
+//     var[x][j] - Kq[x] = sum_{a <= b} (M[x,a] M[x,b]) * Bpack[(a,b)][j],   Bpack = Sigma_j[a][b] (+ Sigma_j[b][a] if a < b)
+// with the A operand (the products) generated on the fly.  The K axis is cut into 16-wide SLICES described by a table:
+//   * off-diagonal pair of 16-blocks (pa < pb): 16 slices, slice i holds a = 16 pa + i, b = 16 pb + kk (kk = 0..15);
+//   * diagonal pair (pa = pb): only the 136 pairs a <= b are enumerated, in 9 slices instead of 16: slice 0 is row 0
+//     (16 entries), slice i = 1..7 packs row i (16 - i entries, b = i + kk) with row 16 - i (i entries, b = kk), slice 8
+//     is row 8 (8 entries, the rest zero).  At T = 128 this is K = 8 * 144 + 28 * 256 = 8320 instead of 9216.
+struct QSlice {
+    int pa, pb, i, diag;
+};
+__host__ __device__ inline int64_t quad_num_slices(int64_t nb) { return nb * 9 + nb * (nb - 1) / 2 * 16; }
+
+__global__ void quad_slice_table_kernel(int nb, QSlice* table) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int i = 0;
-        for (int a = 0; a < nb; ++a)
-            for (int b = a; b < nb; ++b) table[i++] = make_int2(a, b);
+        int64_t n = 0;
+        for (int pa = 0; pa < nb; ++pa)
+            for (int pb = pa; pb < nb; ++pb) {
+                const int ns = pa == pb ? 9 : 16;
+                for (int i = 0; i < ns; ++i) table[n++] = QSlice{pa, pb, i, pa == pb};
+            }
     }
 }
 
-// Bpack[krow][j] = Sigma_j[a][b] (diagonal block pairs) or Sigma_j[a][b] + Sigma_j[b][a] (ab < bb)
-__global__ void quad_pack_kernel(const double* __restrict__ cov, int64_t Sp, int64_t T, const int2* __restrict__ table,
+// (a, b) of entry kk of a slice; returns false for the zero padding of slice 8 of a diagonal pair
+__device__ __forceinline__ bool quad_slice_ab(const QSlice& q, int kk, int64_t& a, int64_t& b) {
+    int al, bl;
+    if (!q.diag) {
+        al = q.i;
+        bl = kk;
+    } else if (q.i == 0) {
+        al = 0;
+        bl = kk;
+    } else if (q.i < 8) {
+        const bool first = kk < 16 - q.i;
+        al = first ? q.i : 16 - q.i;
+        bl = first ? q.i + kk : kk;
+    } else {
+        al = 8;
+        bl = 8 + kk;
+        if (kk >= 8) return false;
+    }
+    a = (int64_t)q.pa * 16 + al;
+    b = (int64_t)q.pb * 16 + bl;
+    return true;
+}
+
+// Bpack[krow][j] = Sigma_j[a][a] (a = b) or Sigma_j[a][b] + Sigma_j[b][a] (a < b)
+__global__ void quad_pack_kernel(const double* __restrict__ cov, int64_t Sp, int64_t T, const QSlice* __restrict__ table,
                                  int64_t nrows, double* __restrict__ Bpack) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nrows * Sp) return;
     int64_t krow = e / Sp, j = e % Sp;
-    int2 pr = table[krow >> 8];
-    int64_t a = (int64_t)pr.x * 16 + ((krow >> 4) & 15);
-    int64_t b = (int64_t)pr.y * 16 + (krow & 15);
+    const QSlice q = table[krow >> 4];
+    int64_t a, b;
     double v = 0.0;
-    if (a < T && b < T) {
+    if (quad_slice_ab(q, (int)(krow & 15), a, b) && a < T && b < T) {
         const double* c = cov + j * T * T;
         v = c[a * T + b];
-        if (pr.x != pr.y) v += c[b * T + a];
+        if (a != b) v += c[b * T + a];
     }
     Bpack[e] = v;
 }
@@ -49,25 +85,24 @@ __global__ void quad_pack_kernel(const double* __restrict__ cov, int64_t Sp, int
 struct AQuad {
     const double* G;  // rows x ldg, the first T columns are M
     int64_t ldg, M, T;
-    const int2* table;
+    const QSlice* table;
     // load() only ISSUES the 16 global loads of the next slice (raw M[x,a], M[x,b]); the products are formed in
-    // store(), after the current slice's DMMAs -- a product in load() would stall the warp on the L2 latency before it
-    // can issue its tensor work (ncu: long_scoreboard 3.2 stalls per issue with the product in load()).
+    // store(), in the middle of the current slice's DMMA stream (gemm_mainloop) -- a product in load() would stall the
+    // warp on the L2 latency before it can issue its tensor work.
     static constexpr int NREG = 16;
     __device__ __forceinline__ void load(int64_t row0, int64_t k0, int t, double regs[16]) const {
         const int kk = t & 15;
         const int r = t >> 4;
-        const int64_t kt = k0 >> 4;
-        const int2 pr = __ldg(table + (kt >> 4));
-        const int64_t a = (int64_t)pr.x * 16 + (kt & 15);
-        const int64_t b = (int64_t)pr.y * 16 + kk;
-        const bool ok = a < T && b < T;
+        const int4 qv = __ldg(reinterpret_cast<const int4*>(table) + (k0 >> 4));
+        const QSlice q{qv.x, qv.y, qv.z, qv.w};
+        int64_t a = 0, b = 0;
+        const bool ok = quad_slice_ab(q, kk, a, b) && a < T && b < T;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            int64_t row = row0 + r + 16 * q;
+        for (int qq = 0; qq < 8; ++qq) {
+            int64_t row = row0 + r + 16 * qq;
             const bool in = ok && row < M;
-            regs[q] = in ? __ldg(G + row * ldg + a) : 0.0;
-            regs[8 + q] = in ? __ldg(G + row * ldg + b) : 0.0;
+            regs[qq] = in ? __ldg(G + row * ldg + a) : 0.0;
+            regs[8 + qq] = in ? __ldg(G + row * ldg + b) : 0.0;
         }
     }
     __device__ __forceinline__ void store(double (*as)[GEMM_LDA_S], int t, const double regs[16]) const {
@@ -79,7 +114,7 @@ struct AQuad {
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-    quadform_kernel(const double* __restrict__ G, int64_t ldg, int64_t rows, int64_t T, const int2* __restrict__ table,
+    quadform_kernel(const double* __restrict__ G, int64_t ldg, int64_t rows, int64_t T, const QSlice* __restrict__ table,
                     int64_t Kdim, const double* __restrict__ Bpack, int64_t Sp, const double* __restrict__ Kq,
                     double* __restrict__ var) {
     extern __shared__ __align__(16) unsigned char gemm_smem_raw[];
@@ -512,7 +547,7 @@ static EpPlan ep_plan(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp) {
     p.m = T + n;
     p.nb = (T + 15) / 16;
     p.nbp = p.nb * (p.nb + 1) / 2;
-    p.Kdim = p.nbp * 256;
+    p.Kdim = quad_num_slices(p.nb) * 16;
     p.nc = N < PS_CHUNK ? (N < 1 ? 1 : N) : PS_CHUNK;
     int64_t o = 0;
     auto take = [&](int64_t bytes) {
@@ -524,7 +559,7 @@ static EpPlan ep_plan(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp) {
     p.off_bext = take(p.m * (p.m + 1) * 8);
     p.off_kc = take(p.nc * p.m * 8);
     p.off_gc = take(p.nc * (p.m + 1) * 8);
-    p.off_table = take((p.nbp + 1) * 8);
+    p.off_table = take((quad_num_slices(p.nb) + 1) * (int64_t)sizeof(QSlice));
     p.off_bpack = take(p.Kdim * Sp * 8);
     p.off_mean = take(p.nc * Sp * 8);
     p.off_var = take(p.nc * Sp * 8);
@@ -573,7 +608,7 @@ extern "C" int tes_ep_acq_f64(int mode, const double* x, int64_t N, int64_t d, c
     double* Bext = (double*)(base + pl.off_bext);
     double* Kc = (double*)(base + pl.off_kc);
     double* Gc = (double*)(base + pl.off_gc);
-    int2* table = (int2*)(base + pl.off_table);
+    QSlice* table = (QSlice*)(base + pl.off_table);
     double* Bpack = (double*)(base + pl.off_bpack);
     double* meanc = (double*)(base + pl.off_mean);
     double* varc = (double*)(base + pl.off_var);
@@ -584,7 +619,7 @@ extern "C" int tes_ep_acq_f64(int mode, const double* x, int64_t N, int64_t d, c
     int rc;
     if ((rc = launch_concat_rows(test_xs, T, X, n, (int)d, xto, st))) return rc;
     if ((rc = launch_build_bext(invpNK, Y, m, T, Bext, st))) return rc;
-    blockpair_table_kernel<<<1, 32, 0, st>>>((int)pl.nb, table);
+    quad_slice_table_kernel<<<1, 32, 0, st>>>((int)pl.nb, table);
     TES_LAUNCH_OK();
     {
         int64_t tot = pl.Kdim * Sp;
