@@ -4,8 +4,8 @@
 
 A "step" is ONE full acquisition step (stages A-D of SURVEY.md section 8) over one batch of synthetic
 input.  Default workload = config C3 of BASELINE.json (the largest single-GPU configuration):
-Hartmann-6 hyper-parameters, 10^6 candidates per GPU (rank 0: the 10^6-point mesh; other ranks:
-seeded uniform candidates), S = 1024 RFF function samples with F = 1024 features each, n = 64
+Hartmann-6 hyper-parameters, 10^6 candidates per GPU (the 10-per-axis mesh of functions.get_meshgrid; with N ranks the
+global mesh has 10 N points along its slowest axis and every rank holds one 10^6-point slab), S = 1024 RFF function samples with F = 1024 features each, n = 64
 observations, TES_ep (criterion ftl, mode empirical, deterministic) on the <= t_max most frequent
 trusted maximizers.  theta/W/b are host-supplied draws (optfunc.py:303-385), inputs of the step.
 
@@ -17,7 +17,7 @@ trusted maximizers.  theta/W/b are host-supplied draws (optfunc.py:303-385), inp
   cpu_baseline / --impl reference: the CPU oracle port of the same step on the box's host cores, on a
            bounded sub-sample of the same workload
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c3s|c3m|c2|c4|c4m|c4s]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c3u|c3s|c3m|c2|c4|c4m|c4s]
   N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 """
 import argparse
@@ -47,10 +47,16 @@ def hartmann6(x):
     return (2.58 + np.sum(alpha * np.exp(-np.sum(A * (x - P) ** 2, axis=2)), axis=1)) / 1.94
 
 
-def meshgrid(xmin, xmax, nx, xdim):
-    """functions.get_meshgrid (functions.py:135-141)."""
+def meshgrid(xmin, xmax, nx, xdim, slab=0, nslab=1):
+    """functions.get_meshgrid (functions.py:135-141).  nslab > 1: the mesh is refined to nx * nslab points along its
+    slowest axis (the second coordinate, np.meshgrid's 'xy' order) and slab `slab` of nx of them is returned, i.e.
+    the contiguous shard of a rank when the global mesh is split across nslab GPUs."""
     x1d = np.linspace(xmin, xmax, nx)
-    xds = np.meshgrid(*([x1d] * xdim))
+    axes = [x1d] * xdim
+    if nslab > 1:
+        axes = list(axes)
+        axes[1] = np.linspace(xmin, xmax, nx * nslab)[slab * nx:(slab + 1) * nx]
+    xds = np.meshgrid(*axes)
     return np.concatenate([xd.reshape(-1, 1) for xd in xds], axis=1)
 
 
@@ -63,6 +69,8 @@ WORKLOADS = {
     # Monte-Carlo sizes of the criterion (I = niteration, Y = nysample)
     "c3": dict(desc="C3 Hartmann-6 TES_ep empirical, 1M candidates x 1024 maximizer samples per GPU",
                d=6, N=10 ** 6, S=1024, F=1024, n=64, t_max=128),
+    "c3u": dict(desc="C3 shapes on UNSTRUCTURED (uniform random) candidates: the general MUFU-bound stage A", d=6,
+                N=10 ** 6, S=1024, F=1024, n=64, t_max=128, uniform=True),
     "c3s": dict(desc="C3 shapes scaled down (smoke)", d=6, N=50_000, S=128, F=256, n=32, t_max=32),
     "c3m": dict(desc="C3 shapes, mid size (profiling)", d=6, N=200_000, S=256, F=1024, n=64, t_max=64),
     "c2": dict(desc="C2 Brooms-Barn pH hyper-parameters, 2-D 20x20 grid, TES_ep (ftl, ep), S=32 (launch-latency case)", d=2,
@@ -126,8 +134,8 @@ def make_workload(name, rank, world, host_only=False):
         hyp = dict(l=np.array([177.9418631280815, 309.4630784148164]), sigma=0.29444226420446995,
                    sigma0=0.06476473751595126)
         Y = rs.randn(n, 1) * 0.5
-    if rank == 0 and d == 6 and N == 10 ** 6:
-        cand = meshgrid(0.0, 1.0, 10, 6)
+    if d == 6 and N == 10 ** 6 and not wl.get("uniform"):
+        cand = meshgrid(0.0, 1.0, 10, 6, slab=rank, nslab=world)      # every rank: a 10^6-point slab of the global mesh
     elif d == 2 and N == 400:
         cand = meshgrid(0.0, 1.0, 20, 2)
     else:
@@ -365,7 +373,26 @@ def main():
     local_pairs = wl["N"] * wl["S"]
     algo_excl_cos = local_pairs * F * (2 * d + 3) / t_rff * 1e-12  # SURVEY 8(d) figure, cos not counted
     screened = wl["N"] >= 32768 and d <= 10
-    if screened and d >= 5:
+    product = ops.detect_product_structure(devt["cand"]) if wl["N"] >= ops.PRODUCT_MIN_N else None
+    if product:
+        # stage A on a product-structured candidate set = one fp64 GEMM per function sample on the DMMA pipe
+        # (csrc/rffprod.cu): 2 * N * 2F flops per sample; operands (nu + nv) * 2F doubles per sample, L2-resident
+        mma_peak = ops.fp64_mma_peak(1.0)
+        gflops = 2.0 * local_pairs * 2 * F
+        achieved = gflops / t_rff * 1e-12
+        roofline = {"bound": "tensor", "pipe": "fp64 tensor pipe (DMMA.8x8x4; tcgen05 has no fp64 path)",
+                    "kernel": "prod_gemm_topk_kernel (+ operand build, list merge, exact refine)",
+                    "achieved": achieved, "peak": mma_peak, "unit": "TFLOP/s", "frac": achieved / mma_peak,
+                    "traffic": None,
+                    "peak_source": "measured in this run: tes_fp64_mma_burn (DMMA.8x8x4 stream, 1 s)",
+                    "fp64_fma_peak_tflops": fp64_peak, "mufu_peak_tcos": mufu_peak,
+                    "algorithmic_excl_cos_tflops": algo_excl_cos,
+                    "equivalent_tcos": local_pairs * F / t_rff * 1e-12,
+                    "per_unit": "product-structured candidates (slow columns [%d, %d), nv=%d): 4F fp64 flops per (candidate, sample) pair "
+                                "instead of F cosines; SURVEY 8d algorithmic = F*(2d+3) flops + F cos" % product,
+                    "launch_ms": t_rff * 1e3, "share_of_step": t_rff * args.steps / dev_s,
+                    "criterion_ms": float(np.mean(rc)) * 1e3 if rc else None}
+    elif screened and d >= 5:
         # stage A = tcgen05/TMEM screen (3xTF32 dot products on the 5th-gen tensor cores, cosine on the MUFU with 1 of
         # every 8 pairs on the FMA pipe) + exact fp64 refine: one cosine per (candidate, sample, feature) on the XU
         # pipe (16 lanes/SM/clk) is the binding resource
@@ -419,6 +446,8 @@ def main():
             "config": dict(config_of(wl), T=out.get("T"), Sp=out.get("Sp"), K=out.get("K"),
                            n_unique_maximizers=out.get("n_unique_maximizers"),
                            l2="flushed between timed iterations (256 MiB memset)",
+                           candidates=("product set U x V detected (slow columns [%d, %d), nv=%d): stage A = fp64 GEMM path" % product)
+                           if product else "unstructured: stage A = tcgen05 screen + fp64 refine (MUFU-bound)",
                            sharding="candidates contiguous per rank; NCCL all-gather of (value,index) partials only"),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(h2d_bytes),

@@ -271,3 +271,81 @@ def test_sample_xmaxs_fmaxs_with_refinement_end_to_end():
     np.testing.assert_allclose(xs[0], rx, atol=1e-9)
     np.testing.assert_allclose(max_xs[0], rx[np.arange(S), best], atol=1e-9)
     np.testing.assert_allclose(max_fs[0], rf[np.arange(S), best], atol=1e-9)
+
+
+# ---- product-structured candidate sets (csrc/rffprod.cu) -------------------------------------------------------------
+def _mesh(axes):
+    """functions.get_meshgrid order (np.meshgrid 'xy', flattened C-order)."""
+    xds = np.meshgrid(*axes)
+    return np.ascontiguousarray(np.concatenate([xd.reshape(-1, 1) for xd in xds], axis=1))
+
+
+@pytest.mark.parametrize("axes_n,S,F,k,shared", [((7, 5, 6, 4), 9, 96, 1, False), ((10, 10, 10, 10, 10), 5, 257, 3, False),
+                                                 ((33, 41), 6, 130, 8, False), ((12, 9, 5), 7, 64, 2, True),
+                                                 ((6, 6, 6, 6, 6, 6), 4, 300, 3, False)])
+def test_product_path_is_bit_identical_to_the_general_kernels(axes_n, S, F, k, shared):
+    """A mesh is detected as U x V and scored by one DMMA GEMM per sample + exact refine: indices AND values are the
+    bits of the C oracle (= of the general kernels)."""
+    from oracle import c_oracle as co
+    from tes_b200 import ops
+    rs = np.random.RandomState(sum(axes_n) + S)
+    d = len(axes_n)
+    cand = _mesh([np.sort(rs.rand(n)) * 2.0 - 0.5 for n in axes_n])
+    Wn = rs.randn(1 if shared else S, F, d) * 2.0
+    bn = 2 * np.pi * rs.rand(1 if shared else S, F, 1)
+    th = rs.randn(S, F, 1)
+    det = ops.detect_product_structure(ops.dev(cand))
+    assert det is not None and cand.shape[0] % det[2] == 0
+    idx, val = ops.rff_topk(cand, Wn, bn, th, 1.3, k=k, idx_offset=1000, method=ops.RFF_PRODUCT)
+    ridx, rval = co.rff_topk(cand, Wn, bn, th, 1.3, k, idx_offset=1000)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ridx)
+    np.testing.assert_array_equal(val.cpu().numpy(), rval)
+    # every admissible split point gives the same answer (meshgrid 'xy' order: columns 1, 0, 2, 3, ... slowest to fastest)
+    for du in range(2, d):
+        nv = int(np.prod(axes_n[du:]))
+        i2, v2, fl = ops.rff_topk_product(cand, Wn, bn, th, 1.3, 0, du, nv, k=k, idx_offset=1000)
+        assert int(fl.sum()) == 0
+        np.testing.assert_array_equal(i2.cpu().numpy(), ridx)
+        np.testing.assert_array_equal(v2.cpu().numpy(), rval)
+
+
+def test_product_path_flags_ties_and_falls_back():
+    """Exact ties (a constant sample; duplicated axis values) cannot be ranked by the GEMM values: the sample is flagged
+    and recomputed by the general kernel -> lowest-index tie rule preserved."""
+    from oracle import c_oracle as co
+    from tes_b200 import ops
+    rs = np.random.RandomState(3)
+    ax = np.sort(rs.rand(40))
+    ax2 = ax.copy()
+    ax2[7] = ax2[6]                                  # duplicated axis value -> duplicated candidates
+    cand = _mesh([ax2, ax, ax[:20]])
+    S, F, d = 5, 80, 3
+    Wn, bn, th = rs.randn(S, F, d), 2 * np.pi * rs.rand(S, F, 1), rs.randn(S, F, 1)
+    th[2] = 0.0                                      # a constant (zero) function sample: every candidate ties
+    det = ops.detect_product_structure(ops.dev(cand))
+    assert det is not None
+    _, _, flag = ops.rff_topk_product(cand, Wn, bn, th, 0.9, det[0], det[1], det[2], k=3)
+    assert int(flag[2]) == 1
+    idx, val = ops.rff_topk(cand, Wn, bn, th, 0.9, k=3, method=ops.RFF_PRODUCT)
+    ridx, rval = co.rff_topk(cand, Wn, bn, th, 0.9, 3)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ridx)
+    np.testing.assert_array_equal(val.cpu().numpy(), rval)
+    assert idx.cpu().numpy()[2].tolist() == [0, 1, 2]
+
+
+def test_product_structure_detection():
+    import torch
+    from tes_b200 import ops
+    rs = np.random.RandomState(0)
+    assert ops.detect_product_structure(ops.dev(rs.rand(5000, 4))) is None
+    m = _mesh([np.linspace(0, 1, 10)] * 6)
+    assert ops.detect_product_structure(ops.dev(m)) == (0, 3, 1000)
+    assert ops.detect_product_structure(ops.dev(m[300_000:600_000])) is not None      # a slab of the mesh (a rank's shard)
+    m2 = m.copy()
+    m2[123457, 4] += 1e-9
+    assert ops.detect_product_structure(ops.dev(m2)) is None
+    # large N: the automatic path takes it and agrees with the general kernel forced explicitly
+    th, Wn, bn = rs.randn(3, 64, 6), rs.randn(3, 64, 6), rs.rand(3, 64, 1)
+    a = ops.rff_topk(m, Wn, bn, th[:, :, :1], 1.0, k=2)
+    b = ops.rff_topk(m, Wn, bn, th[:, :, :1], 1.0, k=2, product=False)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])

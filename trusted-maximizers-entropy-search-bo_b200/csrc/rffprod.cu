@@ -1,0 +1,433 @@
+// rffprod.cu -- Stage A on PRODUCT-STRUCTURED candidate sets (every mesh of the discrete drivers: functions.get_meshgrid,
+// bo_discrete.py; BASELINE configs C2 / C3).
+//
+// If the candidates are U x V in row-major order -- the coordinates in columns [s_lo, s_hi) depend on i / nv only (U) and
+// the other columns on i % nv only (V) -- then
+//     cos(w.x + b) = cos(alpha) cos(beta) - sin(alpha) sin(beta),   alpha = w_U.u + b,  beta = w_V.v
+// and one function sample on the whole set is a GEMM
+//     f_j(u, v) = scale * sum_f [theta_f cos alpha_f(u)] cos beta_f(v) + [-theta_f sin alpha_f(u)] sin beta_f(v)
+//               = scale * (P_j Q_j^T)(u, v),        P_j (nu x 2F),  Q_j (nv x 2F)
+// i.e. 2 nu nv 2F flops on the fp64 tensor pipe (DMMA) instead of nu nv F cosines on the MUFU: 4.3e12 flops instead of
+// 1.07e12 cosines at C3 (N = 10^6 = 1000 x 1000, F = 1024, S = 1024), and only S (nu + nv) F sincos to build the operands.
+//
+// The GEMM values differ from the spec sequence of include/tes_spec.h only by rounding (both are fp64 evaluations of
+// the same function: |difference| <= B_j = 2 u scale sum_f |theta_f| (4 (d + 2) A_j + 3F + 16) with u = 2^-53 and A_j
+// the largest |argument| of the sample, derived in prod_exact_kernel).  Selection therefore works like the other
+// screens: every warp of the GEMM keeps the kp = k + 8 best of its 32 x 32 values, the lists are merged, the kp
+// survivors per sample are re-evaluated with the EXACT spec sequence and the final top-k is taken by (exact value
+// desc, index asc).  A sample whose kp-th best GEMM value is not below its k-th best by more than 2 B_j (exact ties:
+// duplicated candidates, constant samples) is FLAGGED and the caller recomputes with the general kernel, so the result
+// is bit-identical to tes_rff_topk_f64 in every case.
+#include "gemm.cuh"
+#include "gp.cuh"
+
+namespace tes {
+
+constexpr int PROD_MAX_KP = 16;
+__host__ __device__ constexpr int prod_rec(int d) { return (d + 3) & ~1; }   // same record as rff.cu
+
+__global__ void prod_pack_kernel(const double* __restrict__ W, const double* __restrict__ b,
+                                 const double* __restrict__ theta, int64_t S, int64_t F, int d, int w_shared, int rec,
+                                 double* __restrict__ feat) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S * F) return;
+    int64_t j = t / F, f = t % F;
+    int64_t jw = w_shared ? 0 : j;
+    const double* w = W + (jw * F + f) * d;
+    double* o = feat + t * rec;
+    for (int k = 0; k < d; ++k) o[k] = __dmul_rn(w[k], TES_INV_PI);
+    o[d] = __dmul_rn(b[jw * F + f], TES_INV_PI);
+    o[d + 1] = theta[t];
+    for (int k = d + 2; k < rec; ++k) o[k] = 0.0;
+}
+
+// P[g][iu][2f] = theta cos(alpha), P[g][iu][2f+1] = -theta sin(alpha)      (threads: f fastest)
+__global__ void prod_build_p_kernel(const double* __restrict__ cand, int64_t nu, int64_t nv, int d, int s_lo, int s_hi,
+                                    const double* __restrict__ W, const double* __restrict__ b,
+                                    const double* __restrict__ theta, int64_t j0, int64_t G, int64_t F, int w_shared,
+                                    double* __restrict__ P) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * nu * F) return;
+    const int64_t f = t % F, iu = (t / F) % nu, g = t / (F * nu);
+    const int64_t j = j0 + g, jw = w_shared ? 0 : j;
+    const double* w = W + (jw * F + f) * d;
+    const double* u = cand + (iu * nv) * d;
+    double a = b[jw * F + f];
+    for (int k = s_lo; k < s_hi; ++k) a = fma(w[k], u[k], a);
+    double sn, cs;
+    sincos(a, &sn, &cs);
+    const double th = theta[j * F + f];
+    double2 o = make_double2(th * cs, -th * sn);
+    *reinterpret_cast<double2*>(P + ((g * nu + iu) * F + f) * 2) = o;
+}
+
+// Qt[g][2f][iv] = cos(beta), Qt[g][2f+1][iv] = sin(beta)                    (threads: iv fastest)
+__global__ void prod_build_q_kernel(const double* __restrict__ cand, int64_t nv, int d, int s_lo, int s_hi,
+                                    const double* __restrict__ W, int64_t j0, int64_t G, int64_t F, int w_shared,
+                                    double* __restrict__ Qt) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * F * nv) return;
+    const int64_t iv = t % nv, f = (t / nv) % F, g = t / (nv * F);
+    const int64_t jw = w_shared ? 0 : j0 + g;
+    const double* w = W + (jw * F + f) * d;
+    const double* v = cand + iv * d;
+    double a = 0.0;
+    for (int k = 0; k < s_lo; ++k) a = fma(w[k], v[k], a);
+    for (int k = s_hi; k < d; ++k) a = fma(w[k], v[k], a);
+    double sn, cs;
+    sincos(a, &sn, &cs);
+    Qt[((g * F + f) * 2) * nv + iv] = cs;
+    Qt[((g * F + f) * 2 + 1) * nv + iv] = sn;
+}
+
+// C_g = P_g Qt_g on the DMMA core; instead of storing C every warp keeps the kp best of its 32 x 32 values.
+// part lists: (list, g, kp) with list = (tile * 8 + warp).
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+    prod_gemm_topk_kernel(const double* __restrict__ P, const double* __restrict__ Qt, int64_t nu, int64_t nv, int64_t K2,
+                          double scale, int64_t idx_offset, int kp, int64_t G, double* __restrict__ part_val,
+                          int64_t* __restrict__ part_idx) {
+    extern __shared__ __align__(16) unsigned char gemm_smem_raw[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(gemm_smem_raw);
+    const int64_t g = blockIdx.z;
+    const int64_t row0 = (int64_t)blockIdx.x * GEMM_BM;
+    const int64_t col0 = (int64_t)blockIdx.y * GEMM_BN;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    APlain ap{P + g * nu * K2, K2, nu, K2};
+    gemm_mainloop(ap, Qt + g * K2 * nv, nv, K2, nv, row0, col0, sm, acc);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int64_t list = ((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * 8 + warp;
+    double* ov = part_val + (list * G + g) * kp;
+    int64_t* oi = part_idx + (list * G + g) * kp;
+    // scale as the spec does (one rounding after the feature sum)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) acc[i][j][e] = __dmul_rn(scale, acc[i][j][e]);
+    double pv = pos_inf();
+    int64_t pi = -1;
+    for (int r = 0; r < kp; ++r) {
+        double bv = neg_inf();
+        int64_t bi = INT64_MAX;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t row = row0 + gemm_row_of(warp, lane, i);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t col = col0 + gemm_col_of(warp, lane, j, e);
+                    const int64_t ci = row * nv + col + idx_offset;
+                    const double v = acc[i][j][e];
+                    if (row < nu && col < nv && better(pv, pi, v, ci) && better(v, ci, bv, bi)) {
+                        bv = v;
+                        bi = ci;
+                    }
+                }
+        }
+        warp_argmax(bv, bi);
+        const bool found = (bi != INT64_MAX);
+        if (lane == 0) {
+            ov[r] = found ? bv : neg_inf();
+            oi[r] = found ? bi : -1;
+        }
+        if (!found) {
+            for (int q = r + 1; q < kp; ++q)
+                if (lane == 0) {
+                    ov[q] = neg_inf();
+                    oi[q] = -1;
+                }
+            break;
+        }
+        pv = bv;
+        pi = bi;
+    }
+}
+
+// merge `nlist` partial lists per sample: vals/idx (nlist, G, kp) -> (G, kp), one 256-thread CTA per sample, kp rounds of
+// "best entry strictly after the previous winner" (same ordering rule as everywhere: value desc, index asc)
+__global__ void __launch_bounds__(256)
+    prod_merge_kernel(const double* __restrict__ vals, const int64_t* __restrict__ idx, int64_t nlist, int64_t G, int kp,
+                      double* __restrict__ out_val, int64_t* __restrict__ out_idx) {
+    __shared__ double sv[8];
+    __shared__ int64_t si[8];
+    __shared__ double wv;
+    __shared__ int64_t wi;
+    const int64_t g = blockIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t n = nlist * kp;
+    double pv = pos_inf();
+    int64_t pi = -1;
+    for (int r = 0; r < kp; ++r) {
+        double bv = neg_inf();
+        int64_t bi = INT64_MAX;
+        for (int64_t e = t; e < n; e += 256) {
+            const int64_t p = e / kp, q = e % kp;
+            const double v = vals[(p * G + g) * kp + q];
+            const int64_t i = idx[(p * G + g) * kp + q];
+            if (i >= 0 && better(pv, pi, v, i) && better(v, i, bv, bi)) {
+                bv = v;
+                bi = i;
+            }
+        }
+        warp_argmax(bv, bi);
+        if (lane == 0) {
+            sv[warp] = bv;
+            si[warp] = bi;
+        }
+        __syncthreads();
+        if (t == 0) {
+            double v = sv[0];
+            int64_t i = si[0];
+            for (int w = 1; w < 8; ++w)
+                if (si[w] != INT64_MAX && (i == INT64_MAX || better(sv[w], si[w], v, i))) {
+                    v = sv[w];
+                    i = si[w];
+                }
+            const bool found = (i != INT64_MAX);
+            out_val[g * kp + r] = found ? v : neg_inf();
+            out_idx[g * kp + r] = found ? i : -1;
+            wv = v;
+            wi = i;
+        }
+        __syncthreads();
+        if (wi == INT64_MAX) {   // exhausted: the remaining slots are empty
+            for (int q = r + 1 + t; q < kp; q += 256) {
+                out_val[g * kp + q] = neg_inf();
+                out_idx[g * kp + q] = -1;
+            }
+            break;
+        }
+        pv = wv;
+        pi = wi;
+        __syncthreads();
+    }
+}
+
+// exact spec values of the kp survivors of every sample (one thread per (sample, slot): the sequence of
+// rff_value_kernel_generic), and the safety flag of the sample (slot 0).
+__global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const double* __restrict__ feat, int rec,
+                                  int64_t S, int64_t F, double scale, int64_t idx_offset, int k, int kp,
+                                  const double* __restrict__ approx_val, const int64_t* __restrict__ idx,
+                                  const double* __restrict__ xmax, double* __restrict__ exact_val,
+                                  int* __restrict__ flag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S * kp) return;
+    const int64_t j = t / kp;
+    const int r = (int)(t % kp);
+    const double* fj = feat + j * F * rec;
+    const int64_t gi = idx[t];
+    double val = neg_inf();
+    if (gi >= 0) {
+        const double* x = cand + (gi - idx_offset) * d;
+        double acc = 0.0;
+        for (int64_t f = 0; f < F; ++f) {
+            const double* rr = fj + f * rec;
+            double h = __ldg(rr + d);
+            for (int kk = 0; kk < d; ++kk) h = fma(__ldg(rr + kk), __ldg(x + kk), h);
+            acc = fma(__ldg(rr + d + 1), cospi_spec(h), acc);
+        }
+        val = __dmul_rn(scale, acc);
+    }
+    exact_val[t] = val;
+    if (r == 0) {
+        // B_j: both values are fp64 evaluations of the same real function.  Per feature the argument carries
+        // <= 4 (d + 2) u A rounding (prescale by 1/pi, fma chains on both sides; A = largest |argument| of the sample),
+        // cos / sincos and the products <= 16 u, and the two accumulations (F sequential fmas; 2F DMMA steps)
+        // <= 3 F u sum|theta|.  Doubled for margin.
+        double sa = 0.0, am = 0.0;
+        for (int64_t f = 0; f < F; ++f) {
+            const double* rr = fj + f * rec;
+            sa += fabs(__ldg(rr + d + 1));
+            double a = fabs(__ldg(rr + d));
+            for (int kk = 0; kk < d; ++kk) a = fma(fabs(__ldg(rr + kk)), xmax[kk], a);
+            am = a > am ? a : am;
+        }
+        const double u = 1.1102230246251565e-16;
+        const double B = 2.0 * u * scale * sa * (4.0 * (d + 2) * 3.141592653589793 * am + 3.0 * (double)F + 16.0) + 1e-300;
+        const double vk = approx_val[j * kp + (k - 1)], vl = approx_val[j * kp + (kp - 1)];
+        const bool full = idx[j * kp + (kp - 1)] >= 0;   // fewer than kp candidates in total: nothing was cut
+        const bool enough = idx[j * kp + (k - 1)] >= 0;  // NaN values are never selected: let the general kernel decide
+        // safe iff the kp-th best GEMM value is below the k-th best by more than 2B
+        const bool safe = !full || (vl < vk - 2.0 * B);
+        flag[j] = (safe && enough && vk == vk && B == B) ? 0 : 1;
+    }
+}
+
+// xmax[k] = max_i |cand[i][k]| over the product set: the slow coordinates only vary with i / nv, the rest with i % nv
+__global__ void prod_xmax_kernel(const double* __restrict__ cand, int64_t nu, int64_t nv, int d, int s_lo, int s_hi,
+                                 double* __restrict__ xmax) {
+    __shared__ double red[256];
+    for (int k = 0; k < d; ++k) {
+        double m = 0.0;
+        if (k >= s_lo && k < s_hi) {
+            for (int64_t i = threadIdx.x; i < nu; i += blockDim.x) m = fmax(m, fabs(cand[(i * nv) * d + k]));
+        } else {
+            for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) m = fmax(m, fabs(cand[i * d + k]));
+        }
+        red[threadIdx.x] = m;
+        __syncthreads();
+        for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) xmax[k] = red[0];
+        __syncthreads();
+    }
+}
+
+struct ProdPlan {
+    int64_t nu, G, gx, gy, nlist;
+    int rec, kp;
+    int64_t off_feat, off_p, off_q, off_pv, off_pi, off_mv, off_mi, off_ev, off_xmax, total;
+};
+
+static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k) {
+    ProdPlan p;
+    p.nu = N / nv;
+    p.rec = prod_rec((int)d);
+    p.kp = k + 8 > PROD_MAX_KP ? PROD_MAX_KP : k + 8;
+    const int64_t per_sample = (p.nu + nv) * 2 * F * 8;
+    int64_t G = per_sample > 0 ? (int64_t)(1.5e9 / (double)per_sample) : 1;
+    if (G < 1) G = 1;
+    if (G > S) G = S;
+    if (G > 65535) G = 65535;
+    p.G = G;
+    p.gx = (p.nu + GEMM_BM - 1) / GEMM_BM;
+    p.gy = (nv + GEMM_BN - 1) / GEMM_BN;
+    p.nlist = p.gx * p.gy * 8;
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) {
+        int64_t r = o;
+        o += align_up(bytes, 256);
+        return r;
+    };
+    p.off_feat = take(S * F * p.rec * 8);
+    p.off_p = take(G * p.nu * 2 * F * 8);
+    p.off_q = take(G * 2 * F * nv * 8);
+    p.off_pv = take(p.nlist * G * p.kp * 8);
+    p.off_pi = take(p.nlist * G * p.kp * 8);
+    p.off_mv = take(S * p.kp * 8);
+    p.off_mi = take(S * p.kp * 8);
+    p.off_ev = take(S * p.kp * 8);
+    p.off_xmax = take(64 * 8);
+    p.total = o;
+    return p;
+}
+
+// final top-k of the kp survivors by (exact value desc, index asc); one warp per sample
+__global__ void prod_final_kernel(const double* __restrict__ vals, const int64_t* __restrict__ idx, int kp, int k,
+                                  double* __restrict__ out_val, int64_t* __restrict__ out_idx) {
+    const int64_t j = blockIdx.x;
+    const int lane = threadIdx.x;
+    double pv = pos_inf();
+    int64_t pi = -1;
+    for (int r = 0; r < k; ++r) {
+        double bv = neg_inf();
+        int64_t bi = INT64_MAX;
+        for (int e = lane; e < kp; e += 32) {
+            const double v = vals[j * kp + e];
+            const int64_t i = idx[j * kp + e];
+            if (i >= 0 && better(pv, pi, v, i) && better(v, i, bv, bi)) {
+                bv = v;
+                bi = i;
+            }
+        }
+        warp_argmax(bv, bi);
+        const bool found = (bi != INT64_MAX);
+        if (lane == 0) {
+            out_val[j * k + r] = found ? bv : neg_inf();
+            out_idx[j * k + r] = found ? bi : -1;
+        }
+        if (found) {
+            pv = bv;
+            pi = bi;
+        }
+    }
+}
+
+}  // namespace tes
+
+using namespace tes;
+
+extern "C" int64_t tes_rff_topk_product_workspace_bytes(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k) {
+    if (N < 1 || d < 2 || d > 64 || nv < 1 || N % nv != 0 || S < 1 || F < 1 || k < 1 || k > 8) return -1;
+    return prod_plan(N, d, nv, S, F, k).total;
+}
+
+extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d, int64_t s_lo, int64_t s_hi, int64_t nv,
+                                        const double* W, const double* b, const double* theta, int64_t S, int64_t F,
+                                        int w_shared, double sigma, int k, int64_t idx_offset, int64_t* out_idx,
+                                        double* out_val, int* out_flag, void* ws, int64_t ws_bytes, void* stream) {
+    if (N < 1 || !cand) return -1;
+    if (d < 2 || d > 64) return -3;
+    if (s_lo < 0 || s_hi > d || s_lo >= s_hi || s_hi - s_lo >= d) return -4;
+    if (nv < 1 || N % nv != 0) return -5;
+    if (!W) return -6;
+    if (!b) return -7;
+    if (!theta) return -8;
+    if (S < 1 || S > (1 << 24)) return -9;
+    if (F < 1 || F > (1 << 22)) return -10;
+    if (!(sigma >= 0.0)) return -12;
+    if (k < 1 || k > 8) return -13;
+    if (!out_idx) return -15;
+    if (!out_val) return -16;
+    if (!out_flag) return -17;
+    ProdPlan pl = prod_plan(N, d, nv, S, F, k);
+    if (!ws || ws_bytes < pl.total) return -100;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)ws;
+    double* feat = (double*)(base + pl.off_feat);
+    double* P = (double*)(base + pl.off_p);
+    double* Qt = (double*)(base + pl.off_q);
+    double* pv = (double*)(base + pl.off_pv);
+    int64_t* pi = (int64_t*)(base + pl.off_pi);
+    double* mv = (double*)(base + pl.off_mv);
+    int64_t* mi = (int64_t*)(base + pl.off_mi);
+    double* ev = (double*)(base + pl.off_ev);
+    double* xmax = (double*)(base + pl.off_xmax);
+    const double scale = sqrt(2.0 * sigma / (double)F);
+    const int64_t nu = pl.nu, K2 = 2 * F;
+    prod_pack_kernel<<<(unsigned)((S * F + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, (int)d, w_shared, pl.rec, feat);
+    TES_LAUNCH_OK();
+    prod_xmax_kernel<<<1, 256, 0, st>>>(cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, xmax);
+    TES_LAUNCH_OK();
+    TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(GemmSmem)));
+    TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    for (int64_t j0 = 0; j0 < S; j0 += pl.G) {
+        const int64_t G = (S - j0 < pl.G) ? (S - j0) : pl.G;
+        {
+            const int64_t tot = G * nu * F;
+            prod_build_p_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, W,
+                                                                             b, theta, j0, G, F, w_shared, P);
+            TES_LAUNCH_OK();
+        }
+        {
+            const int64_t tot = G * F * nv;
+            prod_build_q_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cand, nv, (int)d, (int)s_lo, (int)s_hi, W, j0,
+                                                                             G, F, w_shared, Qt);
+            TES_LAUNCH_OK();
+        }
+        dim3 grid((unsigned)pl.gx, (unsigned)pl.gy, (unsigned)G);
+        prod_gemm_topk_kernel<<<grid, GEMM_THREADS, sizeof(GemmSmem), st>>>(P, Qt, nu, nv, K2, scale, idx_offset, pl.kp,
+                                                                            G, pv, pi);
+        TES_LAUNCH_OK();
+        prod_merge_kernel<<<(unsigned)G, 256, 0, st>>>(pv, pi, pl.nlist, G, pl.kp, mv + j0 * pl.kp, mi + j0 * pl.kp);
+        TES_LAUNCH_OK();
+    }
+    {
+        const int64_t tot = S * pl.kp;
+        prod_exact_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(cand, (int)d, feat, pl.rec, S, F, scale,
+                                                                       idx_offset, k, pl.kp, mv, mi, xmax, ev, out_flag);
+        TES_LAUNCH_OK();
+    }
+    prod_final_kernel<<<(unsigned)S, 32, 0, st>>>(ev, mi, pl.kp, k, out_val, out_idx);
+    TES_LAUNCH_OK();
+    return 0;
+}

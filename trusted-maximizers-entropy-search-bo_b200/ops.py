@@ -23,10 +23,80 @@ def _rff_args(cand, W, b, theta):
 RFF_AUTO, RFF_FP64, RFF_SCREEN, RFF_SCREEN_MMA, RFF_SCREEN_TC5, RFF_SCREEN_TC5T = 0, 1, 2, 3, 4, 5
 
 
-def rff_topk(cand, W, b, theta, sigma, k=1, idx_offset=0, method=RFF_AUTO):
-    """Top-k candidates of every RFF function sample -> (idx (S,k) int64, val (S,k)) CUDA tensors.
-    utils_for_continuous.py:172-187.  `method`: RFF_AUTO / RFF_FP64 / RFF_SCREEN (identical results)."""
+RFF_PRODUCT = 6          # product-structured candidate sets: one fp64 tensor-pipe GEMM per sample (csrc/rffprod.cu)
+PRODUCT_MIN_N = 1 << 15  # below this the general kernels are launch-bound anyway
+
+
+def detect_product_structure(cand):
+    """Is the candidate set a product U x V in row-major order -- the coordinates in columns [s_lo, s_hi) depend on
+    i // nv only and the other columns on i % nv only (functions.get_meshgrid, or any slab of such a mesh)?
+    -> (s_lo, s_hi, nv) or None; among the admissible splits the most balanced one (|nu - nv| smallest).
+    A few comparisons over the candidate array on the device."""
+    N, d = cand.shape
+    if d < 2 or N < 4:
+        return None
+    best = None
+    # slow = a prefix [0, du) (meshes of >= 3 dimensions) or a suffix [du, d) (the 2-D mesh, whose first column is fast)
+    for s_lo, s_hi in [(0, du) for du in range(1, d)] + [(du, d) for du in range(1, d)]:
+        same = (cand[:, s_lo:s_hi] == cand[0, s_lo:s_hi]).all(dim=1)
+        if bool(same.all()):
+            continue
+        nv = int(torch.nonzero(~same)[0, 0])       # run length of the first row's slow coordinates
+        if nv < 2 or N % nv:
+            continue
+        nu = N // nv
+        if best is not None and abs(nu - nv) >= abs(best[3] - best[2]):
+            continue
+        c3 = cand.reshape(nu, nv, d)
+        fast = [k for k in range(d) if not (s_lo <= k < s_hi)]
+        if bool((c3[:, :, s_lo:s_hi] == c3[:, :1, s_lo:s_hi]).all()) and bool((c3[:, :, fast] == c3[:1, :, fast]).all()):
+            best = (s_lo, s_hi, nv, nu)
+    return None if best is None else best[:3]
+
+
+def rff_topk_product(cand, W, b, theta, sigma, s_lo, s_hi, nv, k=1, idx_offset=0):
+    """tes_rff_topk_product_f64 -> (idx (S,k), val (S,k), flag (S,) int32).  flag[j] = 1: recompute sample j with the
+    general kernel (rff_topk does that)."""
     cand, W, b, theta, N, d, S, F, ws_ = _rff_args(cand, W, b, theta)
+    L = _lib.lib()
+    need = L.tes_rff_topk_product_workspace_bytes(N, d, int(nv), S, F, int(k))
+    if need < 0:
+        raise ValueError("invalid sizes for tes_rff_topk_product_f64: N=%d d=%d nv=%d S=%d F=%d k=%d" % (N, d, nv, S, F, k))
+    ws = WORKSPACE.get(need, cand.device)
+    out_idx = torch.empty((S, k), dtype=torch.int64, device=cand.device)
+    out_val = torch.empty((S, k), dtype=torch.float64, device=cand.device)
+    flag = torch.empty((S,), dtype=torch.int32, device=cand.device)
+    rc = L.tes_rff_topk_product_f64(ptr(cand), N, d, int(s_lo), int(s_hi), int(nv), ptr(W), ptr(b), ptr(theta), S, F, ws_,
+                                    float(sigma), int(k), int(idx_offset), ptr(out_idx), ptr(out_val), ptr(flag), ptr(ws),
+                                    ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_rff_topk_product_f64")
+    return out_idx, out_val, flag
+
+
+def rff_topk(cand, W, b, theta, sigma, k=1, idx_offset=0, method=RFF_AUTO, product=None):
+    """Top-k candidates of every RFF function sample -> (idx (S,k) int64, val (S,k)) CUDA tensors.
+    utils_for_continuous.py:172-187.  `method`: RFF_AUTO / RFF_FP64 / RFF_SCREEN... (identical results).
+    `product`: (s_lo, s_hi, nv) if the caller knows the candidates are a product set, False to skip the check, None (default)
+    to detect it (RFF_AUTO, N >= 32768, k <= 8).  The product path returns the same bits as the general kernels; the
+    samples it flags as unprovable (exact ties, NaN) are recomputed by the general kernel."""
+    cand, W, b, theta, N, d, S, F, ws_ = _rff_args(cand, W, b, theta)
+    if method in (RFF_AUTO, RFF_PRODUCT) and product is not False and k <= 8 and d >= 2 and \
+            (N >= PRODUCT_MIN_N or method == RFF_PRODUCT):
+        if product is None:
+            product = detect_product_structure(cand)
+        if product:
+            idx, val, flag = rff_topk_product(cand, W, b, theta, sigma, product[0], product[1], product[2], k=k,
+                                              idx_offset=idx_offset)
+            bad = torch.nonzero(flag).reshape(-1)
+            if bad.numel():
+                gi, gv = rff_topk(cand, W if ws_ else W[bad], b if ws_ else b[bad], theta[bad], sigma, k=k,
+                                  idx_offset=idx_offset, product=False)
+                idx[bad], val[bad] = gi, gv
+            return idx, val
+        if method == RFF_PRODUCT:
+            raise ValueError("RFF_PRODUCT: the candidate set is not a product U x V in row-major order")
+    if method == RFF_PRODUCT:
+        raise ValueError("RFF_PRODUCT needs k <= 8 and d >= 2")
     L = _lib.lib()
     need = L.tes_rff_topk_workspace_bytes(N, d, S, F, k)
     if need < 0:
@@ -63,7 +133,7 @@ def topk_merge(vals, idx):
     return out_idx, out_val
 
 
-def fp64_fma_peak(seconds=0.5, device=None, fp32=False, mufu=False):
+def fp64_fma_peak(seconds=0.5, device=None, fp32=False, mufu=False, mma=False):
     """Sustained DFMA (fp32=True: packed-FFMA2) rate in TFLOP/s, or (mufu=True) __cosf evaluations in Tcos/s, of
     the current device, CUDA-event timed."""
     import ctypes
@@ -74,7 +144,8 @@ def fp64_fma_peak(seconds=0.5, device=None, fp32=False, mufu=False):
     sink = torch.empty(blocks * 256, dtype=torch.float32 if (fp32 or mufu) else torch.float64, device=dev_)
     flops = ctypes.c_double(0.0)
     iters = 1 << 16
-    burn = L.tes_mufu_cos_burn if mufu else (L.tes_fp32_fma_burn if fp32 else L.tes_fp64_fma_burn)
+    burn = L.tes_mufu_cos_burn if mufu else (L.tes_fp32_fma_burn if fp32 else
+                                             (L.tes_fp64_mma_burn if mma else L.tes_fp64_fma_burn))
 
     def run(it):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -89,6 +160,11 @@ def fp64_fma_peak(seconds=0.5, device=None, fp32=False, mufu=False):
     it2 = max(iters, int(iters * seconds / max(t, 1e-6)))
     t, fl = run(it2)
     return fl / t * 1e-12
+
+
+def fp64_mma_peak(seconds=0.5, device=None):
+    """Sustained DMMA.8x8x4 rate in TFLOP/s (the fp64 tensor pipe the GEMM core runs on)."""
+    return fp64_fma_peak(seconds, device, mma=True)
 
 
 def fp32_fma_peak(seconds=0.5, device=None):
