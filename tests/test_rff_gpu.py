@@ -303,10 +303,18 @@ def test_product_path_is_bit_identical_to_the_general_kernels(axes_n, S, F, k, s
     # every admissible split point gives the same answer (meshgrid 'xy' order: columns 1, 0, 2, 3, ... slowest to fastest)
     for du in range(2, d):
         nv = int(np.prod(axes_n[du:]))
-        i2, v2, fl = ops.rff_topk_product(cand, Wn, bn, th, 1.3, 0, du, nv, k=k, idx_offset=1000)
-        assert int(fl.sum()) == 0
-        np.testing.assert_array_equal(i2.cpu().numpy(), ridx)
-        np.testing.assert_array_equal(v2.cpu().numpy(), rval)
+        for tf32 in (True, False):      # 3xTF32 mma.sync screen / fp64 DMMA GEMM: same bits after the exact refine
+            i2, v2, fl = ops.rff_topk_product(cand, Wn, bn, th, 1.3, 0, du, nv, k=k, idx_offset=1000, tf32=tf32)
+            assert int(fl.sum()) == 0
+            np.testing.assert_array_equal(i2.cpu().numpy(), ridx)
+            np.testing.assert_array_equal(v2.cpu().numpy(), rval)
+    s_lo, s_hi, nv = det
+    for tf32 in (True, False):
+        i2, v2, fl = ops.rff_topk_product(cand, Wn, bn, th, 1.3, s_lo, s_hi, nv, k=k, idx_offset=1000, tf32=tf32)
+        good = (fl == 0).cpu().numpy()
+        assert good.mean() > 0.5
+        np.testing.assert_array_equal(i2.cpu().numpy()[good], ridx[good])
+        np.testing.assert_array_equal(v2.cpu().numpy()[good], rval[good])
 
 
 def test_product_path_flags_ties_and_falls_back():
@@ -324,8 +332,9 @@ def test_product_path_flags_ties_and_falls_back():
     th[2] = 0.0                                      # a constant (zero) function sample: every candidate ties
     det = ops.detect_product_structure(ops.dev(cand))
     assert det is not None
-    _, _, flag = ops.rff_topk_product(cand, Wn, bn, th, 0.9, det[0], det[1], det[2], k=3)
-    assert int(flag[2]) == 1
+    for tf32 in (True, False):
+        _, _, flag = ops.rff_topk_product(cand, Wn, bn, th, 0.9, det[0], det[1], det[2], k=3, tf32=tf32)
+        assert int(flag[2]) == 1
     idx, val = ops.rff_topk(cand, Wn, bn, th, 0.9, k=3, method=ops.RFF_PRODUCT)
     ridx, rval = co.rff_topk(cand, Wn, bn, th, 0.9, 3)
     np.testing.assert_array_equal(idx.cpu().numpy(), ridx)
@@ -349,3 +358,28 @@ def test_product_structure_detection():
     a = ops.rff_topk(m, Wn, bn, th[:, :, :1], 1.0, k=2)
     b = ops.rff_topk(m, Wn, bn, th[:, :, :1], 1.0, k=2, product=False)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("eps", [1e-13, 1e-9, 1e-6, 1e-4])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_product_path_near_ties(eps, seed):
+    """Axis values eps apart give candidates whose function values differ by ~eps -- inside the screen's error bound for
+    the 3xTF32 GEMM (and, for 1e-13, the fp64 one): either both near-tied candidates reach the exact refine or the sample
+    is flagged; the answer is the oracle's in every case."""
+    from oracle import c_oracle as co
+    from tes_b200 import ops
+    rs = np.random.RandomState(100 + seed)
+    ax = np.sort(rs.rand(24))
+    ax2 = ax.copy()
+    ax2[1::2] = ax2[0::2] + eps                       # every axis value has a twin eps away
+    cand = _mesh([ax2, ax2, ax[:12], ax2[:16]])
+    S, F, d = 6, 128, 4
+    Wn, bn, th = rs.randn(S, F, d) * 1.5, 2 * np.pi * rs.rand(S, F, 1), rs.randn(S, F, 1)
+    ridx, rval = co.rff_topk(cand, Wn, bn, th, 1.1, 3)
+    idx, val = ops.rff_topk(cand, Wn, bn, th, 1.1, k=3, method=ops.RFF_PRODUCT)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ridx)
+    np.testing.assert_array_equal(val.cpu().numpy(), rval)
+    det = ops.detect_product_structure(ops.dev(cand))
+    i2, v2, fl = ops.rff_topk_product(cand, Wn, bn, th, 1.1, det[0], det[1], det[2], k=3, tf32=False)
+    good = (fl == 0).cpu().numpy()
+    np.testing.assert_array_equal(i2.cpu().numpy()[good], ridx[good])

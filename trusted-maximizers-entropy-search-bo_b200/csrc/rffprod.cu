@@ -149,6 +149,226 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
     }
 }
 
+// ---- 3xTF32 screen of the same GEMM on the legacy tensor-core path (mma.sync.m16n8k8.tf32) ------------------------
+// p = p_hi + p_lo (two TF32 numbers), q likewise; p q ~ p_hi q_hi + p_hi q_lo + p_lo q_hi.  The operands are split once
+// by the build kernels; the fp32 accumulators are flushed into fp64 sums (in shared memory) every PT_FLUSH k so the
+// accumulation error stays bounded (see prod_exact_kernel for the bound).  Same tile shape and top-k epilogue as the
+// fp64 kernel; operands padded with zeros to whole tiles so the loads need no bounds checks.
+constexpr int PT_BM = 128, PT_BN = 64, PT_BK = 16, PT_THREADS = 256;
+constexpr int PT_LDA = PT_BK + 4;    // floats: row stride 20 -> the 8 rows x 4 k of an A fragment hit 32 distinct banks
+constexpr int PT_LDB = PT_BN + 8;    // floats: row stride 72 -> the 4 k x 8 n of a B fragment hit 32 distinct banks
+constexpr int PT_FLUSH = 256;        // k per fp32 accumulation segment
+struct PtSmem {
+    float ahi[2][PT_BM][PT_LDA];
+    float alo[2][PT_BM][PT_LDA];
+    float bhi[2][PT_BK][PT_LDB];
+    float blo[2][PT_BK][PT_LDB];
+    double sum[32][PT_THREADS];      // fp64 running sums, element e of thread t at [e][t]
+};
+
+__device__ __forceinline__ float to_tf32f(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// Phi/Plo[g][iu][2f], [2f+1] (row stride K2p floats, nup rows per sample); pads are pre-zeroed
+__global__ void prod_build_p32_kernel(const double* __restrict__ cand, int64_t nu, int64_t nv, int d, int s_lo, int s_hi,
+                                      const double* __restrict__ W, const double* __restrict__ b,
+                                      const double* __restrict__ theta, int64_t j0, int64_t G, int64_t F, int w_shared,
+                                      int64_t nup, int64_t K2p, float* __restrict__ Phi, float* __restrict__ Plo) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * nu * F) return;
+    const int64_t f = t % F, iu = (t / F) % nu, g = t / (F * nu);
+    const int64_t j = j0 + g, jw = w_shared ? 0 : j;
+    const double* w = W + (jw * F + f) * d;
+    const double* u = cand + (iu * nv) * d;
+    double a = b[jw * F + f];
+    for (int k = s_lo; k < s_hi; ++k) a = fma(w[k], u[k], a);
+    double sn, cs;
+    sincos(a, &sn, &cs);
+    const double th = theta[j * F + f];
+    const float p0 = (float)(th * cs), p1 = (float)(-th * sn);
+    const float h0 = to_tf32f(p0), h1 = to_tf32f(p1);
+    const int64_t o = (g * nup + iu) * K2p + 2 * f;
+    *reinterpret_cast<float2*>(Phi + o) = make_float2(h0, h1);
+    *reinterpret_cast<float2*>(Plo + o) = make_float2(to_tf32f(p0 - h0), to_tf32f(p1 - h1));
+}
+
+// Qhi/Qlo[g][2f][iv], [2f+1][iv] (row stride nvp floats, K2p rows per sample)
+__global__ void prod_build_q32_kernel(const double* __restrict__ cand, int64_t nv, int d, int s_lo, int s_hi,
+                                      const double* __restrict__ W, int64_t j0, int64_t G, int64_t F, int w_shared,
+                                      int64_t nvp, int64_t K2p, float* __restrict__ Qhi, float* __restrict__ Qlo) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * F * nv) return;
+    const int64_t iv = t % nv, f = (t / nv) % F, g = t / (nv * F);
+    const int64_t jw = w_shared ? 0 : j0 + g;
+    const double* w = W + (jw * F + f) * d;
+    const double* v = cand + iv * d;
+    double a = 0.0;
+    for (int k = 0; k < s_lo; ++k) a = fma(w[k], v[k], a);
+    for (int k = s_hi; k < d; ++k) a = fma(w[k], v[k], a);
+    double sn, cs;
+    sincos(a, &sn, &cs);
+    const float c0 = (float)cs, c1 = (float)sn;
+    const float h0 = to_tf32f(c0), h1 = to_tf32f(c1);
+    const int64_t o = (g * K2p + 2 * f) * nvp + iv;
+    Qhi[o] = h0;
+    Qhi[o + nvp] = h1;
+    Qlo[o] = to_tf32f(c0 - h0);
+    Qlo[o + nvp] = to_tf32f(c1 - h1);
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 1)
+    prod_gemm_topk_tf32_kernel(const float* __restrict__ Phi, const float* __restrict__ Plo, const float* __restrict__ Qhi,
+                               const float* __restrict__ Qlo, int64_t nu, int64_t nv, int64_t nup, int64_t nvp,
+                               int64_t K2p, double scale, int64_t idx_offset, int kp, int64_t G,
+                               double* __restrict__ part_val, int64_t* __restrict__ part_idx) {
+    extern __shared__ __align__(16) unsigned char pt_smem_raw[];
+    PtSmem& sm = *reinterpret_cast<PtSmem*>(pt_smem_raw);
+    const int64_t g = blockIdx.z;
+    const int64_t row0 = (int64_t)blockIdx.x * PT_BM, col0 = (int64_t)blockIdx.y * PT_BN;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;       // warp tile origin inside the CTA tile
+    const float* pa_hi = Phi + (g * nup + row0) * K2p;
+    const float* pa_lo = Plo + (g * nup + row0) * K2p;
+    const float* pb_hi = Qhi + g * K2p * nvp + col0;
+    const float* pb_lo = Qlo + g * K2p * nvp + col0;
+    // global -> register staging: A tile 128 x 16 floats = 512 float4 per array (2 per thread), B 16 x 64 = 256 (1 per thread)
+    const int ar0 = t >> 2, ac = (t & 3) * 4;                    // rows ar0, ar0 + 64; k offset ac
+    const int br = t >> 4, bc = (t & 15) * 4;
+    float4 ra_hi[2], ra_lo[2], rb_hi, rb_lo;
+    auto gload = [&](int64_t k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            ra_hi[h] = __ldg(reinterpret_cast<const float4*>(pa_hi + (int64_t)(ar0 + 64 * h) * K2p + k0 + ac));
+            ra_lo[h] = __ldg(reinterpret_cast<const float4*>(pa_lo + (int64_t)(ar0 + 64 * h) * K2p + k0 + ac));
+        }
+        rb_hi = __ldg(reinterpret_cast<const float4*>(pb_hi + (k0 + br) * nvp + bc));
+        rb_lo = __ldg(reinterpret_cast<const float4*>(pb_lo + (k0 + br) * nvp + bc));
+    };
+    auto sstore = [&](int st) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            *reinterpret_cast<float4*>(&sm.ahi[st][ar0 + 64 * h][ac]) = ra_hi[h];
+            *reinterpret_cast<float4*>(&sm.alo[st][ar0 + 64 * h][ac]) = ra_lo[h];
+        }
+        *reinterpret_cast<float4*>(&sm.bhi[st][br][bc]) = rb_hi;
+        *reinterpret_cast<float4*>(&sm.blo[st][br][bc]) = rb_lo;
+    };
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) sm.sum[e][t] = 0.0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    sm.sum[(i * 4 + j) * 4 + e][t] += (double)acc[i][j][e];
+                    acc[i][j][e] = 0.0f;
+                }
+    };
+    const int64_t nk = K2p / PT_BK;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int64_t kt = 0; kt < nk; ++kt) {
+        const int cur = (int)(kt & 1);
+        if (kt + 1 < nk) gload((kt + 1) * PT_BK);
+#pragma unroll
+        for (int ks = 0; ks < PT_BK; ks += 8) {
+            uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = wr + 16 * i + gq;
+                ah[i][0] = __float_as_uint(sm.ahi[cur][r][ks + tq]);
+                ah[i][1] = __float_as_uint(sm.ahi[cur][r + 8][ks + tq]);
+                ah[i][2] = __float_as_uint(sm.ahi[cur][r][ks + tq + 4]);
+                ah[i][3] = __float_as_uint(sm.ahi[cur][r + 8][ks + tq + 4]);
+                al[i][0] = __float_as_uint(sm.alo[cur][r][ks + tq]);
+                al[i][1] = __float_as_uint(sm.alo[cur][r + 8][ks + tq]);
+                al[i][2] = __float_as_uint(sm.alo[cur][r][ks + tq + 4]);
+                al[i][3] = __float_as_uint(sm.alo[cur][r + 8][ks + tq + 4]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = wc + 8 * j + gq;
+                bh[j][0] = __float_as_uint(sm.bhi[cur][ks + tq][c]);
+                bh[j][1] = __float_as_uint(sm.bhi[cur][ks + tq + 4][c]);
+                bl[j][0] = __float_as_uint(sm.blo[cur][ks + tq][c]);
+                bl[j][1] = __float_as_uint(sm.blo[cur][ks + tq + 4][c]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    mma_tf32(acc[i][j], al[i], bh[j]);   // small terms first
+                    mma_tf32(acc[i][j], ah[i], bl[j]);
+                    mma_tf32(acc[i][j], ah[i], bh[j]);
+                }
+        }
+        if (kt + 1 < nk) sstore(cur ^ 1);
+        if (((kt + 1) * PT_BK) % PT_FLUSH == 0) flush();
+        __syncthreads();
+    }
+    flush();
+    // values in the accumulator layout: acc[i][j][e]: row wr + 16 i + gq + 8 (e >> 1), col wc + 8 j + 2 tq + (e & 1)
+    const int64_t list = ((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * 8 + warp;
+    double* ov = part_val + (list * G + g) * kp;
+    int64_t* oi = part_idx + (list * G + g) * kp;
+    double pv = pos_inf();
+    int64_t pi = -1;
+    for (int r = 0; r < kp; ++r) {
+        double bv = neg_inf();
+        int64_t bi = INT64_MAX;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int64_t row = row0 + wr + 16 * i + gq + 8 * (e >> 1);
+                    const int64_t col = col0 + wc + 8 * j + 2 * tq + (e & 1);
+                    const int64_t ci = row * nv + col + idx_offset;
+                    const double v = __dmul_rn(scale, sm.sum[(i * 4 + j) * 4 + e][t]);
+                    if (row < nu && col < nv && better(pv, pi, v, ci) && better(v, ci, bv, bi)) {
+                        bv = v;
+                        bi = ci;
+                    }
+                }
+        warp_argmax(bv, bi);
+        const bool found = (bi != INT64_MAX);
+        if (lane == 0) {
+            ov[r] = found ? bv : neg_inf();
+            oi[r] = found ? bi : -1;
+        }
+        if (!found) {
+            for (int q = r + 1; q < kp; ++q)
+                if (lane == 0) {
+                    ov[q] = neg_inf();
+                    oi[q] = -1;
+                }
+            break;
+        }
+        pv = bv;
+        pi = bi;
+    }
+}
+
 // merge `nlist` partial lists per sample: vals/idx (nlist, G, kp) -> (G, kp), one 256-thread CTA per sample, kp rounds of
 // "best entry strictly after the previous winner" (same ordering rule as everywhere: value desc, index asc)
 __global__ void __launch_bounds__(256)
@@ -214,7 +434,7 @@ __global__ void __launch_bounds__(256)
 __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const double* __restrict__ feat, int rec,
                                   int64_t S, int64_t F, double scale, int64_t idx_offset, int k, int kp,
                                   const double* __restrict__ approx_val, const int64_t* __restrict__ idx,
-                                  const double* __restrict__ xmax, double* __restrict__ exact_val,
+                                  const double* __restrict__ xmax, int tf32, double* __restrict__ exact_val,
                                   int* __restrict__ flag) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= S * kp) return;
@@ -249,7 +469,12 @@ __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const 
             am = a > am ? a : am;
         }
         const double u = 1.1102230246251565e-16;
-        const double B = 2.0 * u * scale * sa * (4.0 * (d + 2) * 3.141592653589793 * am + 3.0 * (double)F + 16.0) + 1e-300;
+        double B = 2.0 * u * scale * sa * (4.0 * (d + 2) * 3.141592653589793 * am + 3.0 * (double)F + 16.0) + 1e-300;
+        // 3xTF32 screen: operands carried as hi + lo TF32 pairs (residual <= 2^-21 each, dropped lo*lo <= 2^-22):
+        // <= 1.3 * 2^-20 per term; fp32 accumulation in segments of PT_FLUSH k = 3 * PT_FLUSH / 8 mma steps, each
+        // assumed to err by <= 4 * 2^-24 of the segment's sum of |terms| (checked by tests against the fp64 GEMM);
+        // |terms| of a feature sum to <= |theta_f|.  x1.5 margin.
+        if (tf32) B += 1.5 * scale * sa * (1.3 * 9.5367431640625e-07 + 4.0 * 5.9604644775390625e-08 * 3.0 * (PT_FLUSH / 8));
         const double vk = approx_val[j * kp + (k - 1)], vl = approx_val[j * kp + (kp - 1)];
         const bool full = idx[j * kp + (kp - 1)] >= 0;   // fewer than kp candidates in total: nothing was cut
         const bool enough = idx[j * kp + (k - 1)] >= 0;  // NaN values are never selected: let the general kernel decide
@@ -282,17 +507,20 @@ __global__ void prod_xmax_kernel(const double* __restrict__ cand, int64_t nu, in
 }
 
 struct ProdPlan {
-    int64_t nu, G, gx, gy, nlist;
+    int64_t nu, G, gx, gy, nlist, nup, nvp, K2p;
     int rec, kp;
     int64_t off_feat, off_p, off_q, off_pv, off_pi, off_mv, off_mi, off_ev, off_xmax, total;
 };
 
-static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k) {
+static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k, int tf32 = 0) {
     ProdPlan p;
     p.nu = N / nv;
     p.rec = prod_rec((int)d);
     p.kp = k + 8 > PROD_MAX_KP ? PROD_MAX_KP : k + 8;
-    const int64_t per_sample = (p.nu + nv) * 2 * F * 8;
+    p.nup = (p.nu + PT_BM - 1) / PT_BM * PT_BM;
+    p.nvp = (nv + PT_BN - 1) / PT_BN * PT_BN;
+    p.K2p = (2 * F + PT_BK - 1) / PT_BK * PT_BK;
+    const int64_t per_sample = tf32 ? (p.nup + p.nvp) * p.K2p * 8 : (p.nu + nv) * 2 * F * 8;
     int64_t G = per_sample > 0 ? (int64_t)(1.5e9 / (double)per_sample) : 1;
     if (G < 1) G = 1;
     if (G > S) G = S;
@@ -308,8 +536,8 @@ static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F
         return r;
     };
     p.off_feat = take(S * F * p.rec * 8);
-    p.off_p = take(G * p.nu * 2 * F * 8);
-    p.off_q = take(G * 2 * F * nv * 8);
+    p.off_p = take(tf32 ? G * p.nup * p.K2p * 8 : G * p.nu * 2 * F * 8);     // tf32: hi and lo float arrays
+    p.off_q = take(tf32 ? G * p.K2p * p.nvp * 8 : G * 2 * F * nv * 8);
     p.off_pv = take(p.nlist * G * p.kp * 8);
     p.off_pi = take(p.nlist * G * p.kp * 8);
     p.off_mv = take(S * p.kp * 8);
@@ -355,15 +583,17 @@ __global__ void prod_final_kernel(const double* __restrict__ vals, const int64_t
 
 using namespace tes;
 
-extern "C" int64_t tes_rff_topk_product_workspace_bytes(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k) {
+extern "C" int64_t tes_rff_topk_product_workspace_bytes(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k,
+                                                        int tf32) {
     if (N < 1 || d < 2 || d > 64 || nv < 1 || N % nv != 0 || S < 1 || F < 1 || k < 1 || k > 8) return -1;
-    return prod_plan(N, d, nv, S, F, k).total;
+    return prod_plan(N, d, nv, S, F, k, tf32 != 0).total;
 }
 
 extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d, int64_t s_lo, int64_t s_hi, int64_t nv,
                                         const double* W, const double* b, const double* theta, int64_t S, int64_t F,
                                         int w_shared, double sigma, int k, int64_t idx_offset, int64_t* out_idx,
-                                        double* out_val, int* out_flag, void* ws, int64_t ws_bytes, void* stream) {
+                                        double* out_val, int* out_flag, int tf32, void* ws, int64_t ws_bytes,
+                                        void* stream) {
     if (N < 1 || !cand) return -1;
     if (d < 2 || d > 64) return -3;
     if (s_lo < 0 || s_hi > d || s_lo >= s_hi || s_hi - s_lo >= d) return -4;
@@ -378,7 +608,8 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     if (!out_idx) return -15;
     if (!out_val) return -16;
     if (!out_flag) return -17;
-    ProdPlan pl = prod_plan(N, d, nv, S, F, k);
+    tf32 = tf32 != 0;
+    ProdPlan pl = prod_plan(N, d, nv, S, F, k, tf32);
     if (!ws || ws_bytes < pl.total) return -100;
     cudaStream_t st = (cudaStream_t)stream;
     char* base = (char*)ws;
@@ -400,31 +631,55 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(GemmSmem)));
     TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    float* Phi = (float*)P;
+    float* Plo = Phi + pl.G * pl.nup * pl.K2p;
+    float* Qhi = (float*)Qt;
+    float* Qlo = Qhi + pl.G * pl.K2p * pl.nvp;
+    if (tf32) {
+        TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(PtSmem)));
+        // zero the tile padding once (rows >= nu, columns >= nv, k >= 2F are never written by the build kernels)
+        TES_CUDA_OK(cudaMemsetAsync(P, 0, (size_t)(pl.G * pl.nup * pl.K2p * 8), st));
+        TES_CUDA_OK(cudaMemsetAsync(Qt, 0, (size_t)(pl.G * pl.K2p * pl.nvp * 8), st));
+    }
     for (int64_t j0 = 0; j0 < S; j0 += pl.G) {
         const int64_t G = (S - j0 < pl.G) ? (S - j0) : pl.G;
-        {
-            const int64_t tot = G * nu * F;
-            prod_build_p_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, W,
-                                                                             b, theta, j0, G, F, w_shared, P);
-            TES_LAUNCH_OK();
-        }
-        {
-            const int64_t tot = G * F * nv;
-            prod_build_q_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cand, nv, (int)d, (int)s_lo, (int)s_hi, W, j0,
-                                                                             G, F, w_shared, Qt);
-            TES_LAUNCH_OK();
-        }
         dim3 grid((unsigned)pl.gx, (unsigned)pl.gy, (unsigned)G);
-        prod_gemm_topk_kernel<<<grid, GEMM_THREADS, sizeof(GemmSmem), st>>>(P, Qt, nu, nv, K2, scale, idx_offset, pl.kp,
-                                                                            G, pv, pi);
-        TES_LAUNCH_OK();
+        if (tf32) {
+            const int64_t totp = G * nu * F, totq = G * F * nv;
+            prod_build_p32_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(
+                cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, W, b, theta, j0, G, F, w_shared, pl.nup, pl.K2p, Phi, Plo);
+            TES_LAUNCH_OK();
+            prod_build_q32_kernel<<<(unsigned)((totq + 255) / 256), 256, 0, st>>>(
+                cand, nv, (int)d, (int)s_lo, (int)s_hi, W, j0, G, F, w_shared, pl.nvp, pl.K2p, Qhi, Qlo);
+            TES_LAUNCH_OK();
+            prod_gemm_topk_tf32_kernel<<<grid, PT_THREADS, sizeof(PtSmem), st>>>(
+                Phi, Plo, Qhi, Qlo, nu, nv, pl.nup, pl.nvp, pl.K2p, scale, idx_offset, pl.kp, G, pv, pi);
+            TES_LAUNCH_OK();
+        } else {
+            {
+                const int64_t tot = G * nu * F;
+                prod_build_p_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, W,
+                                                                                 b, theta, j0, G, F, w_shared, P);
+                TES_LAUNCH_OK();
+            }
+            {
+                const int64_t tot = G * F * nv;
+                prod_build_q_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cand, nv, (int)d, (int)s_lo, (int)s_hi, W, j0,
+                                                                                 G, F, w_shared, Qt);
+                TES_LAUNCH_OK();
+            }
+            prod_gemm_topk_kernel<<<grid, GEMM_THREADS, sizeof(GemmSmem), st>>>(P, Qt, nu, nv, K2, scale, idx_offset, pl.kp,
+                                                                                G, pv, pi);
+            TES_LAUNCH_OK();
+        }
         prod_merge_kernel<<<(unsigned)G, 256, 0, st>>>(pv, pi, pl.nlist, G, pl.kp, mv + j0 * pl.kp, mi + j0 * pl.kp);
         TES_LAUNCH_OK();
     }
     {
         const int64_t tot = S * pl.kp;
         prod_exact_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(cand, (int)d, feat, pl.rec, S, F, scale,
-                                                                       idx_offset, k, pl.kp, mv, mi, xmax, ev, out_flag);
+                                                                       idx_offset, k, pl.kp, mv, mi, xmax, tf32, ev, out_flag);
         TES_LAUNCH_OK();
     }
     prod_final_kernel<<<(unsigned)S, 32, 0, st>>>(ev, mi, pl.kp, k, out_val, out_idx);
