@@ -154,17 +154,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
 // by the build kernels; the fp32 accumulators are flushed into fp64 sums (in shared memory) every PT_FLUSH k so the
 // accumulation error stays bounded (see prod_exact_kernel for the bound).  Same tile shape and top-k epilogue as the
 // fp64 kernel; operands padded with zeros to whole tiles so the loads need no bounds checks.
-constexpr int PT_BM = 128, PT_BN = 64, PT_BK = 16, PT_THREADS = 256;
-constexpr int PT_LDA = PT_BK + 4;    // floats: row stride 20 -> the 8 rows x 4 k of an A fragment hit 32 distinct banks
+constexpr int PT_BM = 128, PT_BN = 64, PT_BK = 32, PT_THREADS = 256;
+constexpr int PT_LDA = PT_BK + 4;    // floats: row stride 36 -> the 8 rows x 4 k of an A fragment hit 32 distinct banks
 constexpr int PT_LDB = PT_BN + 8;    // floats: row stride 72 -> the 4 k x 8 n of a B fragment hit 32 distinct banks
 constexpr int PT_FLUSH = 256;        // k per fp32 accumulation segment
-struct PtSmem {
+struct PtSmem {                      // 2 stages x (A hi/lo 128 x 32, B hi/lo 32 x 64), filled by cp.async
     float ahi[2][PT_BM][PT_LDA];
     float alo[2][PT_BM][PT_LDA];
     float bhi[2][PT_BK][PT_LDB];
     float blo[2][PT_BK][PT_LDB];
-    double sum[32][PT_THREADS];      // fp64 running sums, element e of thread t at [e][t]
 };
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 __device__ __forceinline__ float to_tf32f(float x) {
     uint32_t r;
@@ -190,10 +195,12 @@ __global__ void prod_build_p32_kernel(const double* __restrict__ cand, int64_t n
     const double* u = cand + (iu * nv) * d;
     double a = b[jw * F + f];
     for (int k = s_lo; k < s_hi; ++k) a = fma(w[k], u[k], a);
-    double sn, cs;
-    sincos(a, &sn, &cs);
+    // the operands are consumed as hi + lo TF32 pairs (2^-21 residual): reduce the argument in fp64, then sincosf
+    // (2 ulp = 2^-22, covered by the 1.3 * 2^-20 term of the bound) instead of the ~4x dearer fp64 sincos
+    float sn, cs;
+    sincosf((float)(a - 6.283185307179586 * rint(a * 0.15915494309189535)), &sn, &cs);
     const double th = theta[j * F + f];
-    const float p0 = (float)(th * cs), p1 = (float)(-th * sn);
+    const float p0 = (float)(th * (double)cs), p1 = (float)(-th * (double)sn);
     const float h0 = to_tf32f(p0), h1 = to_tf32f(p1);
     const int64_t o = (g * nup + iu) * K2p + 2 * f;
     *reinterpret_cast<float2*>(Phi + o) = make_float2(h0, h1);
@@ -213,9 +220,9 @@ __global__ void prod_build_q32_kernel(const double* __restrict__ cand, int64_t n
     double a = 0.0;
     for (int k = 0; k < s_lo; ++k) a = fma(w[k], v[k], a);
     for (int k = s_hi; k < d; ++k) a = fma(w[k], v[k], a);
-    double sn, cs;
-    sincos(a, &sn, &cs);
-    const float c0 = (float)cs, c1 = (float)sn;
+    float sn, cs;
+    sincosf((float)(a - 6.283185307179586 * rint(a * 0.15915494309189535)), &sn, &cs);
+    const float c0 = cs, c1 = sn;
     const float h0 = to_tf32f(c0), h1 = to_tf32f(c1);
     const int64_t o = (g * K2p + 2 * f) * nvp + iv;
     Qhi[o] = h0;
@@ -240,37 +247,34 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
     const float* pa_lo = Plo + (g * nup + row0) * K2p;
     const float* pb_hi = Qhi + g * K2p * nvp + col0;
     const float* pb_lo = Qlo + g * K2p * nvp + col0;
-    // global -> register staging: A tile 128 x 16 floats = 512 float4 per array (2 per thread), B 16 x 64 = 256 (1 per thread)
-    const int ar0 = t >> 2, ac = (t & 3) * 4;                    // rows ar0, ar0 + 64; k offset ac
-    const int br = t >> 4, bc = (t & 15) * 4;
-    float4 ra_hi[2], ra_lo[2], rb_hi, rb_lo;
-    auto gload = [&](int64_t k0) {
+    // global -> shared with cp.async (16-byte chunks, no staging registers): A tile 128 x 32 floats = 1024 chunks per
+    // array (4 per thread), B tile 32 x 64 = 512 chunks per array (2 per thread)
+    auto issue = [&](int st, int64_t k0) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int c = t + 256 * h, r = c >> 3, kc = (c & 7) * 4;
+            cp_async16(&sm.ahi[st][r][kc], pa_hi + (int64_t)r * K2p + k0 + kc);
+            cp_async16(&sm.alo[st][r][kc], pa_lo + (int64_t)r * K2p + k0 + kc);
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            ra_hi[h] = __ldg(reinterpret_cast<const float4*>(pa_hi + (int64_t)(ar0 + 64 * h) * K2p + k0 + ac));
-            ra_lo[h] = __ldg(reinterpret_cast<const float4*>(pa_lo + (int64_t)(ar0 + 64 * h) * K2p + k0 + ac));
+            const int c = t + 256 * h, r = c >> 4, cc = (c & 15) * 4;
+            cp_async16(&sm.bhi[st][r][cc], pb_hi + (k0 + r) * nvp + cc);
+            cp_async16(&sm.blo[st][r][cc], pb_lo + (k0 + r) * nvp + cc);
         }
-        rb_hi = __ldg(reinterpret_cast<const float4*>(pb_hi + (k0 + br) * nvp + bc));
-        rb_lo = __ldg(reinterpret_cast<const float4*>(pb_lo + (k0 + br) * nvp + bc));
-    };
-    auto sstore = [&](int st) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            *reinterpret_cast<float4*>(&sm.ahi[st][ar0 + 64 * h][ac]) = ra_hi[h];
-            *reinterpret_cast<float4*>(&sm.alo[st][ar0 + 64 * h][ac]) = ra_lo[h];
-        }
-        *reinterpret_cast<float4*>(&sm.bhi[st][br][bc]) = rb_hi;
-        *reinterpret_cast<float4*>(&sm.blo[st][br][bc]) = rb_lo;
+        cp_async_commit();
     };
     float acc[2][4][4];
+    double sum[2][4][4];             // fp64 running sums (registers)
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0f;
-#pragma unroll
-    for (int e = 0; e < 32; ++e) sm.sum[e][t] = 0.0;
+            for (int e = 0; e < 4; ++e) {
+                acc[i][j][e] = 0.0f;
+                sum[i][j][e] = 0.0;
+            }
     auto flush = [&]() {
 #pragma unroll
         for (int i = 0; i < 2; ++i)
@@ -278,17 +282,21 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
             for (int j = 0; j < 4; ++j)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    sm.sum[(i * 4 + j) * 4 + e][t] += (double)acc[i][j][e];
+                    sum[i][j][e] += (double)acc[i][j][e];
                     acc[i][j][e] = 0.0f;
                 }
     };
     const int64_t nk = K2p / PT_BK;
-    gload(0);
-    sstore(0);
-    __syncthreads();
+    issue(0, 0);
     for (int64_t kt = 0; kt < nk; ++kt) {
         const int cur = (int)(kt & 1);
-        if (kt + 1 < nk) gload((kt + 1) * PT_BK);
+        if (kt + 1 < nk) {
+            issue(cur ^ 1, (kt + 1) * PT_BK);   // the other stage was released by the barrier that ended slice kt - 1
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
 #pragma unroll
         for (int ks = 0; ks < PT_BK; ks += 8) {
             uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
@@ -321,9 +329,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
                     mma_tf32(acc[i][j], ah[i], bh[j]);
                 }
         }
-        if (kt + 1 < nk) sstore(cur ^ 1);
         if (((kt + 1) * PT_BK) % PT_FLUSH == 0) flush();
-        __syncthreads();
+        __syncthreads();                        // everyone is done reading stage `cur`
     }
     flush();
     // values in the accumulator layout: acc[i][j][e]: row wr + 16 i + gq + 8 (e >> 1), col wc + 8 j + 2 tq + (e & 1)
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
                     const int64_t row = row0 + wr + 16 * i + gq + 8 * (e >> 1);
                     const int64_t col = col0 + wc + 8 * j + 2 * tq + (e & 1);
                     const int64_t ci = row * nv + col + idx_offset;
-                    const double v = __dmul_rn(scale, sm.sum[(i * 4 + j) * 4 + e][t]);
+                    const double v = __dmul_rn(scale, sum[i][j][e]);
                     if (row < nu && col < nv && better(pv, pi, v, ci) && better(v, ci, bv, bi)) {
                         bv = v;
                         bi = ci;
@@ -470,11 +477,12 @@ __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const 
         }
         const double u = 1.1102230246251565e-16;
         double B = 2.0 * u * scale * sa * (4.0 * (d + 2) * 3.141592653589793 * am + 3.0 * (double)F + 16.0) + 1e-300;
-        // 3xTF32 screen: operands carried as hi + lo TF32 pairs (residual <= 2^-21 each, dropped lo*lo <= 2^-22):
-        // <= 1.3 * 2^-20 per term; fp32 accumulation in segments of PT_FLUSH k = 3 * PT_FLUSH / 8 mma steps, each
-        // assumed to err by <= 4 * 2^-24 of the segment's sum of |terms| (checked by tests against the fp64 GEMM);
-        // |terms| of a feature sum to <= |theta_f|.  x1.5 margin.
-        if (tf32) B += 1.5 * scale * sa * (1.3 * 9.5367431640625e-07 + 4.0 * 5.9604644775390625e-08 * 3.0 * (PT_FLUSH / 8));
+        // 3xTF32 screen: every operand is sincosf of the fp64-reduced argument (argument rounding 2^-22.3, sincosf 2 ulp
+        // = 2^-22) carried as a hi + lo TF32 pair (residual 2^-21): <= 2^-20 per operand, plus the dropped lo*lo
+        // (2^-22): <= 2.5 * 2^-20 per term; fp32 accumulation in segments of PT_FLUSH k = 3 * PT_FLUSH / 8 mma steps,
+        // each assumed to err by <= 4 * 2^-24 of the segment's sum of |terms| (the tests compare against the fp64 GEMM
+        // path on ties 1e-13 ... 1e-4 apart); the |terms| of a feature sum to <= |theta_f|.  x1.5 margin.
+        if (tf32) B += 1.5 * scale * sa * (2.5 * 9.5367431640625e-07 + 4.0 * 5.9604644775390625e-08 * 3.0 * (PT_FLUSH / 8));
         const double vk = approx_val[j * kp + (k - 1)], vl = approx_val[j * kp + (kp - 1)];
         const bool full = idx[j * kp + (kp - 1)] >= 0;   // fewer than kp candidates in total: nothing was cut
         const bool enough = idx[j * kp + (k - 1)] >= 0;  // NaN values are never selected: let the general kernel decide
