@@ -158,11 +158,12 @@ constexpr int PT_BM = 128, PT_BN = 64, PT_BK = 32, PT_THREADS = 256;
 constexpr int PT_LDA = PT_BK + 4;    // floats: row stride 36 -> the 8 rows x 4 k of an A fragment hit 32 distinct banks
 constexpr int PT_LDB = PT_BN + 8;    // floats: row stride 72 -> the 4 k x 8 n of a B fragment hit 32 distinct banks
 constexpr int PT_FLUSH = 256;        // k per fp32 accumulation segment
-struct PtSmem {                      // 2 stages x (A hi/lo 128 x 32, B hi/lo 32 x 64), filled by cp.async
-    float ahi[2][PT_BM][PT_LDA];
-    float alo[2][PT_BM][PT_LDA];
-    float bhi[2][PT_BK][PT_LDB];
-    float blo[2][PT_BK][PT_LDB];
+constexpr int PT_NS = 3;             // cp.async stages
+struct PtSmem {                      // 3 stages x (A hi/lo 128 x 32, B hi/lo 32 x 64) = 166 KB, filled by cp.async
+    float ahi[PT_NS][PT_BM][PT_LDA];
+    float alo[PT_NS][PT_BM][PT_LDA];
+    float bhi[PT_NS][PT_BK][PT_LDB];
+    float blo[PT_NS][PT_BK][PT_LDB];
 };
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
@@ -288,49 +289,54 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
     };
     const int64_t nk = K2p / PT_BK;
     issue(0, 0);
+    if (nk > 1) issue(1, PT_BK);
     for (int64_t kt = 0; kt < nk; ++kt) {
-        const int cur = (int)(kt & 1);
-        if (kt + 1 < nk) {
-            issue(cur ^ 1, (kt + 1) * PT_BK);   // the other stage was released by the barrier that ended slice kt - 1
-            cp_async_wait<1>();
-        } else {
+        const int cur = (int)(kt % PT_NS);
+        if (kt + 1 < nk)
+            cp_async_wait<1>();                 // slice kt has landed (slice kt + 1 may still be in flight)
+        else
             cp_async_wait<0>();
-        }
-        __syncthreads();
-#pragma unroll
-        for (int ks = 0; ks < PT_BK; ks += 8) {
-            uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+        __syncthreads();                        // ... for every thread; and everyone is done reading slice kt - 1
+        if (kt + 2 < nk) issue((int)((kt + 2) % PT_NS), (kt + 2) * PT_BK);   // into the stage slice kt - 1 used
+        // fragments of k8-step s + 1 are fetched while the 24 mma of step s issue (register double buffer)
+        uint32_t ah[2][2][4], al[2][2][4], bh[2][4][2], bl[2][4][2];
+        auto frag = [&](int fb, int ks) {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int r = wr + 16 * i + gq;
-                ah[i][0] = __float_as_uint(sm.ahi[cur][r][ks + tq]);
-                ah[i][1] = __float_as_uint(sm.ahi[cur][r + 8][ks + tq]);
-                ah[i][2] = __float_as_uint(sm.ahi[cur][r][ks + tq + 4]);
-                ah[i][3] = __float_as_uint(sm.ahi[cur][r + 8][ks + tq + 4]);
-                al[i][0] = __float_as_uint(sm.alo[cur][r][ks + tq]);
-                al[i][1] = __float_as_uint(sm.alo[cur][r + 8][ks + tq]);
-                al[i][2] = __float_as_uint(sm.alo[cur][r][ks + tq + 4]);
-                al[i][3] = __float_as_uint(sm.alo[cur][r + 8][ks + tq + 4]);
+                ah[fb][i][0] = __float_as_uint(sm.ahi[cur][r][ks + tq]);
+                ah[fb][i][1] = __float_as_uint(sm.ahi[cur][r + 8][ks + tq]);
+                ah[fb][i][2] = __float_as_uint(sm.ahi[cur][r][ks + tq + 4]);
+                ah[fb][i][3] = __float_as_uint(sm.ahi[cur][r + 8][ks + tq + 4]);
+                al[fb][i][0] = __float_as_uint(sm.alo[cur][r][ks + tq]);
+                al[fb][i][1] = __float_as_uint(sm.alo[cur][r + 8][ks + tq]);
+                al[fb][i][2] = __float_as_uint(sm.alo[cur][r][ks + tq + 4]);
+                al[fb][i][3] = __float_as_uint(sm.alo[cur][r + 8][ks + tq + 4]);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int c = wc + 8 * j + gq;
-                bh[j][0] = __float_as_uint(sm.bhi[cur][ks + tq][c]);
-                bh[j][1] = __float_as_uint(sm.bhi[cur][ks + tq + 4][c]);
-                bl[j][0] = __float_as_uint(sm.blo[cur][ks + tq][c]);
-                bl[j][1] = __float_as_uint(sm.blo[cur][ks + tq + 4][c]);
+                bh[fb][j][0] = __float_as_uint(sm.bhi[cur][ks + tq][c]);
+                bh[fb][j][1] = __float_as_uint(sm.bhi[cur][ks + tq + 4][c]);
+                bl[fb][j][0] = __float_as_uint(sm.blo[cur][ks + tq][c]);
+                bl[fb][j][1] = __float_as_uint(sm.blo[cur][ks + tq + 4][c]);
             }
+        };
+        frag(0, 0);
+#pragma unroll
+        for (int s8 = 0; s8 < PT_BK / 8; ++s8) {
+            const int fb = s8 & 1;
+            if (s8 + 1 < PT_BK / 8) frag(fb ^ 1, (s8 + 1) * 8);
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    mma_tf32(acc[i][j], al[i], bh[j]);   // small terms first
-                    mma_tf32(acc[i][j], ah[i], bl[j]);
-                    mma_tf32(acc[i][j], ah[i], bh[j]);
+                    mma_tf32(acc[i][j], al[fb][i], bh[fb][j]);   // small terms first
+                    mma_tf32(acc[i][j], ah[fb][i], bl[fb][j]);
+                    mma_tf32(acc[i][j], ah[fb][i], bh[fb][j]);
                 }
         }
         if (((kt + 1) * PT_BK) % PT_FLUSH == 0) flush();
-        __syncthreads();                        // everyone is done reading stage `cur`
     }
     flush();
     // values in the accumulator layout: acc[i][j][e]: row wr + 16 i + gq + 8 (e >> 1), col wc + 8 j + 2 tq + (e & 1)
