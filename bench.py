@@ -376,30 +376,30 @@ def main():
     product = ops.detect_product_structure(devt["cand"]) if wl["N"] >= ops.PRODUCT_MIN_N else None
     if product:
         # stage A on a product-structured candidate set = one GEMM per function sample (csrc/rffprod.cu), run as a
-        # 3xTF32 screen on the tensor cores (mma.sync m16n8k8, hi/lo TF32 operands, fp32 segments flushed to fp64)
+        # 3xFP16 screen on the tensor cores (mma.sync m16n8k16, hi/lo fp16 operands, fp32 segments flushed to fp64)
         # followed by the exact fp64 re-evaluation of the k + 8 best candidates per sample.
-        # algorithmic: 2 * N * 2F flops per sample (the fp64 GEMM); executed: 3x that in TF32
+        # algorithmic: 2 * N * 2F flops per sample (the fp64 GEMM); executed: 3x that in fp16
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        tf32_peak = 0.5 * bf16          # TF32 dense = half the bf16 rate on this part (1.1 vs 2.25 PFLOP/s nominal)
+        tf32_peak = bf16                # fp16 dense tensor rate = the bf16 rate
         gflops = 2.0 * local_pairs * 2 * F
         achieved = 3.0 * gflops / t_rff * 1e-12
-        roofline = {"bound": "tensor", "pipe": "TF32 tensor cores through legacy mma.sync (no tcgen05/TMEM yet)",
-                    "kernel": "prod_gemm_topk_tf32_kernel (+ operand build, list merge, exact fp64 refine)",
+        roofline = {"bound": "tensor", "pipe": "fp16 tensor cores through legacy mma.sync m16n8k16 (no tcgen05/TMEM yet)",
+                    "kernel": "prod_gemm_topk_f16_kernel (+ operand build, list merge, exact fp64 refine)",
                     "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
                     "traffic": None,
-                    "peak_source": "0.5 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s)" % (
+                    "peak_source": "bf16_tflops_sustained of MEASURED_PEAKS.json (cuBLAS/tcgen05 rate, %s); legacy mma.sync tops out far below it" % (
                         "measured" if peaks else "fallback 1400"),
                     "algorithmic_fp64_gemm_tflops": gflops / t_rff * 1e-12,
                     "fp64_fma_peak_tflops": fp64_peak, "mufu_peak_tcos": mufu_peak,
                     "algorithmic_excl_cos_tflops": algo_excl_cos,
                     "equivalent_tcos": local_pairs * F / t_rff * 1e-12,
                     "per_unit": "product-structured candidates (slow columns [%d, %d), nv=%d): 4F GEMM flops per (candidate, "
-                                "sample) pair (12F executed as 3xTF32) instead of F cosines; SURVEY 8d algorithmic = "
+                                "sample) pair (12F executed as 3xFP16) instead of F cosines; SURVEY 8d algorithmic = "
                                 "F*(2d+3) flops + F cos" % product,
                     "launch_ms": t_rff * 1e3, "share_of_step": t_rff * args.steps / dev_s,
                     "criterion_ms": float(np.mean(rc)) * 1e3 if rc else None}
@@ -457,7 +457,7 @@ def main():
             "config": dict(config_of(wl), T=out.get("T"), Sp=out.get("Sp"), K=out.get("K"),
                            n_unique_maximizers=out.get("n_unique_maximizers"),
                            l2="flushed between timed iterations (256 MiB memset)",
-                           candidates=("product set U x V detected (slow columns [%d, %d), nv=%d): stage A = GEMM path (3xTF32 screen + fp64 refine)" % product)
+                           candidates=("product set U x V detected (slow columns [%d, %d), nv=%d): stage A = GEMM path (3xFP16 tensor-core screen + fp64 refine)" % product)
                            if product else "unstructured: stage A = tcgen05 screen + fp64 refine (MUFU-bound)",
                            sharding="candidates contiguous per rank; NCCL all-gather of (value,index) partials only"),
             "clocks": clocks,

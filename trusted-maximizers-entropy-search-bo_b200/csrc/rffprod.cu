@@ -18,6 +18,8 @@
 // desc, index asc).  A sample whose kp-th best GEMM value is not below its k-th best by more than 2 B_j (exact ties:
 // duplicated candidates, constant samples) is FLAGGED and the caller recomputes with the general kernel, so the result
 // is bit-identical to tes_rff_topk_f64 in every case.
+#include <cuda_fp16.h>
+
 #include "gemm.cuh"
 #include "gp.cuh"
 
@@ -382,6 +384,232 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
     }
 }
 
+// ---- 3xFP16 screen (mma.sync.m16n8k16.f16, fp32 accumulate): same precision class as 3xTF32 (fp16 carries 11
+// significant bits like TF32; hi + lo = 22 bits) at twice the k per instruction.  Both operands are stored K-contiguous
+// (P: (G, nup, K2p), Q: (G, nvp, K2p) halves) because the k16 fragments pack two consecutive k per register.
+constexpr int PH_BK = 64;            // halves per slice = 4 k16 steps
+constexpr int PH_LD = PH_BK + 8;     // halves: row stride 36 words -> the 8 rows x 4 words of a fragment hit 32 banks
+struct PhSmem {                      // 3 stages x (A hi/lo 128 x 64, B hi/lo 64 x 64 halves) = 162 KB
+    __half ahi[PT_NS][PT_BM][PH_LD];
+    __half alo[PT_NS][PT_BM][PH_LD];
+    __half bhi[PT_NS][PT_BN][PH_LD];
+    __half blo[PT_NS][PT_BN][PH_LD];
+};
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+
+// Phi/Plo[g][iu][2f..2f+1] halves (row stride K2p); which = 0: the U side (theta cos a, -theta sin a),
+// which = 1: the V side (cos b, sin b) written to Qhi/Qlo[g][iv][2f..2f+1]
+__global__ void prod_build_f16_kernel(const double* __restrict__ cand, int64_t nrow, int64_t row_stride, int d, int s_lo,
+                                      int s_hi, int which, const double* __restrict__ W, const double* __restrict__ b,
+                                      const double* __restrict__ theta, int64_t j0, int64_t G, int64_t F, int w_shared,
+                                      int64_t nrowp, int64_t K2p, const double* __restrict__ tmax,
+                                      __half* __restrict__ Hi, __half* __restrict__ Lo) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * nrow * F) return;
+    const int64_t f = t % F, ir = (t / F) % nrow, g = t / (F * nrow);
+    const int64_t j = j0 + g, jw = w_shared ? 0 : j;
+    const double* w = W + (jw * F + f) * d;
+    const double* x = cand + (ir * row_stride) * d;
+    double a;
+    if (which == 0) {
+        a = b[jw * F + f];
+        for (int k = s_lo; k < s_hi; ++k) a = fma(w[k], x[k], a);
+    } else {
+        a = 0.0;
+        for (int k = 0; k < s_lo; ++k) a = fma(w[k], x[k], a);
+        for (int k = s_hi; k < d; ++k) a = fma(w[k], x[k], a);
+    }
+    float sn, cs;
+    sincosf((float)(a - 6.283185307179586 * rint(a * 0.15915494309189535)), &sn, &cs);
+    float p0 = cs, p1 = sn;
+    if (which == 0) {
+        const double tm = tmax[j];                       // fp16 has a 5-bit exponent: theta is normalised per sample
+        const double th = tm > 0.0 ? theta[j * F + f] / tm : 0.0;
+        p0 = (float)(th * (double)cs);
+        p1 = (float)(-th * (double)sn);
+    }
+    __half h0, l0, h1, l1;
+    split_f16(p0, h0, l0);
+    split_f16(p1, h1, l1);
+    const int64_t o = (g * nrowp + ir) * K2p + 2 * f;
+    *reinterpret_cast<__half2*>(Hi + o) = __halves2half2(h0, h1);
+    *reinterpret_cast<__half2*>(Lo + o) = __halves2half2(l0, l1);
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 1)
+    prod_gemm_topk_f16_kernel(const __half* __restrict__ Phi, const __half* __restrict__ Plo,
+                              const __half* __restrict__ Qhi, const __half* __restrict__ Qlo, int64_t nu, int64_t nv,
+                              int64_t nup, int64_t nvp, int64_t K2p, double scale0, const double* __restrict__ tmax,
+                              int64_t idx_offset, int kp, int64_t G, double* __restrict__ part_val,
+                              int64_t* __restrict__ part_idx) {
+    extern __shared__ __align__(16) unsigned char pt_smem_raw[];
+    const double scale = scale0 * tmax[blockIdx.z];
+    PhSmem& sm = *reinterpret_cast<PhSmem*>(pt_smem_raw);
+    const int64_t g = blockIdx.z;
+    const int64_t row0 = (int64_t)blockIdx.x * PT_BM, col0 = (int64_t)blockIdx.y * PT_BN;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
+    const __half* pa_hi = Phi + (g * nup + row0) * K2p;
+    const __half* pa_lo = Plo + (g * nup + row0) * K2p;
+    const __half* pb_hi = Qhi + (g * nvp + col0) * K2p;
+    const __half* pb_lo = Qlo + (g * nvp + col0) * K2p;
+    // cp.async, 16-byte chunks of 8 halves: A tile 128 rows x 8 chunks = 1024 per array (4 per thread), B tile 64 rows
+    // x 8 chunks = 512 per array (2 per thread)
+    auto issue = [&](int st, int64_t k0) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int c = t + 256 * h, r = c >> 3, kc = (c & 7) * 8;
+            cp_async16(&sm.ahi[st][r][kc], pa_hi + (int64_t)r * K2p + k0 + kc);
+            cp_async16(&sm.alo[st][r][kc], pa_lo + (int64_t)r * K2p + k0 + kc);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = t + 256 * h, r = c >> 3, kc = (c & 7) * 8;
+            cp_async16(&sm.bhi[st][r][kc], pb_hi + (int64_t)r * K2p + k0 + kc);
+            cp_async16(&sm.blo[st][r][kc], pb_lo + (int64_t)r * K2p + k0 + kc);
+        }
+        cp_async_commit();
+    };
+    float acc[2][4][4];
+    double sum[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[i][j][e] = 0.0f;
+                sum[i][j][e] = 0.0;
+            }
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    sum[i][j][e] += (double)acc[i][j][e];
+                    acc[i][j][e] = 0.0f;
+                }
+    };
+    const int64_t nk = K2p / PH_BK;
+    issue(0, 0);
+    if (nk > 1) issue(1, PH_BK);
+    for (int64_t kt = 0; kt < nk; ++kt) {
+        const int cur = (int)(kt % PT_NS);
+        if (kt + 1 < nk)
+            cp_async_wait<1>();
+        else
+            cp_async_wait<0>();
+        __syncthreads();
+        if (kt + 2 < nk) issue((int)((kt + 2) % PT_NS), (kt + 2) * PH_BK);
+        uint32_t ah[2][2][4], al[2][2][4], bh[2][4][2], bl[2][4][2];
+        auto ld32 = [](const __half* p) { return *reinterpret_cast<const uint32_t*>(p); };
+        auto frag = [&](int fb, int ks) {   // ks in halves; register r of a fragment = 2 consecutive k
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = wr + 16 * i + gq;
+                ah[fb][i][0] = ld32(&sm.ahi[cur][r][ks + 2 * tq]);
+                ah[fb][i][1] = ld32(&sm.ahi[cur][r + 8][ks + 2 * tq]);
+                ah[fb][i][2] = ld32(&sm.ahi[cur][r][ks + 2 * tq + 8]);
+                ah[fb][i][3] = ld32(&sm.ahi[cur][r + 8][ks + 2 * tq + 8]);
+                al[fb][i][0] = ld32(&sm.alo[cur][r][ks + 2 * tq]);
+                al[fb][i][1] = ld32(&sm.alo[cur][r + 8][ks + 2 * tq]);
+                al[fb][i][2] = ld32(&sm.alo[cur][r][ks + 2 * tq + 8]);
+                al[fb][i][3] = ld32(&sm.alo[cur][r + 8][ks + 2 * tq + 8]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = wc + 8 * j + gq;
+                bh[fb][j][0] = ld32(&sm.bhi[cur][c][ks + 2 * tq]);
+                bh[fb][j][1] = ld32(&sm.bhi[cur][c][ks + 2 * tq + 8]);
+                bl[fb][j][0] = ld32(&sm.blo[cur][c][ks + 2 * tq]);
+                bl[fb][j][1] = ld32(&sm.blo[cur][c][ks + 2 * tq + 8]);
+            }
+        };
+        frag(0, 0);
+#pragma unroll
+        for (int s16 = 0; s16 < PH_BK / 16; ++s16) {
+            const int fb = s16 & 1;
+            if (s16 + 1 < PH_BK / 16) frag(fb ^ 1, (s16 + 1) * 16);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    mma_f16(acc[i][j], al[fb][i], bh[fb][j]);
+                    mma_f16(acc[i][j], ah[fb][i], bl[fb][j]);
+                    mma_f16(acc[i][j], ah[fb][i], bh[fb][j]);
+                }
+        }
+        if (((kt + 1) * PH_BK) % PT_FLUSH == 0) flush();
+    }
+    flush();
+    const int64_t list = ((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * 8 + warp;
+    double* ov = part_val + (list * G + g) * kp;
+    int64_t* oi = part_idx + (list * G + g) * kp;
+    double pv = pos_inf();
+    int64_t pi = -1;
+    for (int r = 0; r < kp; ++r) {
+        double bv = neg_inf();
+        int64_t bi = INT64_MAX;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int64_t row = row0 + wr + 16 * i + gq + 8 * (e >> 1);
+                    const int64_t col = col0 + wc + 8 * j + 2 * tq + (e & 1);
+                    const int64_t ci = row * nv + col + idx_offset;
+                    const double v = __dmul_rn(scale, sum[i][j][e]);
+                    if (row < nu && col < nv && better(pv, pi, v, ci) && better(v, ci, bv, bi)) {
+                        bv = v;
+                        bi = ci;
+                    }
+                }
+        warp_argmax(bv, bi);
+        const bool found = (bi != INT64_MAX);
+        if (lane == 0) {
+            ov[r] = found ? bv : neg_inf();
+            oi[r] = found ? bi : -1;
+        }
+        if (!found) {
+            for (int q = r + 1; q < kp; ++q)
+                if (lane == 0) {
+                    ov[q] = neg_inf();
+                    oi[q] = -1;
+                }
+            break;
+        }
+        pv = bv;
+        pi = bi;
+    }
+}
+
+// tmax[j] = max_f |theta[j][f]| (one block per sample)
+__global__ void prod_tmax_kernel(const double* __restrict__ theta, int64_t F, double* __restrict__ tmax) {
+    __shared__ double red[256];
+    const int64_t j = blockIdx.x;
+    double m = 0.0;
+    for (int64_t f = threadIdx.x; f < F; f += blockDim.x) m = fmax(m, fabs(theta[j * F + f]));
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tmax[j] = red[0];
+}
+
 // merge `nlist` partial lists per sample: vals/idx (nlist, G, kp) -> (G, kp), one 256-thread CTA per sample, kp rounds of
 // "best entry strictly after the previous winner" (same ordering rule as everywhere: value desc, index asc)
 __global__ void __launch_bounds__(256)
@@ -447,7 +675,8 @@ __global__ void __launch_bounds__(256)
 __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const double* __restrict__ feat, int rec,
                                   int64_t S, int64_t F, double scale, int64_t idx_offset, int k, int kp,
                                   const double* __restrict__ approx_val, const int64_t* __restrict__ idx,
-                                  const double* __restrict__ xmax, int tf32, double* __restrict__ exact_val,
+                                  const double* __restrict__ xmax, int tf32, const double* __restrict__ tmax,
+                                  double* __restrict__ exact_val,
                                   int* __restrict__ flag) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= S * kp) return;
@@ -489,6 +718,9 @@ __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const 
         // each assumed to err by <= 4 * 2^-24 of the segment's sum of |terms| (the tests compare against the fp64 GEMM
         // path on ties 1e-13 ... 1e-4 apart); the |terms| of a feature sum to <= |theta_f|.  x1.5 margin.
         if (tf32) B += 1.5 * scale * sa * (2.5 * 9.5367431640625e-07 + 4.0 * 5.9604644775390625e-08 * 3.0 * (PT_FLUSH / 8));
+        // fp16 operands (mode 2; same 11-bit significand as TF32, theta normalised by tmax): subnormal rounding adds an
+        // absolute 2^-25 per operand, i.e. <= 2 * 2^-25 per term over 2F terms, in units of scale * tmax
+        if (tf32 == 2) B += 1.5 * scale * tmax[j] * 4.0 * (double)F * 2.98023223876953125e-08;
         const double vk = approx_val[j * kp + (k - 1)], vl = approx_val[j * kp + (kp - 1)];
         const bool full = idx[j * kp + (kp - 1)] >= 0;   // fewer than kp candidates in total: nothing was cut
         const bool enough = idx[j * kp + (k - 1)] >= 0;  // NaN values are never selected: let the general kernel decide
@@ -523,7 +755,7 @@ __global__ void prod_xmax_kernel(const double* __restrict__ cand, int64_t nu, in
 struct ProdPlan {
     int64_t nu, G, gx, gy, nlist, nup, nvp, K2p;
     int rec, kp;
-    int64_t off_feat, off_p, off_q, off_pv, off_pi, off_mv, off_mi, off_ev, off_xmax, total;
+    int64_t off_feat, off_p, off_q, off_pv, off_pi, off_mv, off_mi, off_ev, off_xmax, off_tmax, total;
 };
 
 static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k, int tf32 = 0) {
@@ -533,7 +765,7 @@ static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F
     p.kp = k + 8 > PROD_MAX_KP ? PROD_MAX_KP : k + 8;
     p.nup = (p.nu + PT_BM - 1) / PT_BM * PT_BM;
     p.nvp = (nv + PT_BN - 1) / PT_BN * PT_BN;
-    p.K2p = (2 * F + PT_BK - 1) / PT_BK * PT_BK;
+    p.K2p = (2 * F + PH_BK - 1) / PH_BK * PH_BK;
     const int64_t per_sample = tf32 ? (p.nup + p.nvp) * p.K2p * 8 : (p.nu + nv) * 2 * F * 8;
     int64_t G = per_sample > 0 ? (int64_t)(1.5e9 / (double)per_sample) : 1;
     if (G < 1) G = 1;
@@ -558,6 +790,7 @@ static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F
     p.off_mi = take(S * p.kp * 8);
     p.off_ev = take(S * p.kp * 8);
     p.off_xmax = take(64 * 8);
+    p.off_tmax = take(S * 8);
     p.total = o;
     return p;
 }
@@ -600,7 +833,7 @@ using namespace tes;
 extern "C" int64_t tes_rff_topk_product_workspace_bytes(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k,
                                                         int tf32) {
     if (N < 1 || d < 2 || d > 64 || nv < 1 || N % nv != 0 || S < 1 || F < 1 || k < 1 || k > 8) return -1;
-    return prod_plan(N, d, nv, S, F, k, tf32 != 0).total;
+    return prod_plan(N, d, nv, S, F, k, tf32 != 0).total;   // tf32 / fp16 operand arrays: (hi, lo) x 4 resp. 2 bytes
 }
 
 extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d, int64_t s_lo, int64_t s_hi, int64_t nv,
@@ -622,8 +855,8 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     if (!out_idx) return -15;
     if (!out_val) return -16;
     if (!out_flag) return -17;
-    tf32 = tf32 != 0;
-    ProdPlan pl = prod_plan(N, d, nv, S, F, k, tf32);
+    if (tf32 < 0 || tf32 > 2) return -18;
+    ProdPlan pl = prod_plan(N, d, nv, S, F, k, tf32 != 0);
     if (!ws || ws_bytes < pl.total) return -100;
     cudaStream_t st = (cudaStream_t)stream;
     char* base = (char*)ws;
@@ -636,6 +869,7 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     int64_t* mi = (int64_t*)(base + pl.off_mi);
     double* ev = (double*)(base + pl.off_ev);
     double* xmax = (double*)(base + pl.off_xmax);
+    double* tmax = (double*)(base + pl.off_tmax);
     const double scale = sqrt(2.0 * sigma / (double)F);
     const int64_t nu = pl.nu, K2 = 2 * F;
     prod_pack_kernel<<<(unsigned)((S * F + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, (int)d, w_shared, pl.rec, feat);
@@ -649,17 +883,36 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     float* Plo = Phi + pl.G * pl.nup * pl.K2p;
     float* Qhi = (float*)Qt;
     float* Qlo = Qhi + pl.G * pl.K2p * pl.nvp;
+    __half* Hhi = (__half*)P;
+    __half* Hlo = Hhi + pl.G * pl.nup * pl.K2p;
+    __half* Ghi = (__half*)Qt;
+    __half* Glo = Ghi + pl.G * pl.nvp * pl.K2p;
     if (tf32) {
         TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(PtSmem)));
+        TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(PhSmem)));
         // zero the tile padding once (rows >= nu, columns >= nv, k >= 2F are never written by the build kernels)
         TES_CUDA_OK(cudaMemsetAsync(P, 0, (size_t)(pl.G * pl.nup * pl.K2p * 8), st));
         TES_CUDA_OK(cudaMemsetAsync(Qt, 0, (size_t)(pl.G * pl.K2p * pl.nvp * 8), st));
+        prod_tmax_kernel<<<(unsigned)S, 256, 0, st>>>(theta, F, tmax);
+        TES_LAUNCH_OK();
     }
     for (int64_t j0 = 0; j0 < S; j0 += pl.G) {
         const int64_t G = (S - j0 < pl.G) ? (S - j0) : pl.G;
         dim3 grid((unsigned)pl.gx, (unsigned)pl.gy, (unsigned)G);
-        if (tf32) {
+        if (tf32 == 2) {
+            const int64_t totp = G * nu * F, totq = G * nv * F;
+            prod_build_f16_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(
+                cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, G, F, w_shared, pl.nup, pl.K2p, tmax, Hhi, Hlo);
+            TES_LAUNCH_OK();
+            prod_build_f16_kernel<<<(unsigned)((totq + 255) / 256), 256, 0, st>>>(
+                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, G, F, w_shared, pl.nvp, pl.K2p, tmax, Ghi, Glo);
+            TES_LAUNCH_OK();
+            prod_gemm_topk_f16_kernel<<<grid, PT_THREADS, sizeof(PhSmem), st>>>(
+                Hhi, Hlo, Ghi, Glo, nu, nv, pl.nup, pl.nvp, pl.K2p, scale, tmax + j0, idx_offset, pl.kp, G, pv, pi);
+            TES_LAUNCH_OK();
+        } else if (tf32) {
             const int64_t totp = G * nu * F, totq = G * F * nv;
             prod_build_p32_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(
                 cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, W, b, theta, j0, G, F, w_shared, pl.nup, pl.K2p, Phi, Plo);
@@ -693,7 +946,7 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     {
         const int64_t tot = S * pl.kp;
         prod_exact_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(cand, (int)d, feat, pl.rec, S, F, scale,
-                                                                       idx_offset, k, pl.kp, mv, mi, xmax, tf32, ev, out_flag);
+                                                                       idx_offset, k, pl.kp, mv, mi, xmax, tf32, tmax, ev, out_flag);
         TES_LAUNCH_OK();
     }
     prod_final_kernel<<<(unsigned)S, 32, 0, st>>>(ev, mi, pl.kp, k, out_val, out_idx);

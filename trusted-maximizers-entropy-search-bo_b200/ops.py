@@ -54,13 +54,13 @@ def detect_product_structure(cand):
     return None if best is None else best[:3]
 
 
-def rff_topk_product(cand, W, b, theta, sigma, s_lo, s_hi, nv, k=1, idx_offset=0, tf32=True):
+def rff_topk_product(cand, W, b, theta, sigma, s_lo, s_hi, nv, k=1, idx_offset=0, tf32=2):
     """tes_rff_topk_product_f64 -> (idx (S,k), val (S,k), flag (S,) int32).  flag[j] = 1: recompute sample j with the
-    general kernel (rff_topk does that).  tf32: the GEMM as a 3xTF32 tensor-core screen (default) or in fp64 (DMMA);
-    identical results either way."""
+    general kernel (rff_topk does that).  tf32: 2 = 3xFP16 tensor-core screen (default), 1 = 3xTF32, 0 / False = fp64
+    (DMMA); identical results in every mode."""
     cand, W, b, theta, N, d, S, F, ws_ = _rff_args(cand, W, b, theta)
     L = _lib.lib()
-    need = L.tes_rff_topk_product_workspace_bytes(N, d, int(nv), S, F, int(k), int(bool(tf32)))
+    need = L.tes_rff_topk_product_workspace_bytes(N, d, int(nv), S, F, int(k), int(tf32))
     if need < 0:
         raise ValueError("invalid sizes for tes_rff_topk_product_f64: N=%d d=%d nv=%d S=%d F=%d k=%d" % (N, d, nv, S, F, k))
     ws = WORKSPACE.get(need, cand.device)
@@ -69,7 +69,7 @@ def rff_topk_product(cand, W, b, theta, sigma, s_lo, s_hi, nv, k=1, idx_offset=0
     flag = torch.empty((S,), dtype=torch.int32, device=cand.device)
     rc = L.tes_rff_topk_product_f64(ptr(cand), N, d, int(s_lo), int(s_hi), int(nv), ptr(W), ptr(b), ptr(theta), S, F, ws_,
                                     float(sigma), int(k), int(idx_offset), ptr(out_idx), ptr(out_val), ptr(flag),
-                                    int(bool(tf32)), ptr(ws), ws.numel(), stream_ptr())
+                                    int(tf32), ptr(ws), ws.numel(), stream_ptr())
     _lib.check(rc, "tes_rff_topk_product_f64")
     return out_idx, out_val, flag
 
