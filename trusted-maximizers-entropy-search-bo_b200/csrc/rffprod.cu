@@ -332,11 +332,15 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    mma_tf32(acc[i][j], al[fb][i], bh[fb][j]);   // small terms first
-                    mma_tf32(acc[i][j], ah[fb][i], bl[fb][j]);
-                    mma_tf32(acc[i][j], ah[fb][i], bh[fb][j]);
-                }
+                for (int j = 0; j < 4; ++j) mma_tf32(acc[i][j], al[fb][i], bh[fb][j]);   // small terms first
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_tf32(acc[i][j], ah[fb][i], bl[fb][j]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_tf32(acc[i][j], ah[fb][i], bh[fb][j]);
         }
         if (((kt + 1) * PT_BK) % PT_FLUSH == 0) flush();
     }
@@ -407,41 +411,58 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
 
 // Phi/Plo[g][iu][2f..2f+1] halves (row stride K2p); which = 0: the U side (theta cos a, -theta sin a),
 // which = 1: the V side (cos b, sin b) written to Qhi/Qlo[g][iv][2f..2f+1]
+constexpr int PB_ROWS = 8;           // rows per thread of the operand build (the feature's w is loaded once for them)
 __global__ void prod_build_f16_kernel(const double* __restrict__ cand, int64_t nrow, int64_t row_stride, int d, int s_lo,
                                       int s_hi, int which, const double* __restrict__ W, const double* __restrict__ b,
                                       const double* __restrict__ theta, int64_t j0, int64_t G, int64_t F, int w_shared,
                                       int64_t nrowp, int64_t K2p, const double* __restrict__ tmax,
                                       __half* __restrict__ Hi, __half* __restrict__ Lo) {
+    const int64_t nrb = (nrow + PB_ROWS - 1) / PB_ROWS;
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= G * nrow * F) return;
-    const int64_t f = t % F, ir = (t / F) % nrow, g = t / (F * nrow);
+    if (t >= G * nrb * F) return;
+    const int64_t f = t % F, rb = (t / F) % nrb, g = t / (F * nrb);
     const int64_t j = j0 + g, jw = w_shared ? 0 : j;
     const double* w = W + (jw * F + f) * d;
-    const double* x = cand + (ir * row_stride) * d;
-    double a;
+    double wk[16];
+    int nk_ = 0;
     if (which == 0) {
-        a = b[jw * F + f];
-        for (int k = s_lo; k < s_hi; ++k) a = fma(w[k], x[k], a);
+        for (int k = s_lo; k < s_hi; ++k) wk[nk_++] = w[k];
     } else {
-        a = 0.0;
-        for (int k = 0; k < s_lo; ++k) a = fma(w[k], x[k], a);
-        for (int k = s_hi; k < d; ++k) a = fma(w[k], x[k], a);
+        for (int k = 0; k < s_lo; ++k) wk[nk_++] = w[k];
+        for (int k = s_hi; k < d; ++k) wk[nk_++] = w[k];
     }
-    float sn, cs;
-    sincosf((float)(a - 6.283185307179586 * rint(a * 0.15915494309189535)), &sn, &cs);
-    float p0 = cs, p1 = sn;
+    const double a0 = which == 0 ? b[jw * F + f] : 0.0;
+    double th = 1.0;
     if (which == 0) {
         const double tm = tmax[j];                       // fp16 has a 5-bit exponent: theta is normalised per sample
-        const double th = tm > 0.0 ? theta[j * F + f] / tm : 0.0;
-        p0 = (float)(th * (double)cs);
-        p1 = (float)(-th * (double)sn);
+        th = tm > 0.0 ? theta[j * F + f] / tm : 0.0;
     }
-    __half h0, l0, h1, l1;
-    split_f16(p0, h0, l0);
-    split_f16(p1, h1, l1);
-    const int64_t o = (g * nrowp + ir) * K2p + 2 * f;
-    *reinterpret_cast<__half2*>(Hi + o) = __halves2half2(h0, h1);
-    *reinterpret_cast<__half2*>(Lo + o) = __halves2half2(l0, l1);
+    for (int r = 0; r < PB_ROWS; ++r) {
+        const int64_t ir = rb * PB_ROWS + r;
+        if (ir >= nrow) break;
+        const double* x = cand + (ir * row_stride) * d;
+        double a = a0;
+        int q = 0;
+        if (which == 0) {
+            for (int k = s_lo; k < s_hi; ++k) a = fma(wk[q++], x[k], a);
+        } else {
+            for (int k = 0; k < s_lo; ++k) a = fma(wk[q++], x[k], a);
+            for (int k = s_hi; k < d; ++k) a = fma(wk[q++], x[k], a);
+        }
+        float sn, cs;
+        sincosf((float)(a - 6.283185307179586 * rint(a * 0.15915494309189535)), &sn, &cs);
+        float p0 = cs, p1 = sn;
+        if (which == 0) {
+            p0 = (float)(th * (double)cs);
+            p1 = (float)(-th * (double)sn);
+        }
+        __half h0, l0, h1, l1;
+        split_f16(p0, h0, l0);
+        split_f16(p1, h1, l1);
+        const int64_t o = (g * nrowp + ir) * K2p + 2 * f;
+        *reinterpret_cast<__half2*>(Hi + o) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2*>(Lo + o) = __halves2half2(l0, l1);
+    }
 }
 
 __global__ void __launch_bounds__(PT_THREADS, 1)
@@ -541,14 +562,20 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
         for (int s16 = 0; s16 < PH_BK / 16; ++s16) {
             const int fb = s16 & 1;
             if (s16 + 1 < PH_BK / 16) frag(fb ^ 1, (s16 + 1) * 16);
+            // term by term over the 8 accumulator tiles: consecutive mma never depend on each other (three back-to-back
+            // mma on one accumulator serialise on its latency: ncu `wait` 3.0 per issue, tensor pipe 35 % busy)
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    mma_f16(acc[i][j], al[fb][i], bh[fb][j]);
-                    mma_f16(acc[i][j], ah[fb][i], bl[fb][j]);
-                    mma_f16(acc[i][j], ah[fb][i], bh[fb][j]);
-                }
+                for (int j = 0; j < 4; ++j) mma_f16(acc[i][j], al[fb][i], bh[fb][j]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_f16(acc[i][j], ah[fb][i], bl[fb][j]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_f16(acc[i][j], ah[fb][i], bh[fb][j]);
         }
         if (((kt + 1) * PH_BK) % PT_FLUSH == 0) flush();
     }
@@ -856,6 +883,7 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     if (!out_val) return -16;
     if (!out_flag) return -17;
     if (tf32 < 0 || tf32 > 2) return -18;
+    if (tf32 == 2 && d > 16) tf32 = 1;   // the fp16 operand build keeps a feature's weights in 16 registers
     ProdPlan pl = prod_plan(N, d, nv, S, F, k, tf32 != 0);
     if (!ws || ws_bytes < pl.total) return -100;
     cudaStream_t st = (cudaStream_t)stream;
@@ -902,7 +930,7 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
         const int64_t G = (S - j0 < pl.G) ? (S - j0) : pl.G;
         dim3 grid((unsigned)pl.gx, (unsigned)pl.gy, (unsigned)G);
         if (tf32 == 2) {
-            const int64_t totp = G * nu * F, totq = G * nv * F;
+            const int64_t totp = G * ((nu + PB_ROWS - 1) / PB_ROWS) * F, totq = G * ((nv + PB_ROWS - 1) / PB_ROWS) * F;
             prod_build_f16_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(
                 cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, G, F, w_shared, pl.nup, pl.K2p, tmax, Hhi, Hlo);
             TES_LAUNCH_OK();
