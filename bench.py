@@ -376,7 +376,8 @@ def main():
     product = ops.detect_product_structure(devt["cand"]) if wl["N"] >= ops.PRODUCT_MIN_N else None
     if product:
         # stage A on a product-structured candidate set = one GEMM per function sample (csrc/rffprod.cu), run as a
-        # 3xFP16 screen on the tensor cores (mma.sync m16n8k16, hi/lo fp16 operands, fp32 segments flushed to fp64)
+        # 3xFP16 screen on the tensor cores (tcgen05.mma kind::f16 + TMEM, hi/lo fp16 operands, fp32 segments of 256 k
+        # drained from TMEM into fp64 sums)
         # followed by the exact fp64 re-evaluation of the k + 8 best candidates per sample.
         # algorithmic: 2 * N * 2F flops per sample (the fp64 GEMM); executed: 3x that in fp16
         peaks = {}
@@ -388,11 +389,12 @@ def main():
         tf32_peak = bf16                # fp16 dense tensor rate = the bf16 rate
         gflops = 2.0 * local_pairs * 2 * F
         achieved = 3.0 * gflops / t_rff * 1e-12
-        roofline = {"bound": "tensor", "pipe": "fp16 tensor cores through legacy mma.sync m16n8k16 (no tcgen05/TMEM yet)",
-                    "kernel": "prod_gemm_topk_f16_kernel (+ operand build, list merge, exact fp64 refine)",
+        roofline = {"bound": "tensor", "pipe": "5th-gen tensor cores: tcgen05.mma kind::f16 (M128 N128 K16), accumulators in TMEM, operands by "
+                            "1-D bulk async copies (TMA engine) in a 3-stage mbarrier ring",
+                    "kernel": "prod_gemm_topk_tc_kernel (+ operand build, list merge, exact fp64 refine)",
                     "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
                     "traffic": None,
-                    "peak_source": "bf16_tflops_sustained of MEASURED_PEAKS.json (cuBLAS/tcgen05 rate, %s); legacy mma.sync tops out far below it" % (
+                    "peak_source": "bf16_tflops_sustained of MEASURED_PEAKS.json (cuBLAS, %s)" % (
                         "measured" if peaks else "fallback 1400"),
                     "algorithmic_fp64_gemm_tflops": gflops / t_rff * 1e-12,
                     "fp64_fma_peak_tflops": fp64_peak, "mufu_peak_tcos": mufu_peak,

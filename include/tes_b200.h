@@ -80,7 +80,8 @@ int tes_rff_topk_method_f64(const double* cand, int64_t N, int64_t d, const doub
  * then recomputes with tes_rff_topk_f64 (the Python binding does).  k <= 8.  The structure itself is NOT checked here.
  * tf32 = 1 / 2: the GEMM runs as a 3xTF32 / 3xFP16 screen on mma.sync tensor cores (operands split into hi + lo pairs
  * of 11 significant bits, fp32 accumulation flushed into fp64 every 256 k, a correspondingly wider safety margin; fp16:
- * theta normalised per sample); 0: fp64 (DMMA).  The result is the same in every mode. */
+ * theta normalised per sample); 3: the 3xFP16 GEMM on tcgen05.mma kind::f16 + TMEM with bulk-async-copy operand
+ * staging; 0: fp64 (DMMA).  The result is the same in every mode. */
 int64_t tes_rff_topk_product_workspace_bytes(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k, int tf32);
 int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d, int64_t s_lo, int64_t s_hi, int64_t nv,
                              const double* W, const double* b, const double* theta, int64_t S, int64_t F, int w_shared, double sigma,

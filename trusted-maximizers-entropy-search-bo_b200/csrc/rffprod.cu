@@ -622,6 +622,273 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
     }
 }
 
+// ---- the same 3xFP16 GEMM on the 5th-generation tensor cores: tcgen05.mma kind::f16 + TMEM + bulk async copies ------
+// Operands are laid out by the build kernel in the shared-memory order of the MMA (K-major, no swizzle: core matrix =
+// 8 rows x 16 bytes): per (sample, 128-row tile, stage of 64 k) one contiguous 32 KB block
+//     [hi | lo][8 chunks of 8 halves][128 rows][8 halves]
+// so a stage is filled by two 1-D bulk copies (A block, B block) completing on an mbarrier.
+//   warp 0 (one lane): producer -- 3-stage ring, 64 KB per stage;
+//   warp 1 (one lane): issues 12 tcgen05.mma (M 128 x N 128 x K 16: 4 k16 steps x {lo*hi, hi*lo, hi*hi}) per stage into
+//                      one of two 128-column TMEM accumulators; a SEGMENT = 4 stages = 256 k; tcgen05.commit releases
+//                      the stage to the producer and, at the end of a segment, hands the accumulator to the epilogue;
+//   warps 2..17      : epilogue -- thread = one row (TMEM lane), 32 columns: tcgen05.ld, fp32 -> fp64 running sums
+//                      (the segment flush that bounds the fp32 accumulation error), then the per-warp top-kp.
+constexpr int TC_EPI_WARPS = 16, TC_THREADS = 64 + 32 * TC_EPI_WARPS, TC_NS = 3, TC_BK = 64, TC_SEG = 4;
+constexpr uint32_t TC_BLOCK_BYTES = 2 * 8 * 128 * 16;          // one operand block of a stage (hi + lo) = 32 KB
+constexpr uint32_t TC_STAGE_BYTES = 2 * TC_BLOCK_BYTES;        // A block + B block
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major, no swizzle: LBO = bytes between core matrices adjacent in K, SBO = between core matrices adjacent in M/N
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// D = f32 (bit 4), A = B = f16 (0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t tc_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+#define TC_LD32(v, taddr)                                                                                             \
+    asm volatile(                                                                                                     \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"  \
+        "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),             \
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),       \
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),     \
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])      \
+        : "r"(taddr))
+
+// operand build in MMA order: block index ((g * ntile + tile) * nst + st), inside [hl][chunk][row][8]
+__global__ void prod_build_tc_kernel(const double* __restrict__ cand, int64_t nrow, int64_t row_stride, int d, int s_lo,
+                                     int s_hi, int which, const double* __restrict__ W, const double* __restrict__ b,
+                                     const double* __restrict__ theta, int64_t j0, int64_t G, int64_t F, int w_shared,
+                                     int64_t ntile, int64_t nst, const double* __restrict__ tmax,
+                                     __half* __restrict__ out) {
+    const int64_t nrb = (nrow + PB_ROWS - 1) / PB_ROWS;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * nrb * F) return;
+    const int64_t f = t % F, rb = (t / F) % nrb, g = t / (F * nrb);
+    const int64_t j = j0 + g, jw = w_shared ? 0 : j;
+    const double* w = W + (jw * F + f) * d;
+    double wk[16];
+    int nk_ = 0;
+    if (which == 0) {
+        for (int k = s_lo; k < s_hi; ++k) wk[nk_++] = w[k];
+    } else {
+        for (int k = 0; k < s_lo; ++k) wk[nk_++] = w[k];
+        for (int k = s_hi; k < d; ++k) wk[nk_++] = w[k];
+    }
+    const double a0 = which == 0 ? b[jw * F + f] : 0.0;
+    double th = 1.0;
+    if (which == 0) {
+        const double tm = tmax[j];
+        th = tm > 0.0 ? theta[j * F + f] / tm : 0.0;
+    }
+    const int64_t k2 = 2 * f, st = k2 / TC_BK, chunk = (k2 % TC_BK) / 8, e = k2 % 8;
+    for (int r = 0; r < PB_ROWS; ++r) {
+        const int64_t ir = rb * PB_ROWS + r;
+        if (ir >= nrow) break;
+        const double* x = cand + (ir * row_stride) * d;
+        double a = a0;
+        int q = 0;
+        if (which == 0) {
+            for (int k = s_lo; k < s_hi; ++k) a = fma(wk[q++], x[k], a);
+        } else {
+            for (int k = 0; k < s_lo; ++k) a = fma(wk[q++], x[k], a);
+            for (int k = s_hi; k < d; ++k) a = fma(wk[q++], x[k], a);
+        }
+        float sn, cs;
+        sincosf((float)(a - 6.283185307179586 * rint(a * 0.15915494309189535)), &sn, &cs);
+        float p0 = cs, p1 = sn;
+        if (which == 0) {
+            p0 = (float)(th * (double)cs);
+            p1 = (float)(-th * (double)sn);
+        }
+        __half h0, l0, h1, l1;
+        split_f16(p0, h0, l0);
+        split_f16(p1, h1, l1);
+        const int64_t tile = ir / 128, row = ir % 128;
+        __half* blk = out + ((g * ntile + tile) * nst + st) * (int64_t)(TC_BLOCK_BYTES / 2);
+        const int64_t o = (chunk * 128 + row) * 8 + e;
+        *reinterpret_cast<__half2*>(blk + o) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2*>(blk + 8 * 128 * 8 + o) = __halves2half2(l0, l1);
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    prod_gemm_topk_tc_kernel(const __half* __restrict__ Pt, const __half* __restrict__ Qt, int64_t nu, int64_t nv,
+                             int64_t ntu, int64_t ntv, int64_t nst, double scale0, const double* __restrict__ tmax,
+                             int64_t idx_offset, int kp, int64_t G, double* __restrict__ part_val,
+                             int64_t* __restrict__ part_idx) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    unsigned char* stages = tc_smem_raw;                                            // [TC_NS][A block | B block]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem_raw + TC_NS * TC_STAGE_BYTES);
+    uint64_t* full_b = bars;                 // [TC_NS] producer -> MMA
+    uint64_t* empty_b = bars + TC_NS;        // [TC_NS] MMA (commit) -> producer
+    uint64_t* acc_full = bars + 2 * TC_NS;   // [2] MMA (commit) -> epilogue
+    uint64_t* acc_empty = acc_full + 2;      // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t g = blockIdx.z;
+    const int64_t rt = blockIdx.x, ct = blockIdx.y;
+    const double scale = scale0 * tmax[g];
+    const int64_t nseg = nst / TC_SEG;
+    if (tid == 0) {
+        for (int s = 0; s < TC_NS; ++s) {
+            mbar_init(&full_b[s], 1);
+            mbar_init(&empty_b[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], TC_EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const unsigned char* srcA = reinterpret_cast<const unsigned char*>(Pt) + ((g * ntu + rt) * nst) * (int64_t)TC_BLOCK_BYTES;
+            const unsigned char* srcB = reinterpret_cast<const unsigned char*>(Qt) + ((g * ntv + ct) * nst) * (int64_t)TC_BLOCK_BYTES;
+            for (int64_t st = 0; st < nst; ++st) {
+                const uint32_t s = (uint32_t)(st % TC_NS), ph = (uint32_t)((st / TC_NS) & 1);
+                mbar_wait_relaxed(&empty_b[s], ph ^ 1u, 32);
+                mbar_expect_tx(&full_b[s], TC_STAGE_BYTES);
+                bulk_g2s(stages + s * TC_STAGE_BYTES, srcA + st * (int64_t)TC_BLOCK_BYTES, TC_BLOCK_BYTES, &full_b[s]);
+                bulk_g2s(stages + s * TC_STAGE_BYTES + TC_BLOCK_BYTES, srcB + st * (int64_t)TC_BLOCK_BYTES, TC_BLOCK_BYTES,
+                         &full_b[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc_f16(128, 128);
+            const uint32_t base = smem_u32(stages);
+            for (int64_t seg = 0; seg < nseg; ++seg) {
+                const uint32_t a = (uint32_t)(seg & 1), pa = (uint32_t)((seg >> 1) & 1);
+                mbar_wait_relaxed(&acc_empty[a], pa ^ 1u, 32);
+                tc_fence_after();
+                for (int q4 = 0; q4 < TC_SEG; ++q4) {
+                    const int64_t st = seg * TC_SEG + q4;
+                    const uint32_t s = (uint32_t)(st % TC_NS), ph = (uint32_t)((st / TC_NS) & 1);
+                    mbar_wait_relaxed(&full_b[s], ph, 32);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_BLOCK_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 16; ++ks) {
+                        const uint32_t off = (uint32_t)(2 * ks) * 128u * 16u;      // 2 chunks of 8 halves per k16 step
+                        const uint64_t a_hi = tc_desc(sa + off, 128 * 16, 128);
+                        const uint64_t a_lo = tc_desc(sa + TC_BLOCK_BYTES / 2 + off, 128 * 16, 128);
+                        const uint64_t b_hi = tc_desc(sb + off, 128 * 16, 128);
+                        const uint64_t b_lo = tc_desc(sb + TC_BLOCK_BYTES / 2 + off, 128 * 16, 128);
+                        const uint32_t first = (q4 == 0 && ks == 0) ? 0u : 1u;
+                        tc_mma_f16(tmem + a * 128u, a_lo, b_hi, idesc, first);
+                        tc_mma_f16(tmem + a * 128u, a_hi, b_lo, idesc, 1u);
+                        tc_mma_f16(tmem + a * 128u, a_hi, b_hi, idesc, 1u);
+                    }
+                    tc_commit(&empty_b[s]);            // the stage is free once these MMAs have read it
+                }
+                tc_commit(&acc_full[a]);               // the segment's accumulator is complete
+            }
+        }
+        __syncwarp();
+    } else {
+        const int ew = warp - 2;                       // 0..15
+        const int quarter = warp & 3;                  // TMEM lanes this warp may access
+        const int cb = ew >> 2;                        // columns [32 cb, 32 cb + 32)
+        const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32);
+        double sum[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) sum[c] = 0.0;
+        for (int64_t seg = 0; seg < nseg; ++seg) {
+            const uint32_t a = (uint32_t)(seg & 1), pa = (uint32_t)((seg >> 1) & 1);
+            mbar_wait(&acc_full[a], pa);
+            tc_fence_after();
+            uint32_t v0[32];
+            TC_LD32(v0, t_lane + a * 128u);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_arrive(&acc_empty[a]);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) sum[c] += (double)__uint_as_float(v0[c]);
+        }
+        // per-warp top-kp of its 32 rows x 32 columns: every lane caches the best of its not yet consumed values
+        const int64_t row = rt * 128 + quarter * 32 + lane;
+        const int64_t colb = ct * 128 + cb * 32;
+        const int64_t list = ((int64_t)rt * gridDim.y + ct) * TC_EPI_WARPS + ew;
+        double* ov = part_val + (list * G + g) * kp;
+        int64_t* oi = part_idx + (list * G + g) * kp;
+        uint32_t used = 0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            sum[c] = __dmul_rn(scale, sum[c]);
+            if (!(row < nu && colb + c < nv)) used |= 1u << c;
+        }
+        const int64_t ci0 = row * nv + colb + idx_offset;
+        for (int r = 0; r < kp; ++r) {
+            double bv = neg_inf();
+            int bc = -1;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)           // ascending c = ascending index: strict > keeps the lowest index
+                if (!((used >> c) & 1u) && (bc < 0 || sum[c] > bv)) {
+                    bv = sum[c];
+                    bc = c;
+                }
+            double wv = bv;
+            int64_t wi = bc >= 0 ? ci0 + bc : INT64_MAX;
+            if (bc < 0) wv = neg_inf();
+            warp_argmax(wv, wi);
+            const bool found = (wi != INT64_MAX);
+            if (lane == 0) {
+                ov[r] = found ? wv : neg_inf();
+                oi[r] = found ? wi : -1;
+            }
+            if (!found) {
+                for (int q = r + 1; q < kp; ++q)
+                    if (lane == 0) {
+                        ov[q] = neg_inf();
+                        oi[q] = -1;
+                    }
+                break;
+            }
+            if (bc >= 0 && wi == ci0 + bc) used |= 1u << bc;   // the winning lane consumes its element
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+    }
+}
+
 // tmax[j] = max_f |theta[j][f]| (one block per sample)
 __global__ void prod_tmax_kernel(const double* __restrict__ theta, int64_t F, double* __restrict__ tmax) {
     __shared__ double red[256];
@@ -747,7 +1014,7 @@ __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const 
         if (tf32) B += 1.5 * scale * sa * (2.5 * 9.5367431640625e-07 + 4.0 * 5.9604644775390625e-08 * 3.0 * (PT_FLUSH / 8));
         // fp16 operands (mode 2; same 11-bit significand as TF32, theta normalised by tmax): subnormal rounding adds an
         // absolute 2^-25 per operand, i.e. <= 2 * 2^-25 per term over 2F terms, in units of scale * tmax
-        if (tf32 == 2) B += 1.5 * scale * tmax[j] * 4.0 * (double)F * 2.98023223876953125e-08;
+        if (tf32 >= 2) B += 1.5 * scale * tmax[j] * 4.0 * (double)F * 2.98023223876953125e-08;
         const double vk = approx_val[j * kp + (k - 1)], vl = approx_val[j * kp + (kp - 1)];
         const bool full = idx[j * kp + (kp - 1)] >= 0;   // fewer than kp candidates in total: nothing was cut
         const bool enough = idx[j * kp + (k - 1)] >= 0;  // NaN values are never selected: let the general kernel decide
@@ -785,14 +1052,15 @@ struct ProdPlan {
     int64_t off_feat, off_p, off_q, off_pv, off_pi, off_mv, off_mi, off_ev, off_xmax, off_tmax, total;
 };
 
-static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k, int tf32 = 0) {
+static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k, int tf32 = 0, int tc = 0) {
     ProdPlan p;
     p.nu = N / nv;
     p.rec = prod_rec((int)d);
     p.kp = k + 8 > PROD_MAX_KP ? PROD_MAX_KP : k + 8;
     p.nup = (p.nu + PT_BM - 1) / PT_BM * PT_BM;
     p.nvp = (nv + PT_BN - 1) / PT_BN * PT_BN;
-    p.K2p = (2 * F + PH_BK - 1) / PH_BK * PH_BK;
+    p.K2p = tc ? (2 * F + 255) / 256 * 256 : (2 * F + PH_BK - 1) / PH_BK * PH_BK;
+    if (tc) p.nvp = (nv + 127) / 128 * 128;
     const int64_t per_sample = tf32 ? (p.nup + p.nvp) * p.K2p * 8 : (p.nu + nv) * 2 * F * 8;
     int64_t G = per_sample > 0 ? (int64_t)(1.5e9 / (double)per_sample) : 1;
     if (G < 1) G = 1;
@@ -801,7 +1069,8 @@ static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F
     p.G = G;
     p.gx = (p.nu + GEMM_BM - 1) / GEMM_BM;
     p.gy = (nv + GEMM_BN - 1) / GEMM_BN;
-    p.nlist = p.gx * p.gy * 8;
+    if (tc) p.gy = (nv + 127) / 128;
+    p.nlist = p.gx * p.gy * (tc ? TC_EPI_WARPS : 8);
     int64_t o = 0;
     auto take = [&](int64_t bytes) {
         int64_t r = o;
@@ -860,7 +1129,7 @@ using namespace tes;
 extern "C" int64_t tes_rff_topk_product_workspace_bytes(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k,
                                                         int tf32) {
     if (N < 1 || d < 2 || d > 64 || nv < 1 || N % nv != 0 || S < 1 || F < 1 || k < 1 || k > 8) return -1;
-    return prod_plan(N, d, nv, S, F, k, tf32 != 0).total;   // tf32 / fp16 operand arrays: (hi, lo) x 4 resp. 2 bytes
+    return prod_plan(N, d, nv, S, F, k, tf32 != 0, tf32 == 3).total;   // tf32 / fp16 operand arrays: (hi, lo) x 4 resp. 2 bytes
 }
 
 extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d, int64_t s_lo, int64_t s_hi, int64_t nv,
@@ -882,9 +1151,9 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     if (!out_idx) return -15;
     if (!out_val) return -16;
     if (!out_flag) return -17;
-    if (tf32 < 0 || tf32 > 2) return -18;
-    if (tf32 == 2 && d > 16) tf32 = 1;   // the fp16 operand build keeps a feature's weights in 16 registers
-    ProdPlan pl = prod_plan(N, d, nv, S, F, k, tf32 != 0);
+    if (tf32 < 0 || tf32 > 3) return -18;
+    if (tf32 >= 2 && d > 16) tf32 = 1;   // the fp16 operand build keeps a feature's weights in 16 registers
+    ProdPlan pl = prod_plan(N, d, nv, S, F, k, tf32 != 0, tf32 == 3);
     if (!ws || ws_bytes < pl.total) return -100;
     cudaStream_t st = (cudaStream_t)stream;
     char* base = (char*)ws;
@@ -920,6 +1189,8 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
                                          (int)sizeof(PtSmem)));
         TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(PhSmem)));
+        TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(TC_NS * TC_STAGE_BYTES + 256)));
         // zero the tile padding once (rows >= nu, columns >= nv, k >= 2F are never written by the build kernels)
         TES_CUDA_OK(cudaMemsetAsync(P, 0, (size_t)(pl.G * pl.nup * pl.K2p * 8), st));
         TES_CUDA_OK(cudaMemsetAsync(Qt, 0, (size_t)(pl.G * pl.K2p * pl.nvp * 8), st));
@@ -929,7 +1200,20 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     for (int64_t j0 = 0; j0 < S; j0 += pl.G) {
         const int64_t G = (S - j0 < pl.G) ? (S - j0) : pl.G;
         dim3 grid((unsigned)pl.gx, (unsigned)pl.gy, (unsigned)G);
-        if (tf32 == 2) {
+        if (tf32 == 3) {
+            const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK;
+            const int64_t totp = G * ((nu + PB_ROWS - 1) / PB_ROWS) * F, totq = G * ((nv + PB_ROWS - 1) / PB_ROWS) * F;
+            prod_build_tc_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(
+                cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, G, F, w_shared, ntu, nst, tmax, Hhi);
+            TES_LAUNCH_OK();
+            prod_build_tc_kernel<<<(unsigned)((totq + 255) / 256), 256, 0, st>>>(
+                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, G, F, w_shared, ntv, nst, tmax, Ghi);
+            TES_LAUNCH_OK();
+            dim3 gtc((unsigned)ntu, (unsigned)ntv, (unsigned)G);
+            prod_gemm_topk_tc_kernel<<<gtc, TC_THREADS, TC_NS * TC_STAGE_BYTES + 256, st>>>(
+                Hhi, Ghi, nu, nv, ntu, ntv, nst, scale, tmax + j0, idx_offset, pl.kp, G, pv, pi);
+            TES_LAUNCH_OK();
+        } else if (tf32 == 2) {
             const int64_t totp = G * ((nu + PB_ROWS - 1) / PB_ROWS) * F, totq = G * ((nv + PB_ROWS - 1) / PB_ROWS) * F;
             prod_build_f16_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(
                 cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, G, F, w_shared, pl.nup, pl.K2p, tmax, Hhi, Hlo);

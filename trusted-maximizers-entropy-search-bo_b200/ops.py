@@ -25,6 +25,7 @@ RFF_AUTO, RFF_FP64, RFF_SCREEN, RFF_SCREEN_MMA, RFF_SCREEN_TC5, RFF_SCREEN_TC5T 
 
 RFF_PRODUCT = 6          # product-structured candidate sets: one fp64 tensor-pipe GEMM per sample (csrc/rffprod.cu)
 PRODUCT_MIN_N = 1 << 15  # below this the general kernels are launch-bound anyway
+PRODUCT_MODE = int(__import__("os").environ.get("TES_PRODUCT_MODE", "3"))   # GEMM engine of the product path
 
 
 def detect_product_structure(cand):
@@ -54,10 +55,12 @@ def detect_product_structure(cand):
     return None if best is None else best[:3]
 
 
-def rff_topk_product(cand, W, b, theta, sigma, s_lo, s_hi, nv, k=1, idx_offset=0, tf32=2):
+def rff_topk_product(cand, W, b, theta, sigma, s_lo, s_hi, nv, k=1, idx_offset=0, tf32=None):
     """tes_rff_topk_product_f64 -> (idx (S,k), val (S,k), flag (S,) int32).  flag[j] = 1: recompute sample j with the
     general kernel (rff_topk does that).  tf32: 2 = 3xFP16 tensor-core screen (default), 1 = 3xTF32, 0 / False = fp64
-    (DMMA); identical results in every mode."""
+    (DMMA), 3 = 3xFP16 on tcgen05/TMEM; identical results in every mode.  None: PRODUCT_MODE (env TES_PRODUCT_MODE)."""
+    if tf32 is None:
+        tf32 = PRODUCT_MODE
     cand, W, b, theta, N, d, S, F, ws_ = _rff_args(cand, W, b, theta)
     L = _lib.lib()
     need = L.tes_rff_topk_product_workspace_bytes(N, d, int(nv), S, F, int(k), int(tf32))
