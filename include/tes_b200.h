@@ -177,6 +177,18 @@ int tes_ep_acq_f64(int mode, const double* x, int64_t N, int64_t d, const double
                    uint64_t seed, int64_t n_global, int64_t x_offset, double* out_acq, double* out_mean,
                    double* out_var, void* ws, int64_t ws_bytes, void* stream);
 
+/* Tensor-core SCREEN of the deterministic TES_ep criterion (criteria/evaluate_mp.py:199-219): out_acq (N) = the criterion
+ * with the query variances' quadratic forms (evaluate_mp.py:103-107) computed as a 3xFP16 tcgen05 GEMM, out_eps (N) = a
+ * proven bound on |out_acq - exact| (infinite where the variance could be non-positive or is NaN).  A caller that only
+ * needs the arg-max keeps {x : acq~ + eps >= max(acq~ - eps)} and evaluates those with tes_ep_acq_f64: same arg-max,
+ * same value (tes_b200.acquisition.tes_step does).  Sp <= 128. */
+int64_t tes_ep_acq_screen_workspace_bytes(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp);
+int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, const double* test_xs, int64_t T, const double* X,
+                          int64_t n, const double* Y, const double* l, double sigma, double sigma0,
+                          const double* invpNK, const double* invKobs, const double* p, int64_t Sp,
+                          const double* post_cov, double* out_acq, double* out_eps, void* ws, int64_t ws_bytes,
+                          void* stream);
+
 /* TES_sp acquisition, q = 1 (criteria/evaluate_sample_mp.py:132-336) or batch q <= 8
  * (criteria/evaluate_batch_sample_mp.py:160-382).  x (nx, q, d); post_samples (Sp,T,K);
  * post_mask (Sp,K) bytes (1 = valid); z layout (niter, nysample, Sp, nx, K, q) or NULL for Philox

@@ -246,3 +246,44 @@ def test_tes_sp_whitened_kernel_far_components_and_nan():
     acq = ops.sp_acq(pr["x"], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invpNK"][0],
                      p[keep], P, msk, niter=2, nysample=3, z=z[0]).cpu().numpy()
     assert np.all(np.isnan(acq))
+
+
+@pytest.mark.parametrize("hyp,d,n,T,nx,mode", [(HART6, 6, 30, 20, 40_001, "empirical"), (BRANIN, 2, 6, 9, 19_000, "empirical"),
+                                               (PH, 2, 20, 7, 400, "ep"), (HART6, 6, 40, 70, 20_000, "empirical")])
+def test_tes_ep_screen_bound_holds(hyp, d, n, T, nx, mode):
+    """ops.ep_acq_screen: the 3xFP16 tcgen05 screen of the deterministic criterion stays within its own proven bound of
+    the fp64 criterion on every candidate, and the bound is small enough to prune."""
+    from tes_b200 import ops
+    pr = make_problem(seed=11 + T, d=d, n=n, T=T, nx=nx, hyp=hyp, mode=mode, nsample=max(600, 40 * T))
+    p, pm, pc = _ep_inputs(pr)
+    exact = ops.ep_acq(ops.EP_DETERMINISTIC, pr["x"], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"],
+                       pr["invpNK"][0], pr["invK"][0], p, pm, pc).cpu().numpy()
+    acq, eps = ops.ep_acq_screen(pr["x"], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"],
+                                 pr["invpNK"][0], pr["invK"][0], p, pc)
+    acq, eps = acq.cpu().numpy(), eps.cpu().numpy()
+    fin = np.isfinite(eps) & np.isfinite(exact)
+    assert fin.mean() > 0.99
+    err = np.abs(acq - exact)[fin]
+    assert np.all(err <= eps[fin]), (err.max(), eps[fin][np.argmax(err - eps[fin])])
+    assert np.median(eps[fin]) < 1e-3 * max(1.0, np.abs(exact[fin]).max())
+    # the screen is useful: the bound is far above the actual error but far below the spread of the criterion
+    assert err.max() < 1e-4 * max(1.0, np.abs(exact[fin]).max())
+
+
+def test_tes_step_with_screen_selects_the_same_query():
+    """acquisition.tes_step with the screened criterion (candidates that can still be the arg-max re-evaluated in fp64)
+    returns the same query index, point and VALUE as the fp64 criterion on all candidates."""
+    from tes_b200 import acquisition
+    rs = np.random.RandomState(5)
+    d, n, S, F, N = 6, 24, 48, 128, 70_001
+    l, sigma, sigma0 = HART6["l"], HART6["sigma"], 1e-3
+    cand, X = rs.rand(N, d), rs.rand(n, d)
+    Y = rs.randn(n, 1) * 0.5
+    theta, W, b = onp.draw_random_init_weights_features(d, S, F, X, Y, l.reshape(1, d), sigma, sigma0, rs.randn(S, F, d),
+                                                        rs.rand(S, F, 1), rs.randn(S, F, 1))
+    kw = dict(criterion="ftl", mode="empirical", deterministic=True, ntestsample=3000, seed=3, t_max=40)
+    a = acquisition.tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, screen=False, **kw)
+    b_ = acquisition.tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, screen=True, **kw)
+    assert a["query_idx"] == b_["query_idx"] and a["query_val"] == b_["query_val"]
+    np.testing.assert_array_equal(a["query_x"], b_["query_x"])
+    assert b_["screen_kept"] is not None and 1 <= b_["screen_kept"] <= N // 8

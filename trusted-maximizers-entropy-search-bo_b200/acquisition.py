@@ -132,12 +132,17 @@ def select_test_points(max_xs, resolution=1e-3, t_max=None):
 
 def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="empirical", deterministic=True,
              ntestsample=1000, n_min_sample=2, nysample=10, niteration=10, z_joint=None, z=None, seed=0,
-             duplicate_resolution=1e-3, t_max=None, shard=None, return_acq=False, timers=None, transform=None, q=1):
+             duplicate_resolution=1e-3, t_max=None, shard=None, return_acq=False, timers=None, transform=None, q=1,
+             screen=None):
     """One acquisition step for one hyper-parameter sample.  Returns a dict with the query index /
     point / value and the intermediate sizes.  `criterion`: 'ftl' (TES_ep) or 'sftl' (TES_sp).
     `q` > 1 (criterion 'sftl' only): batch TES_sp (evaluate_batch_sample_mp.py) on the queries formed by every `q`
     consecutive candidates of this rank's slice (nx = N // q batches; the slice length must be a multiple of q);
-    query_idx is then the global batch index and query_x the (q, d) batch."""
+    query_idx is then the global batch index and query_x the (q, d) batch.
+    `screen` (deterministic TES_ep only; default: on when the acquisition vector is not requested, N >= 32768 and at most
+    128 maximizers): score all candidates with the tensor-core screen (ops.ep_acq_screen: value + proven error bound),
+    evaluate only the candidates that can still be the arg-max with the fp64 criterion -- same query index and value.
+    out["screen_kept"] reports how many were re-evaluated (None: the fp64 criterion ran on everything)."""
     from .criteria import evaluate_batch_sample_mp, evaluate_mp, evaluate_sample_mp
     cand = dev(cand)
     N, d = cand.shape
@@ -173,10 +178,26 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
     # ---- D
     tm = _Timed(timers, "criterion")
     tm.__enter__()
+    sub = None   # candidate subset the exact criterion was evaluated on (screened path)
     if criterion == "ftl":
-        acq = evaluate_mp.mp(cand, ls, sigmas, sigma0s, Xd, Yd, d, N, n, 1, nysample, dev(test_k), dev(max_probs),
-                             dev(v0), dev(v1), invK, invpNK, stochastic=not deterministic, niteration=niteration,
-                             z=z, seed=seed, n_global=shard.n_global, x_offset=shard.offset)
+        pk = dev(max_probs).reshape(-1)
+        nzp = torch.nonzero(pk > 0.0).reshape(-1)
+        use_screen = (deterministic and not return_acq and N >= 32768 and nzp.numel() <= 128) if screen is None \
+            else bool(screen and deterministic and nzp.numel() <= 128)
+        if use_screen:
+            acq_t, eps = ops.ep_acq_screen(cand, dev(test_k), Xd, Yd, ls[0], sigma, sigma0, dev(invpNK)[0], dev(invK)[0],
+                                           pk[nzp], dev(v1)[0][nzp])
+            fin = torch.isfinite(acq_t) & torch.isfinite(eps)
+            lb = (acq_t - eps)[fin].max() if bool(fin.any()) else torch.tensor(float("-inf"), device=cand.device)
+            keep = (~fin) | (acq_t + eps >= lb)
+            sub = torch.nonzero(keep).reshape(-1)             # ascending: the first-maximum rule carries over
+            if sub.numel() > max(4096, N // 8):
+                sub = None                                    # bound too loose to pay off: fp64 on everything
+            out["screen_kept"] = None if sub is None else int(sub.numel())
+        xc = cand if sub is None else cand[sub].contiguous()
+        acq = evaluate_mp.mp(xc, ls, sigmas, sigma0s, Xd, Yd, d, xc.shape[0], n, 1, nysample, dev(test_k),
+                             dev(max_probs), dev(v0), dev(v1), invK, invpNK, stochastic=not deterministic,
+                             niteration=niteration, z=z, seed=seed, n_global=shard.n_global, x_offset=shard.offset)
     elif criterion == "sftl" and q > 1:
         out["K"] = int(v0.shape[-1])
         acq = evaluate_batch_sample_mp.mp(cand.reshape(N // q, q, d), ls, sigmas, sigma0s, Xd, Yd, d, n, 1, nysample,
@@ -192,6 +213,8 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
     tm.__exit__()
     # arg-max over all candidates, first maximum wins (bo_discrete.py:806, :1053-1055)
     li, lv = ops.argmax(acq)
+    if sub is not None:
+        li = sub[li.reshape(-1)[0]].reshape(li.shape)
     pair_v = shard.all_gather(lv.reshape(1))
     pair_i = shard.all_gather((li + shard.offset // q).reshape(1))
     qi, qv = ops.topk_merge(pair_v.reshape(-1, 1, 1), pair_i.reshape(-1, 1, 1))

@@ -26,11 +26,6 @@ constexpr double HALF_LOG_2PI = 0.91893853320467274178;
 //   * diagonal pair (pa = pb): only the 136 pairs a <= b are enumerated, in 9 slices instead of 16: slice 0 is row 0
 //     (16 entries), slice i = 1..7 packs row i (16 - i entries, b = i + kk) with row 16 - i (i entries, b = kk), slice 8
 //     is row 8 (8 entries, the rest zero).  At T = 128 this is K = 8 * 144 + 28 * 256 = 8320 instead of 9216.
-struct QSlice {
-    int pa, pb, i, diag;
-};
-__host__ __device__ inline int64_t quad_num_slices(int64_t nb) { return nb * 9 + nb * (nb - 1) / 2 * 16; }
-
 __global__ void quad_slice_table_kernel(int nb, QSlice* table) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int64_t n = 0;
@@ -40,29 +35,6 @@ __global__ void quad_slice_table_kernel(int nb, QSlice* table) {
                 for (int i = 0; i < ns; ++i) table[n++] = QSlice{pa, pb, i, pa == pb};
             }
     }
-}
-
-// (a, b) of entry kk of a slice; returns false for the zero padding of slice 8 of a diagonal pair
-__device__ __forceinline__ bool quad_slice_ab(const QSlice& q, int kk, int64_t& a, int64_t& b) {
-    int al, bl;
-    if (!q.diag) {
-        al = q.i;
-        bl = kk;
-    } else if (q.i == 0) {
-        al = 0;
-        bl = kk;
-    } else if (q.i < 8) {
-        const bool first = kk < 16 - q.i;
-        al = first ? q.i : 16 - q.i;
-        bl = first ? q.i + kk : kk;
-    } else {
-        al = 8;
-        bl = 8 + kk;
-        if (kk >= 8) return false;
-    }
-    a = (int64_t)q.pa * 16 + al;
-    b = (int64_t)q.pb * 16 + bl;
-    return true;
 }
 
 // Bpack[krow][j] = Sigma_j[a][a] (a = b) or Sigma_j[a][b] + Sigma_j[b][a] (a < b)
@@ -670,6 +642,129 @@ extern "C" int tes_ep_acq_f64(int mode, const double* x, int64_t N, int64_t d, c
                                                              out_acq + c0);
             TES_LAUNCH_OK();
         }
+    }
+    return 0;
+}
+
+// ---- TES_ep deterministic, tensor-core SCREEN ------------------------------------------------------------------
+// acq~(x) and a proven bound eps(x) on |acq~(x) - acq(x)|: the quadratic forms run as a 3xFP16 tcgen05 GEMM
+// (rffprod.cu), everything else as in tes_ep_acq_f64.  The caller keeps the candidates with acq~ + eps >= max(acq~ - eps)
+// and evaluates only those with the fp64 path, which leaves the arg-max and its value unchanged.
+//   |q~_j - q_j| <= delta_j = QS_ETA * h_j^2,  h_j = sum_a |M[x,a]| sqrt(Sigma_j[a][a])   (|Sigma_ab| <= sqrt(S_aa S_bb))
+//   QS_ETA = 1.5 * (2.5 * 2^-20 [hi/lo fp16 operands, dropped lo*lo] + 4 * 2^-24 * 96 [fp32 segments of 256 k])
+//   |1/2 log(v~ + s0) - 1/2 log(v + s0)| <= 1/2 log(w / (w - delta)),  w = v~ + s0  (infinite when w <= delta or NaN)
+namespace tes {
+constexpr double QS_ETA = 4.0e-5;
+__global__ void sqrt_diag_kernel(const double* __restrict__ cov, int64_t Sp, int64_t T, double* __restrict__ D) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T * Sp) return;
+    int64_t a = e / Sp, j = e % Sp;
+    double v = cov[(j * T + a) * T + a];
+    D[e] = v > 0.0 ? sqrt(v) : 0.0;
+}
+__global__ void ep_det_screen_kernel(const double* __restrict__ Qt, const double* __restrict__ Kq,
+                                     const double* __restrict__ G, int64_t ldg, const double* __restrict__ D,
+                                     const double* __restrict__ varf, const double* __restrict__ p, int64_t rows,
+                                     int64_t Sp, int64_t T, double sigma0, double* __restrict__ out_acq,
+                                     double* __restrict__ out_eps) {
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    double s = 0.0, er = 0.0;
+    const double* g = G + row * ldg;
+    const double kq = Kq[row];
+    for (int64_t j = lane; j < Sp; j += 32) {
+        double h = 0.0;
+        for (int64_t a = 0; a < T; ++a) h = fma(fabs(__ldg(g + a)), __ldg(D + a * Sp + j), h);
+        const double w = (kq + Qt[row * Sp + j]) + sigma0;
+        const double delta = QS_ETA * h * h + 1e-300;
+        s += ((HALF_LOG_2PI + log(sqrt(w))) + 0.5) * p[j];
+        const double e1 = (w > delta) ? 0.5 * log(w / (w - delta)) : pos_inf();   // NaN w -> false -> +inf
+        er += e1 * p[j];
+    }
+    s = warp_sum(s);
+    er = warp_sum(er);
+    if (lane == 0) {
+        double ent = (HALF_LOG_2PI + log(sqrt(varf[row] + sigma0))) + 0.5;
+        const double a = ent - s / (double)Sp;
+        out_acq[row] = a;
+        out_eps[row] = er / (double)Sp + 1e-13 * fabs(a);   // + rounding slack of the two fp64 evaluations
+    }
+}
+}  // namespace tes
+
+extern "C" int64_t tes_ep_acq_screen_workspace_bytes(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp) {
+    if (N < 0 || T < 1 || n < 1 || d < 1 || Sp < 1 || Sp > 128) return -1;
+    EpPlan pl = ep_plan(N, T, n, d, Sp);
+    return pl.total + quad_screen_a_bytes(pl.nc, pl.Kdim) + quad_screen_b_bytes(pl.Kdim) + align_up(pl.nc * 8, 256) +
+           align_up(T * Sp * 8, 256);
+}
+
+extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, const double* test_xs, int64_t T,
+                                     const double* X, int64_t n, const double* Y, const double* l, double sigma,
+                                     double sigma0, const double* invpNK, const double* invKobs, const double* p,
+                                     int64_t Sp, const double* post_cov, double* out_acq, double* out_eps, void* ws,
+                                     int64_t ws_bytes, void* stream) {
+    if (N < 0 || (N > 0 && !x)) return -1;
+    if (d < 1 || d > 64) return -3;
+    if (T < 1 || !test_xs) return -4;
+    if (n < 1 || !X || !Y) return -6;
+    if (!l) return -9;
+    if (!invpNK) return -12;
+    if (!invKobs) return -13;
+    if (!p) return -14;
+    if (Sp < 1 || Sp > 128) return -15;
+    if (!post_cov) return -16;
+    if (N > 0 && (!out_acq || !out_eps)) return -17;
+    EpPlan pl = ep_plan(N, T, n, d, Sp);
+    if (!ws || ws_bytes < tes_ep_acq_screen_workspace_bytes(N, T, n, d, Sp)) return -100;
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)ws;
+    double* xto = (double*)(base + pl.off_xto);
+    double* Bext = (double*)(base + pl.off_bext);
+    double* Kc = (double*)(base + pl.off_kc);
+    double* Gc = (double*)(base + pl.off_gc);
+    QSlice* table = (QSlice*)(base + pl.off_table);
+    double* Bpack = (double*)(base + pl.off_bpack);
+    double* varc = (double*)(base + pl.off_var);
+    double* Kq = (double*)(base + pl.off_kq);
+    double* Gobs = (double*)(base + pl.off_gobs);
+    double* varf = (double*)(base + pl.off_varf);
+    char* extra = base + pl.total;
+    void* Atc = extra;
+    extra += quad_screen_a_bytes(pl.nc, pl.Kdim);
+    void* Btc = extra;
+    double* colmax = (double*)(extra + align_up((quad_screen_kp(pl.Kdim) / 64) * (int64_t)(2 * 8 * 128 * 16), 256));
+    extra += quad_screen_b_bytes(pl.Kdim);
+    double* rowmax = (double*)extra;
+    extra += align_up(pl.nc * 8, 256);
+    double* Dm = (double*)extra;
+    const int64_t m = pl.m;
+    int rc;
+    if ((rc = launch_concat_rows(test_xs, T, X, n, (int)d, xto, st))) return rc;
+    if ((rc = launch_build_bext(invpNK, Y, m, T, Bext, st))) return rc;
+    quad_slice_table_kernel<<<1, 32, 0, st>>>((int)pl.nb, table);
+    TES_LAUNCH_OK();
+    {
+        int64_t tot = pl.Kdim * Sp;
+        quad_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(post_cov, Sp, T, table, pl.Kdim, Bpack);
+        TES_LAUNCH_OK();
+    }
+    if ((rc = launch_quad_screen_build_b(Bpack, pl.Kdim, Sp, Btc, colmax, st))) return rc;
+    sqrt_diag_kernel<<<(unsigned)((T * Sp + 255) / 256), 256, 0, st>>>(post_cov, Sp, T, Dm);
+    TES_LAUNCH_OK();
+    for (int64_t c0 = 0; c0 < N; c0 += PS_CHUNK) {
+        const int64_t nc = (N - c0 < PS_CHUNK) ? (N - c0) : PS_CHUNK;
+        if ((rc = launch_se_ard(x + c0 * d, nc, xto, m, (int)d, l, sigma, -1, 0.0, Kc, m, st))) return rc;
+        if ((rc = launch_gemm(Kc, m, Bext, m + 1, 1, Gc, m + 1, nc, m + 1, m, st))) return rc;
+        if ((rc = launch_rowdot(Gc, m + 1, Kc, m, nc, m, sigma, -INFINITY, Kq, st))) return rc;
+        if ((rc = launch_quad_screen(Gc, m + 1, nc, T, table, pl.Kdim, Btc, colmax, Sp, Atc, rowmax, varc, st))) return rc;
+        if ((rc = launch_gemm(Kc + T, m, invKobs, n, 1, Gobs, n, nc, n, n, st))) return rc;
+        if ((rc = launch_rowdot(Gobs, n, Kc + T, m, nc, n, sigma, 1e-100, varf, st))) return rc;
+        ep_det_screen_kernel<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(varc, Kq, Gc, m + 1, Dm, varf, p, nc, Sp, T,
+                                                                               sigma0, out_acq + c0, out_eps + c0);
+        TES_LAUNCH_OK();
     }
     return 0;
 }

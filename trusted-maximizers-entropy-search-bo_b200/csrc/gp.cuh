@@ -29,4 +29,43 @@ int launch_concat_rows(const double* a, int64_t na, const double* b, int64_t nb,
                        cudaStream_t st);
 // Bext = [invpNK | invpNK[:, T:] Y]  (m x (m+1))
 int launch_build_bext(const double* invpNK, const double* Y, int64_t m, int64_t T, double* Bext, cudaStream_t st);
+
+// ---- slice table of the symmetric quadratic forms (criteria.cu; shared with the tensor-core screen in rffprod.cu) ----
+struct QSlice {
+    int pa, pb, i, diag;
+};
+__host__ __device__ inline int64_t quad_num_slices(int64_t nb) { return nb * 9 + nb * (nb - 1) / 2 * 16; }
+
+// (a, b) of entry kk of a slice; returns false for the zero padding of slice 8 of a diagonal pair
+__device__ __forceinline__ bool quad_slice_ab(const QSlice& q, int kk, int64_t& a, int64_t& b) {
+    int al, bl;
+    if (!q.diag) {
+        al = q.i;
+        bl = kk;
+    } else if (q.i == 0) {
+        al = 0;
+        bl = kk;
+    } else if (q.i < 8) {
+        const bool first = kk < 16 - q.i;
+        al = first ? q.i : 16 - q.i;
+        bl = first ? q.i + kk : kk;
+    } else {
+        al = 8;
+        bl = 8 + kk;
+        if (kk >= 8) return false;
+    }
+    a = (int64_t)q.pa * 16 + al;
+    b = (int64_t)q.pb * 16 + bl;
+    return true;
+}
+
+
+// tcgen05 screen of the quadratic forms (rffprod.cu): Q~[x][j] ~ sum_k (M[x,a_k] M[x,b_k]) Bpack[k][j] as a 3xFP16 GEMM.
+int64_t quad_screen_kp(int64_t Kdim);                                   // K padded to whole segments
+int64_t quad_screen_a_bytes(int64_t nc, int64_t Kdim);                  // operand A of one candidate chunk
+int64_t quad_screen_b_bytes(int64_t Kdim);                              // operand B (all maximizers, <= 128)
+int launch_quad_screen_build_b(const double* Bpack, int64_t Kdim, int64_t Sp, void* Btc, double* colmax, cudaStream_t st);
+int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, const QSlice* table, int64_t Kdim,
+                       const void* Btc, const double* colmax, int64_t Sp, void* Atc, double* rowmax, double* Qout,
+                       cudaStream_t st);
 }  // namespace tes

@@ -737,7 +737,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     prod_gemm_topk_tc_kernel(const __half* __restrict__ Pt, const __half* __restrict__ Qt, int64_t nu, int64_t nv,
                              int64_t ntu, int64_t ntv, int64_t nst, double scale0, const double* __restrict__ tmax,
                              int64_t idx_offset, int kp, int64_t G, double* __restrict__ part_val,
-                             int64_t* __restrict__ part_idx) {
+                             int64_t* __restrict__ part_idx, double* __restrict__ store_out, int64_t ldo,
+                             const double* __restrict__ rowscale, const double* __restrict__ colscale) {
+    // store_out != nullptr: instead of the top-k epilogue, write rowscale[row] * colscale[col] * sum to
+    // store_out[row * ldo + col] (the quadratic-form screen of the TES_ep criterion)
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     unsigned char* stages = tc_smem_raw;                                            // [TC_NS][A block | B block]
     uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem_raw + TC_NS * TC_STAGE_BYTES);
@@ -749,7 +752,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t g = blockIdx.z;
     const int64_t rt = blockIdx.x, ct = blockIdx.y;
-    const double scale = scale0 * tmax[g];
+    const double scale = tmax ? scale0 * tmax[g] : scale0;
     const int64_t nseg = nst / TC_SEG;
     if (tid == 0) {
         for (int s = 0; s < TC_NS; ++s) {
@@ -842,6 +845,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // per-warp top-kp of its 32 rows x 32 columns: every lane caches the best of its not yet consumed values
         const int64_t row = rt * 128 + quarter * 32 + lane;
         const int64_t colb = ct * 128 + cb * 32;
+        if (store_out) {
+            if (row < nu) {
+                const double rs = scale * rowscale[row];
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (colb + c < nv) store_out[row * ldo + colb + c] = rs * colscale[colb + c] * sum[c];
+            }
+        } else {
         const int64_t list = ((int64_t)rt * gridDim.y + ct) * TC_EPI_WARPS + ew;
         double* ov = part_val + (list * G + g) * kp;
         int64_t* oi = part_idx + (list * G + g) * kp;
@@ -880,6 +891,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
             if (bc >= 0 && wi == ci0 + bc) used |= 1u << bc;   // the winning lane consumes its element
         }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -887,6 +899,146 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
     }
+}
+
+// ---- TES_ep quadratic forms as a 3xFP16 tcgen05 GEMM (screen; criteria.cu refines the candidates near the arg-max) --
+// A[x][k] = M[x,a_k] M[x,b_k] (index pairs of the slice table), normalised per row to max 4096 so that the fp16 hi/lo
+// pair keeps 22 significant bits down to products 2^-37 of the largest; B[k][j] = Bpack[k][j] normalised per column to
+// max 8.  Both in MMA order (see above), K padded with zeros to whole 256-k segments.
+constexpr double QS_AMAX = 4096.0, QS_BMAX = 8.0;
+__global__ void quad_rowmax_kernel(const double* __restrict__ G, int64_t ldg, int64_t nc, int64_t T,
+                                   double* __restrict__ rowmax) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nc) return;
+    double m = 0.0;
+    for (int64_t a = lane; a < T; a += 32) m = fmax(m, fabs(G[row * ldg + a]));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0) rowmax[row] = m;
+}
+// thread = (row, 8-k chunk): 8 products -> one 16-byte store of hi and one of lo; consecutive threads = consecutive rows
+__global__ void quad_build_a_kernel(const double* __restrict__ G, int64_t ldg, int64_t nc, int64_t T,
+                                    const QSlice* __restrict__ table, int64_t Kdim, int64_t Kp,
+                                    const double* __restrict__ rowmax, __half* __restrict__ out) {
+    const int64_t nrowp = (nc + 127) / 128 * 128;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nrowp * (Kp / 8)) return;
+    const int64_t row = t % nrowp, kc = t / nrowp;             // kc = global 8-k chunk
+    const int64_t k0 = kc * 8, st = k0 / TC_BK, chunk = (k0 % TC_BK) / 8;
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) hi[e] = lo[e] = __float2half_rn(0.0f);
+    if (row < nc && k0 < Kdim) {
+        const double rm = rowmax[row];
+        const double sc = rm > 0.0 ? QS_AMAX / (rm * rm) : 0.0;
+        const int4 qv = __ldg(reinterpret_cast<const int4*>(table) + (k0 >> 4));
+        const QSlice q{qv.x, qv.y, qv.z, qv.w};
+        const double* g = G + row * ldg;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int64_t a = 0, b = 0;
+            if (quad_slice_ab(q, (int)((k0 & 15) + e), a, b) && a < T && b < T) {
+                const float pr = (float)(__ldg(g + a) * __ldg(g + b) * sc);
+                split_f16(pr, hi[e], lo[e]);
+            }
+        }
+    }
+    const int64_t tile = row / 128, r = row % 128, nst = Kp / TC_BK;
+    __half* blk = out + (tile * nst + st) * (int64_t)(TC_BLOCK_BYTES / 2);
+    const int64_t o = (chunk * 128 + r) * 8;
+    *reinterpret_cast<uint4*>(blk + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(blk + 8 * 128 * 8 + o) = *reinterpret_cast<const uint4*>(lo);
+}
+__global__ void quad_colmax_kernel(const double* __restrict__ Bpack, int64_t Kdim, int64_t Sp,
+                                   double* __restrict__ colmax) {
+    __shared__ double red[256];
+    const int64_t j = blockIdx.x;
+    double m = 0.0;
+    for (int64_t k = threadIdx.x; k < Kdim; k += blockDim.x) m = fmax(m, fabs(Bpack[k * Sp + j]));
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) colmax[j] = red[0];
+}
+// thread = (column j < 128, 8-k chunk)
+__global__ void quad_build_b_kernel(const double* __restrict__ Bpack, int64_t Kdim, int64_t Kp, int64_t Sp,
+                                    const double* __restrict__ colmax, __half* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 128 * (Kp / 8)) return;
+    const int64_t j = t % 128, kc = t / 128;
+    const int64_t k0 = kc * 8, st = k0 / TC_BK, chunk = (k0 % TC_BK) / 8;
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) hi[e] = lo[e] = __float2half_rn(0.0f);
+    if (j < Sp) {
+        const double cm = colmax[j];
+        const double sc = cm > 0.0 ? QS_BMAX / cm : 0.0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (k0 + e < Kdim) split_f16((float)(Bpack[(k0 + e) * Sp + j] * sc), hi[e], lo[e]);
+    }
+    __half* blk = out + st * (int64_t)(TC_BLOCK_BYTES / 2);
+    const int64_t o = (chunk * 128 + j) * 8;
+    *reinterpret_cast<uint4*>(blk + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(blk + 8 * 128 * 8 + o) = *reinterpret_cast<const uint4*>(lo);
+}
+// out[x][j] *= rowmax[x]^2 / QS_AMAX * colmax[j] / QS_BMAX is folded into the store epilogue through rowscale / colscale
+__global__ void quad_scales_kernel(const double* __restrict__ rowmax, int64_t nc, double* __restrict__ rowscale,
+                                   const double* __restrict__ colmax, int64_t Sp, double* __restrict__ colscale) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nc) rowscale[t] = rowmax[t] * rowmax[t] / QS_AMAX;
+    if (colscale && t < Sp) colscale[t] = colmax[t] / QS_BMAX;
+}
+
+int64_t quad_screen_kp(int64_t Kdim) { return (Kdim + 255) / 256 * 256; }
+int64_t quad_screen_a_bytes(int64_t nc, int64_t Kdim) {
+    return align_up(((nc + 127) / 128) * (quad_screen_kp(Kdim) / TC_BK) * (int64_t)TC_BLOCK_BYTES, 256) + align_up(nc * 8, 256);
+}
+int64_t quad_screen_b_bytes(int64_t Kdim) {
+    return align_up((quad_screen_kp(Kdim) / TC_BK) * (int64_t)TC_BLOCK_BYTES, 256) + 2 * align_up(128 * 8, 256);
+}
+// Btc layout: [operand blocks][colmax (128)][colscale (128)]
+int launch_quad_screen_build_b(const double* Bpack, int64_t Kdim, int64_t Sp, void* Btc, double* colmax, cudaStream_t st) {
+    const int64_t Kp = quad_screen_kp(Kdim);
+    double* colscale = colmax + 128;
+    quad_colmax_kernel<<<(unsigned)Sp, 256, 0, st>>>(Bpack, Kdim, Sp, colmax);
+    TES_LAUNCH_OK();
+    const int64_t tot = 128 * (Kp / 8);
+    quad_build_b_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Bpack, Kdim, Kp, Sp, colmax, (__half*)Btc);
+    TES_LAUNCH_OK();
+    quad_scales_kernel<<<1, 128, 0, st>>>(colmax, 0, nullptr, colmax, Sp, colscale);
+    TES_LAUNCH_OK();
+    return 0;
+}
+// Atc: [operand blocks of the chunk][rowscale (nc)]; rowmax: nc doubles of scratch
+int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, const QSlice* table, int64_t Kdim,
+                       const void* Btc, const double* colmax, int64_t Sp, void* Atc, double* rowmax, double* Qout,
+                       cudaStream_t st) {
+    const int64_t Kp = quad_screen_kp(Kdim), nst = Kp / TC_BK, ntu = (nc + 127) / 128;
+    double* rowscale = (double*)((char*)Atc + align_up(ntu * nst * (int64_t)TC_BLOCK_BYTES, 256));
+    const double* colscale = colmax + 128;
+    quad_rowmax_kernel<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(G, ldg, nc, T, rowmax);
+    TES_LAUNCH_OK();
+    {
+        const int64_t tot = ntu * 128 * (Kp / 8);
+        quad_build_a_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(G, ldg, nc, T, table, Kdim, Kp, rowmax,
+                                                                         (__half*)Atc);
+        TES_LAUNCH_OK();
+    }
+    quad_scales_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(rowmax, nc, rowscale, nullptr, 0, nullptr);
+    TES_LAUNCH_OK();
+    TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(TC_NS * TC_STAGE_BYTES + 256)));
+    dim3 grid((unsigned)ntu, 1, 1);
+    prod_gemm_topk_tc_kernel<<<grid, TC_THREADS, TC_NS * TC_STAGE_BYTES + 256, st>>>(
+        (const __half*)Atc, (const __half*)Btc, nc, Sp, ntu, 1, nst, 1.0, nullptr, 0, 0, 1, nullptr, nullptr, Qout, Sp,
+        rowscale, colscale);
+    TES_LAUNCH_OK();
+    return 0;
 }
 
 // tmax[j] = max_f |theta[j][f]| (one block per sample)
@@ -1211,7 +1363,7 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
             TES_LAUNCH_OK();
             dim3 gtc((unsigned)ntu, (unsigned)ntv, (unsigned)G);
             prod_gemm_topk_tc_kernel<<<gtc, TC_THREADS, TC_NS * TC_STAGE_BYTES + 256, st>>>(
-                Hhi, Ghi, nu, nv, ntu, ntv, nst, scale, tmax + j0, idx_offset, pl.kp, G, pv, pi);
+                Hhi, Ghi, nu, nv, ntu, ntv, nst, scale, tmax + j0, idx_offset, pl.kp, G, pv, pi, nullptr, 0, nullptr, nullptr);
             TES_LAUNCH_OK();
         } else if (tf32 == 2) {
             const int64_t totp = G * ((nu + PB_ROWS - 1) / PB_ROWS) * F, totq = G * ((nv + PB_ROWS - 1) / PB_ROWS) * F;

@@ -349,6 +349,31 @@ def ep_acq(mode, x, test_xs, X, Y, l, sigma, sigma0, invpNK, invKobs, p, post_me
     return (acq, omean, ovar) if want_moments else acq
 
 
+def ep_acq_screen(x, test_xs, X, Y, l, sigma, sigma0, invpNK, invKobs, p, post_cov):
+    """Tensor-core screen of the deterministic TES_ep criterion -> (acq~ (N,), eps (N,)) with |acq~ - acq| <= eps proven
+    (tes_ep_acq_screen_f64; the quadratic forms as a 3xFP16 tcgen05 GEMM).  p / post_cov: maximizers with p > 0 only."""
+    x = dev(x)
+    dv = x.device
+    test_xs, X, Y, invpNK = dev(test_xs, dv), dev(X, dv), dev(Y, dv).reshape(-1), dev(invpNK, dv)
+    p, post_cov, invKobs = dev(p, dv).reshape(-1), dev(post_cov, dv), dev(invKobs, dv)
+    N, d = x.shape
+    T, n, Sp = test_xs.shape[0], X.shape[0], p.numel()
+    if post_cov.shape != (Sp, T, T) or invpNK.shape != (T + n, T + n):
+        raise ValueError("post_cov must be (Sp,T,T) and invpNK (T+n, T+n)")
+    L = _lib.lib()
+    need = L.tes_ep_acq_screen_workspace_bytes(N, T, n, d, Sp)
+    if need < 0:
+        raise ValueError("tes_ep_acq_screen_f64 needs Sp <= 128 and n >= 1")
+    ws = WORKSPACE.get(need, dv)
+    acq = torch.empty((N,), dtype=torch.float64, device=dv)
+    eps = torch.empty((N,), dtype=torch.float64, device=dv)
+    rc = L.tes_ep_acq_screen_f64(ptr(x), N, d, ptr(test_xs), T, ptr(X), n, ptr(Y), ptr(_l(l, d, dv)), float(sigma),
+                                 float(sigma0), ptr(invpNK), ptr(invKobs), ptr(p), Sp, ptr(post_cov), ptr(acq), ptr(eps),
+                                 ptr(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_ep_acq_screen_f64")
+    return acq, eps
+
+
 def sp_acq(x, test_xs, X, Y, l, sigma, sigma0, invpNK, p, post_samples, post_mask, niter=10, nysample=10, z=None,
            seed=0, n_global=None, x_offset=0):
     """TES_sp acquisition; x (nx,d) or (nx,q,d).  evaluate_sample_mp.py / evaluate_batch_sample_mp.py."""
