@@ -457,6 +457,9 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(config_of(wl), T=out.get("T"), Sp=out.get("Sp"), K=out.get("K"),
+                           criterion_screen_kept=out.get("screen_kept"),
+                           criterion_screen_ms=(float(np.mean([a.elapsed_time(b_) for a, b_ in timers["criterion_screen"]]))
+                                                if timers.get("criterion_screen") else None),
                            n_unique_maximizers=out.get("n_unique_maximizers"),
                            l2="flushed between timed iterations (256 MiB memset)",
                            candidates=("product set U x V detected (slow columns [%d, %d), nv=%d): stage A = GEMM path (3xFP16 tensor-core screen + fp64 refine)" % product)

@@ -185,8 +185,9 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
         use_screen = (deterministic and not return_acq and N >= 32768 and nzp.numel() <= 128) if screen is None \
             else bool(screen and deterministic and nzp.numel() <= 128)
         if use_screen:
-            acq_t, eps = ops.ep_acq_screen(cand, dev(test_k), Xd, Yd, ls[0], sigma, sigma0, dev(invpNK)[0], dev(invK)[0],
-                                           pk[nzp], dev(v1)[0][nzp])
+            with _Timed(timers, "criterion_screen"):
+                acq_t, eps = ops.ep_acq_screen(cand, dev(test_k), Xd, Yd, ls[0], sigma, sigma0, dev(invpNK)[0],
+                                               dev(invK)[0], pk[nzp], dev(v1)[0][nzp])
             fin = torch.isfinite(acq_t) & torch.isfinite(eps)
             lb = (acq_t - eps)[fin].max() if bool(fin.any()) else torch.tensor(float("-inf"), device=cand.device)
             keep = (~fin) | (acq_t + eps >= lb)

@@ -662,20 +662,24 @@ __global__ void sqrt_diag_kernel(const double* __restrict__ cov, int64_t Sp, int
     double v = cov[(j * T + a) * T + a];
     D[e] = v > 0.0 ? sqrt(v) : 0.0;
 }
+__global__ void abs_rows_kernel(const double* __restrict__ G, int64_t ldg, int64_t rows, int64_t T,
+                                double* __restrict__ out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * T) return;
+    out[e] = fabs(G[(e / T) * ldg + e % T]);
+}
+// H[x][j] = sum_a |M[x,a]| sqrt(Sigma_j[a][a]) comes from a GEMM (abs_rows_kernel + launch_gemm)
 __global__ void ep_det_screen_kernel(const double* __restrict__ Qt, const double* __restrict__ Kq,
-                                     const double* __restrict__ G, int64_t ldg, const double* __restrict__ D,
-                                     const double* __restrict__ varf, const double* __restrict__ p, int64_t rows,
-                                     int64_t Sp, int64_t T, double sigma0, double* __restrict__ out_acq,
-                                     double* __restrict__ out_eps) {
+                                     const double* __restrict__ H, const double* __restrict__ varf,
+                                     const double* __restrict__ p, int64_t rows, int64_t Sp, double sigma0,
+                                     double* __restrict__ out_acq, double* __restrict__ out_eps) {
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= rows) return;
     double s = 0.0, er = 0.0;
-    const double* g = G + row * ldg;
     const double kq = Kq[row];
     for (int64_t j = lane; j < Sp; j += 32) {
-        double h = 0.0;
-        for (int64_t a = 0; a < T; ++a) h = fma(fabs(__ldg(g + a)), __ldg(D + a * Sp + j), h);
+        const double h = H[row * Sp + j];
         const double w = (kq + Qt[row * Sp + j]) + sigma0;
         const double delta = QS_ETA * h * h + 1e-300;
         s += ((HALF_LOG_2PI + log(sqrt(w))) + 0.5) * p[j];
@@ -697,7 +701,7 @@ extern "C" int64_t tes_ep_acq_screen_workspace_bytes(int64_t N, int64_t T, int64
     if (N < 0 || T < 1 || n < 1 || d < 1 || Sp < 1 || Sp > 128) return -1;
     EpPlan pl = ep_plan(N, T, n, d, Sp);
     return pl.total + quad_screen_a_bytes(pl.nc, pl.Kdim) + quad_screen_b_bytes(pl.Kdim) + align_up(pl.nc * 8, 256) +
-           align_up(T * Sp * 8, 256);
+           align_up(T * Sp * 8, 256) + align_up(pl.nc * T * 8, 256);
 }
 
 extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, const double* test_xs, int64_t T,
@@ -740,6 +744,9 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
     double* rowmax = (double*)extra;
     extra += align_up(pl.nc * 8, 256);
     double* Dm = (double*)extra;
+    extra += align_up(T * Sp * 8, 256);
+    double* absM = (double*)extra;
+    double* Hb = (double*)(base + pl.off_mean);      // nc x Sp (the mean buffer is unused in this mode)
     const int64_t m = pl.m;
     int rc;
     if ((rc = launch_concat_rows(test_xs, T, X, n, (int)d, xto, st))) return rc;
@@ -762,8 +769,11 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
         if ((rc = launch_quad_screen(Gc, m + 1, nc, T, table, pl.Kdim, Btc, colmax, Sp, Atc, rowmax, varc, st))) return rc;
         if ((rc = launch_gemm(Kc + T, m, invKobs, n, 1, Gobs, n, nc, n, n, st))) return rc;
         if ((rc = launch_rowdot(Gobs, n, Kc + T, m, nc, n, sigma, 1e-100, varf, st))) return rc;
-        ep_det_screen_kernel<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(varc, Kq, Gc, m + 1, Dm, varf, p, nc, Sp, T,
-                                                                               sigma0, out_acq + c0, out_eps + c0);
+        abs_rows_kernel<<<(unsigned)((nc * T + 255) / 256), 256, 0, st>>>(Gc, m + 1, nc, T, absM);
+        TES_LAUNCH_OK();
+        if ((rc = launch_gemm(absM, T, Dm, Sp, 1, Hb, Sp, nc, Sp, T, st))) return rc;
+        ep_det_screen_kernel<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(varc, Kq, Hb, varf, p, nc, Sp, sigma0,
+                                                                               out_acq + c0, out_eps + c0);
         TES_LAUNCH_OK();
     }
     return 0;

@@ -676,60 +676,66 @@ __host__ __device__ constexpr uint32_t tc_idesc_f16(int m, int n) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])      \
         : "r"(taddr))
 
-// operand build in MMA order: block index ((g * ntile + tile) * nst + st), inside [hl][chunk][row][8]
-__global__ void prod_build_tc_kernel(const double* __restrict__ cand, int64_t nrow, int64_t row_stride, int d, int s_lo,
-                                     int s_hi, int which, const double* __restrict__ W, const double* __restrict__ b,
-                                     const double* __restrict__ theta, int64_t j0, int64_t G, int64_t F, int w_shared,
-                                     int64_t ntile, int64_t nst, const double* __restrict__ tmax,
-                                     __half* __restrict__ out) {
-    const int64_t nrb = (nrow + PB_ROWS - 1) / PB_ROWS;
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= G * nrb * F) return;
-    const int64_t f = t % F, rb = (t / F) % nrb, g = t / (F * nrb);
+// operand build in MMA order: block index ((g * ntile + tile) * nst + st), inside [hl][chunk][row][8].
+// One CTA per (sample, 128-row tile): the tile's coordinates are staged in shared memory, thread (row, half) walks the
+// 8-k chunks (= 4 features: weights read with block-uniform addresses), row-consecutive threads write consecutive
+// 16-byte slots of the MMA layout.
+__global__ void __launch_bounds__(256)
+    prod_build_tc_kernel(const double* __restrict__ cand, int64_t nrow, int64_t row_stride, int d, int s_lo, int s_hi,
+                         int which, const double* __restrict__ W, const double* __restrict__ b,
+                         const double* __restrict__ theta, int64_t j0, int64_t F, int w_shared, int64_t ntile,
+                         int64_t nst, const double* __restrict__ tmax, __half* __restrict__ out) {
+    __shared__ double xs[16][129];                   // [coordinate slot][row]
+    const int64_t tile = blockIdx.x, g = blockIdx.y;
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int64_t ir = tile * 128 + r;
     const int64_t j = j0 + g, jw = w_shared ? 0 : j;
-    const double* w = W + (jw * F + f) * d;
-    double wk[16];
-    int nk_ = 0;
+    // coordinate slots: the columns this side uses, in order
+    int cols[16], ncol = 0;
     if (which == 0) {
-        for (int k = s_lo; k < s_hi; ++k) wk[nk_++] = w[k];
+        for (int k = s_lo; k < s_hi; ++k) cols[ncol++] = k;
     } else {
-        for (int k = 0; k < s_lo; ++k) wk[nk_++] = w[k];
-        for (int k = s_hi; k < d; ++k) wk[nk_++] = w[k];
+        for (int k = 0; k < s_lo; ++k) cols[ncol++] = k;
+        for (int k = s_hi; k < d; ++k) cols[ncol++] = k;
     }
-    const double a0 = which == 0 ? b[jw * F + f] : 0.0;
-    double th = 1.0;
-    if (which == 0) {
-        const double tm = tmax[j];
-        th = tm > 0.0 ? theta[j * F + f] / tm : 0.0;
+    for (int e = threadIdx.x; e < ncol * 128; e += 256) {
+        const int c = e / 128, rr = e % 128;
+        const int64_t gr = tile * 128 + rr;
+        xs[c][rr] = gr < nrow ? cand[(gr * row_stride) * d + cols[c]] : 0.0;
     }
-    const int64_t k2 = 2 * f, st = k2 / TC_BK, chunk = (k2 % TC_BK) / 8, e = k2 % 8;
-    for (int r = 0; r < PB_ROWS; ++r) {
-        const int64_t ir = rb * PB_ROWS + r;
-        if (ir >= nrow) break;
-        const double* x = cand + (ir * row_stride) * d;
-        double a = a0;
-        int q = 0;
-        if (which == 0) {
-            for (int k = s_lo; k < s_hi; ++k) a = fma(wk[q++], x[k], a);
-        } else {
-            for (int k = 0; k < s_lo; ++k) a = fma(wk[q++], x[k], a);
-            for (int k = s_hi; k < d; ++k) a = fma(wk[q++], x[k], a);
+    __syncthreads();
+    const double tm = which == 0 ? tmax[j] : 1.0;
+    const int64_t nkc = nst * (TC_BK / 8);
+    const int64_t kc_lo = nkc * blockIdx.z / gridDim.z, kc_hi = nkc * (blockIdx.z + 1) / gridDim.z;
+    for (int64_t kc = kc_lo + half; kc < kc_hi; kc += 2) {
+        const int64_t st = kc / (TC_BK / 8), chunk = kc % (TC_BK / 8);
+        __align__(16) __half hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hi[e] = lo[e] = __float2half_rn(0.0f);
+        if (ir < nrow) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t f = kc * 4 + q;
+                if (f >= F) break;
+                const double* w = W + (jw * F + f) * d;
+                double a = which == 0 ? b[jw * F + f] : 0.0;
+                for (int c = 0; c < ncol; ++c) a = fma(__ldg(w + cols[c]), xs[c][r], a);
+                float sn, cs;
+                sincosf((float)(a - 6.283185307179586 * rint(a * 0.15915494309189535)), &sn, &cs);
+                float p0 = cs, p1 = sn;
+                if (which == 0) {
+                    const double th = tm > 0.0 ? theta[j * F + f] / tm : 0.0;
+                    p0 = (float)(th * (double)cs);
+                    p1 = (float)(-th * (double)sn);
+                }
+                split_f16(p0, hi[2 * q], lo[2 * q]);
+                split_f16(p1, hi[2 * q + 1], lo[2 * q + 1]);
+            }
         }
-        float sn, cs;
-        sincosf((float)(a - 6.283185307179586 * rint(a * 0.15915494309189535)), &sn, &cs);
-        float p0 = cs, p1 = sn;
-        if (which == 0) {
-            p0 = (float)(th * (double)cs);
-            p1 = (float)(-th * (double)sn);
-        }
-        __half h0, l0, h1, l1;
-        split_f16(p0, h0, l0);
-        split_f16(p1, h1, l1);
-        const int64_t tile = ir / 128, row = ir % 128;
         __half* blk = out + ((g * ntile + tile) * nst + st) * (int64_t)(TC_BLOCK_BYTES / 2);
-        const int64_t o = (chunk * 128 + row) * 8 + e;
-        *reinterpret_cast<__half2*>(blk + o) = __halves2half2(h0, h1);
-        *reinterpret_cast<__half2*>(blk + 8 * 128 * 8 + o) = __halves2half2(l0, l1);
+        const int64_t o = (chunk * 128 + r) * 8;
+        *reinterpret_cast<uint4*>(blk + o) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(blk + 8 * 128 * 8 + o) = *reinterpret_cast<const uint4*>(lo);
     }
 }
 
@@ -917,38 +923,51 @@ __global__ void quad_rowmax_kernel(const double* __restrict__ G, int64_t ldg, in
     for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
     if (lane == 0) rowmax[row] = m;
 }
-// thread = (row, 8-k chunk): 8 products -> one 16-byte store of hi and one of lo; consecutive threads = consecutive rows
-__global__ void quad_build_a_kernel(const double* __restrict__ G, int64_t ldg, int64_t nc, int64_t T,
-                                    const QSlice* __restrict__ table, int64_t Kdim, int64_t Kp,
-                                    const double* __restrict__ rowmax, __half* __restrict__ out) {
-    const int64_t nrowp = (nc + 127) / 128 * 128;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nrowp * (Kp / 8)) return;
-    const int64_t row = t % nrowp, kc = t / nrowp;             // kc = global 8-k chunk
-    const int64_t k0 = kc * 8, st = k0 / TC_BK, chunk = (k0 % TC_BK) / 8;
-    __align__(16) __half hi[8], lo[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) hi[e] = lo[e] = __float2half_rn(0.0f);
-    if (row < nc && k0 < Kdim) {
+// One CTA per 128-row tile: M[128][T] is staged once in shared memory as floats ([a][row]: conflict-free for
+// row-consecutive threads; the products only need the 22 bits the hi/lo fp16 pair keeps), then the CTA walks the 8-k
+// chunks: thread (row, half) forms 8 products per chunk and writes 16 bytes of hi and of lo -- row-consecutive threads
+// write consecutive 16-byte slots of the MMA layout.  (A first version read M straight from global memory with a
+// row-sized stride between lanes: 0.86 ms per chunk, 45 ms per C3 step.)
+__global__ void __launch_bounds__(256)
+    quad_build_a_kernel(const double* __restrict__ G, int64_t ldg, int64_t nc, int64_t T, const QSlice* __restrict__ table,
+                        int64_t Kdim, int64_t Kp, const double* __restrict__ rowmax, __half* __restrict__ out) {
+    extern __shared__ float qa_sm[];                 // [T][129] (odd stride: conflict-free for both access patterns)
+    const int64_t tile = blockIdx.x;
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int64_t row = tile * 128 + r;
+    for (int64_t e = threadIdx.x; e < T * 128; e += 256) {
+        const int64_t rr = e / T, a = e % T;          // lanes run along a row of M: coalesced reads
+        const int64_t grow = tile * 128 + rr;
+        qa_sm[a * 129 + rr] = grow < nc ? (float)G[grow * ldg + a] : 0.0f;
+    }
+    __syncthreads();
+    float sc = 0.0f;
+    if (row < nc) {
         const double rm = rowmax[row];
-        const double sc = rm > 0.0 ? QS_AMAX / (rm * rm) : 0.0;
-        const int4 qv = __ldg(reinterpret_cast<const int4*>(table) + (k0 >> 4));
-        const QSlice q{qv.x, qv.y, qv.z, qv.w};
-        const double* g = G + row * ldg;
+        sc = rm > 0.0 ? (float)(QS_AMAX / (rm * rm)) : 0.0f;
+    }
+    const int64_t nst = Kp / TC_BK, nkc = Kp / 8;
+    const int64_t kc_lo = nkc * blockIdx.y / gridDim.y, kc_hi = nkc * (blockIdx.y + 1) / gridDim.y;   // k range of this CTA
+    for (int64_t kc = kc_lo + half; kc < kc_hi; kc += 2) {
+        const int64_t k0 = kc * 8, st = k0 / TC_BK, chunk = (k0 % TC_BK) / 8;
+        __align__(16) __half hi[8], lo[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            int64_t a = 0, b = 0;
-            if (quad_slice_ab(q, (int)((k0 & 15) + e), a, b) && a < T && b < T) {
-                const float pr = (float)(__ldg(g + a) * __ldg(g + b) * sc);
-                split_f16(pr, hi[e], lo[e]);
+        for (int e = 0; e < 8; ++e) hi[e] = lo[e] = __float2half_rn(0.0f);
+        if (k0 < Kdim) {
+            const int4 qv = __ldg(reinterpret_cast<const int4*>(table) + (k0 >> 4));
+            const QSlice q{qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                int64_t a = 0, b = 0;
+                if (quad_slice_ab(q, (int)((k0 & 15) + e), a, b) && a < T && b < T)
+                    split_f16(qa_sm[a * 129 + r] * qa_sm[b * 129 + r] * sc, hi[e], lo[e]);
             }
         }
+        __half* blk = out + (tile * nst + st) * (int64_t)(TC_BLOCK_BYTES / 2);
+        const int64_t o = (chunk * 128 + r) * 8;
+        *reinterpret_cast<uint4*>(blk + o) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(blk + 8 * 128 * 8 + o) = *reinterpret_cast<const uint4*>(lo);
     }
-    const int64_t tile = row / 128, r = row % 128, nst = Kp / TC_BK;
-    __half* blk = out + (tile * nst + st) * (int64_t)(TC_BLOCK_BYTES / 2);
-    const int64_t o = (chunk * 128 + r) * 8;
-    *reinterpret_cast<uint4*>(blk + o) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(blk + 8 * 128 * 8 + o) = *reinterpret_cast<const uint4*>(lo);
 }
 __global__ void quad_colmax_kernel(const double* __restrict__ Bpack, int64_t Kdim, int64_t Sp,
                                    double* __restrict__ colmax) {
@@ -1024,9 +1043,10 @@ int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, cons
     quad_rowmax_kernel<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(G, ldg, nc, T, rowmax);
     TES_LAUNCH_OK();
     {
-        const int64_t tot = ntu * 128 * (Kp / 8);
-        quad_build_a_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(G, ldg, nc, T, table, Kdim, Kp, rowmax,
-                                                                         (__half*)Atc);
+        const size_t smem = (size_t)T * 129 * sizeof(float);
+        if (smem > 200 * 1024) return -5;
+        TES_CUDA_OK(cudaFuncSetAttribute(quad_build_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        quad_build_a_kernel<<<dim3((unsigned)ntu, 6), 256, smem, st>>>(G, ldg, nc, T, table, Kdim, Kp, rowmax, (__half*)Atc);
         TES_LAUNCH_OK();
     }
     quad_scales_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(rowmax, nc, rowscale, nullptr, 0, nullptr);
@@ -1354,12 +1374,11 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
         dim3 grid((unsigned)pl.gx, (unsigned)pl.gy, (unsigned)G);
         if (tf32 == 3) {
             const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK;
-            const int64_t totp = G * ((nu + PB_ROWS - 1) / PB_ROWS) * F, totq = G * ((nv + PB_ROWS - 1) / PB_ROWS) * F;
-            prod_build_tc_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(
-                cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, G, F, w_shared, ntu, nst, tmax, Hhi);
+            prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)G, 8), 256, 0, st>>>(
+                cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, ntu, nst, tmax, Hhi);
             TES_LAUNCH_OK();
-            prod_build_tc_kernel<<<(unsigned)((totq + 255) / 256), 256, 0, st>>>(
-                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, G, F, w_shared, ntv, nst, tmax, Ghi);
+            prod_build_tc_kernel<<<dim3((unsigned)ntv, (unsigned)G, 8), 256, 0, st>>>(
+                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, ntv, nst, tmax, Ghi);
             TES_LAUNCH_OK();
             dim3 gtc((unsigned)ntu, (unsigned)ntv, (unsigned)G);
             prod_gemm_topk_tc_kernel<<<gtc, TC_THREADS, TC_NS * TC_STAGE_BYTES + 256, st>>>(
