@@ -759,6 +759,7 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
         TES_LAUNCH_OK();
     }
     if ((rc = launch_quad_screen_build_b(Bpack, pl.Kdim, Sp, Btc, colmax, st))) return rc;
+    if ((rc = launch_quad_screen_ab(table, pl.Kdim, T, colmax, st))) return rc;
     sqrt_diag_kernel<<<(unsigned)((T * Sp + 255) / 256), 256, 0, st>>>(post_cov, Sp, T, Dm);
     TES_LAUNCH_OK();
     for (int64_t c0 = 0; c0 < N; c0 += PS_CHUNK) {

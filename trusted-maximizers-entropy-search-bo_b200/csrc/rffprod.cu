@@ -720,8 +720,10 @@ __global__ void __launch_bounds__(256)
                 const double* w = W + (jw * F + f) * d;
                 double a = which == 0 ? b[jw * F + f] : 0.0;
                 for (int c = 0; c < ncol; ++c) a = fma(__ldg(w + cols[c]), xs[c][r], a);
+                // argument reduced to [-pi, pi] in fp64, then the MUFU pair (__sincosf: abs error <= 2^-21.2 there):
+                // the operand error budget of the screen (prod_exact_kernel) carries 2^-21 for it
                 float sn, cs;
-                sincosf((float)(a - 6.283185307179586 * rint(a * 0.15915494309189535)), &sn, &cs);
+                __sincosf((float)(a - 6.283185307179586 * rint(a * 0.15915494309189535)), &sn, &cs);
                 float p0 = cs, p1 = sn;
                 if (which == 0) {
                     const double th = tm > 0.0 ? theta[j * F + f] / tm : 0.0;
@@ -929,7 +931,7 @@ __global__ void quad_rowmax_kernel(const double* __restrict__ G, int64_t ldg, in
 // write consecutive 16-byte slots of the MMA layout.  (A first version read M straight from global memory with a
 // row-sized stride between lanes: 0.86 ms per chunk, 45 ms per C3 step.)
 __global__ void __launch_bounds__(256)
-    quad_build_a_kernel(const double* __restrict__ G, int64_t ldg, int64_t nc, int64_t T, const QSlice* __restrict__ table,
+    quad_build_a_kernel(const double* __restrict__ G, int64_t ldg, int64_t nc, int64_t T, const uint32_t* __restrict__ ab,
                         int64_t Kdim, int64_t Kp, const double* __restrict__ rowmax, __half* __restrict__ out) {
     extern __shared__ float qa_sm[];                 // [T][129] (odd stride: conflict-free for both access patterns)
     const int64_t tile = blockIdx.x;
@@ -954,20 +956,31 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int e = 0; e < 8; ++e) hi[e] = lo[e] = __float2half_rn(0.0f);
         if (k0 < Kdim) {
-            const int4 qv = __ldg(reinterpret_cast<const int4*>(table) + (k0 >> 4));
-            const QSlice q{qv.x, qv.y, qv.z, qv.w};
+            // ab[k] = a | b << 16 (0xffffffff: padding), decoded once per call by quad_ab_table_kernel
+            const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(ab + k0));
+            const uint4 t1 = __ldg(reinterpret_cast<const uint4*>(ab + k0 + 4));
+            const uint32_t tb[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                int64_t a = 0, b = 0;
-                if (quad_slice_ab(q, (int)((k0 & 15) + e), a, b) && a < T && b < T)
-                    split_f16(qa_sm[a * 129 + r] * qa_sm[b * 129 + r] * sc, hi[e], lo[e]);
-            }
+            for (int e = 0; e < 8; ++e)
+                if (tb[e] != 0xffffffffu)
+                    split_f16(qa_sm[(tb[e] & 0xffffu) * 129 + r] * qa_sm[(tb[e] >> 16) * 129 + r] * sc, hi[e], lo[e]);
         }
         __half* blk = out + (tile * nst + st) * (int64_t)(TC_BLOCK_BYTES / 2);
         const int64_t o = (chunk * 128 + r) * 8;
         *reinterpret_cast<uint4*>(blk + o) = *reinterpret_cast<const uint4*>(hi);
         *reinterpret_cast<uint4*>(blk + 8 * 128 * 8 + o) = *reinterpret_cast<const uint4*>(lo);
     }
+}
+__global__ void quad_ab_table_kernel(const QSlice* __restrict__ table, int64_t Kdim, int64_t Kp, int64_t T,
+                                     uint32_t* __restrict__ ab) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Kp) return;
+    uint32_t v = 0xffffffffu;
+    if (k < Kdim) {
+        int64_t a = 0, b = 0;
+        if (quad_slice_ab(table[k >> 4], (int)(k & 15), a, b) && a < T && b < T) v = (uint32_t)a | ((uint32_t)b << 16);
+    }
+    ab[k] = v;
 }
 __global__ void quad_colmax_kernel(const double* __restrict__ Bpack, int64_t Kdim, int64_t Sp,
                                    double* __restrict__ colmax) {
@@ -1018,7 +1031,8 @@ int64_t quad_screen_a_bytes(int64_t nc, int64_t Kdim) {
     return align_up(((nc + 127) / 128) * (quad_screen_kp(Kdim) / TC_BK) * (int64_t)TC_BLOCK_BYTES, 256) + align_up(nc * 8, 256);
 }
 int64_t quad_screen_b_bytes(int64_t Kdim) {
-    return align_up((quad_screen_kp(Kdim) / TC_BK) * (int64_t)TC_BLOCK_BYTES, 256) + 2 * align_up(128 * 8, 256);
+    return align_up((quad_screen_kp(Kdim) / TC_BK) * (int64_t)TC_BLOCK_BYTES, 256) + 2 * align_up(128 * 8, 256) +
+           align_up(quad_screen_kp(Kdim) * 4, 256);
 }
 // Btc layout: [operand blocks][colmax (128)][colscale (128)]
 int launch_quad_screen_build_b(const double* Bpack, int64_t Kdim, int64_t Sp, void* Btc, double* colmax, cudaStream_t st) {
@@ -1030,6 +1044,14 @@ int launch_quad_screen_build_b(const double* Bpack, int64_t Kdim, int64_t Sp, vo
     quad_build_b_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Bpack, Kdim, Kp, Sp, colmax, (__half*)Btc);
     TES_LAUNCH_OK();
     quad_scales_kernel<<<1, 128, 0, st>>>(colmax, 0, nullptr, colmax, Sp, colscale);
+    TES_LAUNCH_OK();
+    return 0;
+}
+// (a, b) table of the K axis, stored behind colmax / colscale in the B region
+int launch_quad_screen_ab(const QSlice* table, int64_t Kdim, int64_t T, double* colmax, cudaStream_t st) {
+    const int64_t Kp = quad_screen_kp(Kdim);
+    uint32_t* ab = reinterpret_cast<uint32_t*>(colmax + 256);
+    quad_ab_table_kernel<<<(unsigned)((Kp + 255) / 256), 256, 0, st>>>(table, Kdim, Kp, T, ab);
     TES_LAUNCH_OK();
     return 0;
 }
@@ -1046,7 +1068,8 @@ int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, cons
         const size_t smem = (size_t)T * 129 * sizeof(float);
         if (smem > 200 * 1024) return -5;
         TES_CUDA_OK(cudaFuncSetAttribute(quad_build_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        quad_build_a_kernel<<<dim3((unsigned)ntu, 6), 256, smem, st>>>(G, ldg, nc, T, table, Kdim, Kp, rowmax, (__half*)Atc);
+        const uint32_t* ab = reinterpret_cast<const uint32_t*>(colmax + 256);
+        quad_build_a_kernel<<<dim3((unsigned)ntu, 6), 256, smem, st>>>(G, ldg, nc, T, ab, Kdim, Kp, rowmax, (__half*)Atc);
         TES_LAUNCH_OK();
     }
     quad_scales_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(rowmax, nc, rowscale, nullptr, 0, nullptr);
@@ -1179,11 +1202,11 @@ __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const 
         const double u = 1.1102230246251565e-16;
         double B = 2.0 * u * scale * sa * (4.0 * (d + 2) * 3.141592653589793 * am + 3.0 * (double)F + 16.0) + 1e-300;
         // 3xTF32 screen: every operand is sincosf of the fp64-reduced argument (argument rounding 2^-22.3, sincosf 2 ulp
-        // = 2^-22) carried as a hi + lo TF32 pair (residual 2^-21): <= 2^-20 per operand, plus the dropped lo*lo
-        // (2^-22): <= 2.5 * 2^-20 per term; fp32 accumulation in segments of PT_FLUSH k = 3 * PT_FLUSH / 8 mma steps,
+        // = 2^-22; the tcgen05 build uses __sincosf: 2^-21) carried as a hi + lo pair (residual 2^-21): <= 2^-19 per
+        // operand pair, plus the dropped lo*lo (2^-22): <= 4.5 * 2^-20 per term; fp32 accumulation in segments of PT_FLUSH k = 3 * PT_FLUSH / 8 mma steps,
         // each assumed to err by <= 4 * 2^-24 of the segment's sum of |terms| (the tests compare against the fp64 GEMM
         // path on ties 1e-13 ... 1e-4 apart); the |terms| of a feature sum to <= |theta_f|.  x1.5 margin.
-        if (tf32) B += 1.5 * scale * sa * (2.5 * 9.5367431640625e-07 + 4.0 * 5.9604644775390625e-08 * 3.0 * (PT_FLUSH / 8));
+        if (tf32) B += 1.5 * scale * sa * (4.5 * 9.5367431640625e-07 + 4.0 * 5.9604644775390625e-08 * 3.0 * (PT_FLUSH / 8));
         // fp16 operands (mode 2; same 11-bit significand as TF32, theta normalised by tmax): subnormal rounding adds an
         // absolute 2^-25 per operand, i.e. <= 2 * 2^-25 per term over 2F terms, in units of scale * tmax
         if (tf32 >= 2) B += 1.5 * scale * tmax[j] * 4.0 * (double)F * 2.98023223876953125e-08;
