@@ -20,6 +20,8 @@
 // is bit-identical to tes_rff_topk_f64 in every case.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "gemm.cuh"
 #include "gp.cuh"
 
@@ -1026,6 +1028,198 @@ __global__ void quad_scales_kernel(const double* __restrict__ rowmax, int64_t nc
     if (colscale && t < Sp) colscale[t] = colmax[t] / QS_BMAX;
 }
 
+// ---- fused variant: the A operand never leaves the SM -------------------------------------------------------------
+// Persistent CTAs, one 128-row tile at a time.  M[128][T] (pre-scaled by 64 / rowmax, so products stay below QS_AMAX)
+// sits in shared memory as floats next to the (a, b) table; the 16 epilogue warps GENERATE each 64-k stage of A
+// (products, hi/lo split, MMA layout) straight into the stage buffer (generic-proxy stores + fence.proxy.async), the
+// producer warp only streams B, the MMA warp waits for both.  Every fourth stage the same warps drain the finished
+// 256-k segment from TMEM into their fp64 sums.  Saves the 625 MB per chunk that the unfused path writes to and reads
+// back from HBM, and its build kernel.
+constexpr int QF_NS = 2;
+__host__ __device__ inline int64_t qf_msm_floats(int64_t T) { return ((T + 1) * 129 + 3) & ~(int64_t)3; }
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    quad_screen_fused_kernel(const double* __restrict__ G, int64_t ldg, int64_t nc, int64_t T,
+                             const uint32_t* __restrict__ ab, int64_t Kdim, const __half* __restrict__ Bt, int64_t Sp,
+                             int64_t nst, int64_t ntu, const double* __restrict__ rowmax,
+                             const double* __restrict__ colscale, double* __restrict__ Qout) {
+    extern __shared__ __align__(1024) unsigned char qf_smem_raw[];
+    unsigned char* stages = qf_smem_raw;                                            // [QF_NS][A block | B block]
+    float* msm = reinterpret_cast<float*>(qf_smem_raw + QF_NS * TC_STAGE_BYTES);    // [T + 1][129], row T = 0
+    uint32_t* tab = reinterpret_cast<uint32_t*>(msm + qf_msm_floats(T));            // [nst * 64] (129 a | 129 b << 16)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tab + nst * TC_BK);
+    uint64_t* full_b = bars;                 // [2] producer (B block landed) -> MMA
+    uint64_t* a_full = bars + QF_NS;         // [2] generators (A block written) -> MMA
+    uint64_t* empty_b = bars + 2 * QF_NS;    // [2] MMA (commit) -> producer, generators
+    uint64_t* acc_full = bars + 3 * QF_NS;   // [2] MMA (commit) -> epilogue
+    uint64_t* acc_empty = acc_full + 2;      // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t nseg = nst / TC_SEG;
+    const int64_t ntile = blockIdx.x < ntu ? (ntu - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid == 0) {
+        for (int s = 0; s < QF_NS; ++s) {
+            mbar_init(&full_b[s], 1);
+            mbar_init(&a_full[s], TC_EPI_WARPS);
+            mbar_init(&empty_b[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], TC_EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    for (int64_t e = tid; e < nst * TC_BK; e += TC_THREADS) {
+        const uint32_t v = e < Kdim ? ab[e] : 0xffffffffu;
+        const uint32_t a = v == 0xffffffffu ? (uint32_t)T : (v & 0xffffu), b = v == 0xffffffffu ? (uint32_t)T : (v >> 16);
+        tab[e] = (a * 129u) | ((b * 129u) << 16);
+    }
+    for (int e = tid; e < 129; e += TC_THREADS) msm[T * 129 + e] = 0.0f;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const unsigned char* srcB = reinterpret_cast<const unsigned char*>(Bt);
+            int64_t g = 0;
+            for (int64_t it = 0; it < ntile; ++it)
+                for (int64_t st = 0; st < nst; ++st, ++g) {
+                    const uint32_t s = (uint32_t)(g % QF_NS), ph = (uint32_t)((g / QF_NS) & 1);
+                    mbar_wait_relaxed(&empty_b[s], ph ^ 1u, 32);
+                    mbar_expect_tx(&full_b[s], TC_BLOCK_BYTES);
+                    bulk_g2s(stages + s * TC_STAGE_BYTES + TC_BLOCK_BYTES, srcB + st * (int64_t)TC_BLOCK_BYTES,
+                             TC_BLOCK_BYTES, &full_b[s]);
+                }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc_f16(128, 128);
+            const uint32_t base = smem_u32(stages);
+            int64_t g = 0;
+            for (int64_t gs = 0; gs < ntile * nseg; ++gs) {
+                const uint32_t a = (uint32_t)(gs & 1), pa = (uint32_t)((gs >> 1) & 1);
+                mbar_wait_relaxed(&acc_empty[a], pa ^ 1u, 32);
+                tc_fence_after();
+                for (int q4 = 0; q4 < TC_SEG; ++q4, ++g) {
+                    const uint32_t s = (uint32_t)(g % QF_NS), ph = (uint32_t)((g / QF_NS) & 1);
+                    mbar_wait_relaxed(&full_b[s], ph, 32);
+                    mbar_wait_relaxed(&a_full[s], ph, 32);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_BLOCK_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 16; ++ks) {
+                        const uint32_t off = (uint32_t)(2 * ks) * 128u * 16u;
+                        const uint64_t a_hi = tc_desc(sa + off, 128 * 16, 128);
+                        const uint64_t a_lo = tc_desc(sa + TC_BLOCK_BYTES / 2 + off, 128 * 16, 128);
+                        const uint64_t b_hi = tc_desc(sb + off, 128 * 16, 128);
+                        const uint64_t b_lo = tc_desc(sb + TC_BLOCK_BYTES / 2 + off, 128 * 16, 128);
+                        const uint32_t first = (q4 == 0 && ks == 0) ? 0u : 1u;
+                        tc_mma_f16(tmem + a * 128u, a_lo, b_hi, idesc, first);
+                        tc_mma_f16(tmem + a * 128u, a_hi, b_lo, idesc, 1u);
+                        tc_mma_f16(tmem + a * 128u, a_hi, b_hi, idesc, 1u);
+                    }
+                    tc_commit(&empty_b[s]);
+                }
+                tc_commit(&acc_full[a]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int ew = warp - 2;
+        const int quarter = warp & 3, cb = ew >> 2;
+        const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32);
+        const int te = tid - 64, gr = te & 127, part = te >> 7;        // generator role: row gr, chunks 2 part, 2 part + 1
+        const float* mrow = msm + gr;
+        int64_t g = 0, gs = 0;
+        for (int64_t it = 0; it < ntile; ++it) {
+            const int64_t rt = blockIdx.x + it * gridDim.x;
+            // (re)load the tile of M: the 16 generator warps only; the MMAs of the previous tile may still be in flight
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            for (int64_t e = te; e < T * 128; e += 512) {
+                const int64_t rr = e / T, a = e % T;
+                const int64_t grow = rt * 128 + rr;
+                float v = 0.0f;
+                if (grow < nc) {
+                    const double rm = rowmax[grow];
+                    if (rm > 0.0) v = (float)(G[grow * ldg + a] * (64.0 / rm));     // 64^2 = QS_AMAX
+                }
+                msm[a * 129 + rr] = v;
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            double sum[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) sum[c] = 0.0;
+            for (int64_t seg = 0; seg < nseg; ++seg, ++gs) {
+                for (int q4 = 0; q4 < TC_SEG; ++q4, ++g) {
+                    const int64_t st = seg * TC_SEG + q4;
+                    const uint32_t s = (uint32_t)(g % QF_NS), ph = (uint32_t)((g / QF_NS) & 1);
+                    const uint4 tq0 = *reinterpret_cast<const uint4*>(tab + st * TC_BK + part * 16);
+                    const uint4 tq1 = *reinterpret_cast<const uint4*>(tab + st * TC_BK + part * 16 + 4);
+                    const uint4 tq2 = *reinterpret_cast<const uint4*>(tab + st * TC_BK + part * 16 + 8);
+                    const uint4 tq3 = *reinterpret_cast<const uint4*>(tab + st * TC_BK + part * 16 + 12);
+                    const uint32_t tb[16] = {tq0.x, tq0.y, tq0.z, tq0.w, tq1.x, tq1.y, tq1.z, tq1.w,
+                                             tq2.x, tq2.y, tq2.z, tq2.w, tq3.x, tq3.y, tq3.z, tq3.w};
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float p0 = mrow[tb[2 * e] & 0xffffu] * mrow[tb[2 * e] >> 16];
+                        const float p1 = mrow[tb[2 * e + 1] & 0xffffu] * mrow[tb[2 * e + 1] >> 16];
+                        const __half2 h = __floats2half2_rn(p0, p1);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+                        hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+                        lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
+                    mbar_wait(&empty_b[s], ph ^ 1u);
+                    unsigned char* ablk = stages + s * TC_STAGE_BYTES;
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const uint32_t o = (uint32_t)((2 * part + cc) * 128 + gr) * 16u;
+                        *reinterpret_cast<uint4*>(ablk + o) = make_uint4(hi[4 * cc], hi[4 * cc + 1], hi[4 * cc + 2], hi[4 * cc + 3]);
+                        *reinterpret_cast<uint4*>(ablk + TC_BLOCK_BYTES / 2 + o) =
+                            make_uint4(lo[4 * cc], lo[4 * cc + 1], lo[4 * cc + 2], lo[4 * cc + 3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to the MMA
+                    __syncwarp();
+                    if (lane == 0) tc_arrive(&a_full[s]);
+                }
+                const uint32_t a = (uint32_t)(gs & 1), pa = (uint32_t)((gs >> 1) & 1);
+                mbar_wait(&acc_full[a], pa);
+                tc_fence_after();
+                uint32_t v0[32];
+                TC_LD32(v0, t_lane + a * 128u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc_arrive(&acc_empty[a]);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) sum[c] += (double)__uint_as_float(v0[c]);
+            }
+            const int64_t row = rt * 128 + quarter * 32 + lane;
+            if (row < nc) {
+                const double rm = rowmax[row];
+                const double rs = rm * rm / QS_AMAX;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (cb * 32 + c < Sp) Qout[row * Sp + cb * 32 + c] = rs * colscale[cb * 32 + c] * sum[c];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+    }
+}
+
 int64_t quad_screen_kp(int64_t Kdim) { return (Kdim + 255) / 256 * 256; }
 int64_t quad_screen_a_bytes(int64_t nc, int64_t Kdim) {
     return align_up(((nc + 127) / 128) * (quad_screen_kp(Kdim) / TC_BK) * (int64_t)TC_BLOCK_BYTES, 256) + align_up(nc * 8, 256);
@@ -1064,6 +1258,25 @@ int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, cons
     const double* colscale = colmax + 128;
     quad_rowmax_kernel<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(G, ldg, nc, T, rowmax);
     TES_LAUNCH_OK();
+    {
+        // fused kernel (A generated on the SM) whenever M's tile fits beside two stages; TES_QUAD_FUSED=0 disables it
+        const size_t fsm = (size_t)QF_NS * TC_STAGE_BYTES + (size_t)qf_msm_floats(T) * sizeof(float) +
+                           (size_t)nst * TC_BK * sizeof(uint32_t) + 256;
+        const char* env = getenv("TES_QUAD_FUSED");
+        if (fsm <= 227 * 1024 && T <= 500 && !(env && env[0] == '0')) {
+            const uint32_t* ab = reinterpret_cast<const uint32_t*>(colmax + 256);
+            int dev = 0, sms = 148;
+            TES_CUDA_OK(cudaGetDevice(&dev));
+            TES_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            TES_CUDA_OK(cudaFuncSetAttribute(quad_screen_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)fsm));
+            const unsigned grid = (unsigned)(ntu < sms ? ntu : sms);
+            quad_screen_fused_kernel<<<grid, TC_THREADS, fsm, st>>>(G, ldg, nc, T, ab, Kdim, (const __half*)Btc, Sp, nst, ntu,
+                                                                   rowmax, colscale, Qout);
+            TES_LAUNCH_OK();
+            return 0;
+        }
+    }
     {
         const size_t smem = (size_t)T * 129 * sizeof(float);
         if (smem > 200 * 1024) return -5;
