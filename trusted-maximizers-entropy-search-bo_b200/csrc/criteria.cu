@@ -700,8 +700,9 @@ __global__ void ep_det_screen_kernel(const double* __restrict__ Qt, const double
 extern "C" int64_t tes_ep_acq_screen_workspace_bytes(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp) {
     if (N < 0 || T < 1 || n < 1 || d < 1 || Sp < 1 || Sp > 128) return -1;
     EpPlan pl = ep_plan(N, T, n, d, Sp);
-    return pl.total + quad_screen_a_bytes(pl.nc, pl.Kdim) + quad_screen_b_bytes(pl.Kdim) + align_up(pl.nc * 8, 256) +
-           align_up(T * Sp * 8, 256) + align_up(pl.nc * T * 8, 256);
+    const int64_t Ks = quad_screen_kdim(T);
+    return pl.total + quad_screen_a_bytes(pl.nc, Ks) + quad_screen_b_bytes(Ks) + align_up(pl.nc * 8, 256) +
+           align_up(T * Sp * 8, 256) + align_up(pl.nc * T * 8, 256) + align_up(Ks * Sp * 8, 256);
 }
 
 extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, const double* test_xs, int64_t T,
@@ -729,37 +730,31 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
     double* Bext = (double*)(base + pl.off_bext);
     double* Kc = (double*)(base + pl.off_kc);
     double* Gc = (double*)(base + pl.off_gc);
-    QSlice* table = (QSlice*)(base + pl.off_table);
-    double* Bpack = (double*)(base + pl.off_bpack);
     double* varc = (double*)(base + pl.off_var);
     double* Kq = (double*)(base + pl.off_kq);
     double* Gobs = (double*)(base + pl.off_gobs);
     double* varf = (double*)(base + pl.off_varf);
     char* extra = base + pl.total;
     void* Atc = extra;
-    extra += quad_screen_a_bytes(pl.nc, pl.Kdim);
+    const int64_t Ks = quad_screen_kdim(T);      // the screen's own K axis (run order), not the DMMA slice table's
+    extra += quad_screen_a_bytes(pl.nc, Ks);
     void* Btc = extra;
-    double* colmax = (double*)(extra + align_up((quad_screen_kp(pl.Kdim) / 64) * (int64_t)(2 * 8 * 128 * 16), 256));
-    extra += quad_screen_b_bytes(pl.Kdim);
+    double* colmax = (double*)(extra + align_up((quad_screen_kp(Ks) / 64) * (int64_t)(2 * 8 * 128 * 16), 256));
+    extra += quad_screen_b_bytes(Ks);
     double* rowmax = (double*)extra;
     extra += align_up(pl.nc * 8, 256);
     double* Dm = (double*)extra;
     extra += align_up(T * Sp * 8, 256);
     double* absM = (double*)extra;
+    extra += align_up(pl.nc * T * 8, 256);
+    double* Bscr = (double*)extra;                   // Ks x Sp
     double* Hb = (double*)(base + pl.off_mean);      // nc x Sp (the mean buffer is unused in this mode)
     const int64_t m = pl.m;
     int rc;
     if ((rc = launch_concat_rows(test_xs, T, X, n, (int)d, xto, st))) return rc;
     if ((rc = launch_build_bext(invpNK, Y, m, T, Bext, st))) return rc;
-    quad_slice_table_kernel<<<1, 32, 0, st>>>((int)pl.nb, table);
-    TES_LAUNCH_OK();
-    {
-        int64_t tot = pl.Kdim * Sp;
-        quad_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(post_cov, Sp, T, table, pl.Kdim, Bpack);
-        TES_LAUNCH_OK();
-    }
-    if ((rc = launch_quad_screen_build_b(Bpack, pl.Kdim, Sp, Btc, colmax, st))) return rc;
-    if ((rc = launch_quad_screen_ab(table, pl.Kdim, T, colmax, st))) return rc;
+    if ((rc = launch_quad_screen_ab(post_cov, Sp, T, colmax, Bscr, st))) return rc;
+    if ((rc = launch_quad_screen_build_b(Bscr, Ks, Sp, Btc, colmax, st))) return rc;
     sqrt_diag_kernel<<<(unsigned)((T * Sp + 255) / 256), 256, 0, st>>>(post_cov, Sp, T, Dm);
     TES_LAUNCH_OK();
     for (int64_t c0 = 0; c0 < N; c0 += PS_CHUNK) {
@@ -767,7 +762,7 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
         if ((rc = launch_se_ard(x + c0 * d, nc, xto, m, (int)d, l, sigma, -1, 0.0, Kc, m, st))) return rc;
         if ((rc = launch_gemm(Kc, m, Bext, m + 1, 1, Gc, m + 1, nc, m + 1, m, st))) return rc;
         if ((rc = launch_rowdot(Gc, m + 1, Kc, m, nc, m, sigma, -INFINITY, Kq, st))) return rc;
-        if ((rc = launch_quad_screen(Gc, m + 1, nc, T, table, pl.Kdim, Btc, colmax, Sp, Atc, rowmax, varc, st))) return rc;
+        if ((rc = launch_quad_screen(Gc, m + 1, nc, T, Ks, Btc, colmax, Sp, Atc, rowmax, varc, st))) return rc;
         if ((rc = launch_gemm(Kc + T, m, invKobs, n, 1, Gobs, n, nc, n, n, st))) return rc;
         if ((rc = launch_rowdot(Gobs, n, Kc + T, m, nc, n, sigma, 1e-100, varf, st))) return rc;
         abs_rows_kernel<<<(unsigned)((nc * T + 255) / 256), 256, 0, st>>>(Gc, m + 1, nc, T, absM);

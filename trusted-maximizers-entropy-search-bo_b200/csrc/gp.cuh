@@ -65,8 +65,8 @@ int64_t quad_screen_kp(int64_t Kdim);                                   // K pad
 int64_t quad_screen_a_bytes(int64_t nc, int64_t Kdim);                  // operand A of one candidate chunk
 int64_t quad_screen_b_bytes(int64_t Kdim);                              // operand B (all maximizers, <= 128)
 int launch_quad_screen_build_b(const double* Bpack, int64_t Kdim, int64_t Sp, void* Btc, double* colmax, cudaStream_t st);
-int launch_quad_screen_ab(const QSlice* table, int64_t Kdim, int64_t T, double* colmax, cudaStream_t st);
-int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, const QSlice* table, int64_t Kdim,
-                       const void* Btc, const double* colmax, int64_t Sp, void* Atc, double* rowmax, double* Qout,
-                       cudaStream_t st);
+int64_t quad_screen_kdim(int64_t T);                                    // K of the screen (run order, see rffprod.cu)
+int launch_quad_screen_ab(const double* cov, int64_t Sp, int64_t T, double* colmax, double* Bpack, cudaStream_t st);
+int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, int64_t Kdim, const void* Btc,
+                       const double* colmax, int64_t Sp, void* Atc, double* rowmax, double* Qout, cudaStream_t st);
 }  // namespace tes

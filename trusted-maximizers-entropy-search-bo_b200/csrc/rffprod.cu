@@ -973,16 +973,32 @@ __global__ void __launch_bounds__(256)
         *reinterpret_cast<uint4*>(blk + 8 * 128 * 8 + o) = *reinterpret_cast<const uint4*>(lo);
     }
 }
-__global__ void quad_ab_table_kernel(const QSlice* __restrict__ table, int64_t Kdim, int64_t Kp, int64_t T,
-                                     uint32_t* __restrict__ ab) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= Kp) return;
-    uint32_t v = 0xffffffffu;
-    if (k < Kdim) {
-        int64_t a = 0, b = 0;
-        if (quad_slice_ab(table[k >> 4], (int)(k & 15), a, b) && a < T && b < T) v = (uint32_t)a | ((uint32_t)b << 16);
+// K axis of the screen in RUN order: for a = 0 .. T-1 the pairs (a, b), b = a .. T-1, each run padded with empty entries
+// to a multiple of 8 -- every 8-k operand chunk has one a and consecutive b (what the fused kernel's generators exploit)
+__global__ void quad_ab_runs_kernel(int64_t T, int64_t Kp, uint32_t* __restrict__ ab) {
+    for (int64_t k = threadIdx.x; k < Kp; k += blockDim.x) ab[k] = 0xffffffffu;
+    __syncthreads();
+    for (int64_t a = threadIdx.x; a < T; a += blockDim.x) {
+        int64_t off = 0;
+        for (int64_t a2 = 0; a2 < a; ++a2) off += (T - a2 + 7) / 8 * 8;
+        for (int64_t b = a; b < T; ++b) ab[off + b - a] = (uint32_t)a | ((uint32_t)b << 16);
     }
-    ab[k] = v;
+}
+// Bpack[k][j] = Sigma_j[a][a] (a = b), Sigma_j[a][b] + Sigma_j[b][a] (a < b), 0 (padding)
+__global__ void quad_pack_ab_kernel(const double* __restrict__ cov, int64_t Sp, int64_t T, const uint32_t* __restrict__ ab,
+                                    int64_t Kdim, double* __restrict__ Bpack) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Kdim * Sp) return;
+    const int64_t k = e / Sp, j = e % Sp;
+    const uint32_t v = ab[k];
+    double r = 0.0;
+    if (v != 0xffffffffu) {
+        const int64_t a = v & 0xffffu, b = v >> 16;
+        const double* c = cov + j * T * T;
+        r = c[a * T + b];
+        if (a != b) r += c[b * T + a];
+    }
+    Bpack[e] = r;
 }
 __global__ void quad_colmax_kernel(const double* __restrict__ Bpack, int64_t Kdim, int64_t Sp,
                                    double* __restrict__ colmax) {
@@ -1036,7 +1052,7 @@ __global__ void quad_scales_kernel(const double* __restrict__ rowmax, int64_t nc
 // 256-k segment from TMEM into their fp64 sums.  Saves the 625 MB per chunk that the unfused path writes to and reads
 // back from HBM, and its build kernel.
 constexpr int QF_NS = 2;
-__host__ __device__ inline int64_t qf_msm_floats(int64_t T) { return ((T + 1) * 129 + 3) & ~(int64_t)3; }
+__host__ __device__ inline int64_t qf_msm_floats(int64_t T) { return ((T + 8) * 129 + 3) & ~(int64_t)3; }
 __global__ void __launch_bounds__(TC_THREADS, 1)
     quad_screen_fused_kernel(const double* __restrict__ G, int64_t ldg, int64_t nc, int64_t T,
                              const uint32_t* __restrict__ ab, int64_t Kdim, const __half* __restrict__ Bt, int64_t Sp,
@@ -1044,9 +1060,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                              const double* __restrict__ colscale, double* __restrict__ Qout) {
     extern __shared__ __align__(1024) unsigned char qf_smem_raw[];
     unsigned char* stages = qf_smem_raw;                                            // [QF_NS][A block | B block]
-    float* msm = reinterpret_cast<float*>(qf_smem_raw + QF_NS * TC_STAGE_BYTES);    // [T + 1][129], row T = 0
-    uint32_t* tab = reinterpret_cast<uint32_t*>(msm + qf_msm_floats(T));            // [nst * 64] (129 a | 129 b << 16)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tab + nst * TC_BK);
+    float* msm = reinterpret_cast<float*>(qf_smem_raw + QF_NS * TC_STAGE_BYTES);    // [T + 8][129], rows T.. = 0
+    uint2* dsc = reinterpret_cast<uint2*>(msm + qf_msm_floats(T));    // [nst * 8] byte offsets of rows a, b0 per chunk
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dsc + nst * 8);
     uint64_t* full_b = bars;                 // [2] producer (B block landed) -> MMA
     uint64_t* a_full = bars + QF_NS;         // [2] generators (A block written) -> MMA
     uint64_t* empty_b = bars + 2 * QF_NS;    // [2] MMA (commit) -> producer, generators
@@ -1068,12 +1084,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         mbar_fence_init();
     }
-    for (int64_t e = tid; e < nst * TC_BK; e += TC_THREADS) {
-        const uint32_t v = e < Kdim ? ab[e] : 0xffffffffu;
+    // run order (launch_quad_screen_ab): the 8 entries of a chunk are (a, b0), (a, b0 + 1), ... or padding; rows
+    // T .. T + 7 of the tile are zero, so padding needs no test
+    for (int64_t c = tid; c < nst * 8; c += TC_THREADS) {
+        const uint32_t v = c * 8 < Kdim ? ab[c * 8] : 0xffffffffu;
         const uint32_t a = v == 0xffffffffu ? (uint32_t)T : (v & 0xffffu), b = v == 0xffffffffu ? (uint32_t)T : (v >> 16);
-        tab[e] = (a * 129u) | ((b * 129u) << 16);
+        dsc[c] = make_uint2(a * 129u * 4u, b * 129u * 4u);
     }
-    for (int e = tid; e < 129; e += TC_THREADS) msm[T * 129 + e] = 0.0f;
+    for (int e = tid; e < 8 * 129; e += TC_THREADS) msm[T * 129 + e] = 0.0f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "n"(256));
@@ -1136,7 +1154,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int quarter = warp & 3, cb = ew >> 2;
         const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32);
         const int te = tid - 64, gr = te & 127, part = te >> 7;        // generator role: row gr, chunks 2 part, 2 part + 1
-        const float* mrow = msm + gr;
+        const unsigned char* mrow = reinterpret_cast<const unsigned char*>(msm + gr);
         int64_t g = 0, gs = 0;
         for (int64_t it = 0; it < ntile; ++it) {
             const int64_t rt = blockIdx.x + it * gridDim.x;
@@ -1156,26 +1174,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             double sum[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) sum[c] = 0.0;
-            for (int64_t seg = 0; seg < nseg; ++seg, ++gs) {
+            auto drain = [&](int64_t dseg) {
+                const uint32_t a = (uint32_t)(dseg & 1), pa = (uint32_t)((dseg >> 1) & 1);
+                mbar_wait(&acc_full[a], pa);
+                tc_fence_after();
+                uint32_t v0[32];
+                TC_LD32(v0, t_lane + a * 128u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc_arrive(&acc_empty[a]);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) sum[c] += (double)__uint_as_float(v0[c]);
+            };
+            for (int64_t seg = 0; seg < nseg; ++seg) {
                 for (int q4 = 0; q4 < TC_SEG; ++q4, ++g) {
                     const int64_t st = seg * TC_SEG + q4;
                     const uint32_t s = (uint32_t)(g % QF_NS), ph = (uint32_t)((g / QF_NS) & 1);
-                    const uint4 tq0 = *reinterpret_cast<const uint4*>(tab + st * TC_BK + part * 16);
-                    const uint4 tq1 = *reinterpret_cast<const uint4*>(tab + st * TC_BK + part * 16 + 4);
-                    const uint4 tq2 = *reinterpret_cast<const uint4*>(tab + st * TC_BK + part * 16 + 8);
-                    const uint4 tq3 = *reinterpret_cast<const uint4*>(tab + st * TC_BK + part * 16 + 12);
-                    const uint32_t tb[16] = {tq0.x, tq0.y, tq0.z, tq0.w, tq1.x, tq1.y, tq1.z, tq1.w,
-                                             tq2.x, tq2.y, tq2.z, tq2.w, tq3.x, tq3.y, tq3.z, tq3.w};
                     uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float p0 = mrow[tb[2 * e] & 0xffffu] * mrow[tb[2 * e] >> 16];
-                        const float p1 = mrow[tb[2 * e + 1] & 0xffffu] * mrow[tb[2 * e + 1] >> 16];
-                        const __half2 h = __floats2half2_rn(p0, p1);
-                        const float2 hf = __half22float2(h);
-                        const __half2 l = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
-                        hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-                        lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const uint2 ds = dsc[st * 8 + 2 * part + cc];
+                        const float ma = *reinterpret_cast<const float*>(mrow + ds.x);
+                        const unsigned char* pb = mrow + ds.y;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float p0 = ma * *reinterpret_cast<const float*>(pb + (2 * e) * 516);
+                            const float p1 = ma * *reinterpret_cast<const float*>(pb + (2 * e + 1) * 516);
+                            const __half2 h = __floats2half2_rn(p0, p1);
+                            const float2 hf = __half22float2(h);
+                            const __half2 l = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+                            hi[4 * cc + e] = *reinterpret_cast<const uint32_t*>(&h);
+                            lo[4 * cc + e] = *reinterpret_cast<const uint32_t*>(&l);
+                        }
                     }
                     mbar_wait(&empty_b[s], ph ^ 1u);
                     unsigned char* ablk = stages + s * TC_STAGE_BYTES;
@@ -1190,18 +1221,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     __syncwarp();
                     if (lane == 0) tc_arrive(&a_full[s]);
                 }
-                const uint32_t a = (uint32_t)(gs & 1), pa = (uint32_t)((gs >> 1) & 1);
-                mbar_wait(&acc_full[a], pa);
-                tc_fence_after();
-                uint32_t v0[32];
-                TC_LD32(v0, t_lane + a * 128u);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc_arrive(&acc_empty[a]);
-#pragma unroll
-                for (int c = 0; c < 32; ++c) sum[c] += (double)__uint_as_float(v0[c]);
+                // drain the PREVIOUS segment: its MMAs were issued a segment ago, so this wait is (nearly) free and
+                // the tensor pipe keeps running on the stages just generated
+                ++gs;
+                if (seg > 0) drain(gs - 2);
             }
+            drain(gs - 1);
             const int64_t row = rt * 128 + quarter * 32 + lane;
             if (row < nc) {
                 const double rm = rowmax[row];
@@ -1241,18 +1266,25 @@ int launch_quad_screen_build_b(const double* Bpack, int64_t Kdim, int64_t Sp, vo
     TES_LAUNCH_OK();
     return 0;
 }
-// (a, b) table of the K axis, stored behind colmax / colscale in the B region
-int launch_quad_screen_ab(const QSlice* table, int64_t Kdim, int64_t T, double* colmax, cudaStream_t st) {
-    const int64_t Kp = quad_screen_kp(Kdim);
+int64_t quad_screen_kdim(int64_t T) {
+    int64_t k = 0;
+    for (int64_t a = 0; a < T; ++a) k += (T - a + 7) / 8 * 8;
+    return k;
+}
+// (a, b) table of the K axis (run order), stored behind colmax / colscale in the B region; Bpack in the same order
+int launch_quad_screen_ab(const double* cov, int64_t Sp, int64_t T, double* colmax, double* Bpack, cudaStream_t st) {
+    if (T > 0xffff) return -5;
+    const int64_t Kdim = quad_screen_kdim(T), Kp = quad_screen_kp(Kdim);
     uint32_t* ab = reinterpret_cast<uint32_t*>(colmax + 256);
-    quad_ab_table_kernel<<<(unsigned)((Kp + 255) / 256), 256, 0, st>>>(table, Kdim, Kp, T, ab);
+    quad_ab_runs_kernel<<<1, 256, 0, st>>>(T, Kp, ab);
+    TES_LAUNCH_OK();
+    quad_pack_ab_kernel<<<(unsigned)((Kdim * Sp + 255) / 256), 256, 0, st>>>(cov, Sp, T, ab, Kdim, Bpack);
     TES_LAUNCH_OK();
     return 0;
 }
 // Atc: [operand blocks of the chunk][rowscale (nc)]; rowmax: nc doubles of scratch
-int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, const QSlice* table, int64_t Kdim,
-                       const void* Btc, const double* colmax, int64_t Sp, void* Atc, double* rowmax, double* Qout,
-                       cudaStream_t st) {
+int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, int64_t Kdim, const void* Btc,
+                       const double* colmax, int64_t Sp, void* Atc, double* rowmax, double* Qout, cudaStream_t st) {
     const int64_t Kp = quad_screen_kp(Kdim), nst = Kp / TC_BK, ntu = (nc + 127) / 128;
     double* rowscale = (double*)((char*)Atc + align_up(ntu * nst * (int64_t)TC_BLOCK_BYTES, 256));
     const double* colscale = colmax + 128;
@@ -1261,7 +1293,7 @@ int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, cons
     {
         // fused kernel (A generated on the SM) whenever M's tile fits beside two stages; TES_QUAD_FUSED=0 disables it
         const size_t fsm = (size_t)QF_NS * TC_STAGE_BYTES + (size_t)qf_msm_floats(T) * sizeof(float) +
-                           (size_t)nst * TC_BK * sizeof(uint32_t) + 256;
+                           (size_t)nst * 8 * sizeof(uint2) + 256;
         const char* env = getenv("TES_QUAD_FUSED");
         if (fsm <= 227 * 1024 && T <= 500 && !(env && env[0] == '0')) {
             const uint32_t* ab = reinterpret_cast<const uint32_t*>(colmax + 256);
