@@ -692,49 +692,58 @@ __global__ void __launch_bounds__(256)
     const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
     const int64_t ir = tile * 128 + r;
     const int64_t j = j0 + g, jw = w_shared ? 0 : j;
-    // coordinate slots: the columns this side uses, in order
-    int cols[16], ncol = 0;
-    if (which == 0) {
-        for (int k = s_lo; k < s_hi; ++k) cols[ncol++] = k;
-    } else {
-        for (int k = 0; k < s_lo; ++k) cols[ncol++] = k;
-        for (int k = s_hi; k < d; ++k) cols[ncol++] = k;
-    }
+    // coordinate slots: the columns this side uses, in order (arithmetic, not a table: a runtime-indexed array would
+    // live in local memory and put an LDL in front of every DFMA)
+    const int ncol = which == 0 ? s_hi - s_lo : d - (s_hi - s_lo);
+    auto col_of = [&](int c) { return which == 0 ? s_lo + c : (c < s_lo ? c : c + (s_hi - s_lo)); };
     for (int e = threadIdx.x; e < ncol * 128; e += 256) {
         const int c = e / 128, rr = e % 128;
         const int64_t gr = tile * 128 + rr;
-        xs[c][rr] = gr < nrow ? cand[(gr * row_stride) * d + cols[c]] : 0.0;
+        xs[c][rr] = gr < nrow ? cand[(gr * row_stride) * d + col_of(c)] : 0.0;
     }
     __syncthreads();
     const double tm = which == 0 ? tmax[j] : 1.0;
+    const double inv_tm = tm > 0.0 ? 1.0 / tm : 0.0;
     const int64_t nkc = nst * (TC_BK / 8);
     const int64_t kc_lo = nkc * blockIdx.z / gridDim.z, kc_hi = nkc * (blockIdx.z + 1) / gridDim.z;
     for (int64_t kc = kc_lo + half; kc < kc_hi; kc += 2) {
         const int64_t st = kc / (TC_BK / 8), chunk = kc % (TC_BK / 8);
         __align__(16) __half hi[8], lo[8];
+        // the four features of the chunk are evaluated together, branch-free (out-of-range features / rows are clamped
+        // for the loads and zeroed at the end), so their dependent chains -- W from L2, the fp64 dot and reduction, the
+        // MUFU pair, the splits -- overlap instead of running back to back
+        const double* w[4];
+        double a[4], th[4];
+        bool ok[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) hi[e] = lo[e] = __float2half_rn(0.0f);
-        if (ir < nrow) {
+        for (int q = 0; q < 4; ++q) {
+            const int64_t f = kc * 4 + q;
+            ok[q] = f < F && ir < nrow;
+            const int64_t fc = f < F ? f : F - 1;
+            w[q] = W + (jw * F + fc) * d;
+            a[q] = which == 0 ? __ldg(b + jw * F + fc) : 0.0;
+            th[q] = which == 0 ? __ldg(theta + j * F + fc) * inv_tm : 0.0;
+        }
+        for (int c = 0; c < ncol; ++c) {
+            const double x = xs[c][r];
+            const int cc = col_of(c);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int64_t f = kc * 4 + q;
-                if (f >= F) break;
-                const double* w = W + (jw * F + f) * d;
-                double a = which == 0 ? b[jw * F + f] : 0.0;
-                for (int c = 0; c < ncol; ++c) a = fma(__ldg(w + cols[c]), xs[c][r], a);
-                // argument reduced to [-pi, pi] in fp64, then the MUFU pair (__sincosf: abs error <= 2^-21.2 there):
-                // the operand error budget of the screen (prod_exact_kernel) carries 2^-21 for it
-                float sn, cs;
-                __sincosf((float)(a - 6.283185307179586 * rint(a * 0.15915494309189535)), &sn, &cs);
-                float p0 = cs, p1 = sn;
-                if (which == 0) {
-                    const double th = tm > 0.0 ? theta[j * F + f] / tm : 0.0;
-                    p0 = (float)(th * (double)cs);
-                    p1 = (float)(-th * (double)sn);
-                }
-                split_f16(p0, hi[2 * q], lo[2 * q]);
-                split_f16(p1, hi[2 * q + 1], lo[2 * q + 1]);
+            for (int q = 0; q < 4; ++q) a[q] = fma(__ldg(w[q] + cc), x, a[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            // argument reduced to [-pi, pi] in fp64, then the MUFU pair (__sincosf: abs error <= 2^-21.2 there):
+            // the operand error budget of the screen (prod_exact_kernel) carries 2^-21 for it
+            float sn, cs;
+            __sincosf((float)(a[q] - 6.283185307179586 * rint(a[q] * 0.15915494309189535)), &sn, &cs);
+            float p0 = cs, p1 = sn;
+            if (which == 0) {
+                p0 = (float)(th[q] * (double)cs);
+                p1 = (float)(-th[q] * (double)sn);
             }
+            if (!ok[q]) p0 = p1 = 0.0f;
+            split_f16(p0, hi[2 * q], lo[2 * q]);
+            split_f16(p1, hi[2 * q + 1], lo[2 * q + 1]);
         }
         __half* blk = out + ((g * ntile + tile) * nst + st) * (int64_t)(TC_BLOCK_BYTES / 2);
         const int64_t o = (chunk * 128 + r) * 8;
