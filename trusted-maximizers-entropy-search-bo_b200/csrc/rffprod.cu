@@ -752,6 +752,16 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+static int tc_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+            sms = 148;
+    }
+    return sms;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
     prod_gemm_topk_tc_kernel(const __half* __restrict__ Pt, const __half* __restrict__ Qt, int64_t nu, int64_t nv,
                              int64_t ntu, int64_t ntv, int64_t nst, double scale0, const double* __restrict__ tmax,
@@ -769,9 +779,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     uint64_t* acc_empty = acc_full + 2;      // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t g = blockIdx.z;
-    const int64_t rt = blockIdx.x, ct = blockIdx.y;
-    const double scale = tmax ? scale0 * tmax[g] : scale0;
+    // persistent: CTA c takes tiles c, c + gridDim.x, ... of the (rt fastest, then ct, then sample g) order; the barrier
+    // phases run on across tiles, so the next tile's loads and MMAs start while the epilogue warps still rank this one
+    const int64_t ntot = ntu * ntv * G;
+    const int64_t ntile = (int64_t)blockIdx.x < ntot ? (ntot - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t nseg = nst / TC_SEG;
     if (tid == 0) {
         for (int s = 0; s < TC_NS; ++s) {
@@ -796,15 +807,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
     if (warp == 0) {
         if (lane == 0) {
+            int64_t gst = 0;
+            for (int64_t it = 0; it < ntile; ++it) {
+            const int64_t t = blockIdx.x + it * gridDim.x;
+            const int64_t rt = t % ntu, ct = (t / ntu) % ntv, g = t / (ntu * ntv);
             const unsigned char* srcA = reinterpret_cast<const unsigned char*>(Pt) + ((g * ntu + rt) * nst) * (int64_t)TC_BLOCK_BYTES;
             const unsigned char* srcB = reinterpret_cast<const unsigned char*>(Qt) + ((g * ntv + ct) * nst) * (int64_t)TC_BLOCK_BYTES;
-            for (int64_t st = 0; st < nst; ++st) {
-                const uint32_t s = (uint32_t)(st % TC_NS), ph = (uint32_t)((st / TC_NS) & 1);
+            for (int64_t st = 0; st < nst; ++st, ++gst) {
+                const uint32_t s = (uint32_t)(gst % TC_NS), ph = (uint32_t)((gst / TC_NS) & 1);
                 mbar_wait_relaxed(&empty_b[s], ph ^ 1u, 32);
                 mbar_expect_tx(&full_b[s], TC_STAGE_BYTES);
                 bulk_g2s(stages + s * TC_STAGE_BYTES, srcA + st * (int64_t)TC_BLOCK_BYTES, TC_BLOCK_BYTES, &full_b[s]);
                 bulk_g2s(stages + s * TC_STAGE_BYTES + TC_BLOCK_BYTES, srcB + st * (int64_t)TC_BLOCK_BYTES, TC_BLOCK_BYTES,
                          &full_b[s]);
+            }
             }
         }
         __syncwarp();
@@ -812,13 +828,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (lane == 0) {
             const uint32_t idesc = tc_idesc_f16(128, 128);
             const uint32_t base = smem_u32(stages);
-            for (int64_t seg = 0; seg < nseg; ++seg) {
+            int64_t gst = 0;
+            for (int64_t seg = 0; seg < ntile * nseg; ++seg) {
                 const uint32_t a = (uint32_t)(seg & 1), pa = (uint32_t)((seg >> 1) & 1);
                 mbar_wait_relaxed(&acc_empty[a], pa ^ 1u, 32);
                 tc_fence_after();
-                for (int q4 = 0; q4 < TC_SEG; ++q4) {
-                    const int64_t st = seg * TC_SEG + q4;
-                    const uint32_t s = (uint32_t)(st % TC_NS), ph = (uint32_t)((st / TC_NS) & 1);
+                for (int q4 = 0; q4 < TC_SEG; ++q4, ++gst) {
+                    const uint32_t s = (uint32_t)(gst % TC_NS), ph = (uint32_t)((gst / TC_NS) & 1);
                     mbar_wait_relaxed(&full_b[s], ph, 32);
                     tc_fence_after();
                     const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_BLOCK_BYTES;
@@ -845,11 +861,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int quarter = warp & 3;                  // TMEM lanes this warp may access
         const int cb = ew >> 2;                        // columns [32 cb, 32 cb + 32)
         const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32);
+        int64_t gseg = 0;
+        for (int64_t it = 0; it < ntile; ++it) {
+        const int64_t t = blockIdx.x + it * gridDim.x;
+        const int64_t rt = t % ntu, ct = (t / ntu) % ntv, g = t / (ntu * ntv);
+        const double scale = tmax ? scale0 * tmax[g] : scale0;
         double sum[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) sum[c] = 0.0;
-        for (int64_t seg = 0; seg < nseg; ++seg) {
-            const uint32_t a = (uint32_t)(seg & 1), pa = (uint32_t)((seg >> 1) & 1);
+        for (int64_t seg = 0; seg < nseg; ++seg, ++gseg) {
+            const uint32_t a = (uint32_t)(gseg & 1), pa = (uint32_t)((gseg >> 1) & 1);
             mbar_wait(&acc_full[a], pa);
             tc_fence_after();
             uint32_t v0[32];
@@ -872,7 +893,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     if (colb + c < nv) store_out[row * ldo + colb + c] = rs * colscale[colb + c] * sum[c];
             }
         } else {
-        const int64_t list = ((int64_t)rt * gridDim.y + ct) * TC_EPI_WARPS + ew;
+        const int64_t list = (rt * ntv + ct) * TC_EPI_WARPS + ew;
         double* ov = part_val + (list * G + g) * kp;
         int64_t* oi = part_idx + (list * G + g) * kp;
         uint32_t used = 0;
@@ -909,6 +930,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 break;
             }
             if (bc >= 0 && wi == ci0 + bc) used |= 1u << bc;   // the winning lane consumes its element
+        }
         }
         }
     }
@@ -1330,7 +1352,7 @@ int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, int6
     TES_LAUNCH_OK();
     TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(TC_NS * TC_STAGE_BYTES + 256)));
-    dim3 grid((unsigned)ntu, 1, 1);
+    dim3 grid((unsigned)(ntu < tc_sm_count() ? ntu : tc_sm_count()), 1, 1);
     prod_gemm_topk_tc_kernel<<<grid, TC_THREADS, TC_NS * TC_STAGE_BYTES + 256, st>>>(
         (const __half*)Atc, (const __half*)Btc, nc, Sp, ntu, 1, nst, 1.0, nullptr, 0, 0, 1, nullptr, nullptr, Qout, Sp,
         rowscale, colscale);
@@ -1657,7 +1679,8 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
             prod_build_tc_kernel<<<dim3((unsigned)ntv, (unsigned)G, 8), 256, 0, st>>>(
                 cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, ntv, nst, tmax, Ghi);
             TES_LAUNCH_OK();
-            dim3 gtc((unsigned)ntu, (unsigned)ntv, (unsigned)G);
+            const int64_t ntot = ntu * ntv * G;
+            dim3 gtc((unsigned)(ntot < tc_sm_count() ? ntot : tc_sm_count()), 1, 1);
             prod_gemm_topk_tc_kernel<<<gtc, TC_THREADS, TC_NS * TC_STAGE_BYTES + 256, st>>>(
                 Hhi, Ghi, nu, nv, ntu, ntv, nst, scale, tmax + j0, idx_offset, pl.kp, G, pv, pi, nullptr, 0, nullptr, nullptr);
             TES_LAUNCH_OK();
