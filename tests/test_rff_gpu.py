@@ -317,6 +317,37 @@ def test_product_path_is_bit_identical_to_the_general_kernels(axes_n, S, F, k, s
         np.testing.assert_array_equal(v2.cpu().numpy()[good], rval[good])
 
 
+@pytest.mark.parametrize("axes_n,k", [((20, 20, 21, 19), 1), ((30, 17, 23, 9), 8), ((9, 8, 130), 3)])
+def test_product_path_two_level_merge_equals_single_cta_merge(axes_n, k, monkeypatch):
+    """The partial lists of the GEMM screens are merged by prod_merge_regs_kernel (one level when they fit one CTA's
+    registers, else per-block + per-sample); TES_PROD_MERGE=0 keeps the one-CTA-per-sample kernel: same survivors, so
+    the same indices, values and flags, and both equal the C oracle."""
+    from oracle import c_oracle as co
+    from tes_b200 import ops
+    rs = np.random.RandomState(sum(axes_n) + k)
+    d = len(axes_n)
+    cand = _mesh([np.sort(rs.rand(n)) * 1.5 for n in axes_n])
+    S, F = 11, 160
+    Wn = rs.randn(S, F, d) * 1.7
+    bn = 2 * np.pi * rs.rand(S, F, 1)
+    th = rs.randn(S, F, 1)
+    det = ops.detect_product_structure(ops.dev(cand))
+    assert det is not None
+    ridx, rval = co.rff_topk(cand, Wn, bn, th, 0.8, k)
+    for tf32 in (3, 2):
+        out = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("TES_PROD_MERGE", mode)
+            i2, v2, fl = ops.rff_topk_product(cand, Wn, bn, th, 0.8, det[0], det[1], det[2], k=k, tf32=tf32)
+            out[mode] = (i2.cpu().numpy(), v2.cpu().numpy(), fl.cpu().numpy())
+        for a, b_ in zip(out["1"], out["0"]):
+            np.testing.assert_array_equal(a, b_)
+        good = out["1"][2] == 0
+        assert good.mean() > 0.5
+        np.testing.assert_array_equal(out["1"][0][good], ridx[good])
+        np.testing.assert_array_equal(out["1"][1][good], rval[good])
+
+
 def test_product_path_flags_ties_and_falls_back():
     """Exact ties (a constant sample; duplicated axis values) cannot be ranked by the GEMM values: the sample is flagged
     and recomputed by the general kernel -> lowest-index tie rule preserved."""

@@ -682,12 +682,14 @@ __host__ __device__ constexpr uint32_t tc_idesc_f16(int m, int n) {
 // One CTA per (sample, 128-row tile): the tile's coordinates are staged in shared memory, thread (row, half) walks the
 // 8-k chunks (= 4 features: weights read with block-uniform addresses), row-consecutive threads write consecutive
 // 16-byte slots of the MMA layout.
+constexpr int PB_WS_DOUBLES = 1536;
 __global__ void __launch_bounds__(256)
     prod_build_tc_kernel(const double* __restrict__ cand, int64_t nrow, int64_t row_stride, int d, int s_lo, int s_hi,
                          int which, const double* __restrict__ W, const double* __restrict__ b,
                          const double* __restrict__ theta, int64_t j0, int64_t F, int w_shared, int64_t ntile,
                          int64_t nst, const double* __restrict__ tmax, __half* __restrict__ out) {
     __shared__ double xs[16][129];                   // [coordinate slot][row]
+    __shared__ double ws[PB_WS_DOUBLES];             // [feature of the block][w (ncol), b, theta]
     const int64_t tile = blockIdx.x, g = blockIdx.y;
     const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
     const int64_t ir = tile * 128 + r;
@@ -706,49 +708,65 @@ __global__ void __launch_bounds__(256)
     const double inv_tm = tm > 0.0 ? 1.0 / tm : 0.0;
     const int64_t nkc = nst * (TC_BK / 8);
     const int64_t kc_lo = nkc * blockIdx.z / gridDim.z, kc_hi = nkc * (blockIdx.z + 1) / gridDim.z;
-    for (int64_t kc = kc_lo + half; kc < kc_hi; kc += 2) {
-        const int64_t st = kc / (TC_BK / 8), chunk = kc % (TC_BK / 8);
-        __align__(16) __half hi[8], lo[8];
-        // the four features of the chunk are evaluated together, branch-free (out-of-range features / rows are clamped
-        // for the loads and zeroed at the end), so their dependent chains -- W from L2, the fp64 dot and reduction, the
-        // MUFU pair, the splits -- overlap instead of running back to back
-        const double* w[4];
-        double a[4], th[4];
-        bool ok[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int64_t f = kc * 4 + q;
-            ok[q] = f < F && ir < nrow;
-            const int64_t fc = f < F ? f : F - 1;
-            w[q] = W + (jw * F + fc) * d;
-            a[q] = which == 0 ? __ldg(b + jw * F + fc) : 0.0;
-            th[q] = which == 0 ? __ldg(theta + j * F + fc) * inv_tm : 0.0;
+    // feature records [w (ncol), b, theta / tmax] of a block of chunks are staged in shared memory by one coalesced
+    // pass, so the chunk loop reads them as broadcast LDS instead of ~20 block-uniform LDGs from L2 per chunk in front
+    // of every dependent chain
+    const int rs = ncol + 2;
+    const int cpb = (PB_WS_DOUBLES / rs) / 4 < 32 ? (PB_WS_DOUBLES / rs) / 4 : 32;      // chunks per block
+    for (int64_t cb = kc_lo; cb < kc_hi; cb += cpb) {
+        const int64_t ce = cb + cpb < kc_hi ? cb + cpb : kc_hi;
+        const int nf = (int)(ce - cb) * 4;
+        __syncthreads();
+        for (int e = threadIdx.x; e < nf * rs; e += 256) {
+            const int fl = e / rs, c = e % rs;
+            const int64_t f = cb * 4 + fl, fc = f < F ? f : F - 1;
+            double v;
+            if (c < ncol) v = __ldg(W + (jw * F + fc) * d + col_of(c));
+            else if (c == ncol) v = which == 0 ? __ldg(b + jw * F + fc) : 0.0;
+            else v = which == 0 ? __ldg(theta + j * F + fc) * inv_tm : 0.0;
+            ws[e] = v;
         }
-        for (int c = 0; c < ncol; ++c) {
-            const double x = xs[c][r];
-            const int cc = col_of(c);
+        __syncthreads();
+        for (int64_t kc = cb + half; kc < ce; kc += 2) {
+            const int64_t st = kc / (TC_BK / 8), chunk = kc % (TC_BK / 8);
+            __align__(16) __half hi[8], lo[8];
+            // the four features of the chunk are evaluated together, branch-free (out-of-range features / rows are
+            // clamped for the loads and zeroed at the end), so their dependent chains -- the fp64 dot and reduction,
+            // the MUFU pair, the splits -- overlap instead of running back to back
+            const double* rec = ws + (int)(kc - cb) * 4 * rs;
+            double a[4], th[4];
+            bool ok[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) a[q] = fma(__ldg(w[q] + cc), x, a[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            // argument reduced to [-pi, pi] in fp64, then the MUFU pair (__sincosf: abs error <= 2^-21.2 there):
-            // the operand error budget of the screen (prod_exact_kernel) carries 2^-21 for it
-            float sn, cs;
-            __sincosf((float)(a[q] - 6.283185307179586 * rint(a[q] * 0.15915494309189535)), &sn, &cs);
-            float p0 = cs, p1 = sn;
-            if (which == 0) {
-                p0 = (float)(th[q] * (double)cs);
-                p1 = (float)(-th[q] * (double)sn);
+            for (int q = 0; q < 4; ++q) {
+                ok[q] = kc * 4 + q < F && ir < nrow;
+                a[q] = rec[q * rs + ncol];
+                th[q] = rec[q * rs + ncol + 1];
             }
-            if (!ok[q]) p0 = p1 = 0.0f;
-            split_f16(p0, hi[2 * q], lo[2 * q]);
-            split_f16(p1, hi[2 * q + 1], lo[2 * q + 1]);
+            for (int c = 0; c < ncol; ++c) {
+                const double x = xs[c][r];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[q] = fma(rec[q * rs + c], x, a[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                // argument reduced to [-pi, pi] in fp64, then the MUFU pair (__sincosf: abs error <= 2^-21.2 there):
+                // the operand error budget of the screen (prod_exact_kernel) carries 2^-21 for it
+                float sn, cs;
+                __sincosf((float)(a[q] - 6.283185307179586 * rint(a[q] * 0.15915494309189535)), &sn, &cs);
+                float p0 = cs, p1 = sn;
+                if (which == 0) {
+                    p0 = (float)(th[q] * (double)cs);
+                    p1 = (float)(-th[q] * (double)sn);
+                }
+                if (!ok[q]) p0 = p1 = 0.0f;
+                split_f16(p0, hi[2 * q], lo[2 * q]);
+                split_f16(p1, hi[2 * q + 1], lo[2 * q + 1]);
+            }
+            __half* blk = out + ((g * ntile + tile) * nst + st) * (int64_t)(TC_BLOCK_BYTES / 2);
+            const int64_t o = (chunk * 128 + r) * 8;
+            *reinterpret_cast<uint4*>(blk + o) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(blk + 8 * 128 * 8 + o) = *reinterpret_cast<const uint4*>(lo);
         }
-        __half* blk = out + ((g * ntile + tile) * nst + st) * (int64_t)(TC_BLOCK_BYTES / 2);
-        const int64_t o = (chunk * 128 + r) * 8;
-        *reinterpret_cast<uint4*>(blk + o) = *reinterpret_cast<const uint4*>(hi);
-        *reinterpret_cast<uint4*>(blk + 8 * 128 * 8 + o) = *reinterpret_cast<const uint4*>(lo);
     }
 }
 
@@ -1435,6 +1453,114 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Two-level form of the merge for nlist <= 64 * 64 (every mesh the tcgen05 path sees: 1024 lists at C3).  One CTA per
+// sample leaves 148 - G SMs idle and walks 9 k entries kp times; here level 1 runs one CTA per (sample, block of Lc
+// lists), level 2 one CTA per sample over the level-1 results.  Each CTA reads its <= 1024 entries ONCE into registers
+// and runs the same kp rounds ("best entry strictly after the previous winner": value desc, index asc) on them, so the
+// result is the one prod_merge_kernel gives.  Level 1 works in place: the winners of block c replace list c * Lc of the
+// sample (written after the last round; no other CTA touches the lists of this (sample, block)).
+constexpr int MERGE_LC = 64, MERGE_EPT = MERGE_LC * PROD_MAX_KP / 256;
+template <bool LEVEL1>
+__global__ void __launch_bounds__(256)
+    prod_merge_regs_kernel(double* __restrict__ vals, int64_t* __restrict__ idx, int64_t nlist, int64_t G, int kp,
+                           int64_t Lc, double* __restrict__ out_val, int64_t* __restrict__ out_idx) {
+    __shared__ double sv[8], rv[PROD_MAX_KP];
+    __shared__ int64_t si[8], ri[PROD_MAX_KP];
+    __shared__ double wv;
+    __shared__ int64_t wi;
+    const int64_t g = blockIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t p0 = LEVEL1 ? (int64_t)blockIdx.y * Lc : 0;
+    const int64_t np = LEVEL1 ? (nlist - p0 < Lc ? nlist - p0 : Lc) : (nlist + Lc - 1) / Lc;
+    const int64_t pstride = LEVEL1 ? 1 : Lc;
+    const int64_t n = np * kp;
+    double ev[MERGE_EPT];
+    int64_t ei[MERGE_EPT];
+#pragma unroll
+    for (int u = 0; u < MERGE_EPT; ++u) {
+        const int64_t e = t + u * 256;
+        ev[u] = 0.0;
+        ei[u] = -1;
+        if (e < n) {
+            const int64_t o = ((p0 + (e / kp) * pstride) * G + g) * kp + e % kp;
+            ev[u] = vals[o];
+            ei[u] = idx[o];
+        }
+    }
+    if (t < kp) {
+        rv[t] = neg_inf();
+        ri[t] = -1;
+    }
+    double pv = pos_inf();
+    int64_t pi = -1;
+    for (int r = 0; r < kp; ++r) {
+        double bv = neg_inf();
+        int64_t bi = INT64_MAX;
+#pragma unroll
+        for (int u = 0; u < MERGE_EPT; ++u)
+            if (ei[u] >= 0 && better(pv, pi, ev[u], ei[u]) && better(ev[u], ei[u], bv, bi)) {
+                bv = ev[u];
+                bi = ei[u];
+            }
+        warp_argmax(bv, bi);
+        if (lane == 0) {
+            sv[warp] = bv;
+            si[warp] = bi;
+        }
+        __syncthreads();
+        if (t == 0) {
+            double v = sv[0];
+            int64_t i = si[0];
+            for (int w = 1; w < 8; ++w)
+                if (si[w] != INT64_MAX && (i == INT64_MAX || better(sv[w], si[w], v, i))) {
+                    v = sv[w];
+                    i = si[w];
+                }
+            if (i != INT64_MAX) {
+                rv[r] = v;
+                ri[r] = i;
+            }
+            wv = v;
+            wi = i;
+        }
+        __syncthreads();
+        if (wi == INT64_MAX) break;   // exhausted: the remaining slots stay empty
+        pv = wv;
+        pi = wi;
+    }
+    __syncthreads();
+    if (t < kp) {
+        if (LEVEL1) {
+            vals[(p0 * G + g) * kp + t] = rv[t];
+            idx[(p0 * G + g) * kp + t] = ri[t];
+        } else {
+            out_val[g * kp + t] = rv[t];
+            out_idx[g * kp + t] = ri[t];
+        }
+    }
+}
+// TES_PROD_MERGE=0 keeps the one-CTA-per-sample kernel (comparison path of the tests)
+static int launch_prod_merge(double* pv, int64_t* pi, int64_t nlist, int64_t G, int kp, double* out_val, int64_t* out_idx,
+                             cudaStream_t st) {
+    const char* env = getenv("TES_PROD_MERGE");
+    const bool regs = !(env && env[0] == '0') && kp <= PROD_MAX_KP;
+    if (regs && nlist * kp <= 256 * MERGE_EPT) {
+        prod_merge_regs_kernel<false><<<(unsigned)G, 256, 0, st>>>(pv, pi, nlist, G, kp, 1, out_val, out_idx);
+        TES_LAUNCH_OK();
+    } else if (regs && nlist <= (int64_t)MERGE_LC * MERGE_LC) {
+        const int64_t C = (nlist + MERGE_LC - 1) / MERGE_LC;
+        prod_merge_regs_kernel<true><<<dim3((unsigned)G, (unsigned)C), 256, 0, st>>>(pv, pi, nlist, G, kp, MERGE_LC, nullptr,
+                                                                                    nullptr);
+        TES_LAUNCH_OK();
+        prod_merge_regs_kernel<false><<<(unsigned)G, 256, 0, st>>>(pv, pi, nlist, G, kp, MERGE_LC, out_val, out_idx);
+        TES_LAUNCH_OK();
+    } else {
+        prod_merge_kernel<<<(unsigned)G, 256, 0, st>>>(pv, pi, nlist, G, kp, out_val, out_idx);
+        TES_LAUNCH_OK();
+    }
+    return 0;
+}
+
 // exact spec values of the kp survivors of every sample (one thread per (sample, slot): the sequence of
 // rff_value_kernel_generic), and the safety flag of the sample (slot 0).
 __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const double* __restrict__ feat, int rec,
@@ -1723,8 +1849,7 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
                                                                                 G, pv, pi);
             TES_LAUNCH_OK();
         }
-        prod_merge_kernel<<<(unsigned)G, 256, 0, st>>>(pv, pi, pl.nlist, G, pl.kp, mv + j0 * pl.kp, mi + j0 * pl.kp);
-        TES_LAUNCH_OK();
+        if (int rc = launch_prod_merge(pv, pi, pl.nlist, G, pl.kp, mv + j0 * pl.kp, mi + j0 * pl.kp, st)) return rc;
     }
     {
         const int64_t tot = S * pl.kp;
