@@ -18,6 +18,24 @@ def test_se_ard_vs_reference_golden(golden, tag):
     np.testing.assert_allclose(K, g[tag + "_Knm"], rtol=1e-13, atol=1e-15)
 
 
+@pytest.mark.parametrize("N,m,d", [(1, 1, 1), (33, 31, 2), (1000, 189, 6), (257, 65, 10), (70, 40, 16), (50, 20, 17)])
+def test_se_ard_tiled_kernel_is_bit_identical_to_the_per_element_kernel(N, m, d, monkeypatch):
+    """se_ard_tile_kernel (scaled coordinates and norms staged once per 32 x 32 tile) performs the per-element kernel's
+    operations in the same order: identical bits, and both within 1e-13 of the numpy oracle (utils.py:836-859);
+    d = 17 > SE_MAXD takes the per-element kernel either way."""
+    from tes_b200 import ops
+    rs = np.random.RandomState(N + m + d)
+    A, B = rs.rand(N, d) * 3 - 1, rs.rand(m, d) * 3 - 1
+    B[: min(m, N) // 2] = A[: min(m, N) // 2]              # exact duplicates: the cancellation case of the expansion
+    l = rs.rand(d) * 4 + 0.1
+    monkeypatch.setenv("TES_SE_ARD_TILED", "1")
+    K1 = ops.se_ard_cross(A, B, l, 1.37).cpu().numpy()
+    monkeypatch.setenv("TES_SE_ARD_TILED", "0")
+    K0 = ops.se_ard_cross(A, B, l, 1.37).cpu().numpy()
+    np.testing.assert_array_equal(K1, K0)
+    np.testing.assert_allclose(K1, onp.computeKnm(A, B, l, 1.37), rtol=1e-13, atol=1e-15)
+
+
 def test_brooms_barn_known_answer_through_cuda(golden):
     """The reference's only KAT (functions.py:397-398): pH objective maximum 0.73425606, evaluated
     with the CUDA SE-ARD kernel + CUDA Cholesky inverse + CUDA posterior mean."""

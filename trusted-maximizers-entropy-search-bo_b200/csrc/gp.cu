@@ -38,22 +38,75 @@ __global__ void se_ard_kernel(const double* __restrict__ x, int64_t N, const dou
     out[i * ldo + c] = v;
 }
 
+// Tiled form for d <= SE_MAXD: a CTA owns 32 rows x 32 columns; sqrt(l), the scaled coordinates and the squared norms
+// of its rows and columns are formed ONCE in shared memory (the kernel above recomputes d square roots and both norms
+// for every element), then every element is d FMAs and one exp.  Same operations in the same order per element, so
+// the values are the bits of se_ard_kernel (tests/test_stageB_gpu.py compares both).
+constexpr int SE_MAXD = 16, SE_ROWS = 32;
+__global__ void __launch_bounds__(256)
+    se_ard_tile_kernel(const double* __restrict__ x, int64_t N, const double* __restrict__ xb, int64_t m, int d,
+                       const double* __restrict__ l, double sigma, int64_t noise_from, double sigma0,
+                       double* __restrict__ out, int64_t ldo) {
+    __shared__ double s_sl[SE_MAXD], s_b[32][SE_MAXD + 1], s_a[SE_ROWS][SE_MAXD + 1], s_qb[32], s_q[SE_ROWS];
+    const int tx = threadIdx.x, ty = threadIdx.y, t = ty * 32 + tx;
+    const int64_t c0 = (int64_t)blockIdx.x * 32, i0 = (int64_t)blockIdx.y * SE_ROWS;
+    if (t < d) s_sl[t] = sqrt(__ldg(l + t));
+    __syncthreads();
+    for (int e = t; e < 32 * d; e += 256) {
+        const int cc = e / d, k = e % d;
+        const int64_t col = c0 + cc;
+        s_b[cc][k] = col < m ? __dmul_rn(__ldg(xb + col * d + k), s_sl[k]) : 0.0;
+    }
+    for (int e = t; e < SE_ROWS * d; e += 256) {
+        const int rr = e / d, k = e % d;
+        const int64_t row = i0 + rr;
+        s_a[rr][k] = row < N ? __dmul_rn(__ldg(x + row * d + k), s_sl[k]) : 0.0;
+    }
+    __syncthreads();
+    if (t < 32) {
+        double qb = 0.0;
+        for (int k = 0; k < d; ++k) qb = __dadd_rn(qb, __dmul_rn(s_b[t][k], s_b[t][k]));
+        s_qb[t] = qb;
+    } else if (t < 32 + SE_ROWS) {
+        double q = 0.0;
+        for (int k = 0; k < d; ++k) q = __dadd_rn(q, __dmul_rn(s_a[t - 32][k], s_a[t - 32][k]));
+        s_q[t - 32] = q;
+    }
+    __syncthreads();
+    const int64_t c = c0 + tx;
+    if (c >= m) return;
+    const double qb = s_qb[tx];
+#pragma unroll 2
+    for (int r = ty; r < SE_ROWS; r += 8) {
+        const int64_t i = i0 + r;
+        if (i >= N) break;
+        double dot = 0.0;
+        for (int k = 0; k < d; ++k) dot = fma(s_a[r][k], s_b[tx][k], dot);
+        const double dist = __dadd_rn(__dadd_rn(qb, s_q[r]), -2.0 * dot);
+        double v = sigma * exp(-0.5 * dist);
+        if (noise_from >= 0 && i == c && c >= noise_from) v += sigma0;
+        out[i * ldo + c] = v;
+    }
+}
+
+// TES_SE_ARD_TILED=0 keeps the per-element kernel (comparison path of the tests)
 int launch_se_ard(const double* x, int64_t N, const double* xb, int64_t m, int d, const double* l,
                          double sigma, int64_t noise_from, double sigma0, double* out, int64_t ldo,
                          cudaStream_t st) {
     if (N == 0 || m == 0) return 0;
+    const char* env = getenv("TES_SE_ARD_TILED");
+    const bool tiled = d <= SE_MAXD && !(env && env[0] == '0');
+    const int rpb = tiled ? SE_ROWS : 8;                       // rows per CTA
     dim3 block(32, 8);
-    dim3 grid((unsigned)((m + 31) / 32), (unsigned)((N + 7) / 8));
-    if (grid.y > 65535) {  // split rows
-        int64_t rows_per = 65535LL * 8;
-        for (int64_t r0 = 0; r0 < N; r0 += rows_per) {
-            int64_t nr = (N - r0 < rows_per) ? (N - r0) : rows_per;
-            dim3 g2((unsigned)((m + 31) / 32), (unsigned)((nr + 7) / 8));
-            se_ard_kernel<<<g2, block, 0, st>>>(x + r0 * d, nr, xb, m, d, l, sigma,
-                                                noise_from >= 0 ? noise_from - r0 : -1, sigma0, out + r0 * ldo, ldo);
-        }
-    } else {
-        se_ard_kernel<<<grid, block, 0, st>>>(x, N, xb, m, d, l, sigma, noise_from, sigma0, out, ldo);
+    const int64_t rows_per = 65535LL * rpb;
+    for (int64_t r0 = 0; r0 < N; r0 += rows_per) {             // grid.y <= 65535: split rows
+        const int64_t nr = (N - r0 < rows_per) ? (N - r0) : rows_per;
+        dim3 g2((unsigned)((m + 31) / 32), (unsigned)((nr + rpb - 1) / rpb));
+        const int64_t nf = noise_from >= 0 ? noise_from - r0 : -1;
+        if (tiled)
+            se_ard_tile_kernel<<<g2, block, 0, st>>>(x + r0 * d, nr, xb, m, d, l, sigma, nf, sigma0, out + r0 * ldo, ldo);
+        else
+            se_ard_kernel<<<g2, block, 0, st>>>(x + r0 * d, nr, xb, m, d, l, sigma, nf, sigma0, out + r0 * ldo, ldo);
     }
     TES_LAUNCH_OK();
     return 0;
