@@ -723,8 +723,8 @@ __global__ void __launch_bounds__(256)
             double v;
             if (c < ncol) v = __ldg(W + (jw * F + fc) * d + col_of(c));
             else if (c == ncol) v = which == 0 ? __ldg(b + jw * F + fc) : 0.0;
-            else v = which == 0 ? __ldg(theta + j * F + fc) * inv_tm : 0.0;
-            ws[e] = v;
+            else v = __hiloint2double(0, __float_as_int(which == 0 ? (float)(__ldg(theta + j * F + fc) * inv_tm) : 0.0f));
+            ws[e] = v;   // theta / tmax as a float (bit pattern in the low word): the P operand is an fp32 product
         }
         __syncthreads();
         for (int64_t kc = cb + half; kc < ce; kc += 2) {
@@ -734,13 +734,14 @@ __global__ void __launch_bounds__(256)
             // clamped for the loads and zeroed at the end), so their dependent chains -- the fp64 dot and reduction,
             // the MUFU pair, the splits -- overlap instead of running back to back
             const double* rec = ws + (int)(kc - cb) * 4 * rs;
-            double a[4], th[4];
+            double a[4];
+            float th[4];
             bool ok[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 ok[q] = kc * 4 + q < F && ir < nrow;
                 a[q] = rec[q * rs + ncol];
-                th[q] = rec[q * rs + ncol + 1];
+                th[q] = __int_as_float(__double2loint(rec[q * rs + ncol + 1]));
             }
             for (int c = 0; c < ncol; ++c) {
                 const double x = xs[c][r];
@@ -751,12 +752,21 @@ __global__ void __launch_bounds__(256)
             for (int q = 0; q < 4; ++q) {
                 // argument reduced to [-pi, pi] in fp64, then the MUFU pair (__sincosf: abs error <= 2^-21.2 there):
                 // the operand error budget of the screen (prod_exact_kernel) carries 2^-21 for it
+                // rint by the 1.5 * 2^52 shift (exact for |t| < 2^51, round-to-nearest-even like rint): two DADDs on
+                // the fp64 pipe instead of an FRND on the conversion (XU) pipe, which is this kernel's busiest
+                // (69 % before; MUFU.SIN / MUFU.COS and the fp64 -> fp32 conversion live there too).  theta / tmax is
+                // applied as an fp32 product of floats (no fp32 <-> fp64 round trips: 4 fewer XU conversions per
+                // feature); its two roundings are the 0.25 * 2^-20 added to the per-term budget in prod_exact_kernel
                 float sn, cs;
-                __sincosf((float)(a[q] - 6.283185307179586 * rint(a[q] * 0.15915494309189535)), &sn, &cs);
+                const double tt = a[q] * 0.15915494309189535;
+                // (|t| >= 2^51 only loses the reduction: the value bound B of prod_exact_kernel grows with max |a| and
+                // flags such a sample for the general kernel long before)
+                const double red = __dadd_rn(__dadd_rn(tt, 6755399441055744.0), -6755399441055744.0);
+                __sincosf((float)(a[q] - 6.283185307179586 * red), &sn, &cs);
                 float p0 = cs, p1 = sn;
                 if (which == 0) {
-                    p0 = (float)(th[q] * (double)cs);
-                    p1 = (float)(-th[q] * (double)sn);
+                    p0 = __fmul_rn(th[q], cs);
+                    p1 = __fmul_rn(-th[q], sn);
                 }
                 if (!ok[q]) p0 = p1 = 0.0f;
                 split_f16(p0, hi[2 * q], lo[2 * q]);
@@ -1561,7 +1571,7 @@ static int launch_prod_merge(double* pv, int64_t* pi, int64_t nlist, int64_t G, 
     return 0;
 }
 
-// exact spec values of the kp survivors of every sample (one thread per (sample, slot): the sequence of
+// exact spec values of the kp survivors of every sample (one warp per (sample, slot): the sequence of
 // rff_value_kernel_generic), and the safety flag of the sample (slot 0).
 __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const double* __restrict__ feat, int rec,
                                   int64_t S, int64_t F, double scale, int64_t idx_offset, int k, int kp,
@@ -1569,7 +1579,13 @@ __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const 
                                   const double* __restrict__ xmax, int tf32, const double* __restrict__ tmax,
                                   double* __restrict__ exact_val,
                                   int* __restrict__ flag) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // one WARP per (sample, slot): the lanes evaluate 32 features' arguments and cosines in parallel and park
+    // (theta, cos) in shared memory, then every lane replays the spec's sequential fma accumulation over them in feature
+    // order -- the same operations in the same order as one thread walking the F features (which left 2 warps per SM
+    // and 1.3 ms of dependent-latency at C3), so the value is still the bits of rff_value_kernel_generic
+    __shared__ double2 pr[4][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * 4 + warp;
     if (t >= S * kp) return;
     const int64_t j = t / kp;
     const int r = (int)(t % kp);
@@ -1579,28 +1595,47 @@ __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const 
     if (gi >= 0) {
         const double* x = cand + (gi - idx_offset) * d;
         double acc = 0.0;
-        for (int64_t f = 0; f < F; ++f) {
-            const double* rr = fj + f * rec;
-            double h = __ldg(rr + d);
-            for (int kk = 0; kk < d; ++kk) h = fma(__ldg(rr + kk), __ldg(x + kk), h);
-            acc = fma(__ldg(rr + d + 1), cospi_spec(h), acc);
+        for (int64_t f0 = 0; f0 < F; f0 += 32) {
+            const int64_t f = f0 + lane;
+            double2 tc = make_double2(0.0, 0.0);
+            if (f < F) {
+                const double* rr = fj + f * rec;
+                double h = __ldg(rr + d);
+                for (int kk = 0; kk < d; ++kk) h = fma(__ldg(rr + kk), __ldg(x + kk), h);
+                tc = make_double2(__ldg(rr + d + 1), cospi_spec(h));
+            }
+            __syncwarp();
+            pr[warp][lane] = tc;
+            __syncwarp();
+            const int nb = F - f0 < 32 ? (int)(F - f0) : 32;
+            for (int q = 0; q < nb; ++q) {
+                const double2 e = pr[warp][q];
+                acc = fma(e.x, e.y, acc);
+            }
         }
         val = __dmul_rn(scale, acc);
     }
-    exact_val[t] = val;
+    if (lane == 0) exact_val[t] = val;
     if (r == 0) {
         // B_j: both values are fp64 evaluations of the same real function.  Per feature the argument carries
         // <= 4 (d + 2) u A rounding (prescale by 1/pi, fma chains on both sides; A = largest |argument| of the sample),
         // cos / sincos and the products <= 16 u, and the two accumulations (F sequential fmas; 2F DMMA steps)
         // <= 3 F u sum|theta|.  Doubled for margin.
         double sa = 0.0, am = 0.0;
-        for (int64_t f = 0; f < F; ++f) {
+        for (int64_t f = lane; f < F; f += 32) {
             const double* rr = fj + f * rec;
             sa += fabs(__ldg(rr + d + 1));
             double a = fabs(__ldg(rr + d));
             for (int kk = 0; kk < d; ++kk) a = fma(fabs(__ldg(rr + kk)), xmax[kk], a);
             am = a > am ? a : am;
         }
+        sa = warp_sum(sa);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double o = __shfl_xor_sync(0xffffffffu, am, off);
+            am = o > am ? o : am;
+        }
+        if (lane != 0) return;
         const double u = 1.1102230246251565e-16;
         double B = 2.0 * u * scale * sa * (4.0 * (d + 2) * 3.141592653589793 * am + 3.0 * (double)F + 16.0) + 1e-300;
         // 3xTF32 screen: every operand is sincosf of the fp64-reduced argument (argument rounding 2^-22.3, sincosf 2 ulp
@@ -1608,7 +1643,8 @@ __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const 
         // operand pair, plus the dropped lo*lo (2^-22): <= 4.5 * 2^-20 per term; fp32 accumulation in segments of PT_FLUSH k = 3 * PT_FLUSH / 8 mma steps,
         // each assumed to err by <= 4 * 2^-24 of the segment's sum of |terms| (the tests compare against the fp64 GEMM
         // path on ties 1e-13 ... 1e-4 apart); the |terms| of a feature sum to <= |theta_f|.  x1.5 margin.
-        if (tf32) B += 1.5 * scale * sa * (4.5 * 9.5367431640625e-07 + 4.0 * 5.9604644775390625e-08 * 3.0 * (PT_FLUSH / 8));
+        // (+ 0.25 * 2^-20: the tcgen05 build forms theta / tmax * cos as a product of floats, 2 extra roundings of 2^-24)
+        if (tf32) B += 1.5 * scale * sa * (4.75 * 9.5367431640625e-07 + 4.0 * 5.9604644775390625e-08 * 3.0 * (PT_FLUSH / 8));
         // fp16 operands (mode 2; same 11-bit significand as TF32, theta normalised by tmax): subnormal rounding adds an
         // absolute 2^-25 per operand, i.e. <= 2 * 2^-25 per term over 2F terms, in units of scale * tmax
         if (tf32 >= 2) B += 1.5 * scale * tmax[j] * 4.0 * (double)F * 2.98023223876953125e-08;
@@ -1853,7 +1889,7 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     }
     {
         const int64_t tot = S * pl.kp;
-        prod_exact_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(cand, (int)d, feat, pl.rec, S, F, scale,
+        prod_exact_kernel<<<(unsigned)((tot + 3) / 4), 128, 0, st>>>(cand, (int)d, feat, pl.rec, S, F, scale,
                                                                        idx_offset, k, pl.kp, mv, mi, xmax, tf32, tmax, ev, out_flag);
         TES_LAUNCH_OK();
     }
