@@ -393,8 +393,8 @@ def main():
                             "1-D bulk async copies (TMA engine) in a 3-stage mbarrier ring",
                     "kernel": "prod_gemm_topk_tc_kernel (+ operand build, list merge, exact fp64 refine)",
                     "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-                    "traffic": 753.5e6 if wl["name"] == "c3" else None,   # profiles/r01_ncu_prod_gemm_tcgen05.md, per launch
-                    "kernel_alone": "742 us per 45-sample launch = 745 TFLOP/s = 0.56 of the peak (ncu, profiles/)",
+                    "traffic": 775.6e6 if wl["name"] == "c3" else None,   # profiles/r01_ncu_prod_gemm_tcgen05.md, per launch (read 754.5 + write 21.1 MB)
+                    "kernel_alone": "745 us per 45-sample launch = 742 TFLOP/s = 0.56 of the peak (ncu, profiles/)",
                     "peak_source": "bf16_tflops_sustained of MEASURED_PEAKS.json (cuBLAS, %s)" % (
                         "measured" if peaks else "fallback 1400"),
                     "algorithmic_fp64_gemm_tflops": gflops / t_rff * 1e-12,
