@@ -1121,7 +1121,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     unsigned char* stages = qf_smem_raw;                                            // [QF_NS][A block | B block]
     float* msm = reinterpret_cast<float*>(qf_smem_raw + QF_NS * TC_STAGE_BYTES);    // [T + 8][129], rows T.. = 0
     uint2* dsc = reinterpret_cast<uint2*>(msm + qf_msm_floats(T));    // [nst * 8] byte offsets of rows a, b0 per chunk
-    uint64_t* bars = reinterpret_cast<uint64_t*>(dsc + nst * 8);
+    double* rmax_s = reinterpret_cast<double*>(dsc + nst * 8);     // [128] row maxima of the tile (scale of M, of q~)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rmax_s + 128);
     uint64_t* full_b = bars;                 // [2] producer (B block landed) -> MMA
     uint64_t* a_full = bars + QF_NS;         // [2] generators (A block written) -> MMA
     uint64_t* empty_b = bars + 2 * QF_NS;    // [2] MMA (commit) -> producer, generators
@@ -1219,15 +1220,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int64_t rt = blockIdx.x + it * gridDim.x;
             // (re)load the tile of M: the 16 generator warps only; the MMAs of the previous tile may still be in flight
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            for (int64_t e = te; e < T * 128; e += 512) {
-                const int64_t rr = e / T, a = e % T;
+            // a warp per row (8 rows each), lanes over the T columns: one scale (one fp64 division) per row instead of
+            // per element, no index divisions, coalesced independent loads the compiler can batch
+            // The row maximum (quad_rowmax_kernel of the unfused path: max |M[x, a]|, NaN ignored) is formed here by the
+            // same warp, so the fused path needs no separate pass over G and no rowmax launch.
+            for (int rr = te >> 5; rr < 128; rr += TC_EPI_WARPS) {
                 const int64_t grow = rt * 128 + rr;
-                float v = 0.0f;
-                if (grow < nc) {
-                    const double rm = rowmax[grow];
-                    if (rm > 0.0) v = (float)(G[grow * ldg + a] * (64.0 / rm));     // 64^2 = QS_AMAX
-                }
-                msm[a * 129 + rr] = v;
+                const double* gp = G + grow * ldg;
+                double rm = 0.0;
+                if (grow < nc)
+                    for (int a = lane; a < (int)T; a += 32) rm = fmax(rm, fabs(gp[a]));
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, off));
+                const double sc = rm > 0.0 ? 64.0 / rm : 0.0;                       // 64^2 = QS_AMAX
+                if (lane == 0) rmax_s[rr] = rm;
+#pragma unroll 4
+                for (int a = lane; a < (int)T; a += 32) msm[a * 129 + rr] = sc != 0.0 ? (float)(gp[a] * sc) : 0.0f;
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
             double sum[32];
@@ -1288,7 +1296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             drain(gs - 1);
             const int64_t row = rt * 128 + quarter * 32 + lane;
             if (row < nc) {
-                const double rm = rowmax[row];
+                const double rm = rmax_s[quarter * 32 + lane];
                 const double rs = rm * rm / QS_AMAX;
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
@@ -1347,18 +1355,15 @@ int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, int6
     const int64_t Kp = quad_screen_kp(Kdim), nst = Kp / TC_BK, ntu = (nc + 127) / 128;
     double* rowscale = (double*)((char*)Atc + align_up(ntu * nst * (int64_t)TC_BLOCK_BYTES, 256));
     const double* colscale = colmax + 128;
-    quad_rowmax_kernel<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(G, ldg, nc, T, rowmax);
-    TES_LAUNCH_OK();
     {
-        // fused kernel (A generated on the SM) whenever M's tile fits beside two stages; TES_QUAD_FUSED=0 disables it
+        // fused kernel (A generated on the SM, row maxima included) whenever M's tile fits beside two stages;
+        // TES_QUAD_FUSED=0 disables it
         const size_t fsm = (size_t)QF_NS * TC_STAGE_BYTES + (size_t)qf_msm_floats(T) * sizeof(float) +
-                           (size_t)nst * 8 * sizeof(uint2) + 256;
+                           (size_t)nst * 8 * sizeof(uint2) + 128 * sizeof(double) + 256;
         const char* env = getenv("TES_QUAD_FUSED");
         if (fsm <= 227 * 1024 && T <= 500 && !(env && env[0] == '0')) {
             const uint32_t* ab = reinterpret_cast<const uint32_t*>(colmax + 256);
-            int dev = 0, sms = 148;
-            TES_CUDA_OK(cudaGetDevice(&dev));
-            TES_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            const int sms = tc_sm_count();
             TES_CUDA_OK(cudaFuncSetAttribute(quad_screen_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)fsm));
             const unsigned grid = (unsigned)(ntu < sms ? ntu : sms);
@@ -1368,6 +1373,8 @@ int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, int6
             return 0;
         }
     }
+    quad_rowmax_kernel<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(G, ldg, nc, T, rowmax);
+    TES_LAUNCH_OK();
     {
         const size_t smem = (size_t)T * 129 * sizeof(float);
         if (smem > 200 * 1024) return -5;
