@@ -88,6 +88,15 @@ int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d, int64_t s
                              int k, int64_t idx_offset, int64_t* out_idx, double* out_val, int* out_flag, int tf32,
                              void* ws, int64_t ws_bytes, void* stream);
 
+/* Detection of the product structure above on the device (the meshes come from functions.get_meshgrid,
+ * bo_discrete.py:928-941; the reference has no counterpart: it never exploits the structure).
+ * runlen: out_r[k] = first row whose coordinate k differs from row 0 (N if the column is constant) -- the block length nv
+ * of a split is the minimum over its slow columns.  check: for a given nv, out_bad[k] = 1 unless column k is constant
+ * inside every block of nv rows ("slow"), out_bad[d + k] = 1 unless row i equals row i % nv in column k ("fast").
+ * IEEE == comparisons (NaN never equal).  out_r: d int64, out_bad: 2 d int32, device memory. */
+int tes_product_runlen_f64(const double* cand, int64_t N, int64_t d, int64_t* out_r, void* stream);
+int tes_product_check_f64(const double* cand, int64_t N, int64_t d, int64_t nv, int* out_bad, void* stream);
+
 /* All function-sample values, out (S, N).  Replaces utils_for_continuous.get_function_samples
  * (utils_for_continuous.py:257-296) / optfunc.make_function_sample_np.  Debug / small-N use. */
 int tes_rff_eval_f64(const double* cand, int64_t N, int64_t d, const double* W, const double* b,

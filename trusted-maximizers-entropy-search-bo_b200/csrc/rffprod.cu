@@ -1706,6 +1706,25 @@ static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F
     if (G < 1) G = 1;
     if (G > S) G = S;
     if (G > 65535) G = 65535;
+    if (tc && S > G) {
+        // the tcgen05 GEMM is persistent (one CTA per SM walks tiles-per-sample * G tiles): pick the group size in
+        // [2G/3, G] that needs the fewest tile rounds over all S samples, the short last group included (C3: 64 tiles
+        // per sample; G = 45 -> 22 x 20 + 15 = 455 rounds, G = 37 -> 27 x 16 + 11 = 443 = ceil(65536 / 148)); a launch
+        // is charged a quarter of a round for its prologue
+        const int64_t sms = tc_sm_count(), t1 = ((p.nu + 127) / 128) * ((nv + 127) / 128);
+        double best = 1e300;
+        int64_t bg = G;
+        for (int64_t g = G; g >= 1 && 3 * g >= 2 * G; --g) {
+            const int64_t full = S / g, rem = S % g;
+            const double cost = (double)(full * ((t1 * g + sms - 1) / sms) + (t1 * rem + sms - 1) / sms) +
+                                0.25 * (double)(full + (rem ? 1 : 0));
+            if (cost < best - 1e-9) {
+                best = cost;
+                bg = g;
+            }
+        }
+        G = bg;
+    }
     p.G = G;
     p.gx = (p.nu + GEMM_BM - 1) / GEMM_BM;
     p.gy = (nv + GEMM_BN - 1) / GEMM_BN;
@@ -1901,6 +1920,67 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
         TES_LAUNCH_OK();
     }
     prod_final_kernel<<<(unsigned)S, 32, 0, st>>>(ev, mi, pl.kp, k, out_val, out_idx);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
+// ---- product-structure detection (ops.detect_product_structure) ----------------------------------------------------
+// Two passes over the candidate array instead of ~40 framework launches and ~20 host syncs:
+//   runlen:  r[k] = first row whose coordinate k differs from row 0 (N if none)  -> the host derives nv of a split
+//   check:   for a given nv, bad[k] = 1 if column k is not "slow" (constant inside every block of nv rows),
+//            bad[d + k] = 1 if it is not "fast" (row i equals row i % nv)
+// Comparisons are IEEE == (NaN never equal, -0 == +0), as the tensor comparisons they replace.
+namespace tes {
+__global__ void product_runlen_init_kernel(int64_t N, int d, unsigned long long* __restrict__ r) {
+    if ((int)threadIdx.x < d) r[threadIdx.x] = (unsigned long long)N;
+}
+__global__ void __launch_bounds__(256)
+    product_runlen_kernel(const double* __restrict__ cand, int64_t N, int d, unsigned long long* __restrict__ r) {
+    const int64_t tot = N * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e % d);
+        const int64_t i = e / d;
+        if (!(cand[e] == cand[k]) && (unsigned long long)i < r[k]) atomicMin(r + k, (unsigned long long)i);
+    }
+}
+__global__ void __launch_bounds__(256)
+    product_check_kernel(const double* __restrict__ cand, int64_t N, int d, int64_t nv, int* __restrict__ bad) {
+    const int64_t tot = N * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e % d);
+        const int64_t i = e / d;
+        const double v = cand[e];
+        if (!(v == cand[(i / nv) * nv * d + k]) && !bad[k]) bad[k] = 1;
+        if (!(v == cand[(i % nv) * d + k]) && !bad[d + k]) bad[d + k] = 1;
+    }
+}
+}  // namespace tes
+
+extern "C" int tes_product_runlen_f64(const double* cand, int64_t N, int64_t d, int64_t* out_r, void* stream) {
+    if (N < 1 || !cand) return -1;
+    if (d < 1 || d > 64) return -3;
+    if (!out_r) return -4;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* r = reinterpret_cast<unsigned long long*>(out_r);
+    product_runlen_init_kernel<<<1, 64, 0, st>>>(N, (int)d, r);
+    TES_LAUNCH_OK();
+    const int64_t tot = N * d;
+    const int64_t want = (tot + 255) / 256, cap = (int64_t)tc_sm_count() * 8;
+    product_runlen_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(cand, N, (int)d, r);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tes_product_check_f64(const double* cand, int64_t N, int64_t d, int64_t nv, int* out_bad, void* stream) {
+    if (N < 1 || !cand) return -1;
+    if (d < 1 || d > 64) return -3;
+    if (nv < 1 || nv > N) return -4;
+    if (!out_bad) return -5;
+    cudaStream_t st = (cudaStream_t)stream;
+    TES_CUDA_OK(cudaMemsetAsync(out_bad, 0, (size_t)(2 * d) * sizeof(int), st));
+    const int64_t tot = N * d;
+    const int64_t want = (tot + 255) / 256, cap = (int64_t)tc_sm_count() * 8;
+    product_check_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(cand, N, (int)d, nv, out_bad);
     TES_LAUNCH_OK();
     return 0;
 }

@@ -32,25 +32,38 @@ def detect_product_structure(cand):
     """Is the candidate set a product U x V in row-major order -- the coordinates in columns [s_lo, s_hi) depend on
     i // nv only and the other columns on i % nv only (functions.get_meshgrid, or any slab of such a mesh)?
     -> (s_lo, s_hi, nv) or None; among the admissible splits the most balanced one (|nu - nv| smallest).
-    A few comparisons over the candidate array on the device."""
+    Two kinds of pass over the candidate array on the device (tes_product_runlen_f64 once, tes_product_check_f64 once
+    per distinct block length), d and 2 d integers back to the host."""
     N, d = cand.shape
-    if d < 2 or N < 4:
+    if d < 2 or N < 4 or d > 64:
         return None
+    cand = cand.contiguous()
+    L = _lib.lib()
+    r_d = torch.empty((d,), dtype=torch.int64, device=cand.device)
+    _lib.check(L.tes_product_runlen_f64(ptr(cand), N, d, ptr(r_d), stream_ptr()), "tes_product_runlen_f64")
+    r = r_d.cpu().tolist()           # r[k]: first row whose coordinate k differs from row 0 (N: constant column)
+    checked = {}
+
+    def violations(nv):
+        if nv not in checked:
+            bad = torch.empty((2 * d,), dtype=torch.int32, device=cand.device)
+            _lib.check(L.tes_product_check_f64(ptr(cand), N, d, nv, ptr(bad), stream_ptr()), "tes_product_check_f64")
+            checked[nv] = bad.cpu().tolist()
+        return checked[nv]
+
     best = None
     # slow = a prefix [0, du) (meshes of >= 3 dimensions) or a suffix [du, d) (the 2-D mesh, whose first column is fast)
     for s_lo, s_hi in [(0, du) for du in range(1, d)] + [(du, d) for du in range(1, d)]:
-        same = (cand[:, s_lo:s_hi] == cand[0, s_lo:s_hi]).all(dim=1)
-        if bool(same.all()):
+        nv = min(r[s_lo:s_hi])       # run length of the first row's slow coordinates
+        if nv >= N:                  # the slow columns never change
             continue
-        nv = int(torch.nonzero(~same)[0, 0])       # run length of the first row's slow coordinates
         if nv < 2 or N % nv:
             continue
         nu = N // nv
         if best is not None and abs(nu - nv) >= abs(best[3] - best[2]):
             continue
-        c3 = cand.reshape(nu, nv, d)
-        fast = [k for k in range(d) if not (s_lo <= k < s_hi)]
-        if bool((c3[:, :, s_lo:s_hi] == c3[:, :1, s_lo:s_hi]).all()) and bool((c3[:, :, fast] == c3[:1, :, fast]).all()):
+        bad = violations(nv)
+        if not any(bad[s_lo:s_hi]) and not any(bad[d + k] for k in range(d) if not (s_lo <= k < s_hi)):
             best = (s_lo, s_hi, nv, nu)
     return None if best is None else best[:3]
 
