@@ -256,7 +256,28 @@ def run_reference_arm(args, wl, rank):
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
+
+
+_REAL_STDOUT_FD = None
+
+
+def _stdout_to_stderr():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the first
+    communicator when NCCL_DEBUG is set): file descriptor 1 points at stderr until the line is printed."""
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(_REAL_STDOUT_FD, 1)
+    sys.stdout.write(json.dumps(line) + "\n")
+    sys.stdout.flush()
 
 
 def main():
@@ -269,6 +290,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C2 latency case reported beside C3")
     args = ap.parse_args()
+    _stdout_to_stderr()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -508,7 +530,7 @@ def main():
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
