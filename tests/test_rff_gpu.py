@@ -391,6 +391,42 @@ def test_product_structure_detection():
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
 
 
+def test_product_detection_kernels_against_numpy():
+    """tes_product_runlen_f64 / tes_product_check_f64 (the two passes behind ops.detect_product_structure) against
+    their numpy definitions, incl. a constant column, a NaN (never equal: run length 0 when it sits in row 0) and a
+    column that is neither slow nor fast."""
+    import torch
+    from tes_b200 import _lib, ops
+    from tes_b200.device import ptr, stream_ptr
+    rs = np.random.RandomState(5)
+    u, v = np.sort(rs.rand(6, 2)), np.sort(rs.rand(35, 3))
+    cand = np.concatenate([np.repeat(u, 35, axis=0), np.tile(v, (6, 1))], axis=1)     # slow columns 0-1, fast 2-4
+    cand = np.concatenate([cand, np.full((210, 1), 0.25), rs.rand(210, 1)], axis=1)   # constant, unstructured
+    for variant in range(3):
+        c = cand.copy()
+        if variant == 1:
+            c[0, 2] = np.nan
+        if variant == 2:
+            c[57, 0] = np.nan
+        N, d = c.shape
+        cd = ops.dev(c)
+        r = torch.empty((d,), dtype=torch.int64, device=cd.device)
+        assert _lib.lib().tes_product_runlen_f64(ptr(cd), N, d, ptr(r), stream_ptr()) == 0
+        diff = ~(c == c[0])
+        want_r = [int(np.argmax(diff[:, k])) if diff[:, k].any() else N for k in range(d)]
+        assert r.cpu().tolist() == want_r
+        for nv in (35, 7, 210, 1):
+            bad = torch.empty((2 * d,), dtype=torch.int32, device=cd.device)
+            assert _lib.lib().tes_product_check_f64(ptr(cd), N, d, nv, ptr(bad), stream_ptr()) == 0
+            i = np.arange(N)
+            slow_bad = [int((~(c[:, k] == c[(i // nv) * nv, k])).any()) for k in range(d)]
+            fast_bad = [int((~(c[:, k] == c[i % nv, k])).any()) for k in range(d)]
+            assert bad.cpu().tolist() == slow_bad + fast_bad
+    assert ops.detect_product_structure(ops.dev(cand[:, :5])) == (0, 2, 35)
+    assert ops.detect_product_structure(ops.dev(cand)) is None
+
+
+
 @pytest.mark.parametrize("eps", [1e-13, 1e-9, 1e-6, 1e-4])
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_product_path_near_ties(eps, seed):
