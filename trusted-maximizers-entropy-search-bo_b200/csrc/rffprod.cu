@@ -1238,9 +1238,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 for (int a = lane; a < (int)T; a += 32) msm[a * 129 + rr] = sc != 0.0 ? (float)(gp[a] * sc) : 0.0f;
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            double sum[32];
+            // running sums of the 256-k fp32 segments as double-float pairs (hi + lo, error-free TwoSum on the fp32 pipe,
+            // ~2^-46 relative): converting every segment value to fp64 costs a conversion on the XU pipe per value
+            // (16 lanes / clk / SM) -- the drains were 26 % of the kernel's samples
+            float shi[32], slo[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) sum[c] = 0.0;
+            for (int c = 0; c < 32; ++c) shi[c] = slo[c] = 0.0f;
             auto drain = [&](int64_t dseg) {
                 const uint32_t a = (uint32_t)(dseg & 1), pa = (uint32_t)((dseg >> 1) & 1);
                 mbar_wait(&acc_full[a], pa);
@@ -1252,7 +1255,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 __syncwarp();
                 if (lane == 0) tc_arrive(&acc_empty[a]);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) sum[c] += (double)__uint_as_float(v0[c]);
+                for (int c = 0; c < 32; ++c) {
+                    const float v = __uint_as_float(v0[c]);
+                    const float t = __fadd_rn(shi[c], v);
+                    const float bb = __fsub_rn(t, shi[c]);
+                    const float e = __fadd_rn(__fsub_rn(shi[c], __fsub_rn(t, bb)), __fsub_rn(v, bb));
+                    slo[c] = __fadd_rn(slo[c], e);
+                    shi[c] = t;
+                }
             };
             for (int64_t seg = 0; seg < nseg; ++seg) {
                 for (int q4 = 0; q4 < TC_SEG; ++q4, ++g) {
@@ -1300,7 +1310,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const double rs = rm * rm / QS_AMAX;
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
-                    if (cb * 32 + c < Sp) Qout[row * Sp + cb * 32 + c] = rs * colscale[cb * 32 + c] * sum[c];
+                    if (cb * 32 + c < Sp)
+                        Qout[row * Sp + cb * 32 + c] = rs * colscale[cb * 32 + c] * ((double)shi[c] + (double)slo[c]);
             }
         }
     }
