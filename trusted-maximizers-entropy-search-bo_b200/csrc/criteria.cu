@@ -514,13 +514,19 @@ struct EpPlan {
         total;
 };
 
-static EpPlan ep_plan(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp) {
+// The screen's chunk: two 128-row tiles per SM -- its fp64 GEMMs fill whole waves (N = T + n + 1 = 190: 888 CTAs = 3
+// waves of 2 per SM instead of 1.5) and the per-chunk launches halve; set by getenv TES_SCREEN_CHUNK_TILES (1 or 2)
+static const int64_t PS_SCREEN_CHUNK = [] {
+    const char* e = getenv("TES_SCREEN_CHUNK_TILES");
+    return (e && e[0] == '1') ? PS_CHUNK : 2 * PS_CHUNK;
+}();
+static EpPlan ep_plan(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp, int64_t chunk = PS_CHUNK) {
     EpPlan p;
     p.m = T + n;
     p.nb = (T + 15) / 16;
     p.nbp = p.nb * (p.nb + 1) / 2;
     p.Kdim = quad_num_slices(p.nb) * 16;
-    p.nc = N < PS_CHUNK ? (N < 1 ? 1 : N) : PS_CHUNK;
+    p.nc = N < chunk ? (N < 1 ? 1 : N) : chunk;
     int64_t o = 0;
     auto take = [&](int64_t bytes) {
         int64_t r = o;
@@ -699,7 +705,7 @@ __global__ void ep_det_screen_kernel(const double* __restrict__ Qt, const double
 
 extern "C" int64_t tes_ep_acq_screen_workspace_bytes(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp) {
     if (N < 0 || T < 1 || n < 1 || d < 1 || Sp < 1 || Sp > 128) return -1;
-    EpPlan pl = ep_plan(N, T, n, d, Sp);
+    EpPlan pl = ep_plan(N, T, n, d, Sp, PS_SCREEN_CHUNK);
     const int64_t Ks = quad_screen_kdim(T);
     return pl.total + quad_screen_a_bytes(pl.nc, Ks) + quad_screen_b_bytes(Ks) + align_up(pl.nc * 8, 256) +
            align_up(T * Sp * 8, 256) + align_up(pl.nc * T * 8, 256) + align_up(Ks * Sp * 8, 256);
@@ -721,7 +727,7 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
     if (Sp < 1 || Sp > 128) return -15;
     if (!post_cov) return -16;
     if (N > 0 && (!out_acq || !out_eps)) return -17;
-    EpPlan pl = ep_plan(N, T, n, d, Sp);
+    EpPlan pl = ep_plan(N, T, n, d, Sp, PS_SCREEN_CHUNK);
     if (!ws || ws_bytes < tes_ep_acq_screen_workspace_bytes(N, T, n, d, Sp)) return -100;
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -757,8 +763,8 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
     if ((rc = launch_quad_screen_build_b(Bscr, Ks, Sp, Btc, colmax, st))) return rc;
     sqrt_diag_kernel<<<(unsigned)((T * Sp + 255) / 256), 256, 0, st>>>(post_cov, Sp, T, Dm);
     TES_LAUNCH_OK();
-    for (int64_t c0 = 0; c0 < N; c0 += PS_CHUNK) {
-        const int64_t nc = (N - c0 < PS_CHUNK) ? (N - c0) : PS_CHUNK;
+    for (int64_t c0 = 0; c0 < N; c0 += PS_SCREEN_CHUNK) {
+        const int64_t nc = (N - c0 < PS_SCREEN_CHUNK) ? (N - c0) : PS_SCREEN_CHUNK;
         if ((rc = launch_se_ard(x + c0 * d, nc, xto, m, (int)d, l, sigma, -1, 0.0, Kc, m, st))) return rc;
         if ((rc = launch_gemm(Kc, m, Bext, m + 1, 1, Gc, m + 1, nc, m + 1, m, st))) return rc;
         if ((rc = launch_rowdot(Gc, m + 1, Kc, m, nc, m, sigma, -INFINITY, Kq, st))) return rc;
