@@ -212,9 +212,12 @@ int tes_sp_acq_f64(const double* x, int64_t nx, int q, int64_t d, const double* 
 
 /* Batch TES_ep (criteria/evaluate_batch_mp.py:145-331).  As shipped, the reference scores the
  * samples under the STANDARD normal and builds the marginal from that same log-prob (:302,
- * :317-322), so its value is -(sum p) log(sum p) ~ 0 for every input; this entry
- * point returns exactly that closed form. */
-int tes_batch_ep_acq_f64(const double* p, int64_t Sp, int64_t nx, double* out_acq, void* stream);
+ * :317-322), so its value is -(sum p) log(sum p) ~ 0 for every finite input; this entry
+ * point returns exactly that closed form, and NaN for a query x (nx, q, d) with a non-finite
+ * coordinate (which the reference propagates through its kernel/eigh/log_prob chain, :88-141,
+ * :236-241, :296-302 -- the drivers retry on NaN).  p (Sp): max_probs > 0. */
+int tes_batch_ep_acq_f64(const double* p, int64_t Sp, const double* x, int64_t nx, int64_t q, int64_t d,
+                         double* out_acq, void* stream);
 
 /* ============================================================================ Stage A (draw)
  * optfunc.draw_random_init_weights_features_np (optfunc.py:303-385): the RFF posterior weight draw for S function

@@ -5,15 +5,19 @@ The reference (ZhaoxuanWu/Trusted-Maximizers-Entropy-Search-BO, mounted read-onl
 halves (optfunc.draw_random_init_weights_features_np, optfunc.make_function_sample_np,
 utils.computeK*_np, utils.get_testidxs_stats, utils.sample_multivariate_normal_maxidx_np,
 empirical_approximation.get_empirical_stat_from_samples, ep.approximate_EP_np, functions.*)
-import and run unmodified once `tensorflow`, `tensorflow_probability`, `matplotlib` and
-`keras` are pre-seeded in sys.modules as inert stubs and `np.infty` (removed in numpy 2) is
-shimmed.
+import and run unmodified once `matplotlib` and `keras` are pre-seeded in sys.modules as inert
+stubs and `np.infty` (removed in numpy 2) is shimmed.  `tensorflow` and
+`tensorflow_probability` resolve to oracle/tf_shim -- an eager numpy stand-in for the TF-1.14 /
+TFP-0.7 symbols the hot path uses -- so the TF criteria (`criteria.evaluate_mp`, ...) and the TF
+halves of utils.py (`computeKnm`, `chol2inv`, `compute_mean_var_f`, ...) run unmodified too:
+`load("criteria.evaluate_mp").mp(...)`.
 
 This module is used ONLY by tests/golden/make_golden.py (run in the build container to
 produce the committed fixtures) -- /root/reference does not exist on the GPU box, and
 nothing in the product package, bench.py or the -m gpu tests may import it.
 """
 import contextlib
+import importlib
 import io
 import os
 import sys
@@ -32,9 +36,12 @@ def reference_available():
 def _install_stubs():
     if not hasattr(np, "infty"):
         np.infty = np.inf  # utils.py:1669, empirical_approximation.py:66
+    # tensorflow / tensorflow_probability: the eager numpy shim (oracle/tf_shim), so that the
+    # reference's criteria/*.py and the TF halves of utils.py run unmodified
+    from oracle import tf_shim
+    if not tf_shim.installed():
+        tf_shim.install()
     for name in (
-        "tensorflow",
-        "tensorflow_probability",
         "matplotlib",
         "matplotlib.pyplot",
         "keras",
@@ -71,11 +78,13 @@ def load(module_name):
     try:
         with contextlib.redirect_stdout(io.StringIO()):
             # make sure we get the reference's module, not a same-named one of ours
-            for k in ("utils", "optfunc", "ep", "empirical_approximation", "functions"):
+            for k in ("utils", "optfunc", "ep", "empirical_approximation", "functions", "criteria",
+                      "utils_for_continuous"):
                 mod = sys.modules.get(k)
-                if mod is not None and not getattr(mod, "__file__", "").startswith(REFERENCE_ROOT):
+                where = getattr(mod, "__file__", None) or "".join(getattr(mod, "__path__", []))
+                if mod is not None and not where.startswith(REFERENCE_ROOT):
                     del sys.modules[k]
-            mod = __import__(module_name)
+            mod = importlib.import_module(module_name)
             if module_name == "utils" and not hasattr(mod, "ep"):
                 # utils.get_testidxs_stats(mode='ep') raises NameError as shipped
                 # because utils.py never imports ep.  The oracle calls ep.approximate_EP_np

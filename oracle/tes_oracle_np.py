@@ -39,6 +39,11 @@ import scipy.stats as spst
 
 CLIP_MIN = 1e-100  # utils.py:11
 HALF_LOG_2PI = 0.5 * math.log(2.0 * math.pi)
+# utils.py:653-654 computes its constant as tf.cast(0.5 * tf.log(2*np.pi), dtype): TF 1.14 converts the bare
+# Python float to a float32 tensor, so the value is float32(0.5) * logf(float32(2*pi)) widened to fp64
+# (quirk Q12; found by running the reference's own evaluate_mp.py on oracle/tf_shim)
+NORM_ENTROPY_CONST = float(np.float32(0.5) * np.log(np.float32(2.0 * np.pi)))
+assert NORM_ENTROPY_CONST == 0.918938577175140380859375
 
 
 # --------------------------------------------------------------------------------------
@@ -154,8 +159,8 @@ def compute_mean_f_np(x, Xsamples, Ysamples, l, sigma, sigma0):
 
 
 def evaluate_norm_entropy(s):
-    """utils.py:653-654."""
-    return HALF_LOG_2PI + np.log(s) + 0.5
+    """utils.py:653-654 (float32-rounded constant, Q12)."""
+    return NORM_ENTROPY_CONST + np.log(s) + 0.5
 
 
 # --------------------------------------------------------------------------------------

@@ -133,7 +133,7 @@ def test_batch_tes_ep_is_zero_like_the_reference():
     ref = onp.evaluate_batch_mp(xb, pr["ls"], pr["sigmas"], pr["sigma0s"], pr["X"], pr["Y"], d, n, 1, Yn,
                                 pr["test_xs"], pr["max_probs"], pr["v0"], pr["v1"], pr["invK"], pr["invpNK"],
                                 niteration=I, z=z)
-    acq = ops.batch_ep_acq(p, nx).cpu().numpy()
+    acq = ops.batch_ep_acq(p, xb).cpu().numpy()
     assert np.max(np.abs(ref)) < 1e-12 and np.max(np.abs(acq - ref)) < 1e-12  # absolute bound
 
 

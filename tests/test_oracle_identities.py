@@ -36,7 +36,8 @@ def test_deterministic_matches_hand_formula_with_reduce_mean_quirk():
     pr = make_problem(seed=2, nx=9, mode="empirical", nsample=400, hyp=PH, n=15)
     p, qm, qv = _moments(pr)
     _, varf = onp.compute_mean_var_f(pr["x"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invK"][0])
-    H = lambda s: 0.5 * np.log(2 * np.pi * np.e * s ** 2)
+    # analytic normal entropy, shifted by the reference's float32-rounded constant (Q12, utils.py:653-654)
+    H = lambda s: 0.5 * np.log(2 * np.pi * np.e * s ** 2) + (onp.NORM_ENTROPY_CONST - onp.HALF_LOG_2PI)
     ref = H(np.sqrt(varf + pr["sigma0"])) - np.sum(p[:, None] * H(np.sqrt(qv + pr["sigma0"])), axis=0) / len(p)  # Q4
     got = onp.evaluate_mp(pr["x"], pr["ls"], pr["sigmas"], pr["sigma0s"], pr["X"], pr["Y"], 2, pr["nx"], pr["n"], 1, 10,
                           pr["test_xs"], pr["max_probs"], pr["v0"], pr["v1"], pr["invK"], pr["invpNK"])

@@ -75,7 +75,7 @@ SIGNATURES = {
     "tes_sp_acq_f64": (c_int, [c_ptr, c_i64, c_int, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_dbl, c_dbl,
                                c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_u64, c_i64, c_i64,
                                c_ptr, c_ptr, c_i64, c_ptr]),
-    "tes_batch_ep_acq_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
+    "tes_batch_ep_acq_f64": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
     "tes_rff_draw_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
     "tes_rff_draw_f64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_i64, c_i64,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),

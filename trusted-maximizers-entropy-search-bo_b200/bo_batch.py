@@ -154,7 +154,7 @@ def run(f, xs, xmin, xmax, l, sigma, sigma0, criterion="sftl", mode="sample", nq
                             return evaluate_batch_sample_mp.mp(dev(xb), ls, sigmas, sigma0s, Xd, Yd, xdim, X.shape[0], 1,
                                                                nysample, tx, mp_, v0d, v1b, inv_d, niteration=nsto,
                                                                seed=cseed + step, n_global=-1).cpu().numpy()
-                        return ops.batch_ep_acq(mp_[0][mp_[0] > 0], xb.shape[0]).cpu().numpy()
+                        return ops.batch_ep_acq(mp_[0][mp_[0] > 0], dev(xb)).cpu().numpy()
                     qx, qv = utils_for_continuous.optimize_continuous_function(
                         xdim * q, crit, starts.reshape(-1, xdim * q), top_init_k, np.tile(lo, q), np.tile(hi, q),
                         ntrain=ntrain, fd_step=fd_step)

@@ -17,6 +17,11 @@
 namespace tes {
 
 constexpr double HALF_LOG_2PI = 0.91893853320467274178;
+// utils.evaluate_norm_entropy (utils.py:653-654) writes tf.cast(0.5 * tf.log(2*np.pi), dtype): TF turns the
+// bare Python float into a float32 tensor, so the entropy constant is float32(0.5 * logf(6.2831855f)) widened to
+// fp64 -- 4.4e-8 above 0.5*log(2*pi) (SURVEY quirk list, Q12; pinned by tests/golden/criteria.npz).  TFP's
+// Normal.log_prob uses the fp64 constant (HALF_LOG_2PI).
+constexpr double NORM_ENTROPY_CONST = 0.918938577175140380859375;
 
 // ---- TES_ep query moments: var[x][j] = Kq[x] + M[x]^T Sigma_j M[x]  (evaluate_mp.py:103-107) ----
 // The quadratic form is a GEMM over the index pairs (a <= b) of the symmetric Sigma_j:
@@ -134,11 +139,11 @@ __global__ void ep_det_kernel(const double* __restrict__ var, const double* __re
     double s = 0.0;
     for (int64_t j = lane; j < Sp; j += 32) {
         double sd = sqrt(var[row * Sp + j] + sigma0);  // no clipping: negative -> NaN
-        s += ((HALF_LOG_2PI + log(sd)) + 0.5) * p[j];
+        s += ((NORM_ENTROPY_CONST + log(sd)) + 0.5) * p[j];
     }
     s = warp_sum(s);
     if (lane == 0) {
-        double ent = (HALF_LOG_2PI + log(sqrt(varf[row] + sigma0))) + 0.5;
+        double ent = (NORM_ENTROPY_CONST + log(sqrt(varf[row] + sigma0))) + 0.5;
         out[row] = ent - s / (double)Sp;  // reduce_MEAN over j
     }
 }
@@ -499,13 +504,19 @@ __global__ void __launch_bounds__(256)
     if (bad && info && lane == 0) atomicAdd(info, 1);
 }
 
-__global__ void const_fill_kernel(double* out, int64_t n, const double* __restrict__ p, int64_t Sp) {
+__global__ void batch_ep_kernel(double* out, int64_t n, const double* __restrict__ p, int64_t Sp,
+                                const double* __restrict__ x, int64_t qd) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     double s = 0.0;
     for (int64_t j = 0; j < Sp; ++j) s += p[j];
-    // evaluate_batch_mp.py:302-327: ent - cond == -(sum p) * log(sum p) for every input
-    out[e] = -s * log(s);
+    // evaluate_batch_mp.py:302-327: ent - cond == -(sum p) * log(sum p) for every finite input.  A
+    // non-finite coordinate of the query reaches the result through k_x_xto -> cov -> eigh -> y -> log_prob
+    // (:88-141, :236-241, :296-302; inf gives inf - inf in the squared-distance expansion), so the reference
+    // returns NaN for that query (the drivers retry on NaN, bo_batch.py:1080-1081).
+    bool finite = true;
+    for (int64_t c = 0; c < qd; ++c) finite = finite && isfinite(x[e * qd + c]);
+    out[e] = finite ? -s * log(s) : __longlong_as_double(0x7ff8000000000000LL);
 }
 
 struct EpPlan {
@@ -688,14 +699,14 @@ __global__ void ep_det_screen_kernel(const double* __restrict__ Qt, const double
         const double h = H[row * Sp + j];
         const double w = (kq + Qt[row * Sp + j]) + sigma0;
         const double delta = QS_ETA * h * h + 1e-300;
-        s += ((HALF_LOG_2PI + log(sqrt(w))) + 0.5) * p[j];
+        s += ((NORM_ENTROPY_CONST + log(sqrt(w))) + 0.5) * p[j];
         const double e1 = (w > delta) ? 0.5 * log(w / (w - delta)) : pos_inf();   // NaN w -> false -> +inf
         er += e1 * p[j];
     }
     s = warp_sum(s);
     er = warp_sum(er);
     if (lane == 0) {
-        double ent = (HALF_LOG_2PI + log(sqrt(varf[row] + sigma0))) + 0.5;
+        double ent = (NORM_ENTROPY_CONST + log(sqrt(varf[row] + sigma0))) + 0.5;
         const double a = ent - s / (double)Sp;
         out_acq[row] = a;
         out_eps[row] = er / (double)Sp + 1e-13 * fabs(a);   // + rounding slack of the two fp64 evaluations
@@ -954,13 +965,17 @@ extern "C" int tes_sp_acq_f64(const double* x, int64_t nx, int q, int64_t d, con
     return 0;
 }
 
-extern "C" int tes_batch_ep_acq_f64(const double* p, int64_t Sp, int64_t nx, double* out_acq, void* stream) {
+extern "C" int tes_batch_ep_acq_f64(const double* p, int64_t Sp, const double* x, int64_t nx, int64_t q, int64_t d,
+                                    double* out_acq, void* stream) {
     if (!p) return -1;
     if (Sp < 1) return -2;
-    if (nx < 0) return -3;
-    if (nx > 0 && !out_acq) return -4;
+    if (nx < 0) return -4;
+    if (nx > 0 && !x) return -3;
+    if (q < 1) return -5;
+    if (d < 1) return -6;
+    if (nx > 0 && !out_acq) return -7;
     if (nx == 0) return 0;
-    const_fill_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out_acq, nx, p, Sp);
+    batch_ep_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out_acq, nx, p, Sp, x, q * d);
     TES_LAUNCH_OK();
     return 0;
 }

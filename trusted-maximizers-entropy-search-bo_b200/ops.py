@@ -426,10 +426,16 @@ def sp_acq(x, test_xs, X, Y, l, sigma, sigma0, invpNK, p, post_samples, post_mas
     return acq
 
 
-def batch_ep_acq(p, nx):
+def batch_ep_acq(p, x):
+    """Batch TES_ep (evaluate_batch_mp.py:145-331): -(sum p) log(sum p) per query, NaN for a non-finite query.
+    x (nx, q, d)."""
     p = dev(p).reshape(-1)
+    x = dev(x, p.device)
+    if x.dim() != 3:
+        raise ValueError("x must be (nx, batchsize, xdim)")
+    nx, q, d = x.shape
     out = torch.empty((nx,), dtype=torch.float64, device=p.device)
-    rc = _lib.lib().tes_batch_ep_acq_f64(ptr(p), p.numel(), nx, ptr(out), stream_ptr())
+    rc = _lib.lib().tes_batch_ep_acq_f64(ptr(p), p.numel(), ptr(x), nx, q, d, ptr(out), stream_ptr())
     _lib.check(rc, "tes_batch_ep_acq_f64")
     return out
 

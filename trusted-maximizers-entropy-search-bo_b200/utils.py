@@ -106,11 +106,16 @@ def compute_mean_f(x, xdim, n_hyp, Xsamples, Ysamples, ls, sigmas, sigma0s, NKIn
     return _ret(acc, x)
 
 
+NORM_ENTROPY_CONST = 0.918938577175140380859375  # float32(0.5) * logf(float32(2*pi))
+
+
 def evaluate_norm_entropy(s, dtype=None):
-    """utils.py:653-654."""
+    """utils.py:653-654.  The reference's constant is tf.cast(0.5 * tf.log(2*np.pi), dtype): a bare Python
+    float becomes a float32 tensor in TF 1.14, so it is float32(0.5*logf(2*pi)) widened (quirk Q12)."""
+    c = NORM_ENTROPY_CONST
     if torch.is_tensor(s):
-        return 0.5 * np.log(2 * np.pi) + torch.log(s) + 0.5
-    return 0.5 * np.log(2 * np.pi) + np.log(s) + 0.5
+        return c + torch.log(s) + 0.5
+    return c + np.log(s) + 0.5
 
 
 def _np(a):
