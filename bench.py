@@ -7,7 +7,8 @@ input.  Default workload = config C3 of BASELINE.json (the largest single-GPU co
 Hartmann-6 hyper-parameters, 10^6 candidates per GPU (the 10-per-axis mesh of functions.get_meshgrid; with N ranks the
 global mesh has 10 N points along its slowest axis and every rank holds one 10^6-point slab), S = 1024 RFF function samples with F = 1024 features each, n = 64
 observations, TES_ep (criterion ftl, mode empirical, deterministic) on the <= t_max most frequent
-trusted maximizers.  theta/W/b are host-supplied draws (optfunc.py:303-385), inputs of the step.
+trusted maximizers.  The three global-RNG draws of the RFF posterior weight draw (optfunc.py:329, :334, :344) are
+host-supplied inputs of the step; the draw itself (theta/W/b, optfunc.py:303-385) runs inside the timed step.
 
   value    evals/s with every input already resident in HBM (device-timed, max over ranks)
   e2e      the same step through the reference-facing Python API with HOST (pinned) buffers: H2D copies
@@ -27,6 +28,13 @@ import subprocess
 import sys
 import threading
 import time
+
+# the CPU arm uses every host core, whatever the launcher exported (torch.distributed.run
+# sets OMP_NUM_THREADS=1 for its workers).  Must happen before numpy / OpenMP load.
+CPU_THREADS = os.cpu_count() or 1
+if "--impl" in sys.argv and "reference" in sys.argv:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(CPU_THREADS)
 
 import numpy as np
 
@@ -62,7 +70,9 @@ def meshgrid(xmin, xmax, nx, xdim, slab=0, nslab=1):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE rff_screen_tc5_kernel launch, from the ncu --set full capture
 # summarised in profiles/ (filled per workload once measured; None = not captured)
-TC5_TRAFFIC_BYTES = {"c3": 465.8e6}   # profiles/r01_ncu_rff_screen_tc5.md (algorithmic: 115 MB)
+TC5_TRAFFIC_BYTES = {"c3": 465.8e6, "c3u": 465.8e6}   # profiles/r01_ncu_rff_screen_tc5.md (algorithmic: 115 MB)
+# same for ONE launch of the product-path GEMM kernel (stage A on meshes)
+PROD_TRAFFIC_BYTES = {"c3": 775.6e6}  # profiles/r01_ncu_prod_gemm_tcgen05.md (read 754.5 + write 21.1 MB)
 
 WORKLOADS = {
     # d, N per GPU, S function samples, F features, n observations, t_max test points; criterion/mode/q and the
@@ -141,23 +151,15 @@ def make_workload(name, rank, world, host_only=False):
     else:
         cand = np.random.RandomState(7 + rank).rand(N, d) * wl["xmax"]
     np.random.seed(11)  # identical draws on every rank
-    # the RFF posterior weight draw (optfunc.py:303-385): on the device for the b200 arm; the CPU reference arm runs
-    # the oracle's numpy restatement (where the reference runs it).  Same np.random draws, same order, either way.
+    # The three global-RNG draws of the RFF posterior weight draw (optfunc.py:329, :334, :344), in the reference's
+    # order: the INPUTS of a step.  Stage A0 (theta/W/b from them, optfunc.py:303-385) runs INSIDE the timed step, on
+    # the device for the b200 arm and as the oracle's numpy restatement (where the reference runs it) for the CPU arm.
     # The CPU arm only ever uses the first `ns` function samples (cpu_sample_sizes), so it only draws those.
     if host_only:
-        from oracle import tes_oracle_np as onp
         S = min(S, cpu_sample_sizes(wl)[1])
-        randn_W, rand_b, noise = np.random.randn(S, F, d), np.random.rand(S, F, 1), np.random.randn(S, F, 1)
-        theta, W, b = onp.draw_random_init_weights_features(d, S, F, X, Y, hyp["l"].reshape(1, d), hyp["sigma"],
-                                                            hyp["sigma0"], randn_W, rand_b, noise)
-    else:
-        from tes_b200 import optfunc
-        randn_W, rand_b, noise = np.random.randn(S, F, d), np.random.rand(S, F, 1), np.random.randn(S, F, 1)
-        theta, W, b = optfunc.draw_random_init_weights_features_np(d, S, F, X, Y, hyp["l"].reshape(1, d), hyp["sigma"],
-                                                                   hyp["sigma0"], draws=(randn_W, rand_b, noise))
-    wl.update(name=name, hyp=hyp, X=X, Y=Y, cand=np.ascontiguousarray(cand),
-              theta=np.ascontiguousarray(theta.reshape(-1, F)), W=np.ascontiguousarray(W),
-              b=np.ascontiguousarray(b.reshape(-1, F)))
+    randn_W, rand_b, noise = np.random.randn(S, F, d), np.random.rand(S, F, 1), np.random.randn(S, F, 1)
+    wl.update(name=name, hyp=hyp, X=X, Y=Y, cand=np.ascontiguousarray(cand), randn_W=randn_W, rand_b=rand_b,
+              noise=noise)
     return wl
 
 
@@ -190,12 +192,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
                 for nme, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
@@ -204,7 +207,7 @@ class ClockSampler:
         if not sm:
             return None
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": float(np.median(pw)) if pw else None}
 
 
 def cpu_step(wl, n_cand, n_samp, seed=0):
@@ -217,8 +220,8 @@ def cpu_step(wl, n_cand, n_samp, seed=0):
     kw = step_kwargs(wl)
     kw["ntestsample"] = min(kw["ntestsample"], max(1000, 64 * min(wl["t_max"], n_samp)))
     out = pipeline_np.tes_step(cand, wl["X"], wl["Y"], wl["hyp"]["l"], wl["hyp"]["sigma"], wl["hyp"]["sigma0"],
-                               wl["theta"][:n_samp].reshape(n_samp, wl["F"], 1), wl["W"][:n_samp],
-                               wl["b"][:n_samp].reshape(n_samp, wl["F"], 1), seed=seed, **kw)
+                               None, None, None, seed=seed,
+                               draws=(wl["randn_W"][:n_samp], wl["rand_b"][:n_samp], wl["noise"][:n_samp]), **kw)
     dt = time.perf_counter() - t0
     return cand.shape[0] * n_samp, dt, out
 
@@ -236,7 +239,6 @@ def run_reference_arm(args, wl, rank):
     if rank != 0:
         return
     nc, ns = cpu_sample_sizes(wl)
-    cores = os.cpu_count()
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_step(wl, nc, ns)
     times, pairs = [], 0
@@ -245,14 +247,16 @@ def run_reference_arm(args, wl, rank):
         times.append(dt)
     tmean = float(np.mean(times))
     val = pairs / tmean
-    sample = "first %d candidates x first %d function samples of %s (F=%d, n=%d), full step A-D" % (
-        nc, ns, wl["name"], wl["F"], wl["n"])
+    sample = ("first %d candidates x first %d function samples of %s (F=%d, n=%d), full step A0-D (weight draw included); "
+              "threads: OMP_NUM_THREADS=%s OPENBLAS_NUM_THREADS=%s os.cpu_count()=%d" % (
+                  nc, ns, wl["name"], wl["F"], wl["n"], os.environ.get("OMP_NUM_THREADS"),
+                  os.environ.get("OPENBLAS_NUM_THREADS"), os.cpu_count()))
     line = {
         "impl": "reference", "metric": "acq evals/s (candidates x maximizer samples)", "value": val, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tmean * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_of(wl),
-        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": CPU_THREADS, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -280,6 +284,237 @@ def _emit(line):
     sys.stdout.flush()
 
 
+STAGES = [("draw", "A0_draw_ms"), ("rff_topk", "A_maximizers_ms"), ("stage_b", "B_posterior_ms"),
+          ("stage_c", "C_maximizer_stats_ms"), ("criterion", "D_criterion_ms"), ("criterion_screen", "D_screen_ms")]
+REPLICATED = ["X", "Y", "randn_W", "rand_b", "noise"]   # identical on every rank; "cand" is the rank's own shard
+
+
+class Bench:
+    """One process per GPU.  Holds the distributed context and runs timed loops of acquisition.tes_step."""
+
+    def __init__(self, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def gather(self, vec):
+        """(k,) floats of this rank -> (world, k) numpy on every rank."""
+        t = self.torch.tensor(vec, dtype=self.torch.float64, device="cuda")
+        if self.world == 1:
+            return t.cpu().numpy()[None]
+        out = self.torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device="cuda")
+        self.dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy()
+
+    def upload(self, host, names):
+        """Pinned host buffers -> device.  The rank's candidate shard comes over its own PCIe link; the REPLICATED
+        operands cross PCIe once (rank 0) and reach the other GPUs through one NCCL broadcast over NVLink."""
+        torch = self.torch
+        out = {}
+        for k in names:
+            if self.world > 1 and k in REPLICATED:
+                t = host[k].cuda(non_blocking=True) if self.rank == 0 else \
+                    torch.empty(host[k].shape, dtype=host[k].dtype, device="cuda")
+                self.dist.broadcast(t, 0)
+                out[k] = t
+            else:
+                out[k] = host[k].cuda(non_blocking=True)
+        return out
+
+    def run(self, wl, steps, warmup, deterministic=True, want_e2e=True, sample_clocks=False):
+        """Timed loop over one workload -> dict (value, ms, stages, e2e, launches, last step's out)."""
+        torch = self.torch
+        from tes_b200 import _lib, acquisition, ops
+        hyp, kw = wl["hyp"], step_kwargs(wl)
+        kw["deterministic"] = deterministic
+        shard = acquisition.Shard(wl["N"])
+        names = ["cand"] + REPLICATED
+        host = {k: torch.from_numpy(np.ascontiguousarray(wl[k])).pin_memory() for k in names}
+        devt = {k: host[k].cuda(non_blocking=True) for k in names}
+        h2d_bytes = sum(host[k].numel() * 8 for k in names)
+
+        def step(d_, seed, timers=None, **extra):
+            k2 = dict(kw, **extra)
+            return acquisition.tes_step(d_["cand"], d_["X"], d_["Y"], hyp["l"], hyp["sigma"], hyp["sigma0"], None, None,
+                                        None, seed=seed, shard=shard, timers=timers,
+                                        draws=(d_["randn_W"], d_["rand_b"], d_["noise"]), **k2)
+
+        for w in range(warmup):
+            self.flush.zero_()
+            out = step(devt, w)
+        self.barrier()
+        sampler = ClockSampler(self.local_rank) if sample_clocks else None
+        timers = {}
+        ops.STATS["product_flagged"] = 0
+        launches0 = _lib.lib().tes_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for s in range(steps):
+            self.flush.zero_()  # L2 flush between timed iterations (its ~0.05 ms is inside the timed region)
+            out = step(devt, 1000 + s, timers)
+        e1.record()
+        self.barrier()
+        launches = _lib.lib().tes_launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        dev_s = self.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+        pairs_step = shard.n_global * wl["S"]
+        res = {"value": pairs_step * steps / dev_s, "ms_per_step": dev_s / steps * 1e3, "steps": steps, "out": out,
+               "launches": int(launches), "clocks": clocks, "shard": shard, "devt": devt, "step": step,
+               "flagged_samples_per_step": ops.STATS["product_flagged"] / steps, "timers": timers}
+        # per-stage milliseconds (CUDA events on the launching stream), mean over steps; min / max over ranks
+        mine = [float(np.mean([a.elapsed_time(b_) for a, b_ in timers[k]])) if timers.get(k) else float("nan")
+                for k, _ in STAGES]
+        allr = self.gather(mine + [clocks["power_w"] if clocks and clocks.get("power_w") else float("nan")])
+        res["stages"] = {lbl: {"rank0": allr[0, i], "min": float(np.nanmin(allr[:, i])), "max": float(np.nanmax(allr[:, i]))}
+                         if self.world > 1 else allr[0, i] for i, (_, lbl) in enumerate(STAGES)
+                         if not np.all(np.isnan(allr[:, i]))}
+        res["t_stage_a"] = mine[1] * 1e-3
+        res["t_criterion"] = mine[4] * 1e-3
+        if not want_e2e:
+            return res
+
+        # ---- e2e: the same step from pinned HOST buffers, H2D of every input + D2H of the result inside the region
+        def step_e2e(seed):
+            d_ = self.upload(host, names)
+            o = step(d_, seed)
+            _ = o["argmax_idx"].cpu()  # D2H: the S trusted-maximizer indices (+ query idx/value/point already on host)
+            return o
+        step_e2e(0)
+        self.barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for s in range(steps):
+            self.flush.zero_()
+            step_e2e(2000 + s)
+        e1.record()
+        self.barrier()
+        e2e_s = self.max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0))
+        res["e2e"] = {"value": pairs_step * steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(h2d_bytes),
+                      "d2h_bytes_per_step": int(wl["S"] * 8 + 8 + 8 + wl["d"] * wl["q"] * 8),
+                      "ms_per_step": e2e_s / steps * 1e3,
+                      "replicated_inputs": "rank 0 H2D + NCCL broadcast" if self.world > 1 else "H2D"}
+        return res
+
+
+def roofline_of(wl, res, product, peaks, fp64_peak, fp32_peak, mufu_peak):
+    """Roofline object of the dominant kernel group (stage A) from the CUDA-event time of the timed region."""
+    t_rff, t_crit = res["t_stage_a"], res["t_criterion"]
+    d, F = wl["d"], wl["F"]
+    local_pairs = wl["N"] * wl["S"]
+    algo_excl_cos = local_pairs * F * (2 * d + 3) / t_rff * 1e-12  # SURVEY 8(d) figure, cos not counted
+    screened = wl["N"] >= 32768 and d <= 10
+    common = {"launch_ms": t_rff * 1e3, "share_of_step": t_rff * 1e3 / res["ms_per_step"],
+              "criterion_ms": t_crit * 1e3, "algorithmic_excl_cos_tflops": algo_excl_cos,
+              "fp64_fma_peak_tflops": fp64_peak, "mufu_peak_tcos": mufu_peak}
+    if product:
+        # stage A on a product-structured candidate set = one GEMM per function sample (csrc/rffprod.cu), run as a
+        # 3xFP16 screen on the tensor cores (tcgen05.mma kind::f16 + TMEM) followed by the exact fp64 re-evaluation
+        # of the k + 8 best candidates per sample.  algorithmic: 2 * N * 2F flops per sample (the fp64 GEMM being
+        # emulated); executed: 3x that in fp16.
+        bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        gflops = 2.0 * local_pairs * 2 * F
+        achieved = 3.0 * gflops / t_rff * 1e-12
+        return dict(common, **{
+            "bound": "tensor",
+            "pipe": "5th-gen tensor cores: tcgen05.mma kind::f16, accumulators in TMEM, operands generated on the SM",
+            "kernel": "stage-A group: product GEMM + top-k epilogue (+ list merge, exact fp64 refine)",
+            "achieved": achieved, "peak": bf16, "unit": "TFLOP/s", "frac": achieved / bf16,
+            "achieved_is": "EXECUTED 3xFP16 tensor flops (12F per pair) / stage-A time (CUDA events, timed region)",
+            "frac_algorithmic": gflops / t_rff * 1e-12 / bf16,
+            "algorithmic_is": "4F flops per pair (the fp64 GEMM the 3xFP16 split emulates) against the same tensor peak; "
+                              "SURVEY 8d's F*(2d+3) flops + F cos per pair is algorithmically different work (this path "
+                              "replaces the cosines by the angle-addition GEMM) and is reported as algorithmic_excl_cos_tflops",
+            "traffic": PROD_TRAFFIC_BYTES.get(wl["name"]),
+            "peak_source": "bf16_tflops_sustained of MEASURED_PEAKS.json (cuBLAS, %s)" % (
+                "measured" if peaks else "fallback 1400"),
+            "algorithmic_fp64_gemm_tflops": gflops / t_rff * 1e-12,
+            "equivalent_tcos": local_pairs * F / t_rff * 1e-12,
+            "per_unit": "product-structured candidates (slow columns [%d, %d), nv=%d): 4F GEMM flops per (candidate, "
+                        "sample) pair (12F executed as 3xFP16) instead of F cosines" % product})
+    if screened and d >= 5:
+        cos_rate = local_pairs * F / t_rff * 1e-12
+        return dict(common, **{
+            "bound": "mufu", "kernel": "rff_screen_tc5_kernel (+ pack/xmax/bound/refine/fallback/merge)",
+            "achieved": cos_rate, "peak": mufu_peak, "unit": "Tcos/s", "frac": cos_rate / mufu_peak,
+            "frac_algorithmic": cos_rate / mufu_peak,
+            "traffic": TC5_TRAFFIC_BYTES.get(wl["name"]),
+            "peak_source": "measured in this run: tes_mufu_cos_burn (__cosf = FMUL.RZ + MUFU.COS, 8 chains/thread)",
+            "fp32_peak_tflops": fp32_peak, "algorithmic_vs_fp64_peak": algo_excl_cos / fp64_peak,
+            "per_unit": "F cosines (7/8 MUFU.COS, 1/8 FMA-pipe polynomial) + F*(3d+2) TF32 tcgen05 MACs per (candidate, "
+                        "sample) pair; algorithmic = F*(2d+3) flops + F cos (SURVEY 8d)"})
+    if screened:
+        ops32 = local_pairs * F * (d + 5)
+        achieved = 2.0 * ops32 / t_rff * 1e-12
+        return dict(common, **{
+            "bound": "fp32", "kernel": "rff_screen_kernel (+ pack/xmax/bound/refine/fallback/merge)",
+            "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+            "peak_source": "measured in this run: tes_fp32_fma_burn (packed FFMA2, 8 chains/thread, 1 s)",
+            "algorithmic_vs_fp64_peak": algo_excl_cos / fp64_peak, "mufu_cos_per_s": local_pairs * F / t_rff,
+            "per_unit": "F*(d+5) fp32-pipe lane ops + F MUFU.COS per (candidate, sample) pair; "
+                        "algorithmic = F*(2d+3) flops + F cos (SURVEY 8d)"})
+    instr = local_pairs * F * (d + 13)           # fp64-pipe instructions per launch (tes_spec.h sequence)
+    achieved = 2.0 * instr / t_rff * 1e-12       # FMA-equivalent TFLOP/s, same convention as the DFMA burn
+    return dict(common, **{
+        "bound": "fp64", "kernel": "rff_topk_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": achieved / fp64_peak, "traffic": None,
+        "peak_source": "measured in this run: tes_fp64_fma_burn (8 DFMA chains/thread, 1 s sustained)",
+        "per_unit": "F*(d+13) fp64-pipe instr per (candidate, sample) pair = F*(2d+3) flops + F cos"})
+
+
+def parity_check(bench, wl, res):
+    """Outside the timed region: the screened step against the all-fp64 step, and the product-path stage A against
+    the general kernel on the first samples -- the fast paths must select the same things."""
+    torch = bench.torch
+    from tes_b200 import ops, optfunc
+    out = {}
+    devt, step = res["devt"], res["step"]
+    if wl["criterion"] == "ftl":
+        a = step(devt, 4242)
+        b = step(devt, 4242, screen=False)
+        same = (a["query_idx"] == b["query_idx"] and a["query_val"] == b["query_val"]
+                and np.array_equal(a["query_x"], b["query_x"]))
+        out["screened_step_vs_fp64_step"] = {"identical_query": bool(same), "query_idx": int(a["query_idx"]),
+                                             "query_val": a["query_val"], "screen_kept": a.get("screen_kept"),
+                                             "trusted_maximizers_identical": bool(torch.equal(a["argmax_idx"], b["argmax_idx"]))}
+    product = ops.detect_product_structure(devt["cand"]) if wl["N"] >= ops.PRODUCT_MIN_N else None
+    if product:
+        ns = min(16, wl["S"])
+        theta, W, b_ = optfunc.draw_random_init_weights_features(
+            wl["d"], ns, wl["F"], devt["X"], devt["Y"], wl["hyp"]["l"], wl["hyp"]["sigma"], wl["hyp"]["sigma0"],
+            draws=(devt["randn_W"][:ns], devt["rand_b"][:ns], devt["noise"][:ns]))
+        i1, v1 = ops.rff_topk(devt["cand"], W, b_, theta, wl["hyp"]["sigma"], k=3, product=product)
+        i2, v2 = ops.rff_topk(devt["cand"], W, b_, theta, wl["hyp"]["sigma"], k=3, product=False)
+        out["product_stage_a_vs_general_kernel"] = {"samples": ns, "k": 3, "indices_identical": bool(torch.equal(i1, i2)),
+                                                    "values_bit_identical": bool(torch.equal(v1, v2))}
+    return out
+
+
+def c5_sweep(bench, sizes=(64, 128, 256, 512, 1024, 2048), batch=1024, reps=2):
+    """BASELINE config 5: batched maximizer-conditioned chol2inv (utils.py:1859-1883), batch sharded over the ranks
+    without any collective.  One record per m (scripts/bench_chol_sweep.py holds the stand-alone version)."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import bench_chol_sweep as cs
+    return cs.sweep(bench.torch, bench.dist, bench.rank, bench.world, list(sizes), batch, reps, cpu=False,
+                    flush=bench.flush)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -287,8 +522,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--stochastic", action="store_true", help="TES_ep stochastic estimator (the reference's default, "
+                    "bo_discrete.py --deterministic 0) instead of the deterministic one")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the C2 latency case reported beside C3")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads reported beside C3")
     args = ap.parse_args()
     _stdout_to_stderr()
 
@@ -302,237 +539,123 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
-    from tes_b200 import _lib, acquisition, ops
+    from tes_b200 import ops
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    bench = Bench(rank, world, local_rank)
     wl = make_workload(args.workload, rank, world)
-    hyp = wl["hyp"]
-    kw = step_kwargs(wl)
-    shard = acquisition.Shard(wl["N"])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident inputs (for `value`) and pinned host inputs (for `e2e`)
-    names = ["cand", "X", "Y", "theta", "W", "b"]
-    host = {k: torch.from_numpy(wl[k]).pin_memory() for k in names}
-    devt = {k: host[k].cuda(non_blocking=True) for k in names}
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    h2d_bytes = sum(host[k].numel() * 8 for k in names)
-
-    def step_device(seed, timers=None):
-        return acquisition.tes_step(devt["cand"], devt["X"], devt["Y"], hyp["l"], hyp["sigma"], hyp["sigma0"],
-                                    devt["theta"], devt["W"], devt["b"], seed=seed, shard=shard, timers=timers, **kw)
-
-    def step_e2e(seed):
-        d_ = {k: host[k].cuda(non_blocking=True) for k in names}  # pinned host -> device, every step
-        out = acquisition.tes_step(d_["cand"], d_["X"], d_["Y"], hyp["l"], hyp["sigma"], hyp["sigma0"], d_["theta"],
-                                   d_["W"], d_["b"], seed=seed, shard=shard, **kw)
-        _ = out["argmax_idx"].cpu()  # D2H: the S trusted-maximizer indices (+ query idx/value/point already on host)
-        return out
-
-    # ---- fp64 pipe peak (roofline denominator; not in MEASURED_PEAKS.json)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    # ---- in-run pipe peaks (roofline denominators that MEASURED_PEAKS.json does not carry)
     fp64_peak = ops.fp64_fma_peak(1.0)
     fp32_peak = ops.fp32_fma_peak(1.0)
     mufu_peak = ops.mufu_cos_peak(1.0)
 
-    for w in range(args.warmup):
-        flush.zero_()
-        out = step_device(w)
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    timers = {}
-    launches0 = _lib.lib().tes_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    flush_ms = 0.0
-    barrier()
-    e0.record()
-    for s in range(args.steps):
-        flush.zero_()  # L2 flush between timed iterations (its ~0.05 ms is inside the timed region)
-        out = step_device(1000 + s, timers)
-    e1.record()
-    barrier()
-    launches = _lib.lib().tes_launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
-    dev_s = e0.elapsed_time(e1) * 1e-3
-    tt = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_s = float(tt[0])
-    pairs_step = shard.n_global * wl["S"]
-    value = pairs_step * args.steps / dev_s
-
-    # ---- e2e with host buffers
-    step_e2e(0)
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for s in range(args.steps):
-        flush.zero_()
-        out2 = step_e2e(2000 + s)
-    e1.record()
-    barrier()
-    e2e_s = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0)
-    tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_s = float(tt[0])
-    e2e_val = pairs_step * args.steps / e2e_s
-    d2h_bytes = wl["S"] * 8 + 8 + 8 + wl["d"] * 8
-
-    # ---- roofline of the dominant kernel (stage A: rff_pack + rff_topk + merge), CUDA events per launch
-    ra = [a.elapsed_time(b_) * 1e-3 for a, b_ in timers.get("rff_topk", [])]
-    rc = [a.elapsed_time(b_) * 1e-3 for a, b_ in timers.get("criterion", [])]
-    t_rff = float(np.mean(ra)) if ra else float("nan")
-    d, F = wl["d"], wl["F"]
-    local_pairs = wl["N"] * wl["S"]
-    algo_excl_cos = local_pairs * F * (2 * d + 3) / t_rff * 1e-12  # SURVEY 8(d) figure, cos not counted
-    screened = wl["N"] >= 32768 and d <= 10
-    product = ops.detect_product_structure(devt["cand"]) if wl["N"] >= ops.PRODUCT_MIN_N else None
-    if product:
-        # stage A on a product-structured candidate set = one GEMM per function sample (csrc/rffprod.cu), run as a
-        # 3xFP16 screen on the tensor cores (tcgen05.mma kind::f16 + TMEM, hi/lo fp16 operands, fp32 segments of 256 k
-        # drained from TMEM into fp64 sums)
-        # followed by the exact fp64 re-evaluation of the k + 8 best candidates per sample.
-        # algorithmic: 2 * N * 2F flops per sample (the fp64 GEMM); executed: 3x that in fp16
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        tf32_peak = bf16                # fp16 dense tensor rate = the bf16 rate
-        gflops = 2.0 * local_pairs * 2 * F
-        achieved = 3.0 * gflops / t_rff * 1e-12
-        roofline = {"bound": "tensor", "pipe": "5th-gen tensor cores: tcgen05.mma kind::f16 (M128 N128 K16), accumulators in TMEM, operands by "
-                            "1-D bulk async copies (TMA engine) in a 3-stage mbarrier ring",
-                    "kernel": "prod_gemm_topk_tc_kernel (+ operand build, list merge, exact fp64 refine)",
-                    "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-                    "traffic": 775.6e6 if wl["name"] == "c3" else None,   # profiles/r01_ncu_prod_gemm_tcgen05.md, per launch (read 754.5 + write 21.1 MB)
-                    "kernel_alone": "745 us per 45-sample launch = 742 TFLOP/s = 0.56 of the peak (ncu, profiles/)",
-                    "peak_source": "bf16_tflops_sustained of MEASURED_PEAKS.json (cuBLAS, %s)" % (
-                        "measured" if peaks else "fallback 1400"),
-                    "algorithmic_fp64_gemm_tflops": gflops / t_rff * 1e-12,
-                    "fp64_fma_peak_tflops": fp64_peak, "mufu_peak_tcos": mufu_peak,
-                    "algorithmic_excl_cos_tflops": algo_excl_cos,
-                    "equivalent_tcos": local_pairs * F / t_rff * 1e-12,
-                    "per_unit": "product-structured candidates (slow columns [%d, %d), nv=%d): 4F GEMM flops per (candidate, "
-                                "sample) pair (12F executed as 3xFP16) instead of F cosines; SURVEY 8d algorithmic = "
-                                "F*(2d+3) flops + F cos" % product,
-                    "launch_ms": t_rff * 1e3, "share_of_step": t_rff * args.steps / dev_s,
-                    "criterion_ms": float(np.mean(rc)) * 1e3 if rc else None}
-    elif screened and d >= 5:
-        # stage A = tcgen05/TMEM screen (3xTF32 dot products on the 5th-gen tensor cores, cosine on the MUFU with 1 of
-        # every 8 pairs on the FMA pipe) + exact fp64 refine: one cosine per (candidate, sample, feature) on the XU
-        # pipe (16 lanes/SM/clk) is the binding resource
-        cos_rate = local_pairs * F / t_rff * 1e-12
-        roofline = {"bound": "mufu", "kernel": "rff_screen_tc5_kernel (+ pack/xmax/bound/refine/fallback/merge)",
-                    "achieved": cos_rate, "peak": mufu_peak, "unit": "Tcos/s", "frac": cos_rate / mufu_peak,
-                    "traffic": TC5_TRAFFIC_BYTES.get(wl["name"]),
-                    "peak_source": "measured in this run: tes_mufu_cos_burn (__cosf = FMUL.RZ + MUFU.COS, 8 chains/thread)",
-                    "fp64_peak_tflops": fp64_peak, "fp32_peak_tflops": fp32_peak,
-                    "algorithmic_excl_cos_tflops": algo_excl_cos,
-                    "algorithmic_vs_fp64_peak": algo_excl_cos / fp64_peak,
-                    "per_unit": "F cosines (7/8 MUFU.COS, 1/8 FMA-pipe polynomial) + F*(3d+2) TF32 tcgen05 MACs per (candidate, sample) pair; "
-                                "algorithmic = F*(2d+3) flops + F cos (SURVEY 8d)",
-                    "launch_ms": t_rff * 1e3, "share_of_step": t_rff * args.steps / dev_s,
-                    "criterion_ms": float(np.mean(rc)) * 1e3 if rc else None}
-    elif screened:
-        # stage A = fp32 screen (all pairs, packed FFMA2 + MUFU) + exact fp64 refine of the kept candidates.
-        # fp32-pipe lane operations per (pair, feature): d (dot) + 3 (2*pi reduction) + 1 (theta) packed FMA
-        # lanes + 1 FMUL inside __cosf = d + 5, plus 1 MUFU.COS (XU pipe, reported separately).
-        ops32 = local_pairs * F * (d + 5)
-        achieved = 2.0 * ops32 / t_rff * 1e-12
-        roofline = {"bound": "fp32", "kernel": "rff_screen_kernel (+ pack/xmax/bound/refine/fallback/merge)",
-                    "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                    "traffic": None,
-                    "peak_source": "measured in this run: tes_fp32_fma_burn (packed FFMA2, 8 chains/thread, 1 s)",
-                    "fp64_peak_tflops": fp64_peak,
-                    "algorithmic_excl_cos_tflops": algo_excl_cos,
-                    "algorithmic_vs_fp64_peak": algo_excl_cos / fp64_peak,
-                    "mufu_cos_per_s": local_pairs * F / t_rff,
-                    "per_unit": "F*(d+5) fp32-pipe lane ops + F MUFU.COS per (candidate, sample) pair; "
-                                "algorithmic = F*(2d+3) flops + F cos (SURVEY 8d)",
-                    "launch_ms": t_rff * 1e3, "share_of_step": t_rff * args.steps / dev_s,
-                    "criterion_ms": float(np.mean(rc)) * 1e3 if rc else None}
-    else:
-        instr = local_pairs * F * (d + 13)           # fp64-pipe instructions per launch (tes_spec.h sequence)
-        achieved = 2.0 * instr / t_rff * 1e-12       # FMA-equivalent TFLOP/s, same convention as the DFMA burn
-        roofline = {"bound": "fp64", "kernel": "rff_topk_kernel", "achieved": achieved, "peak": fp64_peak,
-                    "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
-                    "peak_source": "measured in this run: tes_fp64_fma_burn (8 DFMA chains/thread, 1 s sustained)",
-                    "algorithmic_excl_cos_tflops": algo_excl_cos,
-                    "per_unit": "F*(d+13) fp64-pipe instr per (candidate, sample) pair = F*(2d+3) flops + F cos",
-                    "launch_ms": t_rff * 1e3, "share_of_step": t_rff * args.steps / dev_s,
-                    "criterion_ms": float(np.mean(rc)) * 1e3 if rc else None}
+    res = bench.run(wl, args.steps, args.warmup, deterministic=not args.stochastic, sample_clocks=True)
+    out = res["out"]
+    product = ops.detect_product_structure(res["devt"]["cand"]) if wl["N"] >= ops.PRODUCT_MIN_N else None
+    roofline = roofline_of(wl, res, product, peaks, fp64_peak, fp32_peak, mufu_peak)
+    parity = parity_check(bench, wl, res)
 
     line = None
     if rank == 0:
+        cfg = config_of(wl)
+        cfg["deterministic"] = not args.stochastic
         line = {
-            "metric": "acq evals/s (candidates x maximizer samples)", "value": value, "unit": "evals/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
+            "metric": "acq evals/s (candidates x maximizer samples)", "value": res["value"], "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(config_of(wl), T=out.get("T"), Sp=out.get("Sp"), K=out.get("K"),
+            "config": dict(cfg, T=out.get("T"), Sp=out.get("Sp"), K=out.get("K"),
+                           step="A0 weight draw (optfunc.py:303-385) + A maximizers + B posteriors + C maximizer "
+                                "statistics + D criterion and arg-max; inputs = candidates, observations and the three "
+                                "global-RNG draws",
                            criterion_screen_kept=out.get("screen_kept"),
-                           criterion_screen_ms=(float(np.mean([a.elapsed_time(b_) for a, b_ in timers["criterion_screen"]]))
-                                                if timers.get("criterion_screen") else None),
                            n_unique_maximizers=out.get("n_unique_maximizers"),
                            l2="flushed between timed iterations (256 MiB memset)",
-                           candidates=("product set U x V detected (slow columns [%d, %d), nv=%d): stage A = GEMM path (3xFP16 tensor-core screen + fp64 refine)" % product)
+                           candidates=("product set U x V detected (slow columns [%d, %d), nv=%d): stage A = GEMM path "
+                                       "(3xFP16 tensor-core screen + fp64 refine)" % product)
                            if product else "unstructured: stage A = tcgen05 screen + fp64 refine (MUFU-bound)",
                            sharding="candidates contiguous per rank; NCCL all-gather of (value,index) partials only"),
-            "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": int(launches),
+            "clocks": res["clocks"],
+            "stage_ms": res["stages"],
+            "stage_a_flagged_samples_per_step": res["flagged_samples_per_step"],
+            "e2e": res["e2e"],
+            "gpu_launches": res["launches"],
             "roofline": roofline,
+            "parity_check": parity,
         }
-    if rank == 0 and world == 1 and args.workload == "c3" and not args.no_secondary:
-        # BASELINE config 2 (the 400-point pH grid, TES_ep mode ep) in the same run: a launch-latency case, reported
-        # beside the headline so that both single-GPU configurations are on the line
+    del res
+    torch.cuda.empty_cache()
+    secondary = {}
+    if args.workload == "c3" and not args.no_secondary and not args.stochastic:
+        # ---- BASELINE config 4 (north star): batch TES_sp q=8, F=4096, 2^21 candidates per GPU (2^24 at 8 GPUs)
+        w4 = make_workload("c4", rank, world)
+        r4 = bench.run(w4, 3, 1, want_e2e=False)
+        if rank == 0:
+            secondary["c4"] = {"workload": w4["desc"], "value": r4["value"], "unit": "evals/s",
+                               "ms_per_step": r4["ms_per_step"], "steps": 3, "warmup": 1, "n_gpus": world,
+                               "global_candidates": r4["shard"].n_global, "stage_ms": r4["stages"],
+                               "T": r4["out"].get("T"), "K": r4["out"].get("K"),
+                               "roofline": {k: v for k, v in roofline_of(w4, r4, None, peaks, fp64_peak, fp32_peak,
+                                                                         mufu_peak).items()
+                                            if k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "share_of_step")}}
+        del w4, r4
+        torch.cuda.empty_cache()
+        # ---- C3 with the reference's DEFAULT estimator (bo_discrete.py --deterministic 0: evaluate_mp.py:220-295)
+        r3 = bench.run(wl, 2, 1, deterministic=False, want_e2e=False)
+        if rank == 0:
+            secondary["c3_stochastic"] = {"workload": wl["desc"] + " -- stochastic estimator, I=%d Y=%d" % (
+                wl["niteration"], wl["nysample"]), "value": r3["value"], "unit": "evals/s",
+                "ms_per_step": r3["ms_per_step"], "steps": 2, "warmup": 1, "stage_ms": r3["stages"]}
+        del r3
+        torch.cuda.empty_cache()
+        if world > 1:
+            # ---- strong scaling: the SAME global 10^6-point mesh split over the ranks
+            ws = make_workload("c3", 0, 1)
+            per = ws["N"] // world
+            ws["cand"] = np.ascontiguousarray(ws["cand"][rank * per:(rank + 1) * per])
+            ws["N"] = per
+            rs_ = bench.run(ws, 5, 2, want_e2e=False)
+            if rank == 0:
+                secondary["c3_strong"] = {"workload": "C3 mesh, 10^6 candidates in total split over %d GPUs" % world,
+                                          "scaling": "strong", "value": rs_["value"], "unit": "evals/s",
+                                          "ms_per_step": rs_["ms_per_step"], "steps": 5, "stage_ms": rs_["stages"]}
+            del ws, rs_
+            torch.cuda.empty_cache()
+        # ---- BASELINE config 5: posterior scaling sweep
+        c5 = c5_sweep(bench)
+        if rank == 0:
+            secondary["c5"] = c5
+    if rank == 0 and world == 1 and args.workload == "c3" and not args.no_secondary and not args.stochastic:
+        # BASELINE config 2 (the 400-point pH grid, TES_ep mode ep): a launch-latency case
         w2 = make_workload("c2", 0, 1)
-        d2 = {k: torch.from_numpy(w2[k]).cuda() for k in names}
-        kw2, sh2 = step_kwargs(w2), acquisition.Shard(w2["N"])
-        run2 = lambda sd: acquisition.tes_step(d2["cand"], d2["X"], d2["Y"], w2["hyp"]["l"], w2["hyp"]["sigma"],
-                                               w2["hyp"]["sigma0"], d2["theta"], d2["W"], d2["b"], seed=sd, shard=sh2, **kw2)
-        for w in range(3):
-            o2 = run2(w)
-        torch.cuda.synchronize()
-        n2, l0 = 20, _lib.lib().tes_launch_count()
-        e0.record()
-        for s in range(n2):
-            flush.zero_()
-            o2 = run2(100 + s)
-        e1.record()
-        torch.cuda.synchronize()
-        ms2 = e0.elapsed_time(e1) / n2
+        r2 = bench.run(w2, 20, 3, want_e2e=False)
         t0 = time.perf_counter()
         cpu_step(w2, w2["N"], w2["S"])
         cpu2 = time.perf_counter() - t0
-        line["secondary"] = {"c2": {"workload": w2["desc"], "ms_per_step": ms2, "value": w2["N"] * w2["S"] / (ms2 * 1e-3),
-                                    "unit": "evals/s", "steps": n2, "T": o2.get("T"),
-                                    "gpu_launches_per_step": (_lib.lib().tes_launch_count() - l0) / n2,
-                                    "cpu_ms_per_step": cpu2 * 1e3, "cpu_cores": os.cpu_count(),
-                                    "note": "whole step incl. EP on the device; host-latency bound (launches + the bucket-count sync)"}}
+        secondary["c2"] = {"workload": w2["desc"], "ms_per_step": r2["ms_per_step"], "value": r2["value"],
+                           "unit": "evals/s", "steps": 20, "T": r2["out"].get("T"),
+                           "gpu_launches_per_step": r2["launches"] / 20, "stage_ms": r2["stages"],
+                           "cpu_ms_per_step": cpu2 * 1e3, "cpu_cores": os.cpu_count(),
+                           "note": "whole step incl. weight draw and EP on the device; host-latency bound"}
+    if rank == 0 and secondary:
+        line["secondary"] = secondary
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         nc, ns = cpu_sample_sizes(wl)
         pairs, dt, info = cpu_step(wl, nc, ns)
         line["cpu_baseline"] = {"value": pairs / dt, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": "first %d candidates x first %d function samples, full step A-D, %.1f s"
+                                "sample": "first %d candidates x first %d function samples, full step A0-D, %.1f s"
                                           % (nc, ns, dt)}
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
         _emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        bench.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

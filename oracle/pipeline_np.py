@@ -21,14 +21,19 @@ def select_test_points(max_xs, resolution=1e-3, t_max=None):
 
 def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="empirical", deterministic=True,
              ntestsample=1000, n_min_sample=2, nysample=10, niteration=10, z_joint=None, z=None, seed=0,
-             duplicate_resolution=1e-3, t_max=None, return_acq=False, transform=None, q=1):
-    """`z` None with a Monte-Carlo criterion: the counter-based draws of include/tes_spec.h (the streams the
+             duplicate_resolution=1e-3, t_max=None, return_acq=False, transform=None, q=1, draws=None):
+    """`draws` = (randn_W, rand_b, randn_noise): the step starts at the RFF posterior weight draw
+    (optfunc.py:303-385, host numpy in the reference) and theta/W/b are ignored.
+    `z` None with a Monte-Carlo criterion: the counter-based draws of include/tes_spec.h (the streams the
     kernels key on the global candidate index), so both paths consume identical normals.  `q` > 1: batch TES_sp
     on every q consecutive candidates (evaluate_batch_sample_mp.py)."""
     N, d = cand.shape
     n = X.shape[0]
     Y = Y.reshape(-1, 1)
     ls, sigmas, sigma0s = np.asarray(l, dtype=np.float64).reshape(1, d), np.array([sigma]), np.array([sigma0])
+    if draws is not None:
+        S_, F_ = draws[0].shape[0], draws[0].shape[1]
+        theta, W, b = onp.draw_random_init_weights_features(d, S_, F_, X, Y, ls, sigma, sigma0, *draws)
     idx, val = co.rff_topk(cand, W, b, theta, sigma, 1)
     test_xs = select_test_points(cand[idx[:, 0]], duplicate_resolution, t_max)
     out = {"n_unique_maximizers": int(test_xs.shape[0]), "argmax_idx": idx[:, 0], "argmax_val": val[:, 0]}

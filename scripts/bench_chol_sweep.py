@@ -42,35 +42,26 @@ def build_stack(torch, m, batch, first, device):
     return A
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=1024)
-    ap.add_argument("--sizes", dest="m", type=int, nargs="*", default=[64, 128, 256, 512, 1024, 2048])
-    ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--no-cpu", action="store_true")
-    args = ap.parse_args()
-    import torch
-    import torch.distributed as dist
+def sweep(torch, dist, rank, world, sizes, batch, reps, cpu=True, flush=None, emit=None):
+    """-> list of one record per m (rank 0; [] elsewhere).  `emit(record)` is called as soon as a size is done."""
     from tes_b200 import _lib, ops
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     dev = torch.device("cuda", torch.cuda.current_device())
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm_peak = float(peaks.get("hbm_gbs", 6535.1))
     fp64_peak = ops.fp64_fma_peak(0.5)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    for m in args.m:
-        local = args.batch // world + (1 if rank < args.batch % world else 0)
-        first = rank * (args.batch // world) + min(rank, args.batch % world)
+    if flush is None:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    records = []
+    for m in sizes:
+        local = batch // world + (1 if rank < batch % world else 0)
+        first = rank * (batch // world) + min(rank, batch % world)
         sub = max(1, min(local, int(16e9 // (m * m * 8))))           # <= 16 GB per array and call
         chunks = [(first + o, min(sub, local - o)) for o in range(0, local, sub)]
         stacks = [build_stack(torch, m, nb, f0, dev) for f0, nb in chunks] if len(chunks) == 1 else None
         times, worst, launches = [], 0.0, 0
         inner = 16 if m <= 256 else 1
-        for rep in range(args.reps + 1):                             # first repetition = warm-up
+        for rep in range(reps + 1):                                  # first repetition = warm-up
             tot = 0.0
             for ci, (f0, nb) in enumerate(chunks):
                 A = stacks[ci] if stacks else build_stack(torch, m, nb, f0, dev)
@@ -98,10 +89,10 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t = float(t[0])
-        flops = args.batch * (m ** 3 / 3.0 + m ** 3)
-        byts = args.batch * 2.0 * m * m * 8
-        line = {"metric": "C5 batched chol2inv", "m": m, "batch": args.batch, "n_gpus": world,
-                "value": args.batch / t, "unit": "matrices/s", "ms": t * 1e3, "calls_per_rank": len(chunks), "calls_per_timing": inner,
+        flops = batch * (m ** 3 / 3.0 + m ** 3)
+        byts = batch * 2.0 * m * m * 8
+        line = {"metric": "C5 batched chol2inv", "m": m, "batch": batch, "n_gpus": world,
+                "value": batch / t, "unit": "matrices/s", "ms": t * 1e3, "calls_per_rank": len(chunks), "calls_per_timing": inner,
                 "launches_per_call": int(launches), "max_residual_A_Ainv_minus_I": worst,
                 "roofline": {"bound": "hbm" if m <= 128 else "fp64",
                              "algorithmic_tflops": flops / t * 1e-12, "fp64_peak_tflops": fp64_peak * world,
@@ -109,7 +100,7 @@ def main():
                              "algorithmic_gbs": byts / t * 1e-9, "hbm_peak_gbs": hbm_peak * world,
                              "frac_hbm": byts / t * 1e-9 / (hbm_peak * world),
                              "per_unit": "m^3/3 + m^3 flops, 2 m^2 8 bytes per matrix (SURVEY 8d)"}}
-        if rank == 0 and not args.no_cpu:
+        if rank == 0 and cpu:
             from oracle import tes_oracle_np as onp
             nb = max(1, min(8, int(2e9 // (m ** 3))))
             Ah = build_stack(torch, m, nb, 0, dev).cpu().numpy()
@@ -119,9 +110,29 @@ def main():
             line["cpu_baseline"] = {"value": nb / dt, "unit": "matrices/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "%d matrices of the same stack through the numpy oracle's multichol2inv" % nb}
         if rank == 0:
-            print(json.dumps(line), flush=True)
+            records.append(line)
+            if emit:
+                emit(line)
         del stacks
         torch.cuda.empty_cache()
+    return records
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--sizes", dest="m", type=int, nargs="*", default=[64, 128, 256, 512, 1024, 2048])
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    sweep(torch, dist, rank, world, args.m, args.batch, args.reps, cpu=not args.no_cpu,
+          emit=lambda line: print(json.dumps(line), flush=True))
     if world > 1:
         dist.destroy_process_group()
 

@@ -133,7 +133,7 @@ def select_test_points(max_xs, resolution=1e-3, t_max=None):
 def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="empirical", deterministic=True,
              ntestsample=1000, n_min_sample=2, nysample=10, niteration=10, z_joint=None, z=None, seed=0,
              duplicate_resolution=1e-3, t_max=None, shard=None, return_acq=False, timers=None, transform=None, q=1,
-             screen=None):
+             screen=None, draws=None):
     """One acquisition step for one hyper-parameter sample.  Returns a dict with the query index /
     point / value and the intermediate sizes.  `criterion`: 'ftl' (TES_ep) or 'sftl' (TES_sp).
     `q` > 1 (criterion 'sftl' only): batch TES_sp (evaluate_batch_sample_mp.py) on the queries formed by every `q`
@@ -142,10 +142,17 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
     `screen` (deterministic TES_ep only; default: on when the acquisition vector is not requested, N >= 32768 and at most
     128 maximizers): score all candidates with the tensor-core screen (ops.ep_acq_screen: value + proven error bound),
     evaluate only the candidates that can still be the arg-max with the fp64 criterion -- same query index and value.
-    out["screen_kept"] reports how many were re-evaluated (None: the fp64 criterion ran on everything)."""
+    out["screen_kept"] reports how many were re-evaluated (None: the fp64 criterion ran on everything).
+    `draws` = (randn_W (S,F,d), rand_b (S,F,1), randn_noise (S,F,1)): the step starts at the RFF posterior weight
+    draw (stage A0, optfunc.py:303-385, on the device) and `theta`, `W`, `b` are ignored (pass None)."""
+    from . import optfunc
     from .criteria import evaluate_batch_sample_mp, evaluate_mp, evaluate_sample_mp
     cand = dev(cand)
     N, d = cand.shape
+    if draws is not None:
+        with _Timed(timers, "draw"):
+            S_, F_ = draws[0].shape[0], draws[0].shape[1]
+            theta, W, b = optfunc.draw_random_init_weights_features(d, S_, F_, X, Y, l, sigma, sigma0, draws=draws)
     shard = shard or Shard(N)
     q = int(q)
     if q > 1 and (criterion != "sftl" or N % q or shard.offset % q):
@@ -161,23 +168,29 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
         out.update(query_x=test_xs[0].cpu().numpy(), query_idx=int(idx[0, 0]), query_val=float("nan"), T=1, Sp=1)
         return out
     # ---- B
+    tb = _Timed(timers, "stage_b")
+    tb.__enter__()
     invK = utils.precomputeInvKs(d, 1, ls, sigmas, sigma0s, Xd)
     mean_t, cov_t = utils.compute_mean_var_f(dev(test_xs), Xd, Yd, ls[0], sigma, sigma0, invK[0], fullcov=True)
+    tb.__exit__()
     # ---- C (device, replicated on every rank with identical draws; only the bucket counts visit the host)
+    tc = _Timed(timers, "stage_c")
+    tc.__enter__()
     T0 = test_xs.shape[0]
     st_mode = "sample" if criterion == "sftl" else mode
     test_k, max_probs, mean_k, cov_k, v0, v1 = utils.get_testidxs_stats(
         1, test_xs, mean_t.reshape(1, T0), cov_t.reshape(1, T0, T0), mode=st_mode, nsample=ntestsample,
         n_min_sample=n_min_sample, z=z_joint, transforms=None if transform is None else [transform],
         seed=None if z_joint is not None else seed)
+    tc.__exit__()
     out.update(T=int(test_k.shape[0]), Sp=int((max_probs[0] > 0).sum()))
     if test_k.shape[0] == 1:
         out.update(query_x=test_k[0].cpu().numpy(), query_idx=-1, query_val=float("nan"))
         return out
-    _, invpNK = evaluate_mp.get_pNK_test_obs(ls, sigmas, sigma0s, 1, Xd, dev(test_k))
-    # ---- D
+    # ---- D (timer "criterion" = invpNK + criterion on every candidate)
     tm = _Timed(timers, "criterion")
     tm.__enter__()
+    _, invpNK = evaluate_mp.get_pNK_test_obs(ls, sigmas, sigma0s, 1, Xd, dev(test_k))
     sub = None   # candidate subset the exact criterion was evaluated on (screened path)
     if criterion == "ftl":
         pk = dev(max_probs).reshape(-1)

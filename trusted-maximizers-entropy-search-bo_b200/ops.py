@@ -23,6 +23,8 @@ def _rff_args(cand, W, b, theta):
 RFF_AUTO, RFF_FP64, RFF_SCREEN, RFF_SCREEN_MMA, RFF_SCREEN_TC5, RFF_SCREEN_TC5T = 0, 1, 2, 3, 4, 5
 
 
+STATS = {"product_flagged": 0}   # samples the product path handed back to the general kernel (diagnostics)
+
 RFF_PRODUCT = 6          # product-structured candidate sets: one fp64 tensor-pipe GEMM per sample (csrc/rffprod.cu)
 PRODUCT_MIN_N = 1 << 15  # below this the general kernels are launch-bound anyway
 PRODUCT_MODE = int(__import__("os").environ.get("TES_PRODUCT_MODE", "3"))   # GEMM engine of the product path
@@ -106,6 +108,7 @@ def rff_topk(cand, W, b, theta, sigma, k=1, idx_offset=0, method=RFF_AUTO, produ
                                               idx_offset=idx_offset)
             bad = torch.nonzero(flag).reshape(-1)
             if bad.numel():
+                STATS["product_flagged"] += int(bad.numel())
                 gi, gv = rff_topk(cand, W if ws_ else W[bad], b if ws_ else b[bad], theta[bad], sigma, k=k,
                                   idx_offset=idx_offset, product=False)
                 idx[bad], val[bad] = gi, gv
