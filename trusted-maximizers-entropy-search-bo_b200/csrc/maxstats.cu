@@ -101,62 +101,114 @@ __global__ void __launch_bounds__(1024) dedup_kernel(const double* __restrict__ 
 // round-robin tournament step are disjoint: one warp per pair, (n-1) steps per sweep.
 constexpr int EIG_MAX_SWEEPS = 40;
 
+// One tournament step = one block barrier.  Eight lanes own a pair (four pairs per warp at a time): they form the
+// three inner products (|g_p|^2, |g_q|^2, g_p . g_q) with a 3-round butterfly, derive the rotation and apply it.
+// The rotation angle only has to be ROUGHLY right (an error of 1e-7 leaves a residual 1e-7 g, gone in the next
+// sweep), so t = tan(theta) is formed in fp32 on exponent-normalised inputs (MUFU square root / reciprocal); what has
+// to be exact is orthogonality, so c = (1 + t^2)^-1/2 comes from an fp32 seed and two fp64 Newton steps and s = c t:
+// c^2 + s^2 = 1 to rounding whatever t is.  This replaces the dependent fp64 sqrt / division / rsqrt sequences
+// (~1700 cycles of latency per step, issued redundantly by every warp) that bound the first versions: ncu of the
+// one-warp-per-pair kernel showed 1200 warp-instructions per warp and step (index divisions, 64-bit shuffles) at 4.4 us
+// per step for n = 64.  The pair schedule is the round-robin tournament, advanced without integer divisions.
+__device__ __forceinline__ void jacobi_rotation(double a, double b, double g, double tol2, double& c, double& sn) {
+    c = 1.0;
+    sn = 0.0;
+    if (!(g != 0.0 && g * g > tol2 * (a * b))) return;
+    const double tau = b - a, gam = 2.0 * g;
+    // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = tau / gam  ==  sign(tau) gam / (|tau| + hypot(tau, gam))
+    const int et = (__double2hiint(tau) >> 20) & 0x7ff, eg = (__double2hiint(gam) >> 20) & 0x7ff;
+    const int em = et > eg ? et : eg;
+    double t;
+    if (em > 64 && em < 1980) {
+        const double sc = __hiloint2double((2046 - em) << 20, 0);          // 2^(1023 - em): max(|tau|, |gam|) -> [1, 2)
+        const float ft = (float)(tau * sc), fg = (float)(gam * sc);
+        const float h = sqrtf(fmaf(ft, ft, fg * fg));
+        const float tf = __fdividef(fg, fabsf(ft) + h);
+        t = (double)(ft < 0.0f ? -tf : tf);
+    } else {
+        const double h = sqrt(fma(tau, tau, gam * gam));
+        t = (tau < 0.0 ? -gam : gam) / (fabs(tau) + h);
+    }
+    const double x = fma(t, t, 1.0);
+    double r = (double)rsqrtf((float)x);
+    r = r * fma(-0.5 * x, r * r, 1.5);
+    r = r * fma(-0.5 * x, r * r, 1.5);
+    c = r;
+    sn = r * t;
+}
+
+template <bool SMEM>
 __global__ void sym_eig_kernel(const double* __restrict__ A, int n, double* __restrict__ evals,
-                               double* __restrict__ evecs, int* __restrict__ sweeps_out, double* __restrict__ gws,
-                               int in_smem) {
+                               double* __restrict__ evecs, int* __restrict__ sweeps_out, double* __restrict__ gws) {
     extern __shared__ double sm_g[];
     __shared__ int s_rot;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int64_t mat = blockIdx.x;
     const double* Ab = A + mat * n * n;
-    double* G = in_smem ? sm_g : gws + mat * n * n;
+    const int ld = SMEM ? n + 1 : n;                      // odd leading dimension: columns start in different banks
+    double* G = SMEM ? sm_g : gws + mat * n * n;
+    const int m = n + (n & 1), npair = m / 2, mm1 = m - 1;
     // column p of G = row p of A (A is symmetric)
-    for (int e = tid; e < n * n; e += nt) G[e] = Ab[e];
+    for (int e = tid; e < n * n; e += nt) G[(e / n) * ld + (e % n)] = Ab[e];
     __syncthreads();
-    const int m = n + (n & 1), npair = m / 2;
     const double tol = 2.2e-16 * sqrt((double)n);
+    const double tol2 = tol * tol;
+    const int grp = lane >> 3, sub = lane & 7;            // pair slot of the warp, lane inside the pair
+    const int kstride = nwarps * 4;
     int sweep = 0;
     for (; sweep < EIG_MAX_SWEEPS && n > 1; ++sweep) {
         if (tid == 0) s_rot = 0;
         __syncthreads();
-        for (int s = 0; s < m - 1; ++s) {
-            for (int k = warp; k < npair; k += nwarps) {
-                int p, q;
-                if (k == 0) {
-                    p = m - 1;
-                    q = s;
-                } else {
-                    p = (s + k) % (m - 1);
-                    q = (s + m - 1 - k) % (m - 1);
-                }
-                if (p >= n || q >= n) continue;  // the padding player of an odd n
-                if (p > q) {
-                    const int t_ = p;
-                    p = q;
-                    q = t_;
-                }
-                double* gp = G + (int64_t)p * n;
-                double* gq = G + (int64_t)q * n;
+        for (int s = 0; s < mm1; ++s) {
+            for (int k0 = warp * 4; k0 < npair; k0 += kstride) {
+                const int k = k0 + grp;
+                // round robin: pair 0 = (m - 1, s); pair k = ((s + k) mod (m - 1), (s - k) mod (m - 1))
+                int p = s + k, q = s - k;
+                if (p >= mm1) p -= mm1;
+                if (q < 0) q += mm1;
+                if (k == 0) p = mm1;
+                const bool live = k < npair && p < n && q < n;   // an odd n pads with an idle player
+                double* gp = G + (live ? p : 0) * ld;
+                double* gq = G + (live ? q : 0) * ld;
                 double a = 0.0, b = 0.0, g = 0.0;
-                for (int i = lane; i < n; i += 32) {
-                    const double x = gp[i], y = gq[i];
-                    a = fma(x, x, a);
-                    b = fma(y, y, b);
-                    g = fma(x, y, g);
+                if (live) {
+                    double a1 = 0.0, b1 = 0.0, g1 = 0.0;
+                    int i = sub;
+                    for (; i + 8 < n; i += 16) {
+                        const double x = gp[i], y = gq[i], x1 = gp[i + 8], y1 = gq[i + 8];
+                        a = fma(x, x, a);
+                        b = fma(y, y, b);
+                        g = fma(x, y, g);
+                        a1 = fma(x1, x1, a1);
+                        b1 = fma(y1, y1, b1);
+                        g1 = fma(x1, y1, g1);
+                    }
+                    if (i < n) {
+                        const double x = gp[i], y = gq[i];
+                        a = fma(x, x, a);
+                        b = fma(y, y, b);
+                        g = fma(x, y, g);
+                    }
+                    a += a1;
+                    b += b1;
+                    g += g1;
                 }
-                a = warp_sum(a);
-                b = warp_sum(b);
-                g = warp_sum(g);
-                if (g != 0.0 && fabs(g) > tol * sqrt(a * b)) {
-                    const double zeta = (b - a) / (2.0 * g);
-                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
-                    for (int i = lane; i < n; i += 32) {
+#pragma unroll
+                for (int off = 4; off > 0; off >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, off);
+                    b += __shfl_xor_sync(0xffffffffu, b, off);
+                    g += __shfl_xor_sync(0xffffffffu, g, off);
+                }
+                // every lane of the group holds the same (a, b, g) and derives the same rotation
+                double c, sn;
+                jacobi_rotation(a, b, g, tol2, c, sn);
+                if (live && sn != 0.0) {
+                    for (int i = sub; i < n; i += 8) {
                         const double x = gp[i], y = gq[i];
                         gp[i] = c * x - sn * y;
                         gq[i] = sn * x + c * y;
                     }
-                    if (lane == 0) s_rot = 1;
+                    if (sub == 0) s_rot = 1;
                 }
             }
             __syncthreads();
@@ -171,7 +223,7 @@ __global__ void sym_eig_kernel(const double* __restrict__ A, int n, double* __re
     if (tid == 0 && sweeps_out) sweeps_out[mat] = sweep;
     // normalise the columns
     for (int k = warp; k < n; k += nwarps) {
-        double* gk = G + (int64_t)k * n;
+        double* gk = G + k * ld;
         double a = 0.0;
         for (int i = lane; i < n; i += 32) a = fma(gk[i], gk[i], a);
         a = warp_sum(a);
@@ -181,7 +233,7 @@ __global__ void sym_eig_kernel(const double* __restrict__ A, int n, double* __re
     __syncthreads();
     // eigenvalues: Rayleigh quotients against the ORIGINAL matrix; eigenvectors out as columns of a row-major (n, n)
     for (int k = warp; k < n; k += nwarps) {
-        const double* vk = G + (int64_t)k * n;
+        const double* vk = G + k * ld;
         double acc = 0.0;
         for (int i = 0; i < n; ++i) {
             double r = 0.0;
@@ -194,7 +246,7 @@ __global__ void sym_eig_kernel(const double* __restrict__ A, int n, double* __re
     double* Vb = evecs + mat * n * n;
     for (int e = tid; e < n * n; e += nt) {
         const int i = e / n, k = e % n;
-        Vb[e] = G[(int64_t)k * n + i];
+        Vb[e] = G[k * ld + i];
     }
 }
 
@@ -438,13 +490,20 @@ extern "C" int tes_sym_eig_f64(const double* A, int64_t batch, int64_t n, double
     if (!evecs) return -5;
     const int in_smem = n <= EIG_SMEM_MAX_N;
     if (!in_smem && (!ws || ws_bytes < tes_sym_eig_workspace_bytes(batch, n))) return -100;
-    const size_t smem = in_smem ? (size_t)n * n * sizeof(double) : 0;
+    const int64_t npair = (n + 1) / 2;
+    const size_t smem = in_smem ? (size_t)n * (n + 1) * sizeof(double) : 0;
     if (smem > 48 * 1024)
-        TES_CUDA_OK(cudaFuncSetAttribute(sym_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int threads = 32 * (int)((n / 2 + 1) / 2);  // two pairs per warp and step
+        TES_CUDA_OK(cudaFuncSetAttribute(sym_eig_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // four pairs per warp at a time (eight lanes each); n = 64: 256 threads, several matrices per SM hide each other's
+    // barrier and fp64 latency
+    int threads = 32 * (int)((npair + 3) / 4);
     threads = threads < 128 ? 128 : (threads > 1024 ? 1024 : threads);
-    sym_eig_kernel<<<(unsigned)batch, threads, smem, (cudaStream_t)stream>>>(A, (int)n, evals, evecs, sweeps,
-                                                                            (double*)ws, in_smem);
+    if (in_smem)
+        sym_eig_kernel<true><<<(unsigned)batch, threads, smem, (cudaStream_t)stream>>>(A, (int)n, evals, evecs, sweeps,
+                                                                                      (double*)ws);
+    else
+        sym_eig_kernel<false><<<(unsigned)batch, threads, smem, (cudaStream_t)stream>>>(A, (int)n, evals, evecs, sweeps,
+                                                                                       (double*)ws);
     TES_LAUNCH_OK();
     return 0;
 }
