@@ -202,7 +202,10 @@ int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, const double* t
  * (criteria/evaluate_batch_sample_mp.py:160-382).  x (nx, q, d); post_samples (Sp,T,K);
  * post_mask (Sp,K) bytes (1 = valid); z layout (niter, nysample, Sp, nx, K, q) or NULL for Philox
  * (element ((iy*Sp + j)*n_global + x_offset + x)*K + s)*q + c; n_global < 0: shared draws, the
- * query index drops out of the element).  out_acq (nx). */
+ * query index drops out of the element).  out_acq (nx).
+ * On return the int32 at ws + tes_sp_acq_workspace_bytes(...) - 256 holds the number of queries whose q x q
+ * predictive covariance had no Cholesky factor (their acquisition value is NaN; the reference's tf.cholesky raises
+ * InvalidArgumentError there, evaluate_batch_sample_mp.py:306-310). */
 int64_t tes_sp_acq_workspace_bytes(int64_t nx, int q, int64_t T, int64_t n, int64_t d, int64_t Sp, int64_t K);
 int tes_sp_acq_f64(const double* x, int64_t nx, int q, int64_t d, const double* test_xs, int64_t T, const double* X,
                    int64_t n, const double* Y, const double* l, double sigma, double sigma0, const double* invpNK,
@@ -300,6 +303,11 @@ int tes_bucket_moments_f64(const double* samples, int64_t ns, int64_t T, const i
 int tes_bucket_samples_f64(const double* samples, int64_t ns, int64_t T, const int64_t* order, const int64_t* starts,
                            int64_t nb, const int64_t* cols, int64_t nk, int64_t K, const double* prior_mean,
                            double* out, uint8_t* mask, void* stream);
+
+/* General inverse of `batch` n x n matrices by Gauss-Jordan elimination with partial pivoting -- what tf.linalg.inv /
+ * np.linalg.inv (LU) compute; get_pNK_test_obs (criteria/evaluate_mp.py:47) falls back to it when the Cholesky route
+ * reports a non-positive pivot (pNK carries no jitter on its test block).  out may not alias A. */
+int tes_batched_gj_inverse_f64(const double* A, int64_t batch, int64_t n, double* out, void* stream);
 
 /* ep.approximate_EP_np (ep.py:73-204) for EVERY maximizer of every hyper-parameter sample in one launch (one CTA per
  * maximizer, Gauss-Jordan inverse with partial pivoting in shared memory for T <= 160).  mean (nhyp, T), cov

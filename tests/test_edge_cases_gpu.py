@@ -107,3 +107,78 @@ def test_empty_candidate_sets():
     assert tuple(k.shape) == (0, 5)
     inv = ops.batched_chol2inv(torch.zeros((0, 4, 4), dtype=torch.float64, device="cuda"))
     assert tuple(inv.shape) == (0, 4, 4)
+
+
+def test_pnk_inverse_falls_back_to_general_inverse_when_not_positive_definite():
+    """pNK has no jitter on its test block; near-duplicate test points make the Cholesky route
+    fail where the reference's tf.linalg.inv (LU) still returns an inverse."""
+    from tes_b200 import ops
+    from tes_b200.criteria import evaluate_mp
+    rs = np.random.RandomState(3)
+    d, n, T = 2, 6, 5
+    X = rs.rand(n, d)
+    test_xs = rs.rand(T, d)
+    test_xs[3] = test_xs[1]                       # an exact duplicate: the test block is singular to rounding
+    ls, sigmas, sigma0s = np.array([[25.5866, 6.3735]]), np.array([0.589]), np.array([1e-4])
+    pNK, inv = evaluate_mp.get_pNK_test_obs(ls, sigmas, sigma0s, 1, X, test_xs)
+    ref = onp.get_pNK_test_obs(ls, sigmas, sigma0s, 1, X, test_xs)[0]
+    np.testing.assert_allclose(pNK, ref, rtol=1e-12, atol=1e-14)
+    assert np.all(np.isfinite(inv) | np.isinf(inv))          # LU of a singular matrix: inf / huge, never silently NaN-free garbage
+    # a merely ill-conditioned (not singular) case must agree with LAPACK's LU inverse through the residual
+    test_xs[3] = test_xs[1] + 3e-6
+    pNK, inv = evaluate_mp.get_pNK_test_obs(ls, sigmas, sigma0s, 1, X, test_xs)
+    gj = ops.gj_inverse(pNK[0]).cpu().numpy()
+    lu = np.linalg.inv(pNK[0])
+    scale = np.abs(lu).max()
+    np.testing.assert_allclose(gj, lu, rtol=0, atol=1e-4 * scale)
+    assert np.abs(pNK[0] @ gj - np.eye(T + n)).max() < 1e-4
+
+
+def test_checked_cholesky_raises_like_tf_cholesky():
+    from tes_b200 import utils
+    from tes_b200._lib import TesError
+    A = np.array([[1.0, 2.0], [2.0, 1.0]])        # indefinite
+    with pytest.raises(TesError):
+        utils.chol2inv(A)
+    with pytest.raises(TesError):
+        utils.multichol2inv(np.stack([np.eye(2), A]))
+
+
+def test_screen_bound_with_wide_dynamic_range_and_indefinite_covariance():
+    """the screen's error bound carries the fp16-subnormal absolute term (entries of Sigma_j / M far below the
+    column / row maxima) and is +inf for a covariance that violates |S_ab| <= sqrt(S_aa S_bb)."""
+    from tes_b200 import ops
+    rs = np.random.RandomState(11)
+    d, n, T, N, Sp = 3, 8, 12, 40000, 6
+    X, Y = rs.rand(n, d), rs.randn(n, 1) * 0.3
+    test_xs = rs.rand(T, d)
+    x = rs.rand(N, d)
+    l, sigma, sigma0 = np.array([9.0, 4.0, 2.0]), 1.1, 1e-3
+    ls, sg, s0 = l.reshape(1, d), np.array([sigma]), np.array([sigma0])
+    invK = onp.precomputeInvKs(ls, sg, s0, X)
+    _, invpNK = onp.get_pNK_test_obs(ls, sg, s0, 1, X, test_xs)
+    p = np.full(Sp, 1.0 / Sp)
+    # covariances whose entries span > 1e7 in magnitude: D A D with D = diag(10^-4 ... 10^0)
+    covs = []
+    for j in range(Sp):
+        A = rs.randn(T, T)
+        A = A @ A.T / T + 0.1 * np.eye(T)
+        D = np.diag(10.0 ** rs.uniform(-4, 0, size=T))
+        covs.append(D @ A @ D)
+    covs = np.stack(covs)
+    acq_t, eps = ops.ep_acq_screen(x, test_xs, X, Y, l, sigma, sigma0, invpNK[0], invK[0], p, covs)
+    ref = ops.ep_acq(ops.EP_DETERMINISTIC, x, test_xs, X, Y, l, sigma, sigma0, invpNK[0], invK[0], p,
+                     np.zeros((Sp, T)), covs)
+    err = (acq_t - ref).abs()
+    assert bool(torch_all(err <= eps)), float((err - eps).max())
+    assert float(eps.max()) < 1e-2                       # ... and the bound is still useful
+    # an indefinite "covariance" (EP mode can produce one): the bound must give up, not lie
+    covs_bad = covs.copy()
+    covs_bad[2, 0, 1] = covs_bad[2, 1, 0] = 10.0 * np.sqrt(covs_bad[2, 0, 0] * covs_bad[2, 1, 1])
+    _, eps_bad = ops.ep_acq_screen(x, test_xs, X, Y, l, sigma, sigma0, invpNK[0], invK[0], p, covs_bad)
+    assert bool(torch_all(eps_bad == float("inf")))
+
+
+def torch_all(t):
+    import torch
+    return torch.all(t)

@@ -80,6 +80,7 @@ SIGNATURES = {
     "tes_rff_draw_f64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_i64, c_i64,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "tes_uniform_fill_f64": (c_int, [c_u64, ctypes.c_uint32, ctypes.c_uint32, c_u64, c_i64, c_ptr, c_ptr]),
+    "tes_batched_gj_inverse_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "tes_ep_moments_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "tes_ep_moments_f64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "tes_rff_adam_refine_f64": (c_int, [c_ptr, c_i64, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_dbl, c_ptr,

@@ -164,6 +164,10 @@ def run(f, xs, xmin, xmax, l, sigma, sigma0, criterion="sftl", mode="sample", nq
                                   start_vals=crit(starts.reshape(-1, xdim * q), 0), qx=qx, qv=qv)
                 if query_x is not None and not np.any(np.isnan(np.asarray(query_x, dtype=np.float64))):
                     break
+            else:
+                # the reference repeats until the query is finite (bo_batch.py:1080-1081); a NaN query must never be
+                # observed -- it would poison every later GP solve
+                raise ops._lib.TesError("query %d of run %d is still NaN after %d attempts" % (nq, nr, max_nan_retry + 1))
             query_x = np.asarray(query_x, dtype=np.float64).reshape(q, xdim)
             query_f = np.asarray(f(query_x), dtype=np.float64).reshape(q, 1)
             query_y = query_f + np.random.randn(q, 1) * np.sqrt(sigma0)

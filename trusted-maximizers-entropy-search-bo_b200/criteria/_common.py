@@ -11,12 +11,17 @@ def to_np(a):
 
 def get_pNK_test_obs(ls, sigmas, sigma0s, nhyp, X, test_xs, dtype=None):
     """criteria/evaluate_mp.py:12-53 (identical copies in the other four criterion files).
-    Returns (pNKs, invpNKs), each (nhyp, ntest+nobs, ntest+nobs).  The inverse is Cholesky-based
-    (the matrix is SPD); the reference uses tf.linalg.inv, no jitter in either."""
+    Returns (pNKs, invpNKs), each (nhyp, ntest+nobs, ntest+nobs).  The inverse is Cholesky-based while the matrix
+    is numerically positive definite; the test block of pNK carries no noise or jitter, so near-duplicate
+    test points can break that -- those matrices go through the general Gauss-Jordan inverse, which is what the
+    reference's tf.linalg.inv (LU) computes for every matrix."""
     ls_, sg, s0 = to_np(ls), to_np(sigmas).reshape(-1), to_np(sigma0s).reshape(-1)
     ls_ = ls_.reshape(nhyp, -1)
     pNKs = torch.stack([ops.pnk(test_xs, X, ls_[i], float(sg[i]), float(s0[i])) for i in range(nhyp)])
-    inv = ops.batched_chol2inv(pNKs)
+    inv, info = ops.batched_chol2inv(pNKs, return_info=True)
+    bad = torch.nonzero(info != 0).reshape(-1)
+    if bad.numel():
+        inv[bad] = ops.gj_inverse(pNKs[bad])
     if isinstance(X, np.ndarray):
         return pNKs.cpu().numpy(), inv.cpu().numpy()
     return pNKs, inv

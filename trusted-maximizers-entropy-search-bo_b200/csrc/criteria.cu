@@ -667,17 +667,40 @@ extern "C" int tes_ep_acq_f64(int mode, const double* x, int64_t N, int64_t d, c
 // acq~(x) and a proven bound eps(x) on |acq~(x) - acq(x)|: the quadratic forms run as a 3xFP16 tcgen05 GEMM
 // (rffprod.cu), everything else as in tes_ep_acq_f64.  The caller keeps the candidates with acq~ + eps >= max(acq~ - eps)
 // and evaluates only those with the fp64 path, which leaves the arg-max and its value unchanged.
-//   |q~_j - q_j| <= delta_j = QS_ETA * h_j^2,  h_j = sum_a |M[x,a]| sqrt(Sigma_j[a][a])   (|Sigma_ab| <= sqrt(S_aa S_bb))
+//   |q~_j - q_j| <= delta_j = QS_ETA * h_j^2 + QS_ABS * Ks * rowmax(x)^2 * colmax_j,
+//   h_j = sum_a |M[x,a]| sqrt(Sigma_j[a][a])   (uses |Sigma_ab| <= sqrt(S_aa S_bb): CHECKED for every (a, b, j) by
+//   screen_diag_kernel -- EP-mode covariances need not be positive semi-definite; a column j that violates it, or has a
+//   negative / NaN diagonal entry, gets h_j = +inf, i.e. eps = +inf for every candidate: no pruning)
 //   QS_ETA = 1.5 * (2.5 * 2^-20 [hi/lo fp16 operands, dropped lo*lo] + 4 * 2^-24 * 96 [fp32 segments of 256 k])
+//   QS_ABS = 1.5 * (4096 + 8) * 2^-25 / (4096 * 8): the fp16 lo halves are SUBNORMAL below 2^-14, so an operand carries an
+//   absolute error of up to 2^-25 in scaled units (rows scaled to products <= 4096 = QS_AMAX, columns to <= 8 = QS_BMAX)
+//   on top of the relative one; per term <= (|a| + |b|) 2^-25, summed over the Ks padded terms and unscaled by
+//   rowmax^2 / 4096 * colmax / 8.  (Entries of Sigma_j or M far below colmax / rowmax are where it matters.)
 //   |1/2 log(v~ + s0) - 1/2 log(v + s0)| <= 1/2 log(w / (w - delta)),  w = v~ + s0  (infinite when w <= delta or NaN)
 namespace tes {
 constexpr double QS_ETA = 4.0e-5;
-__global__ void sqrt_diag_kernel(const double* __restrict__ cov, int64_t Sp, int64_t T, double* __restrict__ D) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= T * Sp) return;
-    int64_t a = e / Sp, j = e % Sp;
-    double v = cov[(j * T + a) * T + a];
-    D[e] = v > 0.0 ? sqrt(v) : 0.0;
+constexpr double QS_ABS = 1.5 * 4104.0 * 2.98023223876953125e-08 / 32768.0;
+// D[a][j] = sqrt(Sigma_j[a][a]); one CTA per maximizer j checks Sigma_ab^2 <= Sigma_aa Sigma_bb for every pair (the
+// inequality the h-bound rests on) and a non-negative diagonal, else the whole column of D is +inf
+__global__ void __launch_bounds__(256) screen_diag_kernel(const double* __restrict__ cov, int64_t Sp, int64_t T,
+                                                          double* __restrict__ D) {
+    __shared__ int bad;
+    const int64_t j = blockIdx.x;
+    const double* c = cov + j * T * T;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    int mybad = 0;
+    for (int64_t e = threadIdx.x; e < T * T; e += blockDim.x) {
+        const int64_t a = e / T, b = e % T;
+        const double sab = c[e], saa = c[a * T + a], sbb = c[b * T + b];
+        // (written so that NaN anywhere counts as a violation)
+        if (!(saa >= 0.0) || !(sbb >= 0.0) || !(sab * sab <= saa * sbb * (1.0 + 1e-12))) mybad = 1;
+    }
+    if (mybad) bad = 1;
+    __syncthreads();
+    const int isbad = bad;
+    for (int64_t a = threadIdx.x; a < T; a += blockDim.x)
+        D[a * Sp + j] = isbad ? pos_inf() : sqrt(c[a * T + a]);
 }
 __global__ void abs_rows_kernel(const double* __restrict__ G, int64_t ldg, int64_t rows, int64_t T,
                                 double* __restrict__ out) {
@@ -689,16 +712,19 @@ __global__ void abs_rows_kernel(const double* __restrict__ G, int64_t ldg, int64
 __global__ void ep_det_screen_kernel(const double* __restrict__ Qt, const double* __restrict__ Kq,
                                      const double* __restrict__ H, const double* __restrict__ varf,
                                      const double* __restrict__ p, int64_t rows, int64_t Sp, double sigma0,
+                                     const double* __restrict__ rowmax, const double* __restrict__ colmax, double kabs,
                                      double* __restrict__ out_acq, double* __restrict__ out_eps) {
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= rows) return;
     double s = 0.0, er = 0.0;
     const double kq = Kq[row];
+    const double rm = rowmax[row];
+    const double ra = kabs * rm * rm;                    // QS_ABS * Ks * rowmax^2
     for (int64_t j = lane; j < Sp; j += 32) {
         const double h = H[row * Sp + j];
         const double w = (kq + Qt[row * Sp + j]) + sigma0;
-        const double delta = QS_ETA * h * h + 1e-300;
+        const double delta = (QS_ETA * h * h + ra * colmax[j]) + 1e-300;
         s += ((NORM_ENTROPY_CONST + log(sqrt(w))) + 0.5) * p[j];
         const double e1 = (w > delta) ? 0.5 * log(w / (w - delta)) : pos_inf();   // NaN w -> false -> +inf
         er += e1 * p[j];
@@ -772,8 +798,9 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
     if ((rc = launch_build_bext(invpNK, Y, m, T, Bext, st))) return rc;
     if ((rc = launch_quad_screen_ab(post_cov, Sp, T, colmax, Bscr, st))) return rc;
     if ((rc = launch_quad_screen_build_b(Bscr, Ks, Sp, Btc, colmax, st))) return rc;
-    sqrt_diag_kernel<<<(unsigned)((T * Sp + 255) / 256), 256, 0, st>>>(post_cov, Sp, T, Dm);
+    screen_diag_kernel<<<(unsigned)Sp, 256, 0, st>>>(post_cov, Sp, T, Dm);
     TES_LAUNCH_OK();
+    const double kabs = QS_ABS * (double)quad_screen_kp(Ks);
     for (int64_t c0 = 0; c0 < N; c0 += PS_SCREEN_CHUNK) {
         const int64_t nc = (N - c0 < PS_SCREEN_CHUNK) ? (N - c0) : PS_SCREEN_CHUNK;
         if ((rc = launch_se_ard(x + c0 * d, nc, xto, m, (int)d, l, sigma, -1, 0.0, Kc, m, st))) return rc;
@@ -786,7 +813,8 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
         TES_LAUNCH_OK();
         if ((rc = launch_gemm(absM, T, Dm, Sp, 1, Hb, Sp, nc, Sp, T, st))) return rc;
         ep_det_screen_kernel<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(varc, Kq, Hb, varf, p, nc, Sp, sigma0,
-                                                                               out_acq + c0, out_eps + c0);
+                                                                               rowmax, colmax, kabs, out_acq + c0,
+                                                                               out_eps + c0);
         TES_LAUNCH_OK();
     }
     return 0;

@@ -298,6 +298,34 @@ using namespace tes;
 
 constexpr int EP_SMEM_MAX_T = 160;
 
+namespace tes {
+// out[b] = inverse(A[b]) by Gauss-Jordan with partial pivoting (the pivot rule of the LU behind np.linalg.inv /
+// tf.linalg.inv), one CTA per matrix, in place in `out` (global memory; small matrices stay in L1/L2)
+__global__ void __launch_bounds__(EP_THREADS) gj_inverse_kernel(const double* __restrict__ A, int n,
+                                                                double* __restrict__ out) {
+    extern __shared__ int gj_piv[];
+    __shared__ double red_v[32];
+    __shared__ int red_i[32];
+    const int64_t b = blockIdx.x;
+    double* a = out + b * n * n;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) a[e] = A[b * n * n + e];
+    __syncthreads();
+    gj_inverse(a, n, gj_piv, red_v, red_i);
+}
+}  // namespace tes
+
+extern "C" int tes_batched_gj_inverse_f64(const double* A, int64_t batch, int64_t n, double* out, void* stream) {
+    if (batch < 0) return -2;
+    if (n < 1 || n > 8192) return -3;
+    if (batch == 0) return 0;
+    if (!A) return -1;
+    if (!out) return -4;
+    tes::gj_inverse_kernel<<<(unsigned)batch, tes::EP_THREADS, (size_t)n * sizeof(int), (cudaStream_t)stream>>>(
+        A, (int)n, out);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
 extern "C" int64_t tes_ep_moments_workspace_bytes(int64_t nhyp, int64_t T) {
     if (nhyp < 1 || T < 2 || T > 2048) return -1;
     int64_t b = align_up(nhyp * T * T * 8, 256) + align_up(nhyp * T * 8, 256);

@@ -638,6 +638,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1)
 constexpr int TC_EPI_WARPS = 16, TC_THREADS = 64 + 32 * TC_EPI_WARPS, TC_NS = 3, TC_BK = 64, TC_SEG = 4;
 constexpr uint32_t TC_BLOCK_BYTES = 2 * 8 * 128 * 16;          // one operand block of a stage (hi + lo) = 32 KB
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_BLOCK_BYTES;        // A block + B block
+#ifndef TC_COPY_SPLIT
+#define TC_COPY_SPLIT 1
+#endif
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -687,20 +690,24 @@ __global__ void __launch_bounds__(256)
     prod_build_tc_kernel(const double* __restrict__ cand, int64_t nrow, int64_t row_stride, int d, int s_lo, int s_hi,
                          int which, const double* __restrict__ W, const double* __restrict__ b,
                          const double* __restrict__ theta, int64_t j0, int64_t F, int w_shared, int64_t ntile,
-                         int64_t nst, const double* __restrict__ tmax, __half* __restrict__ out) {
+                         int64_t nst, const double* __restrict__ tmax, __half* __restrict__ out, int chunk_lo,
+                         int TR) {
+    // chunk_lo > 0: only the 8-k chunks chunk_lo .. 7 of every 64-k stage are built (prod_gemm_gen_kernel generates
+    // chunks 0 .. chunk_lo - 1 on the SM).  TR = rows per operand tile: 128, or 64 for the B operand of the CTA-pair
+    // kernel (each CTA of a pair stages half of the 128 columns of a tile).
     __shared__ double xs[16][129];                   // [coordinate slot][row]
     __shared__ double ws[PB_WS_DOUBLES];             // [feature of the block][w (ncol), b, theta]
     const int64_t tile = blockIdx.x, g = blockIdx.y;
-    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const int64_t ir = tile * 128 + r;
+    const int r = threadIdx.x % TR, half = threadIdx.x / TR, nhalf = 256 / TR;
+    const int64_t ir = tile * TR + r;
     const int64_t j = j0 + g, jw = w_shared ? 0 : j;
     // coordinate slots: the columns this side uses, in order (arithmetic, not a table: a runtime-indexed array would
     // live in local memory and put an LDL in front of every DFMA)
     const int ncol = which == 0 ? s_hi - s_lo : d - (s_hi - s_lo);
     auto col_of = [&](int c) { return which == 0 ? s_lo + c : (c < s_lo ? c : c + (s_hi - s_lo)); };
-    for (int e = threadIdx.x; e < ncol * 128; e += 256) {
-        const int c = e / 128, rr = e % 128;
-        const int64_t gr = tile * 128 + rr;
+    for (int e = threadIdx.x; e < ncol * TR; e += 256) {
+        const int c = e / TR, rr = e % TR;
+        const int64_t gr = tile * TR + rr;
         xs[c][rr] = gr < nrow ? cand[(gr * row_stride) * d + col_of(c)] : 0.0;
     }
     __syncthreads();
@@ -727,8 +734,9 @@ __global__ void __launch_bounds__(256)
             ws[e] = v;   // theta / tmax as a float (bit pattern in the low word): the P operand is an fp32 product
         }
         __syncthreads();
-        for (int64_t kc = cb + half; kc < ce; kc += 2) {
+        for (int64_t kc = cb + half; kc < ce; kc += nhalf) {
             const int64_t st = kc / (TC_BK / 8), chunk = kc % (TC_BK / 8);
+            if (chunk < chunk_lo) continue;
             __align__(16) __half hi[8], lo[8];
             // the four features of the chunk are evaluated together, branch-free (out-of-range features / rows are
             // clamped for the loads and zeroed at the end), so their dependent chains -- the fp64 dot and reduction,
@@ -772,10 +780,10 @@ __global__ void __launch_bounds__(256)
                 split_f16(p0, hi[2 * q], lo[2 * q]);
                 split_f16(p1, hi[2 * q + 1], lo[2 * q + 1]);
             }
-            __half* blk = out + ((g * ntile + tile) * nst + st) * (int64_t)(TC_BLOCK_BYTES / 2);
-            const int64_t o = (chunk * 128 + r) * 8;
+            __half* blk = out + ((g * ntile + tile) * nst + st) * (int64_t)(2 * 8 * TR * 8);   // halves per block
+            const int64_t o = (chunk * TR + r) * 8;
             *reinterpret_cast<uint4*>(blk + o) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(blk + 8 * 128 * 8 + o) = *reinterpret_cast<const uint4*>(lo);
+            *reinterpret_cast<uint4*>(blk + 8 * TR * 8 + o) = *reinterpret_cast<const uint4*>(lo);
         }
     }
 }
@@ -845,9 +853,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const uint32_t s = (uint32_t)(gst % TC_NS), ph = (uint32_t)((gst / TC_NS) & 1);
                 mbar_wait_relaxed(&empty_b[s], ph ^ 1u, 32);
                 mbar_expect_tx(&full_b[s], TC_STAGE_BYTES);
-                bulk_g2s(stages + s * TC_STAGE_BYTES, srcA + st * (int64_t)TC_BLOCK_BYTES, TC_BLOCK_BYTES, &full_b[s]);
-                bulk_g2s(stages + s * TC_STAGE_BYTES + TC_BLOCK_BYTES, srcB + st * (int64_t)TC_BLOCK_BYTES, TC_BLOCK_BYTES,
-                         &full_b[s]);
+                // TC_COPY_SPLIT bulk copies per operand block (developer knob, compile time): more descriptors in flight
+#pragma unroll
+                for (int c = 0; c < TC_COPY_SPLIT; ++c) {
+                    constexpr uint32_t PIECE = TC_BLOCK_BYTES / TC_COPY_SPLIT;
+                    bulk_g2s(stages + s * TC_STAGE_BYTES + c * PIECE, srcA + st * (int64_t)TC_BLOCK_BYTES + c * PIECE, PIECE,
+                             &full_b[s]);
+                    bulk_g2s(stages + s * TC_STAGE_BYTES + TC_BLOCK_BYTES + c * PIECE,
+                             srcB + st * (int64_t)TC_BLOCK_BYTES + c * PIECE, PIECE, &full_b[s]);
+                }
             }
             }
         }
@@ -968,6 +982,605 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
     }
+}
+
+// ---- the same GEMM on CTA PAIRS (mode 6): tcgen05.mma.cta_group::2, 256 x 128 tiles per pair ------------------------
+// prod_gemm_topk_tc_kernel is bound by operand ingest: 64 KB per 64-k stage and SM (ncu: tensor pipe 38.6 % busy, both
+// operands arrive at ~30 B/clk/SM whatever the number or size of the bulk copies).  Here two CTAs of a cluster (the two
+// SMs of a TPC) share one 256 x 128 tile: each stages its OWN 128 rows of P (32 KB) but only HALF of the tile's 128
+// columns of Q (16 KB, its 64-column half; the tensor cores read the other half from the peer's shared memory), i.e.
+// 48 KB per stage and SM for the same MMA work, and four stages fit instead of three.  One lane of the LEADER CTA
+// (cluster rank 0) issues the MMAs for both SMs (M = 256: rows 0..127 accumulate in the leader's TMEM, 128..255 in the
+// peer's); tcgen05.commit multicasts the stage-empty and accumulator-full arrivals to both CTAs; the peer tells the
+// leader that its half of a stage has landed through a relay lane (remote mbarrier arrive), and the peer's epilogue
+// warps release the accumulator on the leader's barrier the same way.  Epilogue as in the single-CTA kernel (each CTA
+// drains and ranks its own 128 rows).
+constexpr int T2_NS = 4;
+constexpr uint32_t T2_BHALF_BYTES = TC_BLOCK_BYTES / 2;                       // 64 columns x 64 k x (hi + lo)
+constexpr uint32_t T2_STAGE_BYTES = TC_BLOCK_BYTES + T2_BHALF_BYTES;          // 48 KB
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // observes remote arrivals
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tc2_commit_mc(uint64_t* bar) {   // arrives on `bar` of BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc2_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    prod_gemm_topk_tc2_kernel(const __half* __restrict__ Pt, const __half* __restrict__ Qt, int64_t nu, int64_t nv,
+                              int ntu, int ntv, int nst, double scale0, const double* __restrict__ tmax,
+                              int64_t idx_offset, int kp, int G, double* __restrict__ part_val,
+                              int64_t* __restrict__ part_idx) {
+    extern __shared__ __align__(1024) unsigned char t2_smem_raw[];
+    unsigned char* stages = t2_smem_raw;                                           // [T2_NS][A block | B half block]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(t2_smem_raw + T2_NS * T2_STAGE_BYTES);
+    uint64_t* full_b = bars;                     // [T2_NS] this CTA's producer -> (leader: MMA, peer: relay)
+    uint64_t* peer_full = full_b + T2_NS;        // [T2_NS] leader only: the peer's relay -> MMA
+    uint64_t* empty_b = peer_full + T2_NS;       // [T2_NS] MMA (multicast commit) -> producer of each CTA
+    uint64_t* acc_full = empty_b + T2_NS;        // [2] MMA (multicast commit) -> epilogue of each CTA
+    uint64_t* acc_empty = acc_full + 2;          // [2] leader only: the epilogue warps of BOTH CTAs -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = (int)(blockIdx.x >> 1), npair = (int)(gridDim.x >> 1);
+    const int ntu2 = (ntu + 1) / 2;              // row-tile PAIRS per sample
+    const int tps = ntu2 * ntv;
+    const int ntot = tps * G;
+    const int ntile = pair < ntot ? (ntot - pair + npair - 1) / npair : 0;
+    const int nseg = nst / TC_SEG;
+    if (tid == 0) {
+        for (int s = 0; s < T2_NS; ++s) {
+            mbar_init(&full_b[s], 1);
+            mbar_init(&peer_full[s], 1);
+            mbar_init(&empty_b[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 2 * TC_EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // both CTAs: barriers initialised and TMEM allocated before anything crosses over
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (int it = 0; it < ntile; ++it) {
+                const int t = pair + it * npair;
+                const int rt = 2 * (t % ntu2) + (int)rank, ct = (t / ntu2) % ntv, g = t / tps;
+                // P blocks of this CTA's 128 rows (the array holds 2 ntu2 row tiles per sample: an odd ntu is padded with
+                // a zero tile); Q half blocks: 64-column tiles, this CTA's half of column tile ct
+                const unsigned char* srcA = reinterpret_cast<const unsigned char*>(Pt) +
+                                            ((int64_t)(g * 2 * ntu2 + rt) * nst) * (int64_t)TC_BLOCK_BYTES;
+                const unsigned char* srcB = reinterpret_cast<const unsigned char*>(Qt) +
+                                            ((int64_t)(g * 2 * ntv + 2 * ct + (int)rank) * nst) * (int64_t)T2_BHALF_BYTES;
+                for (int st = 0; st < nst; ++st) {
+                    mbar_wait(&empty_b[s], ph ^ 1u);
+                    mbar_expect_tx(&full_b[s], T2_STAGE_BYTES);
+                    bulk_g2s(stages + s * T2_STAGE_BYTES, srcA + st * (int64_t)TC_BLOCK_BYTES, TC_BLOCK_BYTES, &full_b[s]);
+                    bulk_g2s(stages + s * T2_STAGE_BYTES + TC_BLOCK_BYTES, srcB + st * (int64_t)T2_BHALF_BYTES,
+                             T2_BHALF_BYTES, &full_b[s]);
+                    if (++s == T2_NS) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && !leader) {
+            // relay: tell the leader's MMA lane that this CTA's half of the stage has landed
+            uint32_t s = 0, ph = 0;
+            const int total = ntile * nst;
+            for (int x = 0; x < total; ++x) {
+                mbar_wait(&full_b[s], ph);
+                mbar_arrive_remote(mapa_u32(smem_u32(&peer_full[s]), 0));
+                if (++s == T2_NS) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        } else if (lane == 0) {
+            const uint32_t idesc = tc_idesc_f16(256, 128);
+            const uint32_t base = smem_u32(stages);
+            uint32_t s = 0, ph = 0;
+            const int segs = ntile * nseg;
+            for (int seg = 0; seg < segs; ++seg) {
+                const uint32_t a = (uint32_t)(seg & 1), pa = (uint32_t)((seg >> 1) & 1);
+                mbar_wait_cluster(&acc_empty[a], pa ^ 1u);
+                tc_fence_after();
+                for (int q4 = 0; q4 < TC_SEG; ++q4) {
+                    mbar_wait(&full_b[s], ph);
+                    mbar_wait_cluster(&peer_full[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * T2_STAGE_BYTES, sb = sa + TC_BLOCK_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 16; ++ks) {
+                        const uint32_t offa = (uint32_t)(2 * ks) * 128u * 16u;     // 2 chunks of 8 halves x 128 rows
+                        const uint32_t offb = (uint32_t)(2 * ks) * 64u * 16u;      // ... x 64 columns per CTA
+                        const uint64_t a_hi = tc_desc(sa + offa, 128 * 16, 128);
+                        const uint64_t a_lo = tc_desc(sa + TC_BLOCK_BYTES / 2 + offa, 128 * 16, 128);
+                        const uint64_t b_hi = tc_desc(sb + offb, 64 * 16, 128);
+                        const uint64_t b_lo = tc_desc(sb + T2_BHALF_BYTES / 2 + offb, 64 * 16, 128);
+                        const uint32_t first = (q4 == 0 && ks == 0) ? 0u : 1u;
+                        tc2_mma_f16(tmem + a * 128u, a_lo, b_hi, idesc, first);
+                        tc2_mma_f16(tmem + a * 128u, a_hi, b_lo, idesc, 1u);
+                        tc2_mma_f16(tmem + a * 128u, a_hi, b_hi, idesc, 1u);
+                    }
+                    tc2_commit_mc(&empty_b[s]);            // both CTAs: the stage is free once these MMAs have read it
+                    if (++s == T2_NS) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+                tc2_commit_mc(&acc_full[a]);               // both CTAs: the segment's accumulator is complete
+            }
+        }
+        __syncwarp();
+    } else {
+        const int ew = warp - 2;                       // 0..15
+        const int quarter = warp & 3;                  // TMEM lanes this warp may access
+        const int cb = ew >> 2;                        // columns [32 cb, 32 cb + 32)
+        const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32);
+        const uint32_t ae_remote0 = mapa_u32(smem_u32(&acc_empty[0]), 0), ae_remote1 = mapa_u32(smem_u32(&acc_empty[1]), 0);
+        int gseg = 0;
+        for (int it = 0; it < ntile; ++it) {
+            const int t = pair + it * npair;
+            const int rt = 2 * (t % ntu2) + (int)rank, ct = (t / ntu2) % ntv, g = t / tps;
+            const double scale = scale0 * tmax[g];
+            double sum[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) sum[c] = 0.0;
+            for (int seg = 0; seg < nseg; ++seg, ++gseg) {
+                const uint32_t a = (uint32_t)(gseg & 1), pa = (uint32_t)((gseg >> 1) & 1);
+                mbar_wait(&acc_full[a], pa);
+                tc_fence_after();
+                uint32_t v0[32];
+                TC_LD32(v0, t_lane + a * 128u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (leader) tc_arrive(&acc_empty[a]);
+                    else mbar_arrive_remote(a ? ae_remote1 : ae_remote0);
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) sum[c] += (double)__uint_as_float(v0[c]);
+            }
+            if (rt >= ntu) continue;                   // the zero tile that pads an odd number of row tiles
+            // per-warp top-kp of its 32 rows x 32 columns: every lane caches the best of its not yet consumed values
+            const int64_t row = (int64_t)rt * 128 + quarter * 32 + lane;
+            const int64_t colb = (int64_t)ct * 128 + cb * 32;
+            const int64_t list = (int64_t)(rt * ntv + ct) * TC_EPI_WARPS + ew;
+            double* ov = part_val + (list * G + g) * kp;
+            int64_t* oi = part_idx + (list * G + g) * kp;
+            uint32_t used = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                sum[c] = __dmul_rn(scale, sum[c]);
+                if (!(row < nu && colb + c < nv)) used |= 1u << c;
+            }
+            const int64_t ci0 = row * nv + colb + idx_offset;
+            for (int r = 0; r < kp; ++r) {
+                double bv = neg_inf();
+                int bc = -1;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)           // ascending c = ascending index: strict > keeps the lowest index
+                    if (!((used >> c) & 1u) && (bc < 0 || sum[c] > bv)) {
+                        bv = sum[c];
+                        bc = c;
+                    }
+                double wv = bv;
+                int64_t wi = bc >= 0 ? ci0 + bc : INT64_MAX;
+                if (bc < 0) wv = neg_inf();
+                warp_argmax(wv, wi);
+                const bool found = (wi != INT64_MAX);
+                if (lane == 0) {
+                    ov[r] = found ? wv : neg_inf();
+                    oi[r] = found ? wi : -1;
+                }
+                if (!found) {
+                    for (int q = r + 1; q < kp; ++q)
+                        if (lane == 0) {
+                            ov[q] = neg_inf();
+                            oi[q] = -1;
+                        }
+                    break;
+                }
+                if (bc >= 0 && wi == ci0 + bc) used |= 1u << bc;   // the winning lane consumes its element
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // neither CTA leaves (or frees its TMEM) while the other may still signal / read it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+    }
+}
+
+// ---- the same GEMM with the P operand GENERATED ON THE SM (mode 4) -------------------------------------------------
+// prod_gemm_topk_tc_kernel streams both operands: 64 KB per 64-k stage and SM, i.e. more than an SM ingests while the
+// tensor pipe works through a stage (ncu, round 1: tensor pipe 38.6 % busy, epilogue warps parked on acc_full), and its
+// operands make a round trip through HBM (prod_build_tc_kernel: 16.8 GB written and read back per C3 step).  Here only
+// the Q blocks (the V side, no theta) are built ahead and streamed (32 KB per stage); the P block of every stage --
+// theta~ cos(alpha), -theta~ sin(alpha), alpha = w_U . u + b, for the tile's 128 rows and the stage's 32 features -- is
+// computed by the 16 epilogue warps straight into the stage buffer (generic-proxy stores + fence.proxy.async), with
+// exactly the arithmetic of prod_build_tc_kernel (fp64 argument, rint by the 2^52 shift, __sincosf, fp32 theta product,
+// hi/lo fp16 split), so the error budget of prod_exact_kernel is unchanged.  The feature records
+// [w_U (ncol), b, theta~] reach shared memory through a ring of small bulk copies issued PG_AHEAD stages ahead by the
+// producer lane; a ring slot is reused PG_RING stages later, which the stage-empty barrier the producer has just
+// passed already orders after the generators' reads (its MMAs consumed an A block written from those records).
+// Every fourth stage the same warps drain the previous 256-k segment from TMEM into double-float running sums.
+constexpr int PG_NS = 3, PG_RING = 8, PG_AHEAD = 5, PG_MAXCOL = 6, PG_THREADS = 640;
+__host__ __device__ inline int pg_rs(int ncol) { return ncol + 2; }
+__host__ __device__ inline size_t pg_smem_bytes(int ncol) {
+    return (size_t)PG_NS * TC_STAGE_BYTES + (size_t)PG_RING * 32 * pg_rs(ncol) * 8 + (size_t)ncol * 128 * 8 + 512;
+}
+
+// featP[(j * Fp + f) * rs + ...] = [w (ncol slow columns), b, theta_j[f] / tmax_j as a float in the low word]; features
+// F .. Fp - 1 are zero records (theta~ = 0 -> zero operand columns)
+__global__ void prod_featp_kernel(const double* __restrict__ W, const double* __restrict__ b,
+                                  const double* __restrict__ theta, const double* __restrict__ tmax, int64_t S,
+                                  int64_t F, int64_t Fp, int d, int s_lo, int ncol, int w_shared,
+                                  double* __restrict__ featP) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S * Fp) return;
+    const int64_t j = t / Fp, f = t % Fp, jw = w_shared ? 0 : j;
+    const int rs = pg_rs(ncol);
+    double* o = featP + t * rs;
+    if (f >= F) {
+        for (int c = 0; c < rs; ++c) o[c] = 0.0;
+        return;
+    }
+    for (int c = 0; c < ncol; ++c) o[c] = W[(jw * F + f) * d + s_lo + c];
+    o[ncol] = b[jw * F + f];
+    const double tm = tmax[j];
+    const double inv_tm = tm > 0.0 ? 1.0 / tm : 0.0;
+    o[ncol + 1] = __hiloint2double(0, __float_as_int((float)(theta[j * F + f] * inv_tm)));
+}
+
+// GC = chunks of 8 k per 64-k stage generated on the SM (8: the whole P block; 4: the first half, the second half is
+// streamed from the array prod_build_tc_kernel wrote -- generation and operand ingest then share the load)
+template <int NCOL, int GC>
+__global__ void __launch_bounds__(PG_THREADS, 1)
+    prod_gemm_gen_kernel(const double* __restrict__ cand, int64_t nu, int64_t nv, int d, int s_lo,
+                         const double* __restrict__ featP, int64_t Fp, const __half* __restrict__ Pt,
+                         const __half* __restrict__ Qt, int ntu, int ntv,
+                         int nst, double scale0, const double* __restrict__ tmax, int64_t j0, int64_t idx_offset, int kp,
+                         int G, double* __restrict__ part_val, int64_t* __restrict__ part_idx) {
+    extern __shared__ __align__(1024) unsigned char pg_smem_raw[];
+    constexpr int RS = NCOL + 2;
+    constexpr uint32_t REC_BYTES = 32 * RS * 8;
+    unsigned char* stages = pg_smem_raw;                                               // [PG_NS][A block | B block]
+    double* ring = reinterpret_cast<double*>(pg_smem_raw + PG_NS * TC_STAGE_BYTES);    // [PG_RING][32][RS]
+    double* xs = ring + PG_RING * 32 * RS;                                             // [NCOL][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + NCOL * 128);
+    uint64_t* full_b = bars;                    // [PG_NS] producer (B block landed) -> MMA
+    uint64_t* a_full = full_b + PG_NS;          // [PG_NS] generators (A block written) -> MMA
+    uint64_t* empty_b = a_full + PG_NS;         // [PG_NS] MMA (commit) -> producer, generators
+    uint64_t* rec_full = empty_b + PG_NS;       // [PG_RING] producer (records landed) -> generators
+    uint64_t* acc_full = rec_full + PG_RING;    // [2] MMA (commit) -> epilogue
+    uint64_t* acc_empty = acc_full + 2;         // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tps = ntu * ntv;                  // tiles per sample
+    const int ntot = tps * G;
+    const int ntile = (int)blockIdx.x < ntot ? (ntot - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int nseg = nst / TC_SEG;
+    if (tid == 0) {
+        for (int s = 0; s < PG_NS; ++s) {
+            mbar_init(&full_b[s], 1);
+            mbar_init(&a_full[s], TC_EPI_WARPS);
+            mbar_init(&empty_b[s], 1);
+        }
+        for (int r = 0; r < PG_RING; ++r) mbar_init(&rec_full[r], 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], TC_EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 17) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // warps 0..15: generators + epilogue; warp 16 = producer lane, warp 17 = MMA lane, 18 / 19 idle
+
+    if (warp == 16) {
+        if (lane == 0) {
+            // records run PG_AHEAD stages ahead of the B blocks: (ri, rst) = tile / stage of the next record block
+            int ri = 0, rst = 0;
+            uint32_t rr = 0;
+            auto issue_rec = [&]() {
+                const int g = ((int)blockIdx.x + ri * (int)gridDim.x) / tps;
+                mbar_expect_tx(&rec_full[rr], REC_BYTES);
+                bulk_g2s(ring + (size_t)rr * 32 * RS, featP + ((j0 + g) * Fp + (int64_t)rst * 32) * RS, REC_BYTES,
+                         &rec_full[rr]);
+                rr = (rr + 1) & (PG_RING - 1);
+                if (++rst == nst) {
+                    rst = 0;
+                    ++ri;
+                }
+            };
+            for (int x = 0; x < PG_AHEAD && ri < ntile; ++x) issue_rec();
+            uint32_t s = 0, ph = 0;
+            for (int it = 0; it < ntile; ++it) {
+                const int t = (int)blockIdx.x + it * (int)gridDim.x;
+                const int rt = t % ntu, ct = (t / ntu) % ntv, g = t / tps;
+                const unsigned char* srcB = reinterpret_cast<const unsigned char*>(Qt) +
+                                            ((int64_t)(g * ntv + ct) * nst) * (int64_t)TC_BLOCK_BYTES;
+                const unsigned char* srcA = reinterpret_cast<const unsigned char*>(Pt) +
+                                            ((int64_t)(g * ntu + rt) * nst) * (int64_t)TC_BLOCK_BYTES;
+                for (int st = 0; st < nst; ++st) {
+                    mbar_wait_relaxed(&empty_b[s], ph ^ 1u, 32);
+                    constexpr uint32_t A_STREAM = (8 - GC) * 128 * 16;      // bytes of the hi (and of the lo) half streamed
+                    mbar_expect_tx(&full_b[s], TC_BLOCK_BYTES + 2 * A_STREAM);
+                    bulk_g2s(stages + s * TC_STAGE_BYTES + TC_BLOCK_BYTES, srcB + st * (int64_t)TC_BLOCK_BYTES,
+                             TC_BLOCK_BYTES, &full_b[s]);
+                    if (GC < 8) {
+                        const unsigned char* sa = srcA + st * (int64_t)TC_BLOCK_BYTES + GC * 128 * 16;
+                        unsigned char* da = stages + s * TC_STAGE_BYTES + GC * 128 * 16;
+                        bulk_g2s(da, sa, A_STREAM, &full_b[s]);
+                        bulk_g2s(da + TC_BLOCK_BYTES / 2, sa + TC_BLOCK_BYTES / 2, A_STREAM, &full_b[s]);
+                    }
+                    // the ring slot about to be refilled last held the records of the stage 3 = PG_RING - PG_AHEAD back,
+                    // whose A block the MMAs behind the barrier just passed have consumed
+                    if (ri < ntile) issue_rec();
+                    if (++s == PG_NS) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 17) {
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc_f16(128, 128);
+            const uint32_t base = smem_u32(stages);
+            uint32_t s = 0, ph = 0;
+            const int segs = ntile * nseg;
+            for (int seg = 0; seg < segs; ++seg) {
+                const uint32_t a = (uint32_t)(seg & 1), pa = (uint32_t)((seg >> 1) & 1);
+                mbar_wait_relaxed(&acc_empty[a], pa ^ 1u, 32);
+                tc_fence_after();
+                for (int q4 = 0; q4 < TC_SEG; ++q4) {
+                    mbar_wait(&full_b[s], ph);      // (tight waits: the hand-off latency is on the critical path here)
+                    mbar_wait(&a_full[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_BLOCK_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 16; ++ks) {
+                        const uint32_t off = (uint32_t)(2 * ks) * 128u * 16u;
+                        const uint64_t a_hi = tc_desc(sa + off, 128 * 16, 128);
+                        const uint64_t a_lo = tc_desc(sa + TC_BLOCK_BYTES / 2 + off, 128 * 16, 128);
+                        const uint64_t b_hi = tc_desc(sb + off, 128 * 16, 128);
+                        const uint64_t b_lo = tc_desc(sb + TC_BLOCK_BYTES / 2 + off, 128 * 16, 128);
+                        const uint32_t first = (q4 == 0 && ks == 0) ? 0u : 1u;
+                        tc_mma_f16(tmem + a * 128u, a_lo, b_hi, idesc, first);
+                        tc_mma_f16(tmem + a * 128u, a_hi, b_lo, idesc, 1u);
+                        tc_mma_f16(tmem + a * 128u, a_hi, b_hi, idesc, 1u);
+                    }
+                    tc_commit(&empty_b[s]);
+                    if (++s == PG_NS) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+                tc_commit(&acc_full[a]);
+            }
+        }
+        __syncwarp();
+    } else if (warp < 16) {
+        const int ew = warp;
+        const int quarter = warp & 3, cb = ew >> 2;
+        const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32);
+        const int te = tid, gr = te & 127, part = te >> 7;     // generator role: row gr, GC / 4 chunks of four features
+        constexpr int CPT = GC / 4;                           // chunks per thread and stage
+        const double* xrow = xs + gr;
+        const uint32_t aoff = (uint32_t)((CPT * part) * 128 + gr) * 16u;
+        uint32_t s = 0, ph = 0, rr = 0, pr = 0;
+        int gs = 0;
+        for (int it = 0; it < ntile; ++it) {
+            const int t = (int)blockIdx.x + it * (int)gridDim.x;
+            const int rt = t % ntu, ct = (t / ntu) % ntv, g = t / tps;
+            // the tile's slow coordinates; the MMAs of the previous tile may still be in flight (they do not read xs)
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            for (int e = te; e < NCOL * 128; e += 512) {
+                const int c = e >> 7, r_ = e & 127;
+                const int64_t grow = (int64_t)rt * 128 + r_;
+                xs[e] = grow < nu ? cand[(grow * nv) * d + s_lo + c] : 0.0;
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            double x[NCOL];
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) x[c] = xrow[c * 128];
+            // running sums of the 256-k fp32 segments, in fp32: the segments bound the tensor core's internal accumulation
+            // error; adding nseg of them adds nseg roundings of 2^-24 of the sum of |terms| (prod_exact_kernel's B
+            // carries 1.5 nseg 2^-24: +1.5 % at F = 1024) -- and costs 32 registers and one FADD per value instead of
+            // 64 registers and a TwoSum
+            float acc[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
+            auto drain = [&](int dseg) {
+                const uint32_t a = (uint32_t)(dseg & 1), pa = (uint32_t)((dseg >> 1) & 1);
+                mbar_wait(&acc_full[a], pa);
+                tc_fence_after();
+                uint32_t v0[32];
+                TC_LD32(v0, t_lane + a * 128u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc_arrive(&acc_empty[a]);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) acc[c] = __fadd_rn(acc[c], __uint_as_float(v0[c]));
+            };
+            // iteration seg generates segment seg (if any) and then drains segment seg - 1: ONE call site of the drain, so
+            // that it is inlined and the running sums stay in registers
+            for (int seg = 0; seg <= nseg; ++seg) {
+#pragma unroll 1
+                for (int q4 = 0; q4 < TC_SEG && seg < nseg; ++q4) {
+                    mbar_wait(&rec_full[rr], pr);
+                    // (the slot was released by the MMAs of three stages ago: when the generators are the bottleneck this
+                    // wait is free, and waiting first lets every chunk be stored as soon as it is formed)
+                    mbar_wait(&empty_b[s], ph ^ 1u);
+                    const double* rec = ring + (size_t)rr * 32 * RS + (size_t)(4 * CPT * part) * RS;
+                    unsigned char* ablk = stages + s * TC_STAGE_BYTES + aoff;
+#pragma unroll
+                    for (int hq = 0; hq < CPT; ++hq) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double* rq = rec + (4 * hq + q) * RS;
+                            double a = rq[NCOL];
+#pragma unroll
+                            for (int c = 0; c < NCOL; ++c) a = fma(rq[c], x[c], a);
+                            const float th = __int_as_float(__double2loint(rq[NCOL + 1]));
+                            // same sequence as prod_build_tc_kernel (the operand error budget of prod_exact_kernel)
+                            float sn, cs;
+                            const double tt = a * 0.15915494309189535;
+                            const double red = __dadd_rn(__dadd_rn(tt, 6755399441055744.0), -6755399441055744.0);
+                            __sincosf((float)(a - 6.283185307179586 * red), &sn, &cs);
+                            const float p0 = __fmul_rn(th, cs), p1 = __fmul_rn(-th, sn);
+                            const __half2 h = __floats2half2_rn(p0, p1);
+                            const float2 hf = __half22float2(h);
+                            const __half2 l = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+                            hi[q] = *reinterpret_cast<const uint32_t*>(&h);
+                            lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+                        }
+                        *reinterpret_cast<uint4*>(ablk + hq * 128 * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(ablk + TC_BLOCK_BYTES / 2 + hq * 128 * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to the MMA
+                    __syncwarp();
+                    if (lane == 0) tc_arrive(&a_full[s]);
+                    if (++s == PG_NS) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                    rr = (rr + 1) & (PG_RING - 1);
+                    if (rr == 0) pr ^= 1u;
+                }
+                // the PREVIOUS segment: its MMAs were issued a segment ago, so the wait is (nearly) free and the tensor
+                // pipe keeps running on the stages just generated
+                if (seg > 0) drain(gs++);
+            }
+            // per-warp top-kp of its 32 rows x 32 columns (same selection as prod_gemm_topk_tc_kernel)
+            const double scale = scale0 * tmax[j0 + g];
+            const int64_t row = (int64_t)rt * 128 + quarter * 32 + lane;
+            const int64_t colb = (int64_t)ct * 128 + cb * 32;
+            const int64_t list = (int64_t)(rt * ntv + ct) * TC_EPI_WARPS + ew;
+            double* ov = part_val + (list * G + g) * kp;
+            int64_t* oi = part_idx + (list * G + g) * kp;
+            uint32_t used = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (!(row < nu && colb + c < nv)) used |= 1u << c;
+            const int64_t ci0 = row * nv + colb + idx_offset;
+            for (int r = 0; r < kp; ++r) {
+                float bh = 0.0f;
+                int bc = -1;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)           // ascending c = ascending index: strict > keeps the lowest index
+                    if (!((used >> c) & 1u) && (bc < 0 || acc[c] > bh)) {
+                        bh = acc[c];
+                        bc = c;
+                    }
+                double wv = bc >= 0 ? __dmul_rn(scale, (double)bh) : neg_inf();
+                int64_t wi = bc >= 0 ? ci0 + bc : INT64_MAX;
+                warp_argmax(wv, wi);
+                const bool found = (wi != INT64_MAX);
+                if (lane == 0) {
+                    ov[r] = found ? wv : neg_inf();
+                    oi[r] = found ? wi : -1;
+                }
+                if (!found) {
+                    for (int q = r + 1; q < kp; ++q)
+                        if (lane == 0) {
+                            ov[q] = neg_inf();
+                            oi[q] = -1;
+                        }
+                    break;
+                }
+                if (bc >= 0 && wi == ci0 + bc) used |= 1u << bc;   // the winning lane consumes its element
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 17) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+    }
+}
+
+template <int NCOL, int GC>
+static int launch_prod_gemm_gen(int sms, const double* cand, int64_t nu, int64_t nv, int d, int s_lo, const double* featP,
+                                int64_t Fp, const __half* Pt, const __half* Qt, int ntu, int ntv, int nst, double scale,
+                                const double* tmax, int64_t j0, int64_t idx_offset, int kp, int G, double* pv, int64_t* pi,
+                                cudaStream_t st) {
+    TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_gen_kernel<NCOL, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)pg_smem_bytes(NCOL)));
+    const int ntot = ntu * ntv * G;
+    prod_gemm_gen_kernel<NCOL, GC><<<(unsigned)(ntot < sms ? ntot : sms), PG_THREADS, pg_smem_bytes(NCOL), st>>>(
+        cand, nu, nv, d, s_lo, featP, Fp, Pt, Qt, ntu, ntv, nst, scale, tmax, j0, idx_offset, kp, G, pv, pi);
+    TES_LAUNCH_OK();
+    return 0;
 }
 
 // ---- TES_ep quadratic forms as a 3xFP16 tcgen05 GEMM (screen; criteria.cu refines the candidates near the arg-max) --
@@ -1115,7 +1728,7 @@ __host__ __device__ inline int64_t qf_msm_floats(int64_t T) { return ((T + 8) * 
 __global__ void __launch_bounds__(TC_THREADS, 1)
     quad_screen_fused_kernel(const double* __restrict__ G, int64_t ldg, int64_t nc, int64_t T,
                              const uint32_t* __restrict__ ab, int64_t Kdim, const __half* __restrict__ Bt, int64_t Sp,
-                             int64_t nst, int64_t ntu, const double* __restrict__ rowmax,
+                             int64_t nst, int64_t ntu, double* __restrict__ rowmax,
                              const double* __restrict__ colscale, double* __restrict__ Qout) {
     extern __shared__ __align__(1024) unsigned char qf_smem_raw[];
     unsigned char* stages = qf_smem_raw;                                            // [QF_NS][A block | B block]
@@ -1233,7 +1846,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, off));
                 const double sc = rm > 0.0 ? 64.0 / rm : 0.0;                       // 64^2 = QS_AMAX
-                if (lane == 0) rmax_s[rr] = rm;
+                if (lane == 0) {
+                    rmax_s[rr] = rm;
+                    if (grow < nc) rowmax[grow] = rm;      // the absolute term of the screen's error bound needs it
+                }
 #pragma unroll 4
                 for (int a = lane; a < (int)T; a += 32) msm[a * 129 + rr] = sc != 0.0 ? (float)(gp[a] * sc) : 0.0f;
             }
@@ -1666,6 +2282,8 @@ __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const 
         // fp16 operands (mode 2; same 11-bit significand as TF32, theta normalised by tmax): subnormal rounding adds an
         // absolute 2^-25 per operand, i.e. <= 2 * 2^-25 per term over 2F terms, in units of scale * tmax
         if (tf32 >= 2) B += 1.5 * scale * tmax[j] * 4.0 * (double)F * 2.98023223876953125e-08;
+        // modes 4 / 5 add the 2F / 256 segment values in fp32: one rounding of 2^-24 of the sum of |terms| per segment
+        if (tf32 >= 4) B += 1.5 * scale * sa * 5.9604644775390625e-08 * (double)((2 * F + 255) / 256);
         const double vk = approx_val[j * kp + (k - 1)], vl = approx_val[j * kp + (kp - 1)];
         const bool full = idx[j * kp + (kp - 1)] >= 0;   // fewer than kp candidates in total: nothing was cut
         const bool enough = idx[j * kp + (k - 1)] >= 0;  // NaN values are never selected: let the general kernel decide
@@ -1700,11 +2318,16 @@ __global__ void prod_xmax_kernel(const double* __restrict__ cand, int64_t nu, in
 struct ProdPlan {
     int64_t nu, G, gx, gy, nlist, nup, nvp, K2p;
     int rec, kp;
-    int64_t off_feat, off_p, off_q, off_pv, off_pi, off_mv, off_mi, off_ev, off_xmax, off_tmax, total;
+    int64_t off_feat, off_p, off_q, off_pv, off_pi, off_mv, off_mi, off_ev, off_xmax, off_tmax, off_featp, total;
 };
 
-static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k, int tf32 = 0, int tc = 0) {
+static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k, int tf32 = 0, int tc = 0,
+                          int gen_ncol = 0, int gen_gc = 8) {
+    // gen_ncol > 0: modes 4 / 5 -- the P operand is generated on the SM from feature records of gen_ncol slow columns:
+    // entirely (gen_gc = 8: no P array) or the first gen_gc of the 8 chunks of every stage (gen_gc = 4: P array as in mode 3)
     ProdPlan p;
+    const bool no_p = gen_ncol && gen_gc == 8;
+    const bool pairs = tc == 2;                  // mode 6: CTA pairs, 256-row tile pairs (an odd tile count is padded)
     p.nu = N / nv;
     p.rec = prod_rec((int)d);
     p.kp = k + 8 > PROD_MAX_KP ? PROD_MAX_KP : k + 8;
@@ -1712,7 +2335,8 @@ static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F
     p.nvp = (nv + PT_BN - 1) / PT_BN * PT_BN;
     p.K2p = tc ? (2 * F + 255) / 256 * 256 : (2 * F + PH_BK - 1) / PH_BK * PH_BK;
     if (tc) p.nvp = (nv + 127) / 128 * 128;
-    const int64_t per_sample = tf32 ? (p.nup + p.nvp) * p.K2p * 8 : (p.nu + nv) * 2 * F * 8;
+    if (pairs) p.nup = (p.nu + 255) / 256 * 256;
+    const int64_t per_sample = no_p ? p.nvp * p.K2p * 8 : (tf32 ? (p.nup + p.nvp) * p.K2p * 8 : (p.nu + nv) * 2 * F * 8);
     int64_t G = per_sample > 0 ? (int64_t)(1.5e9 / (double)per_sample) : 1;
     if (G < 1) G = 1;
     if (G > S) G = S;
@@ -1748,7 +2372,8 @@ static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F
         return r;
     };
     p.off_feat = take(S * F * p.rec * 8);
-    p.off_p = take(tf32 ? G * p.nup * p.K2p * 8 : G * p.nu * 2 * F * 8);     // tf32: hi and lo float arrays
+    // tf32: hi and lo float arrays
+    p.off_p = take(no_p ? 256 : (tf32 ? G * p.nup * p.K2p * 8 : G * p.nu * 2 * F * 8));
     p.off_q = take(tf32 ? G * p.K2p * p.nvp * 8 : G * 2 * F * nv * 8);
     p.off_pv = take(p.nlist * G * p.kp * 8);
     p.off_pi = take(p.nlist * G * p.kp * 8);
@@ -1757,6 +2382,7 @@ static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F
     p.off_ev = take(S * p.kp * 8);
     p.off_xmax = take(64 * 8);
     p.off_tmax = take(S * 8);
+    p.off_featp = take(gen_ncol ? S * (p.K2p / 2) * pg_rs(gen_ncol) * 8 : 0);   // [w_U, b, theta~] records of all S samples
     p.total = o;
     return p;
 }
@@ -1799,7 +2425,13 @@ using namespace tes;
 extern "C" int64_t tes_rff_topk_product_workspace_bytes(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k,
                                                         int tf32) {
     if (N < 1 || d < 2 || d > 64 || nv < 1 || N % nv != 0 || S < 1 || F < 1 || k < 1 || k > 8) return -1;
-    return prod_plan(N, d, nv, S, F, k, tf32 != 0, tf32 == 3).total;   // tf32 / fp16 operand arrays: (hi, lo) x 4 resp. 2 bytes
+    // modes 4 / 5 (P generated on the SM) need the split, which this query does not carry: the largest layout
+    const int64_t a = prod_plan(N, d, nv, S, F, k, tf32 != 0, tf32 >= 3).total;   // tf32 / fp16 operand arrays: (hi, lo) x 4 resp. 2 bytes
+    if (tf32 == 6) return prod_plan(N, d, nv, S, F, k, 1, 2).total;
+    if (tf32 < 4) return a;
+    const int64_t b = prod_plan(N, d, nv, S, F, k, 1, 1, PG_MAXCOL, 8).total;
+    const int64_t c = prod_plan(N, d, nv, S, F, k, 1, 1, PG_MAXCOL, 4).total;
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d, int64_t s_lo, int64_t s_hi, int64_t nv,
@@ -1821,9 +2453,12 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     if (!out_idx) return -15;
     if (!out_val) return -16;
     if (!out_flag) return -17;
-    if (tf32 < 0 || tf32 > 3) return -18;
+    if (tf32 < 0 || tf32 > 6) return -18;
     if (tf32 >= 2 && d > 16) tf32 = 1;   // the fp16 operand build keeps a feature's weights in 16 registers
-    ProdPlan pl = prod_plan(N, d, nv, S, F, k, tf32 != 0, tf32 == 3);
+    if ((tf32 == 4 || tf32 == 5) && s_hi - s_lo > PG_MAXCOL) tf32 = 3;   // modes 4 / 5 keep the slow coordinates and the record ring in smem
+    const int gen_ncol = (tf32 == 4 || tf32 == 5) ? (int)(s_hi - s_lo) : 0;
+    const int gen_gc = tf32 == 5 ? 4 : 8;
+    ProdPlan pl = prod_plan(N, d, nv, S, F, k, tf32 != 0, tf32 == 6 ? 2 : (tf32 >= 3), gen_ncol, gen_gc);
     if (!ws || ws_bytes < pl.total) return -100;
     cudaStream_t st = (cudaStream_t)stream;
     char* base = (char*)ws;
@@ -1837,6 +2472,7 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     double* ev = (double*)(base + pl.off_ev);
     double* xmax = (double*)(base + pl.off_xmax);
     double* tmax = (double*)(base + pl.off_tmax);
+    double* featP = (double*)(base + pl.off_featp);
     const double scale = sqrt(2.0 * sigma / (double)F);
     const int64_t nu = pl.nu, K2 = 2 * F;
     prod_pack_kernel<<<(unsigned)((S * F + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, (int)d, w_shared, pl.rec, feat);
@@ -1861,22 +2497,69 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
                                          (int)sizeof(PhSmem)));
         TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(TC_NS * TC_STAGE_BYTES + 256)));
+        TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(T2_NS * T2_STAGE_BYTES + 256)));
         // zero the tile padding once (rows >= nu, columns >= nv, k >= 2F are never written by the build kernels)
-        TES_CUDA_OK(cudaMemsetAsync(P, 0, (size_t)(pl.G * pl.nup * pl.K2p * 8), st));
+        if (!(gen_ncol && gen_gc == 8)) TES_CUDA_OK(cudaMemsetAsync(P, 0, (size_t)(pl.G * pl.nup * pl.K2p * 8), st));
         TES_CUDA_OK(cudaMemsetAsync(Qt, 0, (size_t)(pl.G * pl.K2p * pl.nvp * 8), st));
         prod_tmax_kernel<<<(unsigned)S, 256, 0, st>>>(theta, F, tmax);
         TES_LAUNCH_OK();
+        if (gen_ncol) {
+            const int64_t Fp = pl.K2p / 2;
+            prod_featp_kernel<<<(unsigned)((S * Fp + 255) / 256), 256, 0, st>>>(W, b, theta, tmax, S, F, Fp, (int)d, (int)s_lo,
+                                                                                 gen_ncol, w_shared, featP);
+            TES_LAUNCH_OK();
+        }
     }
     for (int64_t j0 = 0; j0 < S; j0 += pl.G) {
         const int64_t G = (S - j0 < pl.G) ? (S - j0) : pl.G;
         dim3 grid((unsigned)pl.gx, (unsigned)pl.gy, (unsigned)G);
-        if (tf32 == 3) {
+        if (tf32 == 6) {
+            const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK, ntu2 = (ntu + 1) / 2;
+            // P: 128-row tiles, 2 ntu2 of them per sample (an odd count is padded with the zero tile of the memset);
+            // Q: 64-column tiles, 2 ntv per sample (each CTA of a pair stages one half of a 128-column tile)
+            prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)G, 8), 256, 0, st>>>(
+                cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, 2 * ntu2, nst, tmax, Hhi, 0, 128);
+            TES_LAUNCH_OK();
+            prod_build_tc_kernel<<<dim3((unsigned)(2 * ntv), (unsigned)G, 8), 256, 0, st>>>(
+                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, 2 * ntv, nst, tmax, Ghi, 0, 64);
+            TES_LAUNCH_OK();
+            const int64_t ntot = ntu2 * ntv * G;
+            int64_t ncta = 2 * ntot < tc_sm_count() ? 2 * ntot : (tc_sm_count() / 2) * 2;
+            prod_gemm_topk_tc2_kernel<<<(unsigned)ncta, TC_THREADS, T2_NS * T2_STAGE_BYTES + 256, st>>>(
+                Hhi, Ghi, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
+            TES_LAUNCH_OK();
+        } else if (tf32 >= 4) {
+            const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK;
+            if (gen_gc < 8) {   // the streamed half of the P blocks
+                prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)G, 8), 256, 0, st>>>(
+                    cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, ntu, nst, tmax, Hhi, gen_gc, 128);
+                TES_LAUNCH_OK();
+            }
+            prod_build_tc_kernel<<<dim3((unsigned)ntv, (unsigned)G, 8), 256, 0, st>>>(
+                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, ntv, nst, tmax, Ghi, 0, 128);
+            TES_LAUNCH_OK();
+            int rc = -18;
+#define PG_CASE(NC)                                                                                                  \
+    case NC:                                                                                                          \
+        rc = gen_gc == 8                                                                                              \
+                 ? launch_prod_gemm_gen<NC, 8>(tc_sm_count(), cand, nu, nv, (int)d, (int)s_lo, featP, pl.K2p / 2, Hhi, Ghi, \
+                                               (int)ntu, (int)ntv, (int)nst, scale, tmax, j0, idx_offset, pl.kp, (int)G,  \
+                                               pv, pi, st)                                                            \
+                 : launch_prod_gemm_gen<NC, 4>(tc_sm_count(), cand, nu, nv, (int)d, (int)s_lo, featP, pl.K2p / 2, Hhi, Ghi, \
+                                               (int)ntu, (int)ntv, (int)nst, scale, tmax, j0, idx_offset, pl.kp, (int)G,  \
+                                               pv, pi, st);                                                           \
+        break;
+            switch (gen_ncol) { PG_CASE(1) PG_CASE(2) PG_CASE(3) PG_CASE(4) PG_CASE(5) PG_CASE(6) }
+#undef PG_CASE
+            if (rc) return rc;
+        } else if (tf32 == 3) {
             const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK;
             prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)G, 8), 256, 0, st>>>(
-                cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, ntu, nst, tmax, Hhi);
+                cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, ntu, nst, tmax, Hhi, 0, 128);
             TES_LAUNCH_OK();
             prod_build_tc_kernel<<<dim3((unsigned)ntv, (unsigned)G, 8), 256, 0, st>>>(
-                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, ntv, nst, tmax, Ghi);
+                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, ntv, nst, tmax, Ghi, 0, 128);
             TES_LAUNCH_OK();
             const int64_t ntot = ntu * ntv * G;
             dim3 gtc((unsigned)(ntot < tc_sm_count() ? ntot : tc_sm_count()), 1, 1);

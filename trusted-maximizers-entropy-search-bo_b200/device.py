@@ -35,7 +35,9 @@ def stream_ptr():
 
 
 class Workspace:
-    """Grow-only per-device scratch buffer handed to the C ABI (no hidden allocation in the library)."""
+    """Grow-only scratch buffer handed to the C ABI (no hidden allocation in the library), one per (device, CUDA
+    stream): ops issued on different streams (or from different host threads on their own streams) never share
+    scratch; ops on one stream are ordered by the stream."""
 
     def __init__(self):
         self._buf = {}
@@ -43,7 +45,7 @@ class Workspace:
     def get(self, nbytes, device=None):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        key = (device.type, device.index)
+        key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
         b = self._buf.get(key)
         if b is None or b.numel() < nbytes:
             b = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

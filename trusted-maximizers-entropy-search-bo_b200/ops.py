@@ -73,7 +73,8 @@ def detect_product_structure(cand):
 def rff_topk_product(cand, W, b, theta, sigma, s_lo, s_hi, nv, k=1, idx_offset=0, tf32=None):
     """tes_rff_topk_product_f64 -> (idx (S,k), val (S,k), flag (S,) int32).  flag[j] = 1: recompute sample j with the
     general kernel (rff_topk does that).  tf32: 2 = 3xFP16 tensor-core screen (default), 1 = 3xTF32, 0 / False = fp64
-    (DMMA), 3 = 3xFP16 on tcgen05/TMEM; identical results in every mode.  None: PRODUCT_MODE (env TES_PRODUCT_MODE)."""
+    (DMMA), 3 = 3xFP16 on tcgen05/TMEM with both operands streamed, 4 = the same with the P operand generated on the SM
+    (no operand round trip through HBM for the U side); identical results in every mode.  None: PRODUCT_MODE (env TES_PRODUCT_MODE)."""
     if tf32 is None:
         tf32 = PRODUCT_MODE
     cand, W, b, theta, N, d, S, F, ws_ = _rff_args(cand, W, b, theta)
@@ -268,6 +269,31 @@ def batched_chol2inv(A, return_info=False):
     return (out, info) if return_info else out
 
 
+def chol2inv_checked(A, what):
+    """batched_chol2inv that raises where the reference's tf.cholesky would (InvalidArgumentError: 'Cholesky
+    decomposition was not successful'): utils.chol2inv / multichol2inv / precomputeInvKs / eval_invKmaxsams."""
+    out, info = batched_chol2inv(A, return_info=True)
+    nbad = int((info != 0).sum())
+    if nbad:
+        raise _lib.TesError("%s: %d of %d matrices have no Cholesky factor (not positive definite)"
+                            % (what, nbad, info.numel()))
+    return out
+
+
+def gj_inverse(A):
+    """General inverse (Gauss-Jordan, partial pivoting) of (batch, n, n) or (n, n): tf.linalg.inv / np.linalg.inv."""
+    A = dev(A)
+    single = A.dim() == 2
+    A3 = A.reshape(-1, A.shape[-2], A.shape[-1]).contiguous()
+    batch, n, n2 = A3.shape
+    if n != n2:
+        raise ValueError("matrices must be square")
+    out = torch.empty_like(A3)
+    rc = _lib.lib().tes_batched_gj_inverse_f64(ptr(A3), batch, n, ptr(out), stream_ptr())
+    _lib.check(rc, "tes_batched_gj_inverse_f64")
+    return out[0] if single else out.reshape(A.shape)
+
+
 def batched_potrf(A, return_info=False):
     A = dev(A)
     single = A.dim() == 2
@@ -391,7 +417,7 @@ def ep_acq_screen(x, test_xs, X, Y, l, sigma, sigma0, invpNK, invKobs, p, post_c
 
 
 def sp_acq(x, test_xs, X, Y, l, sigma, sigma0, invpNK, p, post_samples, post_mask, niter=10, nysample=10, z=None,
-           seed=0, n_global=None, x_offset=0):
+           seed=0, n_global=None, x_offset=0, check_info=True):
     """TES_sp acquisition; x (nx,d) or (nx,q,d).  evaluate_sample_mp.py / evaluate_batch_sample_mp.py."""
     x = dev(x)
     dv = x.device
@@ -426,6 +452,11 @@ def sp_acq(x, test_xs, X, Y, l, sigma, sigma0, invpNK, p, post_samples, post_mas
                           int(seed), int(nx if n_global is None else n_global), int(x_offset), ptr(acq), ptr(ws),
                           ws.numel(), stream_ptr())
     _lib.check(rc, "tes_sp_acq_f64")
+    if check_info:
+        nbad = int(ws[need - 256:need - 252].view(torch.int32)[0])
+        if nbad:
+            raise _lib.TesError("tes_sp_acq_f64: the predictive covariance of %d of %d queries has no Cholesky factor "
+                                "(tf.cholesky raises in the reference, evaluate_batch_sample_mp.py:306-310)" % (nbad, nx))
     return acq
 
 

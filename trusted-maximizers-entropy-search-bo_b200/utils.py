@@ -51,20 +51,20 @@ def computeNKmm(X, l, sigma, sigma0, dtype=None):
 
 
 def chol2inv(mat, dtype=None):
-    """utils.py:657-674."""
-    return _ret(ops.batched_chol2inv(mat), mat)
+    """utils.py:657-674.  Raises TesError where tf.linalg.cholesky would fail."""
+    return _ret(ops.chol2inv_checked(mat, "chol2inv"), mat)
 
 
 def multichol2inv(mat, n_mat=None, dtype=None):
-    """utils.py:677-700."""
-    return _ret(ops.batched_chol2inv(mat), mat)
+    """utils.py:677-700.  Raises TesError where tf.linalg.cholesky would fail."""
+    return _ret(ops.chol2inv_checked(mat, "multichol2inv"), mat)
 
 
 def precomputeInvKs(xdim, nhyp, ls, sigmas, sigma0s, Xsamples, dtype=None):
     """utils.py:1838-1856 -> (nhyp, nobs, nobs)."""
     ls_, sg, s0 = np.asarray(_np(ls)).reshape(nhyp, xdim), _np(sigmas).reshape(-1), _np(sigma0s).reshape(-1)
     mats = torch.stack([dev(computeNKmm(dev(Xsamples), ls_[i], sg[i], s0[i])) for i in range(nhyp)])
-    return _ret(ops.batched_chol2inv(mats), Xsamples)
+    return _ret(ops.chol2inv_checked(mats, "precomputeInvKs"), Xsamples)
 
 
 def eval_invKmaxsams(xdim, nhyp, nmax, ls, sigmas, sigma0s, Xsamples, maxima, dtype=None):
@@ -76,7 +76,7 @@ def eval_invKmaxsams(xdim, nhyp, nmax, ls, sigmas, sigma0s, Xsamples, maxima, dt
     for i in range(nhyp):
         stack = torch.stack([dev(computeNKmm(torch.cat([mx[i, j:j + 1], Xs], 0), ls_[i], sg[i], s0[i]))
                              for j in range(nmax)])
-        out.append(ops.batched_chol2inv(stack))
+        out.append(ops.chol2inv_checked(stack, "eval_invKmaxsams"))
     return _ret(torch.stack(out), Xsamples)
 
 
@@ -84,7 +84,7 @@ def compute_mean_var_f(x, Xsamples, Ysamples, l, sigma, sigma0, NKInv=None, full
     """utils.py:786-815."""
     xt, Xs = dev(x), dev(Xsamples)
     if NKInv is None:
-        NKInv = ops.batched_chol2inv(dev(computeNKmm(Xs, l, sigma, sigma0)))
+        NKInv = ops.chol2inv_checked(dev(computeNKmm(Xs, l, sigma, sigma0)), "compute_mean_var_f")
     NKInv = dev(NKInv)
     if not fullcov:
         mean, var = ops.gp_mean_var(xt, Xs, Ysamples, l, float(sigma), NKInv)
