@@ -798,6 +798,10 @@ static int tc_sm_count() {
     return sms;
 }
 
+// HALF = 0: a stage is a whole 64-k operand block pair (64 KB), NS stages.  HALF = 1: a stage is HALF a block pair (32 k,
+// 32 KB: [A hi | A lo | B hi | B lo], 8 KB each), so that 7 stages = 224 KB fill the shared memory instead of
+// 3 x 64 = 192 KB -- the kernel is bound by the latency of the operand pipeline, i.e. by the bytes in flight.
+template <int HALF, int NS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     prod_gemm_topk_tc_kernel(const __half* __restrict__ Pt, const __half* __restrict__ Qt, int64_t nu, int64_t nv,
                              int64_t ntu, int64_t ntv, int64_t nst, double scale0, const double* __restrict__ tmax,
@@ -807,11 +811,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // store_out != nullptr: instead of the top-k epilogue, write rowscale[row] * colscale[col] * sum to
     // store_out[row * ldo + col] (the quadratic-form screen of the TES_ep criterion)
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    unsigned char* stages = tc_smem_raw;                                            // [TC_NS][A block | B block]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem_raw + TC_NS * TC_STAGE_BYTES);
-    uint64_t* full_b = bars;                 // [TC_NS] producer -> MMA
-    uint64_t* empty_b = bars + TC_NS;        // [TC_NS] MMA (commit) -> producer
-    uint64_t* acc_full = bars + 2 * TC_NS;   // [2] MMA (commit) -> epilogue
+    constexpr uint32_t STAGE = HALF ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES;          // bytes per stage
+    constexpr uint32_t PART = HALF ? TC_BLOCK_BYTES / 4 : TC_BLOCK_BYTES / 2;       // bytes of the hi (= of the lo) part
+    constexpr int SUB = HALF ? 2 : 1;                                                // stages per 64-k block pair
+    unsigned char* stages = tc_smem_raw;                                            // [NS][A hi | A lo | B hi | B lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem_raw + NS * STAGE);
+    uint64_t* full_b = bars;                 // [NS] producer -> MMA
+    uint64_t* empty_b = bars + NS;           // [NS] MMA (commit) -> producer
+    uint64_t* acc_full = bars + 2 * NS;      // [2] MMA (commit) -> epilogue
     uint64_t* acc_empty = acc_full + 2;      // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -821,7 +828,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int64_t ntile = (int64_t)blockIdx.x < ntot ? (ntot - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t nseg = nst / TC_SEG;
     if (tid == 0) {
-        for (int s = 0; s < TC_NS; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&full_b[s], 1);
             mbar_init(&empty_b[s], 1);
         }
@@ -849,20 +856,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int64_t rt = t % ntu, ct = (t / ntu) % ntv, g = t / (ntu * ntv);
             const unsigned char* srcA = reinterpret_cast<const unsigned char*>(Pt) + ((g * ntu + rt) * nst) * (int64_t)TC_BLOCK_BYTES;
             const unsigned char* srcB = reinterpret_cast<const unsigned char*>(Qt) + ((g * ntv + ct) * nst) * (int64_t)TC_BLOCK_BYTES;
-            for (int64_t st = 0; st < nst; ++st, ++gst) {
-                const uint32_t s = (uint32_t)(gst % TC_NS), ph = (uint32_t)((gst / TC_NS) & 1);
-                mbar_wait_relaxed(&empty_b[s], ph ^ 1u, 32);
-                mbar_expect_tx(&full_b[s], TC_STAGE_BYTES);
-                // TC_COPY_SPLIT bulk copies per operand block (developer knob, compile time): more descriptors in flight
-#pragma unroll
-                for (int c = 0; c < TC_COPY_SPLIT; ++c) {
-                    constexpr uint32_t PIECE = TC_BLOCK_BYTES / TC_COPY_SPLIT;
-                    bulk_g2s(stages + s * TC_STAGE_BYTES + c * PIECE, srcA + st * (int64_t)TC_BLOCK_BYTES + c * PIECE, PIECE,
-                             &full_b[s]);
-                    bulk_g2s(stages + s * TC_STAGE_BYTES + TC_BLOCK_BYTES + c * PIECE,
-                             srcB + st * (int64_t)TC_BLOCK_BYTES + c * PIECE, PIECE, &full_b[s]);
+            for (int64_t st = 0; st < nst; ++st)
+                for (int h = 0; h < SUB; ++h, ++gst) {
+                    const uint32_t s = (uint32_t)(gst % NS), ph = (uint32_t)((gst / NS) & 1);
+                    mbar_wait_relaxed(&empty_b[s], ph ^ 1u, 32);
+                    mbar_expect_tx(&full_b[s], STAGE);
+                    unsigned char* dst = stages + s * STAGE;
+                    const unsigned char* a = srcA + st * (int64_t)TC_BLOCK_BYTES + h * PART;
+                    const unsigned char* b = srcB + st * (int64_t)TC_BLOCK_BYTES + h * PART;
+                    if (HALF) {     // the hi and the lo half of a 32-k slice are 16 KB apart in the 64-k block
+                        bulk_g2s(dst, a, PART, &full_b[s]);
+                        bulk_g2s(dst + PART, a + TC_BLOCK_BYTES / 2, PART, &full_b[s]);
+                        bulk_g2s(dst + 2 * PART, b, PART, &full_b[s]);
+                        bulk_g2s(dst + 3 * PART, b + TC_BLOCK_BYTES / 2, PART, &full_b[s]);
+                    } else {
+                        bulk_g2s(dst, a, TC_BLOCK_BYTES, &full_b[s]);
+                        bulk_g2s(dst + TC_BLOCK_BYTES, b, TC_BLOCK_BYTES, &full_b[s]);
+                    }
                 }
-            }
             }
         }
         __syncwarp();
@@ -875,18 +886,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const uint32_t a = (uint32_t)(seg & 1), pa = (uint32_t)((seg >> 1) & 1);
                 mbar_wait_relaxed(&acc_empty[a], pa ^ 1u, 32);
                 tc_fence_after();
-                for (int q4 = 0; q4 < TC_SEG; ++q4, ++gst) {
-                    const uint32_t s = (uint32_t)(gst % TC_NS), ph = (uint32_t)((gst / TC_NS) & 1);
+                for (int q4 = 0; q4 < TC_SEG * SUB; ++q4, ++gst) {
+                    const uint32_t s = (uint32_t)(gst % NS), ph = (uint32_t)((gst / NS) & 1);
                     mbar_wait_relaxed(&full_b[s], ph, 32);
                     tc_fence_after();
-                    const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_BLOCK_BYTES;
+                    const uint32_t sa = base + s * STAGE, sb = sa + 2 * PART;
 #pragma unroll
-                    for (int ks = 0; ks < TC_BK / 16; ++ks) {
+                    for (int ks = 0; ks < TC_BK / 16 / SUB; ++ks) {
                         const uint32_t off = (uint32_t)(2 * ks) * 128u * 16u;      // 2 chunks of 8 halves per k16 step
                         const uint64_t a_hi = tc_desc(sa + off, 128 * 16, 128);
-                        const uint64_t a_lo = tc_desc(sa + TC_BLOCK_BYTES / 2 + off, 128 * 16, 128);
+                        const uint64_t a_lo = tc_desc(sa + PART + off, 128 * 16, 128);
                         const uint64_t b_hi = tc_desc(sb + off, 128 * 16, 128);
-                        const uint64_t b_lo = tc_desc(sb + TC_BLOCK_BYTES / 2 + off, 128 * 16, 128);
+                        const uint64_t b_lo = tc_desc(sb + PART + off, 128 * 16, 128);
                         const uint32_t first = (q4 == 0 && ks == 0) ? 0u : 1u;
                         tc_mma_f16(tmem + a * 128u, a_lo, b_hi, idesc, first);
                         tc_mma_f16(tmem + a * 128u, a_hi, b_lo, idesc, 1u);
@@ -2012,10 +2023,10 @@ int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, int6
     }
     quad_scales_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(rowmax, nc, rowscale, nullptr, 0, nullptr);
     TES_LAUNCH_OK();
-    TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc_kernel<0, TC_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(TC_NS * TC_STAGE_BYTES + 256)));
     dim3 grid((unsigned)(ntu < tc_sm_count() ? ntu : tc_sm_count()), 1, 1);
-    prod_gemm_topk_tc_kernel<<<grid, TC_THREADS, TC_NS * TC_STAGE_BYTES + 256, st>>>(
+    prod_gemm_topk_tc_kernel<0, TC_NS><<<grid, TC_THREADS, TC_NS * TC_STAGE_BYTES + 256, st>>>(
         (const __half*)Atc, (const __half*)Btc, nc, Sp, ntu, 1, nst, 1.0, nullptr, 0, 0, 1, nullptr, nullptr, Qout, Sp,
         rowscale, colscale);
     TES_LAUNCH_OK();
@@ -2495,8 +2506,12 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
                                          (int)sizeof(PtSmem)));
         TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(PhSmem)));
-        TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc_kernel<0, TC_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(TC_NS * TC_STAGE_BYTES + 256)));
+        TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(2 * TC_STAGE_BYTES + 256)));
+        TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc_kernel<1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(7 * TC_STAGE_BYTES / 2 + 256)));
         TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(T2_NS * T2_STAGE_BYTES + 256)));
         // zero the tile padding once (rows >= nu, columns >= nv, k >= 2F are never written by the build kernels)
@@ -2563,8 +2578,21 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
             TES_LAUNCH_OK();
             const int64_t ntot = ntu * ntv * G;
             dim3 gtc((unsigned)(ntot < tc_sm_count() ? ntot : tc_sm_count()), 1, 1);
-            prod_gemm_topk_tc_kernel<<<gtc, TC_THREADS, TC_NS * TC_STAGE_BYTES + 256, st>>>(
-                Hhi, Ghi, nu, nv, ntu, ntv, nst, scale, tmax + j0, idx_offset, pl.kp, G, pv, pi, nullptr, 0, nullptr, nullptr);
+            // stage shape (developer knob TES_TC_STAGES, read once): 3 whole stages of 64 KB (default: 22.5 ms at C3) /
+            // 7 half stages of 32 KB (224 KB in flight instead of 192 KB, but 24.9 ms) / 2 whole stages
+            static const int tc_shape = [] {
+                const char* e = getenv("TES_TC_STAGES");
+                return e ? atoi(e) : 3;
+            }();
+            if (tc_shape == 2)
+                prod_gemm_topk_tc_kernel<0, 2><<<gtc, TC_THREADS, 2 * TC_STAGE_BYTES + 256, st>>>(
+                    Hhi, Ghi, nu, nv, ntu, ntv, nst, scale, tmax + j0, idx_offset, pl.kp, G, pv, pi, nullptr, 0, nullptr, nullptr);
+            else if (tc_shape == 3)
+                prod_gemm_topk_tc_kernel<0, TC_NS><<<gtc, TC_THREADS, TC_NS * TC_STAGE_BYTES + 256, st>>>(
+                    Hhi, Ghi, nu, nv, ntu, ntv, nst, scale, tmax + j0, idx_offset, pl.kp, G, pv, pi, nullptr, 0, nullptr, nullptr);
+            else
+                prod_gemm_topk_tc_kernel<1, 7><<<gtc, TC_THREADS, 7 * TC_STAGE_BYTES / 2 + 256, st>>>(
+                    Hhi, Ghi, nu, nv, ntu, ntv, nst, scale, tmax + j0, idx_offset, pl.kp, G, pv, pi, nullptr, 0, nullptr, nullptr);
             TES_LAUNCH_OK();
         } else if (tf32 == 2) {
             const int64_t totp = G * ((nu + PB_ROWS - 1) / PB_ROWS) * F, totq = G * ((nv + PB_ROWS - 1) / PB_ROWS) * F;
