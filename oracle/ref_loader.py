@@ -33,14 +33,31 @@ def reference_available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "utils.py"))
 
 
+GRAPH_MODE = False
+
+
+def use_graph_shim():
+    """Call BEFORE the first load(): `tensorflow` then resolves to oracle/tf_shim/graph.py (lazy graph on torch with
+    variables, assign, AdamOptimizer and Session) -- what utils_for_continuous.sample_xmaxs_fmaxs needs."""
+    global GRAPH_MODE
+    if _cache:
+        raise RuntimeError("use_graph_shim() must be called before any reference module is loaded")
+    GRAPH_MODE = True
+
+
 def _install_stubs():
     if not hasattr(np, "infty"):
         np.infty = np.inf  # utils.py:1669, empirical_approximation.py:66
     # tensorflow / tensorflow_probability: the eager numpy shim (oracle/tf_shim), so that the
-    # reference's criteria/*.py and the TF halves of utils.py run unmodified
-    from oracle import tf_shim
-    if not tf_shim.installed():
-        tf_shim.install()
+    # reference's criteria/*.py and the TF halves of utils.py run unmodified; or the lazy graph shim
+    if GRAPH_MODE:
+        from oracle.tf_shim import graph
+        if sys.modules.get("tensorflow") is not graph:
+            graph.install()
+    else:
+        from oracle import tf_shim
+        if not tf_shim.installed():
+            tf_shim.install()
     for name in (
         "matplotlib",
         "matplotlib.pyplot",

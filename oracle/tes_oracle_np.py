@@ -19,11 +19,17 @@ Pinning:
     get_testidxs_stats, get_empirical_stat_from_samples and approximate_EP are pinned against
     the outputs of the reference's own numpy functions, run in the build container through
     oracle/ref_loader.py by tests/golden/make_golden.py (fixtures in tests/golden/*.npz).
-  * The five TF criteria (evaluate_mp, evaluate_mp_lite, evaluate_sample_mp,
-    evaluate_batch_sample_mp, evaluate_batch_mp) cannot run here (TensorFlow 1.14 absent, no
-    network) and the reference ships no test for them: PARITY UNPINNED for those -- this
-    restatement is the sole authority, cross-checked by analytic identities in
-    tests/test_oracle_identities.py.
+  * The five TF criteria (evaluate_mp, evaluate_mp_lite, evaluate_sample_mp, evaluate_batch_sample_mp,
+    evaluate_batch_mp), get_pNK_test_obs and the TF halves of utils.py (precomputeInvKs, compute_mean_var_f) are
+    pinned on outputs of the reference's OWN files, run unmodified on a numpy-backed TF-1.14/TFP-0.7 shim
+    (oracle/tf_shim; tests/golden/make_golden_criteria.py -> tests/golden/criteria.npz, C1 / C2 / d=6 / nhyp=2 shapes
+    with the draws its TFP sample() calls consumed): tests/test_oracle_criteria_golden.py.  Running them that way
+    exposed quirk Q12 (the float32-rounded constant of utils.evaluate_norm_entropy).
+  * adam_refine_maximizers is pinned on utils_for_continuous.sample_xmaxs_fmaxs run unmodified on a lazy-graph shim
+    (oracle/tf_shim/graph.py: tf.Variable / assign / tf.train.AdamOptimizer per TF 1.14 with autograd gradients
+    through the reference's graph; tests/golden/make_golden_adam.py -> tests/golden/adam.npz).
+  What the shims restate is TensorFlow's published op semantics (third-party, tensorflow-gpu 1.14.0 /
+  tensorflow-probability 0.7.0 per requirements.txt:5-6, not vendored), not the reference's algorithm.
 
 TFP-0.7 semantics used (not vendored in /root/reference; requirements.txt:5-6):
   Normal.sample(n)        = loc + scale * z,  z ~ N(0,1) of shape (n,) + batch_shape
@@ -237,7 +243,7 @@ def adam_refine_maximizers(x0, theta, W, b, sigma, xmin, xmax, ntrain, lr=1e-3, 
     W (S,F,d) or (1,F,d); b (S,F,1) or (1,F,1).  Returns (xs (S,k,d), fvals (S,k)).
     TF-1 Adam (tensorflow/python/training/adam.py): lr_t = lr sqrt(1-beta2^t)/(1-beta1^t);
     m <- beta1 m + (1-beta1) g; v <- beta2 v + (1-beta2) g^2; var <- var - lr_t m / (sqrt(v) + epsilon).
-    parity unpinned (TF graph code; no reference output available) -- this restatement is the authority."""
+    Pinned on the reference's own graph code run on oracle/tf_shim/graph.py (tests/golden/adam.npz)."""
     S, k, d = x0.shape
     F = theta.shape[1]
     scale = np.sqrt(2.0 * sigma / F)

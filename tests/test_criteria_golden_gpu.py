@@ -135,3 +135,21 @@ def test_tes_ep_batch_against_reference(case, tag):
     ref = c["bep_acq_nan"]
     assert np.array_equal(np.isnan(a), np.isnan(ref))
     np.testing.assert_allclose(a[~np.isnan(ref)], ref[~np.isnan(ref)], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["branin", "d6", "h2clip"])
+def test_adam_refinement_against_reference(golden, tag):
+    """tes_rff_adam_refine_f64 through utils_for_continuous.sample_xmaxs_fmaxs vs the reference's own graph code run on
+    the lazy-graph shim (tests/golden/adam.npz)."""
+    from tes_b200 import utils_for_continuous as ufc
+    g = golden("adam")
+    G = lambda n: g["%s_%s" % (tag, n)]  # noqa: E731
+    theta, W, b, init, ls, sigmas = G("theta"), G("W"), G("b"), G("init"), G("ls"), G("sigmas")
+    nhyp, S, F, d = W.shape
+    k, ntrain = int(G("k")), int(G("ntrain"))
+    inits, max_xs, max_fs, _, xs = ufc.sample_xmaxs_fmaxs(d, nhyp, S, F, ls, sigmas, np.full(nhyp, 1e-4), theta, W, b, init,
+                                                         k, xmin=G("xmin"), xmax=G("xmax"), ntrain=ntrain, get_xs=True)
+    np.testing.assert_array_equal(inits, G("start"))
+    np.testing.assert_allclose(xs, G("xs"), rtol=0, atol=1e-10)
+    np.testing.assert_allclose(max_xs, G("max_xs"), rtol=0, atol=1e-10)
+    np.testing.assert_allclose(max_fs, G("max_fs"), rtol=1e-10, atol=1e-11)

@@ -158,3 +158,29 @@ def test_norm_entropy_constant_is_float32_rounded():
     """Q12: utils.py:653-654 -> tf.cast(0.5 * tf.log(2*np.pi), dtype) is a float32 computation."""
     assert onp.NORM_ENTROPY_CONST == float(np.float32(0.5) * np.log(np.float32(2 * np.pi)))
     assert abs(onp.NORM_ENTROPY_CONST - onp.HALF_LOG_2PI) > 4e-8
+
+
+# ---- Adam refinement of the trusted maximizers: reference graph code on the lazy-graph shim ---------------------
+ADAM_CASES = ["branin", "d6", "h2clip"]
+
+
+@pytest.mark.parametrize("tag", ADAM_CASES)
+def test_adam_refinement_matches_reference_graph(golden, tag):
+    """oracle adam_refine_maximizers (+ top-k start points) vs utils_for_continuous.sample_xmaxs_fmaxs run unmodified
+    (tests/golden/make_golden_adam.py: tf.train.AdamOptimizer restated per TF 1.14, gradients by autograd through the
+    reference's own graph)."""
+    g = golden("adam")
+    G = lambda n: g["%s_%s" % (tag, n)]  # noqa: E731
+    theta, W, b, init, ls, sigmas = G("theta"), G("W"), G("b"), G("init"), G("ls"), G("sigmas")
+    k, ntrain = int(G("k")), int(G("ntrain"))
+    for i in range(theta.shape[0]):
+        idx, _ = onp.rff_topk(init, theta[i], W[i], b[i], sigmas[i], k)
+        start = init[idx]                                                   # (S, k, d)
+        np.testing.assert_array_equal(start, G("start")[i])
+        xs, fv = onp.adam_refine_maximizers(start, theta[i], W[i], b[i], sigmas[i], G("xmin"), G("xmax"), ntrain)
+        np.testing.assert_allclose(xs, G("xs")[i], rtol=0, atol=1e-12)
+        best = np.argmax(fv, axis=1)
+        rows = np.arange(fv.shape[0])
+        np.testing.assert_allclose(xs[rows, best], G("max_xs")[i], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(fv[rows, best], G("max_fs")[i], rtol=1e-12, atol=1e-13)
+        assert np.all(xs >= G("xmin") - 1e-15) and np.all(xs <= G("xmax") + 1e-15)
