@@ -96,6 +96,11 @@ int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d, int64_t s
  * IEEE == comparisons (NaN never equal).  out_r: d int64, out_bad: 2 d int32, device memory. */
 int tes_product_runlen_f64(const double* cand, int64_t N, int64_t d, int64_t* out_r, void* stream);
 int tes_product_check_f64(const double* cand, int64_t N, int64_t d, int64_t nv, int* out_bad, void* stream);
+/* "Mesh + tail": the continuous drivers append top_init_k uniform candidates to the grid they score
+ * (utils_for_continuous.py:36-38).  out_first[k] = first row at which column k stops being "slow" for block length nv,
+ * out_first[d + k] = first row at which it stops being "fast" (N: never), so that the longest prefix that IS a product
+ * set can take the GEMM path and only the remaining rows the general kernel.  d <= 32; out_first: 2 d int64. */
+int tes_product_prefix_f64(const double* cand, int64_t N, int64_t d, int64_t nv, int64_t* out_first, void* stream);
 
 /* All function-sample values, out (S, N).  Replaces utils_for_continuous.get_function_samples
  * (utils_for_continuous.py:257-296) / optfunc.make_function_sample_np.  Debug / small-N use. */

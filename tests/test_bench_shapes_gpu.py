@@ -83,7 +83,11 @@ def test_c3_mesh_plus_extra_rows(c3):
     S = 64
     extra = torch.from_numpy(np.random.RandomState(3).rand(5, wl["d"])).cuda()
     cand = torch.cat([dv["cand"], extra], 0).contiguous()
+    pre = ops.detect_product_prefix(cand)
+    assert pre is not None and pre[3] == dv["cand"].shape[0]          # the mesh is found as the product prefix
+    n0 = ops.STATS.get("product_prefix", 0)
     i1, v1 = ops.rff_topk(cand, W[:S], b[:S], theta[:S], wl["hyp"]["sigma"], k=3)
+    assert ops.STATS.get("product_prefix", 0) == n0 + 1                # ... and the GEMM path ran on it
     i2, v2 = ops.rff_topk(cand, W[:S], b[:S], theta[:S], wl["hyp"]["sigma"], k=3, product=False, method=ops.RFF_FP64)
     assert torch.equal(i1, i2) and torch.equal(v1, v2)
     # ... and an extra row that wins must be found: plant the maximizer of sample 0 (perturbed) as an extra row

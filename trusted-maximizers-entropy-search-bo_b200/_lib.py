@@ -43,6 +43,7 @@ SIGNATURES = {
                                         c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_int]),
     "tes_product_runlen_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "tes_product_check_f64": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
+    "tes_product_prefix_f64": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
     "tes_rff_topk_product_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int]),
     "tes_rff_topk_product_f64": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int,
                                          c_dbl, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr]),

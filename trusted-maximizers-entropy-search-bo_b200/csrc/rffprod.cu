@@ -2676,7 +2676,38 @@ __global__ void __launch_bounds__(256)
         if (!(v == cand[(i % nv) * d + k]) && !bad[d + k]) bad[d + k] = 1;
     }
 }
+// first[k] = first row whose column k is not constant inside its block of nv rows ("slow" broken), first[d + k] = first
+// row that differs from row i % nv in column k ("fast" broken); N where the column never breaks
+__global__ void __launch_bounds__(256)
+    product_prefix_kernel(const double* __restrict__ cand, int64_t N, int d, int64_t nv, unsigned long long* __restrict__ first) {
+    const int64_t tot = N * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e % d);
+        const int64_t i = e / d;
+        const double v = cand[e];
+        if (!(v == cand[(i / nv) * nv * d + k]) && (unsigned long long)i < first[k]) atomicMin(&first[k], (unsigned long long)i);
+        if (!(v == cand[(i % nv) * d + k]) && (unsigned long long)i < first[d + k])
+            atomicMin(&first[d + k], (unsigned long long)i);
+    }
+}
 }  // namespace tes
+
+extern "C" int tes_product_prefix_f64(const double* cand, int64_t N, int64_t d, int64_t nv, int64_t* out_first,
+                                      void* stream) {
+    if (N < 1 || !cand) return -1;
+    if (d < 1 || d > 32) return -3;
+    if (nv < 1 || nv > N) return -4;
+    if (!out_first) return -5;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* r = reinterpret_cast<unsigned long long*>(out_first);
+    product_runlen_init_kernel<<<1, 64, 0, st>>>(N, (int)(2 * d), r);
+    TES_LAUNCH_OK();
+    const int64_t tot = N * d;
+    const int64_t want = (tot + 255) / 256, cap = (int64_t)tc_sm_count() * 8;
+    product_prefix_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(cand, N, (int)d, nv, r);
+    TES_LAUNCH_OK();
+    return 0;
+}
 
 extern "C" int tes_product_runlen_f64(const double* cand, int64_t N, int64_t d, int64_t* out_r, void* stream) {
     if (N < 1 || !cand) return -1;

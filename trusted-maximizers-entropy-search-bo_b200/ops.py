@@ -70,6 +70,45 @@ def detect_product_structure(cand):
     return None if best is None else best[:3]
 
 
+def detect_product_prefix(cand, max_tail=None):
+    """"Mesh + tail" (utils_for_continuous.py:36-38 appends top_init_k uniform rows to the grid): the longest prefix of
+    the candidate set that is a product U x V in row-major order -> (s_lo, s_hi, nv, n_prefix) or None.  The tail
+    (N - n_prefix rows) must not exceed `max_tail` (default max(4096, N / 16))."""
+    N, d = cand.shape
+    if d < 2 or N < 8 or d > 32:
+        return None
+    max_tail = max(4096, N // 16) if max_tail is None else max_tail
+    cand = cand.contiguous()
+    L = _lib.lib()
+    r_d = torch.empty((d,), dtype=torch.int64, device=cand.device)
+    _lib.check(L.tes_product_runlen_f64(ptr(cand), N, d, ptr(r_d), stream_ptr()), "tes_product_runlen_f64")
+    r = r_d.cpu().tolist()
+    first = {}
+
+    def firsts(nv):
+        if nv not in first:
+            out = torch.empty((2 * d,), dtype=torch.int64, device=cand.device)
+            _lib.check(L.tes_product_prefix_f64(ptr(cand), N, d, nv, ptr(out), stream_ptr()), "tes_product_prefix_f64")
+            first[nv] = out.cpu().tolist()
+        return first[nv]
+
+    best = None
+    for s_lo, s_hi in [(0, du) for du in range(1, d)] + [(du, d) for du in range(1, d)]:
+        nv = min(r[s_lo:s_hi])
+        if nv >= N or nv < 2:
+            continue
+        f = firsts(nv)
+        bad = min(min(f[s_lo:s_hi]), min(f[d + k] for k in range(d) if not (s_lo <= k < s_hi)))
+        n_pre = (min(bad, N) // nv) * nv
+        nu = n_pre // nv
+        if nu < 2 or N - n_pre > max_tail:
+            continue
+        key = (n_pre, -abs(nu - nv))
+        if best is None or key > best[0]:
+            best = (key, (s_lo, s_hi, nv, n_pre))
+    return None if best is None else best[1]
+
+
 def rff_topk_product(cand, W, b, theta, sigma, s_lo, s_hi, nv, k=1, idx_offset=0, tf32=None):
     """tes_rff_topk_product_f64 -> (idx (S,k), val (S,k), flag (S,) int32).  flag[j] = 1: recompute sample j with the
     general kernel (rff_topk does that).  tf32: 2 = 3xFP16 tensor-core screen (default), 1 = 3xTF32, 0 / False = fp64
@@ -114,6 +153,20 @@ def rff_topk(cand, W, b, theta, sigma, k=1, idx_offset=0, method=RFF_AUTO, produ
                                   idx_offset=idx_offset, product=False)
                 idx[bad], val[bad] = gi, gv
             return idx, val
+        if product is None and method == RFF_AUTO and N >= PRODUCT_MIN_N:
+            # mesh + a few extra rows: product path on the prefix, general kernel on the tail, merge the two lists
+            pre = detect_product_prefix(cand)
+            if pre is not None and pre[3] >= PRODUCT_MIN_N and pre[3] < N:
+                s_lo, s_hi, nv, n_pre = pre
+                STATS["product_prefix"] = STATS.get("product_prefix", 0) + 1
+                i1, v1 = rff_topk(cand[:n_pre], W, b, theta, sigma, k=k, idx_offset=idx_offset, product=(s_lo, s_hi, nv))
+                i2, v2 = rff_topk(cand[n_pre:], W, b, theta, sigma, k=min(k, N - n_pre), idx_offset=idx_offset + n_pre,
+                                  product=False)
+                if i2.shape[1] < k:    # fewer tail rows than k: pad the list with empty entries
+                    padi = torch.full((S, k - i2.shape[1]), -1, dtype=torch.int64, device=cand.device)
+                    padv = torch.full((S, k - v2.shape[1]), float("-inf"), dtype=torch.float64, device=cand.device)
+                    i2, v2 = torch.cat([i2, padi], 1), torch.cat([v2, padv], 1)
+                return topk_merge(torch.stack([v1, v2]), torch.stack([i1, i2]))
         if method == RFF_PRODUCT:
             raise ValueError("RFF_PRODUCT: the candidate set is not a product U x V in row-major order")
     if method == RFF_PRODUCT:
