@@ -7,6 +7,8 @@
 // max_niter.  Here: one CTA per maximizer (all T of them concurrently), the T x T system matrix lives in shared
 // memory and is inverted in place by Gauss-Jordan elimination with partial pivoting (the same pivoting rule as the
 // LU behind np.linalg.inv); Sigma^-1 is computed once by the same routine and shared through L2.
+#include <cstdlib>
+
 #include "tes_common.cuh"
 
 namespace tes {
@@ -292,6 +294,234 @@ __global__ void __launch_bounds__(EP_THREADS) ep_kernel(const double* __restrict
     if (tid == 0 && niter) niter[hy * T + j] = s_count;
 }
 
+// ---- T <= 32: one WARP per maximizer, the system matrix in registers ------------------------------------------------
+// The CTA-per-maximizer kernel above spends its time in block barriers: ~8 per Gauss-Jordan step, T steps per inverse,
+// one inverse per EP iteration (the reference recomputes the full T x T inverse after every single-site update,
+// ep.py:182-185) -- 79 us per iteration at T = 30, 7.9 ms for the 100 iterations of BASELINE config C2.  Here lane c
+// holds COLUMN c of the matrix (col[i], i = row; the step and row loops are fully unrolled, so every register index
+// is static): the pivot search runs inside lane k, rows are exchanged by predicated moves, the multipliers a[i][k]
+// come from lane k by shuffle -- no barrier at all, only warp-synchronous code.  Pivot rule, operation order and
+// rounding of every element are those of gj_inverse / ep_kernel, so the outputs are the same bits.
+constexpr int EPW = 32;
+constexpr int EPW_LD = EPW + 1;
+constexpr int EPW_DOUBLES = 2 * EPW * EPW_LD + 8 * EPW;      // per warp: M, a_cov, 8 vectors
+
+__device__ __forceinline__ void gj_inverse_warp(double (&col)[EPW], int n, int lane, double* __restrict__ Mw) {
+    int mypiv = lane;                 // lane k keeps the pivot row of step k
+    const double INF = pos_inf();
+    // the step loop is NOT unrolled (the body is ~500 instructions: 32 unrolled steps overflow the instruction cache
+    // and ran 15x slower); row k / row p of the lane's column are reached through predicated moves over the
+    // statically indexed registers
+#pragma unroll 1
+    for (int k = 0; k < n; ++k) {
+        // pivot search in column k, rows k..n-1: first maximum of |a_ik|, a NaN candidate counts as +inf
+        double bv = -1.0, rk = 0.0;
+        int bi = k;
+#pragma unroll
+        for (int i = 0; i < EPW; ++i) {
+            if (i == k) rk = col[i];
+            if (i >= k && i < n) {
+                const double v = fabs(col[i]);
+                const double key = v == v ? v : INF;
+                if (key > bv) {
+                    bv = key;
+                    bi = i;
+                }
+            }
+        }
+        const int p = __shfl_sync(0xffffffffu, bi, k);
+        if (lane == k) mypiv = p;
+        if (p != k) {                 // exchange rows k and p of this column
+            double rp = 0.0;
+#pragma unroll
+            for (int i = 0; i < EPW; ++i)
+                if (i == p) {
+                    rp = col[i];
+                    col[i] = rk;
+                }
+            rk = rp;
+        }
+        const double pv = __shfl_sync(0xffffffffu, rk, k);      // a[k][k] lives in lane k
+        const double ipv = 1.0 / pv;
+        const double rkn = (lane == k ? 1.0 : rk) * ipv;        // the normalised row k
+#pragma unroll
+        for (int i = 0; i < EPW; ++i) {
+            const double f = __shfl_sync(0xffffffffu, col[i], k);              // a[i][k] before this step
+            if (i == k) col[i] = rkn;
+            else if (i < n) col[i] = lane == k ? -f * rkn : fma(-f, rkn, col[i]);
+        }
+    }
+    // undo the row interchanges as column interchanges, in reverse order: track where this lane's column ends up
+    int pos = lane;
+    for (int k = n - 1; k >= 0; --k) {
+        const int p = __shfl_sync(0xffffffffu, mypiv, k);
+        if (p != k) pos = pos == k ? p : (pos == p ? k : pos);
+    }
+    if (lane < n) {
+#pragma unroll
+        for (int i = 0; i < EPW; ++i)
+            if (i < n) Mw[i * EPW_LD + pos] = col[i];
+    }
+    __syncwarp();
+}
+
+// M = inv_cov + C diag(1/site_var) C^T (column `lane` built in registers), rhs = h + C (site_mean / site_var);
+// Mw = M^-1, out_mean = Mw rhs -- ep_refresh for one warp
+__device__ __forceinline__ void ep_refresh_warp(double* __restrict__ Mw, int T, int j, const double* __restrict__ inv_cov,
+                                                const double* __restrict__ h, const double* site_m, const double* site_v,
+                                                double* rhs, double* wwv, double* out_mean, int lane) {
+    if (lane < T - 1) {
+        const double w = 1.0 / sqrt(site_v[lane]);     // the reference forms cs / sqrt(site_vars): negative -> NaN
+        wwv[lane] = w * w;
+    }
+    if (lane < T) rhs[lane] = h[lane];
+    __syncwarp();
+    double sw = 0.0, sr = 0.0;
+    if (lane == 0)
+        for (int c = 0; c < T - 1; ++c) {
+            const double w = 1.0 / sqrt(site_v[c]);
+            sw += w * w;
+            sr += site_m[c] / site_v[c];
+        }
+    sw = __shfl_sync(0xffffffffu, sw, 0);
+    sr = __shfl_sync(0xffffffffu, sr, 0);
+    if (lane < T - 1) rhs[ep_other(lane, j)] -= site_m[lane] / site_v[lane];
+    __syncwarp();
+    if (lane == 0) rhs[j] += sr;
+    double col[EPW];
+#pragma unroll
+    for (int i = 0; i < EPW; ++i) col[i] = (i < T && lane < T) ? inv_cov[i * T + lane] : 0.0;
+    if (lane < T) {
+        if (lane == j) {
+#pragma unroll
+            for (int i = 0; i < EPW; ++i)
+                if (i < T) {
+                    if (i == j) col[i] += sw;
+                    else col[i] -= wwv[i < j ? i : i - 1];
+                }
+        } else {
+            const double ww = wwv[lane < j ? lane : lane - 1];
+#pragma unroll
+            for (int i = 0; i < EPW; ++i) {
+                if (i == lane) col[i] += ww;
+                if (i == j) col[i] -= ww;
+            }
+        }
+    }
+    __syncwarp();
+    gj_inverse_warp(col, T, lane, Mw);
+    if (lane < T) {
+        double s = 0.0;
+        for (int k = 0; k < T; ++k) s = fma(Mw[lane * EPW_LD + k], rhs[k], s);
+        out_mean[lane] = s;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(128) ep_warp_kernel(const double* __restrict__ mean_all,
+                                                      const double* __restrict__ cov_all,
+                                                      const double* __restrict__ inv_cov_all,
+                                                      const double* __restrict__ h_all, int T, int64_t nhyp,
+                                                      double resolution, int max_niter, double* __restrict__ post_mean,
+                                                      double* __restrict__ post_cov, int* __restrict__ niter) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t gid = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid;
+    if (gid >= (int64_t)T * nhyp) return;          // whole warps leave: no block-wide barrier below
+    const int j = (int)(gid % T);
+    const int64_t hy = gid / T;
+    const double* mu = mean_all + hy * T;
+    const double* Sg = cov_all + hy * T * T;
+    const double* inv_cov = inv_cov_all + hy * T * T;
+    const double* h = h_all + hy * T;
+    double* Mw = sm + (size_t)wid * EPW_DOUBLES;
+    double* Cw = Mw + EPW * EPW_LD;                // current approximation (a_cov)
+    double* vec = Cw + EPW * EPW_LD;
+    double *a_mean = vec, *n_mean = vec + EPW, *rhs = vec + 2 * EPW, *site_m = vec + 3 * EPW, *site_v = vec + 4 * EPW,
+           *new_m = vec + 5 * EPW, *new_v = vec + 6 * EPW, *wwv = vec + 7 * EPW;
+
+    if (lane < T - 1) {      // site initialisation (ep.py:107-108)
+        const int o = ep_other(lane, j);
+        site_m[lane] = mu[j] - mu[o];
+        site_v[lane] = (Sg[(int64_t)j * T + j] - Sg[(int64_t)o * T + j]) - (Sg[(int64_t)j * T + o] - Sg[(int64_t)o * T + o]);
+    }
+    __syncwarp();
+    ep_refresh_warp(Mw, T, j, inv_cov, h, site_m, site_v, rhs, wwv, a_mean, lane);
+    for (int e = lane; e < T * T; e += 32) Cw[(e / T) * EPW_LD + e % T] = Mw[(e / T) * EPW_LD + e % T];
+    __syncwarp();
+    int count = 0, stop = 0;
+    double diff = 1e10;
+    while (diff > resolution && count < max_niter) {
+        if (lane < T - 1) {      // cavity (ep.py:31-49), truncated-normal moments (:52-60), site proposal (:63-70)
+            const int c = lane, o = ep_other(c, j);
+            const double ctSc = (Cw[j * EPW_LD + j] - Cw[o * EPW_LD + j]) - (Cw[j * EPW_LD + o] - Cw[o * EPW_LD + o]);
+            const double ctm = a_mean[j] - a_mean[o];
+            const double cav_v = 1.0 / (1.0 / ctSc - 1.0 / site_v[c]);
+            const double cav_m = cav_v * (ctm / ctSc - site_m[c] / site_v[c]);
+            const double sd = sqrt(cav_v);
+            const double beta = cav_m / sd;
+            const double poc = norm_pdf(beta) / norm_cdf(beta);
+            const double cf_m = cav_m + sd * poc;
+            const double cf_v = -cav_m * sd * poc - cf_m * cf_m + 2.0 * cav_m * cf_m - cav_m * cav_m + cav_v;
+            const double nv = 1.0 / (1.0 / cf_v - 1.0 / cav_v);
+            new_v[c] = nv;
+            new_m[c] = nv * (cf_m / cf_v - cav_m / cav_v);
+        }
+        __syncwarp();
+        if (lane == 0) {         // ep.py:162-172 (see ep_kernel for the termination guard)
+            int cnt = count + 1;
+            int uidx = cnt % (T - 1);
+            const int last = cnt >= 1 ? cnt - 1 : T - 2;
+            int guard = 0;
+            auto bad = [&](int u) {
+                const double v = new_v[u];
+                return v <= 0.0 || v != v || isinf(v);
+            };
+            while (bad(uidx) && uidx != last) {
+                ++cnt;
+                uidx = cnt % (T - 1);
+                if (++guard >= T - 1 && last >= T - 1) {
+                    stop = 1;
+                    break;
+                }
+            }
+            count = cnt;
+            if (!stop) {
+                site_m[uidx] = new_m[uidx];
+                site_v[uidx] = new_v[uidx];
+            }
+        }
+        count = __shfl_sync(0xffffffffu, count, 0);
+        stop = __shfl_sync(0xffffffffu, stop, 0);
+        __syncwarp();
+        if (stop) break;
+        ep_refresh_warp(Mw, T, j, inv_cov, h, site_m, site_v, rhs, wwv, n_mean, lane);
+        // converge_diff = mean over the (T, T) broadcast of dmean_i^2 + dcov_ik^2 (ep.py:190-193); NaN check
+        double part = 0.0;
+        int nan = 0;
+        for (int e = lane; e < T * T; e += 32) {
+            const int i = e / T, k = e - i * T;
+            const double dm = n_mean[i] - a_mean[i];
+            const double mv = Mw[i * EPW_LD + k];
+            const double dc = mv - Cw[i * EPW_LD + k];
+            part += dm * dm + dc * dc;
+            nan |= (mv != mv) || (n_mean[i] != n_mean[i]);
+        }
+        part = warp_sum(part);
+        nan = __any_sync(0xffffffffu, nan);
+        diff = part / ((double)T * (double)T);
+        if (nan) break;          // ep.py:195-199: keep the previous approximation
+        for (int e = lane; e < T * T; e += 32) Cw[(e / T) * EPW_LD + e % T] = Mw[(e / T) * EPW_LD + e % T];
+        if (lane < T) a_mean[lane] = n_mean[lane];
+        __syncwarp();
+    }
+    __syncwarp();
+    double* a_cov_out = post_cov + (hy * T + j) * (int64_t)T * T;
+    for (int e = lane; e < T * T; e += 32) a_cov_out[e] = Cw[(e / T) * EPW_LD + e % T];
+    if (lane < T) post_mean[(hy * T + j) * (int64_t)T + lane] = a_mean[lane];
+    if (lane == 0 && niter) niter[hy * T + j] = count;
+}
+
 }  // namespace tes
 
 using namespace tes;
@@ -364,6 +594,28 @@ extern "C" int tes_ep_moments_f64(const double* mean, const double* cov, int64_t
     // the prepare step reuses the first nhyp slots of the main kernel's scratch
     ep_prepare_kernel<<<(unsigned)nhyp, EP_THREADS, sm_prep, st>>>(cov, mean, (int)T, inv_cov, h, gscratch, in_smem);
     TES_LAUNCH_OK();
+    static const int ep_mode = [] {                 // developer knob: 0 = warp kernel for T <= 32, 1 / 2 = CTA kernel with 512 / 128 threads
+        const char* e = getenv("TES_EP_MODE");
+        return e ? atoi(e) : 0;
+    }();
+    if (ep_mode == 2) {
+        ep_kernel<<<dim3((unsigned)T, (unsigned)nhyp), 128, sm_main, st>>>(mean, cov, inv_cov, h, (int)T, resolution, max_niter,
+                                                                          post_mean, post_cov, niter, gscratch, in_smem);
+        TES_LAUNCH_OK();
+        return 0;
+    }
+    if (T <= EPW && ep_mode == 0) {
+        // one warp per maximizer, the system matrix in registers (no block barriers); two warps per CTA so that the
+        // maximizers spread over the SMs
+        const int wpb = 2;
+        const size_t smw = (size_t)wpb * EPW_DOUBLES * sizeof(double);
+        const int64_t nwarp = T * nhyp;
+        ep_warp_kernel<<<(unsigned)((nwarp + wpb - 1) / wpb), 32 * wpb, smw, st>>>(mean, cov, inv_cov, h, (int)T, nhyp,
+                                                                                  resolution, max_niter, post_mean,
+                                                                                  post_cov, niter);
+        TES_LAUNCH_OK();
+        return 0;
+    }
     ep_kernel<<<dim3((unsigned)T, (unsigned)nhyp), EP_THREADS, sm_main, st>>>(mean, cov, inv_cov, h, (int)T, resolution,
                                                                              max_niter, post_mean, post_cov, niter,
                                                                              gscratch, in_smem);
