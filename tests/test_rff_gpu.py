@@ -303,13 +303,13 @@ def test_product_path_is_bit_identical_to_the_general_kernels(axes_n, S, F, k, s
     # every admissible split point gives the same answer (meshgrid 'xy' order: columns 1, 0, 2, 3, ... slowest to fastest)
     for du in range(2, d):
         nv = int(np.prod(axes_n[du:]))
-        for tf32 in (6, 5, 4, 3, 2, 1, 0):   # 3xFP16 on tcgen05 (P generated on the SM / streamed) / mma.sync, 3xTF32 mma.sync, fp64 DMMA: same bits after the refine
+        for tf32 in (8, 6, 5, 4, 3, 2, 1, 0):   # 3xFP16 on tcgen05 (P generated on the SM / streamed) / mma.sync, 3xTF32 mma.sync, fp64 DMMA: same bits after the refine
             i2, v2, fl = ops.rff_topk_product(cand, Wn, bn, th, 1.3, 0, du, nv, k=k, idx_offset=1000, tf32=tf32)
             assert int(fl.sum()) == 0
             np.testing.assert_array_equal(i2.cpu().numpy(), ridx)
             np.testing.assert_array_equal(v2.cpu().numpy(), rval)
     s_lo, s_hi, nv = det
-    for tf32 in (6, 5, 4, 3, 2, 1, 0):
+    for tf32 in (8, 6, 5, 4, 3, 2, 1, 0):
         i2, v2, fl = ops.rff_topk_product(cand, Wn, bn, th, 1.3, s_lo, s_hi, nv, k=k, idx_offset=1000, tf32=tf32)
         good = (fl == 0).cpu().numpy()
         assert good.mean() > 0.5
@@ -334,7 +334,7 @@ def test_product_path_two_level_merge_equals_single_cta_merge(axes_n, k, monkeyp
     det = ops.detect_product_structure(ops.dev(cand))
     assert det is not None
     ridx, rval = co.rff_topk(cand, Wn, bn, th, 0.8, k)
-    for tf32 in (6, 5, 4, 3, 2):
+    for tf32 in (8, 6, 5, 4, 3, 2):
         out = {}
         for mode in ("1", "0"):
             monkeypatch.setenv("TES_PROD_MERGE", mode)
@@ -363,7 +363,7 @@ def test_product_path_flags_ties_and_falls_back():
     th[2] = 0.0                                      # a constant (zero) function sample: every candidate ties
     det = ops.detect_product_structure(ops.dev(cand))
     assert det is not None
-    for tf32 in (6, 5, 4, 3, 2, 1, 0):
+    for tf32 in (8, 6, 5, 4, 3, 2, 1, 0):
         _, _, flag = ops.rff_topk_product(cand, Wn, bn, th, 0.9, det[0], det[1], det[2], k=3, tf32=tf32)
         assert int(flag[2]) == 1
     idx, val = ops.rff_topk(cand, Wn, bn, th, 0.9, k=3, method=ops.RFF_PRODUCT)
@@ -447,7 +447,7 @@ def test_product_path_near_ties(eps, seed):
     np.testing.assert_array_equal(idx.cpu().numpy(), ridx)
     np.testing.assert_array_equal(val.cpu().numpy(), rval)
     det = ops.detect_product_structure(ops.dev(cand))
-    for tf32 in (0, 1, 2, 3, 4, 5, 6):
+    for tf32 in (0, 1, 2, 3, 4, 5, 6, 8):
         i2, v2, fl = ops.rff_topk_product(cand, Wn, bn, th, 1.1, det[0], det[1], det[2], k=3, tf32=tf32)
         good = (fl == 0).cpu().numpy()
         np.testing.assert_array_equal(i2.cpu().numpy()[good], ridx[good])

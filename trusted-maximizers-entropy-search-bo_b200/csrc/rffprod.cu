@@ -1259,6 +1259,251 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     }
 }
 
+// ---- CTA pairs with 256 x 256 tiles (mode 8): two operand blocks per SM and stage feed TWICE the MMA work ------------
+// scripts/tc5/mma_rate.cu measures 64 cycles per M128 N128 K16 tcgen05.mma: the 12 MMAs of a 64-k stage need 0.39 us,
+// while every kernel above delivers a 64 KB stage in ~1.2 us (~54 GB/s of operand ingest per SM) -- the product GEMM is
+// bound by operand bytes per MMA, and hi/lo fp16 operands cost 4 bytes per element.  A pair of CTAs on a 256 x 256
+// tile halves those bytes: each CTA stages its own 128 rows of P (32 KB) and ONE of the tile's two 128-column Q blocks
+// (32 KB; the tensor cores of both SMs read both halves), and the leader issues M256 x N256 x K16 MMAs: 24 per stage
+// and SM instead of 12 for the same 64 KB.  The two accumulators of 256 columns fill the tensor memory; every epilogue
+// thread then owns 64 columns (32 of each column tile), which only fit in registers as FP32 running sums (the segments
+// bound the tensor core's internal accumulation error; adding 2F / 256 segment values in fp32 adds one rounding of
+// 2^-24 of the sum of |terms| each -- carried by prod_exact_kernel's bound, +1.5 % at F = 1024).
+constexpr uint32_t T8_STAGE_BYTES = 2 * TC_BLOCK_BYTES;                       // own A block + one B block = 64 KB
+constexpr int T8_NS = 3;
+
+#define TC_LD16(v, taddr)                                                                                             \
+    asm volatile(                                                                                                     \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"      \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),             \
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])        \
+        : "r"(taddr))
+
+// HALF = 1: stages of 32 k (32 KB: [A hi | A lo | B hi | B lo], 8 KB each), NS of them: the pair hand-offs (relay lane,
+// multicast commits) add ~1.6 us to the cycle of a slot, which more, smaller slots hide
+template <int HALF, int NS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    prod_gemm_topk_tc8_kernel(const __half* __restrict__ Pt, const __half* __restrict__ Qt, int64_t nu, int64_t nv,
+                              int ntu, int ntv, int nst, double scale0, const double* __restrict__ tmax,
+                              int64_t idx_offset, int kp, int G, double* __restrict__ part_val,
+                              int64_t* __restrict__ part_idx) {
+    extern __shared__ __align__(1024) unsigned char t8_smem_raw[];
+    constexpr uint32_t STAGE = HALF ? T8_STAGE_BYTES / 2 : T8_STAGE_BYTES;
+    constexpr uint32_t PART = HALF ? TC_BLOCK_BYTES / 4 : TC_BLOCK_BYTES / 2;      // bytes of the hi (= of the lo) part
+    constexpr int SUB = HALF ? 2 : 1;
+    unsigned char* stages = t8_smem_raw;                                           // [NS][A hi | A lo | B hi | B lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(t8_smem_raw + NS * STAGE);
+    uint64_t* full_b = bars;                     // [NS] this CTA's producer -> (leader: MMA, peer: relay)
+    uint64_t* peer_full = full_b + NS;           // [NS] leader only: the peer's relay -> MMA
+    uint64_t* empty_b = peer_full + NS;          // [NS] MMA (multicast commit) -> producer of each CTA
+    uint64_t* acc_full = empty_b + NS;           // [2] MMA (multicast commit) -> epilogue of each CTA
+    uint64_t* acc_empty = acc_full + 2;          // [2] leader only: the epilogue warps of BOTH CTAs -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = (int)(blockIdx.x >> 1), npair = (int)(gridDim.x >> 1);
+    const int ntu2 = (ntu + 1) / 2, ntv2 = (ntv + 1) / 2;     // 256-row / 256-column tile pairs per sample
+    const int tps = ntu2 * ntv2;
+    const int ntot = tps * G;
+    const int ntile = pair < ntot ? (ntot - pair + npair - 1) / npair : 0;
+    const int nseg = nst / TC_SEG;
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full_b[s], 1);
+            mbar_init(&peer_full[s], 1);
+            mbar_init(&empty_b[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 2 * TC_EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (int it = 0; it < ntile; ++it) {
+                const int t = pair + it * npair;
+                const int rt = 2 * (t % ntu2) + (int)rank, ct = 2 * ((t / ntu2) % ntv2) + (int)rank, g = t / tps;
+                // both arrays hold an EVEN number of 128-row tiles per sample (an odd count is padded with a zero tile)
+                const unsigned char* srcA = reinterpret_cast<const unsigned char*>(Pt) +
+                                            ((int64_t)(g * 2 * ntu2 + rt) * nst) * (int64_t)TC_BLOCK_BYTES;
+                const unsigned char* srcB = reinterpret_cast<const unsigned char*>(Qt) +
+                                            ((int64_t)(g * 2 * ntv2 + ct) * nst) * (int64_t)TC_BLOCK_BYTES;
+                for (int st = 0; st < nst; ++st)
+                    for (int h = 0; h < SUB; ++h) {
+                        mbar_wait(&empty_b[s], ph ^ 1u);
+                        mbar_expect_tx(&full_b[s], STAGE);
+                        unsigned char* dst = stages + s * STAGE;
+                        const unsigned char* a = srcA + st * (int64_t)TC_BLOCK_BYTES + h * PART;
+                        const unsigned char* b = srcB + st * (int64_t)TC_BLOCK_BYTES + h * PART;
+                        if (HALF) {
+                            bulk_g2s(dst, a, PART, &full_b[s]);
+                            bulk_g2s(dst + PART, a + TC_BLOCK_BYTES / 2, PART, &full_b[s]);
+                            bulk_g2s(dst + 2 * PART, b, PART, &full_b[s]);
+                            bulk_g2s(dst + 3 * PART, b + TC_BLOCK_BYTES / 2, PART, &full_b[s]);
+                        } else {
+                            bulk_g2s(dst, a, TC_BLOCK_BYTES, &full_b[s]);
+                            bulk_g2s(dst + TC_BLOCK_BYTES, b, TC_BLOCK_BYTES, &full_b[s]);
+                        }
+                        if (++s == NS) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
+                    }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && !leader) {
+            uint32_t s = 0, ph = 0;                 // relay: this CTA's half of the stage has landed
+            const int total = ntile * nst * SUB;
+            for (int x = 0; x < total; ++x) {
+                mbar_wait(&full_b[s], ph);
+                mbar_arrive_remote(mapa_u32(smem_u32(&peer_full[s]), 0));
+                if (++s == NS) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        } else if (lane == 0) {
+            const uint32_t idesc = tc_idesc_f16(256, 256);
+            const uint32_t base = smem_u32(stages);
+            uint32_t s = 0, ph = 0;
+            const int segs = ntile * nseg;
+            for (int seg = 0; seg < segs; ++seg) {
+                const uint32_t a = (uint32_t)(seg & 1), pa = (uint32_t)((seg >> 1) & 1);
+                mbar_wait_cluster(&acc_empty[a], pa ^ 1u);
+                tc_fence_after();
+                for (int q4 = 0; q4 < TC_SEG * SUB; ++q4) {
+                    mbar_wait(&full_b[s], ph);
+                    mbar_wait_cluster(&peer_full[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * STAGE, sb = sa + 2 * PART;
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 16 / SUB; ++ks) {
+                        const uint32_t off = (uint32_t)(2 * ks) * 128u * 16u;
+                        const uint64_t a_hi = tc_desc(sa + off, 128 * 16, 128);
+                        const uint64_t a_lo = tc_desc(sa + PART + off, 128 * 16, 128);
+                        const uint64_t b_hi = tc_desc(sb + off, 128 * 16, 128);
+                        const uint64_t b_lo = tc_desc(sb + PART + off, 128 * 16, 128);
+                        const uint32_t first = (q4 == 0 && ks == 0) ? 0u : 1u;
+                        tc2_mma_f16(tmem + a * 256u, a_lo, b_hi, idesc, first);
+                        tc2_mma_f16(tmem + a * 256u, a_hi, b_lo, idesc, 1u);
+                        tc2_mma_f16(tmem + a * 256u, a_hi, b_hi, idesc, 1u);
+                    }
+                    tc2_commit_mc(&empty_b[s]);
+                    if (++s == NS) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+                tc2_commit_mc(&acc_full[a]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int ew = warp - 2;                       // 0..15
+        const int quarter = warp & 3;                  // TMEM lanes this warp may access
+        const int cb = ew >> 2;                        // columns [32 cb, 32 cb + 32) of EACH of the two column tiles
+        const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32);
+        const uint32_t ae_remote0 = mapa_u32(smem_u32(&acc_empty[0]), 0), ae_remote1 = mapa_u32(smem_u32(&acc_empty[1]), 0);
+        int gseg = 0;
+        for (int it = 0; it < ntile; ++it) {
+            const int t = pair + it * npair;
+            const int rt = 2 * (t % ntu2) + (int)rank, ctp = (t / ntu2) % ntv2, g = t / tps;
+            const double scale = scale0 * tmax[g];
+            float acc[2][32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[0][c] = acc[1][c] = 0.0f;
+            for (int seg = 0; seg < nseg; ++seg, ++gseg) {
+                const uint32_t a = (uint32_t)(gseg & 1), pa = (uint32_t)((gseg >> 1) & 1);
+                mbar_wait(&acc_full[a], pa);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        uint32_t v0[16];
+                        TC_LD16(v0, t_lane + a * 256u + (uint32_t)(h * 128 + q * 16));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) acc[h][q * 16 + c] = __fadd_rn(acc[h][q * 16 + c], __uint_as_float(v0[c]));
+                    }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (leader) tc_arrive(&acc_empty[a]);
+                    else mbar_arrive_remote(a ? ae_remote1 : ae_remote0);
+                }
+            }
+            if (rt >= ntu) continue;                   // the zero tile that pads an odd number of row tiles
+            const int64_t row = (int64_t)rt * 128 + quarter * 32 + lane;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ct = 2 * ctp + h;
+                if (ct >= ntv) continue;
+                // per-warp top-kp of its 32 rows x 32 columns of column tile ct
+                const int64_t colb = (int64_t)ct * 128 + cb * 32;
+                const int64_t list = (int64_t)(rt * ntv + ct) * TC_EPI_WARPS + ew;
+                double* ov = part_val + (list * G + g) * kp;
+                int64_t* oi = part_idx + (list * G + g) * kp;
+                uint32_t used = 0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (!(row < nu && colb + c < nv)) used |= 1u << c;
+                const int64_t ci0 = row * nv + colb + idx_offset;
+                for (int r = 0; r < kp; ++r) {
+                    float bh = 0.0f;
+                    int bc = -1;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)       // ascending c = ascending index: strict > keeps the lowest index
+                        if (!((used >> c) & 1u) && (bc < 0 || acc[h][c] > bh)) {
+                            bh = acc[h][c];
+                            bc = c;
+                        }
+                    double wv = bc >= 0 ? __dmul_rn(scale, (double)bh) : neg_inf();
+                    int64_t wi = bc >= 0 ? ci0 + bc : INT64_MAX;
+                    warp_argmax(wv, wi);
+                    const bool found = (wi != INT64_MAX);
+                    if (lane == 0) {
+                        ov[r] = found ? wv : neg_inf();
+                        oi[r] = found ? wi : -1;
+                    }
+                    if (!found) {
+                        for (int q = r + 1; q < kp; ++q)
+                            if (lane == 0) {
+                                ov[q] = neg_inf();
+                                oi[q] = -1;
+                            }
+                        break;
+                    }
+                    if (bc >= 0 && wi == ci0 + bc) used |= 1u << bc;   // the winning lane consumes its element
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    }
+}
+
 // ---- the same GEMM with the P operand GENERATED ON THE SM (mode 4) -------------------------------------------------
 // prod_gemm_topk_tc_kernel streams both operands: 64 KB per 64-k stage and SM, i.e. more than an SM ingests while the
 // tensor pipe works through a stage (ncu, round 1: tensor pipe 38.6 % busy, epilogue warps parked on acc_full), and its
@@ -2293,8 +2538,8 @@ __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const 
         // fp16 operands (mode 2; same 11-bit significand as TF32, theta normalised by tmax): subnormal rounding adds an
         // absolute 2^-25 per operand, i.e. <= 2 * 2^-25 per term over 2F terms, in units of scale * tmax
         if (tf32 >= 2) B += 1.5 * scale * tmax[j] * 4.0 * (double)F * 2.98023223876953125e-08;
-        // modes 4 / 5 add the 2F / 256 segment values in fp32: one rounding of 2^-24 of the sum of |terms| per segment
-        if (tf32 >= 4) B += 1.5 * scale * sa * 5.9604644775390625e-08 * (double)((2 * F + 255) / 256);
+        // modes 4 / 5 / 8 add the 2F / 256 segment values in fp32: one rounding of 2^-24 of the sum of |terms| per segment
+        if (tf32 == 4 || tf32 == 5 || tf32 == 8) B += 1.5 * scale * sa * 5.9604644775390625e-08 * (double)((2 * F + 255) / 256);
         const double vk = approx_val[j * kp + (k - 1)], vl = approx_val[j * kp + (kp - 1)];
         const bool full = idx[j * kp + (kp - 1)] >= 0;   // fewer than kp candidates in total: nothing was cut
         const bool enough = idx[j * kp + (k - 1)] >= 0;  // NaN values are never selected: let the general kernel decide
@@ -2338,7 +2583,7 @@ static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F
     // entirely (gen_gc = 8: no P array) or the first gen_gc of the 8 chunks of every stage (gen_gc = 4: P array as in mode 3)
     ProdPlan p;
     const bool no_p = gen_ncol && gen_gc == 8;
-    const bool pairs = tc == 2;                  // mode 6: CTA pairs, 256-row tile pairs (an odd tile count is padded)
+    const bool pairs = tc >= 2;                  // modes 6 / 8: CTA pairs, 256-row tile pairs (an odd tile count is padded)
     p.nu = N / nv;
     p.rec = prod_rec((int)d);
     p.kp = k + 8 > PROD_MAX_KP ? PROD_MAX_KP : k + 8;
@@ -2347,6 +2592,7 @@ static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F
     p.K2p = tc ? (2 * F + 255) / 256 * 256 : (2 * F + PH_BK - 1) / PH_BK * PH_BK;
     if (tc) p.nvp = (nv + 127) / 128 * 128;
     if (pairs) p.nup = (p.nu + 255) / 256 * 256;
+    if (tc == 3) p.nvp = (nv + 255) / 256 * 256;   // mode 8: 256-column tile pairs too
     const int64_t per_sample = no_p ? p.nvp * p.K2p * 8 : (tf32 ? (p.nup + p.nvp) * p.K2p * 8 : (p.nu + nv) * 2 * F * 8);
     int64_t G = per_sample > 0 ? (int64_t)(1.5e9 / (double)per_sample) : 1;
     if (G < 1) G = 1;
@@ -2439,6 +2685,7 @@ extern "C" int64_t tes_rff_topk_product_workspace_bytes(int64_t N, int64_t d, in
     // modes 4 / 5 (P generated on the SM) need the split, which this query does not carry: the largest layout
     const int64_t a = prod_plan(N, d, nv, S, F, k, tf32 != 0, tf32 >= 3).total;   // tf32 / fp16 operand arrays: (hi, lo) x 4 resp. 2 bytes
     if (tf32 == 6) return prod_plan(N, d, nv, S, F, k, 1, 2).total;
+    if (tf32 == 8) return prod_plan(N, d, nv, S, F, k, 1, 3).total;
     if (tf32 < 4) return a;
     const int64_t b = prod_plan(N, d, nv, S, F, k, 1, 1, PG_MAXCOL, 8).total;
     const int64_t c = prod_plan(N, d, nv, S, F, k, 1, 1, PG_MAXCOL, 4).total;
@@ -2464,12 +2711,12 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     if (!out_idx) return -15;
     if (!out_val) return -16;
     if (!out_flag) return -17;
-    if (tf32 < 0 || tf32 > 6) return -18;
+    if (tf32 < 0 || tf32 > 8 || tf32 == 7) return -18;
     if (tf32 >= 2 && d > 16) tf32 = 1;   // the fp16 operand build keeps a feature's weights in 16 registers
     if ((tf32 == 4 || tf32 == 5) && s_hi - s_lo > PG_MAXCOL) tf32 = 3;   // modes 4 / 5 keep the slow coordinates and the record ring in smem
     const int gen_ncol = (tf32 == 4 || tf32 == 5) ? (int)(s_hi - s_lo) : 0;
     const int gen_gc = tf32 == 5 ? 4 : 8;
-    ProdPlan pl = prod_plan(N, d, nv, S, F, k, tf32 != 0, tf32 == 6 ? 2 : (tf32 >= 3), gen_ncol, gen_gc);
+    ProdPlan pl = prod_plan(N, d, nv, S, F, k, tf32 != 0, tf32 == 8 ? 3 : (tf32 == 6 ? 2 : (tf32 >= 3)), gen_ncol, gen_gc);
     if (!ws || ws_bytes < pl.total) return -100;
     cudaStream_t st = (cudaStream_t)stream;
     char* base = (char*)ws;
@@ -2514,6 +2761,12 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
                                          (int)(7 * TC_STAGE_BYTES / 2 + 256)));
         TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(T2_NS * T2_STAGE_BYTES + 256)));
+        TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc8_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(3 * T8_STAGE_BYTES + 256)));
+        TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc8_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(6 * T8_STAGE_BYTES / 2 + 256)));
+        TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc8_kernel<1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(7 * T8_STAGE_BYTES / 2 + 256)));
         // zero the tile padding once (rows >= nu, columns >= nv, k >= 2F are never written by the build kernels)
         if (!(gen_ncol && gen_gc == 8)) TES_CUDA_OK(cudaMemsetAsync(P, 0, (size_t)(pl.G * pl.nup * pl.K2p * 8), st));
         TES_CUDA_OK(cudaMemsetAsync(Qt, 0, (size_t)(pl.G * pl.K2p * pl.nvp * 8), st));
@@ -2529,7 +2782,31 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
     for (int64_t j0 = 0; j0 < S; j0 += pl.G) {
         const int64_t G = (S - j0 < pl.G) ? (S - j0) : pl.G;
         dim3 grid((unsigned)pl.gx, (unsigned)pl.gy, (unsigned)G);
-        if (tf32 == 6) {
+        if (tf32 == 8) {
+            const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK, ntu2 = (ntu + 1) / 2, ntv2 = (ntv + 1) / 2;
+            prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)G, 8), 256, 0, st>>>(
+                cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, 2 * ntu2, nst, tmax, Hhi, 0, 128);
+            TES_LAUNCH_OK();
+            prod_build_tc_kernel<<<dim3((unsigned)ntv, (unsigned)G, 8), 256, 0, st>>>(
+                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, 2 * ntv2, nst, tmax, Ghi, 0, 128);
+            TES_LAUNCH_OK();
+            const int64_t ntot = ntu2 * ntv2 * G;
+            int64_t ncta = 2 * ntot < tc_sm_count() ? 2 * ntot : (tc_sm_count() / 2) * 2;
+            static const int t8_shape = [] {      // developer knob: 3 whole stages of 64 KB or 6 / 7 half stages of 32 KB
+                const char* e = getenv("TES_T8_STAGES");
+                return e ? atoi(e) : 3;        // measured at C3: 18.7 ms (3 x 64 KB) / 20.7 ms (6 or 7 x 32 KB)
+            }();
+            if (t8_shape == 3)
+                prod_gemm_topk_tc8_kernel<0, 3><<<(unsigned)ncta, TC_THREADS, 3 * T8_STAGE_BYTES + 256, st>>>(
+                    Hhi, Ghi, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
+            else if (t8_shape == 6)
+                prod_gemm_topk_tc8_kernel<1, 6><<<(unsigned)ncta, TC_THREADS, 6 * T8_STAGE_BYTES / 2 + 256, st>>>(
+                    Hhi, Ghi, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
+            else
+                prod_gemm_topk_tc8_kernel<1, 7><<<(unsigned)ncta, TC_THREADS, 7 * T8_STAGE_BYTES / 2 + 256, st>>>(
+                    Hhi, Ghi, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
+            TES_LAUNCH_OK();
+        } else if (tf32 == 6) {
             const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK, ntu2 = (ntu + 1) / 2;
             // P: 128-row tiles, 2 ntu2 of them per sample (an odd count is padded with the zero tile of the memset);
             // Q: 64-column tiles, 2 ntv per sample (each CTA of a pair stages one half of a 128-column tile)

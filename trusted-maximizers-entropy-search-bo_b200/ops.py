@@ -27,7 +27,7 @@ STATS = {"product_flagged": 0}   # samples the product path handed back to the g
 
 RFF_PRODUCT = 6          # product-structured candidate sets: one fp64 tensor-pipe GEMM per sample (csrc/rffprod.cu)
 PRODUCT_MIN_N = 1 << 15  # below this the general kernels are launch-bound anyway
-PRODUCT_MODE = int(__import__("os").environ.get("TES_PRODUCT_MODE", "3"))   # GEMM engine of the product path
+PRODUCT_MODE = int(__import__("os").environ.get("TES_PRODUCT_MODE", "8"))   # GEMM engine of the product path (8: CTA pairs, 256 x 256 tiles)
 
 
 def detect_product_structure(cand):
@@ -112,8 +112,9 @@ def detect_product_prefix(cand, max_tail=None):
 def rff_topk_product(cand, W, b, theta, sigma, s_lo, s_hi, nv, k=1, idx_offset=0, tf32=None):
     """tes_rff_topk_product_f64 -> (idx (S,k), val (S,k), flag (S,) int32).  flag[j] = 1: recompute sample j with the
     general kernel (rff_topk does that).  tf32: 2 = 3xFP16 tensor-core screen (default), 1 = 3xTF32, 0 / False = fp64
-    (DMMA), 3 = 3xFP16 on tcgen05/TMEM with both operands streamed, 4 = the same with the P operand generated on the SM
-    (no operand round trip through HBM for the U side); identical results in every mode.  None: PRODUCT_MODE (env TES_PRODUCT_MODE)."""
+    (DMMA), 3 = 3xFP16 on tcgen05/TMEM with both operands streamed, 4 / 5 = the same with the P operand (half of it) generated
+    on the SM, 6 = CTA pairs (cta_group::2) on 256 x 128 tiles, 8 = CTA pairs on 256 x 256 tiles (default: half the
+    operand bytes per MMA); identical results in every mode.  None: PRODUCT_MODE (env TES_PRODUCT_MODE)."""
     if tf32 is None:
         tf32 = PRODUCT_MODE
     cand, W, b, theta, N, d, S, F, ws_ = _rff_args(cand, W, b, theta)
