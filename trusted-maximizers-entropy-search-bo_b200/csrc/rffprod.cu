@@ -698,14 +698,14 @@ __global__ void __launch_bounds__(256)
     __shared__ double xs[16][129];                   // [coordinate slot][row]
     __shared__ double ws[PB_WS_DOUBLES];             // [feature of the block][w (ncol), b, theta]
     const int64_t tile = blockIdx.x, g = blockIdx.y;
-    const int r = threadIdx.x % TR, half = threadIdx.x / TR, nhalf = 256 / TR;
+    const int r = threadIdx.x % TR, half = threadIdx.x / TR, nhalf = (int)blockDim.x / TR;   // 256 or 128 threads
     const int64_t ir = tile * TR + r;
     const int64_t j = j0 + g, jw = w_shared ? 0 : j;
     // coordinate slots: the columns this side uses, in order (arithmetic, not a table: a runtime-indexed array would
     // live in local memory and put an LDL in front of every DFMA)
     const int ncol = which == 0 ? s_hi - s_lo : d - (s_hi - s_lo);
     auto col_of = [&](int c) { return which == 0 ? s_lo + c : (c < s_lo ? c : c + (s_hi - s_lo)); };
-    for (int e = threadIdx.x; e < ncol * TR; e += 256) {
+    for (int e = threadIdx.x; e < ncol * TR; e += blockDim.x) {
         const int c = e / TR, rr = e % TR;
         const int64_t gr = tile * TR + rr;
         xs[c][rr] = gr < nrow ? cand[(gr * row_stride) * d + col_of(c)] : 0.0;
@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(256)
         const int64_t ce = cb + cpb < kc_hi ? cb + cpb : kc_hi;
         const int nf = (int)(ce - cb) * 4;
         __syncthreads();
-        for (int e = threadIdx.x; e < nf * rs; e += 256) {
+        for (int e = threadIdx.x; e < nf * rs; e += blockDim.x) {
             const int fl = e / rs, c = e % rs;
             const int64_t f = cb * 4 + fl, fc = f < F ? f : F - 1;
             double v;
@@ -2630,8 +2630,10 @@ static ProdPlan prod_plan(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F
     };
     p.off_feat = take(S * F * p.rec * 8);
     // tf32: hi and lo float arrays
-    p.off_p = take(no_p ? 256 : (tf32 ? G * p.nup * p.K2p * 8 : G * p.nu * 2 * F * 8));
-    p.off_q = take(tf32 ? G * p.K2p * p.nvp * 8 : G * 2 * F * nv * 8);
+    // mode 8 double-buffers the operand arrays: the build of group g + 1 runs on a second stream under the GEMM of group g
+    const int nbuf = tc == 3 ? 2 : 1;
+    p.off_p = take(no_p ? 256 : nbuf * (tf32 ? G * p.nup * p.K2p * 8 : G * p.nu * 2 * F * 8));
+    p.off_q = take(nbuf * (tf32 ? G * p.K2p * p.nvp * 8 : G * 2 * F * nv * 8));
     p.off_pv = take(p.nlist * G * p.kp * 8);
     p.off_pi = take(p.nlist * G * p.kp * 8);
     p.off_mv = take(S * p.kp * 8);
@@ -2763,13 +2765,17 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
                                          (int)(T2_NS * T2_STAGE_BYTES + 256)));
         TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc8_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(3 * T8_STAGE_BYTES + 256)));
+        // the whole 228 KB as shared memory, so that a build CTA of the second stream (30 KB) fits beside the GEMM CTA
+        TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc8_kernel<0, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        TES_CUDA_OK(cudaFuncSetAttribute(prod_build_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc8_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(6 * T8_STAGE_BYTES / 2 + 256)));
         TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc8_kernel<1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(7 * T8_STAGE_BYTES / 2 + 256)));
         // zero the tile padding once (rows >= nu, columns >= nv, k >= 2F are never written by the build kernels)
-        if (!(gen_ncol && gen_gc == 8)) TES_CUDA_OK(cudaMemsetAsync(P, 0, (size_t)(pl.G * pl.nup * pl.K2p * 8), st));
-        TES_CUDA_OK(cudaMemsetAsync(Qt, 0, (size_t)(pl.G * pl.K2p * pl.nvp * 8), st));
+        const size_t nbuf = tf32 == 8 ? 2 : 1;
+        if (!(gen_ncol && gen_gc == 8)) TES_CUDA_OK(cudaMemsetAsync(P, 0, nbuf * (size_t)(pl.G * pl.nup * pl.K2p * 8), st));
+        TES_CUDA_OK(cudaMemsetAsync(Qt, 0, nbuf * (size_t)(pl.G * pl.K2p * pl.nvp * 8), st));
         prod_tmax_kernel<<<(unsigned)S, 256, 0, st>>>(theta, F, tmax);
         TES_LAUNCH_OK();
         if (gen_ncol) {
@@ -2779,33 +2785,96 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
             TES_LAUNCH_OK();
         }
     }
+    // second stream + events of the overlapped operand build (mode 8, more than one group); released when the call
+    // returns (destruction is deferred by the runtime until the enqueued work has finished)
+    struct Overlap {
+        bool on = false;
+        cudaStream_t s2 = nullptr;
+        cudaEvent_t start = nullptr, built[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+        ~Overlap() {
+            for (cudaEvent_t e : {start, built[0], built[1], freed[0], freed[1]})
+                if (e) cudaEventDestroy(e);
+            if (s2) cudaStreamDestroy(s2);
+        }
+    } ov;
+    {
+        static const bool want = [] {
+            // developer knob, default OFF: measured at C3 the overlap buys 0.5 ms of 18.6 (the build CTAs mostly wait
+            // for the persistent GEMM CTAs to leave), not worth a stream created inside the library by default
+            const char* e = getenv("TES_PROD_OVERLAP");
+            return e && e[0] == '1';
+        }();
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);                  // (a capturing stream cannot fork to a stream created here)
+        if (tf32 == 8 && S > pl.G && want && cap == cudaStreamCaptureStatusNone) {
+            int lo = 0, hi = 0;
+            TES_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            TES_CUDA_OK(cudaStreamCreateWithPriority(&ov.s2, cudaStreamNonBlocking, lo));
+            for (cudaEvent_t* e : {&ov.start, &ov.built[0], &ov.built[1], &ov.freed[0], &ov.freed[1]})
+                TES_CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+            ov.on = true;
+        }
+    }
     for (int64_t j0 = 0; j0 < S; j0 += pl.G) {
         const int64_t G = (S - j0 < pl.G) ? (S - j0) : pl.G;
         dim3 grid((unsigned)pl.gx, (unsigned)pl.gy, (unsigned)G);
         if (tf32 == 8) {
+            // operands of group g + 1 are built on a second, low-priority stream into the other half of the double
+            // buffer while the GEMM of group g runs: the build is bound by the conversion / transcendental pipe, the
+            // GEMM by operand delivery, and a 128-thread build CTA fits beside the persistent GEMM CTA of an SM
+            // (registers 55 296 + 8 192, shared memory 197 + 30 KB)
             const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK, ntu2 = (ntu + 1) / 2, ntv2 = (ntv + 1) / 2;
-            prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)G, 8), 256, 0, st>>>(
-                cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, 2 * ntu2, nst, tmax, Hhi, 0, 128);
-            TES_LAUNCH_OK();
-            prod_build_tc_kernel<<<dim3((unsigned)ntv, (unsigned)G, 8), 256, 0, st>>>(
-                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, 2 * ntv2, nst, tmax, Ghi, 0, 128);
-            TES_LAUNCH_OK();
+            const int64_t gi = j0 / pl.G;
+            const size_t pbuf = (size_t)(pl.G * pl.nup * pl.K2p * 4), qbuf = (size_t)(pl.G * pl.K2p * pl.nvp * 4);   // halves
+            auto build = [&](int64_t jj0, int64_t GG, int buf, cudaStream_t bs, int threads) -> int {
+                __half* ph_ = Hhi + buf * pbuf;
+                __half* qh_ = Ghi + buf * qbuf;
+                prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)GG, 8), threads, 0, bs>>>(
+                    cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, jj0, F, w_shared, 2 * ntu2, nst, tmax, ph_, 0, 128);
+                TES_LAUNCH_OK();
+                prod_build_tc_kernel<<<dim3((unsigned)ntv, (unsigned)GG, 8), threads, 0, bs>>>(
+                    cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, jj0, F, w_shared, 2 * ntv2, nst, tmax, qh_, 0, 128);
+                TES_LAUNCH_OK();
+                return 0;
+            };
+            const int buf = (int)(gi & 1);
+            if (!ov.on) {
+                if (int rc = build(j0, G, buf, st, 256)) return rc;
+            } else {
+                if (gi == 0) {
+                    TES_CUDA_OK(cudaEventRecord(ov.start, st));          // tmax, memsets: everything the builds read
+                    TES_CUDA_OK(cudaStreamWaitEvent(ov.s2, ov.start, 0));
+                    if (int rc = build(j0, G, 0, ov.s2, 128)) return rc;
+                    TES_CUDA_OK(cudaEventRecord(ov.built[0], ov.s2));
+                }
+                const int64_t jn = j0 + pl.G;
+                if (jn < S) {                                            // the next group, into the other buffer
+                    const int nb = buf ^ 1;
+                    if (gi >= 1) TES_CUDA_OK(cudaStreamWaitEvent(ov.s2, ov.freed[nb], 0));   // GEMM gi - 1 read it
+                    if (int rc = build(jn, (S - jn < pl.G) ? (S - jn) : pl.G, nb, ov.s2, 128)) return rc;
+                    TES_CUDA_OK(cudaEventRecord(ov.built[nb], ov.s2));
+                }
+                TES_CUDA_OK(cudaStreamWaitEvent(st, ov.built[buf], 0));
+            }
             const int64_t ntot = ntu2 * ntv2 * G;
             int64_t ncta = 2 * ntot < tc_sm_count() ? 2 * ntot : (tc_sm_count() / 2) * 2;
+            const __half* Pg = Hhi + buf * pbuf;
+            const __half* Qg = Ghi + buf * qbuf;
             static const int t8_shape = [] {      // developer knob: 3 whole stages of 64 KB or 6 / 7 half stages of 32 KB
                 const char* e = getenv("TES_T8_STAGES");
                 return e ? atoi(e) : 3;        // measured at C3: 18.7 ms (3 x 64 KB) / 20.7 ms (6 or 7 x 32 KB)
             }();
             if (t8_shape == 3)
                 prod_gemm_topk_tc8_kernel<0, 3><<<(unsigned)ncta, TC_THREADS, 3 * T8_STAGE_BYTES + 256, st>>>(
-                    Hhi, Ghi, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
+                    Pg, Qg, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
             else if (t8_shape == 6)
                 prod_gemm_topk_tc8_kernel<1, 6><<<(unsigned)ncta, TC_THREADS, 6 * T8_STAGE_BYTES / 2 + 256, st>>>(
-                    Hhi, Ghi, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
+                    Pg, Qg, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
             else
                 prod_gemm_topk_tc8_kernel<1, 7><<<(unsigned)ncta, TC_THREADS, 7 * T8_STAGE_BYTES / 2 + 256, st>>>(
-                    Hhi, Ghi, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
+                    Pg, Qg, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
             TES_LAUNCH_OK();
+            if (ov.on) TES_CUDA_OK(cudaEventRecord(ov.freed[buf], st));
         } else if (tf32 == 6) {
             const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK, ntu2 = (ntu + 1) / 2;
             // P: 128-row tiles, 2 ntu2 of them per sample (an odd count is padded with the zero tile of the memset);
