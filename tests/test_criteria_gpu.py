@@ -270,6 +270,25 @@ def test_tes_ep_screen_bound_holds(hyp, d, n, T, nx, mode):
     assert err.max() < 1e-4 * max(1.0, np.abs(exact[fin]).max())
 
 
+def test_tes_ep_screen_fp32_bound_dominates_fp64_bound(monkeypatch):
+    """The bound H = sum_a |M_a| sqrt(Sigma_aa) is formed on the fp32 pipe inside ep_det_screen_h_kernel (operands rounded
+    up, result inflated by the fp32 summation error); TES_SCREEN_H=0 selects the fp64 GEMM.  eps(fp32) >= eps(fp64) on
+    every candidate and at most 1e-4 relative above it; the screen values agree to rounding."""
+    from tes_b200 import ops
+    pr = make_problem(seed=23, d=6, n=30, T=37, nx=9_001, hyp=HART6, mode="empirical", nsample=1500)
+    p, pm, pc = _ep_inputs(pr)
+    run = lambda: [t.cpu().numpy() for t in ops.ep_acq_screen(  # noqa: E731
+        pr["x"], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"], pr["invpNK"][0], pr["invK"][0], p, pc)]
+    a32, e32 = run()
+    monkeypatch.setenv("TES_SCREEN_H", "0")
+    a64, e64 = run()
+    np.testing.assert_allclose(a32, a64, rtol=1e-12, atol=1e-13)
+    fin = np.isfinite(e64)
+    assert np.array_equal(fin, np.isfinite(e32))
+    assert np.all(e32[fin] >= e64[fin] * (1 - 1e-12))
+    assert np.all(e32[fin] <= e64[fin] * (1 + 1e-4) + 1e-18)
+
+
 def test_tes_step_with_screen_selects_the_same_query():
     """acquisition.tes_step with the screened criterion (candidates that can still be the arg-max re-evaluated in fp64)
     returns the same query index, point and VALUE as the fp64 criterion on all candidates."""

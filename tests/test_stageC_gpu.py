@@ -302,6 +302,33 @@ def test_device_ep_vs_oracle(T, nhyp, max_niter, res):
     assert int(nit.min()) >= 1
 
 
+def test_device_ep_kernels_agree(monkeypatch):
+    """T <= 32 has three engines (csrc/ep.cu): four warps per maximizer (default), one warp, one CTA; same pivot rule
+    and element arithmetic, so the moments agree to rounding and the iteration counts are identical."""
+    from tes_b200 import ops
+    rs = np.random.RandomState(30)
+    T, d = 30, 2
+    xs = rs.rand(T, d) * 4.0
+    X, Y = rs.rand(6, d) * 4.0, rs.randn(6, 1)
+    l = np.array([3.0, 5.0])
+    invK = onp.precomputeInvKs(l.reshape(1, d), np.array([1.0]), np.array([1e-2]), X)
+    m, c = onp.compute_mean_var_f(xs, X, Y, l, 1.0, 1e-2, invK[0], fullcov=True)
+    means, covs = m.reshape(1, T), (c + 1e-6 * np.eye(T))[None]
+    res = {}
+    for mode in ("0", "3", "1"):
+        monkeypatch.setenv("TES_EP_MODE", mode)
+        pm, pc, nit = ops.ep_moments(means, covs, 1e-9, 100, return_niter=True)
+        res[mode] = (pm.cpu().numpy(), pc.cpu().numpy(), nit.cpu().numpy())
+    for mode in ("3", "1"):
+        np.testing.assert_array_equal(res[mode][2], res["0"][2])
+        np.testing.assert_allclose(res[mode][0], res["0"][0], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(res[mode][1], res["0"][1], rtol=1e-10, atol=1e-12)
+    j = 7
+    om, oc = onp.approximate_EP(j, means[0].reshape(-1, 1), covs[0], 1e-9, 100)
+    np.testing.assert_allclose(res["0"][0][0, j], om.squeeze(), rtol=0, atol=2e-8)
+    np.testing.assert_allclose(res["0"][1][0, j], oc, rtol=0, atol=2e-8 * np.abs(covs).max())
+
+
 def test_device_ep_mode_through_get_testidxs_stats_cuda_tensors(golden):
     from tes_b200 import utils
     g = golden("maximizer_stats")

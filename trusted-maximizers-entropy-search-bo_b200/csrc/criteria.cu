@@ -720,11 +720,16 @@ namespace tes {
 constexpr double QS_ETA = 4.0e-5;
 constexpr double QS_ABS = 1.5 * 4104.0 * 2.98023223876953125e-08 / 32768.0;
 // D[a][j] = sqrt(Sigma_j[a][a]); one CTA per maximizer j checks Sigma_ab^2 <= Sigma_aa Sigma_bb for every pair (the
-// inequality the h-bound rests on) and a non-negative diagonal, else the whole column of D is +inf
+// inequality the h-bound rests on) and a non-negative diagonal, else the whole column of D is +inf.  Df (optional):
+// the same factor as floats ROUNDED UP, T x 128 with the columns j >= Sp zero (operand of ep_det_screen_h_kernel).
 __global__ void __launch_bounds__(256) screen_diag_kernel(const double* __restrict__ cov, int64_t Sp, int64_t T,
-                                                          double* __restrict__ D) {
+                                                          double* __restrict__ D, float* __restrict__ Df) {
     __shared__ int bad;
     const int64_t j = blockIdx.x;
+    if (j >= Sp) {                                     // zero padding columns of Df (grid = 128 in that mode)
+        for (int64_t a = threadIdx.x; a < T; a += blockDim.x) Df[a * 128 + j] = 0.f;
+        return;
+    }
     const double* c = cov + j * T * T;
     if (threadIdx.x == 0) bad = 0;
     __syncthreads();
@@ -738,8 +743,11 @@ __global__ void __launch_bounds__(256) screen_diag_kernel(const double* __restri
     if (mybad) bad = 1;
     __syncthreads();
     const int isbad = bad;
-    for (int64_t a = threadIdx.x; a < T; a += blockDim.x)
-        D[a * Sp + j] = isbad ? pos_inf() : sqrt(c[a * T + a]);
+    for (int64_t a = threadIdx.x; a < T; a += blockDim.x) {
+        const double v = isbad ? pos_inf() : sqrt(c[a * T + a]);
+        D[a * Sp + j] = v;
+        if (Df) Df[a * 128 + j] = __double2float_ru(v * (1.0 + 1e-15));   // >= the exact root (sqrt is within 1/2 ulp)
+    }
 }
 __global__ void abs_rows_kernel(const double* __restrict__ G, int64_t ldg, int64_t rows, int64_t T,
                                 double* __restrict__ out) {
@@ -777,6 +785,96 @@ __global__ void ep_det_screen_kernel(const double* __restrict__ Qt, const double
         out_eps[row] = er / (double)Sp + 1e-13 * fabs(a);   // + rounding slack of the two fp64 evaluations
     }
 }
+
+// The same, with the bound H computed HERE on the fp32 pipe instead of by abs_rows_kernel + an fp64 GEMM: H only has to
+// be an UPPER bound of sum_a |M[x,a]| sqrt(Sigma_j[a][a]).  |M| and the roots are rounded UP to floats, the T-term
+// fp32 sum of non-negative products loses at most (T + 1) 2^-24 of its value (and 1.4e-45 per product that underflows):
+// H = fl32(sum) * (1 + 2e-5) + 1e-40 >= the exact sum for T <= 256.  Overflow gives +inf, i.e. eps = +inf (no pruning).
+// A warp owns 4 candidate rows (their |M| as [a][4] floats in shared memory: one broadcast LDS.128 per a) and lane l
+// the maximizer columns 4l .. 4l+3 (Df row a: one conflict-free LDS.128): 16 FFMA per two shared loads.
+constexpr int EDS_WARPS = 16;
+constexpr int EDS_ROWS = 4;
+__global__ void __launch_bounds__(EDS_WARPS * 32) ep_det_screen_h_kernel(
+    const double* __restrict__ Qt, const double* __restrict__ Kq, const double* __restrict__ G, int64_t ldg, int T,
+    const float* __restrict__ Df, const double* __restrict__ varf, const double* __restrict__ p, int64_t rows, int Sp,
+    double sigma0, const double* __restrict__ rowmax, const double* __restrict__ colmax, double kabs,
+    double* __restrict__ out_acq, double* __restrict__ out_eps) {
+    extern __shared__ __align__(16) float eds_sm[];
+    float* Ds = eds_sm;                                            // [T][128]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* Ms = eds_sm + (size_t)T * 128 + (size_t)wid * T * EDS_ROWS;   // [T][4]
+    for (int e = threadIdx.x; e < T * 32; e += blockDim.x)
+        reinterpret_cast<float4*>(Ds)[e] = reinterpret_cast<const float4*>(Df)[e];
+    double pj[4], cm[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int j = 4 * lane + c;
+        pj[c] = j < Sp ? p[j] : 0.0;
+        cm[c] = j < Sp ? colmax[j] : 0.0;
+    }
+    __syncthreads();
+    const int64_t ngroups = (rows + EDS_ROWS - 1) / EDS_ROWS;
+    for (int64_t g = (int64_t)blockIdx.x * EDS_WARPS + wid; g < ngroups; g += (int64_t)gridDim.x * EDS_WARPS) {
+        const int64_t r0 = g * EDS_ROWS;
+        {
+            const double* g0 = G + (r0 + 0 < rows ? r0 + 0 : rows - 1) * ldg;
+            const double* g1 = G + (r0 + 1 < rows ? r0 + 1 : rows - 1) * ldg;
+            const double* g2 = G + (r0 + 2 < rows ? r0 + 2 : rows - 1) * ldg;
+            const double* g3 = G + (r0 + 3 < rows ? r0 + 3 : rows - 1) * ldg;
+            for (int a = lane; a < T; a += 32)
+                *reinterpret_cast<float4*>(Ms + a * EDS_ROWS) =
+                    make_float4(__double2float_ru(fabs(g0[a])), __double2float_ru(fabs(g1[a])),
+                                __double2float_ru(fabs(g2[a])), __double2float_ru(fabs(g3[a])));
+        }
+        __syncwarp();
+        float acc[EDS_ROWS][4];
+#pragma unroll
+        for (int r = 0; r < EDS_ROWS; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+        for (int a = 0; a < T; ++a) {
+            const float4 mv = *reinterpret_cast<const float4*>(Ms + a * EDS_ROWS);
+            const float4 dv = *reinterpret_cast<const float4*>(Ds + a * 128 + 4 * lane);
+            const float mr[4] = {mv.x, mv.y, mv.z, mv.w};
+            const float dc[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int r = 0; r < EDS_ROWS; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(mr[r], dc[c], acc[r][c]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < EDS_ROWS; ++r) {
+            const int64_t row = r0 + r;
+            if (row >= rows) break;                    // uniform over the warp
+            const double kq = Kq[row];
+            const double rm = rowmax[row];
+            const double ra = kabs * rm * rm;
+            double s = 0.0, er = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = 4 * lane + c;
+                if (j < Sp) {
+                    const double h = (double)acc[r][c] * (1.0 + 2e-5) + 1e-40;
+                    const double w = (kq + Qt[row * Sp + j]) + sigma0;
+                    const double delta = (QS_ETA * h * h + ra * cm[c]) + 1e-300;
+                    s += ((NORM_ENTROPY_CONST + log(sqrt(w))) + 0.5) * pj[c];
+                    const double e1 = (w > delta) ? 0.5 * log(w / (w - delta)) : pos_inf();   // NaN w -> +inf
+                    er += e1 * pj[c];
+                }
+            }
+            s = warp_sum(s);
+            er = warp_sum(er);
+            if (lane == 0) {
+                const double ent = (NORM_ENTROPY_CONST + log(sqrt(varf[row] + sigma0))) + 0.5;
+                const double a = ent - s / (double)Sp;
+                out_acq[row] = a;
+                out_eps[row] = er / (double)Sp + 1e-13 * fabs(a);
+            }
+        }
+    }
+}
 }  // namespace tes
 
 extern "C" int64_t tes_ep_acq_screen_workspace_bytes(int64_t N, int64_t T, int64_t n, int64_t d, int64_t Sp) {
@@ -784,7 +882,8 @@ extern "C" int64_t tes_ep_acq_screen_workspace_bytes(int64_t N, int64_t T, int64
     EpPlan pl = ep_plan(N, T, n, d, Sp, PS_SCREEN_CHUNK);
     const int64_t Ks = quad_screen_kdim(T);
     return pl.total + quad_screen_a_bytes(pl.nc, Ks) + quad_screen_b_bytes(Ks) + align_up(pl.nc * 8, 256) +
-           align_up(T * Sp * 8, 256) + align_up(pl.nc * T * 8, 256) + align_up(Ks * Sp * 8, 256);
+           align_up(T * Sp * 8, 256) + align_up(pl.nc * T * 8, 256) + align_up(Ks * Sp * 8, 256) +
+           align_up(T * 128 * 4, 256);
 }
 
 extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, const double* test_xs, int64_t T,
@@ -830,14 +929,23 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
     double* absM = (double*)extra;
     extra += align_up(pl.nc * T * 8, 256);
     double* Bscr = (double*)extra;                   // Ks x Sp
+    extra += align_up(Ks * Sp * 8, 256);
+    float* Df = (float*)extra;                       // T x 128 floats, rounded up
     double* Hb = (double*)(base + pl.off_mean);      // nc x Sp (the mean buffer is unused in this mode)
+    // bound H on the fp32 pipe inside the criterion kernel whenever its operands fit in shared memory
+    const size_t eds_smem = ((size_t)T * 128 + (size_t)EDS_WARPS * T * EDS_ROWS) * sizeof(float);
+    const char* hmode = std::getenv("TES_SCREEN_H");
+    const bool fuse_h = eds_smem <= 200 * 1024 && !(hmode && hmode[0] == '0');
+    if (fuse_h)
+        TES_CUDA_OK(cudaFuncSetAttribute(ep_det_screen_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)eds_smem));
     const int64_t m = pl.m;
     int rc;
     if ((rc = launch_concat_rows(test_xs, T, X, n, (int)d, xto, st))) return rc;
     if ((rc = launch_build_bext(invpNK, Y, m, T, Bext, st))) return rc;
     if ((rc = launch_quad_screen_ab(post_cov, Sp, T, colmax, Bscr, st))) return rc;
     if ((rc = launch_quad_screen_build_b(Bscr, Ks, Sp, Btc, colmax, st))) return rc;
-    screen_diag_kernel<<<(unsigned)Sp, 256, 0, st>>>(post_cov, Sp, T, Dm);
+    screen_diag_kernel<<<fuse_h ? 128u : (unsigned)Sp, 256, 0, st>>>(post_cov, Sp, T, Dm, fuse_h ? Df : nullptr);
     TES_LAUNCH_OK();
     const double kabs = QS_ABS * (double)quad_screen_kp(Ks);
     for (int64_t c0 = 0; c0 < N; c0 += PS_SCREEN_CHUNK) {
@@ -848,6 +956,17 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
         if ((rc = launch_quad_screen(Gc, m + 1, nc, T, Ks, Btc, colmax, Sp, Atc, rowmax, varc, st))) return rc;
         if ((rc = launch_gemm(Kc + T, m, invKobs, n, 1, Gobs, n, nc, n, n, st))) return rc;
         if ((rc = launch_rowdot(Gobs, n, Kc + T, m, nc, n, sigma, 1e-100, varf, st))) return rc;
+        if (fuse_h) {
+            const int64_t ngroups = (nc + EDS_ROWS - 1) / EDS_ROWS;
+            int64_t grid = (ngroups + EDS_WARPS - 1) / EDS_WARPS;
+            const int64_t cap = 148 * (int64_t)(eds_smem <= 110 * 1024 ? 2 : 1);
+            if (grid > cap) grid = cap;
+            ep_det_screen_h_kernel<<<(unsigned)grid, EDS_WARPS * 32, eds_smem, st>>>(
+                varc, Kq, Gc, m + 1, (int)T, Df, varf, p, nc, (int)Sp, sigma0, rowmax, colmax, kabs, out_acq + c0,
+                out_eps + c0);
+            TES_LAUNCH_OK();
+            continue;
+        }
         abs_rows_kernel<<<(unsigned)((nc * T + 255) / 256), 256, 0, st>>>(Gc, m + 1, nc, T, absM);
         TES_LAUNCH_OK();
         if ((rc = launch_gemm(absM, T, Dm, Sp, 1, Hb, Sp, nc, Sp, T, st))) return rc;

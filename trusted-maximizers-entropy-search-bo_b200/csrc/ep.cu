@@ -522,6 +522,248 @@ __global__ void __launch_bounds__(128) ep_warp_kernel(const double* __restrict__
     if (lane == 0 && niter) niter[hy * T + j] = count;
 }
 
+
+// ---- T <= 32: FOUR warps per maximizer, ping-pong matrices in shared memory -----------------------------------------
+// The one-warp kernel above is a single dependent instruction stream: ~500 instructions per Gauss-Jordan step (64-bit
+// shuffles for the multipliers, predicated register selects for rows k / p), 47 us per EP iteration at T = 30.  Here
+// a CTA of 128 threads owns one maximizer: lane = column, warp w owns the rows w, w + 4, ...; a step READS the matrix
+// from one shared buffer and WRITES every row of the next one (row exchange folded into the read), so ONE block barrier
+// per step suffices.  Every warp finds the pivot redundantly (lane i looks at a[i][k]; two REDUX.MAX on the halves of
+// |a| as an integer key + a ballot = first maximum, NaN counted as +inf: the rule of gj_inverse), every lane divides
+// 1 / a[lane][k] while the reduction is in flight and the winner's quotient is broadcast.  Per-element arithmetic is
+// that of gj_inverse.  The constant Sigma^-1 and h = Sigma^-1 mu are computed by the same routine inside the kernel
+// (no prepare launch); 1/site_var terms are cached per site (one site changes per iteration).
+constexpr int EPQ_LD = 33;
+constexpr int EPQ_MAT = 32 * EPQ_LD;
+
+// inverse of the n x n matrix in cur (n <= 32); returns the buffer (cur or nxt) that holds it.  All 128 threads call.
+// The step is branch-free: every thread updates its 8 rows of the full 32 x 32 array (the padding rows / columns
+// beyond n are inert: they never enter the pivot search and nothing in the n x n block reads them), row k is written
+// afterwards by its owner, the column-k entries -f * rkn come out of the same fma with a zero addend.
+__device__ __forceinline__ double* gj_inverse_quad(double* cur, double* nxt, int n, int lane, int w) {
+    int Q = lane;                 // where column `lane` of the working matrix ends up (row interchanges undone as
+                                  // column interchanges, composed forward: Q_k = t_0 o t_1 o ... o t_k)
+    const int lrow = lane * EPQ_LD, wrow = w * EPQ_LD;
+#pragma unroll 1
+    for (int k = 0; k < n; ++k) {
+        const double ck = cur[lrow + k];                                   // a[lane][k]
+        const bool inr = lane < n && lane >= k;
+        const double av = fabs(ck);
+        const unsigned long long key = av == av ? (unsigned long long)__double_as_longlong(av) : 0x7ff0000000000000ULL;
+        const unsigned hi = inr ? (unsigned)(key >> 32) : 0u, lo = inr ? (unsigned)key : 0u;
+        const double ipc = 1.0 / ck;
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, (inr && hi == mh) ? lo : 0u);
+        const unsigned bal = __ballot_sync(0xffffffffu, inr && hi == mh && lo == ml);
+        const int p = __ffs(bal) - 1;                                      // pivot row (>= k)
+        const int koff = k * EPQ_LD, poff = p * EPQ_LD;
+        const double rp = cur[poff + lane];
+        const double ipv = __shfl_sync(0xffffffffu, ipc, p);
+        const double rkn = (lane == k ? 1.0 : rp) * ipv;                   // the normalised row k
+        const double nrkn = -rkn;
+        const int qk = __shfl_sync(0xffffffffu, Q, k), qp = __shfl_sync(0xffffffffu, Q, p);
+        Q = lane == k ? qp : (lane == p ? qk : Q);
+        double f[8], v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int ioff = wrow + 4 * r * EPQ_LD;
+            const int soff = ioff == poff ? koff : ioff;                   // rows k and p exchanged
+            f[r] = cur[soff + k];
+            v[r] = cur[soff + lane];
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) nxt[wrow + 4 * r * EPQ_LD + lane] = fma(f[r], nrkn, lane == k ? 0.0 : v[r]);
+        if ((k & 3) == w) nxt[koff + lane] = rkn;
+        __syncthreads();
+        double* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) nxt[wrow + 4 * r * EPQ_LD + Q] = cur[wrow + 4 * r * EPQ_LD + lane];
+    __syncthreads();
+    return nxt;
+}
+
+__global__ void __launch_bounds__(128) ep_quad_kernel(const double* __restrict__ mean_all,
+                                                      const double* __restrict__ cov_all, int T, double resolution,
+                                                      int max_niter, double* __restrict__ post_mean,
+                                                      double* __restrict__ post_cov, int* __restrict__ niter) {
+    __shared__ double buf[4][EPQ_MAT];
+    __shared__ double a_mean[32], n_mean[32], rhs[32], hv[32], site_m[32], site_v[32], new_m[32], new_v[32], wwv[32],
+        qv[32], red[4], scal[2];
+    __shared__ int ctl[2], nanw[4];        // count, stop; NaN flag of each warp
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int j = (int)(blockIdx.x % (unsigned)T);
+    const int64_t hy = blockIdx.x / (unsigned)T;
+    const double* mu = mean_all + hy * T;
+    const double* Sg = cov_all + hy * T * T;
+
+    // Sigma^-1 and h = Sigma^-1 mu (the padding of all four buffers is zero and stays zero)
+    for (int e = tid; e < 4 * EPQ_MAT; e += 128) (&buf[0][0])[e] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = w + 4 * r;
+        if (i < T && lane < T) buf[0][i * EPQ_LD + lane] = Sg[(int64_t)i * T + lane];
+    }
+    if (tid < T - 1) {            // site initialisation (ep.py:107-108): c^T mu and diag(c^T Sigma c)
+        const int o = ep_other(tid, j);
+        const double sm = mu[j] - mu[o];
+        const double sv = (Sg[(int64_t)j * T + j] - Sg[(int64_t)o * T + j]) - (Sg[(int64_t)j * T + o] - Sg[(int64_t)o * T + o]);
+        site_m[tid] = sm;
+        site_v[tid] = sv;
+        const double iw = 1.0 / sqrt(sv);          // the reference forms cs / sqrt(site_vars): negative -> NaN
+        wwv[tid] = iw * iw;
+        qv[tid] = sm / sv;
+    }
+    if (tid == 0) ctl[0] = ctl[1] = 0;
+    __syncthreads();
+    double* IC = gj_inverse_quad(buf[0], buf[1], T, lane, w);
+    double* f0 = IC == buf[0] ? buf[1] : buf[0];
+    double* f1 = buf[2];
+    double* f2 = buf[3];
+    if (tid < T) {
+        double s = 0.0;
+        for (int k = 0; k < T; ++k) s = fma(IC[tid * EPQ_LD + k], mu[k], s);
+        hv[tid] = s;
+    }
+
+    // system matrix M = Sigma^-1 + C diag(1/site_var) C^T into F, rhs = h + C (site_mean / site_var); then F^-1 and
+    // the mean; returns the buffer with the inverse, *other = the second buffer used
+    auto refresh = [&](double* F, double* G2, double* out_mean, double** other) -> double* {
+        if (tid == 0) {
+            double sw = 0.0;
+            for (int c = 0; c < T - 1; ++c) sw += wwv[c];
+            scal[0] = sw;
+        } else if (tid == 32) {
+            double sr = 0.0;
+            for (int c = 0; c < T - 1; ++c) sr += qv[c];
+            scal[1] = sr;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = w + 4 * r;
+            if (i < T && lane < T) {
+                double v = IC[i * EPQ_LD + lane];
+                if (lane == j) {
+                    if (i == j) v += scal[0];
+                    else v -= wwv[i < j ? i : i - 1];
+                } else {
+                    const double ww = wwv[lane < j ? lane : lane - 1];
+                    if (i == lane) v += ww;
+                    if (i == j) v -= ww;
+                }
+                F[i * EPQ_LD + lane] = v;
+            }
+        }
+        if (tid < T) rhs[tid] = tid == j ? hv[j] + scal[1] : hv[tid] - qv[tid < j ? tid : tid - 1];
+        __syncthreads();
+        double* R = gj_inverse_quad(F, G2, T, lane, w);
+        *other = R == F ? G2 : F;
+        if (tid < T) {
+            double s = 0.0;
+            for (int k = 0; k < T; ++k) s = fma(R[tid * EPQ_LD + k], rhs[k], s);
+            out_mean[tid] = s;
+        }
+        __syncthreads();
+        return R;
+    };
+    __syncthreads();
+    double* other;
+    double* Cw = refresh(f0, f1, a_mean, &other);     // current approximation
+    f0 = other;                                        // free buffers: f0, f2
+    f1 = f2;
+    double diff = 1e10;
+    int count = 0;
+    while (diff > resolution && count < max_niter) {
+        if (tid < T - 1) {       // cavity (ep.py:31-49), truncated-normal moments (:52-60), site proposal (:63-70)
+            const int c = tid, o = ep_other(c, j);
+            const double ctSc = (Cw[j * EPQ_LD + j] - Cw[o * EPQ_LD + j]) - (Cw[j * EPQ_LD + o] - Cw[o * EPQ_LD + o]);
+            const double ctm = a_mean[j] - a_mean[o];
+            const double cav_v = 1.0 / (1.0 / ctSc - 1.0 / site_v[c]);
+            const double cav_m = cav_v * (ctm / ctSc - site_m[c] / site_v[c]);
+            const double sd = sqrt(cav_v);
+            const double beta = cav_m / sd;
+            const double poc = norm_pdf(beta) / norm_cdf(beta);
+            const double cf_m = cav_m + sd * poc;
+            const double cf_v = -cav_m * sd * poc - cf_m * cf_m + 2.0 * cav_m * cf_m - cav_m * cav_m + cav_v;
+            const double nv = 1.0 / (1.0 / cf_v - 1.0 / cav_v);
+            new_v[c] = nv;
+            new_m[c] = nv * (cf_m / cf_v - cav_m / cav_v);
+        }
+        __syncthreads();
+        if (tid == 0) {          // ep.py:162-172 (see ep_kernel for the termination guard)
+            int cnt = count + 1;
+            int uidx = cnt % (T - 1);
+            const int last = cnt >= 1 ? cnt - 1 : T - 2;
+            int guard = 0, stop = 0;
+            auto bad = [&](int u) {
+                const double v = new_v[u];
+                return v <= 0.0 || v != v || isinf(v);
+            };
+            while (bad(uidx) && uidx != last) {
+                ++cnt;
+                uidx = cnt % (T - 1);
+                if (++guard >= T - 1 && last >= T - 1) {
+                    stop = 1;
+                    break;
+                }
+            }
+            ctl[0] = cnt;
+            ctl[1] = stop;
+            if (!stop) {
+                const double sm = new_m[uidx], sv = new_v[uidx];
+                site_m[uidx] = sm;
+                site_v[uidx] = sv;
+                const double iw = 1.0 / sqrt(sv);
+                wwv[uidx] = iw * iw;
+                qv[uidx] = sm / sv;
+            }
+        }
+        __syncthreads();
+        count = ctl[0];
+        if (ctl[1]) break;
+        double* R = refresh(f0, f1, n_mean, &other);
+        // converge_diff = mean over the (T, T) broadcast of dmean_i^2 + dcov_ik^2 (ep.py:190-193); NaN check
+        double part = 0.0;
+        int nan = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = w + 4 * r;
+            if (i < T && lane < T) {
+                const double dm = n_mean[i] - a_mean[i];
+                const double mv = R[i * EPQ_LD + lane];
+                const double dc = mv - Cw[i * EPQ_LD + lane];
+                part += dm * dm + dc * dc;
+                nan |= (mv != mv) || (n_mean[i] != n_mean[i]);
+            }
+        }
+        part = warp_sum(part);
+        nan = __any_sync(0xffffffffu, nan);
+        if (lane == 0) {
+            red[w] = part;
+            nanw[w] = nan;
+        }
+        __syncthreads();
+        diff = (((red[0] + red[1]) + red[2]) + red[3]) / ((double)T * (double)T);
+        const int anynan = nanw[0] | nanw[1] | nanw[2] | nanw[3];
+        __syncthreads();
+        if (anynan) break;       // ep.py:195-199: keep the previous approximation
+        if (tid < T) a_mean[tid] = n_mean[tid];
+        f0 = other;              // the inverse becomes the approximation, the old approximation a free buffer
+        f1 = Cw;
+        Cw = R;
+        __syncthreads();
+    }
+    __syncthreads();
+    double* a_cov_out = post_cov + (hy * T + j) * (int64_t)T * T;
+    for (int e = tid; e < T * T; e += 128) a_cov_out[e] = Cw[(e / T) * EPQ_LD + e % T];
+    if (tid < T) post_mean[(hy * T + j) * (int64_t)T + tid] = a_mean[tid];
+    if (tid == 0 && niter) niter[hy * T + j] = count;
+}
+
 }  // namespace tes
 
 using namespace tes;
@@ -591,20 +833,25 @@ extern "C" int tes_ep_moments_f64(const double* mean, const double* cov, int64_t
         TES_CUDA_OK(cudaFuncSetAttribute(ep_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_prep));
     if (sm_main > 48 * 1024)
         TES_CUDA_OK(cudaFuncSetAttribute(ep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_main));
+    // developer knob: 0 = four-warp kernel for T <= 32, 3 = one-warp kernel, 1 / 2 = CTA kernel with 512 / 128 threads
+    const char* ep_env = getenv("TES_EP_MODE");
+    const int ep_mode = ep_env ? atoi(ep_env) : 0;
+    if (T <= 32 && ep_mode == 0) {
+        ep_quad_kernel<<<(unsigned)(T * nhyp), 128, 0, st>>>(mean, cov, (int)T, resolution, max_niter, post_mean, post_cov,
+                                                            niter);
+        TES_LAUNCH_OK();
+        return 0;
+    }
     // the prepare step reuses the first nhyp slots of the main kernel's scratch
     ep_prepare_kernel<<<(unsigned)nhyp, EP_THREADS, sm_prep, st>>>(cov, mean, (int)T, inv_cov, h, gscratch, in_smem);
     TES_LAUNCH_OK();
-    static const int ep_mode = [] {                 // developer knob: 0 = warp kernel for T <= 32, 1 / 2 = CTA kernel with 512 / 128 threads
-        const char* e = getenv("TES_EP_MODE");
-        return e ? atoi(e) : 0;
-    }();
     if (ep_mode == 2) {
         ep_kernel<<<dim3((unsigned)T, (unsigned)nhyp), 128, sm_main, st>>>(mean, cov, inv_cov, h, (int)T, resolution, max_niter,
                                                                           post_mean, post_cov, niter, gscratch, in_smem);
         TES_LAUNCH_OK();
         return 0;
     }
-    if (T <= EPW && ep_mode == 0) {
+    if (T <= EPW && ep_mode == 3) {
         // one warp per maximizer, the system matrix in registers (no block barriers); two warps per CTA so that the
         // maximizers spread over the SMs
         const int wpb = 2;
