@@ -273,7 +273,7 @@ def test_tes_ep_screen_bound_holds(hyp, d, n, T, nx, mode):
 def test_tes_ep_screen_fp32_bound_dominates_fp64_bound(monkeypatch):
     """The bound H = sum_a |M_a| sqrt(Sigma_aa) is formed on the fp32 pipe inside ep_det_screen_h_kernel (operands rounded
     up, result inflated by the fp32 summation error); TES_SCREEN_H=0 selects the fp64 GEMM.  eps(fp32) >= eps(fp64) on
-    every candidate and at most 1e-4 relative above it; the screen values agree to rounding."""
+    every candidate and within 2 % of it; the screen values agree to rounding."""
     from tes_b200 import ops
     pr = make_problem(seed=23, d=6, n=30, T=37, nx=9_001, hyp=HART6, mode="empirical", nsample=1500)
     p, pm, pc = _ep_inputs(pr)
@@ -286,7 +286,11 @@ def test_tes_ep_screen_fp32_bound_dominates_fp64_bound(monkeypatch):
     fin = np.isfinite(e64)
     assert np.array_equal(fin, np.isfinite(e32))
     assert np.all(e32[fin] >= e64[fin] * (1 - 1e-12))
-    assert np.all(e32[fin] <= e64[fin] * (1 + 1e-4) + 1e-18)
+    # ... and not much looser: the fused kernel also replaces 1/2 log(w / (w - delta)) by 1/2 delta / (w - delta) and adds
+    # 1e-13 of the summed |terms| instead of 1e-13 |acq|
+    small = fin & (e64 < 1e-2)
+    assert small.mean() > 0.9
+    assert np.all(e32[small] <= e64[small] * 1.02 + 1e-11)
 
 
 def test_tes_step_with_screen_selects_the_same_query():

@@ -794,11 +794,11 @@ __global__ void ep_det_screen_kernel(const double* __restrict__ Qt, const double
 // the maximizer columns 4l .. 4l+3 (Df row a: one conflict-free LDS.128): 16 FFMA per two shared loads.
 constexpr int EDS_WARPS = 16;
 constexpr int EDS_ROWS = 4;
-__global__ void __launch_bounds__(EDS_WARPS * 32) ep_det_screen_h_kernel(
-    const double* __restrict__ Qt, const double* __restrict__ Kq, const double* __restrict__ G, int64_t ldg, int T,
-    const float* __restrict__ Df, const double* __restrict__ varf, const double* __restrict__ p, int64_t rows, int Sp,
-    double sigma0, const double* __restrict__ rowmax, const double* __restrict__ colmax, double kabs,
-    double* __restrict__ out_acq, double* __restrict__ out_eps) {
+__global__ void __launch_bounds__(EDS_WARPS * 32, 2) ep_det_screen_h_kernel(
+    const double* __restrict__ Qt, const double* __restrict__ G, int64_t ldg, const double* __restrict__ Kc, int64_t ldk,
+    const double* __restrict__ Gobs, int T, int m, int n, double sigma, const float* __restrict__ Df,
+    const double* __restrict__ p, int64_t rows, int Sp, double sigma0, const double* __restrict__ rowmax,
+    const double* __restrict__ colmax, double kabs, double* __restrict__ out_acq, double* __restrict__ out_eps) {
     extern __shared__ __align__(16) float eds_sm[];
     float* Ds = eds_sm;                                            // [T][128]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -816,15 +816,38 @@ __global__ void __launch_bounds__(EDS_WARPS * 32) ep_det_screen_h_kernel(
     const int64_t ngroups = (rows + EDS_ROWS - 1) / EDS_ROWS;
     for (int64_t g = (int64_t)blockIdx.x * EDS_WARPS + wid; g < ngroups; g += (int64_t)gridDim.x * EDS_WARPS) {
         const int64_t r0 = g * EDS_ROWS;
+        // one pass over the rows of G = K [invpNK | w] and K: the |M| tile, and the two row dots of the criterion
+        //   kq = sigma - sum_c G[x][c] K[x][c]  (c < m),  varf = max(sigma - sum_c Gobs[x][c] K[x][T + c], 1e-100)
+        // in the summation order of rowdot_kernel (lane-strided fma chain, butterfly) -> the bits of the fp64 criterion
+        double kq4[EDS_ROWS], vf4[EDS_ROWS];
         {
-            const double* g0 = G + (r0 + 0 < rows ? r0 + 0 : rows - 1) * ldg;
-            const double* g1 = G + (r0 + 1 < rows ? r0 + 1 : rows - 1) * ldg;
-            const double* g2 = G + (r0 + 2 < rows ? r0 + 2 : rows - 1) * ldg;
-            const double* g3 = G + (r0 + 3 < rows ? r0 + 3 : rows - 1) * ldg;
-            for (int a = lane; a < T; a += 32)
-                *reinterpret_cast<float4*>(Ms + a * EDS_ROWS) =
-                    make_float4(__double2float_ru(fabs(g0[a])), __double2float_ru(fabs(g1[a])),
-                                __double2float_ru(fabs(g2[a])), __double2float_ru(fabs(g3[a])));
+            int64_t rr[EDS_ROWS];
+#pragma unroll
+            for (int r = 0; r < EDS_ROWS; ++r) rr[r] = r0 + r < rows ? r0 + r : rows - 1;
+            double sk[EDS_ROWS] = {0.0, 0.0, 0.0, 0.0}, sv[EDS_ROWS] = {0.0, 0.0, 0.0, 0.0};
+            for (int c = lane; c < m; c += 32) {
+                double g[EDS_ROWS];
+#pragma unroll
+                for (int r = 0; r < EDS_ROWS; ++r) {
+                    g[r] = G[rr[r] * ldg + c];
+                    sk[r] = fma(g[r], Kc[rr[r] * ldk + c], sk[r]);
+                }
+                if (c < T)
+                    *reinterpret_cast<float4*>(Ms + c * EDS_ROWS) =
+                        make_float4(__double2float_ru(fabs(g[0])), __double2float_ru(fabs(g[1])),
+                                    __double2float_ru(fabs(g[2])), __double2float_ru(fabs(g[3])));
+            }
+            for (int c = lane; c < n; c += 32) {
+#pragma unroll
+                for (int r = 0; r < EDS_ROWS; ++r) sv[r] = fma(Gobs[rr[r] * n + c], Kc[rr[r] * ldk + T + c], sv[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < EDS_ROWS; ++r) {
+                kq4[r] = sigma - warp_sum(sk[r]);
+                double v = sigma - warp_sum(sv[r]);
+                if (v < 1e-100) v = 1e-100;
+                vf4[r] = v;
+            }
         }
         __syncwarp();
         float acc[EDS_ROWS][4];
@@ -848,10 +871,13 @@ __global__ void __launch_bounds__(EDS_WARPS * 32) ep_det_screen_h_kernel(
         for (int r = 0; r < EDS_ROWS; ++r) {
             const int64_t row = r0 + r;
             if (row >= rows) break;                    // uniform over the warp
-            const double kq = Kq[row];
+            const double kq = kq4[r];
             const double rm = rowmax[row];
             const double ra = kabs * rm * rm;
-            double s = 0.0, er = 0.0;
+            // screen arithmetic (cheaper than the criterion's own sequence, covered by the bound):
+            //   log(sqrt(w)) as 0.5 log(w)   -- differs by rounding only: 1e-13 (|ent| + sum |term| p / Sp) of slack
+            //   1/2 log(w / (w - delta)) <= 1/2 delta / (w - delta)   (-log(1 - t) <= t / (1 - t), t = delta / w)
+            double s = 0.0, er = 0.0, sabs = 0.0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int j = 4 * lane + c;
@@ -859,18 +885,21 @@ __global__ void __launch_bounds__(EDS_WARPS * 32) ep_det_screen_h_kernel(
                     const double h = (double)acc[r][c] * (1.0 + 2e-5) + 1e-40;
                     const double w = (kq + Qt[row * Sp + j]) + sigma0;
                     const double delta = (QS_ETA * h * h + ra * cm[c]) + 1e-300;
-                    s += ((NORM_ENTROPY_CONST + log(sqrt(w))) + 0.5) * pj[c];
-                    const double e1 = (w > delta) ? 0.5 * log(w / (w - delta)) : pos_inf();   // NaN w -> +inf
+                    const double term = ((NORM_ENTROPY_CONST + 0.5 * log(w)) + 0.5) * pj[c];
+                    s += term;
+                    sabs += fabs(term);
+                    const double e1 = (w > delta) ? 0.5 * delta / (w - delta) : pos_inf();   // NaN w -> +inf
                     er += e1 * pj[c];
                 }
             }
             s = warp_sum(s);
             er = warp_sum(er);
+            sabs = warp_sum(sabs);
             if (lane == 0) {
-                const double ent = (NORM_ENTROPY_CONST + log(sqrt(varf[row] + sigma0))) + 0.5;
+                const double ent = (NORM_ENTROPY_CONST + 0.5 * log(vf4[r] + sigma0)) + 0.5;
                 const double a = ent - s / (double)Sp;
                 out_acq[row] = a;
-                out_eps[row] = er / (double)Sp + 1e-13 * fabs(a);
+                out_eps[row] = er / (double)Sp * (1.0 + 1e-12) + 1e-13 * (fabs(ent) + sabs / (double)Sp);
             }
         }
     }
@@ -952,18 +981,18 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
         const int64_t nc = (N - c0 < PS_SCREEN_CHUNK) ? (N - c0) : PS_SCREEN_CHUNK;
         if ((rc = launch_se_ard(x + c0 * d, nc, xto, m, (int)d, l, sigma, -1, 0.0, Kc, m, st))) return rc;
         if ((rc = launch_gemm(Kc, m, Bext, m + 1, 1, Gc, m + 1, nc, m + 1, m, st))) return rc;
-        if ((rc = launch_rowdot(Gc, m + 1, Kc, m, nc, m, sigma, -INFINITY, Kq, st))) return rc;
+        if (!fuse_h && (rc = launch_rowdot(Gc, m + 1, Kc, m, nc, m, sigma, -INFINITY, Kq, st))) return rc;
         if ((rc = launch_quad_screen(Gc, m + 1, nc, T, Ks, Btc, colmax, Sp, Atc, rowmax, varc, st))) return rc;
         if ((rc = launch_gemm(Kc + T, m, invKobs, n, 1, Gobs, n, nc, n, n, st))) return rc;
-        if ((rc = launch_rowdot(Gobs, n, Kc + T, m, nc, n, sigma, 1e-100, varf, st))) return rc;
+        if (!fuse_h && (rc = launch_rowdot(Gobs, n, Kc + T, m, nc, n, sigma, 1e-100, varf, st))) return rc;
         if (fuse_h) {
             const int64_t ngroups = (nc + EDS_ROWS - 1) / EDS_ROWS;
             int64_t grid = (ngroups + EDS_WARPS - 1) / EDS_WARPS;
             const int64_t cap = 148 * (int64_t)(eds_smem <= 110 * 1024 ? 2 : 1);
             if (grid > cap) grid = cap;
             ep_det_screen_h_kernel<<<(unsigned)grid, EDS_WARPS * 32, eds_smem, st>>>(
-                varc, Kq, Gc, m + 1, (int)T, Df, varf, p, nc, (int)Sp, sigma0, rowmax, colmax, kabs, out_acq + c0,
-                out_eps + c0);
+                varc, Gc, m + 1, Kc, m, Gobs, (int)T, (int)m, (int)n, sigma, Df, p, nc, (int)Sp, sigma0, rowmax, colmax,
+                kabs, out_acq + c0, out_eps + c0);
             TES_LAUNCH_OK();
             continue;
         }

@@ -38,11 +38,13 @@ __global__ void se_ard_kernel(const double* __restrict__ x, int64_t N, const dou
     out[i * ldo + c] = v;
 }
 
-// Tiled form for d <= SE_MAXD: a CTA owns 32 rows x 32 columns; sqrt(l), the scaled coordinates and the squared norms
+// Tiled form for d <= SE_MAXD: a CTA owns 128 (or 32) rows x 32 columns (a thread keeps its column's scaled coordinates in
+// registers, the row's come as shared-memory broadcasts); sqrt(l), the scaled coordinates and the squared norms
 // of its rows and columns are formed ONCE in shared memory (the kernel above recomputes d square roots and both norms
 // for every element), then every element is d FMAs and one exp.  Same operations in the same order per element, so
 // the values are the bits of se_ard_kernel (tests/test_stageB_gpu.py compares both).
-constexpr int SE_MAXD = 16, SE_ROWS = 32;
+constexpr int SE_MAXD = 16;
+template <int SE_ROWS>
 __global__ void __launch_bounds__(256)
     se_ard_tile_kernel(const double* __restrict__ x, int64_t N, const double* __restrict__ xb, int64_t m, int d,
                        const double* __restrict__ l, double sigma, int64_t noise_from, double sigma0,
@@ -76,12 +78,17 @@ __global__ void __launch_bounds__(256)
     const int64_t c = c0 + tx;
     if (c >= m) return;
     const double qb = s_qb[tx];
+    double bk[SE_MAXD];
+#pragma unroll
+    for (int k = 0; k < SE_MAXD; ++k) bk[k] = k < d ? s_b[tx][k] : 0.0;
 #pragma unroll 2
     for (int r = ty; r < SE_ROWS; r += 8) {
         const int64_t i = i0 + r;
         if (i >= N) break;
         double dot = 0.0;
-        for (int k = 0; k < d; ++k) dot = fma(s_a[r][k], s_b[tx][k], dot);
+#pragma unroll
+        for (int k = 0; k < SE_MAXD; ++k)
+            if (k < d) dot = fma(s_a[r][k], bk[k], dot);
         const double dist = __dadd_rn(__dadd_rn(qb, s_q[r]), -2.0 * dot);
         double v = sigma * exp(-0.5 * dist);
         if (noise_from >= 0 && i == c && c >= noise_from) v += sigma0;
@@ -96,15 +103,19 @@ int launch_se_ard(const double* x, int64_t N, const double* xb, int64_t m, int d
     if (N == 0 || m == 0) return 0;
     const char* env = getenv("TES_SE_ARD_TILED");
     const bool tiled = d <= SE_MAXD && !(env && env[0] == '0');
-    const int rpb = tiled ? SE_ROWS : 8;                       // rows per CTA
+    // 128-row tiles amortise the per-CTA set-up on the large chunks; small problems keep 32 rows (more CTAs)
+    const bool big = tiled && ((N + 127) / 128) * ((m + 31) / 32) >= 4 * 148;
+    const int rpb = tiled ? (big ? 128 : 32) : 8;              // rows per CTA
     dim3 block(32, 8);
     const int64_t rows_per = 65535LL * rpb;
     for (int64_t r0 = 0; r0 < N; r0 += rows_per) {             // grid.y <= 65535: split rows
         const int64_t nr = (N - r0 < rows_per) ? (N - r0) : rows_per;
         dim3 g2((unsigned)((m + 31) / 32), (unsigned)((nr + rpb - 1) / rpb));
         const int64_t nf = noise_from >= 0 ? noise_from - r0 : -1;
-        if (tiled)
-            se_ard_tile_kernel<<<g2, block, 0, st>>>(x + r0 * d, nr, xb, m, d, l, sigma, nf, sigma0, out + r0 * ldo, ldo);
+        if (tiled && big)
+            se_ard_tile_kernel<128><<<g2, block, 0, st>>>(x + r0 * d, nr, xb, m, d, l, sigma, nf, sigma0, out + r0 * ldo, ldo);
+        else if (tiled)
+            se_ard_tile_kernel<32><<<g2, block, 0, st>>>(x + r0 * d, nr, xb, m, d, l, sigma, nf, sigma0, out + r0 * ldo, ldo);
         else
             se_ard_kernel<<<g2, block, 0, st>>>(x + r0 * d, nr, xb, m, d, l, sigma, nf, sigma0, out + r0 * ldo, ldo);
     }
