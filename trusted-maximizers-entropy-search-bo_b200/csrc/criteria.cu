@@ -710,14 +710,15 @@ extern "C" int tes_ep_acq_f64(int mode, const double* x, int64_t N, int64_t d, c
 //   h_j = sum_a |M[x,a]| sqrt(Sigma_j[a][a])   (uses |Sigma_ab| <= sqrt(S_aa S_bb): CHECKED for every (a, b, j) by
 //   screen_diag_kernel -- EP-mode covariances need not be positive semi-definite; a column j that violates it, or has a
 //   negative / NaN diagonal entry, gets h_j = +inf, i.e. eps = +inf for every candidate: no pruning)
-//   QS_ETA = 1.5 * (2.5 * 2^-20 [hi/lo fp16 operands, dropped lo*lo] + 4 * 2^-24 * 96 [fp32 segments of 256 k])
+//   QS_ETA = 1.5 * (2.5 * 2^-20 [hi/lo fp16 operands, dropped lo*lo] + 4 * 2^-24 * 96 [fp32 segments of 256 k]
+//                   + 64 * 2^-24 [fp32 running sum of <= 64 segments in the fused kernel; the sum of |terms| <= h^2])
 //   QS_ABS = 1.5 * (4096 + 8) * 2^-25 / (4096 * 8): the fp16 lo halves are SUBNORMAL below 2^-14, so an operand carries an
 //   absolute error of up to 2^-25 in scaled units (rows scaled to products <= 4096 = QS_AMAX, columns to <= 8 = QS_BMAX)
 //   on top of the relative one; per term <= (|a| + |b|) 2^-25, summed over the Ks padded terms and unscaled by
 //   rowmax^2 / 4096 * colmax / 8.  (Entries of Sigma_j or M far below colmax / rowmax are where it matters.)
 //   |1/2 log(v~ + s0) - 1/2 log(v + s0)| <= 1/2 log(w / (w - delta)),  w = v~ + s0  (infinite when w <= delta or NaN)
 namespace tes {
-constexpr double QS_ETA = 4.0e-5;
+constexpr double QS_ETA = 4.6e-5;
 constexpr double QS_ABS = 1.5 * 4104.0 * 2.98023223876953125e-08 / 32768.0;
 // D[a][j] = sqrt(Sigma_j[a][a]); one CTA per maximizer j checks Sigma_ab^2 <= Sigma_aa Sigma_bb for every pair (the
 // inequality the h-bound rests on) and a non-negative diagonal, else the whole column of D is +inf.  Df (optional):

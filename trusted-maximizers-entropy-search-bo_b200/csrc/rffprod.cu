@@ -2110,12 +2110,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 for (int a = lane; a < (int)T; a += 32) msm[a * 129 + rr] = sc != 0.0 ? (float)(gp[a] * sc) : 0.0f;
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            // running sums of the 256-k fp32 segments as double-float pairs (hi + lo, error-free TwoSum on the fp32 pipe,
-            // ~2^-46 relative): converting every segment value to fp64 costs a conversion on the XU pipe per value
-            // (16 lanes / clk / SM) -- the drains were 26 % of the kernel's samples
-            float shi[32], slo[32];
+            // running sums of the 256-k fp32 segments in fp32: one rounding of 2^-24 of the partial sum (<= h^2) per
+            // segment, nseg <= 64 of them -- carried by QS_ETA (criteria.cu).  fp64 sums cost a conversion on the XU
+            // pipe per value (16 lanes / clk / SM), double-float pairs 7 fp32 operations per value: the drains were
+            // 26 % of the kernel's samples
+            float shi[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) shi[c] = slo[c] = 0.0f;
+            for (int c = 0; c < 32; ++c) shi[c] = 0.0f;
             auto drain = [&](int64_t dseg) {
                 const uint32_t a = (uint32_t)(dseg & 1), pa = (uint32_t)((dseg >> 1) & 1);
                 mbar_wait(&acc_full[a], pa);
@@ -2127,14 +2128,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 __syncwarp();
                 if (lane == 0) tc_arrive(&acc_empty[a]);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float v = __uint_as_float(v0[c]);
-                    const float t = __fadd_rn(shi[c], v);
-                    const float bb = __fsub_rn(t, shi[c]);
-                    const float e = __fadd_rn(__fsub_rn(shi[c], __fsub_rn(t, bb)), __fsub_rn(v, bb));
-                    slo[c] = __fadd_rn(slo[c], e);
-                    shi[c] = t;
-                }
+                for (int c = 0; c < 32; ++c) shi[c] = __fadd_rn(shi[c], __uint_as_float(v0[c]));
             };
             for (int64_t seg = 0; seg < nseg; ++seg) {
                 for (int q4 = 0; q4 < TC_SEG; ++q4, ++g) {
@@ -2183,7 +2177,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
                     if (cb * 32 + c < Sp)
-                        Qout[row * Sp + cb * 32 + c] = rs * colscale[cb * 32 + c] * ((double)shi[c] + (double)slo[c]);
+                        Qout[row * Sp + cb * 32 + c] = rs * colscale[cb * 32 + c] * (double)shi[c];
             }
         }
     }
@@ -2244,7 +2238,7 @@ int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, int6
         const size_t fsm = (size_t)QF_NS * TC_STAGE_BYTES + (size_t)qf_msm_floats(T) * sizeof(float) +
                            (size_t)nst * 8 * sizeof(uint2) + 128 * sizeof(double) + 256;
         const char* env = getenv("TES_QUAD_FUSED");
-        if (fsm <= 227 * 1024 && T <= 500 && !(env && env[0] == '0')) {
+        if (fsm <= 227 * 1024 && T <= 500 && nst / TC_SEG <= 64 && !(env && env[0] == '0')) {
             const uint32_t* ab = reinterpret_cast<const uint32_t*>(colmax + 256);
             const int sms = tc_sm_count();
             TES_CUDA_OK(cudaFuncSetAttribute(quad_screen_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
