@@ -362,6 +362,7 @@ class Bench:
         sampler = ClockSampler(self.local_rank) if sample_clocks else None
         timers = {}
         ops.STATS["product_flagged"] = 0
+        ops.STATS["product_unresolved"] = 0
         launches0 = _lib.lib().tes_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
@@ -377,7 +378,8 @@ class Bench:
         pairs_step = shard.n_global * wl["S"]
         res = {"value": pairs_step * steps / dev_s, "ms_per_step": dev_s / steps * 1e3, "steps": steps, "out": out,
                "launches": int(launches), "clocks": clocks, "shard": shard, "devt": devt, "step": step,
-               "flagged_samples_per_step": ops.STATS["product_flagged"] / steps, "timers": timers}
+               "flagged_samples_per_step": ops.STATS["product_flagged"] / steps,
+               "unresolved_samples_per_step": ops.STATS.get("product_unresolved", 0) / steps, "timers": timers}
         # per-stage milliseconds (CUDA events on the launching stream), mean over steps; min / max over ranks
         mine = [float(np.mean([a.elapsed_time(b_) for a, b_ in timers[k]])) if timers.get(k) else float("nan")
                 for k, _ in STAGES]
@@ -588,6 +590,7 @@ def main():
             "clocks": res["clocks"],
             "stage_ms": res["stages"],
             "stage_a_flagged_samples_per_step": res["flagged_samples_per_step"],
+            "stage_a_unresolved_samples_per_step": res["unresolved_samples_per_step"],
             "e2e": res["e2e"],
             "gpu_launches": res["launches"],
             "roofline": roofline,

@@ -88,6 +88,20 @@ int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d, int64_t s
                              int k, int64_t idx_offset, int64_t* out_idx, double* out_val, int* out_flag, int tf32,
                              void* ws, int64_t ws_bytes, void* stream);
 
+/* Resolve pass for the samples tes_rff_topk_product_f64 flags because of NEAR-TIES (more than 8 candidates within the
+ * error bound of the k-th best: meshes that are fine along a direction the function sample is flat in).  W / b / theta
+ * of the flagged samples only (S of them).  The CTA-pair tcgen05 GEMM runs twice on them: top-k epilogue (k-th best
+ * value vk, bound B), then a threshold epilogue that emits every candidate whose GEMM value reaches vk - 2B -- a
+ * superset of the true top-k -- followed by the exact fp64 sequence of tes_spec.h on the emitted candidates and the
+ * (value desc, index asc) ranking: the bits of tes_rff_topk_f64 at ~3 % of its cost per sample.  out_flag: 1 where more
+ * than 2048 candidates pass the threshold or NaN is involved (recompute with tes_rff_topk_f64).  d <= 16, k <= 8.
+ * Replaces nothing in the reference (utils_for_continuous.py:172-187 evaluates every candidate in fp64). */
+int64_t tes_rff_topk_product_resolve_workspace_bytes(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F, int k);
+int tes_rff_topk_product_resolve_f64(const double* cand, int64_t N, int64_t d, int64_t s_lo, int64_t s_hi, int64_t nv,
+                                     const double* W, const double* b, const double* theta, int64_t S, int64_t F,
+                                     int w_shared, double sigma, int k, int64_t idx_offset, int64_t* out_idx,
+                                     double* out_val, int* out_flag, void* ws, int64_t ws_bytes, void* stream);
+
 /* Detection of the product structure above on the device (the meshes come from functions.get_meshgrid,
  * bo_discrete.py:928-941; the reference has no counterpart: it never exploits the structure).
  * runlen: out_r[k] = first row whose coordinate k differs from row 0 (N if the column is constant) -- the block length nv

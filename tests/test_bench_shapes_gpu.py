@@ -99,6 +99,28 @@ def test_c3_mesh_plus_extra_rows(c3):
     assert int(j1[0, 1]) == dv["cand"].shape[0]      # the planted duplicate ties with the mesh point: lower index first
 
 
+def test_c3_slab_of_the_8_gpu_mesh_resolves_near_ties_without_the_general_kernel():
+    """Rank 5's slab of the 8-GPU weak-scaling mesh (80 points along the slowest axis): a few function samples are flat
+    along that axis and have more near-ties than the k + 8 survivors; the resolve pass settles them on the GEMM path.
+    Stage A == the general tcgen05 screen kernel for all 1024 samples."""
+    import torch
+    from tes_b200 import ops, optfunc
+    wl = bench.make_workload("c3", 5, 8)
+    dv = {k: torch.from_numpy(np.ascontiguousarray(wl[k])).cuda() for k in ("cand", "X", "Y", "randn_W", "rand_b", "noise")}
+    hyp = wl["hyp"]
+    theta, W, b = optfunc.draw_random_init_weights_features(
+        wl["d"], wl["S"], wl["F"], dv["X"], dv["Y"], hyp["l"], hyp["sigma"], hyp["sigma0"],
+        draws=(dv["randn_W"], dv["rand_b"], dv["noise"]))
+    before = dict(ops.STATS)
+    i1, v1 = ops.rff_topk(dv["cand"], W, b, theta, hyp["sigma"], k=3, idx_offset=5 * 10 ** 6)
+    flagged = ops.STATS["product_flagged"] - before["product_flagged"]
+    unresolved = ops.STATS.get("product_unresolved", 0) - before.get("product_unresolved", 0)
+    assert flagged >= 1 and unresolved == 0
+    i2, v2 = ops.rff_topk(dv["cand"], W, b, theta, hyp["sigma"], k=3, idx_offset=5 * 10 ** 6, product=False,
+                          method=ops.RFF_SCREEN_TC5)
+    assert torch.equal(i1, i2) and torch.equal(v1, v2)
+
+
 @pytest.fixture(scope="module")
 def c4slice():
     import torch

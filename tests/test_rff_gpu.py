@@ -452,3 +452,61 @@ def test_product_path_near_ties(eps, seed):
         good = (fl == 0).cpu().numpy()
         np.testing.assert_array_equal(i2.cpu().numpy()[good], ridx[good])
         np.testing.assert_array_equal(v2.cpu().numpy()[good], rval[good])
+
+
+@pytest.mark.parametrize("k,flat_axes,expect_resolved", [(3, 1, True), (1, 1, True), (8, 1, True), (3, 2, False)])
+def test_product_path_resolve_pass_for_near_tie_clusters(k, flat_axes, expect_resolved):
+    """A mesh that is fine along a direction the function sample is (nearly) flat in: dozens of candidates within the
+    screen's error bound of the best, more than the k + 8 survivors can hold, so every sample is flagged.  The resolve
+    pass (threshold epilogue of the same tcgen05 GEMM + exact refine of everything above vk - 2B) gives the oracle's
+    bits without the general kernel; with a cluster larger than its 2048-entry list it hands the sample on."""
+    from oracle import c_oracle as co
+    from tes_b200 import ops
+    rs = np.random.RandomState(17 + k)
+    ax_fine = np.linspace(0.0, 1.0, 48)
+    cand = _mesh([np.sort(rs.rand(40)), ax_fine, ax_fine[:44], np.sort(rs.rand(30))])   # columns: 1 = slowest ('xy' order)
+    S, F, d = 7, 160, 4
+    Wn, bn, th = rs.randn(S, F, d) * 1.5, 2 * np.pi * rs.rand(S, F, 1), rs.randn(S, F, 1)
+    Wn[:, :, 1] *= 1e-9                      # flat along the slowest mesh axis (column 1): 48-fold near-ties
+    if flat_axes == 2:
+        Wn[:, :, 0] *= 1e-9                  # ... and along the next one: 48 x 40 = 1920-fold, x more within the bound
+        Wn[:, :, 2] *= 1e-7
+    ridx, rval = co.rff_topk(cand, Wn, bn, th, 1.1, k, idx_offset=77)
+    det = ops.detect_product_structure(ops.dev(cand))
+    assert det is not None
+    _, _, fl = ops.rff_topk_product(cand, Wn, bn, th, 1.1, det[0], det[1], det[2], k=k, idx_offset=77)
+    assert int(fl.sum()) == S                # every sample has more near-ties than survivors
+    ri, rv, rfl = ops.rff_topk_product_resolve(cand, Wn, bn, th, 1.1, det[0], det[1], det[2], k=k, idx_offset=77)
+    good = (rfl == 0).cpu().numpy()
+    assert bool(good.all()) == expect_resolved
+    np.testing.assert_array_equal(ri.cpu().numpy()[good], ridx[good])
+    np.testing.assert_array_equal(rv.cpu().numpy()[good], rval[good])
+    before = dict(ops.STATS)
+    idx, val = ops.rff_topk(cand, Wn, bn, th, 1.1, k=k, idx_offset=77, method=ops.RFF_PRODUCT)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ridx)
+    np.testing.assert_array_equal(val.cpu().numpy(), rval)
+    assert ops.STATS["product_flagged"] == before["product_flagged"] + S
+    unresolved = ops.STATS.get("product_unresolved", 0) - before.get("product_unresolved", 0)
+    assert (unresolved == 0) == expect_resolved
+
+
+def test_product_path_resolve_pass_shared_weights_and_nan():
+    """w_shared layout through the resolve pass; a NaN weight makes the threshold NaN: the sample stays flagged."""
+    from oracle import c_oracle as co
+    from tes_b200 import ops
+    rs = np.random.RandomState(5)
+    ax = np.linspace(0.0, 1.0, 40)
+    cand = _mesh([np.sort(rs.rand(36)), ax, np.sort(rs.rand(33))])
+    S, F, d = 5, 96, 3
+    Wn, bn, th = rs.randn(1, F, d), 2 * np.pi * rs.rand(1, F, 1), rs.randn(S, F, 1)
+    Wn[:, :, 1] *= 1e-9
+    det = ops.detect_product_structure(ops.dev(cand))
+    ridx, rval = co.rff_topk(cand, Wn, bn, th, 0.7, 3)
+    ri, rv, rfl = ops.rff_topk_product_resolve(cand, Wn, bn, th, 0.7, det[0], det[1], det[2], k=3)
+    assert int(rfl.sum()) == 0
+    np.testing.assert_array_equal(ri.cpu().numpy(), ridx)
+    np.testing.assert_array_equal(rv.cpu().numpy(), rval)
+    th2 = th.copy()
+    th2[3, 5, 0] = np.nan
+    _, _, rfl = ops.rff_topk_product_resolve(cand, Wn, bn, th2, 0.7, det[0], det[1], det[2], k=3)
+    assert int(rfl[3]) == 1 and int(rfl.sum()) == 1

@@ -47,6 +47,9 @@ SIGNATURES = {
     "tes_rff_topk_product_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int]),
     "tes_rff_topk_product_f64": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int,
                                          c_dbl, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
+    "tes_rff_topk_product_resolve_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_i64, c_int]),
+    "tes_rff_topk_product_resolve_f64": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64,
+                                                 c_int, c_dbl, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "tes_ep_acq_screen_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_i64]),
     "tes_ep_acq_screen_f64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr,
                                       c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),

@@ -1286,7 +1286,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     prod_gemm_topk_tc8_kernel(const __half* __restrict__ Pt, const __half* __restrict__ Qt, int64_t nu, int64_t nv,
                               int ntu, int ntv, int nst, double scale0, const double* __restrict__ tmax,
                               int64_t idx_offset, int kp, int G, double* __restrict__ part_val,
-                              int64_t* __restrict__ part_idx) {
+                              int64_t* __restrict__ part_idx, const double* __restrict__ thr,
+                              int64_t* __restrict__ emit_idx, int* __restrict__ emit_cnt, int emit_cap) {
+    // thr != nullptr (tes_rff_topk_product_resolve_f64): instead of the per-warp top-kp lists, every candidate whose
+    // value reaches thr[g] is appended to emit_idx[g][.] (emit_cnt[g] counts them, entries beyond emit_cap are dropped)
     extern __shared__ __align__(1024) unsigned char t8_smem_raw[];
     constexpr uint32_t STAGE = HALF ? T8_STAGE_BYTES / 2 : T8_STAGE_BYTES;
     constexpr uint32_t PART = HALF ? TC_BLOCK_BYTES / 4 : TC_BLOCK_BYTES / 2;      // bytes of the hi (= of the lo) part
@@ -1451,6 +1454,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             }
             if (rt >= ntu) continue;                   // the zero tile that pads an odd number of row tiles
             const int64_t row = (int64_t)rt * 128 + quarter * 32 + lane;
+            if (thr) {
+                const double th = thr[g];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int ct = 2 * ctp + h;
+                    if (ct >= ntv || row >= nu) continue;
+                    const int64_t colb = (int64_t)ct * 128 + cb * 32;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (colb + c < nv && __dmul_rn(scale, (double)acc[h][c]) >= th) {
+                            const int slot = atomicAdd(emit_cnt + g, 1);
+                            if (slot < emit_cap) emit_idx[(int64_t)g * emit_cap + slot] = row * nv + colb + c + idx_offset;
+                        }
+                }
+                continue;
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int ct = 2 * ctp + h;
@@ -2462,7 +2481,7 @@ __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const 
                                   const double* __restrict__ approx_val, const int64_t* __restrict__ idx,
                                   const double* __restrict__ xmax, int tf32, const double* __restrict__ tmax,
                                   double* __restrict__ exact_val,
-                                  int* __restrict__ flag) {
+                                  int* __restrict__ flag, double* __restrict__ thr_out = nullptr) {
     // one WARP per (sample, slot): the lanes evaluate 32 features' arguments and cosines in parallel and park
     // (theta, cos) in shared memory, then every lane replays the spec's sequential fma accumulation over them in feature
     // order -- the same operations in the same order as one thread walking the F features (which left 2 warps per SM
@@ -2540,6 +2559,98 @@ __global__ void prod_exact_kernel(const double* __restrict__ cand, int d, const 
         // safe iff the kp-th best GEMM value is below the k-th best by more than 2B
         const bool safe = !full || (vl < vk - 2.0 * B);
         flag[j] = (safe && enough && vk == vk && B == B) ? 0 : 1;
+        // every member of the true top-k has a GEMM value >= vk - 2B (resolve pass); NaN: not resolvable
+        if (thr_out) thr_out[j] = (enough && vk == vk && B == B) ? vk - 2.0 * B : __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
+
+// ---- resolve pass (tes_rff_topk_product_resolve_f64): samples the screen could not certify ---------------------------
+// exact spec values of the emitted candidates (one warp per (sample, slot), the sequence of prod_exact_kernel)
+__global__ void prod_exact_list_kernel(const double* __restrict__ cand, int d, const double* __restrict__ feat, int rec,
+                                       int64_t S, int64_t F, double scale, int64_t idx_offset, int cap,
+                                       const int64_t* __restrict__ idx, const int* __restrict__ cnt,
+                                       double* __restrict__ exact_val) {
+    __shared__ double2 pr[4][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * 4 + warp;
+    if (t >= S * cap) return;
+    const int64_t j = t / cap;
+    const int r = (int)(t % cap);
+    const int c = cnt[j];
+    if (r >= (c < cap ? c : cap)) return;
+    const double* fj = feat + j * F * rec;
+    const double* x = cand + (idx[t] - idx_offset) * d;
+    double acc = 0.0;
+    for (int64_t f0 = 0; f0 < F; f0 += 32) {
+        const int64_t f = f0 + lane;
+        double2 tc = make_double2(0.0, 0.0);
+        if (f < F) {
+            const double* rr = fj + f * rec;
+            double h = __ldg(rr + d);
+            for (int kk = 0; kk < d; ++kk) h = fma(__ldg(rr + kk), __ldg(x + kk), h);
+            tc = make_double2(__ldg(rr + d + 1), cospi_spec(h));
+        }
+        __syncwarp();
+        pr[warp][lane] = tc;
+        __syncwarp();
+        const int nb = F - f0 < 32 ? (int)(F - f0) : 32;
+        for (int q = 0; q < nb; ++q) {
+            const double2 e = pr[warp][q];
+            acc = fma(e.x, e.y, acc);
+        }
+    }
+    if (lane == 0) exact_val[t] = __dmul_rn(scale, acc);
+}
+// top-k of a sample's emitted candidates by (exact value desc, index asc); one CTA per sample.  flag = 1 when the list
+// overflowed or the threshold was NaN (the caller falls back to the general kernel for that sample).
+__global__ void __launch_bounds__(256) prod_final_list_kernel(const double* __restrict__ vals, const int64_t* __restrict__ idx,
+                                                              const int* __restrict__ cnt, const double* __restrict__ thr,
+                                                              int cap, int k, double* __restrict__ out_val,
+                                                              int64_t* __restrict__ out_idx, int* __restrict__ flag) {
+    __shared__ double sv[8];
+    __shared__ int64_t si[8];
+    const int64_t j = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = cnt[j];
+    const bool ok = c <= cap && thr[j] == thr[j];
+    if (threadIdx.x == 0) flag[j] = ok ? 0 : 1;
+    const int n = c < cap ? c : cap;
+    double pv = pos_inf();
+    int64_t pi = -1;
+    for (int r = 0; r < k; ++r) {
+        double bv = neg_inf();
+        int64_t bi = INT64_MAX;
+        for (int e = threadIdx.x; e < n; e += 256) {
+            const double v = vals[j * cap + e];
+            const int64_t i = idx[j * cap + e];
+            if (better(pv, pi, v, i) && better(v, i, bv, bi)) {
+                bv = v;
+                bi = i;
+            }
+        }
+        warp_argmax(bv, bi);
+        if (lane == 0) {
+            sv[warp] = bv;
+            si[warp] = bi;
+        }
+        __syncthreads();
+        bv = sv[0];
+        bi = si[0];
+        for (int q = 1; q < 8; ++q)
+            if (si[q] != INT64_MAX && (bi == INT64_MAX || better(sv[q], si[q], bv, bi))) {
+                bv = sv[q];
+                bi = si[q];
+            }
+        __syncthreads();
+        const bool found = (bi != INT64_MAX);
+        if (threadIdx.x == 0) {
+            out_val[j * k + r] = found ? bv : neg_inf();
+            out_idx[j * k + r] = found ? bi : -1;
+        }
+        if (found) {
+            pv = bv;
+            pi = bi;
+        }
     }
 }
 
@@ -2860,13 +2971,16 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
             }();
             if (t8_shape == 3)
                 prod_gemm_topk_tc8_kernel<0, 3><<<(unsigned)ncta, TC_THREADS, 3 * T8_STAGE_BYTES + 256, st>>>(
-                    Pg, Qg, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
+                    Pg, Qg, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi, nullptr, nullptr,
+                    nullptr, 0);
             else if (t8_shape == 6)
                 prod_gemm_topk_tc8_kernel<1, 6><<<(unsigned)ncta, TC_THREADS, 6 * T8_STAGE_BYTES / 2 + 256, st>>>(
-                    Pg, Qg, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
+                    Pg, Qg, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi, nullptr, nullptr,
+                    nullptr, 0);
             else
                 prod_gemm_topk_tc8_kernel<1, 7><<<(unsigned)ncta, TC_THREADS, 7 * T8_STAGE_BYTES / 2 + 256, st>>>(
-                    Pg, Qg, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi);
+                    Pg, Qg, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi, nullptr, nullptr,
+                    nullptr, 0);
             TES_LAUNCH_OK();
             if (ov.on) TES_CUDA_OK(cudaEventRecord(ov.freed[buf], st));
         } else if (tf32 == 6) {
@@ -2982,6 +3096,110 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
         TES_LAUNCH_OK();
     }
     prod_final_kernel<<<(unsigned)S, 32, 0, st>>>(ev, mi, pl.kp, k, out_val, out_idx);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
+// ---- resolve pass for the samples tes_rff_topk_product_f64 flags -----------------------------------------------------
+// A sample is flagged when its (k + 8)-th best GEMM value is within 2B of the k-th best: more than 8 near-ties (meshes
+// that are fine along a direction the sample is flat in), so the k + 8 survivors need not contain the true top-k.
+// Recomputing such a sample with the general kernel costs ~0.4 ms (N = 10^6, F = 1024).  Here instead: the same CTA-pair
+// tcgen05 GEMM runs on the flagged samples only, first with the top-kp epilogue (k-th best value vk, bound B), then with
+// the THRESHOLD epilogue: every candidate whose GEMM value u reaches vk - 2B is emitted (|u - v| <= B for the exact
+// value v, and the k candidates with u >= vk have v >= vk - B, so every member of the true top-k has u >= vk - 2B).
+// The emitted candidates are evaluated with the exact spec sequence and ranked by (value desc, index asc): the bits of
+// tes_rff_topk_f64.  Still flagged afterwards: more than PR_CAP candidates above the threshold, NaN.
+constexpr int PR_CAP = 2048;
+extern "C" int64_t tes_rff_topk_product_resolve_workspace_bytes(int64_t N, int64_t d, int64_t nv, int64_t S, int64_t F,
+                                                                int k) {
+    if (N < 1 || d < 2 || d > 16 || nv < 1 || N % nv != 0 || S < 1 || F < 1 || k < 1 || k > 8) return -1;
+    return prod_plan(N, d, nv, S, F, k, 1, 3).total + align_up(S * 8, 256) + align_up(S * 4, 256) +
+           2 * align_up(S * (int64_t)PR_CAP * 8, 256);
+}
+extern "C" int tes_rff_topk_product_resolve_f64(const double* cand, int64_t N, int64_t d, int64_t s_lo, int64_t s_hi,
+                                                int64_t nv, const double* W, const double* b, const double* theta,
+                                                int64_t S, int64_t F, int w_shared, double sigma, int k,
+                                                int64_t idx_offset, int64_t* out_idx, double* out_val, int* out_flag,
+                                                void* ws, int64_t ws_bytes, void* stream) {
+    if (N < 1 || !cand) return -1;
+    if (d < 2 || d > 16) return -3;
+    if (s_lo < 0 || s_hi > d || s_lo >= s_hi || s_hi - s_lo >= d) return -4;
+    if (nv < 1 || N % nv != 0) return -5;
+    if (!W) return -6;
+    if (!b) return -7;
+    if (!theta) return -8;
+    if (S < 1 || S > (1 << 24)) return -9;
+    if (F < 1 || F > (1 << 22)) return -10;
+    if (!(sigma >= 0.0)) return -12;
+    if (k < 1 || k > 8) return -13;
+    if (!out_idx) return -15;
+    if (!out_val) return -16;
+    if (!out_flag) return -17;
+    ProdPlan pl = prod_plan(N, d, nv, S, F, k, 1, 3);
+    if (!ws || ws_bytes < tes_rff_topk_product_resolve_workspace_bytes(N, d, nv, S, F, k)) return -100;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)ws;
+    double* feat = (double*)(base + pl.off_feat);
+    __half* Hhi = (__half*)(base + pl.off_p);
+    __half* Ghi = (__half*)(base + pl.off_q);
+    double* pv = (double*)(base + pl.off_pv);
+    int64_t* pi = (int64_t*)(base + pl.off_pi);
+    double* mv = (double*)(base + pl.off_mv);
+    int64_t* mi = (int64_t*)(base + pl.off_mi);
+    double* ev = (double*)(base + pl.off_ev);
+    double* xmax = (double*)(base + pl.off_xmax);
+    double* tmax = (double*)(base + pl.off_tmax);
+    char* extra = base + pl.total;
+    double* thr = (double*)extra;
+    extra += align_up(S * 8, 256);
+    int* cnt = (int*)extra;
+    extra += align_up(S * 4, 256);
+    int64_t* lidx = (int64_t*)extra;
+    extra += align_up(S * (int64_t)PR_CAP * 8, 256);
+    double* lval = (double*)extra;
+    const double scale = sqrt(2.0 * sigma / (double)F);
+    const int64_t nu = pl.nu;
+    prod_pack_kernel<<<(unsigned)((S * F + 255) / 256), 256, 0, st>>>(W, b, theta, S, F, (int)d, w_shared, pl.rec, feat);
+    TES_LAUNCH_OK();
+    prod_xmax_kernel<<<1, 256, 0, st>>>(cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, xmax);
+    TES_LAUNCH_OK();
+    TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc8_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(3 * T8_STAGE_BYTES + 256)));
+    TES_CUDA_OK(cudaMemsetAsync(Hhi, 0, (size_t)(pl.G * pl.nup * pl.K2p * 8), st));
+    TES_CUDA_OK(cudaMemsetAsync(Ghi, 0, (size_t)(pl.G * pl.K2p * pl.nvp * 8), st));
+    TES_CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)S * 4, st));
+    prod_tmax_kernel<<<(unsigned)S, 256, 0, st>>>(theta, F, tmax);
+    TES_LAUNCH_OK();
+    const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK, ntu2 = (ntu + 1) / 2, ntv2 = (ntv + 1) / 2;
+    for (int64_t j0 = 0; j0 < S; j0 += pl.G) {
+        const int64_t G = (S - j0 < pl.G) ? (S - j0) : pl.G;
+        prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)G, 8), 256, 0, st>>>(
+            cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, 2 * ntu2, nst, tmax, Hhi, 0, 128);
+        TES_LAUNCH_OK();
+        prod_build_tc_kernel<<<dim3((unsigned)ntv, (unsigned)G, 8), 256, 0, st>>>(
+            cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, 2 * ntv2, nst, tmax, Ghi, 0, 128);
+        TES_LAUNCH_OK();
+        const int64_t ntot = ntu2 * ntv2 * G;
+        const int64_t ncta = 2 * ntot < tc_sm_count() ? 2 * ntot : (tc_sm_count() / 2) * 2;
+        prod_gemm_topk_tc8_kernel<0, 3><<<(unsigned)ncta, TC_THREADS, 3 * T8_STAGE_BYTES + 256, st>>>(
+            Hhi, Ghi, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi, nullptr, nullptr,
+            nullptr, 0);
+        TES_LAUNCH_OK();
+        if (int rc = launch_prod_merge(pv, pi, pl.nlist, G, pl.kp, mv + j0 * pl.kp, mi + j0 * pl.kp, st)) return rc;
+        // vk and B of the group's samples -> thresholds (the exact values of the kp survivors are not needed here)
+        prod_exact_kernel<<<(unsigned)((G * pl.kp + 3) / 4), 128, 0, st>>>(
+            cand, (int)d, feat + j0 * F * pl.rec, pl.rec, G, F, scale, idx_offset, k, pl.kp, mv + j0 * pl.kp, mi + j0 * pl.kp, xmax,
+            8, tmax + j0, ev + j0 * pl.kp, out_flag + j0, thr + j0);
+        TES_LAUNCH_OK();
+        prod_gemm_topk_tc8_kernel<0, 3><<<(unsigned)ncta, TC_THREADS, 3 * T8_STAGE_BYTES + 256, st>>>(
+            Hhi, Ghi, nu, nv, (int)ntu, (int)ntv, (int)nst, scale, tmax + j0, idx_offset, pl.kp, (int)G, pv, pi, thr + j0,
+            lidx + j0 * PR_CAP, cnt + j0, PR_CAP);
+        TES_LAUNCH_OK();
+    }
+    prod_exact_list_kernel<<<(unsigned)((S * PR_CAP + 3) / 4), 128, 0, st>>>(cand, (int)d, feat, pl.rec, S, F, scale,
+                                                                              idx_offset, PR_CAP, lidx, cnt, lval);
+    TES_LAUNCH_OK();
+    prod_final_list_kernel<<<(unsigned)S, 256, 0, st>>>(lval, lidx, cnt, thr, PR_CAP, k, out_val, out_idx, out_flag);
     TES_LAUNCH_OK();
     return 0;
 }

@@ -27,6 +27,7 @@ STATS = {"product_flagged": 0}   # samples the product path handed back to the g
 
 RFF_PRODUCT = 6          # product-structured candidate sets: one fp64 tensor-pipe GEMM per sample (csrc/rffprod.cu)
 PRODUCT_MIN_N = 1 << 15  # below this the general kernels are launch-bound anyway
+RESOLVE_FLAGGED = __import__("os").environ.get("TES_PRODUCT_RESOLVE", "1") != "0"   # resolve pass for near-tie samples
 PRODUCT_MODE = int(__import__("os").environ.get("TES_PRODUCT_MODE", "8"))   # GEMM engine of the product path (8: CTA pairs, 256 x 256 tiles)
 
 
@@ -133,6 +134,26 @@ def rff_topk_product(cand, W, b, theta, sigma, s_lo, s_hi, nv, k=1, idx_offset=0
     return out_idx, out_val, flag
 
 
+def rff_topk_product_resolve(cand, W, b, theta, sigma, s_lo, s_hi, nv, k=1, idx_offset=0):
+    """Samples the product path flagged for near-ties: threshold pass of the same tcgen05 GEMM + exact refine of every
+    candidate above the threshold (tes_rff_topk_product_resolve_f64) -> (idx, val, flag); flag = 1: still unresolved."""
+    cand, W, b, theta, N, d, S, F, ws_ = _rff_args(cand, W, b, theta)
+    L = _lib.lib()
+    need = L.tes_rff_topk_product_resolve_workspace_bytes(N, d, int(nv), S, F, int(k))
+    if need < 0:
+        raise ValueError("invalid sizes for tes_rff_topk_product_resolve_f64: N=%d d=%d nv=%d S=%d F=%d k=%d"
+                         % (N, d, nv, S, F, k))
+    ws = WORKSPACE.get(need, cand.device)
+    out_idx = torch.empty((S, k), dtype=torch.int64, device=cand.device)
+    out_val = torch.empty((S, k), dtype=torch.float64, device=cand.device)
+    flag = torch.empty((S,), dtype=torch.int32, device=cand.device)
+    rc = L.tes_rff_topk_product_resolve_f64(ptr(cand), N, d, int(s_lo), int(s_hi), int(nv), ptr(W), ptr(b), ptr(theta), S, F,
+                                            ws_, float(sigma), int(k), int(idx_offset), ptr(out_idx), ptr(out_val),
+                                            ptr(flag), ptr(ws), ws.numel(), stream_ptr())
+    _lib.check(rc, "tes_rff_topk_product_resolve_f64")
+    return out_idx, out_val, flag
+
+
 def rff_topk(cand, W, b, theta, sigma, k=1, idx_offset=0, method=RFF_AUTO, product=None):
     """Top-k candidates of every RFF function sample -> (idx (S,k) int64, val (S,k)) CUDA tensors.
     utils_for_continuous.py:172-187.  `method`: RFF_AUTO / RFF_FP64 / RFF_SCREEN... (identical results).
@@ -150,9 +171,19 @@ def rff_topk(cand, W, b, theta, sigma, k=1, idx_offset=0, method=RFF_AUTO, produ
             bad = torch.nonzero(flag).reshape(-1)
             if bad.numel():
                 STATS["product_flagged"] += int(bad.numel())
-                gi, gv = rff_topk(cand, W if ws_ else W[bad], b if ws_ else b[bad], theta[bad], sigma, k=k,
-                                  idx_offset=idx_offset, product=False)
-                idx[bad], val[bad] = gi, gv
+                if RESOLVE_FLAGGED and d <= 16:
+                    # near-ties: second pass of the GEMM with a threshold epilogue on the flagged samples only
+                    ri, rv, rflag = rff_topk_product_resolve(cand, W if ws_ else W[bad].contiguous(),
+                                                             b if ws_ else b[bad].contiguous(), theta[bad].contiguous(),
+                                                             sigma, product[0], product[1], product[2], k=k,
+                                                             idx_offset=idx_offset)
+                    idx[bad], val[bad] = ri, rv
+                    bad = bad[torch.nonzero(rflag).reshape(-1)]
+                if bad.numel():
+                    STATS["product_unresolved"] = STATS.get("product_unresolved", 0) + int(bad.numel())
+                    gi, gv = rff_topk(cand, W if ws_ else W[bad], b if ws_ else b[bad], theta[bad], sigma, k=k,
+                                      idx_offset=idx_offset, product=False)
+                    idx[bad], val[bad] = gi, gv
             return idx, val
         if product is None and method == RFF_AUTO and N >= PRODUCT_MIN_N:
             # mesh + a few extra rows: product path on the prefix, general kernel on the tail, merge the two lists
