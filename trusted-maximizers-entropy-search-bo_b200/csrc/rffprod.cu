@@ -686,12 +686,18 @@ __host__ __device__ constexpr uint32_t tc_idesc_f16(int m, int n) {
 // 8-k chunks (= 4 features: weights read with block-uniform addresses), row-consecutive threads write consecutive
 // 16-byte slots of the MMA layout.
 constexpr int PB_WS_DOUBLES = 1536;
+// NC > 0: the number of coordinate columns of this side is a compile-time constant (the dot product and the record
+// offsets unroll, the row's coordinates live in registers); NC = 0: generic.  ncu of the generic kernel at C3: issue
+// slots 80 % busy, 56 thread-instructions per feature of which half were index arithmetic, remainder branches of the
+// d-loop and per-element masking (profiles/r02_ncu_prod_build_tc.md).  Rows >= nrow and features >= F are NOT written:
+// the callers zero the operand arrays once (cudaMemsetAsync) and those positions are padding in every group.
+template <int NC>
 __global__ void __launch_bounds__(256)
-    prod_build_tc_kernel(const double* __restrict__ cand, int64_t nrow, int64_t row_stride, int d, int s_lo, int s_hi,
-                         int which, const double* __restrict__ W, const double* __restrict__ b,
-                         const double* __restrict__ theta, int64_t j0, int64_t F, int w_shared, int64_t ntile,
-                         int64_t nst, const double* __restrict__ tmax, __half* __restrict__ out, int chunk_lo,
-                         int TR) {
+    prod_build_tc_kernel_t(const double* __restrict__ cand, int64_t nrow, int64_t row_stride, int d, int s_lo, int s_hi,
+                           int which, const double* __restrict__ W, const double* __restrict__ b,
+                           const double* __restrict__ theta, int64_t j0, int64_t F, int w_shared, int64_t ntile,
+                           int64_t nst, const double* __restrict__ tmax, __half* __restrict__ out, int chunk_lo,
+                           int TR) {
     // chunk_lo > 0: only the 8-k chunks chunk_lo .. 7 of every 64-k stage are built (prod_gemm_gen_kernel generates
     // chunks 0 .. chunk_lo - 1 on the SM).  TR = rows per operand tile: 128, or 64 for the B operand of the CTA-pair
     // kernel (each CTA of a pair stages half of the 128 columns of a tile).
@@ -703,7 +709,7 @@ __global__ void __launch_bounds__(256)
     const int64_t j = j0 + g, jw = w_shared ? 0 : j;
     // coordinate slots: the columns this side uses, in order (arithmetic, not a table: a runtime-indexed array would
     // live in local memory and put an LDL in front of every DFMA)
-    const int ncol = which == 0 ? s_hi - s_lo : d - (s_hi - s_lo);
+    const int ncol = NC > 0 ? NC : (which == 0 ? s_hi - s_lo : d - (s_hi - s_lo));
     auto col_of = [&](int c) { return which == 0 ? s_lo + c : (c < s_lo ? c : c + (s_hi - s_lo)); };
     for (int e = threadIdx.x; e < ncol * TR; e += blockDim.x) {
         const int c = e / TR, rr = e % TR;
@@ -711,6 +717,12 @@ __global__ void __launch_bounds__(256)
         xs[c][rr] = gr < nrow ? cand[(gr * row_stride) * d + col_of(c)] : 0.0;
     }
     __syncthreads();
+    double xr[NC > 0 ? NC : 1];
+    if (NC > 0) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) xr[c] = xs[c][r];
+    }
+    const bool okrow = ir < nrow;
     const double tm = which == 0 ? tmax[j] : 1.0;
     const double inv_tm = tm > 0.0 ? 1.0 / tm : 0.0;
     const int64_t nkc = nst * (TC_BK / 8);
@@ -720,6 +732,10 @@ __global__ void __launch_bounds__(256)
     // of every dependent chain
     const int rs = ncol + 2;
     const int cpb = (PB_WS_DOUBLES / rs) / 4 < 32 ? (PB_WS_DOUBLES / rs) / 4 : 32;      // chunks per block
+    // this thread's 16-byte slot inside a block: [hl][chunk][row][8 halves]; blocks of 2 * 8 * TR * 8 halves
+    const int64_t blk_halves = (int64_t)(2 * 8 * TR * 8);
+    __half* const tile_out = out + ((g * ntile + tile) * nst) * blk_halves + (int64_t)r * 8;
+    const int lo_off = 8 * TR * 8;
     for (int64_t cb = kc_lo; cb < kc_hi; cb += cpb) {
         const int64_t ce = cb + cpb < kc_hi ? cb + cpb : kc_hi;
         const int nf = (int)(ce - cb) * 4;
@@ -734,37 +750,46 @@ __global__ void __launch_bounds__(256)
             ws[e] = v;   // theta / tmax as a float (bit pattern in the low word): the P operand is an fp32 product
         }
         __syncthreads();
-        for (int64_t kc = cb + half; kc < ce; kc += nhalf) {
-            const int64_t st = kc / (TC_BK / 8), chunk = kc % (TC_BK / 8);
+        if (!okrow) continue;
+        const int nck = (int)(ce - cb);
+        for (int lc = half; lc < nck; lc += nhalf) {
+            const int64_t kc = cb + lc;
+            const int st = (int)(kc >> 3), chunk = (int)(kc & 7);      // TC_BK / 8 = 8 chunks per stage
             if (chunk < chunk_lo) continue;
+            const int nfeat = F - kc * 4 >= 4 ? 4 : (int)(F - kc * 4);  // features of this chunk that exist (<= 0: padding)
+            if (nfeat <= 0) continue;
             __align__(16) __half hi[8], lo[8];
-            // the four features of the chunk are evaluated together, branch-free (out-of-range features / rows are
-            // clamped for the loads and zeroed at the end), so their dependent chains -- the fp64 dot and reduction,
-            // the MUFU pair, the splits -- overlap instead of running back to back
-            const double* rec = ws + (int)(kc - cb) * 4 * rs;
+            // the four features of the chunk are evaluated together, branch-free, so their dependent chains -- the fp64
+            // dot and reduction, the MUFU pair, the splits -- overlap instead of running back to back
+            const double* rec = ws + lc * 4 * rs;
             double a[4];
             float th[4];
-            bool ok[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                ok[q] = kc * 4 + q < F && ir < nrow;
                 a[q] = rec[q * rs + ncol];
                 th[q] = __int_as_float(__double2loint(rec[q * rs + ncol + 1]));
             }
-            for (int c = 0; c < ncol; ++c) {
-                const double x = xs[c][r];
+            if (NC > 0) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) a[q] = fma(rec[q * rs + c], x, a[q]);
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) a[q] = fma(rec[q * rs + c], xr[c], a[q]);
+            } else {
+                for (int c = 0; c < ncol; ++c) {
+                    const double x = xs[c][r];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) a[q] = fma(rec[q * rs + c], x, a[q]);
+                }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 // argument reduced to [-pi, pi] in fp64, then the MUFU pair (__sincosf: abs error <= 2^-21.2 there):
                 // the operand error budget of the screen (prod_exact_kernel) carries 2^-21 for it
                 // rint by the 1.5 * 2^52 shift (exact for |t| < 2^51, round-to-nearest-even like rint): two DADDs on
-                // the fp64 pipe instead of an FRND on the conversion (XU) pipe, which is this kernel's busiest
-                // (69 % before; MUFU.SIN / MUFU.COS and the fp64 -> fp32 conversion live there too).  theta / tmax is
-                // applied as an fp32 product of floats (no fp32 <-> fp64 round trips: 4 fewer XU conversions per
-                // feature); its two roundings are the 0.25 * 2^-20 added to the per-term budget in prod_exact_kernel
+                // the fp64 pipe instead of an FRND on the conversion (XU) pipe (MUFU.SIN / MUFU.COS and the
+                // fp64 -> fp32 conversion live there too).  theta / tmax is applied as an fp32 product of floats (no
+                // fp32 <-> fp64 round trips: 4 fewer XU conversions per feature); its two roundings are the
+                // 0.25 * 2^-20 added to the per-term budget in prod_exact_kernel
                 float sn, cs;
                 const double tt = a[q] * 0.15915494309189535;
                 // (|t| >= 2^51 only loses the reduction: the value bound B of prod_exact_kernel grows with max |a| and
@@ -776,16 +801,45 @@ __global__ void __launch_bounds__(256)
                     p0 = __fmul_rn(th[q], cs);
                     p1 = __fmul_rn(-th[q], sn);
                 }
-                if (!ok[q]) p0 = p1 = 0.0f;
+                if (q >= nfeat) p0 = p1 = 0.0f;          // F not a multiple of 4: the tail of the last chunk
                 split_f16(p0, hi[2 * q], lo[2 * q]);
                 split_f16(p1, hi[2 * q + 1], lo[2 * q + 1]);
             }
-            __half* blk = out + ((g * ntile + tile) * nst + st) * (int64_t)(2 * 8 * TR * 8);   // halves per block
-            const int64_t o = (chunk * TR + r) * 8;
-            *reinterpret_cast<uint4*>(blk + o) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(blk + 8 * TR * 8 + o) = *reinterpret_cast<const uint4*>(lo);
+            __half* blk = tile_out + (int64_t)st * blk_halves + chunk * TR * 8;
+            *reinterpret_cast<uint4*>(blk) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(blk + lo_off) = *reinterpret_cast<const uint4*>(lo);
         }
     }
+}
+template <int NC>
+static void prod_build_tc_launch_t(dim3 grid, int threads, cudaStream_t st, const double* cand, int64_t nrow,
+                                   int64_t row_stride, int d, int s_lo, int s_hi, int which, const double* W, const double* b,
+                                   const double* theta, int64_t j0, int64_t F, int w_shared, int64_t ntile, int64_t nst,
+                                   const double* tmax, __half* out, int chunk_lo, int TR) {
+    static const bool once = [] {     // the whole 228 KB as shared memory: a build CTA fits beside a persistent GEMM CTA
+        cudaFuncSetAttribute(prod_build_tc_kernel_t<NC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        return true;
+    }();
+    (void)once;
+    prod_build_tc_kernel_t<NC><<<grid, threads, 0, st>>>(cand, nrow, row_stride, d, s_lo, s_hi, which, W, b, theta, j0, F,
+                                                         w_shared, ntile, nst, tmax, out, chunk_lo, TR);
+}
+static void launch_prod_build_tc(dim3 grid, int threads, cudaStream_t st, const double* cand, int64_t nrow,
+                                 int64_t row_stride, int d, int s_lo, int s_hi, int which, const double* W, const double* b,
+                                 const double* theta, int64_t j0, int64_t F, int w_shared, int64_t ntile, int64_t nst,
+                                 const double* tmax, __half* out, int chunk_lo, int TR) {
+    const int ncol = which == 0 ? s_hi - s_lo : d - (s_hi - s_lo);
+#define PB_ARGS grid, threads, st, cand, nrow, row_stride, d, s_lo, s_hi, which, W, b, theta, j0, F, w_shared, ntile, nst, tmax, out, chunk_lo, TR
+    switch (ncol) {
+        case 1: prod_build_tc_launch_t<1>(PB_ARGS); break;
+        case 2: prod_build_tc_launch_t<2>(PB_ARGS); break;
+        case 3: prod_build_tc_launch_t<3>(PB_ARGS); break;
+        case 4: prod_build_tc_launch_t<4>(PB_ARGS); break;
+        case 5: prod_build_tc_launch_t<5>(PB_ARGS); break;
+        case 6: prod_build_tc_launch_t<6>(PB_ARGS); break;
+        default: prod_build_tc_launch_t<0>(PB_ARGS); break;
+    }
+#undef PB_ARGS
 }
 
 static int tc_sm_count() {
@@ -2872,7 +2926,6 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
                                          (int)(3 * T8_STAGE_BYTES + 256)));
         // the whole 228 KB as shared memory, so that a build CTA of the second stream (30 KB) fits beside the GEMM CTA
         TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc8_kernel<0, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        TES_CUDA_OK(cudaFuncSetAttribute(prod_build_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc8_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(6 * T8_STAGE_BYTES / 2 + 256)));
         TES_CUDA_OK(cudaFuncSetAttribute(prod_gemm_topk_tc8_kernel<1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2934,11 +2987,9 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
             auto build = [&](int64_t jj0, int64_t GG, int buf, cudaStream_t bs, int threads) -> int {
                 __half* ph_ = Hhi + buf * pbuf;
                 __half* qh_ = Ghi + buf * qbuf;
-                prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)GG, 8), threads, 0, bs>>>(
-                    cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, jj0, F, w_shared, 2 * ntu2, nst, tmax, ph_, 0, 128);
+                launch_prod_build_tc(dim3((unsigned)ntu, (unsigned)GG, 8), threads, bs, cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, jj0, F, w_shared, 2 * ntu2, nst, tmax, ph_, 0, 128);
                 TES_LAUNCH_OK();
-                prod_build_tc_kernel<<<dim3((unsigned)ntv, (unsigned)GG, 8), threads, 0, bs>>>(
-                    cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, jj0, F, w_shared, 2 * ntv2, nst, tmax, qh_, 0, 128);
+                launch_prod_build_tc(dim3((unsigned)ntv, (unsigned)GG, 8), threads, bs, cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, jj0, F, w_shared, 2 * ntv2, nst, tmax, qh_, 0, 128);
                 TES_LAUNCH_OK();
                 return 0;
             };
@@ -2987,11 +3038,9 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
             const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK, ntu2 = (ntu + 1) / 2;
             // P: 128-row tiles, 2 ntu2 of them per sample (an odd count is padded with the zero tile of the memset);
             // Q: 64-column tiles, 2 ntv per sample (each CTA of a pair stages one half of a 128-column tile)
-            prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)G, 8), 256, 0, st>>>(
-                cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, 2 * ntu2, nst, tmax, Hhi, 0, 128);
+            launch_prod_build_tc(dim3((unsigned)ntu, (unsigned)G, 8), 256, st, cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, 2 * ntu2, nst, tmax, Hhi, 0, 128);
             TES_LAUNCH_OK();
-            prod_build_tc_kernel<<<dim3((unsigned)(2 * ntv), (unsigned)G, 8), 256, 0, st>>>(
-                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, 2 * ntv, nst, tmax, Ghi, 0, 64);
+            launch_prod_build_tc(dim3((unsigned)(2 * ntv), (unsigned)G, 8), 256, st, cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, 2 * ntv, nst, tmax, Ghi, 0, 64);
             TES_LAUNCH_OK();
             const int64_t ntot = ntu2 * ntv * G;
             int64_t ncta = 2 * ntot < tc_sm_count() ? 2 * ntot : (tc_sm_count() / 2) * 2;
@@ -3001,12 +3050,10 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
         } else if (tf32 >= 4) {
             const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK;
             if (gen_gc < 8) {   // the streamed half of the P blocks
-                prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)G, 8), 256, 0, st>>>(
-                    cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, ntu, nst, tmax, Hhi, gen_gc, 128);
+                launch_prod_build_tc(dim3((unsigned)ntu, (unsigned)G, 8), 256, st, cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, ntu, nst, tmax, Hhi, gen_gc, 128);
                 TES_LAUNCH_OK();
             }
-            prod_build_tc_kernel<<<dim3((unsigned)ntv, (unsigned)G, 8), 256, 0, st>>>(
-                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, ntv, nst, tmax, Ghi, 0, 128);
+            launch_prod_build_tc(dim3((unsigned)ntv, (unsigned)G, 8), 256, st, cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, ntv, nst, tmax, Ghi, 0, 128);
             TES_LAUNCH_OK();
             int rc = -18;
 #define PG_CASE(NC)                                                                                                  \
@@ -3024,11 +3071,9 @@ extern "C" int tes_rff_topk_product_f64(const double* cand, int64_t N, int64_t d
             if (rc) return rc;
         } else if (tf32 == 3) {
             const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK;
-            prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)G, 8), 256, 0, st>>>(
-                cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, ntu, nst, tmax, Hhi, 0, 128);
+            launch_prod_build_tc(dim3((unsigned)ntu, (unsigned)G, 8), 256, st, cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, ntu, nst, tmax, Hhi, 0, 128);
             TES_LAUNCH_OK();
-            prod_build_tc_kernel<<<dim3((unsigned)ntv, (unsigned)G, 8), 256, 0, st>>>(
-                cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, ntv, nst, tmax, Ghi, 0, 128);
+            launch_prod_build_tc(dim3((unsigned)ntv, (unsigned)G, 8), 256, st, cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, ntv, nst, tmax, Ghi, 0, 128);
             TES_LAUNCH_OK();
             const int64_t ntot = ntu * ntv * G;
             dim3 gtc((unsigned)(ntot < tc_sm_count() ? ntot : tc_sm_count()), 1, 1);
@@ -3173,11 +3218,9 @@ extern "C" int tes_rff_topk_product_resolve_f64(const double* cand, int64_t N, i
     const int64_t ntu = pl.gx, ntv = pl.gy, nst = pl.K2p / TC_BK, ntu2 = (ntu + 1) / 2, ntv2 = (ntv + 1) / 2;
     for (int64_t j0 = 0; j0 < S; j0 += pl.G) {
         const int64_t G = (S - j0 < pl.G) ? (S - j0) : pl.G;
-        prod_build_tc_kernel<<<dim3((unsigned)ntu, (unsigned)G, 8), 256, 0, st>>>(
-            cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, 2 * ntu2, nst, tmax, Hhi, 0, 128);
+        launch_prod_build_tc(dim3((unsigned)ntu, (unsigned)G, 8), 256, st, cand, nu, nv, (int)d, (int)s_lo, (int)s_hi, 0, W, b, theta, j0, F, w_shared, 2 * ntu2, nst, tmax, Hhi, 0, 128);
         TES_LAUNCH_OK();
-        prod_build_tc_kernel<<<dim3((unsigned)ntv, (unsigned)G, 8), 256, 0, st>>>(
-            cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, 2 * ntv2, nst, tmax, Ghi, 0, 128);
+        launch_prod_build_tc(dim3((unsigned)ntv, (unsigned)G, 8), 256, st, cand, nv, 1, (int)d, (int)s_lo, (int)s_hi, 1, W, b, theta, j0, F, w_shared, 2 * ntv2, nst, tmax, Ghi, 0, 128);
         TES_LAUNCH_OK();
         const int64_t ntot = ntu2 * ntv2 * G;
         const int64_t ncta = 2 * ntot < tc_sm_count() ? 2 * ntot : (tc_sm_count() / 2) * 2;
