@@ -621,6 +621,18 @@ def main():
                 "ms_per_step": r3["ms_per_step"], "steps": 2, "warmup": 1, "stage_ms": r3["stages"]}
         del r3
         torch.cuda.empty_cache()
+        # ---- the general case: C3 shapes on UNSTRUCTURED candidates (no product path: tcgen05 screen, MUFU-bound)
+        wu = make_workload("c3u", rank, world)
+        ru = bench.run(wu, 3, 1, want_e2e=False)
+        if rank == 0:
+            secondary["c3u"] = {"workload": wu["desc"], "value": ru["value"], "unit": "evals/s",
+                                "ms_per_step": ru["ms_per_step"], "steps": 3, "warmup": 1, "n_gpus": world,
+                                "stage_ms": ru["stages"],
+                                "roofline": {k: v for k, v in roofline_of(wu, ru, None, peaks, fp64_peak, fp32_peak,
+                                                                          mufu_peak).items()
+                                             if k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "share_of_step")}}
+        del wu, ru
+        torch.cuda.empty_cache()
         if world > 1:
             # ---- strong scaling: the SAME global 10^6-point mesh split over the ranks
             ws = make_workload("c3", 0, 1)

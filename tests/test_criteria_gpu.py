@@ -250,10 +250,13 @@ def test_tes_sp_whitened_kernel_far_components_and_nan():
 
 @pytest.mark.parametrize("hyp,d,n,T,nx,mode", [(HART6, 6, 30, 20, 40_001, "empirical"), (BRANIN, 2, 6, 9, 19_000, "empirical"),
                                                (PH, 2, 20, 7, 400, "ep"), (HART6, 6, 40, 70, 20_000, "empirical")])
-def test_tes_ep_screen_bound_holds(hyp, d, n, T, nx, mode):
+@pytest.mark.parametrize("tri", ["1", "0"])
+def test_tes_ep_screen_bound_holds(hyp, d, n, T, nx, mode, tri, monkeypatch):
     """ops.ep_acq_screen: the 3xFP16 tcgen05 screen of the deterministic criterion stays within its own proven bound of
-    the fp64 criterion on every candidate, and the bound is small enough to prune."""
+    the fp64 criterion on every candidate, and the bound is small enough to prune.  tri = 1: triangular GEMM with the
+    tile of M as the A operand (default); 0: index-pair GEMM with the A operand generated on the SM."""
     from tes_b200 import ops
+    monkeypatch.setenv("TES_QUAD_TRI", tri)
     pr = make_problem(seed=11 + T, d=d, n=n, T=T, nx=nx, hyp=hyp, mode=mode, nsample=max(600, 40 * T))
     p, pm, pc = _ep_inputs(pr)
     exact = ops.ep_acq(ops.EP_DETERMINISTIC, pr["x"], pr["test_xs"], pr["X"], pr["Y"], pr["l"], pr["sigma"], pr["sigma0"],

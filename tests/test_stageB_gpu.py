@@ -135,6 +135,12 @@ def test_argmax_first_maximum_and_nan():
     v[70_000] = np.nan
     i, val = ops.argmax(v)
     assert int(i) == int(np.argmax(v)) == 60_000 and np.isnan(float(val))
+    v[100] = np.inf                      # np.argmax ranks NaN above +inf: still the first NaN
+    i, val = ops.argmax(v)
+    assert int(i) == int(np.argmax(v)) == 60_000 and np.isnan(float(val))
+    v[[60_000, 70_000]] = 0.0
+    i, val = ops.argmax(v)
+    assert int(i) == 100 and float(val) == np.inf
     i, val = ops.argmax(np.array([3.0]))
     assert int(i) == 0
 

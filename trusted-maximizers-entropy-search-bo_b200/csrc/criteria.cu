@@ -913,7 +913,7 @@ extern "C" int64_t tes_ep_acq_screen_workspace_bytes(int64_t N, int64_t T, int64
     const int64_t Ks = quad_screen_kdim(T);
     return pl.total + quad_screen_a_bytes(pl.nc, Ks) + quad_screen_b_bytes(Ks) + align_up(pl.nc * 8, 256) +
            align_up(T * Sp * 8, 256) + align_up(pl.nc * T * 8, 256) + align_up(Ks * Sp * 8, 256) +
-           align_up(T * 128 * 4, 256);
+           align_up(T * 128 * 4, 256) + (T <= 128 ? quad_tri_b_bytes(T) + 256 * 8 : 0);
 }
 
 extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, const double* test_xs, int64_t T,
@@ -961,6 +961,13 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
     double* Bscr = (double*)extra;                   // Ks x Sp
     extra += align_up(Ks * Sp * 8, 256);
     float* Df = (float*)extra;                       // T x 128 floats, rounded up
+    extra += align_up(T * 128 * 4, 256);
+    void* Btri = extra;                              // triangular variant: row blocks of the packed covariances
+    double* colmax_tri = (double*)(extra + (T <= 128 ? quad_tri_b_bytes(T) : 0));     // [colmax (128) | colscale (128)]
+    // quadratic forms: triangular GEMM (A = the tile of M, no generated operand) for T <= 128; TES_QUAD_TRI=0: the
+    // index-pair GEMM with the generated / streamed A operand
+    const char* tmode = std::getenv("TES_QUAD_TRI");
+    const bool tri = T <= 128 && !(tmode && tmode[0] == '0');
     double* Hb = (double*)(base + pl.off_mean);      // nc x Sp (the mean buffer is unused in this mode)
     // bound H on the fp32 pipe inside the criterion kernel whenever its operands fit in shared memory
     const size_t eds_smem = ((size_t)T * 128 + (size_t)EDS_WARPS * T * EDS_ROWS) * sizeof(float);
@@ -973,17 +980,30 @@ extern "C" int tes_ep_acq_screen_f64(const double* x, int64_t N, int64_t d, cons
     int rc;
     if ((rc = launch_concat_rows(test_xs, T, X, n, (int)d, xto, st))) return rc;
     if ((rc = launch_build_bext(invpNK, Y, m, T, Bext, st))) return rc;
-    if ((rc = launch_quad_screen_ab(post_cov, Sp, T, colmax, Bscr, st))) return rc;
-    if ((rc = launch_quad_screen_build_b(Bscr, Ks, Sp, Btc, colmax, st))) return rc;
+    if (tri) {
+        if ((rc = launch_quad_tri_build_b(post_cov, Sp, T, Btri, colmax_tri, st))) return rc;
+        colmax = colmax_tri;
+    } else {
+        if ((rc = launch_quad_screen_ab(post_cov, Sp, T, colmax, Bscr, st))) return rc;
+        if ((rc = launch_quad_screen_build_b(Bscr, Ks, Sp, Btc, colmax, st))) return rc;
+    }
     screen_diag_kernel<<<fuse_h ? 128u : (unsigned)Sp, 256, 0, st>>>(post_cov, Sp, T, Dm, fuse_h ? Df : nullptr);
     TES_LAUNCH_OK();
-    const double kabs = QS_ABS * (double)quad_screen_kp(Ks);
+    // absolute (fp16-subnormal) term of the bound: per (a, b) term (|A| + |B|) 2^-25 in scaled units -- index-pair GEMM:
+    // A = products <= 4096, B <= 8; triangular GEMM: A = M~ <= 64, B <= 8 inside the MMA, times M~_a <= 64 in the
+    // epilogue, whose own floor adds 64 * 8: 64 * 80 per term -- over the T (T + 1) / 2 terms, unscaled by 4096 * 8
+    const double kabs = tri ? 1.5 * 64.0 * 80.0 * 2.98023223876953125e-08 / 32768.0 * (double)quad_tri_terms(T)
+                            : QS_ABS * (double)quad_screen_kp(Ks);
     for (int64_t c0 = 0; c0 < N; c0 += PS_SCREEN_CHUNK) {
         const int64_t nc = (N - c0 < PS_SCREEN_CHUNK) ? (N - c0) : PS_SCREEN_CHUNK;
         if ((rc = launch_se_ard(x + c0 * d, nc, xto, m, (int)d, l, sigma, -1, 0.0, Kc, m, st))) return rc;
         if ((rc = launch_gemm(Kc, m, Bext, m + 1, 1, Gc, m + 1, nc, m + 1, m, st))) return rc;
         if (!fuse_h && (rc = launch_rowdot(Gc, m + 1, Kc, m, nc, m, sigma, -INFINITY, Kq, st))) return rc;
-        if ((rc = launch_quad_screen(Gc, m + 1, nc, T, Ks, Btc, colmax, Sp, Atc, rowmax, varc, st))) return rc;
+        if (tri) {
+            if ((rc = launch_quad_screen_tri(Gc, m + 1, nc, T, Btri, colmax, Sp, rowmax, varc, st))) return rc;
+        } else if ((rc = launch_quad_screen(Gc, m + 1, nc, T, Ks, Btc, colmax, Sp, Atc, rowmax, varc, st))) {
+            return rc;
+        }
         if ((rc = launch_gemm(Kc + T, m, invKobs, n, 1, Gobs, n, nc, n, n, st))) return rc;
         if (!fuse_h && (rc = launch_rowdot(Gobs, n, Kc + T, m, nc, n, sigma, 1e-100, varf, st))) return rc;
         if (fuse_h) {

@@ -66,6 +66,12 @@ int64_t quad_screen_a_bytes(int64_t nc, int64_t Kdim);                  // opera
 int64_t quad_screen_b_bytes(int64_t Kdim);                              // operand B (all maximizers, <= 128)
 int launch_quad_screen_build_b(const double* Bpack, int64_t Kdim, int64_t Sp, void* Btc, double* colmax, cudaStream_t st);
 int64_t quad_screen_kdim(int64_t T);                                    // K of the screen (run order, see rffprod.cu)
+// triangular variant (T <= 128): A = the tile of M, B = row blocks of the packed covariances, dot with M in the epilogue
+int64_t quad_tri_b_bytes(int64_t T);
+int64_t quad_tri_terms(int64_t T);
+int launch_quad_tri_build_b(const double* cov, int64_t Sp, int64_t T, void* Btri, double* colmax, cudaStream_t st);
+int launch_quad_screen_tri(const double* G, int64_t ldg, int64_t nc, int64_t T, const void* Btri, const double* colmax,
+                           int64_t Sp, double* rowmax, double* Qout, cudaStream_t st);
 int launch_quad_screen_ab(const double* cov, int64_t Sp, int64_t T, double* colmax, double* Bpack, cudaStream_t st);
 int launch_quad_screen(const double* G, int64_t ldg, int64_t nc, int64_t T, int64_t Kdim, const void* Btc,
                        const double* colmax, int64_t Sp, void* Atc, double* rowmax, double* Qout, cudaStream_t st);

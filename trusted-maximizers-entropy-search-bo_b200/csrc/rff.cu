@@ -1819,55 +1819,70 @@ extern "C" int tes_cosf_error_probe(float lo, float hi, double e1, int which, do
 
 // arg-max of a vector, first maximum wins (tf.argmax / np.argmax; bo_discrete.py:806, :1053-1055).
 namespace tes {
+__device__ __forceinline__ int64_t warp_min_i64(int64_t v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const int64_t o = __shfl_xor_sync(0xffffffffu, v, off);
+        v = o < v ? o : v;
+    }
+    return v;
+}
+// np.argmax / tf.argmax treat NaN as the maximum: the FIRST NaN wins, also over a +inf at a lower index.  A block that
+// saw a NaN reports (NaN, index of its first NaN); the final kernel takes the lowest such index.
 __global__ void argmax_partial_kernel(const double* __restrict__ v, int64_t N, double* __restrict__ pv,
                                       int64_t* __restrict__ pi) {
     double bv = neg_inf();
     int64_t bi = INT64_MAX;
-    bool has_nan = false;
     int64_t nan_i = INT64_MAX;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (int64_t)gridDim.x * blockDim.x) {
         double x = v[e];
-        if (x != x) {  // numpy/TF arg-max return the first NaN
+        if (x != x) {
             if (e < nan_i) nan_i = e;
-            has_nan = true;
         } else if (better(x, e, bv, bi)) {
             bv = x;
             bi = e;
         }
     }
-    if (has_nan) {
-        bv = pos_inf();
-        bi = nan_i;
-    }
     warp_argmax(bv, bi);
+    nan_i = warp_min_i64(nan_i);
     __shared__ double sv[32];
-    __shared__ int64_t si[32];
+    __shared__ int64_t si[32], sn[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
         sv[warp] = bv;
         si[warp] = bi;
+        sn[warp] = nan_i;
     }
     __syncthreads();
     if (warp == 0) {
         bv = lane < (blockDim.x >> 5) ? sv[lane] : neg_inf();
         bi = lane < (blockDim.x >> 5) ? si[lane] : INT64_MAX;
+        nan_i = lane < (blockDim.x >> 5) ? sn[lane] : INT64_MAX;
         warp_argmax(bv, bi);
+        nan_i = warp_min_i64(nan_i);
         if (lane == 0) {
-            pv[blockIdx.x] = bv;
-            pi[blockIdx.x] = bi == INT64_MAX ? -1 : bi;
+            const bool has_nan = nan_i != INT64_MAX;
+            pv[blockIdx.x] = has_nan ? __longlong_as_double(0x7ff8000000000000LL) : bv;
+            pi[blockIdx.x] = has_nan ? nan_i : (bi == INT64_MAX ? -1 : bi);
         }
     }
 }
 __global__ void argmax_final_kernel(const double* __restrict__ v, const double* __restrict__ pv,
                                     const int64_t* __restrict__ pi, int nb, double* out_val, int64_t* out_idx) {
     double bv = neg_inf();
-    int64_t bi = INT64_MAX;
-    for (int e = threadIdx.x; e < nb; e += 32)
-        if (pi[e] >= 0 && better(pv[e], pi[e], bv, bi)) {
+    int64_t bi = INT64_MAX, nan_i = INT64_MAX;
+    for (int e = threadIdx.x; e < nb; e += 32) {
+        if (pi[e] < 0) continue;
+        if (pv[e] != pv[e]) {
+            if (pi[e] < nan_i) nan_i = pi[e];
+        } else if (better(pv[e], pi[e], bv, bi)) {
             bv = pv[e];
             bi = pi[e];
         }
+    }
     warp_argmax(bv, bi);
+    nan_i = warp_min_i64(nan_i);
+    if (nan_i != INT64_MAX) bi = nan_i;
     if (threadIdx.x == 0) {
         *out_idx = bi == INT64_MAX ? -1 : bi;
         *out_val = bi == INT64_MAX ? neg_inf() : v[bi];  // a NaN winner reports NaN

@@ -2262,6 +2262,336 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
 }
 
+// ---- triangular variant: no generated operand at all ------------------------------------------------------------------
+// q_j(x) = sum_a M_a Y_ja,  Y_ja = sum_{b <= a} c_ab(j) M_b,  c_aa = Sigma_j[a][a], c_ab = Sigma_j[a][b] + Sigma_j[b][a]:
+// for every a ("a-block") ONE small GEMM  C_a[x][j] = sum_{b <= a} M[x][b] c_ab(j)  with A = the tile of M itself (fp16
+// hi / lo, resident in shared memory for the whole tile: no products to generate) and B_a = the a-th row block of the
+// packed covariances, K = a + 1 rounded up to 32 -- the same MMA count as the index-pair formulation (the triangle),
+// and the dot with M_a happens in the epilogue: acc[x][j] += M~[x][a] C_a[x][j] (one tcgen05.ld + 32 FFMA per thread
+// and a-block).  ncu of the fused kernel above: bound by its generator (8192 products + splits per 64-k stage, tensor
+// pipe ~35 %).  Here the 16 epilogue warps only drain.  A CTA owns TWO 128-row tiles at once: both share every B unit
+// (the B stream per SM halves: 5 MB per chunk at T = 125), the four 128-column accumulators (2 tiles x 2 buffers) fill
+// the tensor memory.  T <= 128, S' <= 128.
+// B layout: units of 32 k x 128 columns: [hi | lo][4 chunks of 8 k][128 columns][8 halves] = 16 KB; a-block a has
+// ceil((a + 1) / 32) units; unit index u(a, n) = 16 g (g + 1) + (g + 1)(a - 32 g) + n, g = a / 32.
+constexpr int QT_NS = 5;                                   // B units in flight (80 KB)
+constexpr uint32_t QT_UNIT_BYTES = 2 * 4 * 128 * 16;       // 16 KB
+__host__ __device__ inline int64_t qt_unit_index(int64_t a, int64_t n) {
+    const int64_t g = a / 32;
+    return 16 * g * (g + 1) + (g + 1) * (a - 32 * g) + n;
+}
+__host__ __device__ inline int64_t qt_units(int64_t T) { return qt_unit_index(T, 0); }
+// colmax[j] = max over the packed coefficients |c_ab(j)| (NaN ignored, like quad_colmax_kernel); one CTA per j
+__global__ void __launch_bounds__(256) quad_tri_colmax_kernel(const double* __restrict__ cov, int64_t Sp, int64_t T,
+                                                              double* __restrict__ colmax, double* __restrict__ colscale) {
+    __shared__ double red[256];
+    const int64_t j = blockIdx.x;
+    const double* c = cov + j * T * T;
+    double m = 0.0;
+    for (int64_t e = threadIdx.x; e < T * T; e += blockDim.x) {
+        const int64_t a = e / T, b = e % T;
+        if (b > a) continue;
+        double r = c[a * T + b];
+        if (a != b) r += c[b * T + a];
+        m = fmax(m, fabs(r));
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        colmax[j] = red[0];
+        colscale[j] = red[0] / QS_BMAX;
+    }
+}
+// thread = (unit, chunk of 8 k, column j): 8 coefficients, scaled to max QS_BMAX per column, hi / lo split
+__global__ void quad_tri_build_b_kernel(const double* __restrict__ cov, int64_t Sp, int64_t T,
+                                        const double* __restrict__ colmax, __half* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nu = qt_units(T);
+    if (t >= nu * 4 * 128) return;
+    const int64_t j = t % 128, chunk = (t / 128) % 4, u = t / 512;
+    // (a, n) of unit u: invert u(a, n) group by group
+    int64_t g = 0;
+    while (16 * (g + 1) * (g + 2) <= u) ++g;
+    const int64_t r = u - 16 * g * (g + 1), a = 32 * g + r / (g + 1), n = r % (g + 1);
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) hi[e] = lo[e] = __float2half_rn(0.0f);
+    if (j < Sp && a < T) {
+        const double cm = colmax[j];
+        const double sc = cm > 0.0 ? QS_BMAX / cm : 0.0;
+        const double* c = cov + j * T * T;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int64_t b = 32 * n + 8 * chunk + e;
+            if (b <= a) {
+                double v = c[a * T + b];
+                if (a != b) v += c[b * T + a];
+                split_f16((float)(v * sc), hi[e], lo[e]);
+            }
+        }
+    }
+    __half* blk = out + u * (int64_t)(QT_UNIT_BYTES / 2);
+    const int64_t o = (chunk * 128 + j) * 8;
+    *reinterpret_cast<uint4*>(blk + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(blk + 4 * 128 * 8 + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    quad_screen_tri_kernel(const double* __restrict__ G, int64_t ldg, int64_t nc, int T, const __half* __restrict__ Bt,
+                           int64_t Sp, int64_t npair, double* __restrict__ rowmax, const double* __restrict__ colscale,
+                           double* __restrict__ Qout) {
+    extern __shared__ __align__(1024) unsigned char qt_smem_raw[];
+    unsigned char* Aop = qt_smem_raw;                                   // [2 tiles][2 blocks of 64 k][hi | lo] = 128 KB
+    unsigned char* Bring = qt_smem_raw + 4 * TC_BLOCK_BYTES;            // [QT_NS][16 KB]
+    double* rmax_s = reinterpret_cast<double*>(Bring + QT_NS * QT_UNIT_BYTES);      // [256]
+    double* cs_s = rmax_s + 256;                                                    // [128] colscale
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cs_s + 128);
+    uint64_t* full_b = bars;                 // [QT_NS] producer -> MMA
+    uint64_t* empty_b = bars + QT_NS;        // [QT_NS] MMA (commit) -> producer
+    uint64_t* acc_full = bars + 2 * QT_NS;   // [2] MMA (commit) -> epilogue
+    uint64_t* acc_empty = acc_full + 2;      // [2] epilogue -> MMA
+    uint64_t* a_full = acc_empty + 2;        // [1] epilogue warps (A operands of the pair written) -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t nmine = blockIdx.x < npair ? (npair - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int nunit_all = (int)qt_units(T);
+    if (tid == 0) {
+        for (int s = 0; s < QT_NS; ++s) {
+            mbar_init(&full_b[s], 1);
+            mbar_init(&empty_b[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], TC_EPI_WARPS);
+        }
+        mbar_init(a_full, TC_EPI_WARPS);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid < 128) cs_s[tid] = tid < Sp ? colscale[tid] : 0.0;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const unsigned char* srcB = reinterpret_cast<const unsigned char*>(Bt);
+            uint32_t s = 0, ph = 0;
+            for (int64_t it = 0; it < nmine; ++it)
+                for (int u = 0; u < nunit_all; ++u) {
+                    mbar_wait_relaxed(&empty_b[s], ph ^ 1u, 32);
+                    mbar_expect_tx(&full_b[s], QT_UNIT_BYTES);
+                    bulk_g2s(Bring + s * QT_UNIT_BYTES, srcB + (int64_t)u * QT_UNIT_BYTES, QT_UNIT_BYTES, &full_b[s]);
+                    if (++s == QT_NS) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc_f16(128, 128);
+            // shared-memory descriptors: only the start-address field (bits 0-13, units of 16 bytes) changes between
+            // MMAs, so they are formed once and advanced by 32-bit adds -- the issue thread is a single dependent
+            // instruction stream and ncu showed it, not the tensor pipe, bounding the a-loop (80 instructions per
+            // K16 step, 35 of them rebuilding descriptors: 770 cycles per step for 384 cycles of MMA work)
+            const uint64_t d0 = tc_desc(smem_u32(Aop), 128 * 16, 128);
+            const uint32_t dhi = (uint32_t)(d0 >> 32), a_lo32 = (uint32_t)d0;
+            const uint32_t b_lo32 = (uint32_t)tc_desc(smem_u32(Bring), 128 * 16, 128);
+            auto mk = [&](uint32_t lo32) { return ((uint64_t)dhi << 32) | (uint64_t)lo32; };
+            int64_t gs = 0;
+            uint32_t s = 0, ph = 0;                                   // B ring slot and phase
+            for (int64_t it = 0; it < nmine; ++it) {
+                mbar_wait_relaxed(a_full, (uint32_t)(it & 1), 32);
+                tc_fence_after();
+                for (int a = 0; a < T; ++a, ++gs) {
+                    const uint32_t buf = (uint32_t)(gs & 1), pa = (uint32_t)((gs >> 1) & 1);
+                    mbar_wait_relaxed(&acc_empty[buf], pa ^ 1u, 32);
+                    tc_fence_after();
+                    const int nun = a / 32 + 1;
+                    const uint32_t d_t0 = tmem + buf * 128u, d_t1 = d_t0 + 256u;
+                    for (int n = 0; n < nun; ++n) {
+                        mbar_wait_relaxed(&full_b[s], ph, 32);
+                        tc_fence_after();
+                        const uint32_t sb = b_lo32 + s * (QT_UNIT_BYTES >> 4);
+                        const int nk16 = (a + 1 - 32 * n) > 16 ? 2 : 1;       // the second half of the unit may be all zero
+                        for (int h = 0; h < nk16; ++h) {
+                            const int kk = 2 * n + h;                          // K16 step of the A operand (0 .. 7)
+                            const uint32_t sa = a_lo32 + (uint32_t)(kk >> 2) * (TC_BLOCK_BYTES >> 4) + (uint32_t)(kk & 3) * 256u;
+                            const uint64_t b_hi = mk(sb + (uint32_t)h * 256u), b_lo = mk(sb + (uint32_t)h * 256u + (QT_UNIT_BYTES >> 5));
+                            const uint64_t a0_hi = mk(sa), a0_lo = mk(sa + (TC_BLOCK_BYTES >> 5));
+                            const uint64_t a1_hi = mk(sa + (TC_BLOCK_BYTES >> 3)), a1_lo = mk(sa + (TC_BLOCK_BYTES >> 3) + (TC_BLOCK_BYTES >> 5));
+                            const uint32_t first = (n == 0 && h == 0) ? 0u : 1u;
+                            tc_mma_f16(d_t0, a0_lo, b_hi, idesc, first);
+                            tc_mma_f16(d_t1, a1_lo, b_hi, idesc, first);
+                            tc_mma_f16(d_t0, a0_hi, b_lo, idesc, 1u);
+                            tc_mma_f16(d_t1, a1_hi, b_lo, idesc, 1u);
+                            tc_mma_f16(d_t0, a0_hi, b_hi, idesc, 1u);
+                            tc_mma_f16(d_t1, a1_hi, b_hi, idesc, 1u);
+                        }
+                        tc_commit(&empty_b[s]);
+                        if (++s == QT_NS) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                    tc_commit(&acc_full[buf]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int ew = warp - 2;
+        const int quarter = warp & 3, cb = ew >> 2;
+        const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32);
+        const int te = tid - 64;
+        const int xr = quarter * 32 + lane;                       // this thread's row inside a tile (TMEM lane)
+        int64_t gs = 0;
+        for (int64_t it = 0; it < nmine; ++it) {
+            const int64_t pr = blockIdx.x + it * gridDim.x;
+            // ---- A operands of the pair: a warp per row, lanes over the T columns; row maximum, scale 64 / max,
+            // hi / lo halves straight into the MMA layout ([block of 64 k][hi | lo][chunk][row][8]); k >= T stays zero
+            asm volatile("bar.sync 1, 512;" ::: "memory");        // every warp is done reading the previous pair's M~
+            for (int e = te; e < (int)(4 * TC_BLOCK_BYTES / 16); e += 512) reinterpret_cast<uint4*>(Aop)[e] = make_uint4(0, 0, 0, 0);
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            for (int r0 = te >> 5; r0 < 256; r0 += 2 * TC_EPI_WARPS) {
+                double gv[2][4], rm[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int rr = r0 + u * TC_EPI_WARPS;
+                    const int64_t grow = pr * 256 + rr;
+                    const double* gp = G + grow * ldg;
+                    rm[u] = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int a = lane + 32 * q;
+                        gv[u][q] = (grow < nc && a < T) ? gp[a] : 0.0;
+                        rm[u] = fmax(rm[u], fabs(gv[u][q]));      // fmax ignores NaN, like the row maximum of the other paths
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    rm[0] = fmax(rm[0], __shfl_xor_sync(0xffffffffu, rm[0], off));
+                    rm[1] = fmax(rm[1], __shfl_xor_sync(0xffffffffu, rm[1], off));
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int rr = r0 + u * TC_EPI_WARPS;
+                    const int64_t grow = pr * 256 + rr;
+                    const double sc = rm[u] > 0.0 ? 64.0 / rm[u] : 0.0;                 // 64^2 = QS_AMAX
+                    if (lane == 0) {
+                        rmax_s[rr] = rm[u];
+                        if (grow < nc) rowmax[grow] = rm[u];
+                    }
+                    if (grow < nc && sc != 0.0) {
+                        unsigned char* tb = Aop + (rr >> 7) * 2 * TC_BLOCK_BYTES;
+                        const int x = rr & 127;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int a = lane + 32 * q;
+                            if (a < T) {
+                                __half h, l;
+                                split_f16((float)(gv[u][q] * sc), h, l);
+                                unsigned char* p = tb + (a >> 6) * TC_BLOCK_BYTES + ((((a & 63) >> 3) * 128 + x) * 8 + (a & 7)) * 2;
+                                *reinterpret_cast<__half*>(p) = h;
+                                *reinterpret_cast<__half*>(p + TC_BLOCK_BYTES / 2) = l;
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to the MMA
+            __syncwarp();
+            if (lane == 0) tc_arrive(a_full);
+            asm volatile("bar.sync 1, 512;" ::: "memory");        // M~ of every row is readable below
+
+            float acc[2][32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[0][c] = acc[1][c] = 0.0f;
+            for (int a = 0; a < T; ++a, ++gs) {
+                const uint32_t buf = (uint32_t)(gs & 1), pa = (uint32_t)((gs >> 1) & 1);
+                // M~[x][a] = hi + lo exactly as the tensor core saw it
+                const uint32_t mo = (uint32_t)(a >> 6) * TC_BLOCK_BYTES + (uint32_t)(((((a & 63) >> 3) * 128 + xr) * 8 + (a & 7)) * 2);
+                float mt[2];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const unsigned char* p = Aop + t * 2 * TC_BLOCK_BYTES + mo;
+                    mt[t] = __half2float(*reinterpret_cast<const __half*>(p)) +
+                            __half2float(*reinterpret_cast<const __half*>(p + TC_BLOCK_BYTES / 2));
+                }
+                mbar_wait(&acc_full[buf], pa);
+                tc_fence_after();
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        uint32_t v0[16];
+                        TC_LD16(v0, t_lane + (uint32_t)t * 256u + buf * 128u + (uint32_t)(q * 16));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) acc[t][q * 16 + c] = fmaf(mt[t], __uint_as_float(v0[c]), acc[t][q * 16 + c]);
+                    }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc_arrive(&acc_empty[buf]);
+            }
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int64_t row = pr * 256 + t * 128 + xr;
+                if (row < nc) {
+                    const double rm = rmax_s[t * 128 + xr];
+                    const double rs = rm * rm / QS_AMAX;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (cb * 32 + c < Sp) Qout[row * Sp + cb * 32 + c] = rs * cs_s[cb * 32 + c] * (double)acc[t][c];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    }
+}
+
+int64_t quad_tri_b_bytes(int64_t T) { return align_up(qt_units(T) * (int64_t)QT_UNIT_BYTES, 256); }
+int64_t quad_tri_terms(int64_t T) { return T * (T + 1) / 2; }   // (a, b <= a) terms; the padding is exactly zero in both operands
+// Btri: quad_tri_b_bytes(T); colmax: 256 doubles [colmax (128) | colscale (128)]
+int launch_quad_tri_build_b(const double* cov, int64_t Sp, int64_t T, void* Btri, double* colmax, cudaStream_t st) {
+    if (T < 1 || T > 128 || Sp < 1 || Sp > 128) return -5;
+    quad_tri_colmax_kernel<<<(unsigned)Sp, 256, 0, st>>>(cov, Sp, T, colmax, colmax + 128);
+    TES_LAUNCH_OK();
+    const int64_t tot = qt_units(T) * 4 * 128;
+    quad_tri_build_b_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cov, Sp, T, colmax, (__half*)Btri);
+    TES_LAUNCH_OK();
+    return 0;
+}
+int launch_quad_screen_tri(const double* G, int64_t ldg, int64_t nc, int64_t T, const void* Btri, const double* colmax,
+                           int64_t Sp, double* rowmax, double* Qout, cudaStream_t st) {
+    if (T < 1 || T > 128 || Sp < 1 || Sp > 128) return -5;
+    const size_t smem = 4 * (size_t)TC_BLOCK_BYTES + QT_NS * (size_t)QT_UNIT_BYTES + (256 + 128) * sizeof(double) + 256;
+    TES_CUDA_OK(cudaFuncSetAttribute(quad_screen_tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t npair = (nc + 255) / 256;
+    const int sms = tc_sm_count();
+    const unsigned grid = (unsigned)(npair < sms ? npair : sms);
+    quad_screen_tri_kernel<<<grid, TC_THREADS, smem, st>>>(G, ldg, nc, (int)T, (const __half*)Btri, Sp, npair, rowmax,
+                                                          colmax + 128, Qout);
+    TES_LAUNCH_OK();
+    return 0;
+}
+
 int64_t quad_screen_kp(int64_t Kdim) { return (Kdim + 255) / 256 * 256; }
 int64_t quad_screen_a_bytes(int64_t nc, int64_t Kdim) {
     return align_up(((nc + 127) / 128) * (quad_screen_kp(Kdim) / TC_BK) * (int64_t)TC_BLOCK_BYTES, 256) + align_up(nc * 8, 256);
