@@ -2340,25 +2340,35 @@ __global__ void quad_tri_build_b_kernel(const double* __restrict__ cov, int64_t 
     *reinterpret_cast<uint4*>(blk + 4 * 128 * 8 + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
+// Orientation: D[j][x] = sum_b c_ab(j) M[x][b] -- the covariance unit is the A operand (M = 128 maximizers), BOTH row
+// tiles of the CTA are the B operand (N = 256 candidates): ONE M128 N256 K16 instruction does what two M128 N128 K16
+// did.  ncu of the first orientation (tiles as A): the MMAs were accepted at the pipe's rate (61 cycles each), but the
+// single issuing thread also pays ~290 cycles per 16 KB unit (barrier check, fence, commit) -- issue, not the tensor
+// pipe, bound the a-loop at 48 % pipe-busy; halving the instruction count leaves the issue thread slack.
+// Accumulator: 128 lanes (j) x 256 columns (x), two buffers = the whole tensor memory.  Epilogue thread = (lane j,
+// 64 columns): acc[x] += M~[x][a] D[j][x]; the multipliers of an a-block are a 256-float line in shared memory,
+// written by the epilogue threads one block ahead.
 __global__ void __launch_bounds__(TC_THREADS, 1)
     quad_screen_tri_kernel(const double* __restrict__ G, int64_t ldg, int64_t nc, int T, const __half* __restrict__ Bt,
                            int64_t Sp, int64_t npair, double* __restrict__ rowmax, const double* __restrict__ colscale,
                            double* __restrict__ Qout) {
     extern __shared__ __align__(1024) unsigned char qt_smem_raw[];
-    unsigned char* Aop = qt_smem_raw;                                   // [2 tiles][2 blocks of 64 k][hi | lo] = 128 KB
-    unsigned char* Bring = qt_smem_raw + 4 * TC_BLOCK_BYTES;            // [QT_NS][16 KB]
-    double* rmax_s = reinterpret_cast<double*>(Bring + QT_NS * QT_UNIT_BYTES);      // [256]
+    unsigned char* Mop = qt_smem_raw;                                   // [2 blocks of 64 k][hi | lo][8 chunks][256 rows][8] = 128 KB
+    unsigned char* Cring = qt_smem_raw + 4 * TC_BLOCK_BYTES;            // [QT_NS][16 KB] covariance units
+    double* rmax_s = reinterpret_cast<double*>(Cring + QT_NS * QT_UNIT_BYTES);      // [256]
     double* cs_s = rmax_s + 256;                                                    // [128] colscale
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cs_s + 128);
+    float* mline = reinterpret_cast<float*>(cs_s + 128);                            // [2][256] multipliers of an a-block
+    uint64_t* bars = reinterpret_cast<uint64_t*>(mline + 512);
     uint64_t* full_b = bars;                 // [QT_NS] producer -> MMA
     uint64_t* empty_b = bars + QT_NS;        // [QT_NS] MMA (commit) -> producer
     uint64_t* acc_full = bars + 2 * QT_NS;   // [2] MMA (commit) -> epilogue
     uint64_t* acc_empty = acc_full + 2;      // [2] epilogue -> MMA
-    uint64_t* a_full = acc_empty + 2;        // [1] epilogue warps (A operands of the pair written) -> MMA
+    uint64_t* a_full = acc_empty + 2;        // [1] epilogue warps (M operand of the pair written) -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t nmine = blockIdx.x < npair ? (npair - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int nunit_all = (int)qt_units(T);
+    constexpr uint32_t MBLK = 2 * TC_BLOCK_BYTES;          // one 64-k block of the 256-row operand (hi + lo) = 64 KB
     if (tid == 0) {
         for (int s = 0; s < QT_NS; ++s) {
             mbar_init(&full_b[s], 1);
@@ -2390,7 +2400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 for (int u = 0; u < nunit_all; ++u) {
                     mbar_wait_relaxed(&empty_b[s], ph ^ 1u, 32);
                     mbar_expect_tx(&full_b[s], QT_UNIT_BYTES);
-                    bulk_g2s(Bring + s * QT_UNIT_BYTES, srcB + (int64_t)u * QT_UNIT_BYTES, QT_UNIT_BYTES, &full_b[s]);
+                    bulk_g2s(Cring + s * QT_UNIT_BYTES, srcB + (int64_t)u * QT_UNIT_BYTES, QT_UNIT_BYTES, &full_b[s]);
                     if (++s == QT_NS) {
                         s = 0;
                         ph ^= 1u;
@@ -2400,17 +2410,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = tc_idesc_f16(128, 128);
+            const uint32_t idesc = tc_idesc_f16(128, 256);
             // shared-memory descriptors: only the start-address field (bits 0-13, units of 16 bytes) changes between
-            // MMAs, so they are formed once and advanced by 32-bit adds -- the issue thread is a single dependent
-            // instruction stream and ncu showed it, not the tensor pipe, bounding the a-loop (80 instructions per
-            // K16 step, 35 of them rebuilding descriptors: 770 cycles per step for 384 cycles of MMA work)
-            const uint64_t d0 = tc_desc(smem_u32(Aop), 128 * 16, 128);
-            const uint32_t dhi = (uint32_t)(d0 >> 32), a_lo32 = (uint32_t)d0;
-            const uint32_t b_lo32 = (uint32_t)tc_desc(smem_u32(Bring), 128 * 16, 128);
+            // MMAs, so they are formed once and advanced by 32-bit adds
+            const uint64_t dc = tc_desc(smem_u32(Cring), 128 * 16, 128);     // covariance unit: 128 rows per chunk
+            const uint64_t dm = tc_desc(smem_u32(Mop), 256 * 16, 128);       // candidate operand: 256 rows per chunk
+            const uint32_t dhi = (uint32_t)(dc >> 32), c_lo32 = (uint32_t)dc, m_lo32 = (uint32_t)dm;
             auto mk = [&](uint32_t lo32) { return ((uint64_t)dhi << 32) | (uint64_t)lo32; };
             int64_t gs = 0;
-            uint32_t s = 0, ph = 0;                                   // B ring slot and phase
+            uint32_t s = 0, ph = 0;                                   // ring slot and phase
             for (int64_t it = 0; it < nmine; ++it) {
                 mbar_wait_relaxed(a_full, (uint32_t)(it & 1), 32);
                 tc_fence_after();
@@ -2419,25 +2427,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     mbar_wait_relaxed(&acc_empty[buf], pa ^ 1u, 32);
                     tc_fence_after();
                     const int nun = a / 32 + 1;
-                    const uint32_t d_t0 = tmem + buf * 128u, d_t1 = d_t0 + 256u;
+                    const uint32_t d = tmem + buf * 256u;
                     for (int n = 0; n < nun; ++n) {
                         mbar_wait_relaxed(&full_b[s], ph, 32);
                         tc_fence_after();
-                        const uint32_t sb = b_lo32 + s * (QT_UNIT_BYTES >> 4);
+                        const uint32_t sc = c_lo32 + s * (QT_UNIT_BYTES >> 4);
                         const int nk16 = (a + 1 - 32 * n) > 16 ? 2 : 1;       // the second half of the unit may be all zero
                         for (int h = 0; h < nk16; ++h) {
-                            const int kk = 2 * n + h;                          // K16 step of the A operand (0 .. 7)
-                            const uint32_t sa = a_lo32 + (uint32_t)(kk >> 2) * (TC_BLOCK_BYTES >> 4) + (uint32_t)(kk & 3) * 256u;
-                            const uint64_t b_hi = mk(sb + (uint32_t)h * 256u), b_lo = mk(sb + (uint32_t)h * 256u + (QT_UNIT_BYTES >> 5));
-                            const uint64_t a0_hi = mk(sa), a0_lo = mk(sa + (TC_BLOCK_BYTES >> 5));
-                            const uint64_t a1_hi = mk(sa + (TC_BLOCK_BYTES >> 3)), a1_lo = mk(sa + (TC_BLOCK_BYTES >> 3) + (TC_BLOCK_BYTES >> 5));
-                            const uint32_t first = (n == 0 && h == 0) ? 0u : 1u;
-                            tc_mma_f16(d_t0, a0_lo, b_hi, idesc, first);
-                            tc_mma_f16(d_t1, a1_lo, b_hi, idesc, first);
-                            tc_mma_f16(d_t0, a0_hi, b_lo, idesc, 1u);
-                            tc_mma_f16(d_t1, a1_hi, b_lo, idesc, 1u);
-                            tc_mma_f16(d_t0, a0_hi, b_hi, idesc, 1u);
-                            tc_mma_f16(d_t1, a1_hi, b_hi, idesc, 1u);
+                            const int kk = 2 * n + h;                          // K16 step of the candidate operand (0 .. 7)
+                            const uint32_t sm_ = m_lo32 + (uint32_t)(kk >> 2) * (MBLK >> 4) + (uint32_t)(kk & 3) * 512u;
+                            const uint64_t c_hi = mk(sc + (uint32_t)h * 256u), c_lo = mk(sc + (uint32_t)h * 256u + (QT_UNIT_BYTES >> 5));
+                            const uint64_t m_hi = mk(sm_), m_lo = mk(sm_ + (MBLK >> 5));
+                            tc_mma_f16(d, c_lo, m_hi, idesc, (n == 0 && h == 0) ? 0u : 1u);
+                            tc_mma_f16(d, c_hi, m_lo, idesc, 1u);
+                            tc_mma_f16(d, c_hi, m_hi, idesc, 1u);
                         }
                         tc_commit(&empty_b[s]);
                         if (++s == QT_NS) {
@@ -2452,17 +2455,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         __syncwarp();
     } else {
         const int ew = warp - 2;
-        const int quarter = warp & 3, cb = ew >> 2;
-        const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32);
+        const int quarter = warp & 3, cg = ew >> 2;                // TMEM lane quarter, group of 64 columns
+        const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cg * 64);
         const int te = tid - 64;
-        const int xr = quarter * 32 + lane;                       // this thread's row inside a tile (TMEM lane)
+        const int j = quarter * 32 + lane;                         // this thread's maximizer (TMEM lane)
         int64_t gs = 0;
+        // multiplier M~[x][a] = hi + lo exactly as the tensor core saw it; thread te < 256 owns x = te
+        auto write_line = [&](int a) {
+            if (te < 256) {
+                const unsigned char* p = Mop + (a >> 6) * MBLK + ((((a & 63) >> 3) * 256 + te) * 8 + (a & 7)) * 2;
+                mline[(a & 1) * 256 + te] = __half2float(*reinterpret_cast<const __half*>(p)) +
+                                            __half2float(*reinterpret_cast<const __half*>(p + MBLK / 2));
+            }
+        };
         for (int64_t it = 0; it < nmine; ++it) {
             const int64_t pr = blockIdx.x + it * gridDim.x;
-            // ---- A operands of the pair: a warp per row, lanes over the T columns; row maximum, scale 64 / max,
-            // hi / lo halves straight into the MMA layout ([block of 64 k][hi | lo][chunk][row][8]); k >= T stays zero
+            // ---- candidate operand of the pair: a warp per row, lanes over the T columns; row maximum, scale 64 / max,
+            // hi / lo halves straight into the MMA layout; k >= T and rows >= nc stay zero
             asm volatile("bar.sync 1, 512;" ::: "memory");        // every warp is done reading the previous pair's M~
-            for (int e = te; e < (int)(4 * TC_BLOCK_BYTES / 16); e += 512) reinterpret_cast<uint4*>(Aop)[e] = make_uint4(0, 0, 0, 0);
+            for (int e = te; e < (int)(4 * TC_BLOCK_BYTES / 16); e += 512) reinterpret_cast<uint4*>(Mop)[e] = make_uint4(0, 0, 0, 0);
             asm volatile("bar.sync 1, 512;" ::: "memory");
             for (int r0 = te >> 5; r0 < 256; r0 += 2 * TC_EPI_WARPS) {
                 double gv[2][4], rm[2];
@@ -2494,17 +2505,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         if (grow < nc) rowmax[grow] = rm[u];
                     }
                     if (grow < nc && sc != 0.0) {
-                        unsigned char* tb = Aop + (rr >> 7) * 2 * TC_BLOCK_BYTES;
-                        const int x = rr & 127;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int a = lane + 32 * q;
                             if (a < T) {
                                 __half h, l;
                                 split_f16((float)(gv[u][q] * sc), h, l);
-                                unsigned char* p = tb + (a >> 6) * TC_BLOCK_BYTES + ((((a & 63) >> 3) * 128 + x) * 8 + (a & 7)) * 2;
+                                unsigned char* p = Mop + (a >> 6) * MBLK + ((((a & 63) >> 3) * 256 + rr) * 8 + (a & 7)) * 2;
                                 *reinterpret_cast<__half*>(p) = h;
-                                *reinterpret_cast<__half*>(p + TC_BLOCK_BYTES / 2) = l;
+                                *reinterpret_cast<__half*>(p + MBLK / 2) = l;
                             }
                         }
                     }
@@ -2515,45 +2524,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (lane == 0) tc_arrive(a_full);
             asm volatile("bar.sync 1, 512;" ::: "memory");        // M~ of every row is readable below
 
-            float acc[2][32];
+            float acc[64];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) acc[0][c] = acc[1][c] = 0.0f;
+            for (int c = 0; c < 64; ++c) acc[c] = 0.0f;
+            write_line(0);
             for (int a = 0; a < T; ++a, ++gs) {
                 const uint32_t buf = (uint32_t)(gs & 1), pa = (uint32_t)((gs >> 1) & 1);
-                // M~[x][a] = hi + lo exactly as the tensor core saw it
-                const uint32_t mo = (uint32_t)(a >> 6) * TC_BLOCK_BYTES + (uint32_t)(((((a & 63) >> 3) * 128 + xr) * 8 + (a & 7)) * 2);
-                float mt[2];
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const unsigned char* p = Aop + t * 2 * TC_BLOCK_BYTES + mo;
-                    mt[t] = __half2float(*reinterpret_cast<const __half*>(p)) +
-                            __half2float(*reinterpret_cast<const __half*>(p + TC_BLOCK_BYTES / 2));
-                }
+                asm volatile("bar.sync 1, 512;" ::: "memory");    // line a complete; line a - 1 no longer read
+                if (a + 1 < T) write_line(a + 1);
+                const float* ml = mline + (a & 1) * 256 + cg * 64;
                 mbar_wait(&acc_full[buf], pa);
                 tc_fence_after();
 #pragma unroll
-                for (int t = 0; t < 2; ++t)
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t v0[16];
+                    TC_LD16(v0, t_lane + buf * 256u + (uint32_t)(q * 16));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        uint32_t v0[16];
-                        TC_LD16(v0, t_lane + (uint32_t)t * 256u + buf * 128u + (uint32_t)(q * 16));
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) acc[t][q * 16 + c] = fmaf(mt[t], __uint_as_float(v0[c]), acc[t][q * 16 + c]);
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 m4 = *reinterpret_cast<const float4*>(ml + q * 16 + c4 * 4);
+                        acc[q * 16 + 4 * c4] = fmaf(m4.x, __uint_as_float(v0[4 * c4]), acc[q * 16 + 4 * c4]);
+                        acc[q * 16 + 4 * c4 + 1] = fmaf(m4.y, __uint_as_float(v0[4 * c4 + 1]), acc[q * 16 + 4 * c4 + 1]);
+                        acc[q * 16 + 4 * c4 + 2] = fmaf(m4.z, __uint_as_float(v0[4 * c4 + 2]), acc[q * 16 + 4 * c4 + 2]);
+                        acc[q * 16 + 4 * c4 + 3] = fmaf(m4.w, __uint_as_float(v0[4 * c4 + 3]), acc[q * 16 + 4 * c4 + 3]);
                     }
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc_arrive(&acc_empty[buf]);
             }
+            if (j < Sp) {
+                const double cs = cs_s[j];
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int64_t row = pr * 256 + t * 128 + xr;
-                if (row < nc) {
-                    const double rm = rmax_s[t * 128 + xr];
-                    const double rs = rm * rm / QS_AMAX;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        if (cb * 32 + c < Sp) Qout[row * Sp + cb * 32 + c] = rs * cs_s[cb * 32 + c] * (double)acc[t][c];
+                for (int c = 0; c < 64; ++c) {
+                    const int x = cg * 64 + c;
+                    const int64_t row = pr * 256 + x;
+                    if (row < nc) {
+                        const double rm = rmax_s[x];
+                        Qout[row * Sp + j] = rm * rm / QS_AMAX * cs * (double)acc[c];
+                    }
                 }
             }
         }
@@ -2581,7 +2590,7 @@ int launch_quad_tri_build_b(const double* cov, int64_t Sp, int64_t T, void* Btri
 int launch_quad_screen_tri(const double* G, int64_t ldg, int64_t nc, int64_t T, const void* Btri, const double* colmax,
                            int64_t Sp, double* rowmax, double* Qout, cudaStream_t st) {
     if (T < 1 || T > 128 || Sp < 1 || Sp > 128) return -5;
-    const size_t smem = 4 * (size_t)TC_BLOCK_BYTES + QT_NS * (size_t)QT_UNIT_BYTES + (256 + 128) * sizeof(double) + 256;
+    const size_t smem = 4 * (size_t)TC_BLOCK_BYTES + QT_NS * (size_t)QT_UNIT_BYTES + (256 + 128) * sizeof(double) + 512 * sizeof(float) + 256;
     TES_CUDA_OK(cudaFuncSetAttribute(quad_screen_tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t npair = (nc + 255) / 256;
     const int sms = tc_sm_count();
