@@ -273,6 +273,33 @@ def test_tes_ep_screen_bound_holds(hyp, d, n, T, nx, mode, tri, monkeypatch):
     assert err.max() < 1e-4 * max(1.0, np.abs(exact[fin]).max())
 
 
+def test_tes_ep_screen_more_than_128_test_points():
+    """T > 128 test points (with S' <= 128 maximizer-conditioned posteriors): the triangular GEMM does not apply, the
+    generator kernel runs; the bound still holds.  (The reference pipeline drops test points that are never the
+    maximizer, so T = S' there; the operators accept the general case.)"""
+    from tes_b200 import ops
+    rs = np.random.RandomState(9)
+    d, n, T, Sp, N = 6, 20, 140, 96, 5_000
+    l, sigma, sigma0 = HART6["l"], HART6["sigma"], 1e-3
+    X, Y, test_xs, x = rs.rand(n, d), rs.randn(n, 1) * 0.4, rs.rand(T, d), rs.rand(N, d)
+    ls, sg, s0 = l.reshape(1, d), np.array([sigma]), np.array([sigma0])
+    invK = onp.precomputeInvKs(ls, sg, s0, X)
+    _, invpNK = onp.get_pNK_test_obs(ls, sg, s0, 1, X, test_xs)
+    p = rs.rand(Sp)
+    p /= p.sum()
+    covs = []
+    for _ in range(Sp):
+        A = rs.randn(T, 2 * T)
+        covs.append(A @ A.T / (2 * T) * 0.05)
+    covs = np.stack(covs)
+    exact = ops.ep_acq(ops.EP_DETERMINISTIC, x, test_xs, X, Y, l, sigma, sigma0, invpNK[0], invK[0], p,
+                       np.zeros((Sp, T)), covs).cpu().numpy()
+    acq, eps = [t.cpu().numpy() for t in ops.ep_acq_screen(x, test_xs, X, Y, l, sigma, sigma0, invpNK[0], invK[0], p, covs)]
+    fin = np.isfinite(eps) & np.isfinite(exact)
+    assert fin.mean() > 0.9
+    assert np.all(np.abs(acq - exact)[fin] <= eps[fin])
+
+
 def test_tes_ep_screen_fp32_bound_dominates_fp64_bound(monkeypatch):
     """The bound H = sum_a |M_a| sqrt(Sigma_aa) is formed on the fp32 pipe inside ep_det_screen_h_kernel (operands rounded
     up, result inflated by the fp32 summation error); TES_SCREEN_H=0 selects the fp64 GEMM.  eps(fp32) >= eps(fp64) on
