@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256)
     const int t = threadIdx.x;
     const int ti = t >> 4, tj = t & 15;
     if (t == 0) bad = 0;
+    if (t < CH_NB) rdiag[t] = 1.0;                 // identity padding (k >= nb)
     for (int e = t; e < CH_NB * CH_NB; e += 256) {
         int i = e / CH_NB, j = e % CH_NB;
         a[i][j] = (i < nb && j < nb && j <= i) ? Ab[(k0 + i) * m + k0 + j] : ((i == j && i >= nb) ? 1.0 : 0.0);
@@ -67,8 +68,9 @@ __global__ void __launch_bounds__(256)
         for (int p = 0; p < 4; ++p) colbuf[ti + 16 * p] = r[p][0];
     }
     __syncthreads();
+    // (steps k >= nb only touch the identity padding: column k = e_k, r = 1, no update -- skipped)
 #pragma unroll 1
-    for (int k = 0; k < CH_NB; ++k) {
+    for (int k = 0; k < nb; ++k) {
         const double* cb = colbuf + (k & 1) * CH_NB;
         const double dkk = cb[k];
         const double rs = rsqrt(dkk);
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(256)
         }
     }
 #pragma unroll 1
-    for (int k = 0; k < CH_NB; ++k) {
+    for (int k = 0; k < nb; ++k) {
         const double* rb = rowbuf + (k & 1) * CH_NB;
         double xk[4], lk[4];
 #pragma unroll

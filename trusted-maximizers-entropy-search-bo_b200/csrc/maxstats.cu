@@ -69,9 +69,16 @@ __device__ __forceinline__ double np_sqdist(const double* __restrict__ a, const 
 
 // Walking the rows in order, every not-yet-flagged row flags all LATER rows within `resolution` (Euclidean).
 // The walk is sequential by definition; one CTA, the inner scan over later rows is parallel.
-__global__ void __launch_bounds__(1024) dedup_kernel(const double* __restrict__ xs, int S, int d, double resolution,
-                                                     int* __restrict__ mask, int64_t* __restrict__ leader) {
-    extern __shared__ int smask[];
+// stage != 0: the rows are copied to shared memory first (each of the up to S leader iterations then reads them at
+// shared-memory instead of L2 latency: 0.77 -> ~0.2 ms for the 1024 maximizers of C3).
+__global__ void __launch_bounds__(1024) dedup_kernel(const double* __restrict__ xs_g, int S, int d, double resolution,
+                                                     int* __restrict__ mask, int64_t* __restrict__ leader, int stage) {
+    extern __shared__ __align__(8) unsigned char dd_smem[];
+    double* xs_s = reinterpret_cast<double*>(dd_smem);
+    int* smask = reinterpret_cast<int*>(dd_smem + (stage ? (size_t)S * d * sizeof(double) : 0));
+    if (stage)
+        for (int e = threadIdx.x; e < S * d; e += blockDim.x) xs_s[e] = xs_g[e];
+    const double* xs = stage ? xs_s : xs_g;
     for (int j = threadIdx.x; j < S; j += blockDim.x) {
         smask[j] = 0;
         leader[j] = j;
@@ -464,11 +471,13 @@ extern "C" int tes_dedup_f64(const double* xs, int64_t S, int64_t d, double reso
     if (!xs) return -1;
     if (!mask) return -5;
     if (!leader) return -6;
-    const size_t smem = (size_t)S * sizeof(int);
+    const size_t rows_b = (size_t)S * d * sizeof(double);
+    const int stage = rows_b + (size_t)S * sizeof(int) <= 200 * 1024;
+    const size_t smem = (size_t)S * sizeof(int) + (stage ? rows_b : 0);
     if (smem > 48 * 1024)
         TES_CUDA_OK(cudaFuncSetAttribute(dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = S >= 1024 ? 1024 : (int)((S + 31) / 32 * 32);
-    dedup_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(xs, (int)S, (int)d, resolution, mask, leader);
+    dedup_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(xs, (int)S, (int)d, resolution, mask, leader, stage);
     TES_LAUNCH_OK();
     return 0;
 }
