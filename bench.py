@@ -328,6 +328,9 @@ class Bench:
         torch = self.torch
         out = {}
         for k in names:
+            if k == "cand":
+                out[k] = host[k]      # pinned host tensor: tes_step uploads it on a side stream under the weight draw
+                continue
             if self.world > 1 and k in REPLICATED:
                 t = host[k].cuda(non_blocking=True) if self.rank == 0 else \
                     torch.empty(host[k].shape, dtype=host[k].dtype, device="cuda")

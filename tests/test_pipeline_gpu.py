@@ -142,3 +142,23 @@ def test_step_with_counter_based_draws(criterion, det, q):
     out = acquisition.tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, **kw)
     assert ref["T"] >= 2 and out["acq"].shape[0] == N // q
     _compare(out, ref)
+
+
+def test_step_from_a_pinned_host_candidate_array_overlaps_the_upload_and_gives_the_same_step():
+    """tes_step(draws=...) uploads a pinned host candidate tensor on a side stream under the weight draw (stage A0 does not
+    read the candidates): same outputs as with the candidates already on the device, repeatedly (allocator reuse)."""
+    import torch
+    from tes_b200 import acquisition
+    rs = np.random.RandomState(4)
+    d, n, S, F, N = 3, 9, 24, 96, 40_000
+    l, sigma, sigma0 = np.array([5.0, 2.0, 8.0]), 1.2, 1e-3
+    cand, X, Y = rs.rand(N, d), rs.rand(n, d), rs.randn(n, 1) * 0.4
+    draws = tuple(torch.from_numpy(a).cuda() for a in (rs.randn(S, F, d), rs.rand(S, F, 1), rs.randn(S, F, 1)))
+    kw = dict(criterion="ftl", mode="empirical", deterministic=True, ntestsample=2000, seed=3, t_max=32, draws=draws,
+              return_acq=True)
+    ref = acquisition.tes_step(torch.from_numpy(cand).cuda(), X, Y, l, sigma, sigma0, None, None, None, **kw)
+    host = torch.from_numpy(cand).pin_memory()
+    for _ in range(3):
+        out = acquisition.tes_step(host, X, Y, l, sigma, sigma0, None, None, None, **kw)
+        assert out["query_idx"] == ref["query_idx"] and out["query_val"] == ref["query_val"]
+        assert torch.equal(out["argmax_idx"], ref["argmax_idx"]) and torch.equal(out["acq"], ref["acq"])

@@ -130,6 +130,27 @@ def select_test_points(max_xs, resolution=1e-3, t_max=None):
     return out if torch.is_tensor(max_xs) else out.cpu().numpy()
 
 
+_COPY_STREAMS = {}
+
+
+def _stage_upload(host_t):
+    """Pinned host tensor -> (device tensor, event): the copy runs on a per-device side stream, ordered after the work
+    already enqueued on the current stream (the allocator may hand out memory that work still reads)."""
+    device = torch.device("cuda", torch.cuda.current_device())
+    side = _COPY_STREAMS.get(device.index)
+    if side is None:
+        side = _COPY_STREAMS[device.index] = torch.cuda.Stream(device=device)
+    out = torch.empty(host_t.shape, dtype=host_t.dtype, device=device)
+    ev0 = torch.cuda.Event()
+    ev0.record()
+    side.wait_event(ev0)
+    with torch.cuda.stream(side):
+        out.copy_(host_t, non_blocking=True)
+        ev1 = torch.cuda.Event()
+        ev1.record(side)
+    return out, ev1
+
+
 def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="empirical", deterministic=True,
              ntestsample=1000, n_min_sample=2, nysample=10, niteration=10, z_joint=None, z=None, seed=0,
              duplicate_resolution=1e-3, t_max=None, shard=None, return_acq=False, timers=None, transform=None, q=1,
@@ -147,12 +168,22 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
     draw (stage A0, optfunc.py:303-385, on the device) and `theta`, `W`, `b` are ignored (pass None)."""
     from . import optfunc
     from .criteria import evaluate_batch_sample_mp, evaluate_mp, evaluate_sample_mp
-    cand = dev(cand)
+    # a pinned host candidate array is uploaded on a side stream UNDER the weight draw (the only stage that does not
+    # read the candidates); the compute stream waits for it before stage A
+    staged = None
+    if draws is not None and torch.is_tensor(cand) and not cand.is_cuda and cand.dtype == torch.float64 \
+            and cand.is_contiguous() and cand.is_pinned():
+        staged = _stage_upload(cand)
+        cand = staged[0]
+    else:
+        cand = dev(cand)
     N, d = cand.shape
     if draws is not None:
         with _Timed(timers, "draw"):
             S_, F_ = draws[0].shape[0], draws[0].shape[1]
             theta, W, b = optfunc.draw_random_init_weights_features(d, S_, F_, X, Y, l, sigma, sigma0, draws=draws)
+    if staged is not None:
+        torch.cuda.current_stream().wait_event(staged[1])
     shard = shard or Shard(N)
     q = int(q)
     if q > 1 and (criterion != "sftl" or N % q or shard.offset % q):
