@@ -164,7 +164,7 @@ def test_discrete_maximizer_sampler(golden):
     np.testing.assert_array_equal(mx, xs[ridx])
 
 
-@pytest.mark.parametrize("batch,m", [(3, 512), (2, 1024)])
+@pytest.mark.parametrize("batch,m", [(3, 512), (2, 1024), (2, 449), (1, 2048), (2, 1150)])
 def test_batched_chol2inv_large_property(batch, m):
     """C5 sizes: A A^-1 = I and symmetry (the oracle is too slow to be the checker at the full sweep)."""
     import torch

@@ -144,7 +144,9 @@ __device__ __forceinline__ void gemm_body(const AProv& ap, const double* __restr
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     if (sbn == 1) {
         const int64_t kbeg = kskip == 1 ? (row0 > col0 ? row0 : col0) : (kskip == 2 ? col0 : 0);
-        gemm_mainloop(ap, B, sbk, K, N, row0, col0, sm, acc, kbeg);
+        // kskip = 3: A is lower-triangular -- columns k > row contribute nothing to this row tile
+        const int64_t kend = (kskip == 3 && row0 + GEMM_BM < K) ? row0 + GEMM_BM : K;
+        gemm_mainloop(ap, B, sbk, kend, N, row0, col0, sm, acc, kbeg);
     } else {
         double ra[AProv::NREG], rb[4];
         const int64_t nk = (K + GEMM_BK - 1) / GEMM_BK;

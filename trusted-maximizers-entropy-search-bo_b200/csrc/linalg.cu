@@ -249,7 +249,7 @@ static CholPlan chol_plan(int64_t batch, int64_t m, int want_inverse) {
     p.off_work = take(blocked ? batch * m * m * 8 : 256);                         // trailing-update copy of A
     p.off_dinv = take(batch * p.nblk * CH_NB * CH_NB * 8);                        // inv of diagonal blocks
     p.off_x = take(blocked && want_inverse ? batch * m * m * 8 : 256);            // X = L^-1
-    p.off_s = take(blocked && want_inverse ? batch * CH_NB * m * 8 : 256);        // block-row temporary
+    p.off_s = take(blocked && want_inverse ? batch * (m / 2 + CH_NB) * (m / 2 + CH_NB) * 8 : 256);   // L21 X11 of the recursion
     p.total = o;
     return p;
 }
@@ -276,9 +276,21 @@ static int chol_run(const double* A, int64_t batch, int64_t m, double* L, double
     TES_CUDA_OK(cudaMemcpyAsync(work, A, sizeof(double) * batch * m * m, cudaMemcpyDeviceToDevice, st));
     const int64_t mm = m * m;
     int rc;
+    // LEFT-looking: block column k is updated by ONE GEMM with K = k0 (all previous block columns) right before it is
+    // factored.  The right-looking form (a rank-64 update of the whole trailing matrix after every panel) runs the DMMA
+    // GEMM with K = 64 -- four slices per tile, prologue and epilogue exposed: ~40 % of the pipe; here K grows to m - 64.
     for (int64_t kb = 0; kb < pl.nblk; ++kb) {
         const int64_t k0 = kb * CH_NB;
         const int nb = (int)((m - k0 < CH_NB) ? (m - k0) : CH_NB);
+        if (kb > 0) {
+            // work[k0:, k0:k0+nb] -= L[k0:, :k0] L[k0:k0+nb, :k0]^T
+            GemmArgs u{};
+            u.A = L + k0 * m; u.lda = m; u.transa = 0; u.batchA = mm;
+            u.B = L + k0 * m; u.sbk = 1; u.sbn = m; u.batchB = mm;      // B'[k][c] = L[k0 + c][k]
+            u.C = work + k0 * m + k0; u.ldc = m; u.batchC = mm;
+            u.M = m - k0; u.N = nb; u.K = k0; u.alpha = -1.0; u.beta = 1.0; u.tri = 0; u.batch = (int)batch;
+            if ((rc = launch_gemm_ex(u, st))) return rc;
+        }
         potrf_diag_kernel<<<(unsigned)batch, 256, CH_SMEM, st>>>(work, m, k0, nb, L, Dinv + kb * CH_NB * CH_NB, dstride,
                                                            info, nullptr);
         TES_LAUNCH_OK();
@@ -291,13 +303,6 @@ static int chol_run(const double* A, int64_t batch, int64_t m, double* L, double
         g.C = L + (k0 + nb) * m + k0; g.ldc = m; g.batchC = mm;
         g.M = rest; g.N = nb; g.K = nb; g.alpha = 1.0; g.beta = 0.0; g.tri = 0; g.batch = (int)batch;
         if ((rc = launch_gemm_ex(g, st))) return rc;
-        // update: work[k0+nb:, k0+nb:] -= P P^T   (lower tiles only)
-        GemmArgs u{};
-        u.A = L + (k0 + nb) * m + k0; u.lda = m; u.transa = 0; u.batchA = mm;
-        u.B = L + (k0 + nb) * m + k0; u.sbk = 1; u.sbn = m; u.batchB = mm;  // B'[k][c] = P[c][k]
-        u.C = work + (k0 + nb) * m + (k0 + nb); u.ldc = m; u.batchC = mm;
-        u.M = rest; u.N = rest; u.K = nb; u.alpha = -1.0; u.beta = 1.0; u.tri = 1; u.batch = (int)batch;
-        if ((rc = launch_gemm_ex(u, st))) return rc;
     }
     {
         int64_t tot = batch * mm;
@@ -312,22 +317,45 @@ static int chol_run(const double* A, int64_t batch, int64_t m, double* L, double
         copy_diag_inv_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Dinv, dstride, X, m, batch);
         TES_LAUNCH_OK();
     }
-    for (int64_t ib = 1; ib < pl.nblk; ++ib) {
-        const int64_t i0 = ib * CH_NB;
-        const int nb = (int)((m - i0 < CH_NB) ? (m - i0) : CH_NB);
-        GemmArgs g{};
-        g.A = L + i0 * m; g.lda = m; g.transa = 0; g.batchA = mm;
-        g.B = X; g.sbk = m; g.sbn = 1; g.batchB = mm;
-        g.C = S; g.ldc = m; g.batchC = CH_NB * m;
-        g.M = nb; g.N = i0; g.K = i0; g.alpha = 1.0; g.beta = 0.0; g.tri = 0; g.batch = (int)batch;
-        g.kskip = 2;   // X[:i0, :i0] is lower-triangular: rows k < col contribute nothing
-        if ((rc = launch_gemm_ex(g, st))) return rc;
-        GemmArgs h{};
-        h.A = Dinv + ib * CH_NB * CH_NB; h.lda = CH_NB; h.transa = 0; h.batchA = dstride;
-        h.B = S; h.sbk = m; h.sbn = 1; h.batchB = CH_NB * m;
-        h.C = X + i0 * m; h.ldc = m; h.batchC = mm;
-        h.M = nb; h.N = i0; h.K = nb; h.alpha = -1.0; h.beta = 0.0; h.tri = 0; h.batch = (int)batch;
-        if ((rc = launch_gemm_ex(h, st))) return rc;
+    // RECURSIVE halving: for a diagonal range [r0, r0 + n) split at s (a multiple of 64) the off-diagonal block of the
+    // inverse is X21 = -X22 (L21 X11) -- two GEMMs of (n - s) x s x s and (n - s) x s x (n - s) with both triangular
+    // factors skipped from their zero side, after the two halves themselves.  Square-ish GEMMs with K up to m / 2
+    // instead of the block-row sweep whose GEMMs had M = 64 rows (half of every 128-row tile idle) .
+    struct Range { int64_t r0, n; int phase; };
+    {
+        Range stack[64];
+        int sp = 0;
+        stack[sp++] = {0, m, 0};
+        while (sp > 0) {
+            Range r = stack[--sp];
+            if (r.n <= CH_NB) continue;                      // a diagonal block: already inv(L_ii)
+            const int64_t nblk_r = (r.n + CH_NB - 1) / CH_NB;
+            const int64_t s_ = (nblk_r / 2) * CH_NB;         // first half: whole 64-blocks
+            if (r.phase == 0) {
+                if (sp + 3 > 64) return -3;
+                stack[sp++] = {r.r0, r.n, 1};                // combine after both halves
+                stack[sp++] = {r.r0 + s_, r.n - s_, 0};
+                stack[sp++] = {r.r0, s_, 0};
+                continue;
+            }
+            const int64_t a0 = r.r0, b0 = r.r0 + s_, nb2 = r.n - s_;
+            // S = L21 X11        (nb2 x s_, K = s_; X11 lower-triangular: rows k < col contribute nothing)
+            GemmArgs g{};
+            g.A = L + b0 * m + a0; g.lda = m; g.transa = 0; g.batchA = mm;
+            g.B = X + a0 * m + a0; g.sbk = m; g.sbn = 1; g.batchB = mm;
+            g.C = S; g.ldc = s_; g.batchC = (m / 2 + CH_NB) * (m / 2 + CH_NB);
+            g.M = nb2; g.N = s_; g.K = s_; g.alpha = 1.0; g.beta = 0.0; g.tri = 0; g.batch = (int)batch;
+            g.kskip = 2;
+            if ((rc = launch_gemm_ex(g, st))) return rc;
+            // X21 = -X22 S       (nb2 x s_, K = nb2)
+            GemmArgs h{};
+            h.A = X + b0 * m + b0; h.lda = m; h.transa = 0; h.batchA = mm;
+            h.B = S; h.sbk = s_; h.sbn = 1; h.batchB = (m / 2 + CH_NB) * (m / 2 + CH_NB);
+            h.C = X + b0 * m + a0; h.ldc = m; h.batchC = mm;
+            h.M = nb2; h.N = s_; h.K = nb2; h.alpha = -1.0; h.beta = 0.0; h.tri = 0; h.batch = (int)batch;
+            h.kskip = 3;     // X22 is lower-triangular
+            if ((rc = launch_gemm_ex(h, st))) return rc;
+        }
     }
     // A^-1 = X^T X: lower tiles only, k from max(row0, col0) (X lower-triangular), then mirrored (X^T X is
     // bit-symmetric: the same products in the same order) -- m^3/3 flops instead of 2 m^3
