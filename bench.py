@@ -287,6 +287,7 @@ def _emit(line):
 STAGES = [("draw", "A0_draw_ms"), ("rff_topk", "A_maximizers_ms"), ("stage_b", "B_posterior_ms"),
           ("stage_c", "C_maximizer_stats_ms"), ("criterion", "D_criterion_ms"), ("criterion_screen", "D_screen_ms")]
 REPLICATED = ["X", "Y", "randn_W", "rand_b", "noise"]   # identical on every rank; "cand" is the rank's own shard
+DRAWS = ["randn_W", "rand_b", "noise"]                  # ... of which every rank consumes the slice of its S / world samples
 
 
 class Bench:
@@ -328,8 +329,10 @@ class Bench:
         torch = self.torch
         out = {}
         for k in names:
-            if k == "cand":
-                out[k] = host[k]      # pinned host tensor: tes_step uploads it on a side stream under the weight draw
+            if k == "cand" or k in DRAWS:
+                # pinned host tensors: tes_step uploads the candidates on a side stream under the weight draw, and of the
+                # draws only the slice of function samples this rank draws the weights of (S / world)
+                out[k] = host[k]
                 continue
             if self.world > 1 and k in REPLICATED:
                 t = host[k].cuda(non_blocking=True) if self.rank == 0 else \
@@ -350,7 +353,8 @@ class Bench:
         names = ["cand"] + REPLICATED
         host = {k: torch.from_numpy(np.ascontiguousarray(wl[k])).pin_memory() for k in names}
         devt = {k: host[k].cuda(non_blocking=True) for k in names}
-        h2d_bytes = sum(host[k].numel() * 8 for k in names)
+        split = self.world > 1 and wl["S"] % self.world == 0
+        h2d_bytes = sum(host[k].numel() * 8 // (self.world if (split and k in DRAWS) else 1) for k in names)
 
         def step(d_, seed, timers=None, **extra):
             k2 = dict(kw, **extra)
@@ -414,7 +418,9 @@ class Bench:
         res["e2e"] = {"value": pairs_step * steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(h2d_bytes),
                       "d2h_bytes_per_step": int(wl["S"] * 8 + 8 + 8 + wl["d"] * wl["q"] * 8),
                       "ms_per_step": e2e_s / steps * 1e3,
-                      "replicated_inputs": "rank 0 H2D + NCCL broadcast" if self.world > 1 else "H2D"}
+                      "replicated_inputs": "observations: rank 0 H2D + NCCL broadcast; draws: every rank uploads the slice of "
+                                            "its S / N function samples (the weight draw is sharded by sample, theta / W / b "
+                                            "all-gathered)" if self.world > 1 else "H2D"}
         return res
 
 
@@ -589,7 +595,7 @@ def main():
                            candidates=("product set U x V detected (slow columns [%d, %d), nv=%d): stage A = GEMM path "
                                        "(3xFP16 tensor-core screen + fp64 refine)" % product)
                            if product else "unstructured: stage A = tcgen05 screen + fp64 refine (MUFU-bound)",
-                           sharding="candidates contiguous per rank; NCCL all-gather of (value,index) partials only"),
+                           sharding="candidates contiguous per rank; weight draw sharded by function sample (theta / W / b all-gathered); NCCL all-gather of (value,index) partials"),
             "clocks": res["clocks"],
             "stage_ms": res["stages"],
             "stage_a_flagged_samples_per_step": res["flagged_samples_per_step"],

@@ -341,3 +341,20 @@ def test_device_ep_mode_through_get_testidxs_stats_cuda_tensors(golden):
     assert all(o.is_cuda for o in out)
     np.testing.assert_allclose(out[4][0].cpu().numpy(), g[tag + "_ep_mean"], rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(out[5][0].cpu().numpy(), g[tag + "_ep_cov"], rtol=1e-8, atol=1e-10)
+
+
+def test_weight_draw_of_a_slice_of_samples_is_the_slice_of_the_draw():
+    """Multi-GPU steps shard the weight draw by function sample (acquisition.tes_step): drawing samples [lo, hi) alone gives
+    the bits of the full draw's rows [lo, hi) -- every kernel of stage A0 treats the samples independently."""
+    from tes_b200 import optfunc
+    rs = np.random.RandomState(8)
+    S, F, n, d = 24, 96, 20, 6
+    X, Y = rs.rand(n, d), rs.randn(n, 1) * 0.4
+    l, sigma, sigma0 = np.array([6.9512, 1.9341, 0.506, 4.2067, 5.0986, 3.5949]), 1.423, 1e-4
+    draws = tuple(torch.from_numpy(a).cuda() for a in (rs.randn(S, F, d), rs.rand(S, F, 1), rs.randn(S, F, 1)))
+    full = optfunc.draw_random_init_weights_features(d, S, F, X, Y, l, sigma, sigma0, draws=draws)
+    for lo, hi in ((0, 8), (8, 16), (16, 24), (5, 6)):
+        part = optfunc.draw_random_init_weights_features(d, hi - lo, F, X, Y, l, sigma, sigma0,
+                                                         draws=tuple(t[lo:hi].contiguous() for t in draws))
+        for a, b in zip(full, part):
+            assert torch.equal(a[lo:hi], b)

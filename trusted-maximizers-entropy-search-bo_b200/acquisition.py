@@ -168,23 +168,38 @@ def tes_step(cand, X, Y, l, sigma, sigma0, theta, W, b, criterion="ftl", mode="e
     draw (stage A0, optfunc.py:303-385, on the device) and `theta`, `W`, `b` are ignored (pass None)."""
     from . import optfunc
     from .criteria import evaluate_batch_sample_mp, evaluate_mp, evaluate_sample_mp
-    # a pinned host candidate array is uploaded on a side stream UNDER the weight draw (the only stage that does not
-    # read the candidates); the compute stream waits for it before stage A
+    if not hasattr(cand, "shape"):
+        cand = np.asarray(cand, dtype=np.float64)
+    N, d = int(cand.shape[0]), int(cand.shape[1])
+    shard = shard or Shard(N)
     staged = None
-    if draws is not None and torch.is_tensor(cand) and not cand.is_cuda and cand.dtype == torch.float64 \
-            and cand.is_contiguous() and cand.is_pinned():
-        staged = _stage_upload(cand)
-        cand = staged[0]
+    if draws is not None:
+        # Stage A0.  With R ranks every rank draws the weights of S / R function samples (the draw is independent per
+        # sample: its own W_j, b_j, noise, Gram matrix and eigen-decomposition -- same bits as the replicated draw) and
+        # theta / W / b are all-gathered: stage A scores every sample against the rank's candidate slice.
+        S_, F_ = int(draws[0].shape[0]), int(draws[0].shape[1])
+        split = shard.world > 1 and S_ % shard.world == 0
+        lo = shard.rank * (S_ // shard.world) if split else 0
+        hi = lo + S_ // shard.world if split else S_
+        draws_d = tuple(dev(t[lo:hi]) for t in draws)      # host draws: only this rank's slice crosses PCIe, first
+        # a pinned host candidate array is uploaded on a side stream UNDER the weight draw (the only stage that does
+        # not read the candidates); the compute stream waits for it before stage A
+        if torch.is_tensor(cand) and not cand.is_cuda and cand.dtype == torch.float64 and cand.is_contiguous() \
+                and cand.is_pinned():
+            staged = _stage_upload(cand)
+            cand = staged[0]
+        else:
+            cand = dev(cand)
+        with _Timed(timers, "draw"):
+            theta, W, b = optfunc.draw_random_init_weights_features(d, hi - lo, F_, X, Y, l, sigma, sigma0, draws=draws_d)
+            if split:
+                theta = shard.all_gather(theta).reshape(S_, F_, 1)
+                W = shard.all_gather(W).reshape(S_, F_, d)
+                b = shard.all_gather(b).reshape(S_, F_, 1)
+        if staged is not None:
+            torch.cuda.current_stream().wait_event(staged[1])
     else:
         cand = dev(cand)
-    N, d = cand.shape
-    if draws is not None:
-        with _Timed(timers, "draw"):
-            S_, F_ = draws[0].shape[0], draws[0].shape[1]
-            theta, W, b = optfunc.draw_random_init_weights_features(d, S_, F_, X, Y, l, sigma, sigma0, draws=draws)
-    if staged is not None:
-        torch.cuda.current_stream().wait_event(staged[1])
-    shard = shard or Shard(N)
     q = int(q)
     if q > 1 and (criterion != "sftl" or N % q or shard.offset % q):
         raise ValueError("q > 1 needs criterion='sftl' and candidate slices that are multiples of q")
