@@ -144,8 +144,8 @@ __device__ __forceinline__ void jacobi_rotation(double a, double b, double g, do
     sn = r * t;
 }
 
-template <bool SMEM>
-__global__ void sym_eig_kernel(const double* __restrict__ A, int n, double* __restrict__ evals,
+template <bool SMEM, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) sym_eig_kernel(const double* __restrict__ A, int n, double* __restrict__ evals,
                                double* __restrict__ evecs, int* __restrict__ sweeps_out, double* __restrict__ gws) {
     extern __shared__ double sm_g[];
     __shared__ int s_rot;
@@ -178,6 +178,51 @@ __global__ void sym_eig_kernel(const double* __restrict__ A, int n, double* __re
                 double* gp = G + (live ? p : 0) * ld;
                 double* gq = G + (live ? q : 0) * ld;
                 double a = 0.0, b = 0.0, g = 0.0;
+                if (MAXT == 256) {
+                    // n <= 64 (the instance with <= 256 threads): a lane's 8 elements of both columns stay in registers between the inner products and the
+                    // rotation (one shared-memory read per element and step instead of two); same operation order
+                    double xr[8], yr[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int i = sub + 8 * e;
+                        const bool in = live && i < n;
+                        xr[e] = in ? gp[i] : 0.0;
+                        yr[e] = in ? gq[i] : 0.0;
+                    }
+                    double a1 = 0.0, b1 = 0.0, g1 = 0.0;
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        a = fma(xr[e], xr[e], a);
+                        b = fma(yr[e], yr[e], b);
+                        g = fma(xr[e], yr[e], g);
+                        a1 = fma(xr[e + 1], xr[e + 1], a1);
+                        b1 = fma(yr[e + 1], yr[e + 1], b1);
+                        g1 = fma(xr[e + 1], yr[e + 1], g1);
+                    }
+                    a += a1;
+                    b += b1;
+                    g += g1;
+#pragma unroll
+                    for (int off = 4; off > 0; off >>= 1) {
+                        a += __shfl_xor_sync(0xffffffffu, a, off);
+                        b += __shfl_xor_sync(0xffffffffu, b, off);
+                        g += __shfl_xor_sync(0xffffffffu, g, off);
+                    }
+                    double c, sn;
+                    jacobi_rotation(a, b, g, tol2, c, sn);
+                    if (live && sn != 0.0) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int i = sub + 8 * e;
+                            if (i < n) {
+                                gp[i] = c * xr[e] - sn * yr[e];
+                                gq[i] = sn * xr[e] + c * yr[e];
+                            }
+                        }
+                        if (sub == 0) s_rot = 1;
+                    }
+                    continue;
+                }
                 if (live) {
                     double a1 = 0.0, b1 = 0.0, g1 = 0.0;
                     int i = sub;
@@ -502,17 +547,20 @@ extern "C" int tes_sym_eig_f64(const double* A, int64_t batch, int64_t n, double
     const int64_t npair = (n + 1) / 2;
     const size_t smem = in_smem ? (size_t)n * (n + 1) * sizeof(double) : 0;
     if (smem > 48 * 1024)
-        TES_CUDA_OK(cudaFuncSetAttribute(sym_eig_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TES_CUDA_OK(cudaFuncSetAttribute(sym_eig_kernel<true, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // four pairs per warp at a time (eight lanes each); n = 64: 256 threads, several matrices per SM hide each other's
     // barrier and fp64 latency
     int threads = 32 * (int)((npair + 3) / 4);
     threads = threads < 128 ? 128 : (threads > 1024 ? 1024 : threads);
-    if (in_smem)
-        sym_eig_kernel<true><<<(unsigned)batch, threads, smem, (cudaStream_t)stream>>>(A, (int)n, evals, evecs, sweeps,
-                                                                                      (double*)ws);
+    if (in_smem && n <= 64)     // <= 32 pairs: 256 threads, a lane's elements of both columns in registers, 5 CTAs per SM
+        sym_eig_kernel<true, 256, 3><<<(unsigned)batch, threads, smem, (cudaStream_t)stream>>>(A, (int)n, evals, evecs, sweeps,
+                                                                                              (double*)ws);
+    else if (in_smem)
+        sym_eig_kernel<true, 1024, 1><<<(unsigned)batch, threads, smem, (cudaStream_t)stream>>>(A, (int)n, evals, evecs, sweeps,
+                                                                                               (double*)ws);
     else
-        sym_eig_kernel<false><<<(unsigned)batch, threads, smem, (cudaStream_t)stream>>>(A, (int)n, evals, evecs, sweeps,
-                                                                                       (double*)ws);
+        sym_eig_kernel<false, 1024, 1><<<(unsigned)batch, threads, smem, (cudaStream_t)stream>>>(A, (int)n, evals, evecs, sweeps,
+                                                                                                (double*)ws);
     TES_LAUNCH_OK();
     return 0;
 }
